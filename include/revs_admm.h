@@ -1,0 +1,145 @@
+/*
+ * revs_admm.h -- C ABI of the B200-native REVS distributed EV-charging ADMM path.
+ *
+ * Drop-in boundary: these are the entry points a maintainer of the reference
+ * (rounak-meyur/revs-admm, pure Python + Gurobi) would bind with ctypes to replace the
+ * hot path of lpsolver.py.  Plain pointers and sizes only; every array is dense,
+ * row-major, float64 unless stated.  All functions return REVS_OK (0) or an error
+ * code; revs_last_error() gives the text.  There is NO CPU fallback: every entry point
+ * fails with REVS_ERR_CUDA when no sm_100 device is usable.
+ *
+ * Reference interface replaced by each entry point (file:line in /root/reference):
+ *
+ *   revs_set_sensitivity / revs_set_feeder_tree   lpsolver.py:17-26   compute_Rmat()
+ *                                                 lpsolver.py:179-190 Utility.network()
+ *   revs_set_homes / revs_set_tariff              lpsolver.py:45-62   Home.__init__ inputs
+ *                                                 extract.py:77-119   get_homes_ev_param()
+ *   revs_solve_admm                               lpsolver.py:244-293 solve_ADMM()
+ *   revs_admm_begin / revs_admm_step              lpsolver.py:256-289 one while-iteration
+ *   revs_home_step                                lpsolver.py:45-157  Home(...).solve()
+ *   revs_utility_step                             lpsolver.py:160-240 Utility(...).solve()
+ *   revs_solve_individual                         lpsolver.py:433-463 solve_residence()
+ *   revs_reliability                              drawing.py:28-78    compute_flows(),
+ *                                                                     compute_voltage()
+ *   revs_get_results                              lpsolver.py:292-293 return diff,P_sch,S,C
+ */
+#ifndef REVS_ADMM_H
+#define REVS_ADMM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define REVS_OK 0
+#define REVS_ERR_ARG 1          /* bad argument / call order                          */
+#define REVS_ERR_CUDA 2         /* CUDA error or no usable device                     */
+#define REVS_ERR_INFEASIBLE 3   /* a home sub-problem has no solution (lpsolver.py:148)*/
+#define REVS_ERR_NOCONV 4       /* utility QP hit its iteration / working-set limit    */
+
+#define REVS_REL_VOLTAGE 0      /* out = sqrt(vset^2 - S_v P)   (drawing.py:76)        */
+#define REVS_REL_FLOW 1         /* out = scale[row] * (S_f P)   (drawing.py:57-59)     */
+#define REVS_REL_DROP 2         /* out = S_v P                  (R@P of lpsolver.py:188)*/
+
+typedef struct revs_solver revs_solver;
+
+/* counters of the last revs_solve_* call (what ran on the device) */
+typedef struct revs_stats {
+    int64_t kernel_launches;      /* kernels of this library launched                  */
+    int64_t gemm_launches;        /* ... of which sensitivity contractions             */
+    int64_t qp_outer_iterations;  /* utility working-set rounds, summed over ADMM iters */
+    int64_t qp_newton_iterations; /* restricted Newton steps, summed over columns       */
+    int32_t admm_iterations;
+    int32_t max_working_set;      /* largest per-(feeder,hour) working set seen         */
+    double primal_residual;       /* ||P_est-P_sch||_F / sqrt(H T), last iteration      */
+    double dual_residual;         /* kappa ||P_sch-P_sch_prev||_F / sqrt(H T)           */
+    float gemm_ms;                /* device time in sensitivity contractions (events)   */
+    float home_ms;                /* device time in the batched home solve              */
+    float dual_ms;                /* device time in the fused dual/residual kernel      */
+    float qp_ms;                  /* device time in the per-column QP kernels           */
+    float total_ms;               /* device time of the whole solve                     */
+} revs_stats;
+
+const char* revs_last_error(void);
+int revs_version(void);
+int revs_device_count(int* count);
+
+/* A solver owns the device state of a batch of feeders that live on ONE GPU.
+ * feeder_off[n_feeders+1]: residences of feeder f are homes feeder_off[f]..feeder_off[f+1]-1
+ * of every [H, *] array below (H = feeder_off[n_feeders]).  T = horizon length. */
+int revs_create(revs_solver** out, int device, int n_feeders, const int64_t* feeder_off, int T);
+int revs_destroy(revs_solver* s);
+
+/* Residence-by-residence voltage sensitivity block R_res (n_f x n_f, symmetric, >=0)
+ * of one feeder, from host memory. */
+int revs_set_sensitivity(revs_solver* s, int feeder, const double* R_res);
+
+/* Same block built ON THE DEVICE from the radial feeder itself: n_nodes non-substation
+ * nodes in topological order (parent[i] < i, -1 = substation), r[i] = resistance of the
+ * edge above node i, res_node[n_f] = node index of each residence.  Also enables
+ * revs_reliability() on arbitrary nodes / edges of this feeder. */
+int revs_set_feeder_tree(revs_solver* s, int feeder, int n_nodes, const int32_t* parent,
+                         const double* r, const int32_t* res_node);
+
+/* Per-home inputs (host).  load [H,T] kW; has_ev [H]; rating kW, capacity kWh, initial
+ * SOC, start/end = plug-in window [start,end) in steps.  EV arrays are ignored where
+ * has_ev==0. */
+int revs_set_homes(revs_solver* s, const double* load, const uint8_t* has_ev,
+                   const double* rating, const double* capacity, const double* initial,
+                   const int32_t* start, const int32_t* end);
+int revs_set_tariff(revs_solver* s, const double* cost /* [T] */);
+
+/* Full ADMM run == solve_ADMM(): iter_max iterations from P_est=P_sch=Gamma=0.
+ * tol<=0 reproduces the reference (always iter_max iterations); tol>0 stops early when
+ * both residuals of revs_stats fall below tol.  iters_done may be NULL. */
+int revs_solve_admm(revs_solver* s, double kappa, int iter_max, double vset, double vlow,
+                    double vhigh, double tol, int* iters_done);
+
+/* The same loop one iteration at a time (multi-GPU drivers all-reduce the residual
+ * sums between steps).  sums[3] = {sum (P_est-P_sch)^2, sum (P_sch-P_sch_prev)^2, H*T}
+ * over this solver's homes. */
+int revs_admm_begin(revs_solver* s, double kappa, int iter_max, double vset, double vlow,
+                    double vhigh);
+int revs_admm_step(revs_solver* s, double sums[3]);
+
+/* The two sub-problems on their own, host in/out, all homes of the solver at once.
+ * revs_home_step  == Home(cost, homedata, p_est, p_sch, gamma, kappa).solve() per home:
+ *   P_sch_new = g_opt [H,T], P_ev = p_opt [H,T] (either may be NULL).
+ * revs_utility_step == Utility(graph, P_est, P_sch, Gamma, kappa, vset, vlow, vhigh).solve():
+ *   P_est_new = g_opt [H,T]; lam0 (may be NULL) warm-starts the voltage-row multipliers,
+ *   lam_out (may be NULL) returns them, both [H,T]. */
+int revs_home_step(revs_solver* s, double kappa, const double* p_est, const double* p_sch,
+                   const double* gamma, double* P_sch_new, double* P_ev);
+int revs_utility_step(revs_solver* s, double kappa, double vset, double vlow, double vhigh,
+                      const double* p_est, const double* p_sch, const double* gamma,
+                      const double* lam0, double* P_est_new, double* lam_out);
+
+/* Results of the last ADMM run, to host.  Any pointer may be NULL.
+ * P_sch [H,T], P_ev [H,T], SOC [H,T+1], diff [iters_done,H] (lpsolver.py:286). */
+int revs_get_results(const revs_solver* s, double* P_sch, double* P_ev, double* SOC,
+                     double* diff);
+/* Utility-side iterates of the last run: P_est [H,T], Gamma [H,T]. */
+int revs_get_estimate(const revs_solver* s, double* P_est, double* Gamma);
+
+/* Individual optimum of every home == solve_residence() per home. */
+int revs_solve_individual(revs_solver* s, double* P_res, double* P_ev, double* SOC);
+
+/* LinDistFlow reliability check of a schedule on one feeder (needs set_feeder_tree):
+ * rows = node indices (voltage/drop) or edge indices (= child-node index of the edge,
+ * flow).  P [n_f,T] host schedule of the feeder's residences, or NULL to use the last
+ * ADMM result.  out [n_rows,T] host.  scale [n_rows] only for REVS_REL_FLOW (signed
+ * 1/rating), may be NULL (=1). */
+int revs_reliability(revs_solver* s, int feeder, int kind, int n_rows, const int32_t* rows,
+                     const double* scale, double vset, const double* P, double* out);
+
+/* Plain sensitivity contraction C[M,T] = A[M,K] @ B[K,T] on the tensor cores (FP64
+ * DMMA), host in/out -- exposed so that the GEMM kernel can be tested on its own. */
+int revs_contract(int device, int M, int K, int T, const double* A, const double* B, double* C);
+
+int revs_get_stats(const revs_solver* s, revs_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REVS_ADMM_H */

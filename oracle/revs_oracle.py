@@ -1,0 +1,356 @@
+"""CPU oracle for the REVS distributed EV-charging ADMM loop.  TEST INFRASTRUCTURE ONLY.
+
+This file is a plain numpy (float64) restatement of the reference algorithm.  It is
+the checker for the CUDA path: only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it.  The
+product package ``revs-admm_b200`` never does.
+
+What it restates (reference file:line, /root/reference):
+
+* ``compute_Rmat``          lpsolver.py:17-26 / drawing.py:17-26
+* ``home_subproblem``       lpsolver.py:45-157  (class Home: binary charger MIQP)
+* ``utility_subproblem``    lpsolver.py:160-240 (class Utility: voltage-limited QP)
+* ``solve_ADMM_arrays`` /
+  ``solve_ADMM``            lpsolver.py:244-293 (the iteration, incl. its use of the
+                            *previous* P_est/P_sch/Gamma in the home step)
+* ``solve_residence``       lpsolver.py:433-463 (individual optimum)
+* ``compute_voltage`` /
+  ``compute_flows``         drawing.py:29-78    (LinDistFlow reliability check)
+
+The reference hands both sub-problems to Gurobi (gurobipy is a third-party
+dependency, un-pinned in the reference and absent from this image, so the reference
+itself cannot run here).  The oracle solves the *same mathematical programs* with
+exact methods:
+
+* Home MIQP.  ``p[t] = e[t]*rating`` with binary ``e`` makes the quadratic objective
+  separable and *linear in e*: charging in hour t costs
+  ``D[t] = f_t(load+rating) - f_t(load)``, ``f_t(g)=c_t g + kappa/2 g^2 - a_t g``.
+  SOC is monotone, so ``init <= s[t] <= 1`` and ``s[T] >= 0.9`` reduce to a count
+  window ``n_min <= #charging hours <= n_max``.  Optimum = the n_min cheapest hours of
+  the plug-in window plus further hours while D<0 (up to n_max).  Ties -> lowest t.
+* Utility QP.  Separable over t; for each t it is the Euclidean projection of
+  ``z = (P_est+P_sch)/2 - Gamma/kappa`` onto ``{g>=0, R g <= vhigh^2-vset^2}`` (Gurobi
+  variables default to lb=0; the ``>= vlow`` row is vacuous for g>=0, R>=0, vlow<vset
+  and is asserted so).  Solved by a projected Newton method on the dual with the
+  exact generalised Hessian and an Armijo arc search; terminates on a KKT residual.
+
+PARITY PIN (see tests/test_oracle_golden.py): the reference's own result files
+(tests/golden/ref_out_121144_com2.npz) are reproduced exactly where the reference
+is deterministic -- iteration-1 convergence values of all 267 EV homes to 4e-16, the
+individual optimum's cost and SOC, the SOC recursion, the charge-hour count -- and
+to within tie-break noise afterwards.  From iteration 2 on the reference trajectory
+is NOT a function of its inputs: 138 of the 267 homes have exactly tied optimal
+hours at iteration 1 and Gurobi stops at MIPGap=1e-4, so the hours it returns are
+solver-arbitrary and the ADMM history inherits them.  Parity for later iterations is
+therefore "partially pinned": model constants are identified by the golden data
+(any other vset/vhigh is >=7x further away than two tie-break choices are from each
+other) but a bit-level trajectory match is impossible by construction.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+SOC_TARGET = 0.9      # lpsolver.py:111  s[T] >= 0.9
+SOC_MAX = 1.0         # lpsolver.py:102  ub = 1.0
+PHI_NOISE = 1e-14     # relative rounding noise admitted by the line search of the utility QP
+COUNT_TOL = 1e-9      # slack on the SOC count window (Gurobi's own FeasibilityTol is 1e-6)
+
+
+# --------------------------------------------------------------------------- network
+def compute_Rmat(graph):
+    """lpsolver.py:17-26.  R = 2 F D F^T with F the inverse reduced incidence matrix."""
+    import networkx as nx
+    A = nx.incidence_matrix(graph, nodelist=list(graph.nodes()),
+                            edgelist=list(graph.edges()), oriented=True).toarray()
+    node_ind = [i for i, n in enumerate(graph.nodes()) if graph.nodes[n]["label"] != "S"]
+    F = np.linalg.inv(A[node_ind, :].T)
+    D = np.diag([graph.edges[e]["r"] for e in graph.edges])
+    return 2 * F @ D @ F.T
+
+
+def rmat_from_tree(parent, r):
+    """Same matrix for a rooted tree given as arrays: node i (non-root, topologically
+    ordered so parent[i] < i, parent -1 = substation) hangs on an edge of resistance
+    r[i].  R[i,j] = 2 * (resistance of the common root path of i and j)."""
+    n = len(parent)
+    R = np.zeros((n, n))
+    for i in range(n):
+        p = parent[i]
+        if p >= 0:
+            R[i, :i] = R[p, :i]
+            R[:i, i] = R[i, :i]
+            R[i, i] = R[p, p] + 2.0 * r[i]
+        else:
+            R[i, i] = 2.0 * r[i]
+    return R
+
+
+def residence_block(graph):
+    """Rows/cols of R at the residences, ordered as ``[n for n in graph if label=='H']``
+    (lpsolver.py:184-185)."""
+    nodes = [n for n in graph.nodes if graph.nodes[n]["label"] != "S"]
+    res = [n for n in graph if graph.nodes[n]["label"] == "H"]
+    R = compute_Rmat(graph)
+    pos = {n: i for i, n in enumerate(nodes)}
+    ind = [pos[n] for n in res]
+    return res, R[np.ix_(ind, ind)]
+
+
+# --------------------------------------------------------------------------- home step
+def count_window(rating, capacity, initial):
+    """Number of charging hours allowed by the SOC rows (lpsolver.py:100-111)."""
+    step = rating / capacity
+    n_min = int(np.ceil((SOC_TARGET - initial) / step - COUNT_TOL))
+    n_max = int(np.floor((SOC_MAX - initial) / step + COUNT_TOL))
+    return max(n_min, 0), n_max
+
+
+def pick_hours(delta, start, end, n_min, n_max):
+    """Indices of the optimal charging hours: the n_min smallest ``delta`` inside
+    [start,end) and then more while delta<0 (ties: lowest hour first)."""
+    T = len(delta)
+    lo, hi = max(int(start), 0), min(int(end), T)
+    win = np.arange(lo, hi)
+    if n_min > n_max or n_min > len(win):
+        raise ValueError("home sub-problem infeasible (reference: 'No solution found')")
+    order = win[np.argsort(delta[lo:hi], kind="stable")]
+    n = n_min
+    while n < min(n_max, len(order)) and delta[order[n]] < 0:
+        n += 1
+    return order[:n]
+
+
+def home_delta(cost, load, p_est, p_sch, gamma, kappa, rating):
+    """Cost of switching the charger on in each hour, in a fixed evaluation order
+    (every operation individually rounded; the CUDA kernel uses the same order)."""
+    a = gamma + (kappa / 2.0) * (p_est + p_sch)             # lpsolver.py:119-120
+    return rating * (cost - a) + (kappa * load) * rating + ((0.5 * kappa) * rating) * rating
+
+
+def soc_profile(p, capacity, initial):
+    s = np.empty(len(p) + 1)
+    s[0] = initial
+    for t in range(len(p)):
+        s[t + 1] = s[t] + p[t] / capacity                    # lpsolver.py:109
+    return s
+
+
+def home_subproblem(cost, load, ev, p_est, p_sch, gamma, kappa=5.0):
+    """class Home (lpsolver.py:45-157).  ``ev`` is {} or the dict of extract.py:109-116.
+    Returns (p_opt, s_opt, g_opt)."""
+    cost = np.asarray(cost, float)
+    load = np.asarray(load, float)
+    T = len(cost)
+    if not ev:
+        return np.zeros(T), np.zeros(T + 1), load.copy()
+    rating, cap, init = float(ev["rating"]), float(ev["capacity"]), float(ev["initial"])
+    d = home_delta(cost, load, np.asarray(p_est, float), np.asarray(p_sch, float),
+                   np.asarray(gamma, float), kappa, rating)
+    n_min, n_max = count_window(rating, cap, init)
+    hours = pick_hours(d, ev["start"], ev["end"], n_min, n_max)
+    p = np.zeros(T)
+    p[hours] = rating
+    return p, soc_profile(p, cap, init), load + p
+
+
+def solve_residence_arrays(tariff, load, ev):
+    """solve_residence (lpsolver.py:433-463): minimise 0.01*cost + 0.99*(1-s[T])."""
+    tariff = np.asarray(tariff, float)
+    load = np.asarray(load, float)
+    T = len(tariff)
+    if not ev:
+        return np.zeros(T), np.zeros(T + 1), load.copy()
+    rating, cap, init = float(ev["rating"]), float(ev["capacity"]), float(ev["initial"])
+    d = (0.01 * tariff) * rating - 0.99 * (rating / cap)
+    _, n_max = count_window(rating, cap, init)
+    hours = pick_hours(d, ev["start"], ev["end"], 0, n_max)
+    p = np.zeros(T)
+    p[hours] = rating
+    return p, soc_profile(p, cap, init), load + p
+
+
+# --------------------------------------------------------------------------- utility step
+def project_voltage(z, R, u, lam0=None, tol=1e-11, maxit=500):
+    """argmin 1/2||g-z||^2  s.t. g>=0, R g <= u   (one time step of class Utility).
+
+    Dual: minimise phi(lam) = 1/2||[z - R lam]_+||^2 + u*sum(lam) over lam>=0, by
+    projected Newton (free set = not {lam~0 and gradient>0}; Hessian R_AF R_FA) with
+    an Armijo search along the projection arc.  Returns (g, lam, iterations)."""
+    n = len(z)
+    lam = np.zeros(n) if lam0 is None else np.maximum(lam0, 0.0)
+
+    def phi(lm):
+        gg = np.maximum(z - R @ lm, 0.0)
+        return 0.5 * gg @ gg + u * lm.sum(), gg
+
+    f, g = phi(lam)
+    for it in range(maxit):
+        grad = u - R @ g
+        kkt = np.max(np.abs(np.where(lam > 0, grad, np.minimum(grad, 0.0))))
+        if kkt < tol:
+            return g, lam, it
+        eps = min(1e-8, kkt)
+        free = ~((lam <= eps) & (grad > 0))
+        F = g > 0
+        RAF = R[np.ix_(free, F)]
+        H = RAF @ RAF.T
+        H[np.diag_indices_from(H)] += 1e-10 * np.trace(H) / max(1, H.shape[0]) + 1e-300
+        d = np.zeros(n)
+        d[free] = -np.linalg.solve(H, grad[free])
+        a = 1.0
+        while True:
+            ln = np.maximum(lam + a * d, 0.0)
+            fn, gn = phi(ln)
+            # the last term is the rounding noise of phi itself: close to the solution the
+            # predicted decrease (~kkt^2) drops below it and a plain Armijo test would
+            # reject the (correct) full Newton step
+            if fn <= f + 1e-4 * grad @ (ln - lam) + PHI_NOISE * abs(f) or a < 1e-12:
+                break
+            a *= 0.5
+        lam, f, g = ln, fn, gn
+    raise RuntimeError("utility QP did not converge (kkt=%g)" % kkt)
+
+
+def utility_subproblem(R, p_est, p_sch, gamma, kappa, vset, vlow, vhigh, lam0=None):
+    """class Utility (lpsolver.py:160-240) for one feeder.  Arrays are [homes, T]."""
+    u = vhigh * vhigh - vset * vset
+    lo = vlow * vlow - vset * vset
+    if not (u > 0 and lo <= 0 and R.min() >= 0):
+        raise NotImplementedError("needs vlow <= vset < vhigh and R >= 0")
+    z = (p_est + p_sch) / 2.0 - gamma / kappa
+    n, T = z.shape
+    g = np.empty_like(z)
+    lam = np.zeros_like(z) if lam0 is None else lam0.copy()
+    its = 0
+    for t in range(T):
+        g[:, t], lam[:, t], k = project_voltage(z[:, t], R, u, lam[:, t])
+        its += k
+    return g, lam, its
+
+
+# --------------------------------------------------------------------------- ADMM
+def solve_ADMM_arrays(R_blocks, load, cost, ev_mask, rating, capacity, initial, start, end,
+                      kappa=5.0, iter_max=15, vset=1.0, vlow=0.95, vhigh=1.05,
+                      return_history=False):
+    """solve_ADMM (lpsolver.py:244-293) on arrays.
+
+    R_blocks: list of residence sensitivity blocks, one per feeder; homes are the
+    concatenation of the feeders' residences.  load [H,T]; per-home EV arrays [H].
+    Returns dict(diff [iter_max,H], P_sch, P_ev, SOC, P_est, Gamma)."""
+    load = np.asarray(load, float)
+    cost = np.asarray(cost, float)
+    H, T = load.shape
+    offs = np.concatenate([[0], np.cumsum([b.shape[0] for b in R_blocks])])
+    assert offs[-1] == H
+    P_est = np.zeros((H, T))
+    P_sch = np.zeros((H, T))
+    Gam = np.zeros((H, T))
+    lam = np.zeros((H, T))
+    diff = np.zeros((iter_max, H))
+    P_ev = np.zeros((H, T))
+    SOC = np.zeros((H, T + 1))
+    hist = []
+    nwin = [count_window(rating[i], capacity[i], initial[i]) if ev_mask[i] else (0, 0)
+            for i in range(H)]
+    for k in range(iter_max):
+        # utility estimate (lpsolver.py:258-261)
+        P_est_new = np.empty((H, T))
+        for f, Rb in enumerate(R_blocks):
+            s = slice(offs[f], offs[f + 1])
+            P_est_new[s], lam[s], _ = utility_subproblem(
+                Rb, P_est[s], P_sch[s], Gam[s], kappa, vset, vlow, vhigh, lam[s])
+        # every home, with the PREVIOUS iterates (lpsolver.py:275)
+        P_sch_new = load.copy()
+        for i in np.nonzero(ev_mask)[0]:
+            d = home_delta(cost, load[i], P_est[i], P_sch[i], Gam[i], kappa, rating[i])
+            hrs = pick_hours(d, start[i], end[i], *nwin[i])
+            P_ev[i] = 0.0
+            P_ev[i, hrs] = rating[i]
+            P_sch_new[i] += P_ev[i]
+        check = P_est_new - P_sch_new                        # lpsolver.py:282-283
+        Gam = Gam + (kappa / 2) * check                       # lpsolver.py:284-285
+        diff[k] = np.sqrt((check * check).sum(axis=1)) / T    # lpsolver.py:286
+        P_est, P_sch = P_est_new, P_sch_new
+        if return_history:
+            hist.append((P_est.copy(), P_sch.copy(), Gam.copy()))
+    for i in range(H):
+        SOC[i] = soc_profile(P_ev[i], capacity[i], initial[i]) if ev_mask[i] else 0.0
+    out = dict(diff=diff, P_sch=P_sch, P_ev=P_ev, SOC=SOC, P_est=P_est, Gamma=Gam, lam=lam)
+    if return_history:
+        out["history"] = hist
+    return out
+
+
+def homes_to_arrays(homes, res):
+    """dict-of-homes (extract.py:103-119) -> arrays in residence order."""
+    H = len(res)
+    T = len(homes[res[0]]["LOAD"])
+    load = np.array([homes[h]["LOAD"] for h in res], float)
+    ev_mask = np.array([bool(homes[h]["EV"]) for h in res])
+    get = lambda key, default: np.array(
+        [homes[h]["EV"].get(key, default) if homes[h]["EV"] else default for h in res], float)
+    return dict(load=load, ev_mask=ev_mask, rating=get("rating", 0.0),
+                capacity=get("capacity", 1.0), initial=get("initial", 0.0),
+                start=get("start", 0).astype(int), end=get("end", 0).astype(int)), T, H
+
+
+def solve_ADMM(homes, graph, cost, grbpath=None, kappa=5.0, iter_max=15,
+               vset=1.0, vlow=0.95, vhigh=1.05):
+    """Same signature and return value as lpsolver.py:244 (grbpath unused)."""
+    res, Rres = residence_block(graph)
+    arr, T, H = homes_to_arrays(homes, res)
+    out = solve_ADMM_arrays([Rres], cost=cost, kappa=kappa, iter_max=iter_max,
+                            vset=vset, vlow=vlow, vhigh=vhigh, **arr)
+    diff = {k + 1: {h: out["diff"][k, i] for i, h in enumerate(res)} for k in range(iter_max)}
+    P = {h: out["P_sch"][i] for i, h in enumerate(res)}
+    S = {h: out["P_ev"][i] for i, h in enumerate(res)}
+    C = {h: out["SOC"][i] for i, h in enumerate(res)}
+    return diff, P, S, C
+
+
+def solve_residence(tariff, data, path=None):
+    """Same signature as lpsolver.py:433."""
+    return solve_residence_arrays(tariff, data["LOAD"], data["EV"])
+
+
+# --------------------------------------------------------------------------- reliability check
+def compute_voltage(graph, p_sch, vset=1.0):
+    """drawing.py:62-78."""
+    nodelist = [n for n in graph if graph.nodes[n]["label"] != "S"]
+    res = set(n for n in graph if graph.nodes[n]["label"] == "H")
+    T = len(next(iter(p_sch.values())))
+    R = compute_Rmat(graph)
+    P = np.zeros((len(nodelist), T))
+    for i, n in enumerate(nodelist):
+        if n in res:
+            P[i] = np.asarray(p_sch[n])
+    V = np.sqrt(vset * vset - R @ P)
+    return {h: V[i] for i, h in enumerate(nodelist)}
+
+
+LINE_RATING = {  # drawing.py:29-40 (kVA), repeated in test-dist-ind-opt.py:156-166
+    "OH_Voluta": np.sqrt(3) * 95 * 0.24, "OH_Periwinkle": np.sqrt(3) * 125 * 0.24,
+    "OH_Conch": np.sqrt(3) * 165 * 0.24, "OH_Neritina": np.sqrt(3) * 220 * 0.24,
+    "OH_Runcina": np.sqrt(3) * 265 * 0.24, "OH_Zuzara": np.sqrt(3) * 350 * 0.24,
+    "OH_Swanate": np.sqrt(3) * 145 * 12.47, "OH_Sparrow": np.sqrt(3) * 185 * 12.47,
+    "OH_Raven": np.sqrt(3) * 240 * 12.47, "OH_Pegion": np.sqrt(3) * 315 * 12.47,
+    "OH_Penguin": np.sqrt(3) * 365 * 12.47,
+}
+
+
+def compute_flows(graph, p_sch):
+    """drawing.py:28-60.  Per-edge loading (signed flow / rating)."""
+    import networkx as nx
+    nodelist = [n for n in graph if graph.nodes[n]["label"] != "S"]
+    res = set(n for n in graph if graph.nodes[n]["label"] == "H")
+    nodeind = [i for i, n in enumerate(graph.nodes) if graph.nodes[n]["label"] != "S"]
+    T = len(next(iter(p_sch.values())))
+    A = nx.incidence_matrix(graph, nodelist=list(graph.nodes), edgelist=list(graph.edges),
+                            oriented=True).toarray()
+    A_inv = np.linalg.inv(A[nodeind, :])
+    P = np.zeros((len(nodelist), T))
+    for i, n in enumerate(nodelist):
+        if n in res:
+            P[i] = np.asarray(p_sch[n])
+    Fl = A_inv @ P
+    return {e: Fl[i] / LINE_RATING[graph.edges[e]["type"]] for i, e in enumerate(graph.edges)}

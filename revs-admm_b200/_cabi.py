@@ -1,0 +1,233 @@
+"""ctypes binding of include/revs_admm.h.  No torch types cross this boundary.
+
+The library is the product: if it is missing or no B200 is visible every call raises --
+there is no CPU path in this package.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "librevs_admm.so")
+
+REVS_REL_VOLTAGE, REVS_REL_FLOW, REVS_REL_DROP = 0, 1, 2
+
+
+class RevsError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"revs_admm error {code}: {msg}")
+        self.code = code
+
+
+class Stats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_int64), ("gemm_launches", C.c_int64),
+                ("qp_outer_iterations", C.c_int64), ("qp_newton_iterations", C.c_int64),
+                ("admm_iterations", C.c_int32), ("max_working_set", C.c_int32),
+                ("primal_residual", C.c_double), ("dual_residual", C.c_double),
+                ("gemm_ms", C.c_float), ("home_ms", C.c_float), ("dual_ms", C.c_float),
+                ("qp_ms", C.c_float), ("total_ms", C.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_P = C.c_void_p
+_D = C.POINTER(C.c_double)
+# name -> argtypes   (every symbol include/revs_admm.h declares)
+SIGNATURES = {
+    "revs_last_error": ([], C.c_char_p),
+    "revs_version": ([], C.c_int),
+    "revs_device_count": ([C.POINTER(C.c_int)], C.c_int),
+    "revs_create": ([C.POINTER(_P), C.c_int, C.c_int, C.POINTER(C.c_int64), C.c_int], C.c_int),
+    "revs_destroy": ([_P], C.c_int),
+    "revs_set_sensitivity": ([_P, C.c_int, _D], C.c_int),
+    "revs_set_feeder_tree": ([_P, C.c_int, C.c_int, C.POINTER(C.c_int32), _D, C.POINTER(C.c_int32)], C.c_int),
+    "revs_set_homes": ([_P, _D, C.POINTER(C.c_uint8), _D, _D, _D, C.POINTER(C.c_int32),
+                        C.POINTER(C.c_int32)], C.c_int),
+    "revs_set_tariff": ([_P, _D], C.c_int),
+    "revs_solve_admm": ([_P, C.c_double, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
+                         C.POINTER(C.c_int)], C.c_int),
+    "revs_admm_begin": ([_P, C.c_double, C.c_int, C.c_double, C.c_double, C.c_double], C.c_int),
+    "revs_admm_step": ([_P, _D], C.c_int),
+    "revs_home_step": ([_P, C.c_double, _D, _D, _D, _D, _D], C.c_int),
+    "revs_utility_step": ([_P, C.c_double, C.c_double, C.c_double, C.c_double, _D, _D, _D, _D, _D, _D], C.c_int),
+    "revs_get_results": ([_P, _D, _D, _D, _D], C.c_int),
+    "revs_get_estimate": ([_P, _D, _D], C.c_int),
+    "revs_solve_individual": ([_P, _D, _D, _D], C.c_int),
+    "revs_reliability": ([_P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), _D, C.c_double, _D, _D], C.c_int),
+    "revs_contract": ([C.c_int, C.c_int, C.c_int, C.c_int, _D, _D, _D], C.c_int),
+    "revs_get_stats": ([_P, C.POINTER(Stats)], C.c_int),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen the in-tree library and type every entry point."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RevsError(-1, f"{LIB_PATH} is missing -- run `python revs-admm_b200/_build.py` "
+                                "(there is no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (args, res) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes, fn.restype = args, res
+        _lib = lib
+    return _lib
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(_D)
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None and a.shape != tuple(shape):
+        raise ValueError(f"expected shape {tuple(shape)}, got {a.shape}")
+    return a
+
+
+def _check(rc):
+    if rc != 0:
+        raise RevsError(rc, load().revs_last_error().decode())
+
+
+def device_count():
+    n = C.c_int(0)
+    _check(load().revs_device_count(C.byref(n)))
+    return n.value
+
+
+def contract(A, B, device=0):
+    """C = A @ B through the FP64 tensor-core contraction kernel (host in/out)."""
+    A, B = _f64(A), _f64(B)
+    M, K = A.shape
+    K2, T = B.shape
+    assert K == K2
+    out = np.empty((M, T))
+    _check(load().revs_contract(device, M, K, T, _dp(A), _dp(B), _dp(out)))
+    return out
+
+
+class Solver:
+    """A batch of feeders resident on one GPU (wraps revs_solver*)."""
+
+    def __init__(self, feeder_sizes, T, device=0):
+        self.lib = load()
+        self.sizes = [int(n) for n in feeder_sizes]
+        self.off = np.concatenate([[0], np.cumsum(self.sizes)]).astype(np.int64)
+        self.H, self.T, self.nf = int(self.off[-1]), int(T), len(self.sizes)
+        self._h = _P()
+        _check(self.lib.revs_create(C.byref(self._h), device, self.nf,
+                                    self.off.ctypes.data_as(C.POINTER(C.c_int64)), self.T))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.revs_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- inputs
+    def set_sensitivity(self, feeder, R):
+        n = self.sizes[feeder]
+        R = _f64(R, (n, n))
+        _check(self.lib.revs_set_sensitivity(self._h, feeder, _dp(R)))
+
+    def set_feeder_tree(self, feeder, parent, r, res_node):
+        parent = np.ascontiguousarray(parent, dtype=np.int32)
+        r = _f64(r, (len(parent),))
+        res_node = np.ascontiguousarray(res_node, dtype=np.int32)
+        assert len(res_node) == self.sizes[feeder]
+        i32 = C.POINTER(C.c_int32)
+        _check(self.lib.revs_set_feeder_tree(self._h, feeder, len(parent), parent.ctypes.data_as(i32),
+                                             _dp(r), res_node.ctypes.data_as(i32)))
+
+    def set_homes(self, load, has_ev, rating, capacity, initial, start, end):
+        H, T = self.H, self.T
+        load = _f64(load, (H, T))
+        has_ev = np.ascontiguousarray(has_ev, dtype=np.uint8)
+        rating, capacity, initial = _f64(rating, (H,)), _f64(capacity, (H,)), _f64(initial, (H,))
+        start = np.ascontiguousarray(start, dtype=np.int32)
+        end = np.ascontiguousarray(end, dtype=np.int32)
+        i32 = C.POINTER(C.c_int32)
+        _check(self.lib.revs_set_homes(self._h, _dp(load), has_ev.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                       _dp(rating), _dp(capacity), _dp(initial),
+                                       start.ctypes.data_as(i32), end.ctypes.data_as(i32)))
+
+    def set_tariff(self, cost):
+        cost = _f64(cost, (self.T,))
+        _check(self.lib.revs_set_tariff(self._h, _dp(cost)))
+
+    # ---- solves
+    def solve_admm(self, kappa=5.0, iter_max=15, vset=1.0, vlow=0.95, vhigh=1.05, tol=0.0):
+        done = C.c_int(0)
+        _check(self.lib.revs_solve_admm(self._h, kappa, iter_max, vset, vlow, vhigh, tol, C.byref(done)))
+        return done.value
+
+    def admm_begin(self, kappa=5.0, iter_max=15, vset=1.0, vlow=0.95, vhigh=1.05):
+        _check(self.lib.revs_admm_begin(self._h, kappa, iter_max, vset, vlow, vhigh))
+
+    def admm_step(self):
+        sums = np.zeros(3)
+        _check(self.lib.revs_admm_step(self._h, _dp(sums)))
+        return sums
+
+    def home_step(self, p_est, p_sch, gamma, kappa=5.0):
+        H, T = self.H, self.T
+        g, p = np.empty((H, T)), np.empty((H, T))
+        _check(self.lib.revs_home_step(self._h, kappa, _dp(_f64(p_est, (H, T))), _dp(_f64(p_sch, (H, T))),
+                                       _dp(_f64(gamma, (H, T))), _dp(g), _dp(p)))
+        return g, p
+
+    def utility_step(self, p_est, p_sch, gamma, kappa=5.0, vset=1.0, vlow=0.95, vhigh=1.05, lam0=None):
+        H, T = self.H, self.T
+        g, lam = np.empty((H, T)), np.empty((H, T))
+        l0 = None if lam0 is None else _f64(lam0, (H, T))
+        _check(self.lib.revs_utility_step(self._h, kappa, vset, vlow, vhigh, _dp(_f64(p_est, (H, T))),
+                                          _dp(_f64(p_sch, (H, T))), _dp(_f64(gamma, (H, T))), _dp(l0),
+                                          _dp(g), _dp(lam)))
+        return g, lam
+
+    def results(self, iters=None, want_diff=True):
+        H, T = self.H, self.T
+        iters = self.stats()["admm_iterations"] if iters is None else iters
+        P, E, S = np.empty((H, T)), np.empty((H, T)), np.empty((H, T + 1))
+        D = np.empty((iters, H)) if want_diff else None
+        _check(self.lib.revs_get_results(self._h, _dp(P), _dp(E), _dp(S), _dp(D)))
+        return dict(P_sch=P, P_ev=E, SOC=S, diff=D)
+
+    def estimate(self):
+        H, T = self.H, self.T
+        P, G = np.empty((H, T)), np.empty((H, T))
+        _check(self.lib.revs_get_estimate(self._h, _dp(P), _dp(G)))
+        return P, G
+
+    def solve_individual(self):
+        H, T = self.H, self.T
+        P, E, S = np.empty((H, T)), np.empty((H, T)), np.empty((H, T + 1))
+        _check(self.lib.revs_solve_individual(self._h, _dp(P), _dp(E), _dp(S)))
+        return dict(P_res=P, P_ev=E, SOC=S)
+
+    def reliability(self, feeder, kind, rows, vset=1.0, scale=None, P=None):
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        out = np.empty((len(rows), self.T))
+        sc = None if scale is None else _f64(scale, (len(rows),))
+        Pp = None if P is None else _f64(P, (self.sizes[feeder], self.T))
+        _check(self.lib.revs_reliability(self._h, feeder, kind, len(rows),
+                                         rows.ctypes.data_as(C.POINTER(C.c_int32)), _dp(sc), vset,
+                                         _dp(Pp), _dp(out)))
+        return out
+
+    def stats(self):
+        st = Stats()
+        _check(self.lib.revs_get_stats(self._h, C.byref(st)))
+        return st.as_dict()

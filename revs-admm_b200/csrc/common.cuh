@@ -1,0 +1,49 @@
+// Shared device-side definitions of the REVS ADMM path (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace revs {
+
+constexpr int kPad = 16;        // residences of a feeder are padded to a multiple of this
+constexpr int kWMax = 128;      // largest working set of a (feeder,hour) utility QP column
+constexpr int kAddMax = 32;     // violated voltage rows admitted per working-set round
+
+// One feeder of the batch as the kernels see it.
+struct FeederDev {
+    int n;            // residences
+    int np;           // padded residences (multiple of kPad) == leading dim of R block
+    int64_t off;      // first padded home index
+    int64_t roff;     // offset (doubles) of the n_p x n_p block in the R pool
+};
+
+// Output layout / transform of the sensitivity contraction.
+enum ContractOut : int {
+    kOutTimeMajor = 0,   // out[t*ldo + m] = acc
+    kOutNodeMajor = 1,   // out[m*ldo + t] = acc
+    kOutVoltage = 2,     // out[m*ldo + t] = sqrt(v2 - acc)
+    kOutScaled = 3       // out[m*ldo + t] = scale[m] * acc
+};
+
+// Batched contraction problem: C_f = A_f (M_f x K_f) * B_f^T (T x K_f).
+struct ContractProblem {
+    const double* A; int lda; int M; int K;
+    const double* Bt; int64_t ldb;       // Bt[t*ldb + k]
+    double* out; int64_t ldo;
+    const double* scale;                 // per-row, kOutScaled only
+};
+
+struct ContractTile { int problem; int row0; };
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+}  // namespace revs

@@ -1,0 +1,99 @@
+// Fused dual-price update, per-home convergence value, primal/dual residuals, the
+// convergence test and the target of the next utility step -- one kernel per ADMM
+// iteration, nothing leaves the device.
+//
+// Reference: the tail of the home loop of solve_ADMM (lpsolver.py:281-286)
+//     check = P_est[k+1] - P_sch[k+1]
+//     G[k+1] = G[k] + kappa/2 * check
+//     diff[k+1][h] = ||check|| / T
+// plus the objective data of the next Utility (lpsolver.py:209-211), which is the
+// projection target  z = (P_est + P_sch)/2 - G/kappa.
+//
+// Layout: the utility side keeps its arrays time-major [T][Hp] (one contiguous column per
+// (feeder,hour) QP), the home side home-major [Hp][T] (one contiguous row per home).  A
+// CTA owns 32 homes x T hours and transposes through shared memory, so both sides are
+// read and written in full 256-byte runs.  Per-home norms use warp shuffles; the two
+// global sums are one atomicAdd per CTA, and the last CTA to finish turns them into the
+// residuals and the converged flag.
+#include "kernels.cuh"
+
+namespace revs {
+
+
+
+__global__ void __launch_bounds__(256) dual_update_kernel(DualParams P) {
+    extern __shared__ double tile[];   // [32][T+1]
+    __shared__ double s_part[2][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int h0 = blockIdx.x * 32;
+    const int ldt = P.T + 1;
+
+    for (int t = warp; t < P.T; t += 8) {
+        int h = h0 + lane;
+        tile[lane * ldt + t] = h < P.Hp ? P.g_t[(size_t)t * P.Hp + h] : 0.0;
+    }
+    __syncthreads();
+
+    const double hk = 0.5 * P.kappa;
+    double blk_p = 0.0, blk_d = 0.0;
+    for (int hl = warp; hl < 32; hl += 8) {
+        const int h = h0 + hl;
+        if (h >= P.Hp) break;
+        const size_t base = (size_t)h * P.T;
+        double a1 = 0.0, a2 = 0.0;
+        for (int t = lane; t < P.T; t += 32) {
+            const double e = tile[hl * ldt + t];
+            const double sn = P.p_sch_new[base + t];
+            const double so = P.p_sch_old[base + t];
+            const double gm = P.gamma[base + t];
+            const double check = __dadd_rn(e, -sn);
+            const double g2 = __dadd_rn(gm, __dmul_rn(hk, check));
+            P.gamma[base + t] = g2;
+            P.p_est[base + t] = e;
+            tile[hl * ldt + t] = __dadd_rn(__dmul_rn(__dadd_rn(e, sn), 0.5), -__ddiv_rn(g2, P.kappa));
+            a1 = fma(check, check, a1);
+            const double ds = sn - so;
+            a2 = fma(ds, ds, a2);
+        }
+        a1 = warp_sum(a1);
+        a2 = warp_sum(a2);
+        if (lane == 0) P.diff_k[h] = sqrt(a1) / (double)P.T;
+        blk_p += a1;
+        blk_d += a2;
+    }
+    if (lane == 0) { s_part[0][warp] = blk_p; s_part[1][warp] = blk_d; }
+    __syncthreads();
+
+    for (int t = warp; t < P.T; t += 8) {
+        int h = h0 + lane;
+        if (h < P.Hp) P.z_t[(size_t)t * P.Hp + h] = tile[lane * ldt + t];
+    }
+
+    if (threadIdx.x == 0) {
+        double sp = 0.0, sd = 0.0;
+        for (int w = 0; w < 8; ++w) { sp += s_part[0][w]; sd += s_part[1][w]; }
+        atomicAdd(&P.res->sum_primal, sp);
+        atomicAdd(&P.res->sum_dual, sd);
+        __threadfence();
+        unsigned done = atomicAdd(&P.res->ticket, 1u);
+        if (done == gridDim.x - 1) {   // last CTA: residuals + convergence test
+            __threadfence();
+            double tp = atomicAdd(&P.res->sum_primal, 0.0);
+            double td = atomicAdd(&P.res->sum_dual, 0.0);
+            double r = sqrt(tp / P.count), s = P.kappa * sqrt(td / P.count);
+            P.res->primal = r;
+            P.res->dual = s;
+            P.res->converged = (P.tol > 0.0 && r < P.tol && s < P.tol) ? 1 : 0;
+        }
+    }
+}
+
+cudaError_t launch_dual_update(const DualParams& P, cudaStream_t stream) {
+    size_t smem = (size_t)32 * (P.T + 1) * sizeof(double);
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(dual_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dual_update_kernel<<<(P.Hp + 31) / 32, 256, smem, stream>>>(P);
+    return cudaGetLastError();
+}
+
+}  // namespace revs

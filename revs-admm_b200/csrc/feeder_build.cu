@@ -1,0 +1,84 @@
+// Sensitivity matrices of a radial feeder, built on the device from the tree itself.
+//
+// Reference: compute_Rmat (lpsolver.py:17-26) forms R = 2 F D F^T by inverting the reduced
+// incidence matrix with numpy; compute_flows (drawing.py:28-60) inverts it again for the
+// flow sensitivities.  For a radial feeder both inverses are path indicators, so
+//     R[a][b]   = 2 * (resistance of the common part of the root paths of a and b)
+//     A_inv[e][b] = +-1 iff edge e lies on the root path of b
+// and each entry is one walk up the tree.  Nodes are topologically numbered
+// (parent[i] < i, -1 = substation), so the lowest common ancestor is found by lifting
+// whichever index is larger.
+#include "kernels.cuh"
+
+namespace revs {
+
+// out[m*ld + j] for m < n_rows, j < n_res.  row_node == nullptr means rows are the residences.
+__global__ void sens_voltage_kernel(const int* __restrict__ parent, const double* __restrict__ cumr,
+                                    const int* __restrict__ row_node, const int* __restrict__ res_node,
+                                    int n_rows, int n_res, double* __restrict__ out, int ld) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_res) return;
+    for (int m = blockIdx.y; m < n_rows; m += gridDim.y) {
+        int a = row_node ? row_node[m] : res_node[m];
+        int b = res_node[j];
+        while (a != b) {
+            if (a > b) a = parent[a];
+            else b = parent[b];
+        }
+        out[(size_t)m * ld + j] = a < 0 ? 0.0 : 2.0 * cumr[a];
+    }
+}
+
+// out[m*ld + j] = 1 if the edge above node row_node[m] carries residence j.
+__global__ void sens_flow_kernel(const int* __restrict__ parent, const int* __restrict__ row_node,
+                                 const int* __restrict__ res_node, int n_rows, int n_res,
+                                 double* __restrict__ out, int ld) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_res) return;
+    for (int m = blockIdx.y; m < n_rows; m += gridDim.y) {
+        const int e = row_node[m];
+        int b = res_node[j];
+        while (b > e) b = parent[b];
+        out[(size_t)m * ld + j] = (b == e) ? 1.0 : 0.0;
+    }
+}
+
+// home-major [n][T] -> time-major [T][ld]
+__global__ void to_time_major_kernel(const double* __restrict__ in, int n, int T, double* __restrict__ out,
+                                     int64_t ld) {
+    __shared__ double tile[32][33];
+    const int h0 = blockIdx.x * 32, t0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int h = h0 + r, t = t0 + threadIdx.x;
+        tile[r][threadIdx.x] = (h < n && t < T) ? in[(size_t)h * T + t] : 0.0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int t = t0 + r, h = h0 + threadIdx.x;
+        if (t < T && h < n) out[(size_t)t * ld + h] = tile[threadIdx.x][r];
+    }
+}
+
+cudaError_t launch_sens_voltage(const int* parent, const double* cumr, const int* row_node,
+                                const int* res_node, int n_rows, int n_res, double* out, int ld,
+                                cudaStream_t s) {
+    if (n_rows == 0 || n_res == 0) return cudaSuccess;
+    dim3 grid((n_res + 127) / 128, n_rows < 65535 ? n_rows : 65535);
+    sens_voltage_kernel<<<grid, 128, 0, s>>>(parent, cumr, row_node, res_node, n_rows, n_res, out, ld);
+    return cudaGetLastError();
+}
+cudaError_t launch_sens_flow(const int* parent, const int* row_node, const int* res_node, int n_rows,
+                             int n_res, double* out, int ld, cudaStream_t s) {
+    if (n_rows == 0 || n_res == 0) return cudaSuccess;
+    dim3 grid((n_res + 127) / 128, n_rows < 65535 ? n_rows : 65535);
+    sens_flow_kernel<<<grid, 128, 0, s>>>(parent, row_node, res_node, n_rows, n_res, out, ld);
+    return cudaGetLastError();
+}
+cudaError_t launch_to_time_major(const double* in, int n, int T, double* out, int64_t ld, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    dim3 grid((n + 31) / 32, (T + 31) / 32), block(32, 8);
+    to_time_major_kernel<<<grid, block, 0, s>>>(in, n, T, out, ld);
+    return cudaGetLastError();
+}
+
+}  // namespace revs

@@ -1,0 +1,147 @@
+// Batched per-consumer charging sub-problem: one warp per home.
+//
+// Reference: class Home (lpsolver.py:45-157) and solve_residence (lpsolver.py:433-463),
+// one Gurobi MIQP per home per ADMM iteration.  With p[t] = e[t]*rating, e binary, the
+// objective is separable and linear in e, and the SOC rows collapse to a window on the
+// number of charging hours, so the exact optimum is a selection: the n_min cheapest
+// hours of the plug-in window, then further hours while their cost is negative (up to
+// n_max); ties go to the earliest hour.  Lanes hold the hours (t = lane + 32 j); the rank
+// of every hour is found with warp shuffles, no sort and no shared memory.
+//
+// The hour cost is evaluated with individually rounded operations (__dmul_rn/__dadd_rn)
+// in the order oracle/revs_oracle.py:home_delta uses, so that the selection is
+// bit-identical with the CPU oracle whenever the inputs are.
+#include <math_constants.h>
+
+#include "kernels.cuh"
+
+namespace revs {
+
+constexpr int kMaxSlots = 8;   // hours per lane -> T <= 256
+
+
+template <int SLOTS>
+__global__ void __launch_bounds__(256) home_solve_kernel(HomeParams P) {
+    const int lane = threadIdx.x & 31;
+    const int h = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (h >= P.Hp) return;
+    const size_t base = (size_t)h * P.T;
+    const bool ev = P.has_ev[h] != 0;
+
+    double ld[SLOTS];
+#pragma unroll
+    for (int j = 0; j < SLOTS; ++j) {
+        int t = lane + 32 * j;
+        ld[j] = t < P.T ? P.load[base + t] : 0.0;
+    }
+    if (!ev) {   // warp-uniform: a home without EV only moves its load through
+#pragma unroll
+        for (int j = 0; j < SLOTS; ++j) {
+            int t = lane + 32 * j;
+            if (t < P.T) { P.p_sch_new[base + t] = ld[j]; P.p_ev[base + t] = 0.0; }
+        }
+        return;
+    }
+
+    const double rate = P.rating[h];
+    const int st = P.start[h], en = P.end[h];
+    const int nmin = P.n_min[h], nmax = P.n_max[h];
+    const double kap = P.kappa;
+    const double c0 = __dmul_rn(__dmul_rn(0.5 * kap, rate), rate);
+
+    double d[SLOTS];
+#pragma unroll
+    for (int j = 0; j < SLOTS; ++j) {
+        int t = lane + 32 * j;
+        double v = CUDART_INF;
+        if (t < P.T && t >= st && t < en) {
+            if (P.individual) {
+                // (0.01*c_t)*rating - 0.99*(rating/capacity)   (lpsolver.py:408-415)
+                v = __dadd_rn(__dmul_rn(__dmul_rn(0.01, P.cost[t]), rate), P.ind_const[h]);
+            } else {
+                double s = __dadd_rn(P.p_est[base + t], P.p_sch[base + t]);
+                double a = __dadd_rn(P.gamma[base + t], __dmul_rn(0.5 * kap, s));
+                double x = __dmul_rn(rate, __dadd_rn(P.cost[t], -a));
+                double y = __dmul_rn(__dmul_rn(kap, ld[j]), rate);
+                v = __dadd_rn(__dadd_rn(x, y), c0);
+            }
+        }
+        d[j] = v;
+    }
+
+    // rank[j] = #{hours s : d_s < d_t  or (d_s == d_t and s < t)}
+    int rank[SLOTS];
+#pragma unroll
+    for (int j = 0; j < SLOTS; ++j) rank[j] = 0;
+#pragma unroll
+    for (int js = 0; js < SLOTS; ++js) {
+        for (int src = 0; src < 32; ++src) {
+            double o = __shfl_sync(0xffffffffu, d[js], src);
+            int s = src + 32 * js;
+#pragma unroll
+            for (int j = 0; j < SLOTS; ++j) {
+                int t = lane + 32 * j;
+                rank[j] += (o < d[j]) || (o == d[j] && s < t);
+            }
+        }
+    }
+    int in_window = 0;
+#pragma unroll
+    for (int j = 0; j < SLOTS; ++j) in_window += (d[j] < CUDART_INF) ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) in_window += __shfl_xor_sync(0xffffffffu, in_window, o);
+    if (nmin > nmax || nmin > in_window) {
+        if (lane == 0) atomicExch(P.infeasible, 1);
+    }
+#pragma unroll
+    for (int j = 0; j < SLOTS; ++j) {
+        int t = lane + 32 * j;
+        if (t >= P.T) continue;
+        bool on = d[j] < CUDART_INF && (rank[j] < nmin || (rank[j] < nmax && d[j] < 0.0));
+        double p = on ? rate : 0.0;
+        P.p_ev[base + t] = p;
+        P.p_sch_new[base + t] = __dadd_rn(ld[j], p);
+    }
+}
+
+cudaError_t launch_home_solve(const HomeParams& P, cudaStream_t stream) {
+    const int warps = 8;
+    dim3 grid((P.Hp + warps - 1) / warps), block(32 * warps);
+    int slots = (P.T + 31) / 32;
+    if (slots <= 1) home_solve_kernel<1><<<grid, block, 0, stream>>>(P);
+    else if (slots <= 3) home_solve_kernel<3><<<grid, block, 0, stream>>>(P);
+    else if (slots <= kMaxSlots) home_solve_kernel<kMaxSlots><<<grid, block, 0, stream>>>(P);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
+// SOC[h][t+1] = SOC[h][t] + p_ev[h][t]/capacity  (lpsolver.py:104-109), one thread per home
+// hour would need a scan; T is tiny, so one lane walks a home and a warp covers 32 homes.
+__global__ void soc_profile_kernel(const double* __restrict__ p_ev, const uint8_t* __restrict__ has_ev,
+                                   const double* __restrict__ capacity,
+                                   const double* __restrict__ initial, double* __restrict__ soc,
+                                   int Hp, int T) {
+    int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= Hp) return;
+    double* s = soc + (size_t)h * (T + 1);
+    if (!has_ev[h]) {
+        for (int t = 0; t <= T; ++t) s[t] = 0.0;
+        return;
+    }
+    const double cap = capacity[h];
+    double acc = initial[h];
+    s[0] = acc;
+    for (int t = 0; t < T; ++t) {
+        acc = __dadd_rn(acc, __ddiv_rn(p_ev[(size_t)h * T + t], cap));
+        s[t + 1] = acc;
+    }
+}
+
+cudaError_t launch_soc_profile(const double* p_ev, const uint8_t* has_ev, const double* capacity,
+                               const double* initial, double* soc, int Hp, int T,
+                               cudaStream_t stream) {
+    soc_profile_kernel<<<(Hp + 127) / 128, 128, 0, stream>>>(p_ev, has_ev, capacity, initial, soc, Hp, T);
+    return cudaGetLastError();
+}
+
+}  // namespace revs

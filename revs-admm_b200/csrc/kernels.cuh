@@ -1,0 +1,96 @@
+// Parameter blocks and launchers of the REVS ADMM kernels (one .cu per kernel family).
+#pragma once
+#include "common.cuh"
+
+namespace revs {
+
+// ---- home_solve.cu
+struct HomeParams {
+    const double* load;       // [Hp][T]
+    const double* p_est;      // [Hp][T]  previous utility estimate
+    const double* p_sch;      // [Hp][T]  previous schedule
+    const double* gamma;      // [Hp][T]
+    const double* cost;       // [T]
+    const uint8_t* has_ev;    // [Hp]
+    const double* rating;     // [Hp]
+    const int* start;         // [Hp]
+    const int* end;           // [Hp]
+    const int* n_min;         // [Hp]  from the SOC rows, host-computed
+    const int* n_max;         // [Hp]
+    double* p_sch_new;        // [Hp][T]
+    double* p_ev;             // [Hp][T]
+    int* infeasible;          // flag
+    int Hp, T;
+    double kappa;
+    int individual;           // 1: objective of solve_residence instead of Home
+    const double* ind_const;  // [Hp]  -(0.99*(rating/capacity)), individual mode only
+};
+
+cudaError_t launch_home_solve(const HomeParams& P, cudaStream_t stream);
+cudaError_t launch_soc_profile(const double* p_ev, const uint8_t* has_ev, const double* capacity,
+                               const double* initial, double* soc, int Hp, int T, cudaStream_t stream);
+
+// ---- dual_update.cu
+struct ResidualOut {
+    double sum_primal;     // sum (P_est - P_sch)^2        (this device)
+    double sum_dual;       // sum (P_sch - P_sch_prev)^2
+    double primal;         // sqrt(sum_primal / count)
+    double dual;           // kappa * sqrt(sum_dual / count)
+    int converged;
+    unsigned ticket;
+};
+
+struct DualParams {
+    const double* g_t;         // [T][Hp]  P_est[k+1], time-major (utility output)
+    const double* p_sch_new;   // [Hp][T]
+    const double* p_sch_old;   // [Hp][T]
+    double* gamma;             // [Hp][T]  in: G[k]  out: G[k+1]
+    double* p_est;             // [Hp][T]  out: P_est[k+1], home-major
+    double* z_t;               // [T][Hp]  out: next projection target
+    double* diff_k;            // [Hp]     out
+    ResidualOut* res;
+    int Hp, T;
+    double kappa, tol, count;  // count = real homes * T
+};
+
+cudaError_t launch_dual_update(const DualParams& P, cudaStream_t stream);
+
+// ---- utility_qp.cu
+struct QpParams {
+    const FeederDev* feeders;
+    const double* Rpool;
+    const double* z_t;     // [T][Hp]
+    double* lam_t;         // [T][Hp]   multipliers (dense storage, sparse content)
+    double* g_t;           // [T][Hp]   out: projection = P_est[k+1]
+    const double* v_t;     // [T][Hp]   in (step mode): R g of the stored iterate
+    int* wcount;           // [ncols]
+    int* widx;             // [ncols][kWMax]
+    int* status;           // [ncols] 0 running, 1 converged, 2 working set overflow
+    int* inner_ok;         // [ncols] restricted problem solved to tolerance
+    int* n_running;        // columns still running after this launch
+    unsigned long long* newton_its;
+    int* max_ws;
+    int* n_failed;         // columns whose working set overflowed kWMax
+    int T;
+    int64_t Hp;
+    double u, tol;
+    int init;              // 1: first launch of a utility solve (warm start from lam_t)
+    int inner_max;
+};
+
+cudaError_t launch_utility_qp(const QpParams& P, int ncols, cudaStream_t stream);
+
+// ---- contract_f64.cu
+int contract_tile_rows(int T);
+cudaError_t launch_contract(const ContractProblem* d_problems, const ContractTile* d_tiles, int n_tiles,
+                            int T, int mode, double v2, cudaStream_t stream);
+
+// ---- feeder_build.cu
+cudaError_t launch_sens_voltage(const int* parent, const double* cumr, const int* row_node,
+                                const int* res_node, int n_rows, int n_res, double* out, int ld,
+                                cudaStream_t s);
+cudaError_t launch_sens_flow(const int* parent, const int* row_node, const int* res_node, int n_rows,
+                             int n_res, double* out, int ld, cudaStream_t s);
+cudaError_t launch_to_time_major(const double* in, int n, int T, double* out, int64_t ld, cudaStream_t s);
+
+}  // namespace revs

@@ -1,0 +1,876 @@
+// C ABI and device-side orchestration of the REVS ADMM path (see include/revs_admm.h).
+//
+// One revs_solver owns everything a batch of feeders needs on one B200: the dense
+// sensitivity blocks (n_f^2 doubles per feeder, 128-byte aligned, residences padded to a
+// multiple of 16 so every cp.async of the contraction is aligned), the home-major
+// [Hp][T] arrays of the consumer side, the time-major [T][Hp] arrays of the operator
+// side, the per-(feeder,hour) working sets and a small pinned block of counters that is
+// the only thing the host reads while the loop runs.
+//
+// An ADMM iteration (lpsolver.py:256-289) is, on the device:
+//   stream U:  utility_qp(init) -> { contract_f64 ; utility_qp(step) } until no column runs
+//   stream H:  home_solve           (uses the PREVIOUS iterates, so it overlaps stream U)
+//   stream U:  dual_update          (after both)
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+
+#include "../../include/revs_admm.h"
+#include "kernels.cuh"
+
+using namespace revs;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(x)                                                                               \
+    do {                                                                                    \
+        cudaError_t e_ = (x);                                                               \
+        if (e_ != cudaSuccess)                                                              \
+            return fail(REVS_ERR_CUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                \
+    } while (0)
+
+constexpr double kSocTarget = 0.9;   // lpsolver.py:111
+constexpr double kSocMax = 1.0;      // lpsolver.py:102
+constexpr double kCountTol = 1e-9;
+constexpr double kQpTol = 1e-11;     // KKT / feasibility tolerance of the utility QP
+constexpr int kQpInnerMax = 60;      // Newton steps per launch
+constexpr int kQpRoundMax = 400;     // working-set rounds per utility solve
+
+struct Counters {
+    int n_running;
+    int n_failed;
+    int infeasible;
+    int max_ws;
+    unsigned long long newton_its;
+    ResidualOut res;
+};
+
+struct Tree {
+    int n_nodes = 0;
+    int* d_parent = nullptr;
+    double* d_cumr = nullptr;
+    int* d_res_node = nullptr;
+};
+
+struct TimedSpan { cudaEvent_t a, b; int cat; };
+
+}  // namespace
+
+struct revs_solver {
+    int device = 0, nf = 0, T = 0, ncols = 0;
+    int64_t H = 0, Hp = 0;
+    std::vector<int64_t> off;            // compact home offsets [nf+1]
+    std::vector<FeederDev> feeders;
+    std::vector<char> sens_set;
+    std::vector<Tree> trees;
+    bool homes_set = false, tariff_set = false;
+
+    FeederDev* d_feeders = nullptr;
+    double* d_Rpool = nullptr;
+    // home-major [Hp][T]
+    double *d_load = nullptr, *d_pest = nullptr, *d_psch[2] = {nullptr, nullptr}, *d_gamma = nullptr,
+           *d_pev = nullptr, *d_soc = nullptr;
+    uint8_t* d_has_ev = nullptr;
+    double *d_rating = nullptr, *d_capacity = nullptr, *d_initial = nullptr, *d_indconst = nullptr;
+    int *d_start = nullptr, *d_end = nullptr, *d_nmin = nullptr, *d_nmax = nullptr, *d_zero_i = nullptr;
+    double* d_cost = nullptr;
+    // time-major [T][Hp]
+    double *d_zt = nullptr, *d_lamt = nullptr, *d_gt = nullptr, *d_vt = nullptr;
+    int *d_wcount = nullptr, *d_widx = nullptr, *d_status = nullptr, *d_innerok = nullptr;
+    Counters* d_cnt = nullptr;
+    Counters* h_cnt = nullptr;           // pinned mirror
+    double* d_diff = nullptr;
+    int diff_cap = 0;
+    ContractProblem* d_cprob = nullptr;
+    ContractTile* d_ctiles = nullptr;
+    int n_ctiles = 0;
+    cudaStream_t sU = nullptr, sH = nullptr;
+    cudaEvent_t evHomeDone = nullptr, evDualDone = nullptr, evT0 = nullptr, evT1 = nullptr;
+    std::vector<TimedSpan> spans;
+    size_t span_used = 0;
+
+    // run state
+    double kappa = 5.0, vset = 1.0, vlow = 0.95, vhigh = 1.05, tol = 0.0;
+    int iter_max = 0, k = 0, cur = 0;
+    bool running = false;
+    revs_stats stats{};
+};
+
+namespace {
+
+template <class Tp>
+cudaError_t dalloc(Tp** p, size_t n) {
+    cudaError_t e = cudaMalloc((void**)p, (n ? n : 1) * sizeof(Tp));
+    if (e == cudaSuccess) e = cudaMemset(*p, 0, (n ? n : 1) * sizeof(Tp));
+    return e;
+}
+
+int use_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(REVS_ERR_CUDA, "no CUDA device: %s (this library has no CPU fallback)",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(REVS_ERR_ARG, "device %d out of range (0..%d)", device, n - 1);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp pr;
+    CU(cudaGetDeviceProperties(&pr, device));
+    if (pr.major < 10)
+        return fail(REVS_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    pr.major, pr.minor);
+    return REVS_OK;
+}
+
+TimedSpan* span_begin(revs_solver* s, int cat, cudaStream_t st) {
+    if (s->span_used == s->spans.size()) {
+        TimedSpan sp;
+        cudaEventCreate(&sp.a);
+        cudaEventCreate(&sp.b);
+        sp.cat = cat;
+        s->spans.push_back(sp);
+    }
+    TimedSpan* sp = &s->spans[s->span_used++];
+    sp->cat = cat;
+    cudaEventRecord(sp->a, st);
+    return sp;
+}
+void span_end(TimedSpan* sp, cudaStream_t st) { cudaEventRecord(sp->b, st); }
+
+void spans_collect(revs_solver* s) {   // after the streams are synchronised
+    for (size_t i = 0; i < s->span_used; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, s->spans[i].a, s->spans[i].b) != cudaSuccess) continue;
+        switch (s->spans[i].cat) {
+            case 0: s->stats.gemm_ms += ms; break;
+            case 1: s->stats.home_ms += ms; break;
+            case 2: s->stats.dual_ms += ms; break;
+            case 3: s->stats.qp_ms += ms; break;
+        }
+    }
+    s->span_used = 0;
+}
+
+void count_window(double rating, double cap, double init, int* nmin, int* nmax) {
+    double step = rating / cap;
+    int lo = (int)std::ceil((kSocTarget - init) / step - kCountTol);
+    int hi = (int)std::floor((kSocMax - init) / step + kCountTol);
+    *nmin = lo < 0 ? 0 : lo;
+    *nmax = hi;
+}
+
+// copy a compact host array [H][w] into the padded device layout [Hp][w] (and back)
+int h2d_homes(revs_solver* s, double* dst, const double* src, int w) {
+    for (int f = 0; f < s->nf; ++f) {
+        size_t n = (size_t)(s->off[f + 1] - s->off[f]) * w;
+        if (n) CU(cudaMemcpyAsync(dst + (size_t)s->feeders[f].off * w, src + (size_t)s->off[f] * w,
+                                  n * sizeof(double), cudaMemcpyHostToDevice, s->sU));
+    }
+    return REVS_OK;
+}
+int d2h_homes(const revs_solver* s, double* dst, const double* src, int w) {
+    for (int f = 0; f < s->nf; ++f) {
+        size_t n = (size_t)(s->off[f + 1] - s->off[f]) * w;
+        if (n) CU(cudaMemcpyAsync(dst + (size_t)s->off[f] * w, src + (size_t)s->feeders[f].off * w,
+                                  n * sizeof(double), cudaMemcpyDeviceToHost, s->sU));
+    }
+    return REVS_OK;
+}
+
+template <class Tp>
+int h2d_padded_vec(revs_solver* s, Tp* dst, const Tp* src, Tp fill) {
+    std::vector<Tp> tmp((size_t)s->Hp, fill);
+    for (int f = 0; f < s->nf; ++f)
+        for (int64_t i = s->off[f]; i < s->off[f + 1]; ++i) tmp[s->feeders[f].off + (i - s->off[f])] = src[i];
+    CU(cudaMemcpy(dst, tmp.data(), tmp.size() * sizeof(Tp), cudaMemcpyHostToDevice));
+    return REVS_OK;
+}
+
+int check_ready(const revs_solver* s) {
+    if (!s) return fail(REVS_ERR_ARG, "null solver");
+    if (!s->homes_set) return fail(REVS_ERR_ARG, "revs_set_homes has not been called");
+    if (!s->tariff_set) return fail(REVS_ERR_ARG, "revs_set_tariff has not been called");
+    for (int f = 0; f < s->nf; ++f)
+        if (!s->sens_set[f]) return fail(REVS_ERR_ARG, "feeder %d has no sensitivity block", f);
+    return REVS_OK;
+}
+
+// One utility solve: project z_t onto the voltage polytope of every (feeder,hour) column.
+int utility_solve(revs_solver* s) {
+    QpParams Q;
+    Q.feeders = s->d_feeders;
+    Q.Rpool = s->d_Rpool;
+    Q.z_t = s->d_zt;
+    Q.lam_t = s->d_lamt;
+    Q.g_t = s->d_gt;
+    Q.v_t = s->d_vt;
+    Q.wcount = s->d_wcount;
+    Q.widx = s->d_widx;
+    Q.status = s->d_status;
+    Q.inner_ok = s->d_innerok;
+    Q.n_running = &s->d_cnt->n_running;
+    Q.newton_its = &s->d_cnt->newton_its;
+    Q.max_ws = &s->d_cnt->max_ws;
+    Q.n_failed = &s->d_cnt->n_failed;
+    Q.T = s->T;
+    Q.Hp = s->Hp;
+    Q.u = s->vhigh * s->vhigh - s->vset * s->vset;
+    Q.tol = kQpTol;
+    Q.inner_max = kQpInnerMax;
+
+    Q.init = 1;
+    TimedSpan* sp = span_begin(s, 3, s->sU);
+    CU(launch_utility_qp(Q, s->ncols, s->sU));
+    span_end(sp, s->sU);
+    s->stats.kernel_launches++;
+    Q.init = 0;
+    for (int round = 0;; ++round) {
+        if (round >= kQpRoundMax)
+            return fail(REVS_ERR_NOCONV, "utility QP: %d columns still running after %d working-set rounds",
+                        s->h_cnt->n_running, round);
+        sp = span_begin(s, 0, s->sU);
+        CU(launch_contract(s->d_cprob, s->d_ctiles, s->n_ctiles, s->T, kOutTimeMajor, 0.0, s->sU));
+        span_end(sp, s->sU);
+        CU(cudaMemsetAsync(&s->d_cnt->n_running, 0, sizeof(int), s->sU));
+        sp = span_begin(s, 3, s->sU);
+        CU(launch_utility_qp(Q, s->ncols, s->sU));
+        span_end(sp, s->sU);
+        s->stats.kernel_launches += 2;
+        s->stats.gemm_launches++;
+        s->stats.qp_outer_iterations++;
+        CU(cudaMemcpyAsync(s->h_cnt, s->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, s->sU));
+        CU(cudaStreamSynchronize(s->sU));
+        if (s->h_cnt->n_failed)
+            return fail(REVS_ERR_NOCONV,
+                        "utility QP: %d (feeder,hour) columns need more than %d simultaneously active "
+                        "voltage rows", s->h_cnt->n_failed, kWMax);
+        if (s->h_cnt->n_running == 0) break;
+    }
+    return REVS_OK;
+}
+
+HomeParams home_params(revs_solver* s, int individual) {
+    HomeParams P;
+    P.load = s->d_load;
+    P.p_est = s->d_pest;
+    P.p_sch = s->d_psch[s->cur];
+    P.gamma = s->d_gamma;
+    P.cost = s->d_cost;
+    P.has_ev = s->d_has_ev;
+    P.rating = s->d_rating;
+    P.start = s->d_start;
+    P.end = s->d_end;
+    P.n_min = individual ? s->d_zero_i : s->d_nmin;
+    P.n_max = s->d_nmax;
+    P.p_sch_new = s->d_psch[s->cur ^ 1];
+    P.p_ev = s->d_pev;
+    P.infeasible = &s->d_cnt->infeasible;
+    P.Hp = (int)s->Hp;
+    P.T = s->T;
+    P.kappa = s->kappa;
+    P.individual = individual;
+    P.ind_const = s->d_indconst;
+    return P;
+}
+
+void free_all(revs_solver* s) {
+    cudaSetDevice(s->device);
+    void* ptrs[] = {s->d_feeders, s->d_Rpool, s->d_load, s->d_pest, s->d_psch[0], s->d_psch[1], s->d_gamma,
+                    s->d_pev, s->d_soc, s->d_has_ev, s->d_rating, s->d_capacity, s->d_initial, s->d_indconst,
+                    s->d_start, s->d_end, s->d_nmin, s->d_nmax, s->d_zero_i, s->d_cost, s->d_zt, s->d_lamt,
+                    s->d_gt, s->d_vt, s->d_wcount, s->d_widx, s->d_status, s->d_innerok, s->d_cnt, s->d_diff,
+                    s->d_cprob, s->d_ctiles};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    for (auto& t : s->trees) {
+        if (t.d_parent) cudaFree(t.d_parent);
+        if (t.d_cumr) cudaFree(t.d_cumr);
+        if (t.d_res_node) cudaFree(t.d_res_node);
+    }
+    if (s->h_cnt) cudaFreeHost(s->h_cnt);
+    for (auto& sp : s->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    if (s->evHomeDone) cudaEventDestroy(s->evHomeDone);
+    if (s->evDualDone) cudaEventDestroy(s->evDualDone);
+    if (s->evT0) cudaEventDestroy(s->evT0);
+    if (s->evT1) cudaEventDestroy(s->evT1);
+    if (s->sU) cudaStreamDestroy(s->sU);
+    if (s->sH) cudaStreamDestroy(s->sH);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* revs_last_error(void) { return g_err.c_str(); }
+int revs_version(void) { return 100; }
+
+int revs_device_count(int* count) {
+    if (!count) return fail(REVS_ERR_ARG, "null pointer");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *count = 0; return fail(REVS_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); }
+    *count = n;
+    return REVS_OK;
+}
+
+int revs_create(revs_solver** out, int device, int n_feeders, const int64_t* feeder_off, int T) {
+    if (!out || !feeder_off || n_feeders <= 0 || T <= 0) return fail(REVS_ERR_ARG, "bad arguments");
+    if (T > 256) return fail(REVS_ERR_ARG, "horizon T=%d exceeds the supported 256 steps", T);
+    if (feeder_off[0] != 0) return fail(REVS_ERR_ARG, "feeder_off[0] must be 0");
+    for (int f = 0; f < n_feeders; ++f)
+        if (feeder_off[f + 1] < feeder_off[f]) return fail(REVS_ERR_ARG, "feeder_off must be non-decreasing");
+    int rc = use_device(device);
+    if (rc) return rc;
+
+    revs_solver* s = new revs_solver();
+    s->device = device;
+    s->nf = n_feeders;
+    s->T = T;
+    s->ncols = n_feeders * T;
+    s->off.assign(feeder_off, feeder_off + n_feeders + 1);
+    s->H = feeder_off[n_feeders];
+    s->feeders.resize(n_feeders);
+    s->sens_set.assign(n_feeders, 0);
+    s->trees.resize(n_feeders);
+    int64_t hp = 0, rp = 0;
+    for (int f = 0; f < n_feeders; ++f) {
+        int64_t n = feeder_off[f + 1] - feeder_off[f];
+        int64_t np = (n + kPad - 1) / kPad * kPad;
+        if (np == 0) np = kPad;
+        s->feeders[f] = FeederDev{(int)n, (int)np, hp, rp};
+        hp += np;
+        rp += np * np;
+    }
+    s->Hp = hp;
+    const size_t HT = (size_t)hp * T;
+
+#define TRY(x)                                                                                     \
+    do {                                                                                           \
+        cudaError_t e_ = (x);                                                                      \
+        if (e_ != cudaSuccess) {                                                                   \
+            free_all(s);                                                                           \
+            delete s;                                                                              \
+            return fail(REVS_ERR_CUDA, "%s failed: %s", #x, cudaGetErrorString(e_));               \
+        }                                                                                          \
+    } while (0)
+    TRY(cudaStreamCreateWithFlags(&s->sU, cudaStreamNonBlocking));
+    TRY(cudaStreamCreateWithFlags(&s->sH, cudaStreamNonBlocking));
+    TRY(cudaEventCreateWithFlags(&s->evHomeDone, cudaEventDisableTiming));
+    TRY(cudaEventCreateWithFlags(&s->evDualDone, cudaEventDisableTiming));
+    TRY(cudaEventCreate(&s->evT0));
+    TRY(cudaEventCreate(&s->evT1));
+    TRY(dalloc(&s->d_feeders, (size_t)n_feeders));
+    TRY(cudaMemcpy(s->d_feeders, s->feeders.data(), sizeof(FeederDev) * n_feeders, cudaMemcpyHostToDevice));
+    TRY(dalloc(&s->d_Rpool, (size_t)rp));
+    TRY(dalloc(&s->d_load, HT));
+    TRY(dalloc(&s->d_pest, HT));
+    TRY(dalloc(&s->d_psch[0], HT));
+    TRY(dalloc(&s->d_psch[1], HT));
+    TRY(dalloc(&s->d_gamma, HT));
+    TRY(dalloc(&s->d_pev, HT));
+    TRY(dalloc(&s->d_soc, (size_t)hp * (T + 1)));
+    TRY(dalloc(&s->d_has_ev, (size_t)hp));
+    TRY(dalloc(&s->d_rating, (size_t)hp));
+    TRY(dalloc(&s->d_capacity, (size_t)hp));
+    TRY(dalloc(&s->d_initial, (size_t)hp));
+    TRY(dalloc(&s->d_indconst, (size_t)hp));
+    TRY(dalloc(&s->d_start, (size_t)hp));
+    TRY(dalloc(&s->d_end, (size_t)hp));
+    TRY(dalloc(&s->d_nmin, (size_t)hp));
+    TRY(dalloc(&s->d_nmax, (size_t)hp));
+    TRY(dalloc(&s->d_zero_i, (size_t)hp));
+    TRY(dalloc(&s->d_cost, (size_t)T));
+    TRY(dalloc(&s->d_zt, HT));
+    TRY(dalloc(&s->d_lamt, HT));
+    TRY(dalloc(&s->d_gt, HT));
+    TRY(dalloc(&s->d_vt, HT));
+    TRY(dalloc(&s->d_wcount, (size_t)s->ncols));
+    TRY(dalloc(&s->d_widx, (size_t)s->ncols * kWMax));
+    TRY(dalloc(&s->d_status, (size_t)s->ncols));
+    TRY(dalloc(&s->d_innerok, (size_t)s->ncols));
+    TRY(dalloc(&s->d_cnt, (size_t)1));
+    TRY(cudaHostAlloc((void**)&s->h_cnt, sizeof(Counters), cudaHostAllocDefault));
+    memset(s->h_cnt, 0, sizeof(Counters));
+
+    // contraction table: V_t = R_f * G_t for every feeder, BM-row tiles
+    std::vector<ContractProblem> probs(n_feeders);
+    std::vector<ContractTile> tiles;
+    const int bm = contract_tile_rows(T);
+    for (int f = 0; f < n_feeders; ++f) {
+        const FeederDev& fd = s->feeders[f];
+        probs[f] = ContractProblem{s->d_Rpool + fd.roff, fd.np, fd.np, fd.np, s->d_gt + fd.off, hp,
+                                   s->d_vt + fd.off, hp, nullptr};
+        for (int r0 = 0; r0 < fd.np; r0 += bm) tiles.push_back(ContractTile{f, r0});
+    }
+    s->n_ctiles = (int)tiles.size();
+    TRY(dalloc(&s->d_cprob, probs.size()));
+    TRY(cudaMemcpy(s->d_cprob, probs.data(), probs.size() * sizeof(ContractProblem), cudaMemcpyHostToDevice));
+    TRY(dalloc(&s->d_ctiles, tiles.size()));
+    TRY(cudaMemcpy(s->d_ctiles, tiles.data(), tiles.size() * sizeof(ContractTile), cudaMemcpyHostToDevice));
+#undef TRY
+    *out = s;
+    return REVS_OK;
+}
+
+int revs_destroy(revs_solver* s) {
+    if (!s) return REVS_OK;
+    free_all(s);
+    delete s;
+    return REVS_OK;
+}
+
+int revs_set_sensitivity(revs_solver* s, int feeder, const double* R_res) {
+    if (!s || !R_res || feeder < 0 || feeder >= s->nf) return fail(REVS_ERR_ARG, "bad arguments");
+    CU(cudaSetDevice(s->device));
+    const FeederDev& fd = s->feeders[feeder];
+    for (int64_t i = 0; i < (int64_t)fd.n * fd.n; ++i)
+        if (!(R_res[i] >= 0.0)) return fail(REVS_ERR_ARG, "sensitivity block of feeder %d has a negative or NaN entry", feeder);
+    if (fd.n)
+        CU(cudaMemcpy2D(s->d_Rpool + fd.roff, (size_t)fd.np * sizeof(double), R_res, (size_t)fd.n * sizeof(double),
+                        (size_t)fd.n * sizeof(double), fd.n, cudaMemcpyHostToDevice));
+    s->sens_set[feeder] = 1;
+    return REVS_OK;
+}
+
+int revs_set_feeder_tree(revs_solver* s, int feeder, int n_nodes, const int32_t* parent, const double* r,
+                         const int32_t* res_node) {
+    if (!s || !parent || !r || !res_node || feeder < 0 || feeder >= s->nf || n_nodes <= 0)
+        return fail(REVS_ERR_ARG, "bad arguments");
+    CU(cudaSetDevice(s->device));
+    const FeederDev& fd = s->feeders[feeder];
+    std::vector<double> cumr(n_nodes);
+    for (int i = 0; i < n_nodes; ++i) {
+        if (parent[i] >= i || parent[i] < -1) return fail(REVS_ERR_ARG, "nodes must be topologically ordered (parent[i] < i)");
+        if (!(r[i] >= 0.0)) return fail(REVS_ERR_ARG, "negative or NaN resistance at node %d", i);
+        cumr[i] = (parent[i] < 0 ? 0.0 : cumr[parent[i]]) + r[i];
+    }
+    for (int j = 0; j < fd.n; ++j)
+        if (res_node[j] < 0 || res_node[j] >= n_nodes) return fail(REVS_ERR_ARG, "res_node[%d] out of range", j);
+    Tree& t = s->trees[feeder];
+    if (t.d_parent) { cudaFree(t.d_parent); cudaFree(t.d_cumr); cudaFree(t.d_res_node); t = Tree(); }
+    t.n_nodes = n_nodes;
+    CU(dalloc(&t.d_parent, (size_t)n_nodes));
+    CU(dalloc(&t.d_cumr, (size_t)n_nodes));
+    CU(dalloc(&t.d_res_node, (size_t)fd.np));
+    CU(cudaMemcpy(t.d_parent, parent, sizeof(int) * n_nodes, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(t.d_cumr, cumr.data(), sizeof(double) * n_nodes, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(t.d_res_node, res_node, sizeof(int) * fd.n, cudaMemcpyHostToDevice));
+    CU(launch_sens_voltage(t.d_parent, t.d_cumr, nullptr, t.d_res_node, fd.n, fd.n, s->d_Rpool + fd.roff, fd.np, s->sU));
+    CU(cudaStreamSynchronize(s->sU));
+    s->sens_set[feeder] = 1;
+    return REVS_OK;
+}
+
+int revs_set_homes(revs_solver* s, const double* load, const uint8_t* has_ev, const double* rating,
+                   const double* capacity, const double* initial, const int32_t* start, const int32_t* end) {
+    if (!s || !load || !has_ev) return fail(REVS_ERR_ARG, "bad arguments");
+    CU(cudaSetDevice(s->device));
+    const int64_t H = s->H;
+    std::vector<double> rt(H, 0.0), cp(H, 1.0), in(H, 0.0), ic(H, 0.0);
+    std::vector<int> st(H, 0), en(H, 0), nmin(H, 0), nmax(H, 0);
+    for (int64_t i = 0; i < H; ++i) {
+        if (!has_ev[i]) continue;
+        if (!rating || !capacity || !initial || !start || !end) return fail(REVS_ERR_ARG, "EV arrays missing");
+        if (!(rating[i] > 0.0) || !(capacity[i] > 0.0)) return fail(REVS_ERR_ARG, "home %lld: rating and capacity must be positive", (long long)i);
+        rt[i] = rating[i]; cp[i] = capacity[i]; in[i] = initial[i];
+        st[i] = start[i]; en[i] = end[i];
+        count_window(rating[i], capacity[i], initial[i], &nmin[i], &nmax[i]);
+        ic[i] = -(0.99 * (rating[i] / capacity[i]));
+    }
+    int rc;
+    if ((rc = h2d_homes(s, s->d_load, load, s->T))) return rc;
+    if ((rc = h2d_padded_vec<uint8_t>(s, s->d_has_ev, has_ev, 0))) return rc;
+    if ((rc = h2d_padded_vec<double>(s, s->d_rating, rt.data(), 0.0))) return rc;
+    if ((rc = h2d_padded_vec<double>(s, s->d_capacity, cp.data(), 1.0))) return rc;
+    if ((rc = h2d_padded_vec<double>(s, s->d_initial, in.data(), 0.0))) return rc;
+    if ((rc = h2d_padded_vec<double>(s, s->d_indconst, ic.data(), 0.0))) return rc;
+    if ((rc = h2d_padded_vec<int>(s, s->d_start, st.data(), 0))) return rc;
+    if ((rc = h2d_padded_vec<int>(s, s->d_end, en.data(), 0))) return rc;
+    if ((rc = h2d_padded_vec<int>(s, s->d_nmin, nmin.data(), 0))) return rc;
+    if ((rc = h2d_padded_vec<int>(s, s->d_nmax, nmax.data(), 0))) return rc;
+    CU(cudaStreamSynchronize(s->sU));
+    s->homes_set = true;
+    return REVS_OK;
+}
+
+int revs_set_tariff(revs_solver* s, const double* cost) {
+    if (!s || !cost) return fail(REVS_ERR_ARG, "bad arguments");
+    CU(cudaSetDevice(s->device));
+    CU(cudaMemcpy(s->d_cost, cost, sizeof(double) * s->T, cudaMemcpyHostToDevice));
+    s->tariff_set = true;
+    return REVS_OK;
+}
+
+int revs_admm_begin(revs_solver* s, double kappa, int iter_max, double vset, double vlow, double vhigh) {
+    int rc = check_ready(s);
+    if (rc) return rc;
+    if (!(kappa > 0.0) || iter_max <= 0) return fail(REVS_ERR_ARG, "kappa and iter_max must be positive");
+    const double u = vhigh * vhigh - vset * vset, lo = vlow * vlow - vset * vset;
+    if (!(u > 0.0) || !(lo <= 0.0))
+        return fail(REVS_ERR_ARG, "need vlow <= vset < vhigh (lpsolver.py:181-190 with g >= 0, R >= 0)");
+    CU(cudaSetDevice(s->device));
+    s->kappa = kappa; s->iter_max = iter_max; s->vset = vset; s->vlow = vlow; s->vhigh = vhigh;
+    s->k = 0; s->cur = 0; s->running = true;
+    memset(&s->stats, 0, sizeof s->stats);
+    const size_t HT = (size_t)s->Hp * s->T * sizeof(double);
+    double* zero[] = {s->d_pest, s->d_psch[0], s->d_psch[1], s->d_gamma, s->d_pev, s->d_zt, s->d_lamt, s->d_gt, s->d_vt};
+    for (double* p : zero) CU(cudaMemsetAsync(p, 0, HT, s->sU));
+    CU(cudaMemsetAsync(s->d_cnt, 0, sizeof(Counters), s->sU));
+    CU(cudaMemsetAsync(s->d_wcount, 0, sizeof(int) * s->ncols, s->sU));
+    if (s->diff_cap < iter_max) {
+        if (s->d_diff) CU(cudaFree(s->d_diff));
+        s->d_diff = nullptr;
+        CU(dalloc(&s->d_diff, (size_t)iter_max * s->Hp));
+        s->diff_cap = iter_max;
+    }
+    CU(cudaEventRecord(s->evT0, s->sU));
+    CU(cudaEventRecord(s->evDualDone, s->sU));
+    return REVS_OK;
+}
+
+int revs_admm_step(revs_solver* s, double sums[3]) {
+    if (!s || !s->running) return fail(REVS_ERR_ARG, "revs_admm_begin has not been called");
+    if (s->k >= s->iter_max) return fail(REVS_ERR_ARG, "iter_max iterations already done");
+    CU(cudaSetDevice(s->device));
+
+    // consumer side on its own stream: uses P_est[k], P_sch[k], Gamma[k] (lpsolver.py:275)
+    CU(cudaStreamWaitEvent(s->sH, s->evDualDone, 0));
+    HomeParams hp = home_params(s, 0);
+    TimedSpan* sp = span_begin(s, 1, s->sH);
+    CU(launch_home_solve(hp, s->sH));
+    span_end(sp, s->sH);
+    CU(cudaEventRecord(s->evHomeDone, s->sH));
+    s->stats.kernel_launches++;
+
+    // operator side
+    int rc = utility_solve(s);
+    if (rc) { s->running = false; cudaDeviceSynchronize(); return rc; }
+
+    // fused dual update / residuals / next target
+    CU(cudaStreamWaitEvent(s->sU, s->evHomeDone, 0));
+    CU(cudaMemsetAsync(&s->d_cnt->res, 0, sizeof(ResidualOut), s->sU));
+    DualParams D;
+    D.g_t = s->d_gt;
+    D.p_sch_new = s->d_psch[s->cur ^ 1];
+    D.p_sch_old = s->d_psch[s->cur];
+    D.gamma = s->d_gamma;
+    D.p_est = s->d_pest;
+    D.z_t = s->d_zt;
+    D.diff_k = s->d_diff + (size_t)s->k * s->Hp;
+    D.res = &s->d_cnt->res;
+    D.Hp = (int)s->Hp;
+    D.T = s->T;
+    D.kappa = s->kappa;
+    D.tol = s->tol;
+    D.count = (double)s->H * s->T;
+    sp = span_begin(s, 2, s->sU);
+    CU(launch_dual_update(D, s->sU));
+    span_end(sp, s->sU);
+    s->stats.kernel_launches++;
+    CU(cudaEventRecord(s->evDualDone, s->sU));
+    CU(cudaMemcpyAsync(s->h_cnt, s->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, s->sU));
+    CU(cudaEventRecord(s->evT1, s->sU));
+    CU(cudaStreamSynchronize(s->sU));
+    CU(cudaStreamSynchronize(s->sH));
+    spans_collect(s);
+    if (s->h_cnt->infeasible) {
+        s->running = false;
+        return fail(REVS_ERR_INFEASIBLE, "a home charging sub-problem is infeasible (SOC window vs plug-in window)");
+    }
+    s->cur ^= 1;
+    s->k++;
+    s->stats.admm_iterations = s->k;
+    s->stats.primal_residual = s->h_cnt->res.primal;
+    s->stats.dual_residual = s->h_cnt->res.dual;
+    s->stats.qp_newton_iterations = (int64_t)s->h_cnt->newton_its;
+    s->stats.max_working_set = s->h_cnt->max_ws;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, s->evT0, s->evT1);
+    s->stats.total_ms = ms;
+    if (sums) {
+        sums[0] = s->h_cnt->res.sum_primal;
+        sums[1] = s->h_cnt->res.sum_dual;
+        sums[2] = (double)s->H * s->T;
+    }
+    return REVS_OK;
+}
+
+int revs_solve_admm(revs_solver* s, double kappa, int iter_max, double vset, double vlow, double vhigh,
+                    double tol, int* iters_done) {
+    int rc = revs_admm_begin(s, kappa, iter_max, vset, vlow, vhigh);
+    if (rc) return rc;
+    s->tol = tol;
+    for (int k = 0; k < iter_max; ++k) {
+        rc = revs_admm_step(s, nullptr);
+        if (rc) return rc;
+        if (tol > 0.0 && s->h_cnt->res.converged) break;
+    }
+    s->tol = 0.0;
+    if (iters_done) *iters_done = s->k;
+    return REVS_OK;
+}
+
+int revs_get_results(const revs_solver* s, double* P_sch, double* P_ev, double* SOC, double* diff) {
+    if (!s) return fail(REVS_ERR_ARG, "null solver");
+    if (s->k == 0) return fail(REVS_ERR_ARG, "no ADMM iteration has run");
+    CU(cudaSetDevice(s->device));
+    int rc;
+    if (P_sch && (rc = d2h_homes(s, P_sch, s->d_psch[s->cur], s->T))) return rc;
+    if (P_ev && (rc = d2h_homes(s, P_ev, s->d_pev, s->T))) return rc;
+    if (SOC) {
+        CU(launch_soc_profile(s->d_pev, s->d_has_ev, s->d_capacity, s->d_initial, s->d_soc, (int)s->Hp, s->T, s->sU));
+        const_cast<revs_solver*>(s)->stats.kernel_launches++;
+        if ((rc = d2h_homes(s, SOC, s->d_soc, s->T + 1))) return rc;
+    }
+    if (diff)
+        for (int k = 0; k < s->k; ++k)
+            if ((rc = d2h_homes(s, diff + (size_t)k * s->H, s->d_diff + (size_t)k * s->Hp, 1))) return rc;
+    CU(cudaStreamSynchronize(s->sU));
+    return REVS_OK;
+}
+
+int revs_get_estimate(const revs_solver* s, double* P_est, double* Gamma) {
+    if (!s) return fail(REVS_ERR_ARG, "null solver");
+    CU(cudaSetDevice(s->device));
+    int rc;
+    if (P_est && (rc = d2h_homes(s, P_est, s->d_pest, s->T))) return rc;
+    if (Gamma && (rc = d2h_homes(s, Gamma, s->d_gamma, s->T))) return rc;
+    CU(cudaStreamSynchronize(s->sU));
+    return REVS_OK;
+}
+
+int revs_solve_individual(revs_solver* s, double* P_res, double* P_ev, double* SOC) {
+    if (!s) return fail(REVS_ERR_ARG, "null solver");
+    if (!s->homes_set || !s->tariff_set) return fail(REVS_ERR_ARG, "homes and tariff must be set");
+    CU(cudaSetDevice(s->device));
+    s->running = false;
+    memset(&s->stats, 0, sizeof s->stats);
+    CU(cudaMemsetAsync(s->d_cnt, 0, sizeof(Counters), s->sU));
+    s->cur = 0;
+    HomeParams hp = home_params(s, 1);
+    CU(cudaEventRecord(s->evT0, s->sU));
+    CU(launch_home_solve(hp, s->sU));
+    CU(launch_soc_profile(s->d_pev, s->d_has_ev, s->d_capacity, s->d_initial, s->d_soc, (int)s->Hp, s->T, s->sU));
+    CU(cudaEventRecord(s->evT1, s->sU));
+    s->stats.kernel_launches = 2;
+    int rc;
+    if (P_res && (rc = d2h_homes(s, P_res, s->d_psch[1], s->T))) return rc;
+    if (P_ev && (rc = d2h_homes(s, P_ev, s->d_pev, s->T))) return rc;
+    if (SOC && (rc = d2h_homes(s, SOC, s->d_soc, s->T + 1))) return rc;
+    CU(cudaMemcpyAsync(s->h_cnt, s->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, s->sU));
+    CU(cudaStreamSynchronize(s->sU));
+    cudaEventElapsedTime(&s->stats.total_ms, s->evT0, s->evT1);
+    s->stats.home_ms = s->stats.total_ms;
+    if (s->h_cnt->infeasible) return fail(REVS_ERR_INFEASIBLE, "a home charging sub-problem is infeasible");
+    return REVS_OK;
+}
+
+int revs_home_step(revs_solver* s, double kappa, const double* p_est, const double* p_sch, const double* gamma,
+                   double* P_sch_new, double* P_ev) {
+    if (!s || !p_est || !p_sch || !gamma) return fail(REVS_ERR_ARG, "bad arguments");
+    if (!s->homes_set || !s->tariff_set) return fail(REVS_ERR_ARG, "homes and tariff must be set");
+    CU(cudaSetDevice(s->device));
+    s->running = false;
+    s->kappa = kappa;
+    s->cur = 0;
+    int rc;
+    if ((rc = h2d_homes(s, s->d_pest, p_est, s->T))) return rc;
+    if ((rc = h2d_homes(s, s->d_psch[0], p_sch, s->T))) return rc;
+    if ((rc = h2d_homes(s, s->d_gamma, gamma, s->T))) return rc;
+    CU(cudaMemsetAsync(s->d_cnt, 0, sizeof(Counters), s->sU));
+    HomeParams hp = home_params(s, 0);
+    CU(launch_home_solve(hp, s->sU));
+    s->stats.kernel_launches++;
+    if (P_sch_new && (rc = d2h_homes(s, P_sch_new, s->d_psch[1], s->T))) return rc;
+    if (P_ev && (rc = d2h_homes(s, P_ev, s->d_pev, s->T))) return rc;
+    CU(cudaMemcpyAsync(s->h_cnt, s->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, s->sU));
+    CU(cudaStreamSynchronize(s->sU));
+    if (s->h_cnt->infeasible) return fail(REVS_ERR_INFEASIBLE, "a home charging sub-problem is infeasible");
+    return REVS_OK;
+}
+
+int revs_utility_step(revs_solver* s, double kappa, double vset, double vlow, double vhigh, const double* p_est,
+                      const double* p_sch, const double* gamma, const double* lam0, double* P_est_new,
+                      double* lam_out) {
+    if (!s || !p_est || !p_sch || !gamma) return fail(REVS_ERR_ARG, "bad arguments");
+    for (int f = 0; f < s->nf; ++f)
+        if (!s->sens_set[f]) return fail(REVS_ERR_ARG, "feeder %d has no sensitivity block", f);
+    const double u = vhigh * vhigh - vset * vset, lo = vlow * vlow - vset * vset;
+    if (!(u > 0.0) || !(lo <= 0.0) || !(kappa > 0.0))
+        return fail(REVS_ERR_ARG, "need kappa > 0 and vlow <= vset < vhigh");
+    CU(cudaSetDevice(s->device));
+    s->running = false;
+    s->kappa = kappa; s->vset = vset; s->vlow = vlow; s->vhigh = vhigh;
+    const int T = s->T;
+    const size_t HT = (size_t)s->Hp * T;
+    std::vector<double> zt(HT, 0.0), lt(HT, 0.0);
+    for (int f = 0; f < s->nf; ++f)
+        for (int64_t i = s->off[f]; i < s->off[f + 1]; ++i) {
+            const int64_t hp = s->feeders[f].off + (i - s->off[f]);
+            for (int t = 0; t < T; ++t) {
+                const size_t src = (size_t)i * T + t;
+                zt[(size_t)t * s->Hp + hp] = (p_est[src] + p_sch[src]) / 2.0 - gamma[src] / kappa;
+                if (lam0) lt[(size_t)t * s->Hp + hp] = lam0[src];
+            }
+        }
+    CU(cudaMemcpyAsync(s->d_zt, zt.data(), HT * sizeof(double), cudaMemcpyHostToDevice, s->sU));
+    CU(cudaMemcpyAsync(s->d_lamt, lt.data(), HT * sizeof(double), cudaMemcpyHostToDevice, s->sU));
+    CU(cudaMemsetAsync(s->d_gt, 0, HT * sizeof(double), s->sU));
+    CU(cudaMemsetAsync(s->d_vt, 0, HT * sizeof(double), s->sU));
+    CU(cudaMemsetAsync(s->d_cnt, 0, sizeof(Counters), s->sU));
+    CU(cudaMemsetAsync(s->d_wcount, 0, sizeof(int) * s->ncols, s->sU));
+    memset(&s->stats, 0, sizeof s->stats);
+    int rc = utility_solve(s);
+    spans_collect(s);
+    if (rc) return rc;
+    s->stats.qp_newton_iterations = (int64_t)s->h_cnt->newton_its;
+    s->stats.max_working_set = s->h_cnt->max_ws;
+    std::vector<double> gt(HT);
+    CU(cudaMemcpy(gt.data(), s->d_gt, HT * sizeof(double), cudaMemcpyDeviceToHost));
+    if (lam_out) CU(cudaMemcpy(lt.data(), s->d_lamt, HT * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int f = 0; f < s->nf; ++f)
+        for (int64_t i = s->off[f]; i < s->off[f + 1]; ++i) {
+            const int64_t hp = s->feeders[f].off + (i - s->off[f]);
+            for (int t = 0; t < T; ++t) {
+                if (P_est_new) P_est_new[(size_t)i * T + t] = gt[(size_t)t * s->Hp + hp];
+                if (lam_out) lam_out[(size_t)i * T + t] = lt[(size_t)t * s->Hp + hp];
+            }
+        }
+    return REVS_OK;
+}
+
+int revs_reliability(revs_solver* s, int feeder, int kind, int n_rows, const int32_t* rows, const double* scale,
+                     double vset, const double* P, double* out) {
+    if (!s || feeder < 0 || feeder >= s->nf || n_rows < 0 || !rows || !out) return fail(REVS_ERR_ARG, "bad arguments");
+    if (kind != REVS_REL_VOLTAGE && kind != REVS_REL_FLOW && kind != REVS_REL_DROP) return fail(REVS_ERR_ARG, "bad kind");
+    const Tree& t = s->trees[feeder];
+    if (!t.d_parent) return fail(REVS_ERR_ARG, "feeder %d has no tree (call revs_set_feeder_tree)", feeder);
+    if (!P && s->k == 0) return fail(REVS_ERR_ARG, "no schedule given and no ADMM result available");
+    for (int i = 0; i < n_rows; ++i)
+        if (rows[i] < 0 || rows[i] >= t.n_nodes) return fail(REVS_ERR_ARG, "rows[%d] out of range", i);
+    if (n_rows == 0) return REVS_OK;
+    CU(cudaSetDevice(s->device));
+    const FeederDev& fd = s->feeders[feeder];
+    const int T = s->T;
+    int* d_rows = nullptr;
+    double *d_S = nullptr, *d_Pt = nullptr, *d_P = nullptr, *d_out = nullptr, *d_scale = nullptr;
+    ContractProblem* d_prob = nullptr;
+    ContractTile* d_tiles = nullptr;
+    int rc = REVS_OK;
+    auto cleanup = [&]() {
+        cudaFree(d_rows); cudaFree(d_S); cudaFree(d_Pt); cudaFree(d_P); cudaFree(d_out); cudaFree(d_scale);
+        cudaFree(d_prob); cudaFree(d_tiles);
+    };
+#define TRYR(x)                                                                          \
+    do {                                                                                 \
+        cudaError_t e_ = (x);                                                            \
+        if (e_ != cudaSuccess) {                                                         \
+            cleanup();                                                                   \
+            return fail(REVS_ERR_CUDA, "%s failed: %s", #x, cudaGetErrorString(e_));     \
+        }                                                                                \
+    } while (0)
+    TRYR(dalloc(&d_rows, (size_t)n_rows));
+    TRYR(cudaMemcpy(d_rows, rows, sizeof(int) * n_rows, cudaMemcpyHostToDevice));
+    TRYR(dalloc(&d_S, (size_t)n_rows * fd.np));
+    TRYR(dalloc(&d_Pt, (size_t)T * fd.np));
+    TRYR(dalloc(&d_out, (size_t)n_rows * T));
+    const double* src = s->d_psch[s->cur] + (size_t)fd.off * T;
+    if (P) {
+        TRYR(dalloc(&d_P, (size_t)fd.n * T));
+        TRYR(cudaMemcpy(d_P, P, sizeof(double) * fd.n * T, cudaMemcpyHostToDevice));
+        src = d_P;
+    }
+    if (kind == REVS_REL_FLOW) {
+        TRYR(launch_sens_flow(t.d_parent, d_rows, t.d_res_node, n_rows, fd.n, d_S, fd.np, s->sU));
+        if (scale) {
+            TRYR(dalloc(&d_scale, (size_t)n_rows));
+            TRYR(cudaMemcpy(d_scale, scale, sizeof(double) * n_rows, cudaMemcpyHostToDevice));
+        }
+    } else {
+        TRYR(launch_sens_voltage(t.d_parent, t.d_cumr, d_rows, t.d_res_node, n_rows, fd.n, d_S, fd.np, s->sU));
+    }
+    TRYR(launch_to_time_major(src, fd.n, T, d_Pt, fd.np, s->sU));
+    {
+        ContractProblem pb{d_S, fd.np, n_rows, fd.np, d_Pt, fd.np, d_out, T, d_scale};
+        std::vector<ContractTile> tiles;
+        const int bm = contract_tile_rows(T);
+        for (int r0 = 0; r0 < n_rows; r0 += bm) tiles.push_back(ContractTile{0, r0});
+        TRYR(dalloc(&d_prob, (size_t)1));
+        TRYR(cudaMemcpy(d_prob, &pb, sizeof pb, cudaMemcpyHostToDevice));
+        TRYR(dalloc(&d_tiles, tiles.size()));
+        TRYR(cudaMemcpy(d_tiles, tiles.data(), tiles.size() * sizeof(ContractTile), cudaMemcpyHostToDevice));
+        int mode = kind == REVS_REL_VOLTAGE ? kOutVoltage : (kind == REVS_REL_FLOW ? kOutScaled : kOutNodeMajor);
+        TRYR(launch_contract(d_prob, d_tiles, (int)tiles.size(), T, mode, vset * vset, s->sU));
+    }
+    TRYR(cudaMemcpyAsync(out, d_out, sizeof(double) * n_rows * T, cudaMemcpyDeviceToHost, s->sU));
+    TRYR(cudaStreamSynchronize(s->sU));
+#undef TRYR
+    s->stats.kernel_launches += 3;
+    s->stats.gemm_launches += 1;
+    cleanup();
+    return rc;
+}
+
+int revs_contract(int device, int M, int K, int T, const double* A, const double* B, double* C) {
+    if (M <= 0 || K <= 0 || T <= 0 || !A || !B || !C) return fail(REVS_ERR_ARG, "bad arguments");
+    int rc = use_device(device);
+    if (rc) return rc;
+    const int Kp = (K + kPad - 1) / kPad * kPad;
+    std::vector<double> Ap((size_t)M * Kp, 0.0), Bt((size_t)T * Kp, 0.0);
+    for (int i = 0; i < M; ++i) memcpy(&Ap[(size_t)i * Kp], A + (size_t)i * K, sizeof(double) * K);
+    for (int k = 0; k < K; ++k)
+        for (int t = 0; t < T; ++t) Bt[(size_t)t * Kp + k] = B[(size_t)k * T + t];
+    double *dA = nullptr, *dB = nullptr, *dC = nullptr;
+    ContractProblem* d_prob = nullptr;
+    ContractTile* d_tiles = nullptr;
+    auto cleanup = [&]() { cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(d_prob); cudaFree(d_tiles); };
+#define TRYC(x)                                                                          \
+    do {                                                                                 \
+        cudaError_t e_ = (x);                                                            \
+        if (e_ != cudaSuccess) {                                                         \
+            cleanup();                                                                   \
+            return fail(REVS_ERR_CUDA, "%s failed: %s", #x, cudaGetErrorString(e_));     \
+        }                                                                                \
+    } while (0)
+    TRYC(dalloc(&dA, Ap.size()));
+    TRYC(dalloc(&dB, Bt.size()));
+    TRYC(dalloc(&dC, (size_t)M * T));
+    TRYC(cudaMemcpy(dA, Ap.data(), Ap.size() * sizeof(double), cudaMemcpyHostToDevice));
+    TRYC(cudaMemcpy(dB, Bt.data(), Bt.size() * sizeof(double), cudaMemcpyHostToDevice));
+    ContractProblem pb{dA, Kp, M, Kp, dB, Kp, dC, T, nullptr};
+    std::vector<ContractTile> tiles;
+    const int bm = contract_tile_rows(T);
+    for (int r0 = 0; r0 < M; r0 += bm) tiles.push_back(ContractTile{0, r0});
+    TRYC(dalloc(&d_prob, (size_t)1));
+    TRYC(cudaMemcpy(d_prob, &pb, sizeof pb, cudaMemcpyHostToDevice));
+    TRYC(dalloc(&d_tiles, tiles.size()));
+    TRYC(cudaMemcpy(d_tiles, tiles.data(), tiles.size() * sizeof(ContractTile), cudaMemcpyHostToDevice));
+    TRYC(launch_contract(d_prob, d_tiles, (int)tiles.size(), T, kOutNodeMajor, 0.0, 0));
+    TRYC(cudaMemcpy(C, dC, sizeof(double) * M * T, cudaMemcpyDeviceToHost));
+#undef TRYC
+    cleanup();
+    return REVS_OK;
+}
+
+int revs_get_stats(const revs_solver* s, revs_stats* out) {
+    if (!s || !out) return fail(REVS_ERR_ARG, "bad arguments");
+    *out = s->stats;
+    return REVS_OK;
+}
+
+}  // extern "C"

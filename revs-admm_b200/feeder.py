@@ -1,0 +1,144 @@
+"""Radial feeders as arrays: what the device needs of the reference's networkx graph.
+
+The reference keeps the feeder as a networkx graph (extract.py:56-88 GetDistNet) and turns
+it into dense sensitivity matrices by inverting its incidence matrix (lpsolver.py:17-26).
+Here the graph is reduced once, on the host, to a rooted tree in topological order
+(parent index, resistance of the edge above each node, residence -> node index); the
+dense blocks are then built on the GPU (csrc/feeder_build.cu).
+"""
+from dataclasses import dataclass, field
+
+import numpy as np
+
+
+@dataclass
+class FeederTree:
+    parent: np.ndarray            # int32 [n]  (-1 = substation), parent[i] < i
+    r: np.ndarray                 # float64 [n] resistance of the edge above node i
+    res_node: np.ndarray          # int32 [n_res] tree index of every residence
+    node_ids: list = field(default_factory=list)   # tree index -> graph node id
+    res_ids: list = field(default_factory=list)    # residence order of the reference
+    edge_keys: list = field(default_factory=list)  # tree index -> (u, v) as in graph.edges
+    edge_sign: np.ndarray = None  # +1 if (u, v) points away from the substation
+    edge_type: list = field(default_factory=list)
+
+    @property
+    def n_nodes(self):
+        return len(self.parent)
+
+    @property
+    def n_res(self):
+        return len(self.res_node)
+
+    def cumulative_r(self):
+        c = np.zeros(self.n_nodes)
+        for i in range(self.n_nodes):
+            c[i] = (c[self.parent[i]] if self.parent[i] >= 0 else 0.0) + self.r[i]
+        return c
+
+    def rmat(self):
+        """Dense R over all non-substation nodes in tree order (host, O(n^2)); the
+        matrix of lpsolver.py:17-26 up to the node permutation ``node_ids``."""
+        n = self.n_nodes
+        R = np.zeros((n, n))
+        for i in range(n):
+            p = self.parent[i]
+            if p >= 0:
+                R[i, :i] = R[p, :i]
+                R[:i, i] = R[i, :i]
+                R[i, i] = R[p, p] + 2.0 * self.r[i]
+            else:
+                R[i, i] = 2.0 * self.r[i]
+        return R
+
+
+def tree_from_graph(graph):
+    """Root the reference's feeder graph at its substation (label 'S')."""
+    roots = [n for n in graph.nodes if graph.nodes[n]["label"] == "S"]
+    if len(roots) != 1:
+        raise ValueError("expected exactly one substation node (label 'S')")
+    root = roots[0]
+    if graph.number_of_edges() != graph.number_of_nodes() - 1:
+        raise ValueError("feeder is not radial (edges != nodes - 1)")
+    order, par = [], {}
+    index = {root: -1}
+    stack = [root]
+    while stack:                      # depth-first, parents before children
+        u = stack.pop()
+        for v in graph.neighbors(u):
+            if v in index:
+                continue
+            index[v] = len(order)
+            order.append(v)
+            par[v] = u
+            stack.append(v)
+    if len(order) != graph.number_of_nodes() - 1:
+        raise ValueError("feeder graph is not connected")
+    n = len(order)
+    parent = np.array([index[par[v]] for v in order], dtype=np.int32)
+    r = np.array([graph.edges[par[v], v]["r"] for v in order], dtype=np.float64)
+    orient = {}
+    for (a, b) in graph.edges:
+        orient[frozenset((a, b))] = (a, b)
+    keys, sign, types = [], np.ones(n), []
+    for i, v in enumerate(order):
+        a, b = orient[frozenset((par[v], v))]
+        keys.append((a, b))
+        sign[i] = 1.0 if a == par[v] else -1.0
+        types.append(graph.edges[a, b].get("type"))
+    res_ids = [n_ for n_ in graph if graph.nodes[n_]["label"] == "H"]
+    res_node = np.array([index[h] for h in res_ids], dtype=np.int32)
+    return FeederTree(parent=parent, r=r, res_node=res_node, node_ids=order, res_ids=res_ids,
+                      edge_keys=keys, edge_sign=sign, edge_type=types)
+
+
+def synthetic_feeder(n_homes, seed=0, laterals=5, homes_per_xfmr=2.5,
+                     r_primary=1.0e-6, r_secondary=3.2e-4):
+    """Synthetic radial feeder shaped like the reference's 121144 network: a substation,
+    ``laterals`` primary chains of transformer nodes, 1-4 residences per transformer on
+    secondary lines (the reference has 1126 homes / 462 transformers, primary r ~1e-6,
+    secondary r ~3e-4 with a long tail)."""
+    rng = np.random.default_rng(seed)
+    n_x = max(laterals, int(np.ceil(n_homes / homes_per_xfmr)))
+    lat = np.sort(rng.integers(0, laterals, size=n_x))          # lateral of each transformer
+    first = np.r_[True, lat[1:] != lat[:-1]]
+    parent_x = np.where(first, -1, np.arange(n_x) - 1).astype(np.int32)
+    r_x = r_primary * rng.lognormal(0.0, 0.8, size=n_x)
+    home_x = np.sort(rng.integers(0, n_x, size=n_homes)).astype(np.int32)
+    r_h = r_secondary * rng.lognormal(0.0, 1.0, size=n_homes)
+    parent = np.concatenate([parent_x, home_x]).astype(np.int32)
+    r = np.concatenate([r_x, r_h])
+    res_node = (n_x + np.arange(n_homes)).astype(np.int32)
+    return FeederTree(parent=parent, r=r, res_node=res_node, edge_sign=np.ones(len(parent)))
+
+
+def synthetic_homes(n_homes, T, seed=0, adoption=0.9, rating_kw=4.8, capacity=20.0,
+                    initial=0.2, steps_per_hour=None):
+    """Synthetic home population of the reference's shape: a daily base-load profile with
+    an evening peak, EV adopters with the reference's charger data (revs_config.yaml:12-20),
+    plug-in window 17:00 -> 05:00 as in start_time=11,end_time=23 of a day that starts at
+    06:00.  With T=96 the capacity is scaled so that the charging energy is unchanged."""
+    rng = np.random.default_rng(seed + 7919)
+    sph = steps_per_hour or max(1, T // 24)
+    hours = (np.arange(T) / sph + 6.0) % 24.0
+    shape = 0.6 + 0.5 * np.exp(-0.5 * ((hours - 19.0) / 2.5) ** 2) + 0.25 * np.exp(-0.5 * ((hours - 8.0) / 1.5) ** 2)
+    scale = rng.lognormal(0.3, 0.5, size=(n_homes, 1))
+    load = scale * shape[None, :] * (1.0 + 0.15 * rng.standard_normal((n_homes, T)))
+    load = np.round(np.maximum(load, 0.05), 5)
+    has_ev = (rng.random(n_homes) < adoption).astype(np.uint8)
+    rating = np.full(n_homes, rating_kw)
+    cap = np.full(n_homes, capacity * sph)        # kWh expressed in kW*steps
+    init = np.full(n_homes, initial)
+    start = np.full(n_homes, 11 * sph, dtype=np.int32)
+    end = np.full(n_homes, 23 * sph, dtype=np.int32)
+    return dict(load=load, has_ev=has_ev, rating=rating, capacity=cap, initial=init,
+                start=start, end=end)
+
+
+def synthetic_tariff(T):
+    """The DVP time-of-use tariff of the reference (input/DVP-tariff.txt) rolled to a day
+    that starts at 06:00 (extract.py:24 with shift=6), repeated to T steps."""
+    day = np.array([0.07866] * 5 + [0.095111] * 10 + [0.214357] * 3 + [0.095111] * 6)
+    day = np.roll(day, -6)
+    sph = max(1, T // 24)
+    return np.repeat(day, sph)[:T] if T >= 24 else day[:T]

@@ -1,0 +1,201 @@
+"""Drop-in for the reference's lpsolver.py: same entry points, B200 back end.
+
+Reference                                   here
+------------------------------------------  ---------------------------------------------
+compute_Rmat(graph)        lpsolver.py:17   same matrix, from the rooted tree (host; setup only)
+Home(...).solve()          lpsolver.py:45   Home(...)    -> revs_home_step    (1 warp / home)
+Utility(...).solve()       lpsolver.py:160  Utility(...) -> revs_utility_step (working-set QP
+                                            + FP64 tensor-core contraction)
+solve_ADMM(...)            lpsolver.py:244  whole loop on the device -> revs_solve_admm
+solve_residence(...)       lpsolver.py:433  revs_solve_individual
+solve_central(...)         lpsolver.py:466  out of scope of this path (raises)
+
+Arguments keep the reference's meaning; ``grbpath`` / ``path`` (Gurobi log directories)
+are accepted and ignored.  Everything numerical runs in hand-written CUDA through the C
+ABI of include/revs_admm.h; if the library or the GPU is missing these calls raise.
+"""
+import numpy as np
+
+from . import _cabi
+from .feeder import tree_from_graph
+
+__all__ = ["compute_Rmat", "Home", "Utility", "solve_ADMM", "solve_residence",
+           "solve_residences", "solve_central", "compute_voltage", "compute_flows"]
+
+
+# ------------------------------------------------------------------ helpers
+def _home_arrays(homes, res):
+    """dict-of-homes (extract.get_homes_ev_param) -> the arrays of revs_set_homes."""
+    H = len(res)
+    load = np.array([homes[h]["LOAD"] for h in res], dtype=np.float64)
+    has_ev = np.zeros(H, np.uint8)
+    rating, cap, init = np.zeros(H), np.ones(H), np.zeros(H)
+    start, end = np.zeros(H, np.int32), np.zeros(H, np.int32)
+    for i, h in enumerate(res):
+        ev = homes[h]["EV"]
+        if ev:
+            has_ev[i] = 1
+            rating[i], cap[i], init[i] = ev["rating"], ev["capacity"], ev["initial"]
+            start[i], end[i] = ev["start"], ev["end"]
+    return dict(load=load, has_ev=has_ev, rating=rating, capacity=cap, initial=init,
+                start=start, end=end)
+
+
+def _solver_for_graph(graph, homes, cost, device=0):
+    tree = tree_from_graph(graph)
+    res = tree.res_ids
+    s = _cabi.Solver([len(res)], len(cost), device=device)
+    s.set_feeder_tree(0, tree.parent, tree.r, tree.res_node)
+    s.set_homes(**_home_arrays(homes, res))
+    s.set_tariff(cost)
+    return s, tree, res
+
+
+def _as_table(tab, res, T):
+    if isinstance(tab, dict):
+        return np.array([np.asarray(tab[h], dtype=np.float64) for h in res]).reshape(len(res), T)
+    return np.asarray(tab, dtype=np.float64).reshape(len(res), T)
+
+
+# ------------------------------------------------------------------ network
+def compute_Rmat(graph):
+    """R = 2 F D F^T of lpsolver.py:17-26, rows/cols ordered like
+    ``[n for n in graph.nodes if label != 'S']``."""
+    tree = tree_from_graph(graph)
+    Rt = tree.rmat()
+    pos = {n: i for i, n in enumerate(tree.node_ids)}
+    perm = [pos[n] for n in graph.nodes if graph.nodes[n]["label"] != "S"]
+    return Rt[np.ix_(perm, perm)]
+
+
+# ------------------------------------------------------------------ sub-problems
+class Home:
+    """One consumer's charging problem (lpsolver.py:45-157); solved on the GPU."""
+
+    def __init__(self, cost, homedata, p_est, p_sch, gamma, kappa=5.0):
+        self.c = list(cost)
+        self.T = len(cost)
+        self.data = homedata
+        self.kappa = kappa
+        self._in = [np.asarray(x, dtype=np.float64).reshape(1, self.T) for x in (p_est, p_sch, gamma)]
+
+    def solve(self, grbpath=None):
+        ev = self.data["EV"]
+        with _cabi.Solver([1], self.T) as s:
+            s.set_sensitivity(0, np.zeros((1, 1)))
+            s.set_homes(**_home_arrays({0: self.data}, [0]))
+            s.set_tariff(self.c)
+            g, p = s.home_step(*self._in, kappa=self.kappa)
+        self.g_opt = g[0].tolist()
+        self.p_opt = p[0].tolist()
+        soc = [0.0] * (self.T + 1)
+        if ev:
+            soc[0] = ev["initial"]
+            for t in range(self.T):
+                soc[t + 1] = soc[t] + self.p_opt[t] / ev["capacity"]
+        self.s_opt = soc
+        return
+
+
+class Utility:
+    """The operator's estimate under the voltage limits (lpsolver.py:160-240)."""
+
+    def __init__(self, graph, P_util, P_sch, Gamma, kappa=5.0, vset=1.0, low=0.95, high=1.05):
+        self.tree = tree_from_graph(graph)
+        self.res = self.tree.res_ids
+        self.nodes = [n for n in graph.nodes if graph.nodes[n]["label"] != "S"]
+        self.N = len(self.nodes)
+        self.T = len(Gamma[self.res[0]])
+        self.kappa, self.vset, self.low, self.high = kappa, vset, low, high
+        self._in = [_as_table(x, self.res, self.T) for x in (P_util, P_sch, Gamma)]
+
+    def solve(self, grbpath=None):
+        with _cabi.Solver([len(self.res)], self.T) as s:
+            s.set_feeder_tree(0, self.tree.parent, self.tree.r, self.tree.res_node)
+            g, lam = s.utility_step(*self._in, kappa=self.kappa, vset=self.vset,
+                                    vlow=self.low, vhigh=self.high)
+        self.g_opt = {h: g[i].tolist() for i, h in enumerate(self.res)}
+        self.lam_opt = {h: lam[i] for i, h in enumerate(self.res)}
+        return
+
+
+# ------------------------------------------------------------------ the ADMM loop
+def solve_ADMM(homes, graph, cost, grbpath=None, kappa=5.0, iter_max=15,
+               vset=1.0, vlow=0.95, vhigh=1.05, tol=0.0, device=0, return_stats=False):
+    """Iterative ADMM of lpsolver.py:244-293, entirely on the device.
+
+    Returns ``diff, P_sch, S, C`` exactly like the reference: diff[k][h] for k=1..iter_max,
+    and the last iterate's residence profile, EV charger profile and SOC profile per home.
+    ``tol`` > 0 (an extension) stops once both ADMM residuals fall below it."""
+    s, tree, res = _solver_for_graph(graph, homes, cost, device)
+    with s:
+        done = s.solve_admm(kappa=kappa, iter_max=iter_max, vset=vset, vlow=vlow, vhigh=vhigh, tol=tol)
+        out = s.results(done)
+        stats = s.stats()
+    diff = {k + 1: {h: out["diff"][k, i] for i, h in enumerate(res)} for k in range(done)}
+    P = {h: out["P_sch"][i] for i, h in enumerate(res)}
+    S = {h: out["P_ev"][i] for i, h in enumerate(res)}
+    Csoc = {h: out["SOC"][i] for i, h in enumerate(res)}
+    if return_stats:
+        return diff, P, S, Csoc, stats
+    return diff, P, S, Csoc
+
+
+# ------------------------------------------------------------------ individual optimum
+def solve_residences(tariff, homes, device=0):
+    """solve_residence for a whole dict of homes in one launch."""
+    res = list(homes)
+    with _cabi.Solver([len(res)], len(tariff), device=device) as s:
+        s.set_homes(**_home_arrays(homes, res))
+        s.set_tariff(tariff)
+        out = s.solve_individual()
+    return ({h: out["P_ev"][i] for i, h in enumerate(res)},
+            {h: out["SOC"][i] for i, h in enumerate(res)},
+            {h: out["P_res"][i] for i, h in enumerate(res)})
+
+
+def solve_residence(tariff, data, path=None):
+    """lpsolver.py:433-463: returns p_opt, s_opt, g_opt of one home."""
+    p, s, g = solve_residences(tariff, {0: data})
+    return p[0], s[0], g[0]
+
+
+def solve_central(tariff, homes, dist, path=None, vset=1.0, vmin=0.9, vmax=1.05):
+    raise NotImplementedError(
+        "solve_central (lpsolver.py:466-502, one network-wide MILP) is outside the distributed "
+        "ADMM hot path this package accelerates; see DESIGN.md, scope table row (f)")
+
+
+# ------------------------------------------------------------------ reliability check
+def _schedule_rows(p_sch, tree):
+    T = len(next(iter(p_sch.values())))
+    return np.array([np.asarray(p_sch[h], dtype=np.float64) for h in tree.res_ids]).reshape(tree.n_res, T), T
+
+
+def compute_voltage(graph, p_sch, vset=1.0, device=0):
+    """drawing.py:62-78: {node: voltage profile} for every non-substation node."""
+    tree = tree_from_graph(graph)
+    P, T = _schedule_rows(p_sch, tree)
+    with _cabi.Solver([tree.n_res], T, device=device) as s:
+        s.set_feeder_tree(0, tree.parent, tree.r, tree.res_node)
+        V = s.reliability(0, _cabi.REVS_REL_VOLTAGE, np.arange(tree.n_nodes), vset=vset, P=P)
+    return {n: V[i].tolist() for i, n in enumerate(tree.node_ids)}
+
+
+LINE_RATING_KVA = {  # conductor ampacity x voltage, drawing.py:30-40
+    "OH_Voluta": 95 * 0.24, "OH_Periwinkle": 125 * 0.24, "OH_Conch": 165 * 0.24,
+    "OH_Neritina": 220 * 0.24, "OH_Runcina": 265 * 0.24, "OH_Zuzara": 350 * 0.24,
+    "OH_Swanate": 145 * 12.47, "OH_Sparrow": 185 * 12.47, "OH_Raven": 240 * 12.47,
+    "OH_Pegion": 315 * 12.47, "OH_Penguin": 365 * 12.47,
+}
+
+
+def compute_flows(graph, p_sch, device=0):
+    """drawing.py:28-60: {edge: signed loading = flow / rating} for every line."""
+    tree = tree_from_graph(graph)
+    P, T = _schedule_rows(p_sch, tree)
+    rating = np.array([np.sqrt(3) * LINE_RATING_KVA[t] for t in tree.edge_type])
+    with _cabi.Solver([tree.n_res], T, device=device) as s:
+        s.set_feeder_tree(0, tree.parent, tree.r, tree.res_node)
+        F = s.reliability(0, _cabi.REVS_REL_FLOW, np.arange(tree.n_nodes), scale=tree.edge_sign / rating, P=P)
+    return {e: F[i].tolist() for i, e in enumerate(tree.edge_keys)}

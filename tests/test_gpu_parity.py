@@ -1,0 +1,248 @@
+"""GPU parity tests: the CUDA path through the C ABI against the CPU oracle.
+
+Tolerances are the ones BASELINE.json's north_star states: schedules <= 1e-4 kW per
+home-hour, voltages <= 1e-5 pu, objective rel. <= 1e-6; integer decisions (which hours a
+charger is on) must be identical.
+"""
+import numpy as np
+import pytest
+
+import revs_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL_KW = 1e-4
+TOL_PU = 1e-5
+
+
+def _arrays(homes, res):
+    from revs_admm_b200.lpsolver import _home_arrays
+    return _home_arrays(homes, res)
+
+
+def _oracle_kwargs(a):
+    return dict(load=a["load"], ev_mask=a["has_ev"].astype(bool), rating=a["rating"],
+                capacity=a["capacity"], initial=a["initial"], start=a["start"], end=a["end"])
+
+
+# ----------------------------------------------------------------- contraction
+@pytest.mark.parametrize("M,K,T", [(1, 1, 1), (7, 5, 3), (64, 16, 24), (130, 100, 24), (200, 333, 48),
+                                   (129, 1000, 96), (1126, 1126, 24), (300, 257, 100)])
+def test_contract_matches_numpy(gpu_lib, M, K, T):
+    rng = np.random.default_rng(M * 1000 + K + T)
+    A, B = rng.standard_normal((M, K)), rng.standard_normal((K, T))
+    C = gpu_lib.contract(A, B)
+    ref = A @ B
+    assert np.abs(C - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()) * np.sqrt(K)
+
+
+# ----------------------------------------------------------------- home step
+def test_home_step_bit_exact_random(gpu_lib):
+    from revs_admm_b200.feeder import synthetic_homes, synthetic_tariff
+    for T, H in [(24, 257), (96, 130), (40, 33)]:
+        hm = synthetic_homes(H, T, seed=T)
+        if T == 40:
+            hm["start"][:] = 3
+            hm["end"][:] = 37
+            hm["capacity"][:] = 20.0
+        cost = synthetic_tariff(96)[:T] if T != 24 else synthetic_tariff(24)
+        rng = np.random.default_rng(T)
+        p_est, p_sch = rng.uniform(0, 8, (H, T)), rng.uniform(0, 8, (H, T))
+        gamma = rng.standard_normal((H, T))
+        with gpu_lib.Solver([H], T) as s:
+            s.set_homes(**hm)
+            s.set_tariff(cost)
+            g, p = s.home_step(p_est, p_sch, gamma, kappa=5.0)
+        for i in range(H):
+            ev = {} if not hm["has_ev"][i] else dict(rating=hm["rating"][i], capacity=hm["capacity"][i],
+                                                     initial=hm["initial"][i], start=hm["start"][i], end=hm["end"][i])
+            po, so, go = O.home_subproblem(cost, hm["load"][i], ev, p_est[i], p_sch[i], gamma[i], 5.0)
+            assert np.array_equal(p[i], po), f"home {i} T={T}"
+            assert np.array_equal(g[i], go)
+
+
+def test_home_step_ties_pick_earliest_hour(gpu_lib):
+    T, H = 24, 40
+    load = np.full((H, T), 1.846)
+    cost = np.full(T, 0.0951)
+    hm = dict(load=load, has_ev=np.ones(H, np.uint8), rating=np.full(H, 4.8), capacity=np.full(H, 20.0),
+              initial=np.full(H, 0.2), start=np.full(H, 11, np.int32), end=np.full(H, 23, np.int32))
+    z = np.zeros((H, T))
+    with gpu_lib.Solver([H], T) as s:
+        s.set_homes(**hm)
+        s.set_tariff(cost)
+        g, p = s.home_step(z, z, z)
+    assert (np.nonzero(p[0])[0] == [11, 12, 13]).all()
+    assert np.array_equal(p, np.tile(p[0], (H, 1)))
+
+
+def test_home_step_infeasible_is_an_error(gpu_lib):
+    T, H = 24, 4
+    hm = dict(load=np.ones((H, T)), has_ev=np.ones(H, np.uint8), rating=np.full(H, 4.8),
+              capacity=np.full(H, 20.0), initial=np.full(H, 0.2), start=np.full(H, 11, np.int32),
+              end=np.full(H, 13, np.int32))          # 2-hour window, 3 hours needed
+    z = np.zeros((H, T))
+    with gpu_lib.Solver([H], T) as s:
+        s.set_homes(**hm)
+        s.set_tariff(np.ones(T))
+        with pytest.raises(gpu_lib.RevsError) as e:
+            s.home_step(z, z, z)
+        assert e.value.code == 3
+
+
+# ----------------------------------------------------------------- individual optimum
+def test_individual_matches_oracle_and_golden_objective(gpu_lib, case121144, golden):
+    from revs_admm_b200.lpsolver import solve_residences
+    homes, tariff = case121144["homes"], case121144["tariff"]
+    Pev, soc, Pres = solve_residences(tariff, homes)
+    ev_ids = golden["individual_ev_ids"]
+    c = np.asarray(tariff)
+    for k, h in enumerate(ev_ids):
+        h = int(h)
+        po, so, go = O.solve_residence(tariff, homes[h])
+        assert np.array_equal(Pev[h], po)
+        assert np.allclose(soc[h], so, atol=1e-15)
+        # the reference's own result: same objective (hours may differ where the tariff ties)
+        gold_p, gold_s = golden["individual_P_ev"][k], golden["individual_SOC"][k]
+        obj = 0.01 * c @ Pres[h] + 0.99 * (1 - soc[h][-1])
+        load = Pres[h] - Pev[h]
+        obj_gold = 0.01 * c @ (load + gold_p) + 0.99 * (1 - gold_s[-1])
+        assert abs(obj - obj_gold) <= 1e-6 * abs(obj_gold)
+
+
+# ----------------------------------------------------------------- utility step
+def _rand_state(H, T, load, seed):
+    rng = np.random.default_rng(seed)
+    p_sch = load + 4.8 * (rng.random((H, T)) < 0.15)
+    p_est = np.maximum(p_sch - rng.uniform(0, 1, (H, T)), 0)
+    gamma = rng.standard_normal((H, T)) * 0.5
+    return p_est, p_sch, gamma
+
+
+def test_utility_step_real_feeder(gpu_lib, case121144):
+    from revs_admm_b200.feeder import tree_from_graph
+    dist, homes = case121144["dist"], case121144["homes"]
+    tree = tree_from_graph(dist)
+    res, Rres = O.residence_block(dist)
+    assert res == tree.res_ids
+    a = _arrays(homes, res)
+    H, T = a["load"].shape
+    p_est, p_sch, gamma = _rand_state(H, T, a["load"], 1)
+    with gpu_lib.Solver([H], T) as s:
+        s.set_feeder_tree(0, tree.parent, tree.r, tree.res_node)
+        g, lam = s.utility_step(p_est, p_sch, gamma, kappa=5.0, vset=1.03, vlow=0.95, vhigh=1.05)
+        st = s.stats()
+    go, lo, _ = O.utility_subproblem(Rres, p_est, p_sch, gamma, 5.0, 1.03, 0.95, 1.05)
+    assert np.abs(g - go).max() <= TOL_KW * 1e-2
+    u = 1.05 ** 2 - 1.03 ** 2
+    assert (Rres @ g).max() <= u + 1e-9
+    assert g.min() >= 0.0
+    assert st["gemm_launches"] >= 1 and st["qp_newton_iterations"] > 0
+
+
+def test_utility_step_multi_feeder_synthetic_tight(gpu_lib):
+    from revs_admm_b200.feeder import synthetic_feeder, synthetic_homes
+    sizes, T = [37, 150, 64], 24
+    trees = [synthetic_feeder(n, seed=i, r_secondary=2e-3) for i, n in enumerate(sizes)]
+    H = sum(sizes)
+    hm = synthetic_homes(H, T, seed=3)
+    p_est, p_sch, gamma = _rand_state(H, T, hm["load"], 5)
+    vset, vhigh = 1.0, 1.01                      # tight: many rows active
+    with gpu_lib.Solver(sizes, T) as s:
+        for f, t in enumerate(trees):
+            s.set_feeder_tree(f, t.parent, t.r, t.res_node)
+        g, lam = s.utility_step(p_est, p_sch, gamma, kappa=5.0, vset=vset, vlow=0.9, vhigh=vhigh)
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    for f, t in enumerate(trees):
+        R = O.rmat_from_tree(t.parent, t.r)[np.ix_(t.res_node, t.res_node)]
+        sl = slice(off[f], off[f + 1])
+        go, _, _ = O.utility_subproblem(R, p_est[sl], p_sch[sl], gamma[sl], 5.0, vset, 0.9, vhigh)
+        assert np.abs(g[sl] - go).max() <= TOL_KW * 1e-2
+
+
+# ----------------------------------------------------------------- the whole loop
+def test_admm_real_feeder_matches_oracle(gpu_lib, case121144, golden):
+    """configs[0] of BASELINE.json: 121144 / Com-2 / 90 % / 4800 W, 15 iterations."""
+    from revs_admm_b200.lpsolver import solve_ADMM
+    homes, tariff, dist = case121144["homes"], case121144["tariff"], case121144["dist"]
+    diff, P, S, C, stats = solve_ADMM(homes, dist, tariff, None, kappa=5.0, iter_max=15,
+                                      vset=1.03, vlow=0.95, vhigh=1.05, return_stats=True)
+    do, Po, So, Co = O.solve_ADMM(homes, dist, tariff, None, kappa=5.0, iter_max=15,
+                                  vset=1.03, vlow=0.95, vhigh=1.05)
+    res = list(Po)
+    assert stats["admm_iterations"] == 15 and stats["kernel_launches"] > 45
+    for h in res:
+        assert np.array_equal(S[h], So[h]), f"charging hours differ at home {h}"
+        assert np.abs(P[h] - Po[h]).max() <= TOL_KW
+        assert np.allclose(C[h], Co[h], atol=1e-12)
+    for k in range(1, 16):
+        d = np.array([diff[k][h] for h in res])
+        dref = np.array([do[k][h] for h in res])
+        assert np.abs(d - dref).max() <= 1e-7, f"iteration {k}"
+    # and the reference's own file where it is a function of the inputs: iteration 1
+    ev_ids = [int(h) for h in golden["distributed_ev_ids"]]
+    d1 = np.array([diff[1][h] for h in ev_ids])
+    assert np.abs(d1 - golden["distributed_diff"][:, 0]).max() <= 1e-12
+    # objective (tariff cost of the schedule) rel 1e-6
+    c = np.asarray(tariff)
+    cost = sum(c @ P[h] for h in res)
+    cost_o = sum(c @ Po[h] for h in res)
+    assert abs(cost - cost_o) <= 1e-6 * abs(cost_o)
+    # voltages of the final schedule, GPU reliability check vs oracle
+    from revs_admm_b200.lpsolver import compute_voltage, compute_flows
+    V = compute_voltage(dist, P, vset=1.03)
+    Vo = O.compute_voltage(dist, Po, vset=1.03)
+    assert max(np.abs(np.asarray(V[n]) - Vo[n]).max() for n in Vo) <= TOL_PU
+    Fl = compute_flows(dist, P)
+    Fo = O.compute_flows(dist, Po)
+    assert max(np.abs(np.asarray(Fl[e]) - Fo[e]).max() for e in Fo) <= 1e-6
+
+
+def test_admm_multi_feeder_synthetic_96(gpu_lib):
+    """Shape of configs[2..4]: several feeders, 96 quarter-hour steps, tight limits."""
+    from revs_admm_b200.feeder import synthetic_feeder, synthetic_homes, synthetic_tariff
+    sizes, T = [90, 61, 130], 96
+    trees = [synthetic_feeder(n, seed=10 + i, r_secondary=1e-3) for i, n in enumerate(sizes)]
+    H = sum(sizes)
+    hm = synthetic_homes(H, T, seed=11)
+    cost = synthetic_tariff(T)
+    kw = dict(kappa=5.0, iter_max=6, vset=1.0, vlow=0.95, vhigh=1.02)
+    with gpu_lib.Solver(sizes, T) as s:
+        for f, t in enumerate(trees):
+            s.set_feeder_tree(f, t.parent, t.r, t.res_node)
+        s.set_homes(**hm)
+        s.set_tariff(cost)
+        done = s.solve_admm(**kw)
+        out = s.results(done)
+        P_est, Gam = s.estimate()
+    Rb = [O.rmat_from_tree(t.parent, t.r)[np.ix_(t.res_node, t.res_node)] for t in trees]
+    ref = O.solve_ADMM_arrays(Rb, cost=cost, **_oracle_kwargs(hm), **kw)
+    assert np.array_equal(out["P_ev"], ref["P_ev"])
+    assert np.abs(out["P_sch"] - ref["P_sch"]).max() <= TOL_KW
+    assert np.abs(P_est - ref["P_est"]).max() <= TOL_KW
+    assert np.abs(Gam - ref["Gamma"]).max() <= 1e-4
+    assert np.abs(out["diff"] - ref["diff"]).max() <= 1e-7
+    assert np.allclose(out["SOC"], ref["SOC"], atol=1e-12)
+
+
+def test_admm_early_stop_and_step_api(gpu_lib):
+    from revs_admm_b200.feeder import synthetic_feeder, synthetic_homes, synthetic_tariff
+    n, T = 50, 24
+    t = synthetic_feeder(n, seed=2, r_secondary=1e-5)       # loose network: converges quickly
+    hm = synthetic_homes(n, T, seed=2)
+    with gpu_lib.Solver([n], T) as s:
+        s.set_feeder_tree(0, t.parent, t.r, t.res_node)
+        s.set_homes(**hm)
+        s.set_tariff(synthetic_tariff(T))
+        done = s.solve_admm(iter_max=40, tol=1e-6)
+        assert done < 40
+        st = s.stats()
+        assert st["primal_residual"] < 1e-6 and st["dual_residual"] < 1e-6
+        full = s.results(done)
+        s.admm_begin(iter_max=done)
+        for _ in range(done):
+            sums = s.admm_step()
+        assert sums[2] == n * T
+        again = s.results(done)
+    assert np.array_equal(full["P_sch"], again["P_sch"])
+    assert np.array_equal(full["diff"], again["diff"])
