@@ -53,19 +53,30 @@ import numpy as np
 SOC_TARGET = 0.9      # lpsolver.py:111  s[T] >= 0.9
 SOC_MAX = 1.0         # lpsolver.py:102  ub = 1.0
 PHI_NOISE = 1e-14     # relative rounding noise admitted by the line search of the utility QP
+ARC_MIN = 2.0 ** -20   # shortest step of the arc search before the Hessian shift is raised
 COUNT_TOL = 1e-9      # slack on the SOC count window (Gurobi's own FeasibilityTol is 1e-6)
 
 
 # --------------------------------------------------------------------------- network
 def compute_Rmat(graph):
     """lpsolver.py:17-26.  R = 2 F D F^T with F the inverse reduced incidence matrix."""
-    import networkx as nx
-    A = nx.incidence_matrix(graph, nodelist=list(graph.nodes()),
-                            edgelist=list(graph.edges()), oriented=True).toarray()
+    A = oriented_incidence(graph)
     node_ind = [i for i, n in enumerate(graph.nodes()) if graph.nodes[n]["label"] != "S"]
     F = np.linalg.inv(A[node_ind, :].T)
     D = np.diag([graph.edges[e]["r"] for e in graph.edges])
     return 2 * F @ D @ F.T
+
+
+def oriented_incidence(graph):
+    """networkx.incidence_matrix(graph, nodelist=graph.nodes, edgelist=graph.edges,
+    oriented=True) as a dense array: -1 at the first endpoint of every edge, +1 at the
+    second (written out so that the oracle needs numpy only)."""
+    pos = {n: i for i, n in enumerate(graph.nodes())}
+    A = np.zeros((graph.number_of_nodes(), graph.number_of_edges()))
+    for k, (a, b) in enumerate(graph.edges()):
+        A[pos[a], k] = -1.0
+        A[pos[b], k] = 1.0
+    return A
 
 
 def rmat_from_tree(parent, r):
@@ -170,20 +181,27 @@ def solve_residence_arrays(tariff, load, ev):
 
 
 # --------------------------------------------------------------------------- utility step
-def project_voltage(z, R, u, lam0=None, tol=1e-11, maxit=500):
+def project_voltage(z, R, u, lam0=None, tol=1e-11, maxit=500, rn2=None):
     """argmin 1/2||g-z||^2  s.t. g>=0, R g <= u   (one time step of class Utility).
 
     Dual: minimise phi(lam) = 1/2||[z - R lam]_+||^2 + u*sum(lam) over lam>=0, by
-    projected Newton (free set = not {lam~0 and gradient>0}; Hessian R_AF R_FA) with
-    an Armijo search along the projection arc.  Returns (g, lam, iterations)."""
+    projected Newton (free set = not {lam~0 and gradient>0}; Hessian R_AF R_FA over the
+    homes F with g>0) with an Armijo search along the projection arc.  The Hessian is
+    shifted by mu = 1e-10*tau*mean(|R_a|^2); tau grows (x1e3) whenever the arc search
+    finds no acceptable step (the Hessian is singular or zero where many homes sit at
+    g=0) and relaxes (/10) after full steps -- a Levenberg-Marquardt safeguard that
+    leaves the fixed point untouched.  Returns (g, lam, iterations)."""
     n = len(z)
     lam = np.zeros(n) if lam0 is None else np.maximum(lam0, 0.0)
+    if rn2 is None:
+        rn2 = (R * R).sum(axis=1)
 
     def phi(lm):
         gg = np.maximum(z - R @ lm, 0.0)
         return 0.5 * gg @ gg + u * lm.sum(), gg
 
     f, g = phi(lam)
+    tau = 1.0
     for it in range(maxit):
         grad = u - R @ g
         kkt = np.max(np.abs(np.where(lam > 0, grad, np.minimum(grad, 0.0))))
@@ -193,20 +211,29 @@ def project_voltage(z, R, u, lam0=None, tol=1e-11, maxit=500):
         free = ~((lam <= eps) & (grad > 0))
         F = g > 0
         RAF = R[np.ix_(free, F)]
-        H = RAF @ RAF.T
-        H[np.diag_indices_from(H)] += 1e-10 * np.trace(H) / max(1, H.shape[0]) + 1e-300
-        d = np.zeros(n)
-        d[free] = -np.linalg.solve(H, grad[free])
-        a = 1.0
+        H0 = RAF @ RAF.T
+        scale = rn2[free].mean()
         while True:
-            ln = np.maximum(lam + a * d, 0.0)
-            fn, gn = phi(ln)
-            # the last term is the rounding noise of phi itself: close to the solution the
-            # predicted decrease (~kkt^2) drops below it and a plain Armijo test would
-            # reject the (correct) full Newton step
-            if fn <= f + 1e-4 * grad @ (ln - lam) + PHI_NOISE * abs(f) or a < 1e-12:
+            H = H0.copy()
+            H[np.diag_indices_from(H)] += 1e-10 * tau * scale + 1e-300
+            d = -lam                      # pinned rows (tiny lam, gradient > 0) go to exactly 0
+            d[free] = -np.linalg.solve(H, grad[free])
+            a, found = 1.0, False
+            while a >= ARC_MIN:
+                ln = np.maximum(lam + a * d, 0.0)
+                fn, gn = phi(ln)
+                # the last term is the rounding noise of phi itself: close to the solution
+                # the predicted decrease (~kkt^2) drops below it and a plain Armijo test
+                # would reject the (correct) full Newton step
+                if fn <= f + 1e-4 * grad @ (ln - lam) + PHI_NOISE * abs(f):
+                    found = True
+                    break
+                a *= 0.5
+            if found or tau > 1e40:
                 break
-            a *= 0.5
+            tau *= 1e3
+        if a == 1.0:
+            tau = max(1.0, tau / 10.0)
         lam, f, g = ln, fn, gn
     raise RuntimeError("utility QP did not converge (kkt=%g)" % kkt)
 
@@ -222,8 +249,9 @@ def utility_subproblem(R, p_est, p_sch, gamma, kappa, vset, vlow, vhigh, lam0=No
     g = np.empty_like(z)
     lam = np.zeros_like(z) if lam0 is None else lam0.copy()
     its = 0
+    rn2 = (R * R).sum(axis=1)
     for t in range(T):
-        g[:, t], lam[:, t], k = project_voltage(z[:, t], R, u, lam[:, t])
+        g[:, t], lam[:, t], k = project_voltage(z[:, t], R, u, lam[:, t], rn2=rn2)
         its += k
     return g, lam, its
 
@@ -340,13 +368,11 @@ LINE_RATING = {  # drawing.py:29-40 (kVA), repeated in test-dist-ind-opt.py:156-
 
 def compute_flows(graph, p_sch):
     """drawing.py:28-60.  Per-edge loading (signed flow / rating)."""
-    import networkx as nx
     nodelist = [n for n in graph if graph.nodes[n]["label"] != "S"]
     res = set(n for n in graph if graph.nodes[n]["label"] == "H")
     nodeind = [i for i, n in enumerate(graph.nodes) if graph.nodes[n]["label"] != "S"]
     T = len(next(iter(p_sch.values())))
-    A = nx.incidence_matrix(graph, nodelist=list(graph.nodes), edgelist=list(graph.edges),
-                            oriented=True).toarray()
+    A = oriented_incidence(graph)
     A_inv = np.linalg.inv(A[nodeind, :])
     P = np.zeros((len(nodelist), T))
     for i, n in enumerate(nodelist):

@@ -59,6 +59,7 @@ cudaError_t launch_dual_update(const DualParams& P, cudaStream_t stream);
 struct QpParams {
     const FeederDev* feeders;
     const double* Rpool;
+    const double* rn2;     // [Hp]  squared row norms of the sensitivity blocks
     const double* z_t;     // [T][Hp]
     double* lam_t;         // [T][Hp]   multipliers (dense storage, sparse content)
     double* g_t;           // [T][Hp]   out: projection = P_est[k+1]
@@ -91,6 +92,8 @@ cudaError_t launch_sens_voltage(const int* parent, const double* cumr, const int
                                 cudaStream_t s);
 cudaError_t launch_sens_flow(const int* parent, const int* row_node, const int* res_node, int n_rows,
                              int n_res, double* out, int ld, cudaStream_t s);
+cudaError_t launch_row_norms(const FeederDev* feeders, int n_feeders, const double* Rpool, double* rn2,
+                             cudaStream_t s);
 cudaError_t launch_to_time_major(const double* in, int n, int T, double* out, int64_t ld, cudaStream_t s);
 
 }  // namespace revs

@@ -83,6 +83,8 @@ struct revs_solver {
 
     FeederDev* d_feeders = nullptr;
     double* d_Rpool = nullptr;
+    double* d_rn2 = nullptr;
+    bool rn2_valid = false;
     // home-major [Hp][T]
     double *d_load = nullptr, *d_pest = nullptr, *d_psch[2] = {nullptr, nullptr}, *d_gamma = nullptr,
            *d_pev = nullptr, *d_soc = nullptr;
@@ -215,6 +217,12 @@ int utility_solve(revs_solver* s) {
     QpParams Q;
     Q.feeders = s->d_feeders;
     Q.Rpool = s->d_Rpool;
+    Q.rn2 = s->d_rn2;
+    if (!s->rn2_valid) {
+        CU(launch_row_norms(s->d_feeders, s->nf, s->d_Rpool, s->d_rn2, s->sU));
+        s->rn2_valid = true;
+        s->stats.kernel_launches++;
+    }
     Q.z_t = s->d_zt;
     Q.lam_t = s->d_lamt;
     Q.g_t = s->d_gt;
@@ -290,7 +298,7 @@ HomeParams home_params(revs_solver* s, int individual) {
 
 void free_all(revs_solver* s) {
     cudaSetDevice(s->device);
-    void* ptrs[] = {s->d_feeders, s->d_Rpool, s->d_load, s->d_pest, s->d_psch[0], s->d_psch[1], s->d_gamma,
+    void* ptrs[] = {s->d_feeders, s->d_Rpool, s->d_rn2, s->d_load, s->d_pest, s->d_psch[0], s->d_psch[1], s->d_gamma,
                     s->d_pev, s->d_soc, s->d_has_ev, s->d_rating, s->d_capacity, s->d_initial, s->d_indconst,
                     s->d_start, s->d_end, s->d_nmin, s->d_nmax, s->d_zero_i, s->d_cost, s->d_zt, s->d_lamt,
                     s->d_gt, s->d_vt, s->d_wcount, s->d_widx, s->d_status, s->d_innerok, s->d_cnt, s->d_diff,
@@ -377,6 +385,7 @@ int revs_create(revs_solver** out, int device, int n_feeders, const int64_t* fee
     TRY(dalloc(&s->d_feeders, (size_t)n_feeders));
     TRY(cudaMemcpy(s->d_feeders, s->feeders.data(), sizeof(FeederDev) * n_feeders, cudaMemcpyHostToDevice));
     TRY(dalloc(&s->d_Rpool, (size_t)rp));
+    TRY(dalloc(&s->d_rn2, (size_t)hp));
     TRY(dalloc(&s->d_load, HT));
     TRY(dalloc(&s->d_pest, HT));
     TRY(dalloc(&s->d_psch[0], HT));
@@ -444,6 +453,7 @@ int revs_set_sensitivity(revs_solver* s, int feeder, const double* R_res) {
         CU(cudaMemcpy2D(s->d_Rpool + fd.roff, (size_t)fd.np * sizeof(double), R_res, (size_t)fd.n * sizeof(double),
                         (size_t)fd.n * sizeof(double), fd.n, cudaMemcpyHostToDevice));
     s->sens_set[feeder] = 1;
+    s->rn2_valid = false;
     return REVS_OK;
 }
 
@@ -473,6 +483,7 @@ int revs_set_feeder_tree(revs_solver* s, int feeder, int n_nodes, const int32_t*
     CU(launch_sens_voltage(t.d_parent, t.d_cumr, nullptr, t.d_res_node, fd.n, fd.n, s->d_Rpool + fd.roff, fd.np, s->sU));
     CU(cudaStreamSynchronize(s->sU));
     s->sens_set[feeder] = 1;
+    s->rn2_valid = false;
     return REVS_OK;
 }
 

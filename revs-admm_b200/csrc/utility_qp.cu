@@ -26,6 +26,7 @@ constexpr int kQpThreads = 256;
 constexpr int kJT = 32;                  // columns of R per Hessian tile
 constexpr int kHld = kWMax + 1;          // leading dim of H in shared memory
 constexpr int kTld = kJT + 1;
+constexpr double kArcMin = 9.5367431640625e-07;   // 2^-20, shortest arc-search step
 
 
 struct QpSmem {
@@ -142,6 +143,7 @@ __global__ void __launch_bounds__(kQpThreads, 1) utility_qp_kernel(QpParams P) {
     double* g = P.g_t + col;
     const double* v = P.v_t + col;
     const double u = P.u, tol = P.tol;
+    const double* rn2 = P.rn2 + fd.off;
 
     // ------------------------------------------------------------ working set
     int m = 0;
@@ -239,6 +241,7 @@ __global__ void __launch_bounds__(kQpThreads, 1) utility_qp_kernel(QpParams P) {
 
     // ------------------------------------------------------------ restricted projected Newton
     double phi = eval_phi(R, ld, n, z, S.idx, S.lam, m, u, g, S);
+    double tau = 1.0;
     int ok = 0, its = 0;
     for (; its < P.inner_max; ++its) {
         __syncthreads();
@@ -259,85 +262,89 @@ __global__ void __launch_bounds__(kQpThreads, 1) utility_qp_kernel(QpParams P) {
         const double kkt = block_max(kk, S);
         if (kkt < tol) { ok = 1; break; }
 
-        // free rows (not pinned at zero with a positive gradient)
+        // free rows; rows pinned at (almost) zero with a positive gradient go to exactly 0
         const double eps = fmin(1e-8, kkt);
         if (tid == 0) {
             int k = 0;
+            double sc = 0.0;
             for (int a = 0; a < m; ++a) {
                 bool bound = (S.lam[a] <= eps) && (S.grad[a] > 0.0);
-                S.dir[a] = 0.0;
-                if (!bound) S.fl[k++] = a;
+                S.dir[a] = -S.lam[a];
+                if (!bound) { S.fl[k++] = a; sc += rn2[S.idx[a]]; }
             }
             S.ibcast[1] = k;
+            S.bcast[0] = k ? sc / (double)k : 0.0;
         }
         __syncthreads();
         const int mf = S.ibcast[1];
-        if (mf == 0) { ok = 1; break; }         // cannot happen with kkt>=tol; defensive
+        const double scale = S.bcast[0];    // mean |R_a|^2 of the free rows: curvature scale
 
-        // Hessian H = R_{A,F} R_{F,A}, register-blocked over a 16x16 thread grid
-        {
-            const int nb = (mf + 15) >> 4;
-            if (nb <= 1) hessian<1>(R, ld, n, g, mf, S);
-            else if (nb <= 2) hessian<2>(R, ld, n, g, mf, S);
-            else if (nb <= 3) hessian<3>(R, ld, n, g, mf, S);
-            else if (nb <= 4) hessian<4>(R, ld, n, g, mf, S);
-            else if (nb <= 6) hessian<6>(R, ld, n, g, mf, S);
-            else hessian<8>(R, ld, n, g, mf, S);
-            double tr = 0.0;
-            for (int p = tid; p < mf; p += kQpThreads) tr += S.H[p * kHld + p];
-            tr = block_sum(tr, S);
-            const double reg = 1e-10 * tr / (double)mf + 1e-300;
-            for (int p = tid; p < mf; p += kQpThreads) S.H[p * kHld + p] += reg;
-            __syncthreads();
-        }
-
-        // Cholesky H = L L^T (lower, in place)
-        for (int k = 0; k < mf; ++k) {
-            if (tid == 0) S.H[k * kHld + k] = sqrt(fmax(S.H[k * kHld + k], 1e-300));
-            __syncthreads();
-            const double dkk = S.H[k * kHld + k];
-            for (int i = k + 1 + tid; i < mf; i += kQpThreads) S.H[i * kHld + k] /= dkk;
-            __syncthreads();
-            const int cnt = mf - k - 1;
-            for (int e = tid; e < cnt * cnt; e += kQpThreads) {
-                int i = k + 1 + e / cnt, j = k + 1 + e % cnt;
-                if (j <= i) S.H[i * kHld + j] = fma(-S.H[i * kHld + k], S.H[j * kHld + k], S.H[i * kHld + j]);
-            }
-            __syncthreads();
-        }
-        // solve L y = -grad_A ; L^T d = y   (trial[] is scratch for y)
-        for (int p = tid; p < mf; p += kQpThreads) S.trial[p] = -S.grad[S.fl[p]];
-        __syncthreads();
-        for (int k = 0; k < mf; ++k) {
-            if (tid == 0) S.trial[k] /= S.H[k * kHld + k];
-            __syncthreads();
-            const double yk = S.trial[k];
-            for (int i = k + 1 + tid; i < mf; i += kQpThreads) S.trial[i] = fma(-S.H[i * kHld + k], yk, S.trial[i]);
-            __syncthreads();
-        }
-        for (int k = mf - 1; k >= 0; --k) {
-            if (tid == 0) S.trial[k] /= S.H[k * kHld + k];
-            __syncthreads();
-            const double xk = S.trial[k];
-            for (int i = tid; i < k; i += kQpThreads) S.trial[i] = fma(-S.H[k * kHld + i], xk, S.trial[i]);
-            __syncthreads();
-        }
-        for (int p = tid; p < mf; p += kQpThreads) S.dir[S.fl[p]] = S.trial[p];
-        __syncthreads();
-
-        // Armijo search along the projection arc
         double alpha = 1.0, phin = phi;
-        for (;;) {
-            for (int a = tid; a < m; a += kQpThreads) S.trial[a] = fmax(fma(alpha, S.dir[a], S.lam[a]), 0.0);
-            __syncthreads();
-            double sl = 0.0;
-            for (int a = tid; a < m; a += kQpThreads) sl = fma(S.grad[a], S.trial[a] - S.lam[a], sl);
-            const double slope = block_sum(sl, S);
-            phin = eval_phi(R, ld, n, z, S.idx, S.trial, m, u, nullptr, S);
-            // + rounding noise of phi itself, see oracle/revs_oracle.py:project_voltage
-            if (phin <= phi + 1e-4 * slope + 1e-14 * fabs(phi) || alpha < 1e-12) break;
-            alpha *= 0.5;
+        for (;;) {   // Levenberg-Marquardt safeguard: raise the shift until the arc search succeeds
+            if (mf > 0) {
+                // Hessian H = R_{A,F} R_{F,A}, register-blocked over a 16x16 thread grid
+                const int nb = (mf + 15) >> 4;
+                if (nb <= 1) hessian<1>(R, ld, n, g, mf, S);
+                else if (nb <= 2) hessian<2>(R, ld, n, g, mf, S);
+                else if (nb <= 3) hessian<3>(R, ld, n, g, mf, S);
+                else if (nb <= 4) hessian<4>(R, ld, n, g, mf, S);
+                else if (nb <= 6) hessian<6>(R, ld, n, g, mf, S);
+                else hessian<8>(R, ld, n, g, mf, S);
+                const double reg = 1e-10 * tau * scale + 1e-300;
+                for (int p = tid; p < mf; p += kQpThreads) S.H[p * kHld + p] += reg;
+                __syncthreads();
+
+                // Cholesky H = L L^T (lower, in place)
+                for (int k = 0; k < mf; ++k) {
+                    if (tid == 0) S.H[k * kHld + k] = sqrt(fmax(S.H[k * kHld + k], 1e-300));
+                    __syncthreads();
+                    const double dkk = S.H[k * kHld + k];
+                    for (int i = k + 1 + tid; i < mf; i += kQpThreads) S.H[i * kHld + k] /= dkk;
+                    __syncthreads();
+                    const int cnt = mf - k - 1;
+                    for (int e = tid; e < cnt * cnt; e += kQpThreads) {
+                        int i = k + 1 + e / cnt, j = k + 1 + e % cnt;
+                        if (j <= i) S.H[i * kHld + j] = fma(-S.H[i * kHld + k], S.H[j * kHld + k], S.H[i * kHld + j]);
+                    }
+                    __syncthreads();
+                }
+                // solve L y = -grad_A ; L^T d = y   (trial[] is scratch for y)
+                for (int p = tid; p < mf; p += kQpThreads) S.trial[p] = -S.grad[S.fl[p]];
+                __syncthreads();
+                for (int k = 0; k < mf; ++k) {
+                    if (tid == 0) S.trial[k] /= S.H[k * kHld + k];
+                    __syncthreads();
+                    const double yk = S.trial[k];
+                    for (int i = k + 1 + tid; i < mf; i += kQpThreads) S.trial[i] = fma(-S.H[i * kHld + k], yk, S.trial[i]);
+                    __syncthreads();
+                }
+                for (int k = mf - 1; k >= 0; --k) {
+                    if (tid == 0) S.trial[k] /= S.H[k * kHld + k];
+                    __syncthreads();
+                    const double xk = S.trial[k];
+                    for (int i = tid; i < k; i += kQpThreads) S.trial[i] = fma(-S.H[k * kHld + i], xk, S.trial[i]);
+                    __syncthreads();
+                }
+                for (int p = tid; p < mf; p += kQpThreads) S.dir[S.fl[p]] = S.trial[p];
+                __syncthreads();
+            }
+
+            // Armijo search along the projection arc
+            bool found = false;
+            for (alpha = 1.0; alpha >= kArcMin; alpha *= 0.5) {
+                for (int a = tid; a < m; a += kQpThreads) S.trial[a] = fmax(fma(alpha, S.dir[a], S.lam[a]), 0.0);
+                __syncthreads();
+                double sl = 0.0;
+                for (int a = tid; a < m; a += kQpThreads) sl = fma(S.grad[a], S.trial[a] - S.lam[a], sl);
+                const double slope = block_sum(sl, S);
+                phin = eval_phi(R, ld, n, z, S.idx, S.trial, m, u, nullptr, S);
+                // + rounding noise of phi itself, see oracle/revs_oracle.py:project_voltage
+                if (phin <= phi + 1e-4 * slope + 1e-14 * fabs(phi)) { found = true; break; }
+            }
+            if (found || tau > 1e40 || mf == 0) break;
+            tau *= 1e3;
         }
+        if (alpha == 1.0) tau = fmax(1.0, tau / 10.0);
         __syncthreads();
         for (int a = tid; a < m; a += kQpThreads) S.lam[a] = S.trial[a];
         __syncthreads();

@@ -1,0 +1,102 @@
+"""Host-side logic and the C-ABI surface, no GPU needed."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import INPUT, ROOT
+
+
+def test_cabi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "revs_admm.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(revs_[a-z_0-9]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    lib_path = os.path.join(ROOT, "revs-admm_b200", "librevs_admm.so")
+    if not os.path.exists(lib_path):
+        import __graft_entry__ as g
+        g.build()
+    lib = ctypes.CDLL(lib_path)
+    for name in declared:
+        assert hasattr(lib, name), name
+    from revs_admm_b200 import _cabi
+    assert declared == set(_cabi.SIGNATURES)
+
+
+def test_no_cpu_fallback_without_gpu():
+    import revs_admm_b200 as r
+    try:
+        n = r.device_count()
+    except r.RevsError:
+        n = 0
+    if n > 0:
+        pytest.skip("a GPU is visible")
+    with pytest.raises(r.RevsError):
+        r.Solver([4], 24)
+    with pytest.raises(r.RevsError):
+        r.contract(np.eye(4), np.eye(4))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "revs-admm_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "revs_oracle" not in txt.replace("oracle/revs_oracle.py", ""), f
+
+
+def test_extract_formats(tmp_path):
+    from revs_admm_b200 import extract
+    tariff = extract.GetTariff(INPUT, "DVP", 6)
+    assert len(tariff) == 24 and tariff[0] == 0.095111 and tariff[9] == 0.214357
+    com = extract.GetCommunity(f"{INPUT}/121144-com.txt", 2)
+    assert len(com) == 297
+    homes = extract.GetHomeLoad(INPUT, 121, 6)
+    assert len(homes) == 1126 and all(len(v) == 24 for v in homes.values())
+    g = extract.GetDistNet(INPUT, 121144)
+    assert g.number_of_nodes() == 1692 and g.number_of_edges() == 1691
+    with pytest.raises(ValueError):
+        extract.GetTariff(INPUT, "nope", 6)
+    hp = extract.get_homes_ev_param(homes, g, com[:3], 4.8, 20, 0.2, 11, 23)
+    assert hp[com[0]]["EV"] == dict(rating=4.8, capacity=20.0, initial=0.2, start=11, end=23)
+    assert sum(bool(v["EV"]) for v in hp.values()) == 3
+    # result file round trip
+    P = {h: np.arange(24.0) + h % 7 for h in com[:5]}
+    E = {h: np.zeros(24) for h in com[:3]}
+    S = {h: np.linspace(0.2, 0.92, 25) for h in com[:3]}
+    diff = {1: {h: 0.5 for h in com[:3]}, 2: {h: 0.25 for h in com[:3]}}
+    path = tmp_path / "r.txt"
+    path.write_text(extract.combine_result(P, E, S, com[:3], diff))
+    back = extract.read_result(str(path))
+    assert list(back) == ["Residence Usage Profile", "EV Charger Usage Profile",
+                          "EV Charger State of Charge Profile", "EV Convergence over Iterations"]
+    assert np.array_equal(back["Residence Usage Profile"][com[4]], P[com[4]])
+    assert np.array_equal(back["EV Convergence over Iterations"][com[0]], [0.5, 0.25])
+
+
+def test_tree_from_graph_and_synthetic():
+    from revs_admm_b200 import extract
+    from revs_admm_b200.feeder import synthetic_feeder, synthetic_homes, synthetic_tariff, tree_from_graph
+    g = extract.GetDistNet(INPUT, 121144)
+    t = tree_from_graph(g)
+    assert t.n_nodes == 1691 and t.n_res == 1126
+    assert (t.parent < np.arange(t.n_nodes)).all() and (t.parent >= -1).all()
+    assert (t.parent == -1).sum() == 5            # five feeder lines leave the substation
+    s = synthetic_feeder(1000, seed=3)
+    assert s.n_res == 1000 and (s.parent < np.arange(s.n_nodes)).all()
+    hm = synthetic_homes(1000, 96, seed=3)
+    assert hm["load"].shape == (1000, 96) and hm["load"].min() > 0
+    assert 0.85 < hm["has_ev"].mean() < 0.95
+    assert len(synthetic_tariff(96)) == 96 and len(synthetic_tariff(24)) == 24
+
+
+def test_revs_fixture_interface(case121144):
+    fx = case121144["fx"]
+    assert fx.com == 2 and fx.optim == "distributed"
+    assert fx.out_dir.endswith("121144-com2/distributed")
+    assert len(case121144["saved"]["ev_homes"]) == 267
+    with pytest.raises(NotImplementedError):
+        fx.get_centralized_optimal(case121144["tariff"], case121144["homes"], case121144["dist"])
