@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""REVS ADMM benchmark (driver contract: one JSON line on stdout from rank 0).
+
+A "step" is one complete distributed-ADMM schedule (reference: lpsolver.solve_ADMM,
+max_iterations = 15 as in revs_config.yaml) of this rank's synthetic home population:
+weak scaling, 125k homes x 96 quarter-hour steps per GPU in feeders of 1000 residences
+(8 GPUs = the 1M-home target of BASELINE.json).  metric = home-hours scheduled per second
+(homes x 24 h of horizon / time of the whole schedule, all ranks).
+
+  value : device-resident inputs, timed with CUDA events on the library's own stream
+  e2e   : the C-ABI call sequence a reference user makes, HOST buffers in, HOST results out
+          (set_feeder_tree, set_homes, set_tariff, solve_admm, get_results) inside the
+          timed region
+  roofline / kernels : per-kernel achieved rates from the library's CUDA-event spans
+  cpu_baseline : the CPU oracle (a port of the reference: Gurobi is not installable) on a
+          bounded sample of the same workload, host cores of this box, rank 0 / N=1 only
+
+`--impl reference` times that CPU port as the reference arm.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HOURS = 24.0
+WORKLOADS = {
+    # name: (feeders per GPU, homes per feeder, T)
+    "synthetic-multifeeder-125k-homes-per-gpu-x96": (125, 1000, 96),
+    "synthetic-radial-10k-homes-x96": (1, 10000, 96),
+    "synthetic-12x1000-homes-x24": (12, 1000, 24),
+    "tiny": (4, 200, 96),
+}
+ADMM = dict(kappa=5.0, iter_max=15, vset=1.03, vlow=0.95, vhigh=1.05)   # revs_config.yaml / revs_fixture.py:245-249
+
+
+def make_rank_problem(workload, rank):
+    from revs_admm_b200.feeder import synthetic_feeder, synthetic_homes, synthetic_tariff
+    nf, n, T = WORKLOADS[workload]
+    trees = [synthetic_feeder(n, seed=1000 * rank + f, laterals=max(5, n // 100)) for f in range(nf)]
+    hm = synthetic_homes(nf * n, T, seed=77 + rank)
+    return trees, hm, synthetic_tariff(T), [n] * nf, T
+
+
+def pinned_like(a):
+    """Copy into page-locked host memory (torch is only the allocator here)."""
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    return t.numpy(), t
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def fp64_gemm_peak_tflops():
+    """cuBLAS DGEMM on this box: the denominator for the FP64 tensor-core contraction
+    (MEASURED_PEAKS.json has no fp64 figure)."""
+    import torch
+    n = 6144
+    a = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    torch.matmul(a, b)
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+# ------------------------------------------------------------------------------ CPU reference arm
+def cpu_port_sample(workload, budget_homes=None):
+    """One bounded sample of the workload through the CPU oracle: one synthetic feeder of the
+    workload's shape, full horizon, all 15 ADMM iterations.  Returns (home_hours/s, seconds, desc)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import revs_oracle as O
+    from revs_admm_b200.feeder import synthetic_feeder, synthetic_homes, synthetic_tariff
+    nf, n, T = WORKLOADS[workload]
+    n_s = min(n, budget_homes or n)
+    tree = synthetic_feeder(n_s, seed=0, laterals=max(5, n_s // 100))
+    hm = synthetic_homes(n_s, T, seed=77)
+    Rb = [O.rmat_from_tree(tree.parent, tree.r)[np.ix_(tree.res_node, tree.res_node)]]
+    t0 = time.perf_counter()
+    O.solve_ADMM_arrays(Rb, load=hm["load"], cost=synthetic_tariff(T), ev_mask=hm["has_ev"].astype(bool),
+                        rating=hm["rating"], capacity=hm["capacity"], initial=hm["initial"],
+                        start=hm["start"], end=hm["end"], **ADMM)
+    dt = time.perf_counter() - t0
+    return n_s * HOURS / dt, dt, f"1 feeder x {n_s} homes x {T} steps x {ADMM['iter_max']} ADMM iterations (oracle/revs_oracle.py, numpy/BLAS)"
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    vals, secs, desc = [], [], ""
+    for i in range(args.warmup + args.steps):
+        v, dt, desc = cpu_port_sample(args.workload, args.cpu_sample_homes)
+        if i >= args.warmup:
+            vals.append(v)
+            secs.append(dt)
+    value = float(np.mean(vals))
+    nf, n, T = WORKLOADS[args.workload]
+    line = {
+        "impl": "reference", "metric": "home_hours_scheduled_per_sec", "value": value, "unit": "home-hours/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "feeders_per_gpu": nf, "homes_per_feeder": n, "T": T, **ADMM},
+        "cpu_baseline": {"value": value, "unit": "home-hours/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": "home-hours/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference needs gurobipy (absent, not installable offline); this arm times the CPU port of its algorithm",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------ GPU arm
+def run_gpu(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import revs_admm_b200 as R
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    trees, hm, cost, sizes, T = make_rank_problem(args.workload, rank)
+    H = sum(sizes)
+    # page-locked host copies of everything that crosses PCIe in the e2e leg
+    keep = []
+    hm_p = {}
+    for k, v in hm.items():
+        hm_p[k], t = pinned_like(v)
+        keep.append(t)
+    cost_p, t = pinned_like(cost)
+    keep.append(t)
+
+    s = R.Solver(sizes, T, device=local_rank)
+
+    def upload():
+        for f, tr in enumerate(trees):
+            s.set_feeder_tree(f, tr.parent, tr.r, tr.res_node)
+        s.set_homes(**hm_p)
+        s.set_tariff(cost_p)
+
+    upload()
+    stats_acc = {k: 0.0 for k in ("gemm_ms", "home_ms", "dual_ms", "qp_ms", "total_ms", "kernel_launches",
+                                  "gemm_launches", "qp_outer_iterations", "qp_newton_iterations")}
+    # ---- device-resident leg ("value")
+    for _ in range(args.warmup):
+        s.solve_admm(**ADMM)
+    barrier()
+    with ClockSampler(local_rank) as clk:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dev_ms = 0.0
+        for _ in range(args.steps):
+            s.solve_admm(**ADMM)
+            st = s.stats()
+            dev_ms += st["total_ms"]
+            for k in stats_acc:
+                stats_acc[k] += st[k]
+        e1.record()
+        barrier()
+        wall_ms = e0.elapsed_time(e1)
+    ms_step = max_over_ranks(wall_ms / args.steps)
+    total_homes = sum_over_ranks(H)
+    value = total_homes * HOURS / (ms_step * 1e-3)
+    last = s.stats()
+
+    # ---- end-to-end leg: host buffers in, host results out, every step
+    for _ in range(min(args.warmup, 1)):
+        upload(); s.solve_admm(**ADMM); s.results()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        upload()
+        s.solve_admm(**ADMM)
+        out = s.results()
+    torch.cuda.synchronize()
+    e2e_wall = (time.perf_counter() - t0) * 1e3 / args.steps
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(max(e2e_wall, e0.elapsed_time(e1) / args.steps))
+    e2e_value = total_homes * HOURS / (e2e_ms * 1e-3)
+    h2d = sum(v.nbytes for v in hm_p.values()) + cost_p.nbytes + sum(tr.parent.nbytes + tr.r.nbytes + tr.res_node.nbytes for tr in trees)
+    d2h = sum(v.nbytes for v in out.values() if v is not None)
+
+    # ---- per-kernel achieved rates (CUDA-event spans inside the library, timed region only)
+    hbm_peak, peak_src = measured_peaks()
+    iters = ADMM["iter_max"] * args.steps
+    ev_frac = float(hm["has_ev"].mean())
+    n_p = [(n + 15) // 16 * 16 for n in sizes]
+    Hp = sum(n_p)
+    home_bytes = Hp * T * (ev_frac * 48 + (1 - ev_frac) * 24)          # per launch, DESIGN.md kernel table
+    dual_bytes = Hp * T * 56
+    gemm_flops = sum(2.0 * n * n * T for n in n_p)
+    gemm_bytes = sum(8.0 * n * n + 16.0 * n * T for n in n_p)
+    kernels = {}
+    if stats_acc["home_ms"] > 0:
+        ms = stats_acc["home_ms"] / iters
+        kernels["home_solve"] = {"bound": "hbm", "ms_per_launch": ms, "achieved": home_bytes / (ms * 1e-3) / 1e9,
+                                 "peak": hbm_peak, "unit": "GB/s"}
+    if stats_acc["dual_ms"] > 0:
+        ms = stats_acc["dual_ms"] / iters
+        kernels["dual_update"] = {"bound": "hbm", "ms_per_launch": ms, "achieved": dual_bytes / (ms * 1e-3) / 1e9,
+                                  "peak": hbm_peak, "unit": "GB/s"}
+    f64_peak = fp64_gemm_peak_tflops() if rank == 0 else 0.0
+    if stats_acc["gemm_launches"] > 0:
+        ms = stats_acc["gemm_ms"] / stats_acc["gemm_launches"]
+        kernels["contract_f64"] = {"bound": "tensor", "ms_per_launch": ms, "achieved": gemm_flops / (ms * 1e-3) / 1e12,
+                                   "peak": f64_peak, "unit": "TFLOP/s", "hbm_gbs": gemm_bytes / (ms * 1e-3) / 1e9,
+                                   "peak_source": "cuBLAS DGEMM 6144^3 measured in this run"}
+    if stats_acc["qp_ms"] > 0:
+        kernels["utility_qp"] = {"bound": "latency/fp64", "ms_total": stats_acc["qp_ms"] / args.steps,
+                                 "launches_per_step": (stats_acc["gemm_launches"] / args.steps) + ADMM["iter_max"]}
+    for k in kernels.values():
+        if "peak" in k and k["peak"]:
+            k["frac"] = k["achieved"] / k["peak"]
+    share = {k: stats_acc[k] / max(stats_acc["total_ms"], 1e-9) for k in ("gemm_ms", "home_ms", "dual_ms", "qp_ms")}
+    dominant = max(share, key=share.get)
+    dom_name = {"gemm_ms": "contract_f64", "home_ms": "home_solve", "dual_ms": "dual_update", "qp_ms": "utility_qp"}[dominant]
+    # the roofline object: the contraction is the kernel whose bound is a hardware peak of the
+    # step's arithmetic (the QP kernel's time is reported beside it in `kernels`/`share`)
+    roof_k = kernels.get("contract_f64") if dom_name in ("utility_qp", "contract_f64") else kernels.get(dom_name)
+    roofline = None
+    if roof_k:
+        roofline = {"kernel": "contract_f64" if dom_name in ("utility_qp", "contract_f64") else dom_name,
+                    "bound": roof_k["bound"], "achieved": roof_k["achieved"], "peak": roof_k["peak"],
+                    "unit": roof_k["unit"], "frac": roof_k.get("frac"), "traffic": None,
+                    "peak_source": roof_k.get("peak_source", peak_src)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, dt, desc = cpu_port_sample(args.workload, args.cpu_sample_homes)
+        cpu = {"value": v, "unit": "home-hours/s", "cores": os.cpu_count() or 1, "kind": "port", "sample": desc,
+               "seconds": dt}
+
+    if rank == 0:
+        nf, n, _ = WORKLOADS[args.workload]
+        line = {
+            "metric": "home_hours_scheduled_per_sec", "value": value, "unit": "home-hours/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "feeders_per_gpu": nf, "homes_per_feeder": n, "T": T,
+                       "homes_total": int(total_homes), **ADMM,
+                       "l2": "working set per solve > L2 (sensitivity blocks %.2f GB per GPU)" % (sum(8.0 * x * x for x in n_p) / 1e9)},
+            "admm_iters_per_sec": ADMM["iter_max"] / (ms_step * 1e-3),
+            "home_steps_per_sec": total_homes * T / (ms_step * 1e-3),
+            "device_ms_per_step": dev_ms / args.steps,
+            "e2e": {"value": e2e_value, "unit": "home-hours/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(stats_acc["kernel_launches"]),
+            "roofline": roofline, "kernels": kernels, "share_of_device_time": share, "dominant_kernel": dom_name,
+            "qp": {"outer_rounds_per_step": stats_acc["qp_outer_iterations"] / args.steps,
+                   "newton_steps_per_step": stats_acc["qp_newton_iterations"] / args.steps,
+                   "max_working_set": last["max_working_set"]},
+            "residuals": {"primal": last["primal_residual"], "dual": last["dual_residual"]},
+            "clocks": clk.summary(), "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    s.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
+    ap.add_argument("--workload", default="synthetic-multifeeder-125k-homes-per-gpu-x96", choices=list(WORKLOADS))
+    ap.add_argument("--cpu-sample-homes", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_gpu(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()
