@@ -57,7 +57,8 @@ typedef struct revs_stats {
     float gemm_ms;                /* device time in sensitivity contractions (events)   */
     float home_ms;                /* device time in the batched home solve              */
     float dual_ms;                /* device time in the fused dual/residual kernel      */
-    float qp_ms;                  /* device time in the per-column QP kernels           */
+    float qp_ms;                  /* device time in the per-column QP kernels (both)    */
+    float qp_big_ms;              /* ... of which the |W|>32 instantiation              */
     float total_ms;               /* device time of the whole solve                     */
 } revs_stats;
 

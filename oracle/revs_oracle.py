@@ -31,8 +31,10 @@ exact methods:
 * Utility QP.  Separable over t; for each t it is the Euclidean projection of
   ``z = (P_est+P_sch)/2 - Gamma/kappa`` onto ``{g>=0, R g <= vhigh^2-vset^2}`` (Gurobi
   variables default to lb=0; the ``>= vlow`` row is vacuous for g>=0, R>=0, vlow<vset
-  and is asserted so).  Solved by a projected Newton method on the dual with the
-  exact generalised Hessian and an Armijo arc search; terminates on a KKT residual.
+  and is asserted so).  Solved on the dual (convex, piecewise quadratic): minimise the
+  current quadratic piece exactly over the multipliers (primal-dual active set), line
+  search on the true dual, repeat; safeguarded by a projected-Newton arc step.
+  Terminates on a KKT residual (1e-11), i.e. at the unique QP solution.
 
 PARITY PIN (see tests/test_oracle_golden.py): the reference's own result files
 (tests/golden/ref_out_121144_com2.npz) are reproduced exactly where the reference
@@ -53,7 +55,9 @@ import numpy as np
 SOC_TARGET = 0.9      # lpsolver.py:111  s[T] >= 0.9
 SOC_MAX = 1.0         # lpsolver.py:102  ub = 1.0
 PHI_NOISE = 1e-14     # relative rounding noise admitted by the line search of the utility QP
-ARC_MIN = 2.0 ** -20   # shortest step of the arc search before the Hessian shift is raised
+ARC_MIN = 2.0 ** -20   # shortest step of the line search before falling back / raising the shift
+PDAS_MAX = 40          # active-set guesses per quadratic piece before falling back
+HESS_SHIFT = 1e-12     # relative diagonal shift of the model Hessian (keeps it positive definite)
 COUNT_TOL = 1e-9      # slack on the SOC count window (Gurobi's own FeasibilityTol is 1e-6)
 
 
@@ -181,16 +185,39 @@ def solve_residence_arrays(tariff, load, ev):
 
 
 # --------------------------------------------------------------------------- utility step
-def project_voltage(z, R, u, lam0=None, tol=1e-11, maxit=500, rn2=None):
+def bound_qp_pdas(H, c, x0, maxit=PDAS_MAX):
+    """min 1/2 (x-x0)^T H (x-x0) + c^T (x-x0)  s.t. x >= 0  by the primal-dual active set
+    method: guess the positive set A, solve H_AA x_A = (H x0 - c)_A, x_I = 0, move the rows
+    with x<=0 out and the rows with a negative multiplier in, repeat.  Returns (x, True) at
+    a KKT point, (None, False) if the guesses cycle (the caller then takes a safeguarded
+    Newton step instead)."""
+    m = len(c)
+    b = H @ x0 - c
+    A = (x0 > 0) | (c < 0)
+    for _ in range(maxit):
+        x = np.zeros(m)
+        if A.any():
+            x[A] = np.linalg.solve(H[np.ix_(A, A)], b[A])
+        mu = H @ x - b                       # model gradient; must be >= 0 off A
+        bad_in = A & (x <= 0)
+        bad_out = (~A) & (mu < 0)
+        if not bad_in.any() and not bad_out.any():
+            return x, True
+        A = (A & ~bad_in) | bad_out
+    return None, False
+
+
+def project_voltage(z, R, u, lam0=None, tol=1e-11, maxit=200, rn2=None):
     """argmin 1/2||g-z||^2  s.t. g>=0, R g <= u   (one time step of class Utility).
 
-    Dual: minimise phi(lam) = 1/2||[z - R lam]_+||^2 + u*sum(lam) over lam>=0, by
-    projected Newton (free set = not {lam~0 and gradient>0}; Hessian R_AF R_FA over the
-    homes F with g>0) with an Armijo search along the projection arc.  The Hessian is
-    shifted by mu = 1e-10*tau*mean(|R_a|^2); tau grows (x1e3) whenever the arc search
-    finds no acceptable step (the Hessian is singular or zero where many homes sit at
-    g=0) and relaxes (/10) after full steps -- a Levenberg-Marquardt safeguard that
-    leaves the fixed point untouched.  Returns (g, lam, iterations)."""
+    Dual: minimise phi(lam) = 1/2||[z - R lam]_+||^2 + u*sum(lam) over lam >= 0 (convex,
+    piecewise quadratic; the pieces are the sets F of homes with g>0).  Each iteration
+    takes the quadratic piece at the current point on the working rows W = {lam>0} u
+    {violated rows}, H = R_WF R_FW, minimises it EXACTLY over lam_W >= 0 (bound_qp_pdas)
+    and searches phi along the segment to that minimiser (both ends feasible, no
+    projection).  If the active-set guesses cycle, the step is the projected-Newton arc
+    step with a Levenberg-Marquardt shift instead (globally convergent on its own).
+    Terminates on the KKT residual.  Returns (g, lam, iterations)."""
     n = len(z)
     lam = np.zeros(n) if lam0 is None else np.maximum(lam0, 0.0)
     if rn2 is None:
@@ -207,33 +234,52 @@ def project_voltage(z, R, u, lam0=None, tol=1e-11, maxit=500, rn2=None):
         kkt = np.max(np.abs(np.where(lam > 0, grad, np.minimum(grad, 0.0))))
         if kkt < tol:
             return g, lam, it
-        eps = min(1e-8, kkt)
-        free = ~((lam <= eps) & (grad > 0))
+        W = (lam > 0) | (grad < 0)
         F = g > 0
-        RAF = R[np.ix_(free, F)]
-        H0 = RAF @ RAF.T
-        scale = rn2[free].mean()
-        while True:
-            H = H0.copy()
-            H[np.diag_indices_from(H)] += 1e-10 * tau * scale + 1e-300
-            d = -lam                      # pinned rows (tiny lam, gradient > 0) go to exactly 0
-            d[free] = -np.linalg.solve(H, grad[free])
-            a, found = 1.0, False
+        RWF = R[np.ix_(W, F)]
+        H0 = RWF @ RWF.T
+        scale = rn2[W].mean()
+        H = H0.copy()
+        H[np.diag_indices_from(H)] += HESS_SHIFT * scale + 1e-300
+        x, ok = bound_qp_pdas(H, grad[W], lam[W])
+        if ok:
+            d = np.zeros(n)
+            d[W] = x - lam[W]
+            slope = grad @ d
+            a = 1.0
             while a >= ARC_MIN:
-                ln = np.maximum(lam + a * d, 0.0)
+                ln = np.maximum(lam + a * d, 0.0)        # max() only strips rounding
                 fn, gn = phi(ln)
-                # the last term is the rounding noise of phi itself: close to the solution
-                # the predicted decrease (~kkt^2) drops below it and a plain Armijo test
-                # would reject the (correct) full Newton step
-                if fn <= f + 1e-4 * grad @ (ln - lam) + PHI_NOISE * abs(f):
-                    found = True
+                # PHI_NOISE: rounding noise of phi itself; close to the solution the
+                # predicted decrease (~kkt^2) drops below it
+                if fn <= f + 1e-4 * a * slope + PHI_NOISE * abs(f):
                     break
                 a *= 0.5
-            if found or tau > 1e40:
-                break
-            tau *= 1e3
-        if a == 1.0:
-            tau = max(1.0, tau / 10.0)
+            else:
+                ok = False
+        if not ok:   # safeguarded projected-Newton arc step on the same rows
+            eps = min(1e-8, kkt)
+            free = W & ~((lam <= eps) & (grad > 0))
+            fw = free[W]
+            while True:
+                Hf = H0[np.ix_(fw, fw)].copy()
+                Hf[np.diag_indices_from(Hf)] += HESS_SHIFT * tau * scale + 1e-300
+                d = -lam
+                d[free] = -np.linalg.solve(Hf, grad[free])
+                d[~W] = 0.0
+                a, found = 1.0, False
+                while a >= ARC_MIN:
+                    ln = np.maximum(lam + a * d, 0.0)
+                    fn, gn = phi(ln)
+                    if fn <= f + 1e-4 * grad @ (ln - lam) + PHI_NOISE * abs(f):
+                        found = True
+                        break
+                    a *= 0.5
+                if found or tau > 1e40:
+                    break
+                tau *= 1e3
+            if a == 1.0:
+                tau = max(1.0, tau / 10.0)
         lam, f, g = ln, fn, gn
     raise RuntimeError("utility QP did not converge (kkt=%g)" % kkt)
 

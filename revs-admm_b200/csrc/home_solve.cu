@@ -5,8 +5,9 @@
 // objective is separable and linear in e, and the SOC rows collapse to a window on the
 // number of charging hours, so the exact optimum is a selection: the n_min cheapest
 // hours of the plug-in window, then further hours while their cost is negative (up to
-// n_max); ties go to the earliest hour.  Lanes hold the hours (t = lane + 32 j); the rank
-// of every hour is found with warp shuffles, no sort and no shared memory.
+// n_max); ties go to the earliest hour.  Lanes hold the hours (t = lane + 32 j); hours are
+// picked with warp-shuffle arg-min rounds (or a full shuffle ranking when many hours are
+// needed), no sort and no shared memory.
 //
 // The hour cost is evaluated with individually rounded operations (__dmul_rn/__dadd_rn)
 // in the order oracle/revs_oracle.py:home_delta uses, so that the selection is
@@ -18,6 +19,7 @@
 namespace revs {
 
 constexpr int kMaxSlots = 8;   // hours per lane -> T <= 256
+constexpr int kSelectRounds = 24;   // up to this many charging hours: iterative arg-min, else full ranking
 
 
 template <int SLOTS>
@@ -69,22 +71,6 @@ __global__ void __launch_bounds__(256) home_solve_kernel(HomeParams P) {
         d[j] = v;
     }
 
-    // rank[j] = #{hours s : d_s < d_t  or (d_s == d_t and s < t)}
-    int rank[SLOTS];
-#pragma unroll
-    for (int j = 0; j < SLOTS; ++j) rank[j] = 0;
-#pragma unroll
-    for (int js = 0; js < SLOTS; ++js) {
-        for (int src = 0; src < 32; ++src) {
-            double o = __shfl_sync(0xffffffffu, d[js], src);
-            int s = src + 32 * js;
-#pragma unroll
-            for (int j = 0; j < SLOTS; ++j) {
-                int t = lane + 32 * j;
-                rank[j] += (o < d[j]) || (o == d[j] && s < t);
-            }
-        }
-    }
     int in_window = 0;
 #pragma unroll
     for (int j = 0; j < SLOTS; ++j) in_window += (d[j] < CUDART_INF) ? 1 : 0;
@@ -93,12 +79,57 @@ __global__ void __launch_bounds__(256) home_solve_kernel(HomeParams P) {
     if (nmin > nmax || nmin > in_window) {
         if (lane == 0) atomicExch(P.infeasible, 1);
     }
+
+    bool on[SLOTS];
+#pragma unroll
+    for (int j = 0; j < SLOTS; ++j) on[j] = false;
+    if (nmax <= kSelectRounds) {
+        // few charging hours (the usual case): pull the cheapest remaining hour out of the
+        // warp nmax times -- (cost, hour) lexicographic arg-min over 5 shuffle steps
+        for (int cnt = 0; cnt < nmax; ++cnt) {
+            double best = CUDART_INF;
+            int bt = 0x7fffffff;
+#pragma unroll
+            for (int j = 0; j < SLOTS; ++j)
+                if (!on[j] && d[j] < best) { best = d[j]; bt = lane + 32 * j; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int ot = __shfl_xor_sync(0xffffffffu, bt, o);
+                if (ob < best || (ob == best && ot < bt)) { best = ob; bt = ot; }
+            }
+            if (!(best < CUDART_INF)) break;                 // window exhausted
+            if (cnt >= nmin && !(best < 0.0)) break;         // optional hours only while they pay
+#pragma unroll
+            for (int j = 0; j < SLOTS; ++j)
+                if (bt == lane + 32 * j) on[j] = true;
+        }
+    } else {
+        // rank[j] = #{hours s : d_s < d_t  or (d_s == d_t and s < t)}
+        int rank[SLOTS];
+#pragma unroll
+        for (int j = 0; j < SLOTS; ++j) rank[j] = 0;
+#pragma unroll
+        for (int js = 0; js < SLOTS; ++js) {
+            for (int src = 0; src < 32; ++src) {
+                double o = __shfl_sync(0xffffffffu, d[js], src);
+                int s = src + 32 * js;
+#pragma unroll
+                for (int j = 0; j < SLOTS; ++j) {
+                    int t = lane + 32 * j;
+                    rank[j] += (o < d[j]) || (o == d[j] && s < t);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < SLOTS; ++j)
+            on[j] = d[j] < CUDART_INF && (rank[j] < nmin || (rank[j] < nmax && d[j] < 0.0));
+    }
 #pragma unroll
     for (int j = 0; j < SLOTS; ++j) {
         int t = lane + 32 * j;
         if (t >= P.T) continue;
-        bool on = d[j] < CUDART_INF && (rank[j] < nmin || (rank[j] < nmax && d[j] < 0.0));
-        double p = on ? rate : 0.0;
+        double p = on[j] ? rate : 0.0;
         P.p_ev[base + t] = p;
         P.p_sch_new[base + t] = __dadd_rn(ld[j], p);
     }

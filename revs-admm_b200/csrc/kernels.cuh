@@ -72,6 +72,9 @@ struct QpParams {
     unsigned long long* newton_its;
     int* max_ws;
     int* n_failed;         // columns whose working set overflowed kWMax
+    int* cls;              // [ncols] instantiation that owns the column (see qp_class_cap)
+    int* n_cls;            // [kQpClasses] running columns per class after this round
+    unsigned long long* dbg;  // optional [4]: arc evaluations, LM retries, max Newton steps, max evaluations
     int T;
     int64_t Hp;
     double u, tol;
@@ -79,7 +82,7 @@ struct QpParams {
     int inner_max;
 };
 
-cudaError_t launch_utility_qp(const QpParams& P, int ncols, cudaStream_t stream);
+cudaError_t launch_utility_qp(const QpParams& P, int ncols, int cls, cudaStream_t stream);
 
 // ---- contract_f64.cu
 int contract_tile_rows(int T);

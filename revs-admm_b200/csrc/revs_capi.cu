@@ -14,6 +14,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <cmath>
 #include <string>
 #include <vector>
@@ -53,11 +54,13 @@ constexpr int kQpInnerMax = 60;      // Newton steps per launch
 constexpr int kQpRoundMax = 400;     // working-set rounds per utility solve
 
 struct Counters {
-    int n_running;
+    int n_running;   // n_running and n_cls are reset together before every working-set round
+    int n_cls[kQpClasses];
     int n_failed;
     int infeasible;
     int max_ws;
     unsigned long long newton_its;
+    unsigned long long dbg[4];
     ResidualOut res;
 };
 
@@ -94,7 +97,7 @@ struct revs_solver {
     double* d_cost = nullptr;
     // time-major [T][Hp]
     double *d_zt = nullptr, *d_lamt = nullptr, *d_gt = nullptr, *d_vt = nullptr;
-    int *d_wcount = nullptr, *d_widx = nullptr, *d_status = nullptr, *d_innerok = nullptr;
+    int *d_wcount = nullptr, *d_widx = nullptr, *d_status = nullptr, *d_innerok = nullptr, *d_cls = nullptr;
     Counters* d_cnt = nullptr;
     Counters* h_cnt = nullptr;           // pinned mirror
     double* d_diff = nullptr;
@@ -163,6 +166,7 @@ void spans_collect(revs_solver* s) {   // after the streams are synchronised
             case 1: s->stats.home_ms += ms; break;
             case 2: s->stats.dual_ms += ms; break;
             case 3: s->stats.qp_ms += ms; break;
+            case 4: s->stats.qp_ms += ms; s->stats.qp_big_ms += ms; break;
         }
     }
     s->span_used = 0;
@@ -235,6 +239,9 @@ int utility_solve(revs_solver* s) {
     Q.newton_its = &s->d_cnt->newton_its;
     Q.max_ws = &s->d_cnt->max_ws;
     Q.n_failed = &s->d_cnt->n_failed;
+    Q.cls = s->d_cls;
+    Q.n_cls = s->d_cnt->n_cls;
+    Q.dbg = getenv("REVS_DEBUG") ? s->d_cnt->dbg : nullptr;
     Q.T = s->T;
     Q.Hp = s->Hp;
     Q.u = s->vhigh * s->vhigh - s->vset * s->vset;
@@ -242,10 +249,15 @@ int utility_solve(revs_solver* s) {
     Q.inner_max = kQpInnerMax;
 
     Q.init = 1;
-    TimedSpan* sp = span_begin(s, 3, s->sU);
-    CU(launch_utility_qp(Q, s->ncols, s->sU));
-    span_end(sp, s->sU);
-    s->stats.kernel_launches++;
+    TimedSpan* sp = nullptr;
+    bool use[kQpClasses];
+    for (int cl = 0; cl < kQpClasses; ++cl) {     // every class once: the first one classifies
+        sp = span_begin(s, cl == 0 ? 3 : 4, s->sU);
+        CU(launch_utility_qp(Q, s->ncols, cl, s->sU));
+        span_end(sp, s->sU);
+        use[cl] = true;                           // unknown until the first read-back
+    }
+    s->stats.kernel_launches += kQpClasses;
     Q.init = 0;
     for (int round = 0;; ++round) {
         if (round >= kQpRoundMax)
@@ -254,11 +266,15 @@ int utility_solve(revs_solver* s) {
         sp = span_begin(s, 0, s->sU);
         CU(launch_contract(s->d_cprob, s->d_ctiles, s->n_ctiles, s->T, kOutTimeMajor, 0.0, s->sU));
         span_end(sp, s->sU);
-        CU(cudaMemsetAsync(&s->d_cnt->n_running, 0, sizeof(int), s->sU));
-        sp = span_begin(s, 3, s->sU);
-        CU(launch_utility_qp(Q, s->ncols, s->sU));
-        span_end(sp, s->sU);
-        s->stats.kernel_launches += 2;
+        s->stats.kernel_launches++;
+        CU(cudaMemsetAsync(&s->d_cnt->n_running, 0, (1 + kQpClasses) * sizeof(int), s->sU));
+        for (int cl = 0; cl < kQpClasses; ++cl) {
+            if (!use[cl]) continue;
+            sp = span_begin(s, cl == 0 ? 3 : 4, s->sU);
+            CU(launch_utility_qp(Q, s->ncols, cl, s->sU));
+            span_end(sp, s->sU);
+            s->stats.kernel_launches++;
+        }
         s->stats.gemm_launches++;
         s->stats.qp_outer_iterations++;
         CU(cudaMemcpyAsync(s->h_cnt, s->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, s->sU));
@@ -267,7 +283,15 @@ int utility_solve(revs_solver* s) {
             return fail(REVS_ERR_NOCONV,
                         "utility QP: %d (feeder,hour) columns need more than %d simultaneously active "
                         "voltage rows", s->h_cnt->n_failed, kWMax);
+        if (getenv("REVS_DEBUG"))
+            fprintf(stderr, "[revs] admm %d round %d: running %d by class %d/%d/%d pieces_total %llu max_ws %d | phi evals %llu "
+                    "pdas guesses %llu max pieces/launch %llu fallbacks %llu\n",
+                    s->k, round, s->h_cnt->n_running, s->h_cnt->n_cls[0], s->h_cnt->n_cls[1], s->h_cnt->n_cls[2],
+                    s->h_cnt->newton_its, s->h_cnt->max_ws, s->h_cnt->dbg[0], s->h_cnt->dbg[1], s->h_cnt->dbg[2],
+                    s->h_cnt->dbg[3]);
         if (s->h_cnt->n_running == 0) break;
+        use[0] = true;
+        for (int cl = 1; cl < kQpClasses; ++cl) use[cl] = s->h_cnt->n_cls[cl] > 0;
     }
     return REVS_OK;
 }
@@ -301,7 +325,7 @@ void free_all(revs_solver* s) {
     void* ptrs[] = {s->d_feeders, s->d_Rpool, s->d_rn2, s->d_load, s->d_pest, s->d_psch[0], s->d_psch[1], s->d_gamma,
                     s->d_pev, s->d_soc, s->d_has_ev, s->d_rating, s->d_capacity, s->d_initial, s->d_indconst,
                     s->d_start, s->d_end, s->d_nmin, s->d_nmax, s->d_zero_i, s->d_cost, s->d_zt, s->d_lamt,
-                    s->d_gt, s->d_vt, s->d_wcount, s->d_widx, s->d_status, s->d_innerok, s->d_cnt, s->d_diff,
+                    s->d_gt, s->d_vt, s->d_wcount, s->d_widx, s->d_status, s->d_innerok, s->d_cls, s->d_cnt, s->d_diff,
                     s->d_cprob, s->d_ctiles};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -412,6 +436,7 @@ int revs_create(revs_solver** out, int device, int n_feeders, const int64_t* fee
     TRY(dalloc(&s->d_widx, (size_t)s->ncols * kWMax));
     TRY(dalloc(&s->d_status, (size_t)s->ncols));
     TRY(dalloc(&s->d_innerok, (size_t)s->ncols));
+    TRY(dalloc(&s->d_cls, (size_t)s->ncols));
     TRY(dalloc(&s->d_cnt, (size_t)1));
     TRY(cudaHostAlloc((void**)&s->h_cnt, sizeof(Counters), cudaHostAllocDefault));
     memset(s->h_cnt, 0, sizeof(Counters));

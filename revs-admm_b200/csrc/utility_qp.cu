@@ -6,67 +6,105 @@
 // onto { g >= 0,  R g <= u },  u = vhigh^2 - vset^2  (Gurobi's default lb=0; the vlow row
 // is vacuous for g>=0, R>=0, vlow<=vset -- checked on the host).
 //
-// Method (exact, terminates on KKT residuals, same fixed point as the oracle's
-// project_voltage): work on the dual
+// Method (exact, terminates on KKT residuals; same algorithm and fixed point as the
+// oracle's project_voltage): work on the dual
 //     min_{lam>=0}  phi(lam) = 1/2 || [z - R lam]_+ ||^2 + u sum(lam)
-// with a WORKING SET W of voltage rows (only a few tens of the ~10^3 rows of a feeder ever
-// carry a multiplier).  A launch of this kernel
-//   1. reads the voltages  v = R g  of the current iterate, produced for ALL rows and all
+// which is convex and piecewise quadratic, the pieces being the sets F of homes with g>0.
+// Only a few tens of the ~10^3 voltage rows of a feeder ever carry a multiplier, so a column
+// keeps a WORKING SET W of rows.  A launch of this kernel
+//   1. reads the voltages  v = R g  of the stored iterate, produced for ALL rows and all
 //      hours at once by the tensor-core contraction (contract_f64.cu),
-//   2. drops rows whose multiplier is zero, admits the most violated rows (v > u),
-//   3. solves the dual restricted to W by projected Newton: Hessian R_WF R_FW over the
-//      homes F with g>0, Cholesky in shared memory, Armijo search along the projection
-//      arc.  This touches only |W| rows of R (coalesced row reads), never the full block.
+//   2. drops rows whose multiplier is zero and admits the most violated rows (v > u),
+//   3. iterates on W:  assemble the Hessian of the current piece  H = R_WF R_FW  (the only
+//      step that streams rows of R, coalesced); minimise the piece EXACTLY over lam_W >= 0
+//      with a primal-dual active-set loop that lives entirely in shared memory (blocked
+//      Cholesky of H_AA, the sequential part inside one warp); search phi along the segment
+//      to that minimiser.  If the active-set guesses cycle, take a projected-Newton arc step
+//      with a Levenberg-Marquardt shift instead.
 // and the host alternates it with the contraction until no column has a violated row.
+//
+// Three instantiations share the code: |W| <= 32 (128 threads, 19 KB of shared memory,
+// >= 4 CTAs per SM), |W| <= 64 (256 threads, 54 KB, 2 per SM) and |W| <= 128 (256 threads,
+// 175 KB, 1 per SM).  A column carries a class flag; it is classified by the size of its
+// warm-start set and handed to the next class when it outgrows the current one.
 #include "kernels.cuh"
 
 namespace revs {
 
-constexpr int kQpThreads = 256;
 constexpr int kJT = 32;                  // columns of R per Hessian tile
-constexpr int kHld = kWMax + 1;          // leading dim of H in shared memory
 constexpr int kTld = kJT + 1;
-constexpr double kArcMin = 9.5367431640625e-07;   // 2^-20, shortest arc-search step
+constexpr double kArcMin = 9.5367431640625e-07;   // 2^-20, shortest line-search step
+constexpr int kPdasMax = 40;             // active-set guesses per quadratic piece
+constexpr double kHessShift = 1e-12;     // relative diagonal shift of the model Hessian
 
-
+// Shared memory of one column.  Hb holds two things at once: the strict lower triangle of
+// the model Hessian H (row i, column j<i at Hb[i*HLD+j], its diagonal in hdiag) and, in the
+// unused upper part, the Cholesky factor of a principal sub-matrix, L(p,q) (p>=q) at
+// Hb[q*HLD+p+1] -- so the active-set loop can refactor without reassembling H.
+template <int WMAX, int THREADS>
 struct QpSmem {
-    double H[kWMax * kHld];
-    double tileR[kWMax * kTld];
-    double lam[kWMax], trial[kWMax], grad[kWMax], dir[kWMax];
-    double red[kQpThreads / 32];
+    double Hb[WMAX * (WMAX + 1)];
+    double tileR[WMAX * kTld];
+    double hdiag[WMAX];
+    double lam[WMAX], trial[WMAX], grad[WMAX], dir[WMAX], b[WMAX], y[WMAX];
+    double red[3 * (THREADS / 32)];
     double bcast[2];
-    int idx[kWMax], fl[kWMax];
-    int ired[kQpThreads / 32];
+    int idx[WMAX], fl[WMAX], inA[WMAX];
+    int ired[THREADS / 32];
     int ibcast[2];
 };
 
-__device__ __forceinline__ double block_sum(double v, QpSmem& S) {
-    v = warp_sum(v);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) S.red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double r = 0.0;
+// sum K values over the CTA with one barrier pair
+template <int K, int THREADS, class S>
+__device__ __forceinline__ void block_sum(double (&v)[K], S& sm) {
 #pragma unroll
-    for (int w = 0; w < kQpThreads / 32; ++w) r += S.red[w];
-    return r;
+    for (int k = 0; k < K; ++k) v[k] = warp_sum(v[k]);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) sm.red[k * (THREADS / 32) + (threadIdx.x >> 5)] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double r = 0.0;
+#pragma unroll
+        for (int w = 0; w < THREADS / 32; ++w) r += sm.red[k * (THREADS / 32) + w];
+        v[k] = r;
+    }
 }
-__device__ __forceinline__ double block_max(double v, QpSmem& S) {
+template <int THREADS, class S>
+__device__ __forceinline__ double block_max(double v, S& sm) {
     v = warp_max(v);
     __syncthreads();
-    if ((threadIdx.x & 31) == 0) S.red[threadIdx.x >> 5] = v;
+    if ((threadIdx.x & 31) == 0) sm.red[threadIdx.x >> 5] = v;
     __syncthreads();
-    double r = S.red[0];
+    double r = sm.red[0];
 #pragma unroll
-    for (int w = 1; w < kQpThreads / 32; ++w) r = fmax(r, S.red[w]);
+    for (int w = 1; w < THREADS / 32; ++w) r = fmax(r, sm.red[w]);
+    return r;
+}
+template <int THREADS, class S>
+__device__ __forceinline__ int block_count(bool p, S& sm) {
+    const unsigned bal = __ballot_sync(0xffffffffu, p);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm.ired[threadIdx.x >> 5] = __popc(bal);
+    __syncthreads();
+    int r = 0;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; ++w) r += sm.ired[w];
     return r;
 }
 
-// phi(lam) for multipliers lam[0..m) on rows idx[0..m); optionally stores g.
+// phi(lam) for multipliers lam[0..m) on rows idx[0..m); optionally stores g; optionally
+// returns slope = sum grad_a (lam_a - base_a) in the same reduction.
+template <int THREADS, class S>
 __device__ double eval_phi(const double* __restrict__ R, int ld, int n, const double* __restrict__ z,
-                           const int* idx, const double* lam, int m, double u, double* g_store,
-                           QpSmem& S) {
-    double part = 0.0;
-    for (int j = threadIdx.x; j < n; j += kQpThreads) {
+                           const int* idx, const double* lam, int m, double u, double* g_store, S& sm,
+                           const double* grad = nullptr, const double* base = nullptr,
+                           double* slope = nullptr) {
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (int j = threadIdx.x; j < n; j += THREADS) {
         double pi = 0.0;
         for (int a = 0; a < m; ++a) {
             const double l = lam[a];
@@ -74,65 +112,212 @@ __device__ double eval_phi(const double* __restrict__ R, int ld, int n, const do
         }
         const double gj = fmax(z[j] - pi, 0.0);
         if (g_store) g_store[j] = gj;
-        part = fma(gj, gj, part);
+        acc[0] = fma(gj, gj, acc[0]);
     }
-    double sl = 0.0;
-    for (int a = threadIdx.x; a < m; a += kQpThreads) sl += lam[a];
-    return 0.5 * block_sum(part, S) + u * block_sum(sl, S);
+    for (int a = threadIdx.x; a < m; a += THREADS) {
+        acc[1] += lam[a];
+        if (grad) acc[2] = fma(grad[a], lam[a] - base[a], acc[2]);
+    }
+    block_sum<3, THREADS>(acc, sm);
+    if (slope) *slope = acc[2];
+    return 0.5 * acc[0] + u * acc[1];
 }
 
-// H[p][q] = sum_{j: g_j>0} R[row_p][j] R[row_q][j] for the mf free rows, NB = ceil(mf/16).
-template <int NB>
-__device__ void hessian(const double* __restrict__ R, int ld, int n, const double* g, int mf, QpSmem& S) {
+// H[p][q] = sum_{j: g_j>0} R[idx_p][j] R[idx_q][j] over the m working rows -> lower triangle
+// of Hb and hdiag.  Threads form a 16 x (THREADS/16) grid; thread (tx,ty) owns rows
+// ty + TY*a, columns tx + 16*b, a < NBP, b < NBQ.
+template <int WMAX, int THREADS, int NBP, int NBQ, class S>
+__device__ void hessian(const double* __restrict__ R, int ld, int n, const double* g, int m, S& sm) {
+    constexpr int TY = THREADS / 16;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx = tid & 15, ty = tid >> 4;
-    double acc[NB][NB];
+    double acc[NBP][NBQ];
 #pragma unroll
-    for (int a = 0; a < NB; ++a)
+    for (int a = 0; a < NBP; ++a)
 #pragma unroll
-        for (int b = 0; b < NB; ++b) acc[a][b] = 0.0;
-    // rows beyond mf read a zero row of the tile
-    for (int p = mf + warp; p < 16 * NB; p += kQpThreads / 32) S.tileR[p * kTld + lane] = 0.0;
+        for (int b = 0; b < NBQ; ++b) acc[a][b] = 0.0;
+    // rows beyond m read a zero row of the tile
+    constexpr int kRows = (TY * NBP > 16 * NBQ) ? TY * NBP : 16 * NBQ;
+    for (int p = m + warp; p < kRows && p < WMAX; p += THREADS / 32) sm.tileR[p * kTld + lane] = 0.0;
     for (int j0 = 0; j0 < n; j0 += kJT) {
         __syncthreads();
-        for (int p = warp; p < mf; p += kQpThreads / 32) {
+        for (int p = warp; p < m; p += THREADS / 32) {
             const int j = j0 + lane;
             double val = 0.0;
-            if (j < n && g[j] > 0.0) val = R[(size_t)S.idx[S.fl[p]] * ld + j];
-            S.tileR[p * kTld + lane] = val;
+            if (j < n && g[j] > 0.0) val = R[(size_t)sm.idx[p] * ld + j];
+            sm.tileR[p * kTld + lane] = val;
         }
         __syncthreads();
 #pragma unroll 4
         for (int jj = 0; jj < kJT; ++jj) {
-            double pa[NB], qb[NB];
+            double pa[NBP], qb[NBQ];
 #pragma unroll
-            for (int a = 0; a < NB; ++a) pa[a] = S.tileR[(ty + 16 * a) * kTld + jj];
+            for (int a = 0; a < NBP; ++a) pa[a] = sm.tileR[(ty + TY * a) * kTld + jj];
 #pragma unroll
-            for (int b = 0; b < NB; ++b) qb[b] = S.tileR[(tx + 16 * b) * kTld + jj];
+            for (int b = 0; b < NBQ; ++b) qb[b] = sm.tileR[(tx + 16 * b) * kTld + jj];
 #pragma unroll
-            for (int a = 0; a < NB; ++a)
+            for (int a = 0; a < NBP; ++a)
 #pragma unroll
-                for (int b = 0; b < NB; ++b) acc[a][b] = fma(pa[a], qb[b], acc[a][b]);
+                for (int b = 0; b < NBQ; ++b) acc[a][b] = fma(pa[a], qb[b], acc[a][b]);
         }
     }
     __syncthreads();
 #pragma unroll
-    for (int a = 0; a < NB; ++a)
+    for (int a = 0; a < NBP; ++a)
 #pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            const int p = ty + 16 * a, q = tx + 16 * b;
-            if (p < mf && q < mf) S.H[p * kHld + q] = acc[a][b];
+        for (int b = 0; b < NBQ; ++b) {
+            const int p = ty + TY * a, q = tx + 16 * b;
+            if (p < m && q < m) {
+                if (p > q) sm.Hb[p * (WMAX + 1) + q] = acc[a][b];
+                else if (p == q) sm.hdiag[p] = acc[a][b];
+            }
         }
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(kQpThreads, 1) utility_qp_kernel(QpParams P) {
+// ---- dense SPD solves in shared memory on a principal sub-matrix of H.  The factor lives
+// in the upper part of Hb: L(p,q) = Hb[q*HLD + p + 1].  Blocked by 32 so that the
+// sequential part runs inside one warp (lanes own rows, __syncwarp / shuffles only) and the
+// CTA meets at three barriers per 32 columns instead of three per column.
+#define LV(p, q) Hb[(q) * HLD + (p) + 1]
+
+// Factor H[fl,fl] + shift*I (fl ascending, ma entries) and solve for rhs y[0..ma) in place.
+template <int WMAX, int THREADS, class S>
+__device__ void factor_solve(int ma, double shift, S& sm) {
+    constexpr int HLD = WMAX + 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* Hb = sm.Hb;
+    double* y = sm.y;
+    // gather the sub-matrix into the factor storage
+    for (int e = tid; e < ma * ma; e += THREADS) {
+        const int p = e % ma, q = e / ma;
+        if (p < q) continue;
+        const int ip = sm.fl[p], iq = sm.fl[q];
+        LV(p, q) = (p == q) ? sm.hdiag[ip] + shift : Hb[ip * HLD + iq];
+    }
+    __syncthreads();
+    for (int kb = 0; kb < ma; kb += 32) {
+        const int bs = min(32, ma - kb), r0 = kb + bs, rem = ma - r0;
+        if (warp == 0) {                                   // diagonal block, lanes own rows
+            const bool row = lane < bs;
+            for (int k = 0; k < bs; ++k) {
+                const double dkk = sqrt(fmax(LV(kb + k, kb + k), 1e-300));
+                __syncwarp();
+                if (lane == k) LV(kb + k, kb + k) = dkk;
+                double lik = 0.0;
+                if (row && lane > k) { lik = LV(kb + lane, kb + k) / dkk; LV(kb + lane, kb + k) = lik; }
+                __syncwarp();
+                if (row && lane > k)
+                    for (int j = k + 1; j <= lane; ++j)
+                        LV(kb + lane, kb + j) = fma(-lik, LV(kb + j, kb + k), LV(kb + lane, kb + j));
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        if (rem > 0) {
+            for (int r = tid; r < rem; r += THREADS) {     // panel below the block, one thread per row
+                const int i = r0 + r;
+                for (int k = 0; k < bs; ++k) {
+                    double acc = LV(i, kb + k);
+                    for (int q = 0; q < k; ++q) acc = fma(-LV(i, kb + q), LV(kb + k, kb + q), acc);
+                    LV(i, kb + k) = acc / LV(kb + k, kb + k);
+                }
+            }
+            __syncthreads();
+            for (int e = tid; e < rem * rem; e += THREADS) {   // trailing lower triangle
+                const int i = e % rem, j = e / rem;
+                if (j > i) continue;
+                double acc = 0.0;
+                for (int k = 0; k < bs; ++k) acc = fma(LV(r0 + i, kb + k), LV(r0 + j, kb + k), acc);
+                LV(r0 + i, r0 + j) -= acc;
+            }
+            __syncthreads();
+        }
+    }
+    for (int kb = 0; kb < ma; kb += 32) {                  // L y = b
+        const int bs = min(32, ma - kb), r0 = kb + bs;
+        if (warp == 0) {
+            double v = lane < bs ? y[kb + lane] : 0.0;
+            for (int k = 0; k < bs; ++k) {
+                const double yk = __shfl_sync(0xffffffffu, v, k) / LV(kb + k, kb + k);
+                if (lane == k) v = yk;
+                if (lane > k && lane < bs) v = fma(-LV(kb + lane, kb + k), yk, v);
+            }
+            if (lane < bs) y[kb + lane] = v;
+        }
+        __syncthreads();
+        for (int i = r0 + tid; i < ma; i += THREADS) {
+            double acc = y[i];
+            for (int k = 0; k < bs; ++k) acc = fma(-LV(i, kb + k), y[kb + k], acc);
+            y[i] = acc;
+        }
+        __syncthreads();
+    }
+    for (int kb = ((ma - 1) / 32) * 32; kb >= 0; kb -= 32) {   // L^T x = y
+        const int bs = min(32, ma - kb);
+        if (warp == 0) {
+            double v = lane < bs ? y[kb + lane] : 0.0;
+            for (int k = bs - 1; k >= 0; --k) {
+                const double xk = __shfl_sync(0xffffffffu, v, k) / LV(kb + k, kb + k);
+                if (lane == k) v = xk;
+                if (lane < k) v = fma(-LV(kb + k, kb + lane), xk, v);
+            }
+            if (lane < bs) y[kb + lane] = v;
+        }
+        __syncthreads();
+        for (int i = tid; i < kb; i += THREADS) {
+            double acc = y[i];
+            for (int k = 0; k < bs; ++k) acc = fma(-LV(kb + k, i), y[kb + k], acc);
+            y[i] = acc;
+        }
+        __syncthreads();
+    }
+}
+#undef LV
+
+// ordered list fl[0..) of the rows i < m with flag[i] != 0; returns its length
+template <int THREADS, class S>
+__device__ int compact_flags(const int* flag, int m, S& sm) {
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        int base = 0;
+        for (int i0 = 0; i0 < m; i0 += 32) {
+            const int i = i0 + lane;
+            const bool on = i < m && flag[i] != 0;
+            const unsigned bal = __ballot_sync(0xffffffffu, on);
+            if (on) sm.fl[base + __popc(bal & ((1u << lane) - 1))] = i;
+            base += __popc(bal);
+        }
+        if (lane == 0) sm.ibcast[1] = base;
+    }
+    __syncthreads();
+    return sm.ibcast[1];
+}
+
+// (H v)_i over the m working rows for a vector v supported on fl[0..ma): thread per row
+template <int WMAX, class S>
+__device__ __forceinline__ double hess_row_dot(int i, const double* v, int ma, S& sm) {
+    constexpr int HLD = WMAX + 1;
+    double acc = 0.0;
+    for (int p = 0; p < ma; ++p) {
+        const int j = sm.fl[p];
+        const double h = (i > j) ? sm.Hb[i * HLD + j] : ((i < j) ? sm.Hb[j * HLD + i] : sm.hdiag[i]);
+        acc = fma(h, v[j], acc);
+    }
+    return acc;
+}
+
+template <int WMAX, int THREADS, int CLS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
+    constexpr bool BIG = CLS == kQpClasses - 1;   // last class: nowhere to hand a column on to
+    using S = QpSmem<WMAX, THREADS>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    QpSmem& S = *reinterpret_cast<QpSmem*>(smem_raw);
+    S& sm = *reinterpret_cast<S*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c = blockIdx.x;
     const int f = c / P.T, t = c % P.T;
     if (!P.init && P.status[c] != 0) return;
+    if ((CLS > 0 || !P.init) && P.cls[c] != CLS) return;   // column of another instantiation
 
     const FeederDev fd = P.feeders[f];
     const int n = fd.n, ld = fd.np;
@@ -144,6 +329,7 @@ __global__ void __launch_bounds__(kQpThreads, 1) utility_qp_kernel(QpParams P) {
     const double* v = P.v_t + col;
     const double u = P.u, tol = P.tol;
     const double* rn2 = P.rn2 + fd.off;
+    int* widx = P.widx + (size_t)c * kWMax;
 
     // ------------------------------------------------------------ working set
     int m = 0;
@@ -152,58 +338,63 @@ __global__ void __launch_bounds__(kQpThreads, 1) utility_qp_kernel(QpParams P) {
         // (ordered compaction, so the working-set order -- and with it every rounding -- is
         // reproducible from run to run)
         int base = 0;
-        for (int j0 = 0; j0 < n; j0 += kQpThreads) {
+        for (int j0 = 0; j0 < n; j0 += THREADS) {
             const int j = j0 + tid;
             const bool on = j < n && lam_g[j] > 0.0;
             const unsigned bal = __ballot_sync(0xffffffffu, on);
             __syncthreads();
-            if (lane == 0) S.ired[warp] = __popc(bal);
+            if (lane == 0) sm.ired[warp] = __popc(bal);
             __syncthreads();
             int before = 0, total = 0;
 #pragma unroll
-            for (int w = 0; w < kQpThreads / 32; ++w) {
-                before += (w < warp) ? S.ired[w] : 0;
-                total += S.ired[w];
+            for (int w = 0; w < THREADS / 32; ++w) {
+                before += (w < warp) ? sm.ired[w] : 0;
+                total += sm.ired[w];
             }
             if (on) {
                 const int pos = base + before + __popc(bal & ((1u << lane) - 1));
-                if (pos < kWMax) { S.idx[pos] = j; S.lam[pos] = lam_g[j]; }
-                else lam_g[j] = 0.0;   // cannot be carried; re-admitted if violated
+                if (pos < WMAX) { sm.idx[pos] = j; sm.lam[pos] = lam_g[j]; }
+                else if (BIG) lam_g[j] = 0.0;   // cannot be carried; re-admitted if violated
             }
             base += total;
         }
         __syncthreads();
-        m = min(base, kWMax);
+        if (CLS == 0) {                         // the first instantiation classifies the column
+            int cl = 0;
+            while (cl < kQpClasses - 1 && base > qp_class_cap(cl)) ++cl;
+            if (tid == 0) P.cls[c] = cl;
+            if (cl != 0) return;
+        }
+        m = min(base, WMAX);
     } else {
         const int m_old = P.wcount[c];
         // keep rows with a positive multiplier (serial compaction keeps the order stable)
         if (tid == 0) {
             int k = 0;
             for (int a = 0; a < m_old; ++a) {
-                int i = P.widx[(size_t)c * kWMax + a];
+                int i = widx[a];
                 double l = lam_g[i];
-                if (l > 0.0) { S.idx[k] = i; S.lam[k] = l; ++k; }
+                if (l > 0.0) { sm.idx[k] = i; sm.lam[k] = l; ++k; }
             }
-            S.ibcast[0] = k;
+            sm.ibcast[0] = k;
         }
         __syncthreads();
-        m = S.ibcast[0];
+        m = sm.ibcast[0];
         // violated rows outside W, most violated first; key order (viol desc, index asc)
         double prev_v = 1e300;
         int prev_i = -1;
         int added = 0, n_viol_left = 0;
-        const int room = min(kAddMax, kWMax - m);
+        const int room = min(kAddMax, WMAX - m);
         for (int round = 0; round <= room; ++round) {
             double best = -1.0;
             int besti = 0x7fffffff;
-            for (int j = tid; j < n; j += kQpThreads) {
+            for (int j = tid; j < n; j += THREADS) {
                 const double viol = v[j] - u;
                 if (viol > tol && !(lam_g[j] > 0.0)) {
                     bool after_prev = (viol < prev_v) || (viol == prev_v && j > prev_i);
                     if (after_prev && (viol > best || (viol == best && j < besti))) { best = viol; besti = j; }
                 }
             }
-            // block arg-max
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 double ob = __shfl_xor_sync(0xffffffffu, best, o);
@@ -211,16 +402,16 @@ __global__ void __launch_bounds__(kQpThreads, 1) utility_qp_kernel(QpParams P) {
                 if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
             }
             __syncthreads();
-            if (lane == 0) { S.red[warp] = best; S.ired[warp] = besti; }
+            if (lane == 0) { sm.red[warp] = best; sm.ired[warp] = besti; }
             __syncthreads();
-            best = S.red[0]; besti = S.ired[0];
+            best = sm.red[0]; besti = sm.ired[0];
 #pragma unroll
-            for (int w = 1; w < kQpThreads / 32; ++w) {
-                if (S.red[w] > best || (S.red[w] == best && S.ired[w] < besti)) { best = S.red[w]; besti = S.ired[w]; }
+            for (int w = 1; w < THREADS / 32; ++w) {
+                if (sm.red[w] > best || (sm.red[w] == best && sm.ired[w] < besti)) { best = sm.red[w]; besti = sm.ired[w]; }
             }
             if (best < 0.0) break;              // no further violated row
             if (round == room) { n_viol_left = 1; break; }
-            if (tid == 0) { S.idx[m + added] = besti; S.lam[m + added] = 0.0; }
+            if (tid == 0) { sm.idx[m + added] = besti; sm.lam[m + added] = 0.0; }
             ++added;
             prev_v = best; prev_i = besti;
         }
@@ -229,153 +420,190 @@ __global__ void __launch_bounds__(kQpThreads, 1) utility_qp_kernel(QpParams P) {
             if (tid == 0) P.status[c] = 1;      // KKT point of the full problem
             return;
         }
-        if (added == 0 && n_viol_left && m == kWMax) {
-            if (tid == 0) { P.status[c] = 2; atomicAdd(P.n_failed, 1); }
-            return;
+        if (n_viol_left && m + added == WMAX) {
+            if (!BIG) {                         // hand the column over, state untouched
+                if (tid == 0) { P.cls[c] = CLS + 1; atomicAdd(P.n_running, 1); atomicAdd(P.n_cls + CLS + 1, 1); }
+                return;
+            }
+            if (added == 0) {
+                if (tid == 0) { P.status[c] = 2; atomicAdd(P.n_failed, 1); }
+                return;
+            }
         }
         // clear the stored multipliers of the old set; rewritten at the end
-        for (int a = tid; a < m_old; a += kQpThreads) lam_g[P.widx[(size_t)c * kWMax + a]] = 0.0;
+        for (int a = tid; a < m_old; a += THREADS) lam_g[widx[a]] = 0.0;
         m += added;
         __syncthreads();
     }
 
-    // ------------------------------------------------------------ restricted projected Newton
-    double phi = eval_phi(R, ld, n, z, S.idx, S.lam, m, u, g, S);
+    // ------------------------------------------------------------ piecewise-quadratic descent on W
+    double phi = eval_phi<THREADS>(R, ld, n, z, sm.idx, sm.lam, m, u, g, sm);
     double tau = 1.0;
     int ok = 0, its = 0;
+    unsigned n_evals = 0, n_pdas = 0, n_fallback = 0;
     for (; its < P.inner_max; ++its) {
         __syncthreads();
         // gradient on W:  u - R[idx_a] . g
-        for (int a = warp; a < m; a += kQpThreads / 32) {
-            const double* row = R + (size_t)S.idx[a] * ld;
+        for (int a = warp; a < m; a += THREADS / 32) {
+            const double* row = R + (size_t)sm.idx[a] * ld;
             double acc = 0.0;
             for (int j = lane; j < n; j += 32) acc = fma(row[j], g[j], acc);
             acc = warp_sum(acc);
-            if (lane == 0) S.grad[a] = u - acc;
+            if (lane == 0) sm.grad[a] = u - acc;
         }
         __syncthreads();
         double kk = 0.0;
-        for (int a = tid; a < m; a += kQpThreads) {
-            double gr = S.grad[a];
-            kk = fmax(kk, fabs(S.lam[a] > 0.0 ? gr : fmin(gr, 0.0)));
+        for (int a = tid; a < m; a += THREADS) {
+            double gr = sm.grad[a];
+            kk = fmax(kk, fabs(sm.lam[a] > 0.0 ? gr : fmin(gr, 0.0)));
         }
-        const double kkt = block_max(kk, S);
+        const double kkt = block_max<THREADS>(kk, sm);
         if (kkt < tol) { ok = 1; break; }
 
-        // free rows; rows pinned at (almost) zero with a positive gradient go to exactly 0
-        const double eps = fmin(1e-8, kkt);
-        if (tid == 0) {
-            int k = 0;
-            double sc = 0.0;
-            for (int a = 0; a < m; ++a) {
-                bool bound = (S.lam[a] <= eps) && (S.grad[a] > 0.0);
-                S.dir[a] = -S.lam[a];
-                if (!bound) { S.fl[k++] = a; sc += rn2[S.idx[a]]; }
-            }
-            S.ibcast[1] = k;
-            S.bcast[0] = k ? sc / (double)k : 0.0;
+        // model Hessian of the current piece on all of W
+        if constexpr (WMAX <= 64) {
+            hessian<WMAX, THREADS, WMAX / (THREADS / 16), WMAX / 16>(R, ld, n, g, m, sm);
+        } else {
+            const int nb = (m + 15) >> 4;
+            if (nb <= 4) hessian<WMAX, THREADS, 4, 4>(R, ld, n, g, m, sm);
+            else if (nb <= 6) hessian<WMAX, THREADS, 6, 6>(R, ld, n, g, m, sm);
+            else hessian<WMAX, THREADS, 8, 8>(R, ld, n, g, m, sm);
         }
+        double sc[1] = {0.0};
+        for (int a = tid; a < m; a += THREADS) sc[0] += rn2[sm.idx[a]];
+        block_sum<1, THREADS>(sc, sm);
+        const double scale = sc[0] / (double)m;      // mean |R_a|^2: curvature scale
+        const double shift = kHessShift * scale + 1e-300;
+
+        // ---- exact minimiser of the piece over lam_W >= 0: primal-dual active set
+        // b = H lam - grad ; A = {lam > 0} u {grad < 0}
+        for (int a = tid; a < m; a += THREADS) sm.inA[a] = (sm.lam[a] > 0.0) ? 1 : 0;
         __syncthreads();
-        const int mf = S.ibcast[1];
-        const double scale = S.bcast[0];    // mean |R_a|^2 of the free rows: curvature scale
+        int ma = compact_flags<THREADS>(sm.inA, m, sm);
+        for (int i = tid; i < m; i += THREADS)
+            sm.b[i] = hess_row_dot<WMAX>(i, sm.lam, ma, sm) + shift * sm.lam[i] - sm.grad[i];
+        __syncthreads();
+        for (int a = tid; a < m; a += THREADS) sm.inA[a] = (sm.lam[a] > 0.0 || sm.grad[a] < 0.0) ? 1 : 0;
+        __syncthreads();
+        bool pdas_ok = false;
+        for (int guess = 0; guess < kPdasMax; ++guess) {
+            ++n_pdas;
+            ma = compact_flags<THREADS>(sm.inA, m, sm);
+            for (int a = tid; a < m; a += THREADS) sm.trial[a] = 0.0;
+            if (ma > 0) {
+                for (int p = tid; p < ma; p += THREADS) sm.y[p] = sm.b[sm.fl[p]];
+                __syncthreads();
+                factor_solve<WMAX, THREADS>(ma, shift, sm);
+                for (int p = tid; p < ma; p += THREADS) sm.trial[sm.fl[p]] = sm.y[p];
+            }
+            __syncthreads();
+            bool bad = false;
+            for (int i = tid; i < m; i += THREADS) {
+                if (sm.inA[i]) {
+                    if (sm.trial[i] <= 0.0) { bad = true; sm.inA[i] = 0; }
+                } else {
+                    const double mu = hess_row_dot<WMAX>(i, sm.trial, ma, sm) - sm.b[i];
+                    if (mu < 0.0) { bad = true; sm.inA[i] = 1; }
+                }
+            }
+            if (block_count<THREADS>(bad, sm) == 0) { pdas_ok = true; break; }
+        }
 
         double alpha = 1.0, phin = phi;
-        for (;;) {   // Levenberg-Marquardt safeguard: raise the shift until the arc search succeeds
-            if (mf > 0) {
-                // Hessian H = R_{A,F} R_{F,A}, register-blocked over a 16x16 thread grid
-                const int nb = (mf + 15) >> 4;
-                if (nb <= 1) hessian<1>(R, ld, n, g, mf, S);
-                else if (nb <= 2) hessian<2>(R, ld, n, g, mf, S);
-                else if (nb <= 3) hessian<3>(R, ld, n, g, mf, S);
-                else if (nb <= 4) hessian<4>(R, ld, n, g, mf, S);
-                else if (nb <= 6) hessian<6>(R, ld, n, g, mf, S);
-                else hessian<8>(R, ld, n, g, mf, S);
-                const double reg = 1e-10 * tau * scale + 1e-300;
-                for (int p = tid; p < mf; p += kQpThreads) S.H[p * kHld + p] += reg;
-                __syncthreads();
-
-                // Cholesky H = L L^T (lower, in place)
-                for (int k = 0; k < mf; ++k) {
-                    if (tid == 0) S.H[k * kHld + k] = sqrt(fmax(S.H[k * kHld + k], 1e-300));
-                    __syncthreads();
-                    const double dkk = S.H[k * kHld + k];
-                    for (int i = k + 1 + tid; i < mf; i += kQpThreads) S.H[i * kHld + k] /= dkk;
-                    __syncthreads();
-                    const int cnt = mf - k - 1;
-                    for (int e = tid; e < cnt * cnt; e += kQpThreads) {
-                        int i = k + 1 + e / cnt, j = k + 1 + e % cnt;
-                        if (j <= i) S.H[i * kHld + j] = fma(-S.H[i * kHld + k], S.H[j * kHld + k], S.H[i * kHld + j]);
-                    }
-                    __syncthreads();
-                }
-                // solve L y = -grad_A ; L^T d = y   (trial[] is scratch for y)
-                for (int p = tid; p < mf; p += kQpThreads) S.trial[p] = -S.grad[S.fl[p]];
-                __syncthreads();
-                for (int k = 0; k < mf; ++k) {
-                    if (tid == 0) S.trial[k] /= S.H[k * kHld + k];
-                    __syncthreads();
-                    const double yk = S.trial[k];
-                    for (int i = k + 1 + tid; i < mf; i += kQpThreads) S.trial[i] = fma(-S.H[i * kHld + k], yk, S.trial[i]);
-                    __syncthreads();
-                }
-                for (int k = mf - 1; k >= 0; --k) {
-                    if (tid == 0) S.trial[k] /= S.H[k * kHld + k];
-                    __syncthreads();
-                    const double xk = S.trial[k];
-                    for (int i = tid; i < k; i += kQpThreads) S.trial[i] = fma(-S.H[k * kHld + i], xk, S.trial[i]);
-                    __syncthreads();
-                }
-                for (int p = tid; p < mf; p += kQpThreads) S.dir[S.fl[p]] = S.trial[p];
-                __syncthreads();
-            }
-
-            // Armijo search along the projection arc
-            bool found = false;
+        bool stepped = false;
+        if (pdas_ok) {
+            // search phi on the segment lam -> minimiser (both feasible)
+            for (int a = tid; a < m; a += THREADS) sm.dir[a] = sm.trial[a] - sm.lam[a];
+            __syncthreads();
             for (alpha = 1.0; alpha >= kArcMin; alpha *= 0.5) {
-                for (int a = tid; a < m; a += kQpThreads) S.trial[a] = fmax(fma(alpha, S.dir[a], S.lam[a]), 0.0);
+                for (int a = tid; a < m; a += THREADS) sm.trial[a] = fmax(fma(alpha, sm.dir[a], sm.lam[a]), 0.0);
                 __syncthreads();
-                double sl = 0.0;
-                for (int a = tid; a < m; a += kQpThreads) sl = fma(S.grad[a], S.trial[a] - S.lam[a], sl);
-                const double slope = block_sum(sl, S);
-                phin = eval_phi(R, ld, n, z, S.idx, S.trial, m, u, nullptr, S);
+                double slope;
+                phin = eval_phi<THREADS>(R, ld, n, z, sm.idx, sm.trial, m, u, nullptr, sm, sm.grad, sm.lam, &slope);
+                ++n_evals;
                 // + rounding noise of phi itself, see oracle/revs_oracle.py:project_voltage
-                if (phin <= phi + 1e-4 * slope + 1e-14 * fabs(phi)) { found = true; break; }
+                if (phin <= phi + 1e-4 * slope + 1e-14 * fabs(phi)) { stepped = true; break; }
             }
-            if (found || tau > 1e40 || mf == 0) break;
-            tau *= 1e3;
         }
-        if (alpha == 1.0) tau = fmax(1.0, tau / 10.0);
+        if (!stepped) {
+            // safeguard: projected-Newton arc step on the free rows with an LM shift
+            ++n_fallback;
+            const double eps = fmin(1e-8, kkt);
+            for (int a = tid; a < m; a += THREADS) {
+                const bool bound = (sm.lam[a] <= eps) && (sm.grad[a] > 0.0);
+                sm.inA[a] = bound ? 0 : 1;
+            }
+            __syncthreads();
+            const int mf = compact_flags<THREADS>(sm.inA, m, sm);
+            for (;;) {
+                for (int a = tid; a < m; a += THREADS) sm.dir[a] = -sm.lam[a];
+                if (mf > 0) {
+                    for (int p = tid; p < mf; p += THREADS) sm.y[p] = -sm.grad[sm.fl[p]];
+                    __syncthreads();
+                    factor_solve<WMAX, THREADS>(mf, 1e-10 * tau * scale + 1e-300, sm);
+                    for (int p = tid; p < mf; p += THREADS) sm.dir[sm.fl[p]] = sm.y[p];
+                }
+                __syncthreads();
+                bool found = false;
+                for (alpha = 1.0; alpha >= kArcMin; alpha *= 0.5) {
+                    for (int a = tid; a < m; a += THREADS) sm.trial[a] = fmax(fma(alpha, sm.dir[a], sm.lam[a]), 0.0);
+                    __syncthreads();
+                    double slope;
+                    phin = eval_phi<THREADS>(R, ld, n, z, sm.idx, sm.trial, m, u, nullptr, sm, sm.grad, sm.lam, &slope);
+                    ++n_evals;
+                    if (phin <= phi + 1e-4 * slope + 1e-14 * fabs(phi)) { found = true; break; }
+                }
+                if (found || tau > 1e40 || mf == 0) break;
+                tau *= 1e3;
+            }
+            if (alpha == 1.0) tau = fmax(1.0, tau / 10.0);
+        }
         __syncthreads();
-        for (int a = tid; a < m; a += kQpThreads) S.lam[a] = S.trial[a];
+        for (int a = tid; a < m; a += THREADS) sm.lam[a] = sm.trial[a];
         __syncthreads();
-        phi = eval_phi(R, ld, n, z, S.idx, S.lam, m, u, g, S);
+        phi = eval_phi<THREADS>(R, ld, n, z, sm.idx, sm.lam, m, u, g, sm);
     }
 
     // ------------------------------------------------------------ persist
     __syncthreads();
-    for (int a = tid; a < m; a += kQpThreads) {
-        lam_g[S.idx[a]] = S.lam[a];
-        P.widx[(size_t)c * kWMax + a] = S.idx[a];
+    for (int a = tid; a < m; a += THREADS) {
+        lam_g[sm.idx[a]] = sm.lam[a];
+        widx[a] = sm.idx[a];
     }
     if (tid == 0) {
         P.wcount[c] = m;
         P.inner_ok[c] = ok;
         P.status[c] = 0;
         atomicAdd(P.n_running, 1);
+        atomicAdd(P.n_cls + CLS, 1);
         atomicAdd(P.newton_its, (unsigned long long)its);
         atomicMax(P.max_ws, m);
+        if (P.dbg) {
+            atomicAdd(P.dbg + 0, (unsigned long long)n_evals);
+            atomicAdd(P.dbg + 1, (unsigned long long)n_pdas);
+            atomicMax(P.dbg + 2, (unsigned long long)its);
+            atomicAdd(P.dbg + 3, (unsigned long long)n_fallback);
+        }
     }
 }
 
-cudaError_t launch_utility_qp(const QpParams& P, int ncols, cudaStream_t stream) {
+cudaError_t launch_utility_qp(const QpParams& P, int ncols, int cls, cudaStream_t stream) {
+    using S0 = QpSmem<32, 128>;
+    using S1 = QpSmem<64, 256>;
+    using S2 = QpSmem<kWMax, 256>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(utility_qp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)sizeof(QpSmem));
+        cudaError_t e = cudaFuncSetAttribute(utility_qp_kernel<64, 256, 1, 2>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S1));
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(utility_qp_kernel<kWMax, 256, 2, 1>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S2));
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    utility_qp_kernel<<<ncols, kQpThreads, sizeof(QpSmem), stream>>>(P);
+    if (cls == 0) utility_qp_kernel<32, 128, 0, 4><<<ncols, 128, sizeof(S0), stream>>>(P);
+    else if (cls == 1) utility_qp_kernel<64, 256, 1, 2><<<ncols, 256, sizeof(S1), stream>>>(P);
+    else utility_qp_kernel<kWMax, 256, 2, 1><<<ncols, 256, sizeof(S2), stream>>>(P);
     return cudaGetLastError();
 }
 

@@ -39,8 +39,8 @@ def test_contract_matches_numpy(gpu_lib, M, K, T):
 # ----------------------------------------------------------------- home step
 def test_home_step_bit_exact_random(gpu_lib):
     from revs_admm_b200.feeder import synthetic_homes, synthetic_tariff
-    for T, H in [(24, 257), (96, 130), (40, 33)]:
-        hm = synthetic_homes(H, T, seed=T)
+    for T, H, slow in [(24, 257, False), (96, 130, False), (40, 33, False), (96, 77, True)]:
+        hm = synthetic_homes(H, T, seed=T, rating_kw=1.2 if slow else 4.8)   # slow: 47..53 hours -> ranking path
         if T == 40:
             hm["start"][:] = 3
             hm["end"][:] = 37
