@@ -10,7 +10,7 @@
  *
  * Reference interface replaced by each entry point (file:line in /root/reference):
  *
- *   revs_set_sensitivity / revs_set_feeder_tree   lpsolver.py:17-26   compute_Rmat()
+ *   revs_set_sensitivity / revs_set_feeder_tree(s) lpsolver.py:17-26  compute_Rmat()
  *                                                 lpsolver.py:179-190 Utility.network()
  *   revs_set_homes / revs_set_tariff              lpsolver.py:45-62   Home.__init__ inputs
  *                                                 extract.py:77-119   get_homes_ev_param()
@@ -48,6 +48,7 @@ typedef struct revs_solver revs_solver;
 typedef struct revs_stats {
     int64_t kernel_launches;      /* kernels of this library launched                  */
     int64_t gemm_launches;        /* ... of which sensitivity contractions             */
+    int64_t gemm_full_launches;   /* ... of which over all columns (first round of an iteration) */
     int64_t qp_outer_iterations;  /* utility working-set rounds, summed over ADMM iters */
     int64_t qp_newton_iterations; /* restricted Newton steps, summed over columns       */
     int32_t admm_iterations;
@@ -55,6 +56,7 @@ typedef struct revs_stats {
     double primal_residual;       /* ||P_est-P_sch||_F / sqrt(H T), last iteration      */
     double dual_residual;         /* kappa ||P_sch-P_sch_prev||_F / sqrt(H T)           */
     float gemm_ms;                /* device time in sensitivity contractions (events)   */
+    float gemm_full_ms;           /* ... of which the launches over ALL (feeder,hour) columns */
     float home_ms;                /* device time in the batched home solve              */
     float dual_ms;                /* device time in the fused dual/residual kernel      */
     float qp_ms;                  /* device time in the per-column QP kernels (both)    */
@@ -82,6 +84,12 @@ int revs_set_sensitivity(revs_solver* s, int feeder, const double* R_res);
  * revs_reliability() on arbitrary nodes / edges of this feeder. */
 int revs_set_feeder_tree(revs_solver* s, int feeder, int n_nodes, const int32_t* parent,
                          const double* r, const int32_t* res_node);
+
+/* All feeders of the solver at once (one upload, one kernel): node_off[n_feeders+1] offsets
+ * into the concatenated parent / r arrays (parent indices are local to their feeder),
+ * res_node [H] in the home order of revs_create (node indices local to the feeder). */
+int revs_set_feeder_trees(revs_solver* s, const int64_t* node_off, const int32_t* parent,
+                          const double* r, const int32_t* res_node);
 
 /* Per-home inputs (host).  load [H,T] kW; has_ev [H]; rating kW, capacity kWh, initial
  * SOC, start/end = plug-in window [start,end) in steps.  EV arrays are ignored where

@@ -21,11 +21,11 @@ class RevsError(RuntimeError):
 
 
 class Stats(C.Structure):
-    _fields_ = [("kernel_launches", C.c_int64), ("gemm_launches", C.c_int64),
+    _fields_ = [("kernel_launches", C.c_int64), ("gemm_launches", C.c_int64), ("gemm_full_launches", C.c_int64),
                 ("qp_outer_iterations", C.c_int64), ("qp_newton_iterations", C.c_int64),
                 ("admm_iterations", C.c_int32), ("max_working_set", C.c_int32),
                 ("primal_residual", C.c_double), ("dual_residual", C.c_double),
-                ("gemm_ms", C.c_float), ("home_ms", C.c_float), ("dual_ms", C.c_float),
+                ("gemm_ms", C.c_float), ("gemm_full_ms", C.c_float), ("home_ms", C.c_float), ("dual_ms", C.c_float),
                 ("qp_ms", C.c_float), ("qp_big_ms", C.c_float), ("total_ms", C.c_float)]
 
     def as_dict(self):
@@ -43,6 +43,7 @@ SIGNATURES = {
     "revs_destroy": ([_P], C.c_int),
     "revs_set_sensitivity": ([_P, C.c_int, _D], C.c_int),
     "revs_set_feeder_tree": ([_P, C.c_int, C.c_int, C.POINTER(C.c_int32), _D, C.POINTER(C.c_int32)], C.c_int),
+    "revs_set_feeder_trees": ([_P, C.POINTER(C.c_int64), C.POINTER(C.c_int32), _D, C.POINTER(C.c_int32)], C.c_int),
     "revs_set_homes": ([_P, _D, C.POINTER(C.c_uint8), _D, _D, _D, C.POINTER(C.c_int32),
                         C.POINTER(C.c_int32)], C.c_int),
     "revs_set_tariff": ([_P, _D], C.c_int),
@@ -151,6 +152,18 @@ class Solver:
         _check(self.lib.revs_set_feeder_tree(self._h, feeder, len(parent), parent.ctypes.data_as(i32),
                                              _dp(r), res_node.ctypes.data_as(i32)))
 
+    def set_feeder_trees(self, trees):
+        """All feeders in one call; `trees` are feeder.FeederTree-like (parent, r, res_node)."""
+        assert len(trees) == self.nf
+        node_off = np.concatenate([[0], np.cumsum([len(t.parent) for t in trees])]).astype(np.int64)
+        parent = np.ascontiguousarray(np.concatenate([t.parent for t in trees]), dtype=np.int32)
+        r = _f64(np.concatenate([t.r for t in trees]))
+        res = np.ascontiguousarray(np.concatenate([t.res_node for t in trees]), dtype=np.int32)
+        assert len(res) == self.H
+        i32 = C.POINTER(C.c_int32)
+        _check(self.lib.revs_set_feeder_trees(self._h, node_off.ctypes.data_as(C.POINTER(C.c_int64)),
+                                              parent.ctypes.data_as(i32), _dp(r), res.ctypes.data_as(i32)))
+
     def set_homes(self, load, has_ev, rating, capacity, initial, start, end):
         H, T = self.H, self.T
         load = _f64(load, (H, T))
@@ -197,11 +210,17 @@ class Solver:
                                           _dp(g), _dp(lam)))
         return g, lam
 
-    def results(self, iters=None, want_diff=True):
+    def results(self, iters=None, want_diff=True, out=None):
+        """`out`: optional dict of preallocated (e.g. page-locked) arrays P_sch, P_ev, SOC, diff."""
         H, T = self.H, self.T
         iters = self.stats()["admm_iterations"] if iters is None else iters
-        P, E, S = np.empty((H, T)), np.empty((H, T)), np.empty((H, T + 1))
-        D = np.empty((iters, H)) if want_diff else None
+        if out is not None:
+            P, E, S, D = out["P_sch"], out["P_ev"], out["SOC"], out.get("diff")
+            assert P.shape == (H, T) and E.shape == (H, T) and S.shape == (H, T + 1)
+            assert D is None or (D.shape[0] >= iters and D.shape[1] == H and D.flags.c_contiguous)
+        else:
+            P, E, S = np.empty((H, T)), np.empty((H, T)), np.empty((H, T + 1))
+            D = np.empty((iters, H)) if want_diff else None
         _check(self.lib.revs_get_results(self._h, _dp(P), _dp(E), _dp(S), _dp(D)))
         return dict(P_sch=P, P_ev=E, SOC=S, diff=D)
 

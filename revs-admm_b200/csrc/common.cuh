@@ -33,6 +33,7 @@ struct ContractProblem {
     const double* Bt; int64_t ldb;       // Bt[t*ldb + k]
     double* out; int64_t ldo;
     const double* scale;                 // per-row, kOutScaled only
+    const int* col_status;               // optional [T]: columns with status != 0 are skipped
 };
 
 struct ContractTile { int problem; int row0; };

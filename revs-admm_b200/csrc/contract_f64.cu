@@ -63,6 +63,20 @@ contract_f64_kernel(const ContractProblem* __restrict__ problems,
     const int wn = (warp / WARPS_M) * Cfg::kWN;
     const int nk = pb.K / kBK;
 
+    // columns whose QP has converged keep their voltages: skip their 8-wide groups, and the
+    // whole tile when no column of this feeder is still running
+    unsigned act = 0xffffffffu;
+    if (pb.col_status) {
+        act = 0u;
+#pragma unroll
+        for (int j = 0; j < Cfg::kNT; ++j) {
+            const int colj = n0 + wn + j * 8 + (lane & 7);
+            const bool on = colj < T && pb.col_status[colj] == 0;
+            if (__any_sync(0xffffffffu, on)) act |= 1u << j;
+        }
+        if (__syncthreads_or(act != 0u) == 0) return;
+    }
+
     auto load_stage = [&](int stage, int kt) {
         const int k0 = kt * kBK;
         double* a = sA + (size_t)stage * BM * kLds;
@@ -114,7 +128,8 @@ contract_f64_kernel(const ContractProblem* __restrict__ problems,
 #pragma unroll
             for (int i = 0; i < Cfg::kMT; ++i)
 #pragma unroll
-                for (int j = 0; j < Cfg::kNT; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                for (int j = 0; j < Cfg::kNT; ++j)
+                    if (act & (1u << j)) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
     }
     cp_async_wait<0>();
@@ -127,6 +142,7 @@ contract_f64_kernel(const ContractProblem* __restrict__ problems,
         const double sc = (mode == kOutScaled && pb.scale) ? pb.scale[row] : 1.0;
 #pragma unroll
         for (int j = 0; j < Cfg::kNT; ++j) {
+            if (!(act & (1u << j))) continue;
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int col = n0 + wn + j * 8 + 2 * fk + e;

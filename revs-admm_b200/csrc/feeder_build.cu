@@ -29,6 +29,27 @@ __global__ void sens_voltage_kernel(const int* __restrict__ parent, const double
     }
 }
 
+// All residence blocks of a batch of feeders in one launch (blockIdx.z = feeder).
+__global__ void sens_voltage_batched_kernel(const FeederDev* __restrict__ feeders, const int64_t* __restrict__ node_off,
+                                            const int* __restrict__ parent, const double* __restrict__ cumr,
+                                            const int* __restrict__ res_node, double* __restrict__ Rpool) {
+    const FeederDev fd = feeders[blockIdx.z];
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= fd.n) return;
+    const int* par = parent + node_off[blockIdx.z];
+    const double* cr = cumr + node_off[blockIdx.z];
+    const int* res = res_node + fd.off;
+    const int bj = res[j];
+    for (int m = blockIdx.y; m < fd.n; m += gridDim.y) {
+        int a = res[m], b = bj;
+        while (a != b) {
+            if (a > b) a = par[a];
+            else b = par[b];
+        }
+        Rpool[fd.roff + (size_t)m * fd.np + j] = a < 0 ? 0.0 : 2.0 * cr[a];
+    }
+}
+
 // out[m*ld + j] = 1 if the edge above node row_node[m] carries residence j.
 __global__ void sens_flow_kernel(const int* __restrict__ parent, const int* __restrict__ row_node,
                                  const int* __restrict__ res_node, int n_rows, int n_res,
@@ -85,6 +106,17 @@ cudaError_t launch_sens_voltage(const int* parent, const double* cumr, const int
     if (n_rows == 0 || n_res == 0) return cudaSuccess;
     dim3 grid((n_res + 127) / 128, n_rows < 65535 ? n_rows : 65535);
     sens_voltage_kernel<<<grid, 128, 0, s>>>(parent, cumr, row_node, res_node, n_rows, n_res, out, ld);
+    return cudaGetLastError();
+}
+cudaError_t launch_sens_voltage_batched(const FeederDev* feeders, int n_feeders, int max_n, const int64_t* node_off,
+                                        const int* parent, const double* cumr, const int* res_node, double* Rpool,
+                                        cudaStream_t s) {
+    if (n_feeders == 0 || max_n == 0) return cudaSuccess;
+    for (int f0 = 0; f0 < n_feeders; f0 += 65535) {
+        const int nz = n_feeders - f0 < 65535 ? n_feeders - f0 : 65535;
+        dim3 grid((max_n + 127) / 128, max_n < 256 ? max_n : 256, nz);
+        sens_voltage_batched_kernel<<<grid, 128, 0, s>>>(feeders + f0, node_off + f0, parent, cumr, res_node, Rpool);
+    }
     return cudaGetLastError();
 }
 cudaError_t launch_sens_flow(const int* parent, const int* row_node, const int* res_node, int n_rows,

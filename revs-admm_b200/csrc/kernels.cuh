@@ -93,6 +93,9 @@ cudaError_t launch_contract(const ContractProblem* d_problems, const ContractTil
 cudaError_t launch_sens_voltage(const int* parent, const double* cumr, const int* row_node,
                                 const int* res_node, int n_rows, int n_res, double* out, int ld,
                                 cudaStream_t s);
+cudaError_t launch_sens_voltage_batched(const FeederDev* feeders, int n_feeders, int max_n, const int64_t* node_off,
+                                        const int* parent, const double* cumr, const int* res_node, double* Rpool,
+                                        cudaStream_t s);
 cudaError_t launch_sens_flow(const int* parent, const int* row_node, const int* res_node, int n_rows,
                              int n_res, double* out, int ld, cudaStream_t s);
 cudaError_t launch_row_norms(const FeederDev* feeders, int n_feeders, const double* Rpool, double* rn2,

@@ -69,6 +69,7 @@ struct Tree {
     int* d_parent = nullptr;
     double* d_cumr = nullptr;
     int* d_res_node = nullptr;
+    bool pooled = false;     // sub-range of the solver's tree pool (revs_set_feeder_trees)
 };
 
 struct TimedSpan { cudaEvent_t a, b; int cat; };
@@ -87,6 +88,10 @@ struct revs_solver {
     FeederDev* d_feeders = nullptr;
     double* d_Rpool = nullptr;
     double* d_rn2 = nullptr;
+    int *d_pool_parent = nullptr, *d_pool_res = nullptr;   // revs_set_feeder_trees
+    double* d_pool_cumr = nullptr;
+    int64_t* d_pool_off = nullptr;
+    size_t pool_nodes = 0;
     bool rn2_valid = false;
     // home-major [Hp][T]
     double *d_load = nullptr, *d_pest = nullptr, *d_psch[2] = {nullptr, nullptr}, *d_gamma = nullptr,
@@ -113,6 +118,7 @@ struct revs_solver {
     // run state
     double kappa = 5.0, vset = 1.0, vlow = 0.95, vhigh = 1.05, tol = 0.0;
     int iter_max = 0, k = 0, cur = 0;
+    int warm_cls = kQpClasses - 1;   // largest QP class the stored multipliers can need
     bool running = false;
     revs_stats stats{};
 };
@@ -163,6 +169,7 @@ void spans_collect(revs_solver* s) {   // after the streams are synchronised
         if (cudaEventElapsedTime(&ms, s->spans[i].a, s->spans[i].b) != cudaSuccess) continue;
         switch (s->spans[i].cat) {
             case 0: s->stats.gemm_ms += ms; break;
+            case 5: s->stats.gemm_ms += ms; s->stats.gemm_full_ms += ms; break;
             case 1: s->stats.home_ms += ms; break;
             case 2: s->stats.dual_ms += ms; break;
             case 3: s->stats.qp_ms += ms; break;
@@ -248,25 +255,32 @@ int utility_solve(revs_solver* s) {
     Q.tol = kQpTol;
     Q.inner_max = kQpInnerMax;
 
-    Q.init = 1;
+    // First launch of the solve: evaluate the warm start only (g = [z - R lam]_+), so that
+    // the first descent already sees the voltages of the new target z.
+    Q.init = 2;
     TimedSpan* sp = nullptr;
     bool use[kQpClasses];
-    for (int cl = 0; cl < kQpClasses; ++cl) {     // every class once: the first one classifies
+    for (int cl = 0; cl < kQpClasses; ++cl) {
+        // a class whose capacity no warm-start set can need is skipped: all multipliers come
+        // from the previous ADMM iteration, whose largest class is known
+        use[cl] = cl <= s->warm_cls;
+        if (!use[cl]) continue;
         sp = span_begin(s, cl == 0 ? 3 : 4, s->sU);
         CU(launch_utility_qp(Q, s->ncols, cl, s->sU));
         span_end(sp, s->sU);
-        use[cl] = true;                           // unknown until the first read-back
+        s->stats.kernel_launches++;
     }
-    s->stats.kernel_launches += kQpClasses;
     Q.init = 0;
+    int top_cls = 0;
     for (int round = 0;; ++round) {
         if (round >= kQpRoundMax)
             return fail(REVS_ERR_NOCONV, "utility QP: %d columns still running after %d working-set rounds",
                         s->h_cnt->n_running, round);
-        sp = span_begin(s, 0, s->sU);
+        sp = span_begin(s, round == 0 ? 5 : 0, s->sU);   // round 0: every column is running
         CU(launch_contract(s->d_cprob, s->d_ctiles, s->n_ctiles, s->T, kOutTimeMajor, 0.0, s->sU));
         span_end(sp, s->sU);
         s->stats.kernel_launches++;
+        if (round == 0) s->stats.gemm_full_launches++;
         CU(cudaMemsetAsync(&s->d_cnt->n_running, 0, (1 + kQpClasses) * sizeof(int), s->sU));
         for (int cl = 0; cl < kQpClasses; ++cl) {
             if (!use[cl]) continue;
@@ -291,8 +305,12 @@ int utility_solve(revs_solver* s) {
                     s->h_cnt->dbg[3]);
         if (s->h_cnt->n_running == 0) break;
         use[0] = true;
-        for (int cl = 1; cl < kQpClasses; ++cl) use[cl] = s->h_cnt->n_cls[cl] > 0;
+        for (int cl = 1; cl < kQpClasses; ++cl) {
+            use[cl] = s->h_cnt->n_cls[cl] > 0;
+            if (use[cl]) top_cls = cl;
+        }
     }
+    s->warm_cls = top_cls;
     return REVS_OK;
 }
 
@@ -322,7 +340,7 @@ HomeParams home_params(revs_solver* s, int individual) {
 
 void free_all(revs_solver* s) {
     cudaSetDevice(s->device);
-    void* ptrs[] = {s->d_feeders, s->d_Rpool, s->d_rn2, s->d_load, s->d_pest, s->d_psch[0], s->d_psch[1], s->d_gamma,
+    void* ptrs[] = {s->d_feeders, s->d_Rpool, s->d_rn2, s->d_pool_parent, s->d_pool_res, s->d_pool_cumr, s->d_pool_off, s->d_load, s->d_pest, s->d_psch[0], s->d_psch[1], s->d_gamma,
                     s->d_pev, s->d_soc, s->d_has_ev, s->d_rating, s->d_capacity, s->d_initial, s->d_indconst,
                     s->d_start, s->d_end, s->d_nmin, s->d_nmax, s->d_zero_i, s->d_cost, s->d_zt, s->d_lamt,
                     s->d_gt, s->d_vt, s->d_wcount, s->d_widx, s->d_status, s->d_innerok, s->d_cls, s->d_cnt, s->d_diff,
@@ -330,6 +348,7 @@ void free_all(revs_solver* s) {
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (auto& t : s->trees) {
+        if (t.pooled) continue;
         if (t.d_parent) cudaFree(t.d_parent);
         if (t.d_cumr) cudaFree(t.d_cumr);
         if (t.d_res_node) cudaFree(t.d_res_node);
@@ -448,7 +467,7 @@ int revs_create(revs_solver** out, int device, int n_feeders, const int64_t* fee
     for (int f = 0; f < n_feeders; ++f) {
         const FeederDev& fd = s->feeders[f];
         probs[f] = ContractProblem{s->d_Rpool + fd.roff, fd.np, fd.np, fd.np, s->d_gt + fd.off, hp,
-                                   s->d_vt + fd.off, hp, nullptr};
+                                   s->d_vt + fd.off, hp, nullptr, s->d_status + (size_t)f * T};
         for (int r0 = 0; r0 < fd.np; r0 += bm) tiles.push_back(ContractTile{f, r0});
     }
     s->n_ctiles = (int)tiles.size();
@@ -497,7 +516,8 @@ int revs_set_feeder_tree(revs_solver* s, int feeder, int n_nodes, const int32_t*
     for (int j = 0; j < fd.n; ++j)
         if (res_node[j] < 0 || res_node[j] >= n_nodes) return fail(REVS_ERR_ARG, "res_node[%d] out of range", j);
     Tree& t = s->trees[feeder];
-    if (t.d_parent) { cudaFree(t.d_parent); cudaFree(t.d_cumr); cudaFree(t.d_res_node); t = Tree(); }
+    if (t.d_parent && !t.pooled) { cudaFree(t.d_parent); cudaFree(t.d_cumr); cudaFree(t.d_res_node); }
+    t = Tree();
     t.n_nodes = n_nodes;
     CU(dalloc(&t.d_parent, (size_t)n_nodes));
     CU(dalloc(&t.d_cumr, (size_t)n_nodes));
@@ -508,6 +528,60 @@ int revs_set_feeder_tree(revs_solver* s, int feeder, int n_nodes, const int32_t*
     CU(launch_sens_voltage(t.d_parent, t.d_cumr, nullptr, t.d_res_node, fd.n, fd.n, s->d_Rpool + fd.roff, fd.np, s->sU));
     CU(cudaStreamSynchronize(s->sU));
     s->sens_set[feeder] = 1;
+    s->rn2_valid = false;
+    return REVS_OK;
+}
+
+int revs_set_feeder_trees(revs_solver* s, const int64_t* node_off, const int32_t* parent, const double* r,
+                          const int32_t* res_node) {
+    if (!s || !node_off || !parent || !r || !res_node) return fail(REVS_ERR_ARG, "bad arguments");
+    CU(cudaSetDevice(s->device));
+    if (node_off[0] != 0) return fail(REVS_ERR_ARG, "node_off[0] must be 0");
+    const int64_t total = node_off[s->nf];
+    std::vector<double> cumr((size_t)total);
+    std::vector<int> res_p((size_t)s->Hp, 0);
+    for (int f = 0; f < s->nf; ++f) {
+        const int64_t o = node_off[f], nn = node_off[f + 1] - o;
+        if (nn <= 0) return fail(REVS_ERR_ARG, "feeder %d has no nodes", f);
+        for (int64_t i = 0; i < nn; ++i) {
+            const int p = parent[o + i];
+            if (p >= i || p < -1) return fail(REVS_ERR_ARG, "feeder %d: nodes must be topologically ordered (parent[i] < i)", f);
+            if (!(r[o + i] >= 0.0)) return fail(REVS_ERR_ARG, "feeder %d: negative or NaN resistance at node %lld", f, (long long)i);
+            cumr[o + i] = (p < 0 ? 0.0 : cumr[o + p]) + r[o + i];
+        }
+        for (int64_t j = s->off[f]; j < s->off[f + 1]; ++j) {
+            if (res_node[j] < 0 || res_node[j] >= nn) return fail(REVS_ERR_ARG, "res_node[%lld] out of range", (long long)j);
+            res_p[s->feeders[f].off + (j - s->off[f])] = res_node[j];
+        }
+    }
+    if (s->pool_nodes < (size_t)total) {
+        if (s->d_pool_parent) { cudaFree(s->d_pool_parent); cudaFree(s->d_pool_cumr); s->d_pool_parent = nullptr; s->d_pool_cumr = nullptr; }
+        CU(dalloc(&s->d_pool_parent, (size_t)total));
+        CU(dalloc(&s->d_pool_cumr, (size_t)total));
+        s->pool_nodes = (size_t)total;
+    }
+    if (!s->d_pool_res) CU(dalloc(&s->d_pool_res, (size_t)s->Hp));
+    if (!s->d_pool_off) CU(dalloc(&s->d_pool_off, (size_t)s->nf + 1));
+    CU(cudaMemcpyAsync(s->d_pool_parent, parent, sizeof(int) * total, cudaMemcpyHostToDevice, s->sU));
+    CU(cudaMemcpyAsync(s->d_pool_cumr, cumr.data(), sizeof(double) * total, cudaMemcpyHostToDevice, s->sU));
+    CU(cudaMemcpyAsync(s->d_pool_res, res_p.data(), sizeof(int) * s->Hp, cudaMemcpyHostToDevice, s->sU));
+    CU(cudaMemcpyAsync(s->d_pool_off, node_off, sizeof(int64_t) * (s->nf + 1), cudaMemcpyHostToDevice, s->sU));
+    int max_n = 0;
+    for (int f = 0; f < s->nf; ++f) {
+        Tree& t = s->trees[f];
+        if (t.d_parent && !t.pooled) { cudaFree(t.d_parent); cudaFree(t.d_cumr); cudaFree(t.d_res_node); }
+        t.n_nodes = (int)(node_off[f + 1] - node_off[f]);
+        t.d_parent = s->d_pool_parent + node_off[f];
+        t.d_cumr = s->d_pool_cumr + node_off[f];
+        t.d_res_node = s->d_pool_res + s->feeders[f].off;
+        t.pooled = true;
+        s->sens_set[f] = 1;
+        if (s->feeders[f].n > max_n) max_n = s->feeders[f].n;
+    }
+    CU(launch_sens_voltage_batched(s->d_feeders, s->nf, max_n, s->d_pool_off, s->d_pool_parent, s->d_pool_cumr,
+                                   s->d_pool_res, s->d_Rpool, s->sU));
+    CU(cudaStreamSynchronize(s->sU));     // the host staging vectors die here
+    s->stats.kernel_launches++;
     s->rn2_valid = false;
     return REVS_OK;
 }
@@ -562,6 +636,7 @@ int revs_admm_begin(revs_solver* s, double kappa, int iter_max, double vset, dou
     CU(cudaSetDevice(s->device));
     s->kappa = kappa; s->iter_max = iter_max; s->vset = vset; s->vlow = vlow; s->vhigh = vhigh;
     s->k = 0; s->cur = 0; s->running = true;
+    s->warm_cls = 0;                 // multipliers start at zero
     memset(&s->stats, 0, sizeof s->stats);
     const size_t HT = (size_t)s->Hp * s->T * sizeof(double);
     double* zero[] = {s->d_pest, s->d_psch[0], s->d_psch[1], s->d_gamma, s->d_pev, s->d_zt, s->d_lamt, s->d_gt, s->d_vt};
@@ -771,6 +846,7 @@ int revs_utility_step(revs_solver* s, double kappa, double vset, double vlow, do
     CU(cudaMemsetAsync(s->d_cnt, 0, sizeof(Counters), s->sU));
     CU(cudaMemsetAsync(s->d_wcount, 0, sizeof(int) * s->ncols, s->sU));
     memset(&s->stats, 0, sizeof s->stats);
+    s->warm_cls = kQpClasses - 1;    // caller-supplied multipliers: any class
     int rc = utility_solve(s);
     spans_collect(s);
     if (rc) return rc;
@@ -842,7 +918,7 @@ int revs_reliability(revs_solver* s, int feeder, int kind, int n_rows, const int
     }
     TRYR(launch_to_time_major(src, fd.n, T, d_Pt, fd.np, s->sU));
     {
-        ContractProblem pb{d_S, fd.np, n_rows, fd.np, d_Pt, fd.np, d_out, T, d_scale};
+        ContractProblem pb{d_S, fd.np, n_rows, fd.np, d_Pt, fd.np, d_out, T, d_scale, nullptr};
         std::vector<ContractTile> tiles;
         const int bm = contract_tile_rows(T);
         for (int r0 = 0; r0 < n_rows; r0 += bm) tiles.push_back(ContractTile{0, r0});
@@ -888,7 +964,7 @@ int revs_contract(int device, int M, int K, int T, const double* A, const double
     TRYC(dalloc(&dC, (size_t)M * T));
     TRYC(cudaMemcpy(dA, Ap.data(), Ap.size() * sizeof(double), cudaMemcpyHostToDevice));
     TRYC(cudaMemcpy(dB, Bt.data(), Bt.size() * sizeof(double), cudaMemcpyHostToDevice));
-    ContractProblem pb{dA, Kp, M, Kp, dB, Kp, dC, T, nullptr};
+    ContractProblem pb{dA, Kp, M, Kp, dB, Kp, dC, T, nullptr, nullptr};
     std::vector<ContractTile> tiles;
     const int bm = contract_tile_rows(T);
     for (int r0 = 0; r0 < M; r0 += bm) tiles.push_back(ContractTile{0, r0});

@@ -333,6 +333,7 @@ __global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
 
     // ------------------------------------------------------------ working set
     int m = 0;
+    bool clean = false;   // step launch that found no violated row: v is still valid if g stays put
     if (P.init) {
         // warm start: rows that carried a multiplier in the previous ADMM iteration
         // (ordered compaction, so the working-set order -- and with it every rounding -- is
@@ -430,6 +431,7 @@ __global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
                 return;
             }
         }
+        clean = (added == 0 && n_viol_left == 0);
         // clear the stored multipliers of the old set; rewritten at the end
         for (int a = tid; a < m_old; a += THREADS) lam_g[widx[a]] = 0.0;
         m += added;
@@ -441,7 +443,8 @@ __global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
     double tau = 1.0;
     int ok = 0, its = 0;
     unsigned n_evals = 0, n_pdas = 0, n_fallback = 0;
-    for (; its < P.inner_max; ++its) {
+    const int inner_max = (P.init == 2) ? 0 : P.inner_max;   // init==2: evaluate the warm start only
+    for (; its < inner_max; ++its) {
         __syncthreads();
         // gradient on W:  u - R[idx_a] . g
         for (int a = warp; a < m; a += THREADS / 32) {
@@ -460,14 +463,24 @@ __global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
         const double kkt = block_max<THREADS>(kk, sm);
         if (kkt < tol) { ok = 1; break; }
 
-        // model Hessian of the current piece on all of W
-        if constexpr (WMAX <= 64) {
-            hessian<WMAX, THREADS, WMAX / (THREADS / 16), WMAX / 16>(R, ld, n, g, m, sm);
-        } else {
-            const int nb = (m + 15) >> 4;
-            if (nb <= 4) hessian<WMAX, THREADS, 4, 4>(R, ld, n, g, m, sm);
-            else if (nb <= 6) hessian<WMAX, THREADS, 6, 6>(R, ld, n, g, m, sm);
-            else hessian<WMAX, THREADS, 8, 8>(R, ld, n, g, m, sm);
+        // model Hessian of the current piece on all of W (register block sized to m)
+        {
+            constexpr int TY = THREADS / 16;
+            const int nq = (m + 15) >> 4, np_ = (m + TY - 1) / TY;
+            (void)nq; (void)np_;
+            if constexpr (WMAX == 32) {            // TY = 8: rows in blocks of 8, columns of 16
+                if (np_ <= 1) hessian<WMAX, THREADS, 1, 1>(R, ld, n, g, m, sm);
+                else if (np_ <= 2) hessian<WMAX, THREADS, 2, 1>(R, ld, n, g, m, sm);
+                else if (np_ <= 3) hessian<WMAX, THREADS, 3, 2>(R, ld, n, g, m, sm);
+                else hessian<WMAX, THREADS, 4, 2>(R, ld, n, g, m, sm);
+            } else {                               // TY = 16
+                if (nq <= 1) hessian<WMAX, THREADS, 1, 1>(R, ld, n, g, m, sm);
+                else if (nq <= 2) hessian<WMAX, THREADS, 2, 2>(R, ld, n, g, m, sm);
+                else if (nq <= 3) hessian<WMAX, THREADS, 3, 3>(R, ld, n, g, m, sm);
+                else if (nq <= 4 || WMAX == 64) hessian<WMAX, THREADS, 4, 4>(R, ld, n, g, m, sm);
+                else if (nq <= 6) hessian<WMAX, THREADS, (WMAX > 64 ? 6 : 4), (WMAX > 64 ? 6 : 4)>(R, ld, n, g, m, sm);
+                else hessian<WMAX, THREADS, (WMAX > 64 ? 8 : 4), (WMAX > 64 ? 8 : 4)>(R, ld, n, g, m, sm);
+            }
         }
         double sc[1] = {0.0};
         for (int a = tid; a < m; a += THREADS) sc[0] += rn2[sm.idx[a]];
@@ -570,11 +583,14 @@ __global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
         lam_g[sm.idx[a]] = sm.lam[a];
         widx[a] = sm.idx[a];
     }
+    // no violated row and the stored iterate already satisfies KKT on W: it is the solution
+    // (g was not touched, so the voltages the violation scan used are its voltages)
+    const bool done = clean && ok && its == 0;
     if (tid == 0) {
         P.wcount[c] = m;
         P.inner_ok[c] = ok;
-        P.status[c] = 0;
-        atomicAdd(P.n_running, 1);
+        P.status[c] = done ? 1 : 0;
+        if (!done) atomicAdd(P.n_running, 1);
         atomicAdd(P.n_cls + CLS, 1);
         atomicAdd(P.newton_its, (unsigned long long)its);
         atomicMax(P.max_ws, m);

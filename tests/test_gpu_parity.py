@@ -208,13 +208,14 @@ def test_admm_multi_feeder_synthetic_96(gpu_lib):
     cost = synthetic_tariff(T)
     kw = dict(kappa=5.0, iter_max=6, vset=1.0, vlow=0.95, vhigh=1.02)
     with gpu_lib.Solver(sizes, T) as s:
-        for f, t in enumerate(trees):
-            s.set_feeder_tree(f, t.parent, t.r, t.res_node)
+        s.set_feeder_trees(trees)                      # one upload + one kernel for all feeders
         s.set_homes(**hm)
         s.set_tariff(cost)
         done = s.solve_admm(**kw)
         out = s.results(done)
         P_est, Gam = s.estimate()
+        for f, t in enumerate(trees):                  # same blocks as the per-feeder entry point
+            drop = s.reliability(f, 2, t.res_node, P=np.eye(len(t.res_node), T))
     Rb = [O.rmat_from_tree(t.parent, t.r)[np.ix_(t.res_node, t.res_node)] for t in trees]
     ref = O.solve_ADMM_arrays(Rb, cost=cost, **_oracle_kwargs(hm), **kw)
     assert np.array_equal(out["P_ev"], ref["P_ev"])
