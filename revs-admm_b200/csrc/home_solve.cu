@@ -85,21 +85,31 @@ __global__ void __launch_bounds__(256) home_solve_kernel(HomeParams P) {
     for (int j = 0; j < SLOTS; ++j) on[j] = false;
     if (nmax <= kSelectRounds) {
         // few charging hours (the usual case): pull the cheapest remaining hour out of the
-        // warp nmax times -- (cost, hour) lexicographic arg-min over 5 shuffle steps
+        // warp nmax times.  Costs become order-preserving 64-bit integer keys, so the
+        // (cost, hour) lexicographic arg-min is three hardware warp reductions (REDUX)
+        // instead of a shuffle tree on doubles.
+        unsigned long long key[SLOTS];
+#pragma unroll
+        for (int j = 0; j < SLOTS; ++j) {
+            const unsigned long long b = (unsigned long long)__double_as_longlong(d[j] + 0.0);   // -0 -> +0
+            key[j] = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+        }
+        const unsigned long long kInf = 0xFFF0000000000000ull;      // key of +inf
         for (int cnt = 0; cnt < nmax; ++cnt) {
-            double best = CUDART_INF;
-            int bt = 0x7fffffff;
+            unsigned long long best = ~0ull;
 #pragma unroll
             for (int j = 0; j < SLOTS; ++j)
-                if (!on[j] && d[j] < best) { best = d[j]; bt = lane + 32 * j; }
+                if (!on[j] && key[j] < best) best = key[j];
+            const unsigned hi = __reduce_min_sync(0xffffffffu, (unsigned)(best >> 32));
+            const unsigned lo = __reduce_min_sync(0xffffffffu, (unsigned)(best >> 32) == hi ? (unsigned)best : 0xffffffffu);
+            const unsigned long long win = ((unsigned long long)hi << 32) | lo;
+            if (win >= kInf) break;                                   // window exhausted
+            if (cnt >= nmin && win >= 0x8000000000000000ull) break;   // optional hours only while cost < 0
+            int myt = 0x7fffffff;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const int ot = __shfl_xor_sync(0xffffffffu, bt, o);
-                if (ob < best || (ob == best && ot < bt)) { best = ob; bt = ot; }
-            }
-            if (!(best < CUDART_INF)) break;                 // window exhausted
-            if (cnt >= nmin && !(best < 0.0)) break;         // optional hours only while they pay
+            for (int j = SLOTS - 1; j >= 0; --j)
+                if (!on[j] && key[j] == win) myt = lane + 32 * j;
+            const int bt = (int)__reduce_min_sync(0xffffffffu, (unsigned)myt);
 #pragma unroll
             for (int j = 0; j < SLOTS; ++j)
                 if (bt == lane + 32 * j) on[j] = true;

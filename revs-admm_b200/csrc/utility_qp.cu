@@ -31,7 +31,7 @@
 
 namespace revs {
 
-constexpr int kJT = 32;                  // columns of R per Hessian tile
+constexpr int kJT = 64;                  // columns of R per Hessian tile
 constexpr int kTld = kJT + 1;
 constexpr double kArcMin = 9.5367431640625e-07;   // 2^-20, shortest line-search step
 constexpr int kPdasMax = 40;             // active-set guesses per quadratic piece
@@ -138,14 +138,19 @@ __device__ void hessian(const double* __restrict__ R, int ld, int n, const doubl
         for (int b = 0; b < NBQ; ++b) acc[a][b] = 0.0;
     // rows beyond m read a zero row of the tile
     constexpr int kRows = (TY * NBP > 16 * NBQ) ? TY * NBP : 16 * NBQ;
-    for (int p = m + warp; p < kRows && p < WMAX; p += THREADS / 32) sm.tileR[p * kTld + lane] = 0.0;
+    for (int p = m + warp; p < kRows && p < WMAX; p += THREADS / 32)
+        for (int l = lane; l < kJT; l += 32) sm.tileR[p * kTld + l] = 0.0;
     for (int j0 = 0; j0 < n; j0 += kJT) {
         __syncthreads();
         for (int p = warp; p < m; p += THREADS / 32) {
-            const int j = j0 + lane;
-            double val = 0.0;
-            if (j < n && g[j] > 0.0) val = R[(size_t)sm.idx[p] * ld + j];
-            sm.tileR[p * kTld + lane] = val;
+            const double* row = R + (size_t)sm.idx[p] * ld;
+#pragma unroll
+            for (int l = lane; l < kJT; l += 32) {
+                const int j = j0 + l;
+                double val = 0.0;
+                if (j < n && g[j] > 0.0) val = row[j];
+                sm.tileR[p * kTld + l] = val;
+            }
         }
         __syncthreads();
 #pragma unroll 4
@@ -603,23 +608,28 @@ __global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
     }
 }
 
+constexpr int kMinB0 = 6, kMinB1 = 3;    // resident CTAs per SM the small / medium instantiations are compiled for
+
 cudaError_t launch_utility_qp(const QpParams& P, int ncols, int cls, cudaStream_t stream) {
     using S0 = QpSmem<32, 128>;
     using S1 = QpSmem<64, 256>;
     using S2 = QpSmem<kWMax, 256>;
+    auto k0 = utility_qp_kernel<32, 128, 0, kMinB0>;
+    auto k1 = utility_qp_kernel<64, 256, 1, kMinB1>;
+    auto k2 = utility_qp_kernel<kWMax, 256, 2, 1>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(utility_qp_kernel<64, 256, 1, 2>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S1));
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(utility_qp_kernel<kWMax, 256, 2, 1>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S2));
+        cudaError_t e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S1));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S2));
+        // many small CTAs per SM: ask for the largest shared-memory carve-out
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k0, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k1, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    if (cls == 0) utility_qp_kernel<32, 128, 0, 4><<<ncols, 128, sizeof(S0), stream>>>(P);
-    else if (cls == 1) utility_qp_kernel<64, 256, 1, 2><<<ncols, 256, sizeof(S1), stream>>>(P);
-    else utility_qp_kernel<kWMax, 256, 2, 1><<<ncols, 256, sizeof(S2), stream>>>(P);
+    if (cls == 0) k0<<<ncols, 128, sizeof(S0), stream>>>(P);
+    else if (cls == 1) k1<<<ncols, 256, sizeof(S1), stream>>>(P);
+    else k2<<<ncols, 256, sizeof(S2), stream>>>(P);
     return cudaGetLastError();
 }
 
