@@ -38,6 +38,16 @@ struct ContractProblem {
 
 struct ContractTile { int problem; int row0; };
 
+// Screening contraction (BF16 in, FP32 out, time-major): V~_f = A_f (M x K) * B_f^T (T x K).
+struct ScreenProblem {
+    const void* A_; int lda; int M; int K;      // __nv_bfloat16
+    const void* Bt_; int64_t ldb;               // __nv_bfloat16, Bt[t*ldb + k]
+    float* out; int64_t ldo;                    // out[t*ldo + m]
+    const int* col_status;                      // optional [T]: columns with status != 0 are skipped
+};
+
+constexpr double kScreenMargin = 0.01;   // rows with v~ <= (1-margin) u are proven feasible (see screen_bf16.cu)
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -63,7 +63,8 @@ struct QpParams {
     const double* z_t;     // [T][Hp]
     double* lam_t;         // [T][Hp]   multipliers (dense storage, sparse content)
     double* g_t;           // [T][Hp]   out: projection = P_est[k+1]
-    const double* v_t;     // [T][Hp]   in (step mode): R g of the stored iterate
+    double* v_t;           // [T][Hp]   in (step mode): R g of the stored iterate
+    const float* v32_t;    // optional [T][Hp]: BF16-screened voltages; v_t is then filled here (exact for candidates)
     int* wcount;           // [ncols]
     int* widx;             // [ncols][kWMax]
     int* status;           // [ncols] 0 running, 1 converged, 2 working set overflow
@@ -74,7 +75,7 @@ struct QpParams {
     int* n_failed;         // columns whose working set overflowed kWMax
     int* cls;              // [ncols] instantiation that owns the column (see qp_class_cap)
     int* n_cls;            // [kQpClasses] running columns per class after this round
-    unsigned long long* dbg;  // optional [4]: arc evaluations, LM retries, max Newton steps, max evaluations
+    unsigned long long* dbg;  // optional [4 + 5*kQpClasses]: counts, then per-class phase cycles
     int T;
     int64_t Hp;
     double u, tol;
@@ -88,6 +89,12 @@ cudaError_t launch_utility_qp(const QpParams& P, int ncols, int cls, cudaStream_
 int contract_tile_rows(int T);
 cudaError_t launch_contract(const ContractProblem* d_problems, const ContractTile* d_tiles, int n_tiles,
                             int T, int mode, double v2, cudaStream_t stream);
+
+// ---- screen_bf16.cu
+int screen_tile_rows();
+cudaError_t launch_to_bf16(const double* in, void* out, size_t n, cudaStream_t s);
+cudaError_t launch_screen(const ScreenProblem* d_problems, const ContractTile* d_tiles, int n_tiles, int T,
+                          cudaStream_t stream);
 
 // ---- feeder_build.cu
 cudaError_t launch_sens_voltage(const int* parent, const double* cumr, const int* row_node,

@@ -60,7 +60,7 @@ struct Counters {
     int infeasible;
     int max_ws;
     unsigned long long newton_its;
-    unsigned long long dbg[4];
+    unsigned long long dbg[4 + 5 * kQpClasses];
     ResidualOut res;
 };
 
@@ -88,10 +88,17 @@ struct revs_solver {
     FeederDev* d_feeders = nullptr;
     double* d_Rpool = nullptr;
     double* d_rn2 = nullptr;
+    void *d_Rbf = nullptr, *d_gbf = nullptr;   // BF16 copies for the screening contraction
+    float* d_v32 = nullptr;
+    ScreenProblem* d_sprob = nullptr;
+    ContractTile* d_stiles = nullptr;
+    int n_stiles = 0;
+    bool screen = true;                        // BF16 screening + exact recheck instead of the FP64 contraction in the loop
     int *d_pool_parent = nullptr, *d_pool_res = nullptr;   // revs_set_feeder_trees
     double* d_pool_cumr = nullptr;
     int64_t* d_pool_off = nullptr;
     size_t pool_nodes = 0;
+    size_t Rpool_elems = 0;
     bool rn2_valid = false;
     // home-major [Hp][T]
     double *d_load = nullptr, *d_pest = nullptr, *d_psch[2] = {nullptr, nullptr}, *d_gamma = nullptr,
@@ -111,6 +118,8 @@ struct revs_solver {
     ContractTile* d_ctiles = nullptr;
     int n_ctiles = 0;
     cudaStream_t sU = nullptr, sH = nullptr;
+    cudaStream_t sQ[kQpClasses] = {};          // the larger QP classes run beside class 0
+    cudaEvent_t evV = nullptr, evQ[kQpClasses] = {};
     cudaEvent_t evHomeDone = nullptr, evDualDone = nullptr, evT0 = nullptr, evT1 = nullptr;
     std::vector<TimedSpan> spans;
     size_t span_used = 0;
@@ -231,13 +240,15 @@ int utility_solve(revs_solver* s) {
     Q.rn2 = s->d_rn2;
     if (!s->rn2_valid) {
         CU(launch_row_norms(s->d_feeders, s->nf, s->d_Rpool, s->d_rn2, s->sU));
+        CU(launch_to_bf16(s->d_Rpool, s->d_Rbf, s->Rpool_elems, s->sU));
         s->rn2_valid = true;
-        s->stats.kernel_launches++;
+        s->stats.kernel_launches += 2;
     }
     Q.z_t = s->d_zt;
     Q.lam_t = s->d_lamt;
     Q.g_t = s->d_gt;
     Q.v_t = s->d_vt;
+    Q.v32_t = s->screen ? s->d_v32 : nullptr;
     Q.wcount = s->d_wcount;
     Q.widx = s->d_widx;
     Q.status = s->d_status;
@@ -277,18 +288,35 @@ int utility_solve(revs_solver* s) {
             return fail(REVS_ERR_NOCONV, "utility QP: %d columns still running after %d working-set rounds",
                         s->h_cnt->n_running, round);
         sp = span_begin(s, round == 0 ? 5 : 0, s->sU);   // round 0: every column is running
-        CU(launch_contract(s->d_cprob, s->d_ctiles, s->n_ctiles, s->T, kOutTimeMajor, 0.0, s->sU));
+        if (s->screen) {
+            CU(launch_to_bf16(s->d_gt, s->d_gbf, (size_t)s->Hp * s->T, s->sU));
+            CU(launch_screen(s->d_sprob, s->d_stiles, s->n_stiles, s->T, s->sU));
+            s->stats.kernel_launches++;
+        } else {
+            CU(launch_contract(s->d_cprob, s->d_ctiles, s->n_ctiles, s->T, kOutTimeMajor, 0.0, s->sU));
+        }
         span_end(sp, s->sU);
         s->stats.kernel_launches++;
         if (round == 0) s->stats.gemm_full_launches++;
         CU(cudaMemsetAsync(&s->d_cnt->n_running, 0, (1 + kQpClasses) * sizeof(int), s->sU));
-        for (int cl = 0; cl < kQpClasses; ++cl) {
+        // the larger classes go first, each on its own stream, so that their long CTAs
+        // overlap with the many short ones of class 0
+        CU(cudaEventRecord(s->evV, s->sU));
+        for (int cl = kQpClasses - 1; cl >= 1; --cl) {
             if (!use[cl]) continue;
-            sp = span_begin(s, cl == 0 ? 3 : 4, s->sU);
-            CU(launch_utility_qp(Q, s->ncols, cl, s->sU));
-            span_end(sp, s->sU);
+            CU(cudaStreamWaitEvent(s->sQ[cl], s->evV, 0));
+            sp = span_begin(s, 4, s->sQ[cl]);
+            CU(launch_utility_qp(Q, s->ncols, cl, s->sQ[cl]));
+            span_end(sp, s->sQ[cl]);
+            CU(cudaEventRecord(s->evQ[cl], s->sQ[cl]));
             s->stats.kernel_launches++;
         }
+        sp = span_begin(s, 3, s->sU);
+        CU(launch_utility_qp(Q, s->ncols, 0, s->sU));
+        span_end(sp, s->sU);
+        s->stats.kernel_launches++;
+        for (int cl = 1; cl < kQpClasses; ++cl)
+            if (use[cl]) CU(cudaStreamWaitEvent(s->sU, s->evQ[cl], 0));
         s->stats.gemm_launches++;
         s->stats.qp_outer_iterations++;
         CU(cudaMemcpyAsync(s->h_cnt, s->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, s->sU));
@@ -311,6 +339,12 @@ int utility_solve(revs_solver* s) {
         }
     }
     s->warm_cls = top_cls;
+    if (getenv("REVS_DEBUG") && s->k == s->iter_max - 1)
+        for (int cl = 0; cl < kQpClasses; ++cl) {
+            const unsigned long long* p = s->h_cnt->dbg + 4 + 5 * cl;
+            fprintf(stderr, "[revs] class %d phase Mcycles: grad+kkt %.1f hessian %.1f pdas %.1f search %.1f final-eval %.1f\n", cl,
+                    p[0] * 1e-6, p[1] * 1e-6, p[2] * 1e-6, p[3] * 1e-6, p[4] * 1e-6);
+        }
     return REVS_OK;
 }
 
@@ -340,7 +374,7 @@ HomeParams home_params(revs_solver* s, int individual) {
 
 void free_all(revs_solver* s) {
     cudaSetDevice(s->device);
-    void* ptrs[] = {s->d_feeders, s->d_Rpool, s->d_rn2, s->d_pool_parent, s->d_pool_res, s->d_pool_cumr, s->d_pool_off, s->d_load, s->d_pest, s->d_psch[0], s->d_psch[1], s->d_gamma,
+    void* ptrs[] = {s->d_feeders, s->d_Rpool, s->d_rn2, s->d_Rbf, s->d_gbf, s->d_v32, s->d_sprob, s->d_stiles, s->d_pool_parent, s->d_pool_res, s->d_pool_cumr, s->d_pool_off, s->d_load, s->d_pest, s->d_psch[0], s->d_psch[1], s->d_gamma,
                     s->d_pev, s->d_soc, s->d_has_ev, s->d_rating, s->d_capacity, s->d_initial, s->d_indconst,
                     s->d_start, s->d_end, s->d_nmin, s->d_nmax, s->d_zero_i, s->d_cost, s->d_zt, s->d_lamt,
                     s->d_gt, s->d_vt, s->d_wcount, s->d_widx, s->d_status, s->d_innerok, s->d_cls, s->d_cnt, s->d_diff,
@@ -359,6 +393,11 @@ void free_all(revs_solver* s) {
     if (s->evDualDone) cudaEventDestroy(s->evDualDone);
     if (s->evT0) cudaEventDestroy(s->evT0);
     if (s->evT1) cudaEventDestroy(s->evT1);
+    if (s->evV) cudaEventDestroy(s->evV);
+    for (int cl = 1; cl < kQpClasses; ++cl) {
+        if (s->evQ[cl]) cudaEventDestroy(s->evQ[cl]);
+        if (s->sQ[cl]) cudaStreamDestroy(s->sQ[cl]);
+    }
     if (s->sU) cudaStreamDestroy(s->sU);
     if (s->sH) cudaStreamDestroy(s->sH);
 }
@@ -421,6 +460,11 @@ int revs_create(revs_solver** out, int device, int n_feeders, const int64_t* fee
     } while (0)
     TRY(cudaStreamCreateWithFlags(&s->sU, cudaStreamNonBlocking));
     TRY(cudaStreamCreateWithFlags(&s->sH, cudaStreamNonBlocking));
+    TRY(cudaEventCreateWithFlags(&s->evV, cudaEventDisableTiming));
+    for (int cl = 1; cl < kQpClasses; ++cl) {
+        TRY(cudaStreamCreateWithFlags(&s->sQ[cl], cudaStreamNonBlocking));
+        TRY(cudaEventCreateWithFlags(&s->evQ[cl], cudaEventDisableTiming));
+    }
     TRY(cudaEventCreateWithFlags(&s->evHomeDone, cudaEventDisableTiming));
     TRY(cudaEventCreateWithFlags(&s->evDualDone, cudaEventDisableTiming));
     TRY(cudaEventCreate(&s->evT0));
@@ -429,6 +473,13 @@ int revs_create(revs_solver** out, int device, int n_feeders, const int64_t* fee
     TRY(cudaMemcpy(s->d_feeders, s->feeders.data(), sizeof(FeederDev) * n_feeders, cudaMemcpyHostToDevice));
     TRY(dalloc(&s->d_Rpool, (size_t)rp));
     TRY(dalloc(&s->d_rn2, (size_t)hp));
+    s->Rpool_elems = (size_t)rp;
+    TRY(cudaMalloc(&s->d_Rbf, (size_t)(rp ? rp : 1) * 2));
+    TRY(cudaMemset(s->d_Rbf, 0, (size_t)(rp ? rp : 1) * 2));
+    TRY(cudaMalloc(&s->d_gbf, HT * 2));
+    TRY(cudaMemset(s->d_gbf, 0, HT * 2));
+    TRY(dalloc(&s->d_v32, HT));
+    if (getenv("REVS_EXACT_GEMM")) s->screen = false;
     TRY(dalloc(&s->d_load, HT));
     TRY(dalloc(&s->d_pest, HT));
     TRY(dalloc(&s->d_psch[0], HT));
@@ -469,6 +520,23 @@ int revs_create(revs_solver** out, int device, int n_feeders, const int64_t* fee
         probs[f] = ContractProblem{s->d_Rpool + fd.roff, fd.np, fd.np, fd.np, s->d_gt + fd.off, hp,
                                    s->d_vt + fd.off, hp, nullptr, s->d_status + (size_t)f * T};
         for (int r0 = 0; r0 < fd.np; r0 += bm) tiles.push_back(ContractTile{f, r0});
+    }
+    {   // screening table: same products in BF16 -> FP32
+        std::vector<ScreenProblem> sp(n_feeders);
+        std::vector<ContractTile> st;
+        const int sbm = screen_tile_rows();
+        for (int f = 0; f < n_feeders; ++f) {
+            const FeederDev& fd = s->feeders[f];
+            sp[f] = ScreenProblem{(const char*)s->d_Rbf + 2 * fd.roff, fd.np, fd.np, fd.np,
+                                  (const char*)s->d_gbf + 2 * fd.off, hp, s->d_v32 + fd.off, hp,
+                                  s->d_status + (size_t)f * T};
+            for (int r0 = 0; r0 < fd.np; r0 += sbm) st.push_back(ContractTile{f, r0});
+        }
+        s->n_stiles = (int)st.size();
+        TRY(dalloc(&s->d_sprob, sp.size()));
+        TRY(cudaMemcpy(s->d_sprob, sp.data(), sp.size() * sizeof(ScreenProblem), cudaMemcpyHostToDevice));
+        TRY(dalloc(&s->d_stiles, st.size()));
+        TRY(cudaMemcpy(s->d_stiles, st.data(), st.size() * sizeof(ContractTile), cudaMemcpyHostToDevice));
     }
     s->n_ctiles = (int)tiles.size();
     TRY(dalloc(&s->d_cprob, probs.size()));

@@ -34,6 +34,8 @@ namespace revs {
 constexpr int kJT = 64;                  // columns of R per Hessian tile
 constexpr int kTld = kJT + 1;
 constexpr double kArcMin = 9.5367431640625e-07;   // 2^-20, shortest line-search step
+constexpr int kChgMax = 128;             // most sign changes handled by a rank update of H
+constexpr int kMaskWords = 512;          // feeders up to 16384 residences keep a mask of F
 constexpr int kPdasMax = 40;             // active-set guesses per quadratic piece
 constexpr double kHessShift = 1e-12;     // relative diagonal shift of the model Hessian
 
@@ -50,6 +52,8 @@ struct QpSmem {
     double red[3 * (THREADS / 32)];
     double bcast[2];
     int idx[WMAX], fl[WMAX], inA[WMAX];
+    int chg[kChgMax];                     // homes that changed side of g>0 (index*2 + left)
+    unsigned fmask[kMaskWords];           // F the stored Hessian was formed for
     int ired[THREADS / 32];
     int ibcast[2];
 };
@@ -123,11 +127,16 @@ __device__ double eval_phi(const double* __restrict__ R, int ld, int n, const do
     return 0.5 * acc[0] + u * acc[1];
 }
 
-// H[p][q] = sum_{j: g_j>0} R[idx_p][j] R[idx_q][j] over the m working rows -> lower triangle
-// of Hb and hdiag.  Threads form a 16 x (THREADS/16) grid; thread (tx,ty) owns rows
-// ty + TY*a, columns tx + 16*b, a < NBP, b < NBQ.
-template <int WMAX, int THREADS, int NBP, int NBQ, class S>
-__device__ void hessian(const double* __restrict__ R, int ld, int n, const double* g, int m, S& sm) {
+// Model Hessian H[p][q] = sum_{j in F} R[idx_p][j] R[idx_q][j] over the m working rows, F =
+// homes with g>0 -> lower triangle of Hb and hdiag.  Threads form a 16 x (THREADS/16) grid;
+// thread (tx,ty) owns rows ty + TY*a, columns tx + 16*b, a < NBP, b < NBQ; blocks that lie
+// strictly above the diagonal are not computed.
+//   INCR = false: from scratch, streaming all n columns of the working rows (coalesced).
+//   INCR = true : rank-|list| correction  H += sum_c sgn_c r_c r_c^T  for the homes that
+//                 entered (+) or left (-) F since H was last formed (chg list in smem).
+// Either way sm.fmask ends up holding the bit mask of F the stored H corresponds to.
+template <int WMAX, int THREADS, int NBP, int NBQ, bool INCR, class S>
+__device__ void hessian(const double* __restrict__ R, int ld, int n, const double* g, int m, int nchg, S& sm) {
     constexpr int TY = THREADS / 16;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx = tid & 15, ty = tid >> 4;
@@ -140,30 +149,38 @@ __device__ void hessian(const double* __restrict__ R, int ld, int n, const doubl
     constexpr int kRows = (TY * NBP > 16 * NBQ) ? TY * NBP : 16 * NBQ;
     for (int p = m + warp; p < kRows && p < WMAX; p += THREADS / 32)
         for (int l = lane; l < kJT; l += 32) sm.tileR[p * kTld + l] = 0.0;
-    for (int j0 = 0; j0 < n; j0 += kJT) {
+    const int total = INCR ? nchg : n;
+    for (int j0 = 0; j0 < total; j0 += kJT) {
         __syncthreads();
         for (int p = warp; p < m; p += THREADS / 32) {
             const double* row = R + (size_t)sm.idx[p] * ld;
 #pragma unroll
             for (int l = lane; l < kJT; l += 32) {
-                const int j = j0 + l;
+                const int c = j0 + l;
                 double val = 0.0;
-                if (j < n && g[j] > 0.0) val = row[j];
+                if (INCR) {
+                    if (c < nchg) val = row[sm.chg[c] >> 1];
+                } else {
+                    if (c < n && g[c] > 0.0) val = row[c];
+                }
                 sm.tileR[p * kTld + l] = val;
             }
         }
         __syncthreads();
+        const int jmax = min(kJT, total - j0);
 #pragma unroll 4
-        for (int jj = 0; jj < kJT; ++jj) {
+        for (int jj = 0; jj < jmax; ++jj) {
             double pa[NBP], qb[NBQ];
+            const double sg = INCR ? ((sm.chg[j0 + jj] & 1) ? -1.0 : 1.0) : 1.0;
 #pragma unroll
-            for (int a = 0; a < NBP; ++a) pa[a] = sm.tileR[(ty + TY * a) * kTld + jj];
+            for (int a = 0; a < NBP; ++a) pa[a] = sm.tileR[(ty + TY * a) * kTld + jj] * sg;
 #pragma unroll
             for (int b = 0; b < NBQ; ++b) qb[b] = sm.tileR[(tx + 16 * b) * kTld + jj];
 #pragma unroll
             for (int a = 0; a < NBP; ++a)
 #pragma unroll
-                for (int b = 0; b < NBQ; ++b) acc[a][b] = fma(pa[a], qb[b], acc[a][b]);
+                for (int b = 0; b < NBQ; ++b)
+                    if (TY * (a + 1) > 16 * b) acc[a][b] = fma(pa[a], qb[b], acc[a][b]);
         }
     }
     __syncthreads();
@@ -173,11 +190,50 @@ __device__ void hessian(const double* __restrict__ R, int ld, int n, const doubl
         for (int b = 0; b < NBQ; ++b) {
             const int p = ty + TY * a, q = tx + 16 * b;
             if (p < m && q < m) {
-                if (p > q) sm.Hb[p * (WMAX + 1) + q] = acc[a][b];
-                else if (p == q) sm.hdiag[p] = acc[a][b];
+                if (INCR) {
+                    if (p > q) sm.Hb[p * (WMAX + 1) + q] += acc[a][b];
+                    else if (p == q) sm.hdiag[p] += acc[a][b];
+                } else {
+                    if (p > q) sm.Hb[p * (WMAX + 1) + q] = acc[a][b];
+                    else if (p == q) sm.hdiag[p] = acc[a][b];
+                }
             }
         }
     __syncthreads();
+}
+
+// Compare F = {g>0} with the mask the stored H was formed for.  Returns the number of homes
+// that changed side (their indices*2+left? in sm.chg, ordered), or -1 if there are more than
+// kChgMax (the caller then recomputes H from scratch).  Updates the mask.
+template <int THREADS, class S>
+__device__ int mask_changes(const double* g, int n, S& sm) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int base = 0;
+    bool overflow = false;
+    for (int j0 = 0; j0 < n; j0 += THREADS) {
+        const int j = j0 + tid;
+        const bool now = j < n && g[j] > 0.0;
+        const unsigned bal_now = __ballot_sync(0xffffffffu, now);
+        const unsigned old = (j0 + warp * 32 < n) ? sm.fmask[(j0 >> 5) + warp] : 0u;
+        const unsigned diff = bal_now ^ old;
+        __syncthreads();
+        if (lane == 0) { sm.ired[warp] = __popc(diff); if (j0 + warp * 32 < n) sm.fmask[(j0 >> 5) + warp] = bal_now; }
+        __syncthreads();
+        int before = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < THREADS / 32; ++w) {
+            before += (w < warp) ? sm.ired[w] : 0;
+            tot += sm.ired[w];
+        }
+        if ((diff >> lane) & 1u) {
+            const int pos = base + before + __popc(diff & ((1u << lane) - 1));
+            if (pos < kChgMax) sm.chg[pos] = (j << 1) | (now ? 0 : 1);     // low bit: left F
+        }
+        base += tot;
+        if (base > kChgMax) overflow = true;
+    }
+    __syncthreads();
+    return overflow ? -1 : base;
 }
 
 // ---- dense SPD solves in shared memory on a principal sub-matrix of H.  The factor lives
@@ -331,7 +387,7 @@ __global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
     const double* z = P.z_t + col;
     double* lam_g = P.lam_t + col;
     double* g = P.g_t + col;
-    const double* v = P.v_t + col;
+    double* v = P.v_t + col;
     const double u = P.u, tol = P.tol;
     const double* rn2 = P.rn2 + fd.off;
     int* widx = P.widx + (size_t)c * kWMax;
@@ -373,6 +429,31 @@ __global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
         }
         m = min(base, WMAX);
     } else {
+        if (P.v32_t) {
+            // Voltages came from the BF16 screening pass: rows at or below (1-margin) u are
+            // proven feasible; every other row without a multiplier is a candidate whose
+            // voltage is recomputed here exactly (FP64 row of R times g), one warp per row.
+            const float* v32 = P.v32_t + col;
+            const double thr = (1.0 - kScreenMargin) * u;
+            for (int j0 = 0; j0 < n; j0 += THREADS) {
+                const int j = j0 + tid;
+                const float a = j < n ? v32[j] : 0.f;
+                const bool cand = j < n && (double)a > thr && !(lam_g[j] > 0.0);
+                if (j < n && !cand) v[j] = (double)a;
+                unsigned bal = __ballot_sync(0xffffffffu, cand);
+                while (bal) {
+                    const int bit = __ffs(bal) - 1;
+                    bal &= bal - 1;
+                    const int row_i = j0 + warp * 32 + bit;
+                    const double* row = R + (size_t)row_i * ld;
+                    double acc = 0.0;
+                    for (int k = lane; k < n; k += 32) acc = fma(row[k], g[k], acc);
+                    acc = warp_sum(acc);
+                    if (lane == 0) v[row_i] = acc;
+                }
+            }
+            __syncthreads();
+        }
         const int m_old = P.wcount[c];
         // keep rows with a positive multiplier (serial compaction keeps the order stable)
         if (tid == 0) {
@@ -448,6 +529,9 @@ __global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
     double tau = 1.0;
     int ok = 0, its = 0;
     unsigned n_evals = 0, n_pdas = 0, n_fallback = 0;
+    bool have_H = false;   // Hb/hdiag hold the Hessian for the mask in sm.fmask
+    long long tc[5] = {0, 0, 0, 0, 0}, t0 = clock64(), t1;   // phase cycles (debug)
+#define PHASE(i) do { t1 = clock64(); tc[i] += t1 - t0; t0 = t1; } while (0)
     const int inner_max = (P.init == 2) ? 0 : P.inner_max;   // init==2: evaluate the warm start only
     for (; its < inner_max; ++its) {
         __syncthreads();
@@ -466,27 +550,47 @@ __global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
             kk = fmax(kk, fabs(sm.lam[a] > 0.0 ? gr : fmin(gr, 0.0)));
         }
         const double kkt = block_max<THREADS>(kk, sm);
+        PHASE(0);
         if (kkt < tol) { ok = 1; break; }
 
-        // model Hessian of the current piece on all of W (register block sized to m)
+        // model Hessian of the current piece on all of W (register block sized to m): from
+        // scratch on the first piece of a launch, afterwards a rank update for the few homes
+        // that crossed g = 0
         {
+            int nchg = -1;
+            if (n <= kMaskWords * 32) {
+                if (have_H) nchg = mask_changes<THREADS>(g, n, sm);
+                else {
+                    for (int w = tid; w < (n + 31) / 32; w += THREADS) sm.fmask[w] = 0u;
+                    __syncthreads();
+                    (void)mask_changes<THREADS>(g, n, sm);       // records F; H is formed below
+                }
+            }
             constexpr int TY = THREADS / 16;
             const int nq = (m + 15) >> 4, np_ = (m + TY - 1) / TY;
             (void)nq; (void)np_;
+#define HESS(NP, NQ)                                                                          \
+    do {                                                                                      \
+        if (have_H && nchg >= 0) { if (nchg > 0) hessian<WMAX, THREADS, NP, NQ, true>(R, ld, n, g, m, nchg, sm); } \
+        else hessian<WMAX, THREADS, NP, NQ, false>(R, ld, n, g, m, 0, sm);                     \
+    } while (0)
             if constexpr (WMAX == 32) {            // TY = 8: rows in blocks of 8, columns of 16
-                if (np_ <= 1) hessian<WMAX, THREADS, 1, 1>(R, ld, n, g, m, sm);
-                else if (np_ <= 2) hessian<WMAX, THREADS, 2, 1>(R, ld, n, g, m, sm);
-                else if (np_ <= 3) hessian<WMAX, THREADS, 3, 2>(R, ld, n, g, m, sm);
-                else hessian<WMAX, THREADS, 4, 2>(R, ld, n, g, m, sm);
+                if (np_ <= 1) HESS(1, 1);
+                else if (np_ <= 2) HESS(2, 1);
+                else if (np_ <= 3) HESS(3, 2);
+                else HESS(4, 2);
             } else {                               // TY = 16
-                if (nq <= 1) hessian<WMAX, THREADS, 1, 1>(R, ld, n, g, m, sm);
-                else if (nq <= 2) hessian<WMAX, THREADS, 2, 2>(R, ld, n, g, m, sm);
-                else if (nq <= 3) hessian<WMAX, THREADS, 3, 3>(R, ld, n, g, m, sm);
-                else if (nq <= 4 || WMAX == 64) hessian<WMAX, THREADS, 4, 4>(R, ld, n, g, m, sm);
-                else if (nq <= 6) hessian<WMAX, THREADS, (WMAX > 64 ? 6 : 4), (WMAX > 64 ? 6 : 4)>(R, ld, n, g, m, sm);
-                else hessian<WMAX, THREADS, (WMAX > 64 ? 8 : 4), (WMAX > 64 ? 8 : 4)>(R, ld, n, g, m, sm);
+                if (nq <= 1) HESS(1, 1);
+                else if (nq <= 2) HESS(2, 2);
+                else if (nq <= 3) HESS(3, 3);
+                else if (nq <= 4 || WMAX == 64) HESS(4, 4);
+                else if (nq <= 6) HESS((WMAX > 64 ? 6 : 4), (WMAX > 64 ? 6 : 4));
+                else HESS((WMAX > 64 ? 8 : 4), (WMAX > 64 ? 8 : 4));
             }
+#undef HESS
+            have_H = true;
         }
+        PHASE(1);
         double sc[1] = {0.0};
         for (int a = tid; a < m; a += THREADS) sc[0] += rn2[sm.idx[a]];
         block_sum<1, THREADS>(sc, sm);
@@ -527,6 +631,7 @@ __global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
             if (block_count<THREADS>(bad, sm) == 0) { pdas_ok = true; break; }
         }
 
+        PHASE(2);
         double alpha = 1.0, phin = phi;
         bool stepped = false;
         if (pdas_ok) {
@@ -576,10 +681,12 @@ __global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
             }
             if (alpha == 1.0) tau = fmax(1.0, tau / 10.0);
         }
+        PHASE(3);
         __syncthreads();
         for (int a = tid; a < m; a += THREADS) sm.lam[a] = sm.trial[a];
         __syncthreads();
         phi = eval_phi<THREADS>(R, ld, n, z, sm.idx, sm.lam, m, u, g, sm);
+        PHASE(4);
     }
 
     // ------------------------------------------------------------ persist
@@ -604,6 +711,7 @@ __global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
             atomicAdd(P.dbg + 1, (unsigned long long)n_pdas);
             atomicMax(P.dbg + 2, (unsigned long long)its);
             atomicAdd(P.dbg + 3, (unsigned long long)n_fallback);
+            for (int i = 0; i < 5; ++i) atomicAdd(P.dbg + 4 + 5 * CLS + i, (unsigned long long)tc[i]);
         }
     }
 }
