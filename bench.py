@@ -215,7 +215,7 @@ def run_gpu(args, rank, world, local_rank):
         s.set_tariff(cost_p)
 
     upload()
-    stats_acc = {k: 0.0 for k in ("gemm_ms", "gemm_full_ms", "gemm_full_launches", "home_ms", "dual_ms", "qp_ms", "qp_big_ms", "total_ms", "kernel_launches",
+    stats_acc = {k: 0.0 for k in ("gemm_ms", "gemm_full_ms", "gemm_full_launches", "home_ms", "dual_ms", "qp_ms", "qp_big_ms", "qp_flops", "total_ms", "kernel_launches",
                                   "gemm_launches", "qp_outer_iterations", "qp_newton_iterations")}
     # ---- device-resident leg ("value")
     for _ in range(args.warmup):
@@ -261,50 +261,75 @@ def run_gpu(args, rank, world, local_rank):
 
     # ---- per-kernel achieved rates (CUDA-event spans inside the library, timed region only)
     hbm_peak, peak_src = measured_peaks()
+    bf16_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained", 1346.3) \
+        if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1400.0
     iters = ADMM["iter_max"] * args.steps
     ev_frac = float(hm["has_ev"].mean())
+    window = float(np.mean((hm["end"] - hm["start"])[hm["has_ev"] > 0])) / T if ev_frac > 0 else 0.0
     n_p = [(n + 15) // 16 * 16 for n in sizes]
     Hp = sum(n_p)
-    home_bytes = Hp * T * (ev_frac * 48 + (1 - ev_frac) * 24)          # per launch, DESIGN.md kernel table
+    # DESIGN.md kernel table: EV home reads load + (P_est,P_sch,Gamma inside the plug-in window), writes P_sch',P_ev
+    home_bytes = Hp * T * (ev_frac * (8 + 24 * window + 16) + (1 - ev_frac) * 24)
     dual_bytes = Hp * T * 56
     gemm_flops = sum(2.0 * n * n * T for n in n_p)
-    gemm_bytes = sum(8.0 * n * n + 16.0 * n * T for n in n_p)
+    f64_peak = fp64_gemm_peak_tflops() if rank == 0 else 0.0
     kernels = {}
     if stats_acc["home_ms"] > 0:
         ms = stats_acc["home_ms"] / iters
         kernels["home_solve"] = {"bound": "hbm", "ms_per_launch": ms, "achieved": home_bytes / (ms * 1e-3) / 1e9,
-                                 "peak": hbm_peak, "unit": "GB/s"}
+                                 "peak": hbm_peak, "unit": "GB/s", "bytes_per_launch": home_bytes}
     if stats_acc["dual_ms"] > 0:
         ms = stats_acc["dual_ms"] / iters
         kernels["dual_update"] = {"bound": "hbm", "ms_per_launch": ms, "achieved": dual_bytes / (ms * 1e-3) / 1e9,
-                                  "peak": hbm_peak, "unit": "GB/s"}
-    f64_peak = fp64_gemm_peak_tflops() if rank == 0 else 0.0
+                                  "peak": hbm_peak, "unit": "GB/s", "bytes_per_launch": dual_bytes}
     if stats_acc["gemm_full_launches"] > 0:
-        ms = stats_acc["gemm_full_ms"] / stats_acc["gemm_full_launches"]   # launches over all columns only
-        kernels["contract_f64"] = {"bound": "tensor", "ms_per_launch": ms, "achieved": gemm_flops / (ms * 1e-3) / 1e12,
-                                   "peak": f64_peak, "unit": "TFLOP/s", "hbm_gbs": gemm_bytes / (ms * 1e-3) / 1e9,
-                                   "peak_source": "cuBLAS DGEMM 6144^3 measured in this run",
-                                   "launches_per_step": stats_acc["gemm_launches"] / args.steps,
-                                   "ms_total_per_step": stats_acc["gemm_ms"] / args.steps}
+        # in-loop voltage check over ALL columns: BF16 screening contraction (+ fp64->bf16 cast of g)
+        ms = stats_acc["gemm_full_ms"] / stats_acc["gemm_full_launches"]
+        sbytes = sum(2.0 * n * n for n in n_p) + Hp * T * (8 + 2 + 2 + 4)
+        kernels["screen_bf16"] = {"bound": "hbm", "ms_per_launch": ms, "achieved": sbytes / (ms * 1e-3) / 1e9,
+                                  "peak": hbm_peak, "unit": "GB/s", "tflops": gemm_flops / (ms * 1e-3) / 1e12,
+                                  "tensor_peak_tflops": bf16_peak, "bytes_per_launch": sbytes,
+                                  "launches_per_step": stats_acc["gemm_launches"] / args.steps,
+                                  "ms_total_per_step": stats_acc["gemm_ms"] / args.steps}
+    qp_flops = stats_acc["qp_flops"]
     if stats_acc["qp_ms"] > 0:
-        kernels["utility_qp"] = {"bound": "latency/fp64", "ms_total": stats_acc["qp_ms"] / args.steps,
-                                 "ms_big_instantiation": stats_acc["qp_big_ms"] / args.steps,
-                                 "launches_per_step": (stats_acc["gemm_launches"] / args.steps) + ADMM["iter_max"]}
+        # spans of the three working-set classes overlap (separate streams): wall share is total - rest
+        rest = stats_acc["gemm_ms"] + stats_acc["dual_ms"]
+        qp_wall = max(stats_acc["total_ms"] - rest, 1e-9)
+        kernels["utility_qp"] = {"bound": "tensor", "note": "FP64 FMA pipe; latency/occupancy-bound, see profiles/",
+                                 "ms_wall_per_step": qp_wall / args.steps,
+                                 "achieved": qp_flops / (qp_wall * 1e-3) / 1e12, "peak": f64_peak, "unit": "TFLOP/s",
+                                 "flops_per_step": qp_flops / args.steps,
+                                 "ms_sum_of_class_spans": stats_acc["qp_ms"] / args.steps,
+                                 "ms_classes_ge_33_rows": stats_acc["qp_big_ms"] / args.steps}
+    # FP64 DMMA contraction (reliability check / exact mode): one extra solve outside the timed region
+    if rank == 0:
+        s.set_option("screen", 0)
+        s.solve_admm(**ADMM)
+        st = s.stats()
+        s.set_option("screen", 1)
+        if st["gemm_full_launches"] > 0:
+            ms = st["gemm_full_ms"] / st["gemm_full_launches"]
+            kernels["contract_f64"] = {"bound": "tensor", "ms_per_launch": ms, "achieved": gemm_flops / (ms * 1e-3) / 1e12,
+                                       "peak": f64_peak, "unit": "TFLOP/s",
+                                       "peak_source": "cuBLAS DGEMM 6144^3 measured in this run",
+                                       "note": "exact mode (screen=0), measured outside the timed region",
+                                       "ms_per_step_exact_mode": st["total_ms"]}
     for k in kernels.values():
         if "peak" in k and k["peak"]:
             k["frac"] = k["achieved"] / k["peak"]
-    share = {k: stats_acc[k] / max(stats_acc["total_ms"], 1e-9) for k in ("gemm_ms", "home_ms", "dual_ms", "qp_ms")}
-    dominant = max(share, key=share.get)
-    dom_name = {"gemm_ms": "contract_f64", "home_ms": "home_solve", "dual_ms": "dual_update", "qp_ms": "utility_qp"}[dominant]
-    # the roofline object: the contraction is the kernel whose bound is a hardware peak of the
-    # step's arithmetic (the QP kernel's time is reported beside it in `kernels`/`share`)
-    roof_k = kernels.get("contract_f64") if dom_name in ("utility_qp", "contract_f64") else kernels.get(dom_name)
+    tot = max(stats_acc["total_ms"], 1e-9)
+    share = {"screen_bf16": stats_acc["gemm_ms"] / tot, "home_solve(overlapped)": stats_acc["home_ms"] / tot,
+             "dual_update": stats_acc["dual_ms"] / tot,
+             "utility_qp": 1.0 - (stats_acc["gemm_ms"] + stats_acc["dual_ms"]) / tot}
+    dom_name = "utility_qp"
+    roof_k = kernels.get("utility_qp")
     roofline = None
     if roof_k:
-        roofline = {"kernel": "contract_f64" if dom_name in ("utility_qp", "contract_f64") else dom_name,
-                    "bound": roof_k["bound"], "achieved": roof_k["achieved"], "peak": roof_k["peak"],
+        roofline = {"kernel": dom_name, "bound": roof_k["bound"], "achieved": roof_k["achieved"], "peak": roof_k["peak"],
                     "unit": roof_k["unit"], "frac": roof_k.get("frac"), "traffic": None,
-                    "peak_source": roof_k.get("peak_source", peak_src)}
+                    "peak_source": "cuBLAS DGEMM 6144^3 measured in this run (FP64 tensor pipe; MEASURED_PEAKS.json has no FP64 figure)",
+                    "note": "dominant kernel by time; FP64 FMA work counted in-kernel; HBM-bound kernels are in `kernels`"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

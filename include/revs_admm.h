@@ -22,6 +22,8 @@
  *   revs_reliability                              drawing.py:28-78    compute_flows(),
  *                                                                     compute_voltage()
  *   revs_get_results                              lpsolver.py:292-293 return diff,P_sch,S,C
+ *   revs_set_option / revs_get_stats / revs_version / revs_last_error / revs_device_count
+ *                                                 no reference counterpart (library plumbing)
  */
 #ifndef REVS_ADMM_H
 #define REVS_ADMM_H
@@ -55,6 +57,7 @@ typedef struct revs_stats {
     int32_t max_working_set;      /* largest per-(feeder,hour) working set seen         */
     double primal_residual;       /* ||P_est-P_sch||_F / sqrt(H T), last iteration      */
     double dual_residual;         /* kappa ||P_sch-P_sch_prev||_F / sqrt(H T)           */
+    double qp_flops;              /* algorithmic FP64 flops of the utility QP kernels   */
     float gemm_ms;                /* device time in sensitivity contractions (events)   */
     float gemm_full_ms;           /* ... of which the launches over ALL (feeder,hour) columns */
     float home_ms;                /* device time in the batched home solve              */
@@ -145,6 +148,10 @@ int revs_reliability(revs_solver* s, int feeder, int kind, int n_rows, const int
 /* Plain sensitivity contraction C[M,T] = A[M,K] @ B[K,T] on the tensor cores (FP64
  * DMMA), host in/out -- exposed so that the GEMM kernel can be tested on its own. */
 int revs_contract(int device, int M, int K, int T, const double* A, const double* B, double* C);
+
+/* Options: "screen" (default 1) = BF16 tensor-core screening of the voltage rows with exact
+ * FP64 recheck of the candidates inside the loop; 0 = FP64 DMMA contraction of every row. */
+int revs_set_option(revs_solver* s, const char* name, double value);
 
 int revs_get_stats(const revs_solver* s, revs_stats* out);
 

@@ -24,7 +24,7 @@ class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_int64), ("gemm_launches", C.c_int64), ("gemm_full_launches", C.c_int64),
                 ("qp_outer_iterations", C.c_int64), ("qp_newton_iterations", C.c_int64),
                 ("admm_iterations", C.c_int32), ("max_working_set", C.c_int32),
-                ("primal_residual", C.c_double), ("dual_residual", C.c_double),
+                ("primal_residual", C.c_double), ("dual_residual", C.c_double), ("qp_flops", C.c_double),
                 ("gemm_ms", C.c_float), ("gemm_full_ms", C.c_float), ("home_ms", C.c_float), ("dual_ms", C.c_float),
                 ("qp_ms", C.c_float), ("qp_big_ms", C.c_float), ("total_ms", C.c_float)]
 
@@ -58,6 +58,7 @@ SIGNATURES = {
     "revs_solve_individual": ([_P, _D, _D, _D], C.c_int),
     "revs_reliability": ([_P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), _D, C.c_double, _D, _D], C.c_int),
     "revs_contract": ([C.c_int, C.c_int, C.c_int, C.c_int, _D, _D, _D], C.c_int),
+    "revs_set_option": ([_P, C.c_char_p, C.c_double], C.c_int),
     "revs_get_stats": ([_P, C.POINTER(Stats)], C.c_int),
 }
 
@@ -245,6 +246,9 @@ class Solver:
                                          rows.ctypes.data_as(C.POINTER(C.c_int32)), _dp(sc), vset,
                                          _dp(Pp), _dp(out)))
         return out
+
+    def set_option(self, name, value):
+        _check(self.lib.revs_set_option(self._h, name.encode(), float(value)))
 
     def stats(self):
         st = Stats()

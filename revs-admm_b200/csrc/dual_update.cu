@@ -21,7 +21,7 @@ namespace revs {
 
 
 
-__global__ void __launch_bounds__(256) dual_update_kernel(DualParams P) {
+__global__ void __launch_bounds__(256, 4) dual_update_kernel(DualParams P) {
     extern __shared__ double tile[];   // [32][T+1]
     __shared__ double s_part[2][8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -64,6 +64,7 @@ struct QpParams {
     double* lam_t;         // [T][Hp]   multipliers (dense storage, sparse content)
     double* g_t;           // [T][Hp]   out: projection = P_est[k+1]
     double* v_t;           // [T][Hp]   in (step mode): R g of the stored iterate
+    void* gbf_t;           // optional [T][Hp] __nv_bfloat16 copy of g, written with it
     const float* v32_t;    // optional [T][Hp]: BF16-screened voltages; v_t is then filled here (exact for candidates)
     int* wcount;           // [ncols]
     int* widx;             // [ncols][kWMax]
@@ -72,6 +73,7 @@ struct QpParams {
     int* n_running;        // columns still running after this launch
     unsigned long long* newton_its;
     int* max_ws;
+    unsigned long long* flops;   // algorithmic FP64 flops executed by the QP kernels
     int* n_failed;         // columns whose working set overflowed kWMax
     int* cls;              // [ncols] instantiation that owns the column (see qp_class_cap)
     int* n_cls;            // [kQpClasses] running columns per class after this round

@@ -60,6 +60,7 @@ struct Counters {
     int infeasible;
     int max_ws;
     unsigned long long newton_its;
+    unsigned long long qp_flops;
     unsigned long long dbg[4 + 5 * kQpClasses];
     ResidualOut res;
 };
@@ -249,6 +250,7 @@ int utility_solve(revs_solver* s) {
     Q.g_t = s->d_gt;
     Q.v_t = s->d_vt;
     Q.v32_t = s->screen ? s->d_v32 : nullptr;
+    Q.gbf_t = s->screen ? s->d_gbf : nullptr;
     Q.wcount = s->d_wcount;
     Q.widx = s->d_widx;
     Q.status = s->d_status;
@@ -256,6 +258,7 @@ int utility_solve(revs_solver* s) {
     Q.n_running = &s->d_cnt->n_running;
     Q.newton_its = &s->d_cnt->newton_its;
     Q.max_ws = &s->d_cnt->max_ws;
+    Q.flops = &s->d_cnt->qp_flops;
     Q.n_failed = &s->d_cnt->n_failed;
     Q.cls = s->d_cls;
     Q.n_cls = s->d_cnt->n_cls;
@@ -289,9 +292,7 @@ int utility_solve(revs_solver* s) {
                         s->h_cnt->n_running, round);
         sp = span_begin(s, round == 0 ? 5 : 0, s->sU);   // round 0: every column is running
         if (s->screen) {
-            CU(launch_to_bf16(s->d_gt, s->d_gbf, (size_t)s->Hp * s->T, s->sU));
             CU(launch_screen(s->d_sprob, s->d_stiles, s->n_stiles, s->T, s->sU));
-            s->stats.kernel_launches++;
         } else {
             CU(launch_contract(s->d_cprob, s->d_ctiles, s->n_ctiles, s->T, kOutTimeMajor, 0.0, s->sU));
         }
@@ -777,6 +778,7 @@ int revs_admm_step(revs_solver* s, double sums[3]) {
     s->stats.primal_residual = s->h_cnt->res.primal;
     s->stats.dual_residual = s->h_cnt->res.dual;
     s->stats.qp_newton_iterations = (int64_t)s->h_cnt->newton_its;
+    s->stats.qp_flops = (double)s->h_cnt->qp_flops;
     s->stats.max_working_set = s->h_cnt->max_ws;
     float ms = 0.f;
     cudaEventElapsedTime(&ms, s->evT0, s->evT1);
@@ -1045,6 +1047,12 @@ int revs_contract(int device, int M, int K, int T, const double* A, const double
 #undef TRYC
     cleanup();
     return REVS_OK;
+}
+
+int revs_set_option(revs_solver* s, const char* name, double value) {
+    if (!s || !name) return fail(REVS_ERR_ARG, "bad arguments");
+    if (!strcmp(name, "screen")) { s->screen = value != 0.0; return REVS_OK; }
+    return fail(REVS_ERR_ARG, "unknown option '%s'", name);
 }
 
 int revs_get_stats(const revs_solver* s, revs_stats* out) {

@@ -12,9 +12,10 @@
 // pass reads the sensitivity blocks at 2 bytes per entry instead of 8 and runs at the BF16
 // tensor rate, ~10x less time than the FP64 DMMA contraction it replaces in the loop.
 //
-// Kernel: CTA tile 128 (rows) x 96 (hours) x 64 (k), 8 warps (4x2), mma.sync.m16n8k16.bf16
-// with ldmatrix operand fetch from a 4-stage cp.async ring; rows of the shared tiles are
-// padded to 72 elements (144 B) so that every ldmatrix phase is bank-conflict free.
+// Kernel: CTA tile 128 (rows) x 96 (hours) x 32 (k), 8 warps (4x2), mma.sync.m16n8k16.bf16
+// with ldmatrix operand fetch from a 4-stage cp.async ring (72 KB, 3 CTAs per SM); rows of
+// the shared tiles are padded to 40 elements (80 B) so that every ldmatrix phase is
+// bank-conflict free.
 // Columns whose QP has converged are skipped exactly like in contract_f64.cu.
 #include <cuda_bf16.h>
 
@@ -24,7 +25,7 @@ namespace revs {
 
 namespace {
 
-constexpr int kSBM = 128, kSBN = 96, kSBK = 64, kSStages = 4;
+constexpr int kSBM = 128, kSBN = 96, kSBK = 32, kSStages = 4;
 constexpr int kSLd = kSBK + 8;            // padded row, in bf16 elements
 constexpr int kSThreads = 256;
 constexpr int kSWarpsM = 4, kSWarpsN = 2;
@@ -48,7 +49,7 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], const unsigned (&a)[4], 
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-__global__ void __launch_bounds__(kSThreads)
+__global__ void __launch_bounds__(kSThreads, 3)
 screen_bf16_kernel(const ScreenProblem* __restrict__ problems, const ContractTile* __restrict__ tiles, int T) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(smem_raw);          // [stages][BM][kSLd]

@@ -27,6 +27,8 @@
 // >= 4 CTAs per SM), |W| <= 64 (256 threads, 54 KB, 2 per SM) and |W| <= 128 (256 threads,
 // 175 KB, 1 per SM).  A column carries a class flag; it is classified by the size of its
 // warm-start set and handed to the next class when it outgrows the current one.
+#include <cuda_bf16.h>
+
 #include "kernels.cuh"
 
 namespace revs {
@@ -106,7 +108,7 @@ template <int THREADS, class S>
 __device__ double eval_phi(const double* __restrict__ R, int ld, int n, const double* __restrict__ z,
                            const int* idx, const double* lam, int m, double u, double* g_store, S& sm,
                            const double* grad = nullptr, const double* base = nullptr,
-                           double* slope = nullptr) {
+                           double* slope = nullptr, __nv_bfloat16* gbf_store = nullptr) {
     double acc[3] = {0.0, 0.0, 0.0};
     for (int j = threadIdx.x; j < n; j += THREADS) {
         double pi = 0.0;
@@ -115,7 +117,10 @@ __device__ double eval_phi(const double* __restrict__ R, int ld, int n, const do
             if (l != 0.0) pi = fma(R[(size_t)idx[a] * ld + j], l, pi);
         }
         const double gj = fmax(z[j] - pi, 0.0);
-        if (g_store) g_store[j] = gj;
+        if (g_store) {
+            g_store[j] = gj;
+            if (gbf_store) gbf_store[j] = __float2bfloat16_rn((float)gj);   // operand of the screening contraction
+        }
         acc[0] = fma(gj, gj, acc[0]);
     }
     for (int a = threadIdx.x; a < m; a += THREADS) {
@@ -525,10 +530,12 @@ __global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
     }
 
     // ------------------------------------------------------------ piecewise-quadratic descent on W
-    double phi = eval_phi<THREADS>(R, ld, n, z, sm.idx, sm.lam, m, u, g, sm);
+    __nv_bfloat16* gbf = P.gbf_t ? reinterpret_cast<__nv_bfloat16*>(P.gbf_t) + col : nullptr;
+    double phi = eval_phi<THREADS>(R, ld, n, z, sm.idx, sm.lam, m, u, g, sm, nullptr, nullptr, nullptr, gbf);
     double tau = 1.0;
     int ok = 0, its = 0;
     unsigned n_evals = 0, n_pdas = 0, n_fallback = 0;
+    double flops = 2.0 * m * n;                 // algorithmic FP64 flops of this launch (first evaluation)
     bool have_H = false;   // Hb/hdiag hold the Hessian for the mask in sm.fmask
     long long tc[5] = {0, 0, 0, 0, 0}, t0 = clock64(), t1;   // phase cycles (debug)
 #define PHASE(i) do { t1 = clock64(); tc[i] += t1 - t0; t0 = t1; } while (0)
@@ -551,6 +558,7 @@ __global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
         }
         const double kkt = block_max<THREADS>(kk, sm);
         PHASE(0);
+        flops += 2.0 * m * n;
         if (kkt < tol) { ok = 1; break; }
 
         // model Hessian of the current piece on all of W (register block sized to m): from
@@ -588,6 +596,7 @@ __global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
                 else HESS((WMAX > 64 ? 8 : 4), (WMAX > 64 ? 8 : 4));
             }
 #undef HESS
+            flops += (double)m * (m + 1) * ((nchg >= 0 && have_H) ? nchg : n);   // lower triangle, 2 flops per MAC
             have_H = true;
         }
         PHASE(1);
@@ -611,6 +620,7 @@ __global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
         for (int guess = 0; guess < kPdasMax; ++guess) {
             ++n_pdas;
             ma = compact_flags<THREADS>(sm.inA, m, sm);
+            flops += (2.0 / 3.0) * ma * ma * ma + 4.0 * ma * ma + 2.0 * m * ma;
             for (int a = tid; a < m; a += THREADS) sm.trial[a] = 0.0;
             if (ma > 0) {
                 for (int p = tid; p < ma; p += THREADS) sm.y[p] = sm.b[sm.fl[p]];
@@ -644,6 +654,7 @@ __global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
                 double slope;
                 phin = eval_phi<THREADS>(R, ld, n, z, sm.idx, sm.trial, m, u, nullptr, sm, sm.grad, sm.lam, &slope);
                 ++n_evals;
+                flops += 2.0 * m * n;
                 // + rounding noise of phi itself, see oracle/revs_oracle.py:project_voltage
                 if (phin <= phi + 1e-4 * slope + 1e-14 * fabs(phi)) { stepped = true; break; }
             }
@@ -674,6 +685,7 @@ __global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
                     double slope;
                     phin = eval_phi<THREADS>(R, ld, n, z, sm.idx, sm.trial, m, u, nullptr, sm, sm.grad, sm.lam, &slope);
                     ++n_evals;
+                    flops += 2.0 * m * n;
                     if (phin <= phi + 1e-4 * slope + 1e-14 * fabs(phi)) { found = true; break; }
                 }
                 if (found || tau > 1e40 || mf == 0) break;
@@ -685,7 +697,8 @@ __global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
         __syncthreads();
         for (int a = tid; a < m; a += THREADS) sm.lam[a] = sm.trial[a];
         __syncthreads();
-        phi = eval_phi<THREADS>(R, ld, n, z, sm.idx, sm.lam, m, u, g, sm);
+        phi = eval_phi<THREADS>(R, ld, n, z, sm.idx, sm.lam, m, u, g, sm, nullptr, nullptr, nullptr, gbf);
+        flops += 2.0 * m * n;
         PHASE(4);
     }
 
@@ -706,6 +719,7 @@ __global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
         atomicAdd(P.n_cls + CLS, 1);
         atomicAdd(P.newton_its, (unsigned long long)its);
         atomicMax(P.max_ws, m);
+        atomicAdd(P.flops, (unsigned long long)flops);
         if (P.dbg) {
             atomicAdd(P.dbg + 0, (unsigned long long)n_evals);
             atomicAdd(P.dbg + 1, (unsigned long long)n_pdas);
