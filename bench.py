@@ -57,15 +57,36 @@ def pinned_like(a):
 
 
 class ClockSampler:
+    """SM clock / throttle reasons DURING the timed region (NVML every 20 ms; nvidia-smi as fallback)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
         self.index, self.rows, self.stop = index, [], threading.Event()
         self.th = threading.Thread(target=self._run, daemon=True)
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
     def _run(self):
+        nv = self.nvml
         while not self.stop.is_set():
             try:
+                if nv is not None:
+                    sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                        else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    flags = ["Active" if r & m else "Not Active" for m in (0x8, 0x40, 0x20, 0x4)]  # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap
+                    self.rows.append([str(sm), str(self.max_sm), "0"] + flags)
+                    self.stop.wait(0.02)
+                    continue
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
                 self.rows.append([x.strip() for x in out.strip().split(",")])
@@ -87,7 +108,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def measured_peaks():

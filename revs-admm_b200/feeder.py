@@ -141,4 +141,4 @@ def synthetic_tariff(T):
     day = np.array([0.07866] * 5 + [0.095111] * 10 + [0.214357] * 3 + [0.095111] * 6)
     day = np.roll(day, -6)
     sph = max(1, T // 24)
-    return np.repeat(day, sph)[:T] if T >= 24 else day[:T]
+    return np.resize(np.repeat(day, sph), T) if T >= 24 else day[:T]

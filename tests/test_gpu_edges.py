@@ -1,0 +1,154 @@
+"""GPU edge cases: ragged shapes, degenerate populations, option/exactness cross-checks, errors."""
+import numpy as np
+import pytest
+
+import revs_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem(sizes, T, seed, r_secondary=1e-3, **hkw):
+    from revs_admm_b200.feeder import synthetic_feeder, synthetic_homes, synthetic_tariff
+    trees = [synthetic_feeder(n, seed=seed + i, r_secondary=r_secondary, laterals=max(1, min(5, n))) for i, n in enumerate(sizes)]
+    hm = synthetic_homes(sum(sizes), T, seed=seed, **hkw)
+    return trees, hm, synthetic_tariff(T) if T >= 24 else np.linspace(0.05, 0.2, T)
+
+
+def _oracle(trees, hm, cost, kw):
+    Rb = [O.rmat_from_tree(t.parent, t.r)[np.ix_(t.res_node, t.res_node)] for t in trees]
+    return O.solve_ADMM_arrays(Rb, load=hm["load"], cost=cost, ev_mask=hm["has_ev"].astype(bool), rating=hm["rating"],
+                               capacity=hm["capacity"], initial=hm["initial"], start=hm["start"], end=hm["end"], **kw)
+
+
+def _gpu(lib, sizes, T, trees, hm, cost, kw, screen=1):
+    with lib.Solver(sizes, T) as s:
+        s.set_option("screen", screen)
+        s.set_feeder_trees(trees)
+        s.set_homes(**hm)
+        s.set_tariff(cost)
+        done = s.solve_admm(**kw)
+        out = s.results(done)
+        out["P_est"], out["Gamma"] = s.estimate()
+        out["stats"] = s.stats()
+    return out
+
+
+@pytest.mark.parametrize("sizes,T", [([1], 24), ([17, 1, 33], 24), ([5, 3], 7), ([40], 1), ([30, 21], 100), ([12], 256)])
+def test_ragged_shapes_match_oracle(gpu_lib, sizes, T):
+    trees, hm, cost = _problem(sizes, T, seed=sum(sizes) + T)
+    if T < 24:      # plug-in window must fit the horizon
+        hm["start"][:] = 0
+        hm["end"][:] = T
+        hm["capacity"][:] = 4.8 * max(1, T // 2) / 0.75      # ~T/2 charging steps needed
+    kw = dict(kappa=5.0, iter_max=4, vset=1.0, vlow=0.95, vhigh=1.02)
+    out = _gpu(gpu_lib, sizes, T, trees, hm, cost, kw)
+    ref = _oracle(trees, hm, cost, kw)
+    assert np.array_equal(out["P_ev"], ref["P_ev"])
+    assert np.abs(out["P_sch"] - ref["P_sch"]).max() <= 1e-4
+    assert np.abs(out["P_est"] - ref["P_est"]).max() <= 1e-4
+    assert np.abs(out["diff"] - ref["diff"]).max() <= 1e-7
+    assert np.allclose(out["SOC"], ref["SOC"], atol=1e-12)
+
+
+@pytest.mark.parametrize("adoption", [0.0, 1.0])
+def test_no_ev_and_all_ev(gpu_lib, adoption):
+    sizes, T = [60, 45], 24
+    trees, hm, cost = _problem(sizes, T, seed=9, adoption=adoption)
+    kw = dict(kappa=5.0, iter_max=5, vset=1.0, vlow=0.95, vhigh=1.02)
+    out = _gpu(gpu_lib, sizes, T, trees, hm, cost, kw)
+    ref = _oracle(trees, hm, cost, kw)
+    assert np.array_equal(out["P_ev"], ref["P_ev"])
+    assert np.abs(out["P_sch"] - ref["P_sch"]).max() <= 1e-4
+    if adoption == 0.0:
+        assert np.array_equal(out["P_sch"], hm["load"]) and out["SOC"].max() == 0.0
+
+
+def test_screening_is_exact(gpu_lib):
+    """BF16 screening + FP64 recheck must give bit-identical results to the FP64 contraction."""
+    sizes, T = [130, 77, 201], 96
+    trees, hm, cost = _problem(sizes, T, seed=21)
+    kw = dict(kappa=5.0, iter_max=6, vset=1.0, vlow=0.95, vhigh=1.015)
+    a = _gpu(gpu_lib, sizes, T, trees, hm, cost, kw, screen=1)
+    b = _gpu(gpu_lib, sizes, T, trees, hm, cost, kw, screen=0)
+    for k in ("P_sch", "P_ev", "SOC", "diff", "P_est", "Gamma"):
+        assert np.array_equal(a[k], b[k]), k
+    assert a["stats"]["gemm_launches"] == b["stats"]["gemm_launches"] > 0
+
+
+def test_dense_block_input_equals_tree_input(gpu_lib):
+    sizes, T = [48, 31], 24
+    trees, hm, cost = _problem(sizes, T, seed=5)
+    kw = dict(kappa=5.0, iter_max=4, vset=1.0, vlow=0.95, vhigh=1.02)
+    a = _gpu(gpu_lib, sizes, T, trees, hm, cost, kw)
+    with gpu_lib.Solver(sizes, T) as s:
+        for f, t in enumerate(trees):
+            s.set_sensitivity(f, O.rmat_from_tree(t.parent, t.r)[np.ix_(t.res_node, t.res_node)])
+        s.set_homes(**hm)
+        s.set_tariff(cost)
+        done = s.solve_admm(**kw)
+        b = s.results(done)
+    assert np.array_equal(a["P_ev"], b["P_ev"])
+    assert np.abs(a["P_sch"] - b["P_sch"]).max() <= 1e-9
+
+
+def test_reliability_kinds_on_synthetic_tree(gpu_lib):
+    from revs_admm_b200.feeder import synthetic_feeder
+    T = 24
+    t = synthetic_feeder(75, seed=3, r_secondary=1e-3)
+    rng = np.random.default_rng(0)
+    P = rng.uniform(0, 6, (75, T))
+    R = O.rmat_from_tree(t.parent, t.r)
+    Pall = np.zeros((t.n_nodes, T))
+    Pall[t.res_node] = P
+    with gpu_lib.Solver([75], T) as s:
+        s.set_feeder_tree(0, t.parent, t.r, t.res_node)
+        rows = np.arange(t.n_nodes)
+        drop = s.reliability(0, 2, rows, P=P)
+        volt = s.reliability(0, 0, rows, vset=1.03, P=P)
+        flow = s.reliability(0, 1, rows, P=P, scale=np.full(t.n_nodes, 0.5))
+        with pytest.raises(gpu_lib.RevsError):
+            s.reliability(0, 0, [t.n_nodes], P=P)
+    assert np.abs(drop - R @ Pall).max() <= 1e-12
+    assert np.abs(volt - np.sqrt(1.03 ** 2 - R @ Pall)).max() <= 1e-12
+    # flow on the edge above node i = load of its subtree
+    sub = Pall.copy()
+    for i in range(t.n_nodes - 1, -1, -1):
+        if t.parent[i] >= 0:
+            sub[t.parent[i]] += sub[i]
+    assert np.abs(flow - 0.5 * sub).max() <= 1e-10
+
+
+def test_argument_errors(gpu_lib):
+    from revs_admm_b200.feeder import synthetic_feeder, synthetic_homes
+    with pytest.raises(gpu_lib.RevsError):
+        gpu_lib.Solver([4], 300)                       # horizon limit
+    with gpu_lib.Solver([20], 24) as s:
+        with pytest.raises(gpu_lib.RevsError):         # nothing set yet
+            s.solve_admm()
+        t = synthetic_feeder(20, seed=1)
+        s.set_feeder_tree(0, t.parent, t.r, t.res_node)
+        s.set_homes(**synthetic_homes(20, 24, seed=1))
+        s.set_tariff(np.ones(24))
+        with pytest.raises(gpu_lib.RevsError):         # vhigh <= vset
+            s.solve_admm(vset=1.05, vhigh=1.05)
+        with pytest.raises(gpu_lib.RevsError):
+            s.set_option("nonsense", 1)
+        with pytest.raises(gpu_lib.RevsError):         # parent after child
+            s.set_feeder_tree(0, t.parent[::-1].copy(), t.r, t.res_node)
+        assert s.solve_admm(iter_max=2) == 2
+
+
+def test_working_set_overflow_is_loud(gpu_lib):
+    """More than 128 simultaneously binding voltage rows in one (feeder,hour) column is outside
+    what this round's QP kernel holds in shared memory: it must fail with REVS_ERR_NOCONV."""
+    from revs_admm_b200.feeder import synthetic_feeder, synthetic_homes, synthetic_tariff
+    n, T = 1000, 24      # the oracle finds up to 149 binding rows per hour on this feeder
+    t = synthetic_feeder(n, seed=0, laterals=5)
+    hm = synthetic_homes(n, T, seed=77)
+    with gpu_lib.Solver([n], T) as s:
+        s.set_feeder_tree(0, t.parent, t.r, t.res_node)
+        s.set_homes(**hm)
+        s.set_tariff(synthetic_tariff(T))
+        with pytest.raises(gpu_lib.RevsError) as e:
+            s.solve_admm(iter_max=4, vset=1.03, vlow=0.95, vhigh=1.05)
+        assert e.value.code == 4
