@@ -149,8 +149,15 @@ int revs_reliability(revs_solver* s, int feeder, int kind, int n_rows, const int
  * DMMA), host in/out -- exposed so that the GEMM kernel can be tested on its own. */
 int revs_contract(int device, int M, int K, int T, const double* A, const double* B, double* C);
 
+/* The in-loop screening contraction on its own: C ~ A @ B with BF16 operands and FP32
+ * accumulation (relative error <= 0.5 % for non-negative data).  impl 0 = mma.sync kernel,
+ * impl 1 = tcgen05 / TMEM / TMA kernel (T <= 96). */
+int revs_screen_contract(int device, int M, int K, int T, const double* A, const double* B, double* C,
+                         int impl);
+
 /* Options: "screen" (default 1) = BF16 tensor-core screening of the voltage rows with exact
- * FP64 recheck of the candidates inside the loop; 0 = FP64 DMMA contraction of every row. */
+ * FP64 recheck of the candidates inside the loop; 0 = FP64 DMMA contraction of every row.
+ * "screen_impl" = 0 mma.sync screening kernel, 1 tcgen05/TMEM/TMA screening kernel. */
 int revs_set_option(revs_solver* s, const char* name, double value);
 
 int revs_get_stats(const revs_solver* s, revs_stats* out);

@@ -59,6 +59,7 @@ SIGNATURES = {
     "revs_reliability": ([_P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), _D, C.c_double, _D, _D], C.c_int),
     "revs_contract": ([C.c_int, C.c_int, C.c_int, C.c_int, _D, _D, _D], C.c_int),
     "revs_set_option": ([_P, C.c_char_p, C.c_double], C.c_int),
+    "revs_screen_contract": ([C.c_int, C.c_int, C.c_int, C.c_int, _D, _D, _D, C.c_int], C.c_int),
     "revs_get_stats": ([_P, C.POINTER(Stats)], C.c_int),
 }
 
@@ -110,6 +111,17 @@ def contract(A, B, device=0):
     assert K == K2
     out = np.empty((M, T))
     _check(load().revs_contract(device, M, K, T, _dp(A), _dp(B), _dp(out)))
+    return out
+
+
+def screen_contract(A, B, impl=0, device=0):
+    """C ~ A @ B through the BF16 screening kernel (impl 0: mma.sync, 1: tcgen05/TMA)."""
+    A, B = _f64(A), _f64(B)
+    M, K = A.shape
+    K2, T = B.shape
+    assert K == K2
+    out = np.empty((M, T))
+    _check(load().revs_screen_contract(device, M, K, T, _dp(A), _dp(B), _dp(out), impl))
     return out
 
 

@@ -98,6 +98,16 @@ cudaError_t launch_to_bf16(const double* in, void* out, size_t n, cudaStream_t s
 cudaError_t launch_screen(const ScreenProblem* d_problems, const ContractTile* d_tiles, int n_tiles, int T,
                           cudaStream_t stream);
 
+// ---- screen_tc5.cu (tcgen05 / TMEM / TMA implementation of the same contraction)
+int screen_tc5_tile_rows();
+size_t screen_tc5_map_bytes();
+uint32_t screen_tc5_box_rows_a();
+uint32_t screen_tc5_box_rows_b();
+cudaError_t screen_tc5_encode(void* host_map, const void* gptr, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
+                              uint32_t box_rows);
+cudaError_t launch_screen_tc5(const ScreenProblem* d_problems, const ContractTile* d_tiles, int n_tiles, const void* d_maps_a,
+                              const void* d_map_b, const int* d_b_col0, int T, cudaStream_t stream);
+
 // ---- feeder_build.cu
 cudaError_t launch_sens_voltage(const int* parent, const double* cumr, const int* row_node,
                                 const int* res_node, int n_rows, int n_res, double* out, int ld,

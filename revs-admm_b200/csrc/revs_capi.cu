@@ -95,6 +95,10 @@ struct revs_solver {
     ContractTile* d_stiles = nullptr;
     int n_stiles = 0;
     bool screen = true;                        // BF16 screening + exact recheck instead of the FP64 contraction in the loop
+    int screen_impl = 0;                       // 0: mma.sync kernel, 1: tcgen05/TMEM/TMA kernel
+    void *d_maps_a = nullptr, *d_map_b = nullptr;   // CUtensorMap per feeder block / for the bf16 schedule
+    int* d_bcol0 = nullptr;
+    bool tc5_ready = false;
     int *d_pool_parent = nullptr, *d_pool_res = nullptr;   // revs_set_feeder_trees
     double* d_pool_cumr = nullptr;
     int64_t* d_pool_off = nullptr;
@@ -292,7 +296,11 @@ int utility_solve(revs_solver* s) {
                         s->h_cnt->n_running, round);
         sp = span_begin(s, round == 0 ? 5 : 0, s->sU);   // round 0: every column is running
         if (s->screen) {
-            CU(launch_screen(s->d_sprob, s->d_stiles, s->n_stiles, s->T, s->sU));
+            if (s->screen_impl == 1 && s->tc5_ready)
+                CU(launch_screen_tc5(s->d_sprob, s->d_stiles, s->n_stiles, s->d_maps_a,
+                                     (const char*)s->d_maps_a + (size_t)s->nf * screen_tc5_map_bytes(), s->d_bcol0, s->T, s->sU));
+            else
+                CU(launch_screen(s->d_sprob, s->d_stiles, s->n_stiles, s->T, s->sU));
         } else {
             CU(launch_contract(s->d_cprob, s->d_ctiles, s->n_ctiles, s->T, kOutTimeMajor, 0.0, s->sU));
         }
@@ -375,7 +383,7 @@ HomeParams home_params(revs_solver* s, int individual) {
 
 void free_all(revs_solver* s) {
     cudaSetDevice(s->device);
-    void* ptrs[] = {s->d_feeders, s->d_Rpool, s->d_rn2, s->d_Rbf, s->d_gbf, s->d_v32, s->d_sprob, s->d_stiles, s->d_pool_parent, s->d_pool_res, s->d_pool_cumr, s->d_pool_off, s->d_load, s->d_pest, s->d_psch[0], s->d_psch[1], s->d_gamma,
+    void* ptrs[] = {s->d_feeders, s->d_Rpool, s->d_rn2, s->d_Rbf, s->d_gbf, s->d_v32, s->d_sprob, s->d_stiles, s->d_maps_a, s->d_map_b, s->d_bcol0, s->d_pool_parent, s->d_pool_res, s->d_pool_cumr, s->d_pool_off, s->d_load, s->d_pest, s->d_psch[0], s->d_psch[1], s->d_gamma,
                     s->d_pev, s->d_soc, s->d_has_ev, s->d_rating, s->d_capacity, s->d_initial, s->d_indconst,
                     s->d_start, s->d_end, s->d_nmin, s->d_nmax, s->d_zero_i, s->d_cost, s->d_zt, s->d_lamt,
                     s->d_gt, s->d_vt, s->d_wcount, s->d_widx, s->d_status, s->d_innerok, s->d_cls, s->d_cnt, s->d_diff,
@@ -538,6 +546,29 @@ int revs_create(revs_solver** out, int device, int n_feeders, const int64_t* fee
         TRY(cudaMemcpy(s->d_sprob, sp.data(), sp.size() * sizeof(ScreenProblem), cudaMemcpyHostToDevice));
         TRY(dalloc(&s->d_stiles, st.size()));
         TRY(cudaMemcpy(s->d_stiles, st.data(), st.size() * sizeof(ContractTile), cudaMemcpyHostToDevice));
+        // tensor maps of the tcgen05 implementation (same 128-row tiling)
+        if (T <= (int)screen_tc5_box_rows_b() && screen_tc5_tile_rows() == sbm) {
+            const size_t mb = screen_tc5_map_bytes();
+            std::vector<unsigned char> maps((size_t)(n_feeders + 1) * mb);
+            std::vector<int> bcol(n_feeders);
+            bool ok = true;
+            for (int f = 0; f < n_feeders && ok; ++f) {
+                const FeederDev& fd = s->feeders[f];
+                ok = screen_tc5_encode(maps.data() + (size_t)f * mb, (const char*)s->d_Rbf + 2 * fd.roff, fd.np, fd.np, fd.np,
+                                       screen_tc5_box_rows_a()) == cudaSuccess;
+                bcol[f] = (int)fd.off;
+            }
+            ok = ok && screen_tc5_encode(maps.data() + (size_t)n_feeders * mb, s->d_gbf, T, hp, hp, screen_tc5_box_rows_b()) == cudaSuccess;
+            if (ok) {
+                TRY(cudaMalloc(&s->d_maps_a, maps.size()));
+                TRY(cudaMemcpy(s->d_maps_a, maps.data(), maps.size(), cudaMemcpyHostToDevice));
+                s->d_map_b = nullptr;   // last entry of the same allocation
+                TRY(dalloc(&s->d_bcol0, (size_t)n_feeders));
+                TRY(cudaMemcpy(s->d_bcol0, bcol.data(), sizeof(int) * n_feeders, cudaMemcpyHostToDevice));
+                s->tc5_ready = true;
+                if (getenv("REVS_SCREEN_TC5")) s->screen_impl = atoi(getenv("REVS_SCREEN_TC5"));
+            }
+        }
     }
     s->n_ctiles = (int)tiles.size();
     TRY(dalloc(&s->d_cprob, probs.size()));
@@ -1049,9 +1080,76 @@ int revs_contract(int device, int M, int K, int T, const double* A, const double
     return REVS_OK;
 }
 
+int revs_screen_contract(int device, int M, int K, int T, const double* A, const double* B, double* C, int impl) {
+    if (M <= 0 || K <= 0 || T <= 0 || !A || !B || !C) return fail(REVS_ERR_ARG, "bad arguments");
+    int rc = use_device(device);
+    if (rc) return rc;
+    const int Kp = (K + kPad - 1) / kPad * kPad;
+    std::vector<double> Ap((size_t)M * Kp, 0.0), Bt((size_t)T * Kp, 0.0);
+    for (int i = 0; i < M; ++i) memcpy(&Ap[(size_t)i * Kp], A + (size_t)i * K, sizeof(double) * K);
+    for (int k = 0; k < K; ++k)
+        for (int t = 0; t < T; ++t) Bt[(size_t)t * Kp + k] = B[(size_t)k * T + t];
+    double *dA = nullptr, *dB = nullptr;
+    void *dAb = nullptr, *dBb = nullptr, *dmaps = nullptr;
+    float* dC = nullptr;
+    int* dcol = nullptr;
+    ScreenProblem* d_prob = nullptr;
+    ContractTile* d_tiles = nullptr;
+    auto cleanup = [&]() { cudaFree(dA); cudaFree(dB); cudaFree(dAb); cudaFree(dBb); cudaFree(dC); cudaFree(d_prob); cudaFree(d_tiles); cudaFree(dmaps); cudaFree(dcol); };
+#define TRYS(x)                                                                          \
+    do {                                                                                 \
+        cudaError_t e_ = (x);                                                            \
+        if (e_ != cudaSuccess) {                                                         \
+            cleanup();                                                                   \
+            return fail(REVS_ERR_CUDA, "%s failed: %s", #x, cudaGetErrorString(e_));     \
+        }                                                                                \
+    } while (0)
+    TRYS(dalloc(&dA, Ap.size()));
+    TRYS(dalloc(&dB, Bt.size()));
+    TRYS(cudaMalloc(&dAb, Ap.size() * 2));
+    TRYS(cudaMalloc(&dBb, Bt.size() * 2));
+    TRYS(dalloc(&dC, (size_t)M * T));
+    TRYS(cudaMemcpy(dA, Ap.data(), Ap.size() * sizeof(double), cudaMemcpyHostToDevice));
+    TRYS(cudaMemcpy(dB, Bt.data(), Bt.size() * sizeof(double), cudaMemcpyHostToDevice));
+    TRYS(launch_to_bf16(dA, dAb, Ap.size(), 0));
+    TRYS(launch_to_bf16(dB, dBb, Bt.size(), 0));
+    ScreenProblem pb{dAb, Kp, M, Kp, dBb, Kp, dC, M, nullptr};
+    std::vector<ContractTile> tiles;
+    for (int r0 = 0; r0 < M; r0 += screen_tile_rows()) tiles.push_back(ContractTile{0, r0});
+    TRYS(dalloc(&d_prob, (size_t)1));
+    TRYS(cudaMemcpy(d_prob, &pb, sizeof pb, cudaMemcpyHostToDevice));
+    TRYS(dalloc(&d_tiles, tiles.size()));
+    TRYS(cudaMemcpy(d_tiles, tiles.data(), tiles.size() * sizeof(ContractTile), cudaMemcpyHostToDevice));
+    if (impl == 1) {
+        if (T > (int)screen_tc5_box_rows_b()) { cleanup(); return fail(REVS_ERR_ARG, "tcgen05 screening kernel handles T <= 96"); }
+        const size_t mb = screen_tc5_map_bytes();
+        std::vector<unsigned char> maps(2 * mb);
+        TRYS(screen_tc5_encode(maps.data(), dAb, M, Kp, Kp, screen_tc5_box_rows_a()));
+        TRYS(screen_tc5_encode(maps.data() + mb, dBb, T, Kp, Kp, screen_tc5_box_rows_b()));
+        TRYS(cudaMalloc(&dmaps, maps.size()));
+        TRYS(cudaMemcpy(dmaps, maps.data(), maps.size(), cudaMemcpyHostToDevice));
+        TRYS(dalloc(&dcol, (size_t)1));
+        TRYS(launch_screen_tc5(d_prob, d_tiles, (int)tiles.size(), dmaps, (const char*)dmaps + mb, dcol, T, 0));
+    } else {
+        TRYS(launch_screen(d_prob, d_tiles, (int)tiles.size(), T, 0));
+    }
+    std::vector<float> out((size_t)M * T);
+    TRYS(cudaMemcpy(out.data(), dC, out.size() * sizeof(float), cudaMemcpyDeviceToHost));
+#undef TRYS
+    for (int i = 0; i < M; ++i)
+        for (int t = 0; t < T; ++t) C[(size_t)i * T + t] = (double)out[(size_t)t * M + i];
+    cleanup();
+    return REVS_OK;
+}
+
 int revs_set_option(revs_solver* s, const char* name, double value) {
     if (!s || !name) return fail(REVS_ERR_ARG, "bad arguments");
     if (!strcmp(name, "screen")) { s->screen = value != 0.0; return REVS_OK; }
+    if (!strcmp(name, "screen_impl")) {
+        if (value != 0.0 && !s->tc5_ready) return fail(REVS_ERR_ARG, "tcgen05 screening kernel unavailable (T > 96 or tensor-map encoding failed)");
+        s->screen_impl = value != 0.0 ? 1 : 0;
+        return REVS_OK;
+    }
     return fail(REVS_ERR_ARG, "unknown option '%s'", name);
 }
 

@@ -247,3 +247,38 @@ def test_admm_early_stop_and_step_api(gpu_lib):
         again = s.results(done)
     assert np.array_equal(full["P_sch"], again["P_sch"])
     assert np.array_equal(full["diff"], again["diff"])
+
+
+# ----------------------------------------------------------------- screening contraction
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("M,K,T", [(128, 64, 96), (1008, 1008, 96), (130, 100, 24), (77, 333, 5), (300, 48, 96)])
+def test_screen_contract_bound(gpu_lib, impl, M, K, T):
+    """BF16 screening product: rigorous one-sided bound v <= 1.0045 v~ on non-negative data,
+    for the mma.sync kernel (impl 0) and the tcgen05/TMEM/TMA kernel (impl 1)."""
+    rng = np.random.default_rng(M + K + T)
+    A = rng.uniform(0, 2e-2, (M, K)) * (rng.random((M, K)) < 0.7)
+    B = rng.uniform(0, 8, (K, T))
+    C = gpu_lib.screen_contract(A, B, impl=impl)
+    ref = A @ B
+    assert C.shape == ref.shape
+    rel = np.abs(C - ref) / np.maximum(ref, 1e-300)
+    assert rel[ref > 0].max() <= 4.5e-3
+    assert (ref <= 1.0045 * C + 1e-30).all()
+
+
+def test_screen_impls_agree_in_the_loop(gpu_lib):
+    from revs_admm_b200.feeder import synthetic_feeder, synthetic_homes, synthetic_tariff
+    sizes, T = [130, 77, 201], 96
+    trees = [synthetic_feeder(n, seed=30 + i, r_secondary=1e-3) for i, n in enumerate(sizes)]
+    hm = synthetic_homes(sum(sizes), T, seed=31)
+    outs = []
+    for impl in (0, 1):
+        with gpu_lib.Solver(sizes, T) as s:
+            s.set_option("screen_impl", impl)
+            s.set_feeder_trees(trees)
+            s.set_homes(**hm)
+            s.set_tariff(synthetic_tariff(T))
+            done = s.solve_admm(kappa=5.0, iter_max=5, vset=1.0, vlow=0.95, vhigh=1.015)
+            outs.append(s.results(done))
+    for k in ("P_sch", "P_ev", "SOC", "diff"):
+        assert np.array_equal(outs[0][k], outs[1][k]), k
