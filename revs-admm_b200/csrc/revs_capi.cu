@@ -566,6 +566,7 @@ int revs_create(revs_solver** out, int device, int n_feeders, const int64_t* fee
                 TRY(dalloc(&s->d_bcol0, (size_t)n_feeders));
                 TRY(cudaMemcpy(s->d_bcol0, bcol.data(), sizeof(int) * n_feeders, cudaMemcpyHostToDevice));
                 s->tc5_ready = true;
+                s->screen_impl = 1;       // sm_100a-native kernel by default
                 if (getenv("REVS_SCREEN_TC5")) s->screen_impl = atoi(getenv("REVS_SCREEN_TC5"));
             }
         }

@@ -7,7 +7,7 @@
 //   CTA = one 128-row tile of one feeder's sensitivity block x all (<= 96) hours.
 //   warp 0 (one lane)  TMA producer: per 64-wide k block one box of A (128 x 64 bf16) from
 //                      the feeder's tensor map and one box of B (96 x 64) from the map of
-//                      the time-major schedule, into a 5-stage ring (28 KB per stage)
+//                      the time-major schedule, into a 3-stage ring (28 KB per stage, 2 CTAs per SM)
 //   warp 1 (one lane)  MMA issuer: 4 x tcgen05.mma.kind::f16 (M=128, N=96, K=16) per stage,
 //                      tcgen05.commit frees the stage / signals the epilogue
 //   warps 2..5         epilogue: tcgen05.ld 32 lanes x 96 columns each (thread = row),
@@ -23,7 +23,7 @@ namespace revs {
 
 namespace {
 
-constexpr int kBM = 128, kBN = 96, kBK = 64, kStagesT = 5;
+constexpr int kBM = 128, kBN = 96, kBK = 64, kStagesT = 3;   // 87 KB -> two CTAs per SM
 constexpr int kUmmaK = 16;
 constexpr int kThreadsT = 192;                       // 6 warps
 constexpr uint32_t kABytes = kBM * kBK * 2, kBBytes = kBN * kBK * 2;
@@ -89,7 +89,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 // idesc: c=F32 (1<<4), a=BF16 (1<<7), b=BF16 (1<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
 
-__global__ void __launch_bounds__(kThreadsT, 1)
+__global__ void __launch_bounds__(kThreadsT, 2)
 screen_tc5_kernel(const ScreenProblem* __restrict__ problems, const ContractTile* __restrict__ tiles,
                   const CUtensorMap* __restrict__ maps_a, const CUtensorMap* __restrict__ map_b,
                   const int* __restrict__ b_col0, int T) {
