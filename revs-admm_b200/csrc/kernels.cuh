@@ -77,6 +77,10 @@ struct QpParams {
     int* n_failed;         // columns whose working set overflowed kWMax
     int* cls;              // [ncols] instantiation that owns the column (see qp_class_cap)
     int* n_cls;            // [kQpClasses] running columns per class after this round
+    const int* order;      // optional [kQpClasses][ncols] work lists (order_columns_kernel)
+    const int* order_count;   // [kQpClasses]
+    int ncols;
+    long long* trace;      // optional debug [ncols][12]: start ns, end ns, smid, class/m/pieces, phase cycles ...
     unsigned long long* dbg;  // optional [4 + 5*kQpClasses]: counts, then per-class phase cycles
     int T;
     int64_t Hp;
@@ -85,7 +89,9 @@ struct QpParams {
     int inner_max;
 };
 
-cudaError_t launch_utility_qp(const QpParams& P, int ncols, int cls, cudaStream_t stream);
+cudaError_t launch_utility_qp(const QpParams& P, int grid, int cls, cudaStream_t stream);
+cudaError_t launch_order_columns(const int* status, const int* cls, const int* wcount, int ncols, int* order,
+                                 int* order_count, cudaStream_t stream);
 
 // ---- contract_f64.cu
 int contract_tile_rows(int T);

@@ -115,6 +115,7 @@ struct revs_solver {
     // time-major [T][Hp]
     double *d_zt = nullptr, *d_lamt = nullptr, *d_gt = nullptr, *d_vt = nullptr;
     int *d_wcount = nullptr, *d_widx = nullptr, *d_status = nullptr, *d_innerok = nullptr, *d_cls = nullptr;
+    int *d_order = nullptr, *d_order_count = nullptr;
     Counters* d_cnt = nullptr;
     Counters* h_cnt = nullptr;           // pinned mirror
     double* d_diff = nullptr;
@@ -266,6 +267,16 @@ int utility_solve(revs_solver* s) {
     Q.n_failed = &s->d_cnt->n_failed;
     Q.cls = s->d_cls;
     Q.n_cls = s->d_cnt->n_cls;
+    Q.order = nullptr;
+    Q.order_count = s->d_order_count;
+    Q.ncols = s->ncols;
+    Q.trace = nullptr;
+    long long* d_trace = nullptr;
+    int trace_round = -1;
+    if (const char* e = getenv("REVS_DEBUG_TRACE")) {   // "<admm iteration>,<round>": per-column timeline of that launch
+        int ti = -1, tr = -1;
+        if (sscanf(e, "%d,%d", &ti, &tr) == 2 && ti == s->k) trace_round = tr;
+    }
     Q.dbg = getenv("REVS_DEBUG") ? s->d_cnt->dbg : nullptr;
     Q.T = s->T;
     Q.Hp = s->Hp;
@@ -289,7 +300,10 @@ int utility_solve(revs_solver* s) {
         s->stats.kernel_launches++;
     }
     Q.init = 0;
+    Q.order = s->d_order;
     int top_cls = 0;
+    int grid[kQpClasses];
+    for (int cl = 0; cl < kQpClasses; ++cl) grid[cl] = s->ncols;
     for (int round = 0;; ++round) {
         if (round >= kQpRoundMax)
             return fail(REVS_ERR_NOCONV, "utility QP: %d columns still running after %d working-set rounds",
@@ -308,6 +322,13 @@ int utility_solve(revs_solver* s) {
         s->stats.kernel_launches++;
         if (round == 0) s->stats.gemm_full_launches++;
         CU(cudaMemsetAsync(&s->d_cnt->n_running, 0, (1 + kQpClasses) * sizeof(int), s->sU));
+        if (round == trace_round) {
+            CU(cudaMalloc(&d_trace, sizeof(long long) * 12 * s->ncols));
+            CU(cudaMemsetAsync(d_trace, 0, sizeof(long long) * 12 * s->ncols, s->sU));
+            Q.trace = d_trace;
+        }
+        CU(launch_order_columns(s->d_status, s->d_cls, s->d_wcount, s->ncols, s->d_order, s->d_order_count, s->sU));
+        s->stats.kernel_launches++;
         // the larger classes go first, each on its own stream, so that their long CTAs
         // overlap with the many short ones of class 0
         CU(cudaEventRecord(s->evV, s->sU));
@@ -315,13 +336,13 @@ int utility_solve(revs_solver* s) {
             if (!use[cl]) continue;
             CU(cudaStreamWaitEvent(s->sQ[cl], s->evV, 0));
             sp = span_begin(s, 4, s->sQ[cl]);
-            CU(launch_utility_qp(Q, s->ncols, cl, s->sQ[cl]));
+            CU(launch_utility_qp(Q, grid[cl], cl, s->sQ[cl]));
             span_end(sp, s->sQ[cl]);
             CU(cudaEventRecord(s->evQ[cl], s->sQ[cl]));
             s->stats.kernel_launches++;
         }
         sp = span_begin(s, 3, s->sU);
-        CU(launch_utility_qp(Q, s->ncols, 0, s->sU));
+        CU(launch_utility_qp(Q, grid[0], 0, s->sU));
         span_end(sp, s->sU);
         s->stats.kernel_launches++;
         for (int cl = 1; cl < kQpClasses; ++cl)
@@ -330,6 +351,17 @@ int utility_solve(revs_solver* s) {
         s->stats.qp_outer_iterations++;
         CU(cudaMemcpyAsync(s->h_cnt, s->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, s->sU));
         CU(cudaStreamSynchronize(s->sU));
+        if (d_trace) {
+            std::vector<long long> hb((size_t)12 * s->ncols);
+            cudaMemcpy(hb.data(), d_trace, hb.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+            if (FILE* fp = fopen(getenv("REVS_DEBUG_TRACE_FILE") ? getenv("REVS_DEBUG_TRACE_FILE") : "revs_trace.bin", "wb")) {
+                fwrite(hb.data(), sizeof(long long), hb.size(), fp);
+                fclose(fp);
+            }
+            cudaFree(d_trace);
+            d_trace = nullptr;
+            Q.trace = nullptr;
+        }
         if (s->h_cnt->n_failed)
             return fail(REVS_ERR_NOCONV,
                         "utility QP: %d (feeder,hour) columns need more than %d simultaneously active "
@@ -342,7 +374,10 @@ int utility_solve(revs_solver* s) {
                     s->h_cnt->dbg[3]);
         if (s->h_cnt->n_running == 0) break;
         use[0] = true;
-        for (int cl = 1; cl < kQpClasses; ++cl) {
+        for (int cl = 0; cl < kQpClasses; ++cl) {
+            // columns only leave the running set or move up a class (counted in n_cls of the new class)
+            grid[cl] = s->h_cnt->n_cls[cl] < s->ncols ? s->h_cnt->n_cls[cl] : s->ncols;
+            if (cl == 0) continue;
             use[cl] = s->h_cnt->n_cls[cl] > 0;
             if (use[cl]) top_cls = cl;
         }
@@ -386,7 +421,7 @@ void free_all(revs_solver* s) {
     void* ptrs[] = {s->d_feeders, s->d_Rpool, s->d_rn2, s->d_Rbf, s->d_gbf, s->d_v32, s->d_sprob, s->d_stiles, s->d_maps_a, s->d_map_b, s->d_bcol0, s->d_pool_parent, s->d_pool_res, s->d_pool_cumr, s->d_pool_off, s->d_load, s->d_pest, s->d_psch[0], s->d_psch[1], s->d_gamma,
                     s->d_pev, s->d_soc, s->d_has_ev, s->d_rating, s->d_capacity, s->d_initial, s->d_indconst,
                     s->d_start, s->d_end, s->d_nmin, s->d_nmax, s->d_zero_i, s->d_cost, s->d_zt, s->d_lamt,
-                    s->d_gt, s->d_vt, s->d_wcount, s->d_widx, s->d_status, s->d_innerok, s->d_cls, s->d_cnt, s->d_diff,
+                    s->d_gt, s->d_vt, s->d_wcount, s->d_widx, s->d_status, s->d_innerok, s->d_cls, s->d_order, s->d_order_count, s->d_cnt, s->d_diff,
                     s->d_cprob, s->d_ctiles};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -516,6 +551,8 @@ int revs_create(revs_solver** out, int device, int n_feeders, const int64_t* fee
     TRY(dalloc(&s->d_status, (size_t)s->ncols));
     TRY(dalloc(&s->d_innerok, (size_t)s->ncols));
     TRY(dalloc(&s->d_cls, (size_t)s->ncols));
+    TRY(dalloc(&s->d_order, (size_t)s->ncols * kQpClasses));
+    TRY(dalloc(&s->d_order_count, (size_t)kQpClasses));
     TRY(dalloc(&s->d_cnt, (size_t)1));
     TRY(cudaHostAlloc((void**)&s->h_cnt, sizeof(Counters), cudaHostAllocDefault));
     memset(s->h_cnt, 0, sizeof(Counters));

@@ -56,6 +56,8 @@ struct QpSmem {
     int idx[WMAX], fl[WMAX], inA[WMAX];
     int chg[kChgMax];                     // homes that changed side of g>0 (index*2 + left)
     unsigned fmask[kMaskWords];           // F the stored Hessian was formed for
+    unsigned dmask[kMaskWords];           // scratch: homes that changed side since then
+    unsigned short pairs[40];             // (p<<8 | q) of the lower-triangle pairs (small working sets)
     int ired[THREADS / 32];
     int ibcast[2];
 };
@@ -150,17 +152,21 @@ __device__ void hessian(const double* __restrict__ R, int ld, int n, const doubl
     for (int a = 0; a < NBP; ++a)
 #pragma unroll
         for (int b = 0; b < NBQ; ++b) acc[a][b] = 0.0;
+    // the tile buffer holds kRows rows; fewer rows -> wider tiles -> fewer barriers
+    constexpr int kRows = ((TY * NBP > 16 * NBQ) ? TY * NBP : 16 * NBQ) < WMAX ? ((TY * NBP > 16 * NBQ) ? TY * NBP : 16 * NBQ) : WMAX;
+    constexpr int kJt = ((WMAX * kTld / kRows - 1) / 32 * 32) < 256 ? ((WMAX * kTld / kRows - 1) / 32 * 32) : 256;
+    constexpr int kTl = kJt + 1;
+    static_assert(kJt >= 32 && kRows * kTl <= WMAX * kTld, "tile does not fit");
     // rows beyond m read a zero row of the tile
-    constexpr int kRows = (TY * NBP > 16 * NBQ) ? TY * NBP : 16 * NBQ;
-    for (int p = m + warp; p < kRows && p < WMAX; p += THREADS / 32)
-        for (int l = lane; l < kJT; l += 32) sm.tileR[p * kTld + l] = 0.0;
+    for (int p = m + warp; p < kRows; p += THREADS / 32)
+        for (int l = lane; l < kJt; l += 32) sm.tileR[p * kTl + l] = 0.0;
     const int total = INCR ? nchg : n;
-    for (int j0 = 0; j0 < total; j0 += kJT) {
+    for (int j0 = 0; j0 < total; j0 += kJt) {
         __syncthreads();
         for (int p = warp; p < m; p += THREADS / 32) {
             const double* row = R + (size_t)sm.idx[p] * ld;
 #pragma unroll
-            for (int l = lane; l < kJT; l += 32) {
+            for (int l = lane; l < kJt; l += 32) {
                 const int c = j0 + l;
                 double val = 0.0;
                 if (INCR) {
@@ -168,19 +174,19 @@ __device__ void hessian(const double* __restrict__ R, int ld, int n, const doubl
                 } else {
                     if (c < n && g[c] > 0.0) val = row[c];
                 }
-                sm.tileR[p * kTld + l] = val;
+                sm.tileR[p * kTl + l] = val;
             }
         }
         __syncthreads();
-        const int jmax = min(kJT, total - j0);
+        const int jmax = min(kJt, total - j0);
 #pragma unroll 4
         for (int jj = 0; jj < jmax; ++jj) {
             double pa[NBP], qb[NBQ];
             const double sg = INCR ? ((sm.chg[j0 + jj] & 1) ? -1.0 : 1.0) : 1.0;
 #pragma unroll
-            for (int a = 0; a < NBP; ++a) pa[a] = sm.tileR[(ty + TY * a) * kTld + jj] * sg;
+            for (int a = 0; a < NBP; ++a) pa[a] = sm.tileR[(ty + TY * a) * kTl + jj] * sg;
 #pragma unroll
-            for (int b = 0; b < NBQ; ++b) qb[b] = sm.tileR[(tx + 16 * b) * kTld + jj];
+            for (int b = 0; b < NBQ; ++b) qb[b] = sm.tileR[(tx + 16 * b) * kTl + jj];
 #pragma unroll
             for (int a = 0; a < NBP; ++a)
 #pragma unroll
@@ -207,38 +213,113 @@ __device__ void hessian(const double* __restrict__ R, int ld, int n, const doubl
     __syncthreads();
 }
 
-// Compare F = {g>0} with the mask the stored H was formed for.  Returns the number of homes
-// that changed side (their indices*2+left? in sm.chg, ordered), or -1 if there are more than
-// kChgMax (the caller then recomputes H from scratch).  Updates the mask.
-template <int THREADS, class S>
-__device__ int mask_changes(const double* g, int n, S& sm) {
+// Small working sets (m <= kPairM): one (p,q) pair of the lower triangle per warp slot, the
+// lanes split the columns, partial sums stay in registers over all tiles and are reduced
+// with shuffles once at the end -- every thread does useful work and each accumulator is its
+// own dependency chain.  Same contract as hessian<>.
+constexpr int kPairM = 8;
+constexpr int kPairMax = kPairM * (kPairM + 1) / 2;     // 78
+
+template <int WMAX, int THREADS, bool INCR, class S>
+__device__ void hessian_pairs(const double* __restrict__ R, int ld, int n, const double* g, int m, int nchg, S& sm) {
+    constexpr int NW = THREADS / 32;
+    constexpr int kAcc = (kPairMax + NW - 1) / NW;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int base = 0;
-    bool overflow = false;
-    for (int j0 = 0; j0 < n; j0 += THREADS) {
-        const int j = j0 + tid;
-        const bool now = j < n && g[j] > 0.0;
-        const unsigned bal_now = __ballot_sync(0xffffffffu, now);
-        const unsigned old = (j0 + warp * 32 < n) ? sm.fmask[(j0 >> 5) + warp] : 0u;
-        const unsigned diff = bal_now ^ old;
-        __syncthreads();
-        if (lane == 0) { sm.ired[warp] = __popc(diff); if (j0 + warp * 32 < n) sm.fmask[(j0 >> 5) + warp] = bal_now; }
-        __syncthreads();
-        int before = 0, tot = 0;
+    const int npairs = m * (m + 1) / 2;
+    const int jt = min(256, (WMAX * kTld / m) & ~31), tl = jt + 1;
+    double acc[kAcc];
 #pragma unroll
-        for (int w = 0; w < THREADS / 32; ++w) {
-            before += (w < warp) ? sm.ired[w] : 0;
-            tot += sm.ired[w];
+    for (int k = 0; k < kAcc; ++k) acc[k] = 0.0;
+    for (int idx = tid; idx < npairs; idx += THREADS) {   // pair index -> (p, q), p >= q
+        int p = 0;
+        while ((p + 1) * (p + 2) / 2 <= idx) ++p;
+        sm.pairs[idx] = (unsigned short)((p << 8) | (idx - p * (p + 1) / 2));
+    }
+    const int total = INCR ? nchg : n;
+    for (int j0 = 0; j0 < total; j0 += jt) {
+        __syncthreads();
+        for (int p = warp; p < m; p += NW) {
+            const double* row = R + (size_t)sm.idx[p] * ld;
+            for (int l = lane; l < jt; l += 32) {
+                const int c = j0 + l;
+                double val = 0.0;
+                if (INCR) {
+                    if (c < nchg) val = row[sm.chg[c] >> 1];
+                } else if (c < n) {
+                    const double rv = row[c];
+                    val = g[c] > 0.0 ? rv : 0.0;
+                }
+                sm.tileR[p * tl + l] = val;
+            }
         }
-        if ((diff >> lane) & 1u) {
-            const int pos = base + before + __popc(diff & ((1u << lane) - 1));
-            if (pos < kChgMax) sm.chg[pos] = (j << 1) | (now ? 0 : 1);     // low bit: left F
+        __syncthreads();
+        const int jmax = min(jt, total - j0);
+#pragma unroll
+        for (int k = 0; k < kAcc; ++k) {
+            if (warp + k * NW >= npairs) break;
+            const int pq = sm.pairs[warp + k * NW];
+            const double* tp = sm.tileR + (pq >> 8) * tl;
+            const double* tq = sm.tileR + (pq & 255) * tl;
+            double a = acc[k];
+            for (int l = lane; l < jmax; l += 32) {
+                double prod = tp[l] * tq[l];
+                if (INCR && (sm.chg[j0 + l] & 1)) prod = -prod;
+                a += prod;
+            }
+            acc[k] = a;
         }
-        base += tot;
-        if (base > kChgMax) overflow = true;
     }
     __syncthreads();
-    return overflow ? -1 : base;
+#pragma unroll
+    for (int k = 0; k < kAcc; ++k) {
+        if (warp + k * NW >= npairs) break;
+        const double v = warp_sum(acc[k]);
+        if (lane == 0) {
+            const int pq = sm.pairs[warp + k * NW], p = pq >> 8, q = pq & 255;
+            if (p == q) { if (INCR) sm.hdiag[p] += v; else sm.hdiag[p] = v; }
+            else { double* h = &sm.Hb[p * (WMAX + 1) + q]; if (INCR) *h += v; else *h = v; }
+        }
+    }
+    __syncthreads();
+}
+
+// Compare F = {g>0} with the mask the stored H was formed for.  Returns the number of homes
+// that changed side (index*2 + left? in sm.chg, ascending), or -1 if there are more than
+// kChgMax (the caller then recomputes H from scratch).  Updates the mask.  Every warp owns a
+// contiguous range of 32-home words, so ordering needs one prefix over the warps only.
+template <int THREADS, class S>
+__device__ int mask_changes(const double* g, int n, S& sm) {
+    constexpr int NW = THREADS / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwords = (n + 31) >> 5, wpw = (nwords + NW - 1) / NW;
+    const int w0 = warp * wpw, w1 = min(nwords, w0 + wpw);
+    int cnt = 0;
+    for (int w = w0; w < w1; ++w) {
+        const int j = (w << 5) + lane;
+        const unsigned now = __ballot_sync(0xffffffffu, j < n && g[j] > 0.0);
+        const unsigned diff = now ^ sm.fmask[w];
+        if (lane == 0) { sm.fmask[w] = now; sm.dmask[w] = diff; }
+        cnt += __popc(diff);
+    }
+    if (lane == 0) sm.ired[warp] = cnt;
+    __syncthreads();
+    int before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        before += (w < warp) ? sm.ired[w] : 0;
+        total += sm.ired[w];
+    }
+    if (total <= kChgMax) {
+        int pos = before;
+        for (int w = w0; w < w1; ++w) {
+            const unsigned diff = sm.dmask[w], now = sm.fmask[w];
+            if ((diff >> lane) & 1u)
+                sm.chg[pos + __popc(diff & ((1u << lane) - 1))] = ((((w << 5) + lane)) << 1) | (((now >> lane) & 1u) ? 0 : 1);
+            pos += __popc(diff);
+        }
+    }
+    __syncthreads();
+    return total > kChgMax ? -1 : total;
 }
 
 // ---- dense SPD solves in shared memory on a principal sub-matrix of H.  The factor lives
@@ -380,8 +461,15 @@ __global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     S& sm = *reinterpret_cast<S*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int c = blockIdx.x;
+    int c = blockIdx.x;
+    if (P.order) {             // longest-first list of this class's running columns
+        if ((int)blockIdx.x >= P.order_count[CLS]) return;
+        c = P.order[(size_t)CLS * P.ncols + blockIdx.x];
+    }
     const int f = c / P.T, t = c % P.T;
+    long long tr_start = 0;
+    const long long tr_clk0 = clock64();
+    if (P.trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_start));
     if (!P.init && P.status[c] != 0) return;
     if ((CLS > 0 || !P.init) && P.cls[c] != CLS) return;   // column of another instantiation
 
@@ -540,6 +628,13 @@ __global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
     long long tc[5] = {0, 0, 0, 0, 0}, t0 = clock64(), t1;   // phase cycles (debug)
 #define PHASE(i) do { t1 = clock64(); tc[i] += t1 - t0; t0 = t1; } while (0)
     const int inner_max = (P.init == 2) ? 0 : P.inner_max;   // init==2: evaluate the warm start only
+    double scale = 0.0;                         // mean |R_a|^2 over W: curvature scale of the Hessian shifts
+    if (inner_max > 0 && m > 0) {
+        double sc[1] = {0.0};
+        for (int a = tid; a < m; a += THREADS) sc[0] += rn2[sm.idx[a]];
+        block_sum<1, THREADS>(sc, sm);
+        scale = sc[0] / (double)m;
+    }
     for (; its < inner_max; ++its) {
         __syncthreads();
         // gradient on W:  u - R[idx_a] . g
@@ -577,6 +672,10 @@ __global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
             constexpr int TY = THREADS / 16;
             const int nq = (m + 15) >> 4, np_ = (m + TY - 1) / TY;
             (void)nq; (void)np_;
+            if (m <= kPairM) {
+                if (have_H && nchg >= 0) { if (nchg > 0) hessian_pairs<WMAX, THREADS, true>(R, ld, n, g, m, nchg, sm); }
+                else hessian_pairs<WMAX, THREADS, false>(R, ld, n, g, m, 0, sm);
+            } else {
 #define HESS(NP, NQ)                                                                          \
     do {                                                                                      \
         if (have_H && nchg >= 0) { if (nchg > 0) hessian<WMAX, THREADS, NP, NQ, true>(R, ld, n, g, m, nchg, sm); } \
@@ -596,14 +695,11 @@ __global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
                 else HESS((WMAX > 64 ? 8 : 4), (WMAX > 64 ? 8 : 4));
             }
 #undef HESS
+            }
             flops += (double)m * (m + 1) * ((nchg >= 0 && have_H) ? nchg : n);   // lower triangle, 2 flops per MAC
             have_H = true;
         }
         PHASE(1);
-        double sc[1] = {0.0};
-        for (int a = tid; a < m; a += THREADS) sc[0] += rn2[sm.idx[a]];
-        block_sum<1, THREADS>(sc, sm);
-        const double scale = sc[0] / (double)m;      // mean |R_a|^2: curvature scale
         const double shift = kHessShift * scale + 1e-300;
 
         // ---- exact minimiser of the piece over lam_W >= 0: primal-dual active set
@@ -720,6 +816,15 @@ __global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
         atomicAdd(P.newton_its, (unsigned long long)its);
         atomicMax(P.max_ws, m);
         atomicAdd(P.flops, (unsigned long long)flops);
+        if (P.trace) {
+            long long tr_end; unsigned smid;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_end));
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            long long* rec = P.trace + 12 * (size_t)c;
+            rec[0] = tr_start; rec[1] = tr_end; rec[2] = smid; rec[3] = ((long long)CLS << 40) | ((long long)m << 20) | its;
+            for (int i = 0; i < 5; ++i) rec[4 + i] = tc[i];
+            rec[9] = n_pdas; rec[10] = n_evals; rec[11] = clock64() - tr_clk0;
+        }
         if (P.dbg) {
             atomicAdd(P.dbg + 0, (unsigned long long)n_evals);
             atomicAdd(P.dbg + 1, (unsigned long long)n_pdas);
@@ -730,9 +835,42 @@ __global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
     }
 }
 
+// Work list per class for one working-set round: running columns of the class, largest
+// previous working set first (longest-processing-time-first keeps the tail of a launch
+// short: a column with 30 rows costs ~10x one with 3).  Counting sort, one CTA.
+__global__ void __launch_bounds__(1024) order_columns_kernel(const int* __restrict__ status, const int* __restrict__ cls,
+                                                             const int* __restrict__ wcount, int ncols,
+                                                             int* __restrict__ order, int* __restrict__ order_count) {
+    __shared__ int hist[kQpClasses][kWMax + 2];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < kQpClasses * (kWMax + 2); i += 1024) (&hist[0][0])[i] = 0;
+    __syncthreads();
+    for (int c = tid; c < ncols; c += 1024)
+        if (status[c] == 0) atomicAdd(&hist[cls[c]][kWMax - min(wcount[c], kWMax)], 1);
+    __syncthreads();
+    if (tid < kQpClasses) {
+        int acc = 0;
+        for (int k = 0; k <= kWMax; ++k) { int h = hist[tid][k]; hist[tid][k] = acc; acc += h; }
+        order_count[tid] = acc;
+    }
+    __syncthreads();
+    for (int c = tid; c < ncols; c += 1024)
+        if (status[c] == 0) {
+            const int cl = cls[c];
+            const int pos = atomicAdd(&hist[cl][kWMax - min(wcount[c], kWMax)], 1);
+            order[(size_t)cl * ncols + pos] = c;
+        }
+}
+
+cudaError_t launch_order_columns(const int* status, const int* cls, const int* wcount, int ncols, int* order,
+                                 int* order_count, cudaStream_t stream) {
+    order_columns_kernel<<<1, 1024, 0, stream>>>(status, cls, wcount, ncols, order, order_count);
+    return cudaGetLastError();
+}
+
 constexpr int kMinB0 = 6, kMinB1 = 3;    // resident CTAs per SM the small / medium instantiations are compiled for
 
-cudaError_t launch_utility_qp(const QpParams& P, int ncols, int cls, cudaStream_t stream) {
+cudaError_t launch_utility_qp(const QpParams& P, int grid, int cls, cudaStream_t stream) {
     using S0 = QpSmem<32, 128>;
     using S1 = QpSmem<64, 256>;
     using S2 = QpSmem<kWMax, 256>;
@@ -749,9 +887,10 @@ cudaError_t launch_utility_qp(const QpParams& P, int ncols, int cls, cudaStream_
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    if (cls == 0) k0<<<ncols, 128, sizeof(S0), stream>>>(P);
-    else if (cls == 1) k1<<<ncols, 256, sizeof(S1), stream>>>(P);
-    else k2<<<ncols, 256, sizeof(S2), stream>>>(P);
+    if (grid <= 0) return cudaSuccess;
+    if (cls == 0) k0<<<grid, 128, sizeof(S0), stream>>>(P);
+    else if (cls == 1) k1<<<grid, 256, sizeof(S1), stream>>>(P);
+    else k2<<<grid, 256, sizeof(S2), stream>>>(P);
     return cudaGetLastError();
 }
 
