@@ -126,6 +126,28 @@ cudaError_t launch_sens_flow(const int* parent, const int* row_node, const int* 
     sens_flow_kernel<<<grid, 128, 0, s>>>(parent, row_node, res_node, n_rows, n_res, out, ld);
     return cudaGetLastError();
 }
+// compact [H][w] <-> padded [Hp][w] home-major arrays (hmap[h] = padded row of compact home h)
+__global__ void pack_rows_kernel(const double* __restrict__ src, double* __restrict__ dst, const int64_t* __restrict__ hmap,
+                                 int64_t H, int w, int to_padded) {
+    const int64_t total = H * w;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t h = i / w;
+        const int k = (int)(i - h * w);
+        const int64_t p = hmap[h] * w + k;
+        if (to_padded) dst[p] = src[i];
+        else dst[i] = src[p];
+    }
+}
+
+cudaError_t launch_pack_rows(const double* src, double* dst, const int64_t* hmap, int64_t H, int w, int to_padded,
+                             cudaStream_t s) {
+    if (H == 0) return cudaSuccess;
+    int64_t blocks = (H * w + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    pack_rows_kernel<<<(unsigned)blocks, 256, 0, s>>>(src, dst, hmap, H, w, to_padded);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_to_time_major(const double* in, int n, int T, double* out, int64_t ld, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
     dim3 grid((n + 31) / 32, (T + 31) / 32), block(32, 8);

@@ -125,6 +125,8 @@ cudaError_t launch_sens_flow(const int* parent, const int* row_node, const int* 
                              int n_res, double* out, int ld, cudaStream_t s);
 cudaError_t launch_row_norms(const FeederDev* feeders, int n_feeders, const double* Rpool, double* rn2,
                              cudaStream_t s);
+cudaError_t launch_pack_rows(const double* src, double* dst, const int64_t* hmap, int64_t H, int w, int to_padded,
+                             cudaStream_t s);
 cudaError_t launch_to_time_major(const double* in, int n, int T, double* out, int64_t ld, cudaStream_t s);
 
 }  // namespace revs

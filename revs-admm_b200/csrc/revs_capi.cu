@@ -89,6 +89,8 @@ struct revs_solver {
     FeederDev* d_feeders = nullptr;
     double* d_Rpool = nullptr;
     double* d_rn2 = nullptr;
+    double* d_stage = nullptr;                 // compact staging [H][T+1] for host transfers
+    int64_t* d_hmap = nullptr;                 // compact home -> padded home
     void *d_Rbf = nullptr, *d_gbf = nullptr;   // BF16 copies for the screening contraction
     float* d_v32 = nullptr;
     ScreenProblem* d_sprob = nullptr;
@@ -202,21 +204,19 @@ void count_window(double rating, double cap, double init, int* nmin, int* nmax) 
     *nmax = hi;
 }
 
-// copy a compact host array [H][w] into the padded device layout [Hp][w] (and back)
+// copy a compact host array [H][w] into the padded device layout [Hp][w] (and back): one
+// transfer through a device staging buffer plus a scatter / gather kernel, independent of
+// the number of feeders
 int h2d_homes(revs_solver* s, double* dst, const double* src, int w) {
-    for (int f = 0; f < s->nf; ++f) {
-        size_t n = (size_t)(s->off[f + 1] - s->off[f]) * w;
-        if (n) CU(cudaMemcpyAsync(dst + (size_t)s->feeders[f].off * w, src + (size_t)s->off[f] * w,
-                                  n * sizeof(double), cudaMemcpyHostToDevice, s->sU));
-    }
+    if (s->H == 0) return REVS_OK;
+    CU(cudaMemcpyAsync(s->d_stage, src, (size_t)s->H * w * sizeof(double), cudaMemcpyHostToDevice, s->sU));
+    CU(launch_pack_rows(s->d_stage, dst, s->d_hmap, s->H, w, 1, s->sU));
     return REVS_OK;
 }
 int d2h_homes(const revs_solver* s, double* dst, const double* src, int w) {
-    for (int f = 0; f < s->nf; ++f) {
-        size_t n = (size_t)(s->off[f + 1] - s->off[f]) * w;
-        if (n) CU(cudaMemcpyAsync(dst + (size_t)s->off[f] * w, src + (size_t)s->feeders[f].off * w,
-                                  n * sizeof(double), cudaMemcpyDeviceToHost, s->sU));
-    }
+    if (s->H == 0) return REVS_OK;
+    CU(launch_pack_rows(src, s->d_stage, s->d_hmap, s->H, w, 0, s->sU));
+    CU(cudaMemcpyAsync(dst, s->d_stage, (size_t)s->H * w * sizeof(double), cudaMemcpyDeviceToHost, s->sU));
     return REVS_OK;
 }
 
@@ -418,7 +418,7 @@ HomeParams home_params(revs_solver* s, int individual) {
 
 void free_all(revs_solver* s) {
     cudaSetDevice(s->device);
-    void* ptrs[] = {s->d_feeders, s->d_Rpool, s->d_rn2, s->d_Rbf, s->d_gbf, s->d_v32, s->d_sprob, s->d_stiles, s->d_maps_a, s->d_map_b, s->d_bcol0, s->d_pool_parent, s->d_pool_res, s->d_pool_cumr, s->d_pool_off, s->d_load, s->d_pest, s->d_psch[0], s->d_psch[1], s->d_gamma,
+    void* ptrs[] = {s->d_feeders, s->d_Rpool, s->d_rn2, s->d_stage, s->d_hmap, s->d_Rbf, s->d_gbf, s->d_v32, s->d_sprob, s->d_stiles, s->d_maps_a, s->d_map_b, s->d_bcol0, s->d_pool_parent, s->d_pool_res, s->d_pool_cumr, s->d_pool_off, s->d_load, s->d_pest, s->d_psch[0], s->d_psch[1], s->d_gamma,
                     s->d_pev, s->d_soc, s->d_has_ev, s->d_rating, s->d_capacity, s->d_initial, s->d_indconst,
                     s->d_start, s->d_end, s->d_nmin, s->d_nmax, s->d_zero_i, s->d_cost, s->d_zt, s->d_lamt,
                     s->d_gt, s->d_vt, s->d_wcount, s->d_widx, s->d_status, s->d_innerok, s->d_cls, s->d_order, s->d_order_count, s->d_cnt, s->d_diff,
@@ -517,6 +517,14 @@ int revs_create(revs_solver** out, int device, int n_feeders, const int64_t* fee
     TRY(cudaMemcpy(s->d_feeders, s->feeders.data(), sizeof(FeederDev) * n_feeders, cudaMemcpyHostToDevice));
     TRY(dalloc(&s->d_Rpool, (size_t)rp));
     TRY(dalloc(&s->d_rn2, (size_t)hp));
+    TRY(dalloc(&s->d_stage, (size_t)s->H * (T + 1)));
+    {
+        std::vector<int64_t> hmap((size_t)s->H);
+        for (int f = 0; f < n_feeders; ++f)
+            for (int64_t i = feeder_off[f]; i < feeder_off[f + 1]; ++i) hmap[i] = s->feeders[f].off + (i - feeder_off[f]);
+        TRY(dalloc(&s->d_hmap, hmap.size()));
+        TRY(cudaMemcpy(s->d_hmap, hmap.data(), hmap.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+    }
     s->Rpool_elems = (size_t)rp;
     TRY(cudaMalloc(&s->d_Rbf, (size_t)(rp ? rp : 1) * 2));
     TRY(cudaMemset(s->d_Rbf, 0, (size_t)(rp ? rp : 1) * 2));

@@ -92,6 +92,47 @@ def tree_from_graph(graph):
                       edge_keys=keys, edge_sign=sign, edge_type=types)
 
 
+def split_zones(tree):
+    """Split a feeder at the substation into its independent voltage zones.
+
+    Two nodes that leave the substation on different lines share no edge of their root
+    paths, so the sensitivity matrix R (lpsolver.py:17-26) is block diagonal over the
+    subtrees of the substation's children -- the reference's `<net>-com.txt` communities are
+    exactly these blocks.  The operator QP therefore separates over them, and solving the
+    zones as separate (smaller) feeders is the same problem with less memory, less work and
+    smaller working sets.  Returns [(zone_tree, home_positions)], home_positions indexing the
+    residence order of `tree`; zones without residences are dropped."""
+    n = tree.n_nodes
+    zone = np.empty(n, dtype=np.int64)
+    nz = 0
+    for i in range(n):
+        p = tree.parent[i]
+        if p < 0:
+            zone[i] = nz
+            nz += 1
+        else:
+            zone[i] = zone[p]
+    res_zone = zone[tree.res_node]
+    out = []
+    for z in range(nz):
+        homes = np.nonzero(res_zone == z)[0]
+        if len(homes) == 0:
+            continue
+        nodes = np.nonzero(zone == z)[0]                    # ascending -> still topological
+        local = np.full(n, -1, dtype=np.int64)
+        local[nodes] = np.arange(len(nodes))
+        par = tree.parent[nodes]
+        par = np.where(par >= 0, local[np.maximum(par, 0)], -1).astype(np.int32)
+        zt = FeederTree(parent=par, r=tree.r[nodes].copy(), res_node=local[tree.res_node[homes]].astype(np.int32),
+                        node_ids=[tree.node_ids[i] for i in nodes] if tree.node_ids else [],
+                        res_ids=[tree.res_ids[i] for i in homes] if tree.res_ids else [],
+                        edge_keys=[tree.edge_keys[i] for i in nodes] if tree.edge_keys else [],
+                        edge_sign=tree.edge_sign[nodes].copy() if tree.edge_sign is not None else None,
+                        edge_type=[tree.edge_type[i] for i in nodes] if tree.edge_type else [])
+        out.append((zt, homes))
+    return out
+
+
 def synthetic_feeder(n_homes, seed=0, laterals=5, homes_per_xfmr=2.5,
                      r_primary=1.0e-6, r_secondary=3.2e-4):
     """Synthetic radial feeder shaped like the reference's 121144 network: a substation,

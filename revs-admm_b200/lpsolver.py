@@ -17,7 +17,7 @@ ABI of include/revs_admm.h; if the library or the GPU is missing these calls rai
 import numpy as np
 
 from . import _cabi
-from .feeder import tree_from_graph
+from .feeder import split_zones, tree_from_graph
 
 __all__ = ["compute_Rmat", "Home", "Utility", "solve_ADMM", "solve_residence",
            "solve_residences", "solve_central", "compute_voltage", "compute_flows"]
@@ -41,14 +41,24 @@ def _home_arrays(homes, res):
                 start=start, end=end)
 
 
-def _solver_for_graph(graph, homes, cost, device=0):
+def _zones(graph):
+    """Rooted tree of the feeder, its independent voltage zones (subtrees of the substation's
+    children; R is block diagonal over them) and the residence permutation zone order ->
+    reference order."""
     tree = tree_from_graph(graph)
+    zones = split_zones(tree)
+    perm = np.concatenate([h for _, h in zones]) if zones else np.zeros(0, dtype=np.int64)
+    return tree, zones, perm
+
+
+def _solver_for_graph(graph, homes, cost, device=0):
+    tree, zones, perm = _zones(graph)
     res = tree.res_ids
-    s = _cabi.Solver([len(res)], len(cost), device=device)
-    s.set_feeder_tree(0, tree.parent, tree.r, tree.res_node)
-    s.set_homes(**_home_arrays(homes, res))
+    s = _cabi.Solver([len(h) for _, h in zones], len(cost), device=device)
+    s.set_feeder_trees([z for z, _ in zones])
+    s.set_homes(**_home_arrays(homes, [res[i] for i in perm]))
     s.set_tariff(cost)
-    return s, tree, res
+    return s, tree, res, perm
 
 
 def _as_table(tab, res, T):
@@ -101,7 +111,7 @@ class Utility:
     """The operator's estimate under the voltage limits (lpsolver.py:160-240)."""
 
     def __init__(self, graph, P_util, P_sch, Gamma, kappa=5.0, vset=1.0, low=0.95, high=1.05):
-        self.tree = tree_from_graph(graph)
+        self.tree, self.zones, self.perm = _zones(graph)
         self.res = self.tree.res_ids
         self.nodes = [n for n in graph.nodes if graph.nodes[n]["label"] != "S"]
         self.N = len(self.nodes)
@@ -110,12 +120,12 @@ class Utility:
         self._in = [_as_table(x, self.res, self.T) for x in (P_util, P_sch, Gamma)]
 
     def solve(self, grbpath=None):
-        with _cabi.Solver([len(self.res)], self.T) as s:
-            s.set_feeder_tree(0, self.tree.parent, self.tree.r, self.tree.res_node)
-            g, lam = s.utility_step(*self._in, kappa=self.kappa, vset=self.vset,
+        with _cabi.Solver([len(h) for _, h in self.zones], self.T) as s:
+            s.set_feeder_trees([z for z, _ in self.zones])
+            g, lam = s.utility_step(*[x[self.perm] for x in self._in], kappa=self.kappa, vset=self.vset,
                                     vlow=self.low, vhigh=self.high)
-        self.g_opt = {h: g[i].tolist() for i, h in enumerate(self.res)}
-        self.lam_opt = {h: lam[i] for i, h in enumerate(self.res)}
+        self.g_opt = {self.res[j]: g[k].tolist() for k, j in enumerate(self.perm)}
+        self.lam_opt = {self.res[j]: lam[k] for k, j in enumerate(self.perm)}
         return
 
 
@@ -127,15 +137,17 @@ def solve_ADMM(homes, graph, cost, grbpath=None, kappa=5.0, iter_max=15,
     Returns ``diff, P_sch, S, C`` exactly like the reference: diff[k][h] for k=1..iter_max,
     and the last iterate's residence profile, EV charger profile and SOC profile per home.
     ``tol`` > 0 (an extension) stops once both ADMM residuals fall below it."""
-    s, tree, res = _solver_for_graph(graph, homes, cost, device)
+    s, tree, res, perm = _solver_for_graph(graph, homes, cost, device)
     with s:
         done = s.solve_admm(kappa=kappa, iter_max=iter_max, vset=vset, vlow=vlow, vhigh=vhigh, tol=tol)
         out = s.results(done)
         stats = s.stats()
-    diff = {k + 1: {h: out["diff"][k, i] for i, h in enumerate(res)} for k in range(done)}
-    P = {h: out["P_sch"][i] for i, h in enumerate(res)}
-    S = {h: out["P_ev"][i] for i, h in enumerate(res)}
-    Csoc = {h: out["SOC"][i] for i, h in enumerate(res)}
+    inv = np.empty(len(perm), dtype=np.int64)          # reference residence index -> solver row
+    inv[perm] = np.arange(len(perm))
+    diff = {k + 1: {h: out["diff"][k, inv[i]] for i, h in enumerate(res)} for k in range(done)}
+    P = {h: out["P_sch"][inv[i]] for i, h in enumerate(res)}
+    S = {h: out["P_ev"][inv[i]] for i, h in enumerate(res)}
+    Csoc = {h: out["SOC"][inv[i]] for i, h in enumerate(res)}
     if return_stats:
         return diff, P, S, Csoc, stats
     return diff, P, S, Csoc
@@ -167,19 +179,31 @@ def solve_central(tariff, homes, dist, path=None, vset=1.0, vmin=0.9, vmax=1.05)
 
 
 # ------------------------------------------------------------------ reliability check
-def _schedule_rows(p_sch, tree):
+def _reliability(graph, p_sch, kind, vset, scale_of_zone, fill, device):
+    """Run the contraction zone by zone; nodes of zones without residences get `fill`."""
+    tree, zones, perm = _zones(graph)
     T = len(next(iter(p_sch.values())))
-    return np.array([np.asarray(p_sch[h], dtype=np.float64) for h in tree.res_ids]).reshape(tree.n_res, T), T
+    out = {}
+    if zones:
+        P = np.array([np.asarray(p_sch[tree.res_ids[j]], dtype=np.float64) for j in perm]).reshape(len(perm), T)
+        off = np.concatenate([[0], np.cumsum([len(h) for _, h in zones])])
+        with _cabi.Solver([len(h) for _, h in zones], T, device=device) as s:
+            s.set_feeder_trees([z for z, _ in zones])
+            for f, (z, _) in enumerate(zones):
+                vals = s.reliability(f, kind, np.arange(z.n_nodes), vset=vset, scale=scale_of_zone(z),
+                                     P=P[off[f]:off[f + 1]])
+                out[f] = (z, vals)
+    return tree, T, out, fill
 
 
 def compute_voltage(graph, p_sch, vset=1.0, device=0):
     """drawing.py:62-78: {node: voltage profile} for every non-substation node."""
-    tree = tree_from_graph(graph)
-    P, T = _schedule_rows(p_sch, tree)
-    with _cabi.Solver([tree.n_res], T, device=device) as s:
-        s.set_feeder_tree(0, tree.parent, tree.r, tree.res_node)
-        V = s.reliability(0, _cabi.REVS_REL_VOLTAGE, np.arange(tree.n_nodes), vset=vset, P=P)
-    return {n: V[i].tolist() for i, n in enumerate(tree.node_ids)}
+    tree, T, out, _ = _reliability(graph, p_sch, _cabi.REVS_REL_VOLTAGE, vset, lambda z: None, vset, device)
+    volt = {n: [vset] * T for n in tree.node_ids}
+    for z, V in out.values():
+        for i, n in enumerate(z.node_ids):
+            volt[n] = V[i].tolist()
+    return volt
 
 
 LINE_RATING_KVA = {  # conductor ampacity x voltage, drawing.py:30-40
@@ -192,10 +216,12 @@ LINE_RATING_KVA = {  # conductor ampacity x voltage, drawing.py:30-40
 
 def compute_flows(graph, p_sch, device=0):
     """drawing.py:28-60: {edge: signed loading = flow / rating} for every line."""
-    tree = tree_from_graph(graph)
-    P, T = _schedule_rows(p_sch, tree)
-    rating = np.array([np.sqrt(3) * LINE_RATING_KVA[t] for t in tree.edge_type])
-    with _cabi.Solver([tree.n_res], T, device=device) as s:
-        s.set_feeder_tree(0, tree.parent, tree.r, tree.res_node)
-        F = s.reliability(0, _cabi.REVS_REL_FLOW, np.arange(tree.n_nodes), scale=tree.edge_sign / rating, P=P)
-    return {e: F[i].tolist() for i, e in enumerate(tree.edge_keys)}
+    def scale(z):
+        rating = np.array([np.sqrt(3) * LINE_RATING_KVA[t] for t in z.edge_type])
+        return z.edge_sign / rating
+    tree, T, out, _ = _reliability(graph, p_sch, _cabi.REVS_REL_FLOW, 1.0, scale, 0.0, device)
+    flows = {e: [0.0] * T for e in tree.edge_keys}
+    for z, F in out.values():
+        for i, e in enumerate(z.edge_keys):
+            flows[e] = F[i].tolist()
+    return flows
