@@ -8,8 +8,9 @@ namespace revs {
 constexpr int kPad = 16;        // residences of a feeder are padded to a multiple of this
 constexpr int kWMax = 128;      // largest working set of a (feeder,hour) utility QP column
 constexpr int kAddMax = 32;     // violated voltage rows admitted per working-set round
-constexpr int kQpClasses = 3;   // utility QP instantiations by working-set capacity
-__host__ __device__ constexpr int qp_class_cap(int cls) { return cls == 0 ? 32 : (cls == 1 ? 64 : kWMax); }
+constexpr int kWW = 16;         // working-set capacity of the warp-per-column QP kernel
+constexpr int kQpClasses = 4;   // utility QP instantiations: 0 = warp kernel, 1..3 = CTA kernels by capacity
+__host__ __device__ constexpr int qp_class_cap(int cls) { return cls == 0 ? kWW : (cls == 1 ? 32 : (cls == 2 ? 64 : kWMax)); }
 
 // One feeder of the batch as the kernels see it.
 struct FeederDev {

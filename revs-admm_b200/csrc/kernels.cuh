@@ -90,6 +90,10 @@ struct QpParams {
 };
 
 cudaError_t launch_utility_qp(const QpParams& P, int grid, int cls, cudaStream_t stream);
+// ---- utility_qp_warp.cu
+int qp_warp_max_n();
+cudaError_t launch_qp_init(const QpParams& P, int max_warp_n, cudaStream_t stream);
+cudaError_t launch_utility_qp_warp(const QpParams& P, int n_cols_bound, int max_n, cudaStream_t stream);
 cudaError_t launch_order_columns(const int* status, const int* cls, const int* wcount, int ncols, int* order,
                                  int* order_count, cudaStream_t stream);
 

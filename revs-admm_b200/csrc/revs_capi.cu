@@ -14,6 +14,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <cstdlib>
 #include <cmath>
 #include <string>
@@ -96,6 +97,7 @@ struct revs_solver {
     ScreenProblem* d_sprob = nullptr;
     ContractTile* d_stiles = nullptr;
     int n_stiles = 0;
+    bool use_warp_kernel = true;               // class 0: one warp per small column (utility_qp_warp.cu)
     bool screen = true;                        // BF16 screening + exact recheck instead of the FP64 contraction in the loop
     int screen_impl = 0;                       // 0: mma.sync kernel, 1: tcgen05/TMEM/TMA kernel
     void *d_maps_a = nullptr, *d_map_b = nullptr;   // CUtensorMap per feeder block / for the bf16 schedule
@@ -284,21 +286,22 @@ int utility_solve(revs_solver* s) {
     Q.tol = kQpTol;
     Q.inner_max = kQpInnerMax;
 
-    // First launch of the solve: evaluate the warm start only (g = [z - R lam]_+), so that
-    // the first descent already sees the voltages of the new target z.
-    Q.init = 2;
-    TimedSpan* sp = nullptr;
-    bool use[kQpClasses];
-    for (int cl = 0; cl < kQpClasses; ++cl) {
-        // a class whose capacity no warm-start set can need is skipped: all multipliers come
-        // from the previous ADMM iteration, whose largest class is known
-        use[cl] = cl <= s->warm_cls;
-        if (!use[cl]) continue;
-        sp = span_begin(s, cl == 0 ? 3 : 4, s->sU);
-        CU(launch_utility_qp(Q, s->ncols, cl, s->sU));
-        span_end(sp, s->sU);
-        s->stats.kernel_launches++;
+    // Start of the solve: working sets from the stored multipliers, class by their size,
+    // g = [z - R lam]_+ for the new target -- one warp per column.
+    Q.init = 0;
+    int max_n = 0, warp_n = 0;                     // largest zone / largest zone the warp kernel takes
+    for (int f = 0; f < s->nf; ++f) {
+        max_n = std::max(max_n, s->feeders[f].n);
+        if (s->feeders[f].n <= qp_warp_max_n()) warp_n = std::max(warp_n, s->feeders[f].n);
     }
+    const int max_warp_n = s->use_warp_kernel ? qp_warp_max_n() : 0;
+    TimedSpan* sp = span_begin(s, 3, s->sU);
+    CU(launch_qp_init(Q, max_warp_n, s->sU));
+    span_end(sp, s->sU);
+    s->stats.kernel_launches++;
+    bool use[kQpClasses];
+    for (int cl = 0; cl < kQpClasses; ++cl) use[cl] = cl <= s->warm_cls || cl <= 1;
+    if (max_warp_n == 0 || warp_n == 0) use[0] = false;
     Q.init = 0;
     Q.order = s->d_order;
     int top_cls = 0;
@@ -330,21 +333,23 @@ int utility_solve(revs_solver* s) {
         CU(launch_order_columns(s->d_status, s->d_cls, s->d_wcount, s->ncols, s->d_order, s->d_order_count, s->sU));
         s->stats.kernel_launches++;
         // the larger classes go first, each on its own stream, so that their long CTAs
-        // overlap with the many short ones of class 0
+        // overlap with the many short columns of the small classes
         CU(cudaEventRecord(s->evV, s->sU));
         for (int cl = kQpClasses - 1; cl >= 1; --cl) {
             if (!use[cl]) continue;
             CU(cudaStreamWaitEvent(s->sQ[cl], s->evV, 0));
-            sp = span_begin(s, 4, s->sQ[cl]);
+            sp = span_begin(s, cl == 1 ? 3 : 4, s->sQ[cl]);
             CU(launch_utility_qp(Q, grid[cl], cl, s->sQ[cl]));
             span_end(sp, s->sQ[cl]);
             CU(cudaEventRecord(s->evQ[cl], s->sQ[cl]));
             s->stats.kernel_launches++;
         }
-        sp = span_begin(s, 3, s->sU);
-        CU(launch_utility_qp(Q, grid[0], 0, s->sU));
-        span_end(sp, s->sU);
-        s->stats.kernel_launches++;
+        if (use[0]) {
+            sp = span_begin(s, 3, s->sU);
+            CU(launch_utility_qp_warp(Q, grid[0], warp_n, s->sU));
+            span_end(sp, s->sU);
+            s->stats.kernel_launches++;
+        }
         for (int cl = 1; cl < kQpClasses; ++cl)
             if (use[cl]) CU(cudaStreamWaitEvent(s->sU, s->evQ[cl], 0));
         s->stats.gemm_launches++;
@@ -367,17 +372,15 @@ int utility_solve(revs_solver* s) {
                         "utility QP: %d (feeder,hour) columns need more than %d simultaneously active "
                         "voltage rows", s->h_cnt->n_failed, kWMax);
         if (getenv("REVS_DEBUG"))
-            fprintf(stderr, "[revs] admm %d round %d: running %d by class %d/%d/%d pieces_total %llu max_ws %d | phi evals %llu "
+            fprintf(stderr, "[revs] admm %d round %d: running %d by class %d/%d/%d/%d pieces_total %llu max_ws %d | phi evals %llu "
                     "pdas guesses %llu max pieces/launch %llu fallbacks %llu\n",
-                    s->k, round, s->h_cnt->n_running, s->h_cnt->n_cls[0], s->h_cnt->n_cls[1], s->h_cnt->n_cls[2],
+                    s->k, round, s->h_cnt->n_running, s->h_cnt->n_cls[0], s->h_cnt->n_cls[1], s->h_cnt->n_cls[2], s->h_cnt->n_cls[3],
                     s->h_cnt->newton_its, s->h_cnt->max_ws, s->h_cnt->dbg[0], s->h_cnt->dbg[1], s->h_cnt->dbg[2],
                     s->h_cnt->dbg[3]);
         if (s->h_cnt->n_running == 0) break;
-        use[0] = true;
         for (int cl = 0; cl < kQpClasses; ++cl) {
             // columns only leave the running set or move up a class (counted in n_cls of the new class)
             grid[cl] = s->h_cnt->n_cls[cl] < s->ncols ? s->h_cnt->n_cls[cl] : s->ncols;
-            if (cl == 0) continue;
             use[cl] = s->h_cnt->n_cls[cl] > 0;
             if (use[cl]) top_cls = cl;
         }
@@ -1191,6 +1194,7 @@ int revs_screen_contract(int device, int M, int K, int T, const double* A, const
 int revs_set_option(revs_solver* s, const char* name, double value) {
     if (!s || !name) return fail(REVS_ERR_ARG, "bad arguments");
     if (!strcmp(name, "screen")) { s->screen = value != 0.0; return REVS_OK; }
+    if (!strcmp(name, "warp_kernel")) { s->use_warp_kernel = value != 0.0; return REVS_OK; }
     if (!strcmp(name, "screen_impl")) {
         if (value != 0.0 && !s->tc5_ready) return fail(REVS_ERR_ARG, "tcgen05 screening kernel unavailable (T > 96 or tensor-map encoding failed)");
         s->screen_impl = value != 0.0 ? 1 : 0;

@@ -23,10 +23,11 @@
 //      with a Levenberg-Marquardt shift instead.
 // and the host alternates it with the contraction until no column has a violated row.
 //
-// Three instantiations share the code: |W| <= 32 (128 threads, 19 KB of shared memory,
-// >= 4 CTAs per SM), |W| <= 64 (256 threads, 54 KB, 2 per SM) and |W| <= 128 (256 threads,
-// 175 KB, 1 per SM).  A column carries a class flag; it is classified by the size of its
-// warm-start set and handed to the next class when it outgrows the current one.
+// Three instantiations share the code (classes 1-3): |W| <= 32 (128 threads, ~30 KB of shared
+// memory, 6 CTAs per SM), |W| <= 64 (256 threads, ~73 KB, 3 per SM) and |W| <= 128 (256
+// threads, ~210 KB, 1 per SM).  Class 0 is the warp-per-column kernel of utility_qp_warp.cu
+// for small columns.  A column carries a class flag; qp_init_kernel classifies it by the size
+// of its warm-start set and a kernel hands it to the next class when it outgrows its own.
 #include <cuda_bf16.h>
 
 #include "kernels.cuh"
@@ -470,8 +471,8 @@ __global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
     long long tr_start = 0;
     const long long tr_clk0 = clock64();
     if (P.trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_start));
-    if (!P.init && P.status[c] != 0) return;
-    if ((CLS > 0 || !P.init) && P.cls[c] != CLS) return;   // column of another instantiation
+    if (P.status[c] != 0) return;
+    if (P.cls[c] != CLS) return;   // column of another instantiation
 
     const FeederDev fd = P.feeders[f];
     const int n = fd.n, ld = fd.np;
@@ -488,40 +489,7 @@ __global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
     // ------------------------------------------------------------ working set
     int m = 0;
     bool clean = false;   // step launch that found no violated row: v is still valid if g stays put
-    if (P.init) {
-        // warm start: rows that carried a multiplier in the previous ADMM iteration
-        // (ordered compaction, so the working-set order -- and with it every rounding -- is
-        // reproducible from run to run)
-        int base = 0;
-        for (int j0 = 0; j0 < n; j0 += THREADS) {
-            const int j = j0 + tid;
-            const bool on = j < n && lam_g[j] > 0.0;
-            const unsigned bal = __ballot_sync(0xffffffffu, on);
-            __syncthreads();
-            if (lane == 0) sm.ired[warp] = __popc(bal);
-            __syncthreads();
-            int before = 0, total = 0;
-#pragma unroll
-            for (int w = 0; w < THREADS / 32; ++w) {
-                before += (w < warp) ? sm.ired[w] : 0;
-                total += sm.ired[w];
-            }
-            if (on) {
-                const int pos = base + before + __popc(bal & ((1u << lane) - 1));
-                if (pos < WMAX) { sm.idx[pos] = j; sm.lam[pos] = lam_g[j]; }
-                else if (BIG) lam_g[j] = 0.0;   // cannot be carried; re-admitted if violated
-            }
-            base += total;
-        }
-        __syncthreads();
-        if (CLS == 0) {                         // the first instantiation classifies the column
-            int cl = 0;
-            while (cl < kQpClasses - 1 && base > qp_class_cap(cl)) ++cl;
-            if (tid == 0) P.cls[c] = cl;
-            if (cl != 0) return;
-        }
-        m = min(base, WMAX);
-    } else {
+    {
         if (P.v32_t) {
             // Voltages came from the BF16 screening pass: rows at or below (1-margin) u are
             // proven feasible; every other row without a multiplier is a candidate whose
@@ -627,7 +595,7 @@ __global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
     bool have_H = false;   // Hb/hdiag hold the Hessian for the mask in sm.fmask
     long long tc[5] = {0, 0, 0, 0, 0}, t0 = clock64(), t1;   // phase cycles (debug)
 #define PHASE(i) do { t1 = clock64(); tc[i] += t1 - t0; t0 = t1; } while (0)
-    const int inner_max = (P.init == 2) ? 0 : P.inner_max;   // init==2: evaluate the warm start only
+    const int inner_max = P.inner_max;
     double scale = 0.0;                         // mean |R_a|^2 over W: curvature scale of the Hessian shifts
     if (inner_max > 0 && m > 0) {
         double sc[1] = {0.0};
@@ -874,9 +842,9 @@ cudaError_t launch_utility_qp(const QpParams& P, int grid, int cls, cudaStream_t
     using S0 = QpSmem<32, 128>;
     using S1 = QpSmem<64, 256>;
     using S2 = QpSmem<kWMax, 256>;
-    auto k0 = utility_qp_kernel<32, 128, 0, kMinB0>;
-    auto k1 = utility_qp_kernel<64, 256, 1, kMinB1>;
-    auto k2 = utility_qp_kernel<kWMax, 256, 2, 1>;
+    auto k0 = utility_qp_kernel<32, 128, 1, kMinB0>;
+    auto k1 = utility_qp_kernel<64, 256, 2, kMinB1>;
+    auto k2 = utility_qp_kernel<kWMax, 256, 3, 1>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S1));
@@ -888,9 +856,10 @@ cudaError_t launch_utility_qp(const QpParams& P, int grid, int cls, cudaStream_t
         attr_set = true;
     }
     if (grid <= 0) return cudaSuccess;
-    if (cls == 0) k0<<<grid, 128, sizeof(S0), stream>>>(P);
-    else if (cls == 1) k1<<<grid, 256, sizeof(S1), stream>>>(P);
-    else k2<<<grid, 256, sizeof(S2), stream>>>(P);
+    if (cls == 1) k0<<<grid, 128, sizeof(S0), stream>>>(P);
+    else if (cls == 2) k1<<<grid, 256, sizeof(S1), stream>>>(P);
+    else if (cls == 3) k2<<<grid, 256, sizeof(S2), stream>>>(P);
+    else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }
 
