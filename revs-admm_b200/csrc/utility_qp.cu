@@ -803,36 +803,29 @@ __global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
     }
 }
 
-// Work list per class for one working-set round: running columns of the class, largest
-// previous working set first (longest-processing-time-first keeps the tail of a launch
-// short: a column with 30 rows costs ~10x one with 3).  Counting sort, one CTA.
-__global__ void __launch_bounds__(1024) order_columns_kernel(const int* __restrict__ status, const int* __restrict__ cls,
-                                                             const int* __restrict__ wcount, int ncols,
-                                                             int* __restrict__ order, int* __restrict__ order_count) {
-    __shared__ int hist[kQpClasses][kWMax + 2];
+// Work list per class for one working-set round: the running columns of each class,
+// compacted (block-level counts, one atomic per class and CTA).  order_count must be zero.
+__global__ void __launch_bounds__(256) order_columns_kernel(const int* __restrict__ status, const int* __restrict__ cls,
+                                                            int ncols, int* __restrict__ order, int* __restrict__ order_count) {
+    __shared__ int cnt[kQpClasses], base[kQpClasses];
     const int tid = threadIdx.x;
-    for (int i = tid; i < kQpClasses * (kWMax + 2); i += 1024) (&hist[0][0])[i] = 0;
+    if (tid < kQpClasses) cnt[tid] = 0;
     __syncthreads();
-    for (int c = tid; c < ncols; c += 1024)
-        if (status[c] == 0) atomicAdd(&hist[cls[c]][kWMax - min(wcount[c], kWMax)], 1);
+    const int c = blockIdx.x * blockDim.x + tid;
+    int cl = -1, pos = 0;
+    if (c < ncols && status[c] == 0) { cl = cls[c]; pos = atomicAdd(&cnt[cl], 1); }
     __syncthreads();
-    if (tid < kQpClasses) {
-        int acc = 0;
-        for (int k = 0; k <= kWMax; ++k) { int h = hist[tid][k]; hist[tid][k] = acc; acc += h; }
-        order_count[tid] = acc;
-    }
+    if (tid < kQpClasses) base[tid] = cnt[tid] ? atomicAdd(&order_count[tid], cnt[tid]) : 0;
     __syncthreads();
-    for (int c = tid; c < ncols; c += 1024)
-        if (status[c] == 0) {
-            const int cl = cls[c];
-            const int pos = atomicAdd(&hist[cl][kWMax - min(wcount[c], kWMax)], 1);
-            order[(size_t)cl * ncols + pos] = c;
-        }
+    if (cl >= 0) order[(size_t)cl * ncols + base[cl] + pos] = c;
 }
 
 cudaError_t launch_order_columns(const int* status, const int* cls, const int* wcount, int ncols, int* order,
                                  int* order_count, cudaStream_t stream) {
-    order_columns_kernel<<<1, 1024, 0, stream>>>(status, cls, wcount, ncols, order, order_count);
+    (void)wcount;
+    cudaError_t e = cudaMemsetAsync(order_count, 0, kQpClasses * sizeof(int), stream);
+    if (e != cudaSuccess) return e;
+    order_columns_kernel<<<(ncols + 255) / 256, 256, 0, stream>>>(status, cls, ncols, order, order_count);
     return cudaGetLastError();
 }
 

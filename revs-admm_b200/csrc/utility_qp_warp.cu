@@ -123,6 +123,23 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) utility_qp_warp_kernel(QpPa
     int* widx = P.widx + (size_t)c * kWMax;
     const unsigned full = 0xffffffffu;
 
+    const int m_old = P.wcount[c];
+    const double thr = (1.0 - kScreenMargin) * u;
+    // ---- fast exit: no multipliers and every screened voltage below the safe threshold ->
+    // g = [z]_+ from qp_init_kernel is already the projection (most columns, most rounds)
+    if (m_old == 0) {
+        bool any_cand = false;
+#pragma unroll
+        for (int k = 0; k < NJ; ++k) {
+            const int j = lane + 32 * k;
+            if (j < n) any_cand |= P.v32_t ? ((double)(P.v32_t + col)[j] > thr) : (v[j] - u > tol);
+        }
+        if (!__any_sync(full, any_cand)) {
+            if (lane == 0) { P.status[c] = 1; P.inner_ok[c] = 1; atomicAdd(P.n_cls + 0, 1); }
+            return;
+        }
+    }
+
     // ---- this lane's homes
     double zj[NJ], gj[NJ], vj[NJ];
     bool haslam[NJ];
@@ -131,12 +148,11 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) utility_qp_warp_kernel(QpPa
         const int j = lane + 32 * k;
         zj[k] = j < n ? z[j] : 0.0;
         gj[k] = j < n ? g[j] : 0.0;
-        haslam[k] = j < n && lam_g[j] > 0.0;
+        haslam[k] = m_old > 0 && j < n && lam_g[j] > 0.0;
     }
     // ---- voltages: screened (BF16) values, exact FP64 recheck of the candidates
     if (P.v32_t) {
         const float* v32 = P.v32_t + col;
-        const double thr = (1.0 - kScreenMargin) * u;
 #pragma unroll
         for (int k = 0; k < NJ; ++k) {
             const int j = lane + 32 * k;
@@ -163,7 +179,6 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) utility_qp_warp_kernel(QpPa
     }
 
     // ---- working set: keep rows with a positive multiplier (order preserved), lanes = rows
-    const int m_old = P.wcount[c];
     int idx = 0;
     double lam = 0.0;
     int m = 0;
