@@ -23,7 +23,7 @@ namespace revs {
 
 namespace {
 
-constexpr int kWarpsPerCta = 8;
+constexpr int kWarpsPerCta = 1;              // one column per CTA: a finished column frees its slot at once
 constexpr int kHW = kWW + 1;                 // leading dim of the per-warp 16x16 matrices
 constexpr double kArcMinW = 9.5367431640625e-07;
 constexpr int kPdasMaxW = 40;
@@ -123,6 +123,9 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) utility_qp_warp_kernel(QpPa
     int* widx = P.widx + (size_t)c * kWMax;
     const unsigned full = 0xffffffffu;
 
+    long long tr_start = 0;
+    if (P.trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_start));
+    const long long tr_clk0 = clock64();
     const int m_old = P.wcount[c];
     const double thr = (1.0 - kScreenMargin) * u;
     // ---- fast exit: no multipliers and every screened voltage below the safe threshold ->
@@ -295,29 +298,65 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) utility_qp_warp_kernel(QpPa
         const double kkt = warp_max(kk);
         if (kkt < tol) { ok = 1; break; }
 
-        // Hessian: rank-1 updates for the homes whose membership of F changed
+        // Hessian.  First piece: H[p][q] = sum over F of row p times row q, every row read
+        // coalesced (lanes = homes), two q at a time so the loads overlap.  Later pieces:
+        // signed rank-1 updates for the homes whose membership of F changed.
         {
             int nupd = 0;
+            if (!have_H) {
+                for (int p = 0; p < m; ++p) {
+                    const double* rp_ptr = R + (size_t)__shfl_sync(full, idx, p) * ld;
+                    double rp[NJ];
 #pragma unroll
-            for (int k = 0; k < NJ; ++k) {
-                const bool now = gj[k] > 0.0;
-                const bool was = have_H && ((fbits >> k) & 1u);
-                unsigned chg = __ballot_sync(full, now != was);
-                const unsigned nowb = __ballot_sync(full, now);
-                while (chg) {
-                    const int src = __ffs(chg) - 1;
-                    chg &= chg - 1;
-                    const int j = src + 32 * k;
-                    const double sgn = ((nowb >> src) & 1u) ? 1.0 : -1.0;
-                    const double ra = row ? R[(size_t)idx * ld + j] : 0.0;
-#pragma unroll
-                    for (int q = 0; q < kWW; ++q) {
-                        const double rq = warp_bcast(ra, q);
-                        if (q <= lane) hrow[q] = fma(sgn * ra, rq, hrow[q]);
+                    for (int k = 0; k < NJ; ++k) {
+                        const int j = lane + 32 * k;
+                        rp[k] = (j < n && gj[k] > 0.0) ? rp_ptr[j] : 0.0;
                     }
-                    ++nupd;
+                    for (int q = 0; q <= p; q += 2) {
+                        const double* r0 = R + (size_t)__shfl_sync(full, idx, q) * ld;
+                        const double* r1 = R + (size_t)__shfl_sync(full, idx, min(q + 1, p)) * ld;
+                        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                        for (int k = 0; k < NJ; ++k) {
+                            const int j = lane + 32 * k;
+                            if (j < n) { a0 = fma(rp[k], r0[j], a0); a1 = fma(rp[k], r1[j], a1); }
+                        }
+                        a0 = warp_sum(a0);
+                        a1 = warp_sum(a1);
+                        if (lane == p) {
+#pragma unroll
+                            for (int qq = 0; qq < kWW; ++qq) {
+                                if (qq == q) hrow[qq] = a0;
+                                if (qq == q + 1 && q + 1 <= p) hrow[qq] = a1;
+                            }
+                        }
+                    }
                 }
-                fbits = now ? (fbits | (1u << k)) : (fbits & ~(1u << k));
+#pragma unroll
+                for (int k = 0; k < NJ; ++k) { if (gj[k] > 0.0) { fbits |= 1u << k; ++nupd; } else fbits &= ~(1u << k); }
+                nupd = __reduce_add_sync(full, nupd);
+            } else {
+#pragma unroll
+                for (int k = 0; k < NJ; ++k) {
+                    const bool now = gj[k] > 0.0;
+                    const bool was = (fbits >> k) & 1u;
+                    unsigned chg = __ballot_sync(full, now != was);
+                    const unsigned nowb = __ballot_sync(full, now);
+                    while (chg) {
+                        const int src = __ffs(chg) - 1;
+                        chg &= chg - 1;
+                        const int j = src + 32 * k;
+                        const double sgn = ((nowb >> src) & 1u) ? 1.0 : -1.0;
+                        const double ra = row ? R[(size_t)idx * ld + j] : 0.0;
+#pragma unroll
+                        for (int q = 0; q < kWW; ++q) {
+                            const double rq = warp_bcast(ra, q);
+                            if (q <= lane) hrow[q] = fma(sgn * ra, rq, hrow[q]);
+                        }
+                        ++nupd;
+                    }
+                    fbits = now ? (fbits | (1u << k)) : (fbits & ~(1u << k));
+                }
             }
             have_H = true;
             flops += (double)m * (m + 1) * nupd;
@@ -439,6 +478,14 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) utility_qp_warp_kernel(QpPa
         atomicAdd(P.newton_its, (unsigned long long)its);
         atomicMax(P.max_ws, m);
         atomicAdd(P.flops, (unsigned long long)flops);
+        if (P.trace) {
+            long long tr_end; unsigned smid;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_end));
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            long long* rec = P.trace + 12 * (size_t)c;
+            rec[0] = tr_start; rec[1] = tr_end; rec[2] = smid; rec[3] = ((long long)m << 20) | its;
+            rec[11] = clock64() - tr_clk0;
+        }
     }
 }
 
