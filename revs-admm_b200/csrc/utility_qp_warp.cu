@@ -102,7 +102,7 @@ cudaError_t launch_qp_init(const QpParams& P, int max_warp_n, cudaStream_t strea
 
 // ------------------------------------------------------------------------------------------
 template <int NJ>
-__global__ void __launch_bounds__(32 * kWarpsPerCta) utility_qp_warp_kernel(QpParams P) {
+__global__ void __launch_bounds__(32 * kWarpsPerCta, 20) utility_qp_warp_kernel(QpParams P) {
     __shared__ WarpSmem smem_all[kWarpsPerCta];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     WarpSmem& sm = smem_all[wib];
