@@ -48,6 +48,10 @@ def make_rank_problem(workload, rank, split=True):
     networkx feeder); homes are reordered accordingly."""
     from revs_admm_b200.feeder import split_zones, synthetic_feeder, synthetic_homes, synthetic_tariff
     nf, n, T = WORKLOADS[workload]
+    # weak scaling = fixed work per GPU: every rank holds a copy of the same synthetic population
+    # (different random draws differ by up to 30 % in QP work); REVS_BENCH_SEED=rank restores distinct draws
+    seed_env = os.environ.get("REVS_BENCH_SEED", "0")
+    rank = rank if seed_env == "rank" else int(seed_env)
     feeders = [synthetic_feeder(n, seed=1000 * rank + f, laterals=max(5, n // 100)) for f in range(nf)]
     hm = synthetic_homes(nf * n, T, seed=77 + rank)
     if not split:
@@ -383,6 +387,7 @@ def run_gpu(args, rank, world, local_rank):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "feeders_per_gpu": nf, "homes_per_feeder": n, "T": T,
                        "voltage_zones_per_gpu": len(sizes), "homes_total": int(total_homes), **ADMM,
+                       "population": "same synthetic draw on every rank (fixed work per GPU)",
                        "l2": "working set per solve > L2 (sensitivity blocks %.2f GB per GPU)" % (sum(8.0 * x * x for x in n_p) / 1e9)},
             "admm_iters_per_sec": ADMM["iter_max"] / (ms_step * 1e-3),
             "home_steps_per_sec": total_homes * T / (ms_step * 1e-3),
