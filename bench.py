@@ -267,8 +267,11 @@ def run_gpu(args, rank, world, local_rank):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         dev_ms = 0.0
+        host_ms = 0.0
         for _ in range(args.steps):
+            th = time.perf_counter()
             s.solve_admm(**ADMM)
+            host_ms += (time.perf_counter() - th) * 1e3
             st = s.stats()
             dev_ms += st["total_ms"]
             for k in stats_acc:
@@ -277,6 +280,11 @@ def run_gpu(args, rank, world, local_rank):
         barrier()
         wall_ms = e0.elapsed_time(e1)
     ms_step = max_over_ranks(wall_ms / args.steps)
+    per_rank = [[wall_ms / args.steps, host_ms / args.steps, dev_ms / args.steps]]
+    if world > 1:
+        tg = [torch.zeros(3, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(tg, torch.tensor(per_rank[0], dtype=torch.float64, device=dev))
+        per_rank = [[round(float(x), 3) for x in t.tolist()] for t in tg]
     total_homes = sum_over_ranks(H)
     value = total_homes * HOURS / (ms_step * 1e-3)
     last = s.stats()
@@ -345,7 +353,7 @@ def run_gpu(args, rank, world, local_rank):
                                  "ms_sum_of_class_spans": stats_acc["qp_ms"] / args.steps,
                                  "ms_classes_ge_33_rows": stats_acc["qp_big_ms"] / args.steps}
     # FP64 DMMA contraction (reliability check / exact mode): one extra solve outside the timed region
-    if rank == 0:
+    if rank == 0 and not args.no_exact:
         s.set_option("screen", 0)
         s.solve_admm(**ADMM)
         st = s.stats()
@@ -392,6 +400,7 @@ def run_gpu(args, rank, world, local_rank):
             "admm_iters_per_sec": ADMM["iter_max"] / (ms_step * 1e-3),
             "home_steps_per_sec": total_homes * T / (ms_step * 1e-3),
             "device_ms_per_step": dev_ms / args.steps,
+            "per_rank_ms": {"columns": ["wall (CUDA events)", "host wall of solve_admm", "device span of the ADMM loop"], "rows": per_rank},
             "e2e": {"value": e2e_value, "unit": "home-hours/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(stats_acc["kernel_launches"]),
@@ -417,6 +426,7 @@ def main():
     ap.add_argument("--workload", default="synthetic-multifeeder-125k-homes-per-gpu-x96", choices=list(WORKLOADS))
     ap.add_argument("--cpu-sample-homes", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-exact", action="store_true", help="skip the extra exact-mode (FP64 contraction) solve used for the contract_f64 figure")
     ap.add_argument("--no-split", action="store_true", help="hand whole feeders to the solver instead of their voltage zones")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

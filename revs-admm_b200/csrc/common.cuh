@@ -10,6 +10,8 @@ constexpr int kWMax = 128;      // largest working set of a (feeder,hour) utilit
 constexpr int kAddMax = 32;     // violated voltage rows admitted per working-set round
 constexpr int kWW = 16;         // working-set capacity of the warp-per-column QP kernel
 constexpr int kQpClasses = 4;   // utility QP instantiations: 0 = warp kernel, 1..3 = CTA kernels by capacity
+constexpr int kQpLists = 12;    // work lists: classes 1..3 at [1..3], the warp kernel's buckets at [4..7] (zones <= 128) and [8..11] (<= 256)
+constexpr int kWarpMaxN = 256;  // largest zone the warp-per-column QP kernel takes
 __host__ __device__ constexpr int qp_class_cap(int cls) { return cls == 0 ? kWW : (cls == 1 ? 32 : (cls == 2 ? 64 : kWMax)); }
 
 // One feeder of the batch as the kernels see it.
@@ -45,9 +47,13 @@ struct ScreenProblem {
     const void* Bt_; int64_t ldb;               // __nv_bfloat16, Bt[t*ldb + k]
     float* out; int64_t ldo;                    // out[t*ldo + m]
     const int* col_status;                      // optional [T]: columns with status != 0 are skipped
+    int* col_cand;                              // optional [T]: set to 1 when any row of the column has v~ > thr
 };
 
 constexpr double kScreenMargin = 0.01;   // rows with v~ <= (1-margin) u are proven feasible (see screen_bf16.cu)
+constexpr double kScreenUp = 1.005;      // v <= kScreenUp * v~ for the BF16/FP32 product of non-negative terms, K <= 16384
+constexpr int kVerifyMaxN = 512;         // zones up to this size verify all voltage rows inside the QP kernels
+constexpr int kQpBuckets = 4;            // work lists of the warp kernel: |W| >= 3, 2, 1, 0 (hardest first)
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -82,21 +82,22 @@ __global__ void to_time_major_kernel(const double* __restrict__ in, int n, int T
 
 // rn2[off + i] = sum_j R_f[i][j]^2 : curvature scale of the utility QP, one warp per row
 __global__ void row_norms_kernel(const FeederDev* __restrict__ feeders, const double* __restrict__ Rpool,
-                                 double* __restrict__ rn2) {
+                                 double* __restrict__ rn2, double* __restrict__ rmax) {
     const FeederDev fd = feeders[blockIdx.y];
     const int lane = threadIdx.x & 31;
     for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < fd.n; i += gridDim.x * (blockDim.x >> 5)) {
         const double* row = Rpool + fd.roff + (size_t)i * fd.np;
-        double acc = 0.0;
-        for (int j = lane; j < fd.n; j += 32) acc = fma(row[j], row[j], acc);
+        double acc = 0.0, mx = 0.0;
+        for (int j = lane; j < fd.n; j += 32) { acc = fma(row[j], row[j], acc); mx = fmax(mx, row[j]); }
         acc = warp_sum(acc);
-        if (lane == 0) rn2[fd.off + i] = acc;
+        mx = warp_max(mx);
+        if (lane == 0) { rn2[fd.off + i] = acc; rmax[fd.off + i] = mx; }
     }
 }
 
-cudaError_t launch_row_norms(const FeederDev* feeders, int n_feeders, const double* Rpool, double* rn2,
+cudaError_t launch_row_norms(const FeederDev* feeders, int n_feeders, const double* Rpool, double* rn2, double* rmax,
                              cudaStream_t s) {
-    row_norms_kernel<<<dim3(64, n_feeders), 256, 0, s>>>(feeders, Rpool, rn2);
+    row_norms_kernel<<<dim3(64, n_feeders), 256, 0, s>>>(feeders, Rpool, rn2, rmax);
     return cudaGetLastError();
 }
 

@@ -60,6 +60,9 @@ struct QpParams {
     const FeederDev* feeders;
     const double* Rpool;
     const double* rn2;     // [Hp]  squared row norms of the sensitivity blocks
+    const double* rmax;    // [Hp]  largest entry of every row of the sensitivity blocks
+    int* cand;             // [ncols] set by the screening pass: some row has v~ above the safe threshold
+    int* queue;            // work-queue head of the persistent warp kernel (= order_count + kQpLists)
     const double* z_t;     // [T][Hp]
     double* lam_t;         // [T][Hp]   multipliers (dense storage, sparse content)
     double* g_t;           // [T][Hp]   out: projection = P_est[k+1]
@@ -69,7 +72,8 @@ struct QpParams {
     int* wcount;           // [ncols]
     int* widx;             // [ncols][kWMax]
     int* status;           // [ncols] 0 running, 1 converged, 2 working set overflow
-    int* inner_ok;         // [ncols] restricted problem solved to tolerance
+    int* inner_ok;         // [ncols] 1: restricted problem solved to tolerance; 2: handed to the next class
+                           //         untouched since the last screening pass (picked up by the sweep launch)
     int* n_running;        // columns still running after this launch
     unsigned long long* newton_its;
     int* max_ws;
@@ -77,8 +81,10 @@ struct QpParams {
     int* n_failed;         // columns whose working set overflowed kWMax
     int* cls;              // [ncols] instantiation that owns the column (see qp_class_cap)
     int* n_cls;            // [kQpClasses] running columns per class after this round
-    const int* order;      // optional [kQpClasses][ncols] work lists (order_columns_kernel)
-    const int* order_count;   // [kQpClasses]
+    const int* order;      // optional [kQpLists][ncols] work lists (order_columns_kernel)
+    const int* order_count;   // [kQpLists + 1]
+    int sweep;             // 1: this launch only takes columns handed over during the current round
+    int warp_m_max;        // warm working sets above this size start in class 1 (qp_init_kernel)
     int ncols;
     long long* trace;      // optional debug [ncols][12]: start ns, end ns, smid, class/m/pieces, phase cycles ...
     unsigned long long* dbg;  // optional [4 + 5*kQpClasses]: counts, then per-class phase cycles
@@ -93,9 +99,12 @@ cudaError_t launch_utility_qp(const QpParams& P, int grid, int cls, cudaStream_t
 // ---- utility_qp_warp.cu
 int qp_warp_max_n();
 cudaError_t launch_qp_init(const QpParams& P, int max_warp_n, cudaStream_t stream);
-cudaError_t launch_utility_qp_warp(const QpParams& P, int n_cols_bound, int max_n, cudaStream_t stream);
-cudaError_t launch_order_columns(const int* status, const int* cls, const int* wcount, int ncols, int* order,
-                                 int* order_count, cudaStream_t stream);
+int qp_warp_ctas_per_sm();
+int qp_warp_m_max_default();
+cudaError_t launch_utility_qp_warp(const QpParams& P, int nj, int ctas_per_sm, cudaStream_t stream);
+// mode 0: first round of a solve (columns without multipliers and without screening candidates finish here);
+// mode 1: later rounds (every running column); mode 2: sweep (columns handed over in this round)
+cudaError_t launch_order_columns(const QpParams& P, int mode, int* order, int* order_count, cudaStream_t stream);
 
 // ---- contract_f64.cu
 int contract_tile_rows(int T);
@@ -105,7 +114,7 @@ cudaError_t launch_contract(const ContractProblem* d_problems, const ContractTil
 // ---- screen_bf16.cu
 int screen_tile_rows();
 cudaError_t launch_to_bf16(const double* in, void* out, size_t n, cudaStream_t s);
-cudaError_t launch_screen(const ScreenProblem* d_problems, const ContractTile* d_tiles, int n_tiles, int T,
+cudaError_t launch_screen(const ScreenProblem* d_problems, const ContractTile* d_tiles, int n_tiles, int T, double thr,
                           cudaStream_t stream);
 
 // ---- screen_tc5.cu (tcgen05 / TMEM / TMA implementation of the same contraction)
@@ -116,7 +125,7 @@ uint32_t screen_tc5_box_rows_b();
 cudaError_t screen_tc5_encode(void* host_map, const void* gptr, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
                               uint32_t box_rows);
 cudaError_t launch_screen_tc5(const ScreenProblem* d_problems, const ContractTile* d_tiles, int n_tiles, const void* d_maps_a,
-                              const void* d_map_b, const int* d_b_col0, int T, cudaStream_t stream);
+                              const void* d_map_b, const int* d_b_col0, int T, double thr, cudaStream_t stream);
 
 // ---- feeder_build.cu
 cudaError_t launch_sens_voltage(const int* parent, const double* cumr, const int* row_node,
@@ -127,7 +136,7 @@ cudaError_t launch_sens_voltage_batched(const FeederDev* feeders, int n_feeders,
                                         cudaStream_t s);
 cudaError_t launch_sens_flow(const int* parent, const int* row_node, const int* res_node, int n_rows,
                              int n_res, double* out, int ld, cudaStream_t s);
-cudaError_t launch_row_norms(const FeederDev* feeders, int n_feeders, const double* Rpool, double* rn2,
+cudaError_t launch_row_norms(const FeederDev* feeders, int n_feeders, const double* Rpool, double* rn2, double* rmax,
                              cudaStream_t s);
 cudaError_t launch_pack_rows(const double* src, double* dst, const int64_t* hmap, int64_t H, int w, int to_padded,
                              cudaStream_t s);

@@ -11,6 +11,7 @@
 //   stream U:  utility_qp(init) -> { contract_f64 ; utility_qp(step) } until no column runs
 //   stream H:  home_solve           (uses the PREVIOUS iterates, so it overlaps stream U)
 //   stream U:  dual_update          (after both)
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -53,6 +54,8 @@ constexpr double kCountTol = 1e-9;
 constexpr double kQpTol = 1e-11;     // KKT / feasibility tolerance of the utility QP
 constexpr int kQpInnerMax = 60;      // Newton steps per launch
 constexpr int kQpRoundMax = 400;     // working-set rounds per utility solve
+constexpr int kSweepGrid = 64;       // CTAs per class of the hand-over sweep launch
+constexpr int kSpecGrid = 148;       // CTAs per class of a speculatively enqueued round
 
 struct Counters {
     int n_running;   // n_running and n_cls are reset together before every working-set round
@@ -76,6 +79,11 @@ struct Tree {
 
 struct TimedSpan { cudaEvent_t a, b; int cat; };
 
+double g_host_sync_ms = 0.0, g_host_round_ms = 0.0, g_cat_ms[16] = {0};   // REVS_DEBUG_HOST: host time waiting / per working-set round
+inline double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 }  // namespace
 
 struct revs_solver {
@@ -90,6 +98,8 @@ struct revs_solver {
     FeederDev* d_feeders = nullptr;
     double* d_Rpool = nullptr;
     double* d_rn2 = nullptr;
+    double* d_rmax = nullptr;
+    int* d_cand = nullptr;
     double* d_stage = nullptr;                 // compact staging [H][T+1] for host transfers
     int64_t* d_hmap = nullptr;                 // compact home -> padded home
     void *d_Rbf = nullptr, *d_gbf = nullptr;   // BF16 copies for the screening contraction
@@ -186,12 +196,13 @@ void spans_collect(revs_solver* s) {   // after the streams are synchronised
     for (size_t i = 0; i < s->span_used; ++i) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, s->spans[i].a, s->spans[i].b) != cudaSuccess) continue;
+        g_cat_ms[s->spans[i].cat & 15] += ms;
         switch (s->spans[i].cat) {
             case 0: s->stats.gemm_ms += ms; break;
             case 5: s->stats.gemm_ms += ms; s->stats.gemm_full_ms += ms; break;
             case 1: s->stats.home_ms += ms; break;
             case 2: s->stats.dual_ms += ms; break;
-            case 3: s->stats.qp_ms += ms; break;
+            case 3: case 6: case 7: case 8: case 9: s->stats.qp_ms += ms; break;
             case 4: s->stats.qp_ms += ms; s->stats.qp_big_ms += ms; break;
         }
     }
@@ -246,8 +257,13 @@ int utility_solve(revs_solver* s) {
     Q.feeders = s->d_feeders;
     Q.Rpool = s->d_Rpool;
     Q.rn2 = s->d_rn2;
+    Q.rmax = s->d_rmax;
+    Q.cand = s->screen ? s->d_cand : nullptr;
+    Q.queue = s->d_order_count + kQpLists;
+    Q.sweep = 0;
+    Q.warp_m_max = getenv("REVS_WARP_M_MAX") ? atoi(getenv("REVS_WARP_M_MAX")) : qp_warp_m_max_default();
     if (!s->rn2_valid) {
-        CU(launch_row_norms(s->d_feeders, s->nf, s->d_Rpool, s->d_rn2, s->sU));
+        CU(launch_row_norms(s->d_feeders, s->nf, s->d_Rpool, s->d_rn2, s->d_rmax, s->sU));
         CU(launch_to_bf16(s->d_Rpool, s->d_Rbf, s->Rpool_elems, s->sU));
         s->rn2_valid = true;
         s->stats.kernel_launches += 2;
@@ -289,13 +305,14 @@ int utility_solve(revs_solver* s) {
     // Start of the solve: working sets from the stored multipliers, class by their size,
     // g = [z - R lam]_+ for the new target -- one warp per column.
     Q.init = 0;
-    int max_n = 0, warp_n = 0;                     // largest zone / largest zone the warp kernel takes
+    int max_n = 0, warp_n = 0, small_n = 0;        // largest zone / largest zone the warp kernel takes / zones <= 128
     for (int f = 0; f < s->nf; ++f) {
         max_n = std::max(max_n, s->feeders[f].n);
         if (s->feeders[f].n <= qp_warp_max_n()) warp_n = std::max(warp_n, s->feeders[f].n);
+        if (s->feeders[f].n <= 128) ++small_n;
     }
     const int max_warp_n = s->use_warp_kernel ? qp_warp_max_n() : 0;
-    TimedSpan* sp = span_begin(s, 3, s->sU);
+    TimedSpan* sp = span_begin(s, 6, s->sU);
     CU(launch_qp_init(Q, max_warp_n, s->sU));
     span_end(sp, s->sU);
     s->stats.kernel_launches++;
@@ -307,17 +324,18 @@ int utility_solve(revs_solver* s) {
     int top_cls = 0;
     int grid[kQpClasses];
     for (int cl = 0; cl < kQpClasses; ++cl) grid[cl] = s->ncols;
-    for (int round = 0;; ++round) {
-        if (round >= kQpRoundMax)
-            return fail(REVS_ERR_NOCONV, "utility QP: %d columns still running after %d working-set rounds",
-                        s->h_cnt->n_running, round);
+    const double thr = (1.0 - kScreenMargin) * Q.u;
+    // One working-set round, enqueued without waiting: screening pass, work lists, the QP classes
+    // side by side.  `spec`: the round is enqueued before the host knows whether any column is
+    // still running (small CTA grids; with empty lists every kernel exits at once).
+    auto enqueue_round = [&](int round, bool spec) -> int {
         sp = span_begin(s, round == 0 ? 5 : 0, s->sU);   // round 0: every column is running
         if (s->screen) {
             if (s->screen_impl == 1 && s->tc5_ready)
                 CU(launch_screen_tc5(s->d_sprob, s->d_stiles, s->n_stiles, s->d_maps_a,
-                                     (const char*)s->d_maps_a + (size_t)s->nf * screen_tc5_map_bytes(), s->d_bcol0, s->T, s->sU));
+                                     (const char*)s->d_maps_a + (size_t)s->nf * screen_tc5_map_bytes(), s->d_bcol0, s->T, thr, s->sU));
             else
-                CU(launch_screen(s->d_sprob, s->d_stiles, s->n_stiles, s->T, s->sU));
+                CU(launch_screen(s->d_sprob, s->d_stiles, s->n_stiles, s->T, thr, s->sU));
         } else {
             CU(launch_contract(s->d_cprob, s->d_ctiles, s->n_ctiles, s->T, kOutTimeMajor, 0.0, s->sU));
         }
@@ -330,32 +348,93 @@ int utility_solve(revs_solver* s) {
             CU(cudaMemsetAsync(d_trace, 0, sizeof(long long) * 12 * s->ncols, s->sU));
             Q.trace = d_trace;
         }
-        CU(launch_order_columns(s->d_status, s->d_cls, s->d_wcount, s->ncols, s->d_order, s->d_order_count, s->sU));
+        CU(launch_order_columns(Q, round == 0 ? 0 : 1, s->d_order, s->d_order_count, s->sU));
         s->stats.kernel_launches++;
+        if (getenv("REVS_DEBUG_LISTS")) {
+            int oc[kQpLists];
+            std::vector<int> cd((size_t)s->ncols);
+            cudaStreamSynchronize(s->sU);
+            cudaMemcpy(oc, s->d_order_count, sizeof oc, cudaMemcpyDeviceToHost);
+            cudaMemcpy(cd.data(), s->d_cand, sizeof(int) * s->ncols, cudaMemcpyDeviceToHost);
+            long nc = 0;
+            for (int v : cd) nc += v != 0;
+            fprintf(stderr, "[revs] admm %d round %d lists: cls1-3 %d/%d/%d warp buckets %d/%d/%d/%d + %d/%d/%d/%d, cand flags %ld, thr %.6g\n", s->k, round,
+                    oc[1], oc[2], oc[3], oc[4], oc[5], oc[6], oc[7], oc[8], oc[9], oc[10], oc[11], nc, thr);
+        }
         // the larger classes go first, each on its own stream, so that their long CTAs
         // overlap with the many short columns of the small classes
         CU(cudaEventRecord(s->evV, s->sU));
         for (int cl = kQpClasses - 1; cl >= 1; --cl) {
-            if (!use[cl]) continue;
+            if (!use[cl] && !spec) continue;       // a speculative round takes hand-overs to any class
             CU(cudaStreamWaitEvent(s->sQ[cl], s->evV, 0));
             sp = span_begin(s, cl == 1 ? 3 : 4, s->sQ[cl]);
-            CU(launch_utility_qp(Q, grid[cl], cl, s->sQ[cl]));
+            CU(launch_utility_qp(Q, spec ? std::min(grid[cl], kSpecGrid) : grid[cl], cl, s->sQ[cl]));
             span_end(sp, s->sQ[cl]);
             CU(cudaEventRecord(s->evQ[cl], s->sQ[cl]));
             s->stats.kernel_launches++;
         }
         if (use[0]) {
-            sp = span_begin(s, 3, s->sU);
-            CU(launch_utility_qp_warp(Q, grid[0], warp_n, s->sU));
+            // zones of 129..256 residences (NJ = 8 instantiation, few and long columns) share the SMs
+            // with the small zones: one CTA per SM on a side stream
+            const bool two = warp_n > 128 && small_n > 0;
+            static const int split = getenv("REVS_WARP_SPLIT") ? atoi(getenv("REVS_WARP_SPLIT")) : 0;   // CTAs/SM of the big-zone kernel; 0: one after the other
+            cudaStream_t sBig = split > 0 ? s->sQ[0] : s->sU;
+            if (two) {
+                if (split > 0) CU(cudaStreamWaitEvent(sBig, s->evV, 0));
+                sp = span_begin(s, 7, sBig);
+                CU(launch_utility_qp_warp(Q, 8, split > 0 ? split : qp_warp_ctas_per_sm(), sBig));
+                span_end(sp, sBig);
+                CU(cudaEventRecord(s->evQ[0], sBig));
+                s->stats.kernel_launches++;
+            }
+            sp = span_begin(s, 8, s->sU);
+            CU(launch_utility_qp_warp(Q, (warp_n > 128 && !two) ? 8 : 4, qp_warp_ctas_per_sm() - (two ? split : 0), s->sU));
             span_end(sp, s->sU);
             s->stats.kernel_launches++;
+            if (two) CU(cudaStreamWaitEvent(s->sU, s->evQ[0], 0));
         }
         for (int cl = 1; cl < kQpClasses; ++cl)
-            if (use[cl]) CU(cudaStreamWaitEvent(s->sU, s->evQ[cl], 0));
+            if (use[cl] || spec) CU(cudaStreamWaitEvent(s->sU, s->evQ[cl], 0));
+        // sweep: columns handed to a larger class during this round are taken by that class
+        // at once (their state is consistent with the last screening pass), without a host
+        // round trip; one small grid per class, empty lists cost a few microseconds
+        static const bool do_sweep = getenv("REVS_SWEEP") && atoi(getenv("REVS_SWEEP"));
+        if (do_sweep && (max_n <= kVerifyMaxN || use[0])) {
+            Q.sweep = 1;
+            sp = span_begin(s, 9, s->sU);
+            CU(launch_order_columns(Q, 2, s->d_order, s->d_order_count, s->sU));
+            s->stats.kernel_launches++;
+            for (int cl = 1; cl < kQpClasses; ++cl) {
+                CU(launch_utility_qp(Q, kSweepGrid, cl, s->sU));
+                s->stats.kernel_launches++;
+            }
+            span_end(sp, s->sU);
+            Q.sweep = 0;
+        }
         s->stats.gemm_launches++;
         s->stats.qp_outer_iterations++;
+        return REVS_OK;
+    };
+    static const bool want_spec = getenv("REVS_SPEC") && atoi(getenv("REVS_SPEC"));   // off: with in-kernel verification one round is the norm
+    const bool speculate = want_spec && trace_round < 0 && !getenv("REVS_DEBUG") && !getenv("REVS_DEBUG_LISTS");
+    for (int round = 0;; ++round) {
+        if (round >= kQpRoundMax)
+            return fail(REVS_ERR_NOCONV, "utility QP: %d columns still running after %d working-set rounds",
+                        s->h_cnt->n_running, round);
+        int rc = enqueue_round(round, false);
+        if (rc) return rc;
+        if (round == 0 && speculate) {
+            // most solves need exactly one more round for a handful of columns: enqueue it now
+            // instead of idling the GPU over a host round trip
+            rc = enqueue_round(++round, true);
+            if (rc) return rc;
+        }
         CU(cudaMemcpyAsync(s->h_cnt, s->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, s->sU));
-        CU(cudaStreamSynchronize(s->sU));
+        {
+            const double t0 = now_ms();
+            CU(cudaStreamSynchronize(s->sU));
+            g_host_sync_ms += now_ms() - t0;
+        }
         if (d_trace) {
             std::vector<long long> hb((size_t)12 * s->ncols);
             cudaMemcpy(hb.data(), d_trace, hb.size() * sizeof(long long), cudaMemcpyDeviceToHost);
@@ -367,6 +446,8 @@ int utility_solve(revs_solver* s) {
             d_trace = nullptr;
             Q.trace = nullptr;
         }
+        if (s->h_cnt->infeasible)
+            return fail(REVS_ERR_INFEASIBLE, "a home charging sub-problem is infeasible (SOC window vs plug-in window)");
         if (s->h_cnt->n_failed)
             return fail(REVS_ERR_NOCONV,
                         "utility QP: %d (feeder,hour) columns need more than %d simultaneously active "
@@ -379,7 +460,7 @@ int utility_solve(revs_solver* s) {
                     s->h_cnt->dbg[3]);
         if (s->h_cnt->n_running == 0) break;
         for (int cl = 0; cl < kQpClasses; ++cl) {
-            // columns only leave the running set or move up a class (counted in n_cls of the new class)
+            // n_cls: columns of the class that are still running (or were handed to it)
             grid[cl] = s->h_cnt->n_cls[cl] < s->ncols ? s->h_cnt->n_cls[cl] : s->ncols;
             use[cl] = s->h_cnt->n_cls[cl] > 0;
             if (use[cl]) top_cls = cl;
@@ -421,7 +502,7 @@ HomeParams home_params(revs_solver* s, int individual) {
 
 void free_all(revs_solver* s) {
     cudaSetDevice(s->device);
-    void* ptrs[] = {s->d_feeders, s->d_Rpool, s->d_rn2, s->d_stage, s->d_hmap, s->d_Rbf, s->d_gbf, s->d_v32, s->d_sprob, s->d_stiles, s->d_maps_a, s->d_map_b, s->d_bcol0, s->d_pool_parent, s->d_pool_res, s->d_pool_cumr, s->d_pool_off, s->d_load, s->d_pest, s->d_psch[0], s->d_psch[1], s->d_gamma,
+    void* ptrs[] = {s->d_feeders, s->d_Rpool, s->d_rn2, s->d_rmax, s->d_cand, s->d_stage, s->d_hmap, s->d_Rbf, s->d_gbf, s->d_v32, s->d_sprob, s->d_stiles, s->d_maps_a, s->d_map_b, s->d_bcol0, s->d_pool_parent, s->d_pool_res, s->d_pool_cumr, s->d_pool_off, s->d_load, s->d_pest, s->d_psch[0], s->d_psch[1], s->d_gamma,
                     s->d_pev, s->d_soc, s->d_has_ev, s->d_rating, s->d_capacity, s->d_initial, s->d_indconst,
                     s->d_start, s->d_end, s->d_nmin, s->d_nmax, s->d_zero_i, s->d_cost, s->d_zt, s->d_lamt,
                     s->d_gt, s->d_vt, s->d_wcount, s->d_widx, s->d_status, s->d_innerok, s->d_cls, s->d_order, s->d_order_count, s->d_cnt, s->d_diff,
@@ -441,7 +522,7 @@ void free_all(revs_solver* s) {
     if (s->evT0) cudaEventDestroy(s->evT0);
     if (s->evT1) cudaEventDestroy(s->evT1);
     if (s->evV) cudaEventDestroy(s->evV);
-    for (int cl = 1; cl < kQpClasses; ++cl) {
+    for (int cl = 0; cl < kQpClasses; ++cl) {
         if (s->evQ[cl]) cudaEventDestroy(s->evQ[cl]);
         if (s->sQ[cl]) cudaStreamDestroy(s->sQ[cl]);
     }
@@ -508,7 +589,7 @@ int revs_create(revs_solver** out, int device, int n_feeders, const int64_t* fee
     TRY(cudaStreamCreateWithFlags(&s->sU, cudaStreamNonBlocking));
     TRY(cudaStreamCreateWithFlags(&s->sH, cudaStreamNonBlocking));
     TRY(cudaEventCreateWithFlags(&s->evV, cudaEventDisableTiming));
-    for (int cl = 1; cl < kQpClasses; ++cl) {
+    for (int cl = 0; cl < kQpClasses; ++cl) {
         TRY(cudaStreamCreateWithFlags(&s->sQ[cl], cudaStreamNonBlocking));
         TRY(cudaEventCreateWithFlags(&s->evQ[cl], cudaEventDisableTiming));
     }
@@ -520,6 +601,8 @@ int revs_create(revs_solver** out, int device, int n_feeders, const int64_t* fee
     TRY(cudaMemcpy(s->d_feeders, s->feeders.data(), sizeof(FeederDev) * n_feeders, cudaMemcpyHostToDevice));
     TRY(dalloc(&s->d_Rpool, (size_t)rp));
     TRY(dalloc(&s->d_rn2, (size_t)hp));
+    TRY(dalloc(&s->d_rmax, (size_t)hp));
+    TRY(dalloc(&s->d_cand, (size_t)s->ncols));
     TRY(dalloc(&s->d_stage, (size_t)s->H * (T + 1)));
     {
         std::vector<int64_t> hmap((size_t)s->H);
@@ -562,8 +645,8 @@ int revs_create(revs_solver** out, int device, int n_feeders, const int64_t* fee
     TRY(dalloc(&s->d_status, (size_t)s->ncols));
     TRY(dalloc(&s->d_innerok, (size_t)s->ncols));
     TRY(dalloc(&s->d_cls, (size_t)s->ncols));
-    TRY(dalloc(&s->d_order, (size_t)s->ncols * kQpClasses));
-    TRY(dalloc(&s->d_order_count, (size_t)kQpClasses));
+    TRY(dalloc(&s->d_order, (size_t)s->ncols * kQpLists));
+    TRY(dalloc(&s->d_order_count, (size_t)2 * kQpLists));
     TRY(dalloc(&s->d_cnt, (size_t)1));
     TRY(cudaHostAlloc((void**)&s->h_cnt, sizeof(Counters), cudaHostAllocDefault));
     memset(s->h_cnt, 0, sizeof(Counters));
@@ -586,7 +669,7 @@ int revs_create(revs_solver** out, int device, int n_feeders, const int64_t* fee
             const FeederDev& fd = s->feeders[f];
             sp[f] = ScreenProblem{(const char*)s->d_Rbf + 2 * fd.roff, fd.np, fd.np, fd.np,
                                   (const char*)s->d_gbf + 2 * fd.off, hp, s->d_v32 + fd.off, hp,
-                                  s->d_status + (size_t)f * T};
+                                  s->d_status + (size_t)f * T, s->d_cand + (size_t)f * T};
             for (int r0 = 0; r0 < fd.np; r0 += sbm) st.push_back(ContractTile{f, r0});
         }
         s->n_stiles = (int)st.size();
@@ -803,7 +886,8 @@ int revs_admm_begin(revs_solver* s, double kappa, int iter_max, double vset, dou
     return REVS_OK;
 }
 
-int revs_admm_step(revs_solver* s, double sums[3]) {
+namespace {
+int admm_step_impl(revs_solver* s, double sums[3], bool sync_now) {
     if (!s || !s->running) return fail(REVS_ERR_ARG, "revs_admm_begin has not been called");
     if (s->k >= s->iter_max) return fail(REVS_ERR_ARG, "iter_max iterations already done");
     CU(cudaSetDevice(s->device));
@@ -845,6 +929,10 @@ int revs_admm_step(revs_solver* s, double sums[3]) {
     CU(cudaEventRecord(s->evDualDone, s->sU));
     CU(cudaMemcpyAsync(s->h_cnt, s->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, s->sU));
     CU(cudaEventRecord(s->evT1, s->sU));
+    s->cur ^= 1;
+    s->k++;
+    s->stats.admm_iterations = s->k;
+    if (!sync_now) return REVS_OK;       // the next iteration is enqueued behind this one
     CU(cudaStreamSynchronize(s->sU));
     CU(cudaStreamSynchronize(s->sH));
     spans_collect(s);
@@ -852,9 +940,6 @@ int revs_admm_step(revs_solver* s, double sums[3]) {
         s->running = false;
         return fail(REVS_ERR_INFEASIBLE, "a home charging sub-problem is infeasible (SOC window vs plug-in window)");
     }
-    s->cur ^= 1;
-    s->k++;
-    s->stats.admm_iterations = s->k;
     s->stats.primal_residual = s->h_cnt->res.primal;
     s->stats.dual_residual = s->h_cnt->res.dual;
     s->stats.qp_newton_iterations = (int64_t)s->h_cnt->newton_its;
@@ -870,18 +955,32 @@ int revs_admm_step(revs_solver* s, double sums[3]) {
     }
     return REVS_OK;
 }
+}  // namespace
+
+int revs_admm_step(revs_solver* s, double sums[3]) { return admm_step_impl(s, sums, true); }
 
 int revs_solve_admm(revs_solver* s, double kappa, int iter_max, double vset, double vlow, double vhigh,
                     double tol, int* iters_done) {
+    const double th0 = now_ms();
+    g_host_sync_ms = 0.0;
+    for (double& v : g_cat_ms) v = 0.0;
     int rc = revs_admm_begin(s, kappa, iter_max, vset, vlow, vhigh);
     if (rc) return rc;
+    const double th1 = now_ms();
     s->tol = tol;
     for (int k = 0; k < iter_max; ++k) {
-        rc = revs_admm_step(s, nullptr);
+        // with a fixed iteration count (tol <= 0, the reference's setting) nothing has to come
+        // back to the host between iterations
+        rc = admm_step_impl(s, nullptr, tol > 0.0 || k == iter_max - 1);
         if (rc) return rc;
         if (tol > 0.0 && s->h_cnt->res.converged) break;
     }
     s->tol = 0.0;
+    if (getenv("REVS_DEBUG_HOST"))
+        fprintf(stderr, "[revs host] dev %d: begin %.3f ms, loop %.3f ms (waiting in round syncs %.3f ms), device span %.3f ms | "
+                "span sums: screen %.2f+%.2f home %.2f dual %.2f cls1 %.2f cls2-3 %.2f init %.2f warp8 %.2f warp4 %.2f sweep %.2f\n",
+                s->device, th1 - th0, now_ms() - th1, g_host_sync_ms, s->stats.total_ms, g_cat_ms[5], g_cat_ms[0], g_cat_ms[1],
+                g_cat_ms[2], g_cat_ms[3], g_cat_ms[4], g_cat_ms[6], g_cat_ms[7], g_cat_ms[8], g_cat_ms[9]);
     if (iters_done) *iters_done = s->k;
     return REVS_OK;
 }
@@ -1162,7 +1261,7 @@ int revs_screen_contract(int device, int M, int K, int T, const double* A, const
     TRYS(cudaMemcpy(dB, Bt.data(), Bt.size() * sizeof(double), cudaMemcpyHostToDevice));
     TRYS(launch_to_bf16(dA, dAb, Ap.size(), 0));
     TRYS(launch_to_bf16(dB, dBb, Bt.size(), 0));
-    ScreenProblem pb{dAb, Kp, M, Kp, dBb, Kp, dC, M, nullptr};
+    ScreenProblem pb{dAb, Kp, M, Kp, dBb, Kp, dC, M, nullptr, nullptr};
     std::vector<ContractTile> tiles;
     for (int r0 = 0; r0 < M; r0 += screen_tile_rows()) tiles.push_back(ContractTile{0, r0});
     TRYS(dalloc(&d_prob, (size_t)1));
@@ -1178,9 +1277,9 @@ int revs_screen_contract(int device, int M, int K, int T, const double* A, const
         TRYS(cudaMalloc(&dmaps, maps.size()));
         TRYS(cudaMemcpy(dmaps, maps.data(), maps.size(), cudaMemcpyHostToDevice));
         TRYS(dalloc(&dcol, (size_t)1));
-        TRYS(launch_screen_tc5(d_prob, d_tiles, (int)tiles.size(), dmaps, (const char*)dmaps + mb, dcol, T, 0));
+        TRYS(launch_screen_tc5(d_prob, d_tiles, (int)tiles.size(), dmaps, (const char*)dmaps + mb, dcol, T, 0.0, 0));
     } else {
-        TRYS(launch_screen(d_prob, d_tiles, (int)tiles.size(), T, 0));
+        TRYS(launch_screen(d_prob, d_tiles, (int)tiles.size(), T, 0.0, 0));
     }
     std::vector<float> out((size_t)M * T);
     TRYS(cudaMemcpy(out.data(), dC, out.size() * sizeof(float), cudaMemcpyDeviceToHost));

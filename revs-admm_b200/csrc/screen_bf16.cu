@@ -50,7 +50,7 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], const unsigned (&a)[4], 
 }
 
 __global__ void __launch_bounds__(kSThreads, 3)
-screen_bf16_kernel(const ScreenProblem* __restrict__ problems, const ContractTile* __restrict__ tiles, int T) {
+screen_bf16_kernel(const ScreenProblem* __restrict__ problems, const ContractTile* __restrict__ tiles, int T, double thr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(smem_raw);          // [stages][BM][kSLd]
     __nv_bfloat16* sB = sA + (size_t)kSStages * kSBM * kSLd;                 // [stages][BN][kSLd]
@@ -153,7 +153,10 @@ screen_bf16_kernel(const ScreenProblem* __restrict__ problems, const ContractTil
             for (int e = 0; e < 4; ++e) {
                 const int row = m0 + wm + i * 16 + g8 + ((e >> 1) << 3);
                 const int colj = n0 + wn + j * 8 + 2 * t4 + (e & 1);
-                if (row < pb.M && colj < T) pb.out[(size_t)colj * pb.ldo + row] = acc[i][j][e];
+                if (row < pb.M && colj < T) {
+                    pb.out[(size_t)colj * pb.ldo + row] = acc[i][j][e];
+                    if (pb.col_cand && (double)acc[i][j][e] > thr) pb.col_cand[colj] = 1;   // the column needs the QP kernel
+                }
             }
         }
 }
@@ -175,7 +178,7 @@ cudaError_t launch_to_bf16(const double* in, void* out, size_t n, cudaStream_t s
     return cudaGetLastError();
 }
 
-cudaError_t launch_screen(const ScreenProblem* d_problems, const ContractTile* d_tiles, int n_tiles, int T,
+cudaError_t launch_screen(const ScreenProblem* d_problems, const ContractTile* d_tiles, int n_tiles, int T, double thr,
                           cudaStream_t stream) {
     if (n_tiles == 0) return cudaSuccess;
     static bool attr_set = false;
@@ -184,7 +187,7 @@ cudaError_t launch_screen(const ScreenProblem* d_problems, const ContractTile* d
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    screen_bf16_kernel<<<dim3(n_tiles, (T + kSBN - 1) / kSBN), kSThreads, kSSmem, stream>>>(d_problems, d_tiles, T);
+    screen_bf16_kernel<<<dim3(n_tiles, (T + kSBN - 1) / kSBN), kSThreads, kSSmem, stream>>>(d_problems, d_tiles, T, thr);
     return cudaGetLastError();
 }
 

@@ -92,7 +92,7 @@ constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBN
 __global__ void __launch_bounds__(kThreadsT, 2)
 screen_tc5_kernel(const ScreenProblem* __restrict__ problems, const ContractTile* __restrict__ tiles,
                   const CUtensorMap* __restrict__ maps_a, const CUtensorMap* __restrict__ map_b,
-                  const int* __restrict__ b_col0, int T) {
+                  const int* __restrict__ b_col0, int T, double thr) {
     extern __shared__ unsigned char smem_raw[];
     const ContractTile tile = tiles[blockIdx.x];
     const ScreenProblem pb = problems[tile.problem];
@@ -172,7 +172,11 @@ screen_tc5_kernel(const ScreenProblem* __restrict__ problems, const ContractTile
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const int t = c0 + j;
-                    if (t < T) pb.out[(size_t)t * pb.ldo + row] = __uint_as_float(v[j]);
+                    if (t < T) {
+                        const float a = __uint_as_float(v[j]);
+                        pb.out[(size_t)t * pb.ldo + row] = a;
+                        if (pb.col_cand && (double)a > thr) pb.col_cand[t] = 1;   // the column needs the QP kernel
+                    }
                 }
             }
         }
@@ -224,7 +228,7 @@ uint32_t screen_tc5_box_rows_a() { return kBM; }
 uint32_t screen_tc5_box_rows_b() { return kBN; }
 
 cudaError_t launch_screen_tc5(const ScreenProblem* d_problems, const ContractTile* d_tiles, int n_tiles, const void* d_maps_a,
-                              const void* d_map_b, const int* d_b_col0, int T, cudaStream_t stream) {
+                              const void* d_map_b, const int* d_b_col0, int T, double thr, cudaStream_t stream) {
     if (n_tiles == 0) return cudaSuccess;
     if (T > kBN) return cudaErrorInvalidValue;
     static bool attr_set = false;
@@ -234,7 +238,7 @@ cudaError_t launch_screen_tc5(const ScreenProblem* d_problems, const ContractTil
         attr_set = true;
     }
     screen_tc5_kernel<<<n_tiles, kThreadsT, kSmemT, stream>>>(d_problems, d_tiles, reinterpret_cast<const CUtensorMap*>(d_maps_a),
-                                                            reinterpret_cast<const CUtensorMap*>(d_map_b), d_b_col0, T);
+                                                            reinterpret_cast<const CUtensorMap*>(d_map_b), d_b_col0, T, thr);
     return cudaGetLastError();
 }
 

@@ -28,6 +28,8 @@
 // threads, ~210 KB, 1 per SM).  Class 0 is the warp-per-column kernel of utility_qp_warp.cu
 // for small columns.  A column carries a class flag; qp_init_kernel classifies it by the size
 // of its warm-start set and a kernel hands it to the next class when it outgrows its own.
+#include <algorithm>
+
 #include <cuda_bf16.h>
 
 #include "kernels.cuh"
@@ -455,18 +457,35 @@ __device__ __forceinline__ double hess_row_dot(int i, const double* v, int ma, S
     return acc;
 }
 
-template <int WMAX, int THREADS, int CLS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
-    constexpr bool BIG = CLS == kQpClasses - 1;   // last class: nowhere to hand a column on to
-    using S = QpSmem<WMAX, THREADS>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    S& sm = *reinterpret_cast<S*>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int c = blockIdx.x;
-    if (P.order) {             // longest-first list of this class's running columns
-        if ((int)blockIdx.x >= P.order_count[CLS]) return;
-        c = P.order[(size_t)CLS * P.ncols + blockIdx.x];
+constexpr int kAddMaxVerify = 8;
+constexpr int kCtaPassMax = 16;          // admit / solve / verify passes of one launch (zones <= kVerifyMaxN)
+
+// exact voltages of ALL rows for the g in global memory: one warp per row
+template <int THREADS>
+__device__ void exact_voltages(const double* __restrict__ R, int ld, int n, const double* g, double* v) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NW = THREADS / 32;
+    for (int i0 = 4 * warp; i0 < n; i0 += 4 * NW) {       // four rows per warp step: loads and reductions overlap
+        double a[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int k = lane; k < n; k += 32) {
+            const double gk = g[k];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) a[q] = fma(R[(size_t)min(i0 + q, n - 1) * ld + k], gk, a[q]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) a[q] += __shfl_xor_sync(0xffffffffu, a[q], o);
+        }
+        if (lane < 4 && i0 + lane < n) v[i0 + lane] = lane == 0 ? a[0] : (lane == 1 ? a[1] : (lane == 2 ? a[2] : a[3]));
     }
+    __syncthreads();
+}
+
+template <int WMAX, int THREADS, int CLS, class S>
+__device__ void qp_column(const QpParams& P, const int c, S& sm) {
+    constexpr bool BIG = CLS == kQpClasses - 1;   // last class: nowhere to hand a column on to
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int f = c / P.T, t = c % P.T;
     long long tr_start = 0;
     const long long tr_clk0 = clock64();
@@ -486,11 +505,25 @@ __global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
     const double* rn2 = P.rn2 + fd.off;
     int* widx = P.widx + (size_t)c * kWMax;
 
+    // Zones up to kVerifyMaxN residences finish inside this launch: after the restricted solve
+    // the voltages of ALL rows are recomputed exactly for the new g (a warp per row, the block
+    // of R is L2-resident) and violated rows are admitted in a further pass.  Larger zones leave
+    // the check to the next tensor-core screening pass of the host loop.
+    const bool self_verify = n <= kVerifyMaxN;
+    int inner_prev = P.inner_ok[c];   // 1 solved earlier; 2/3 handed over in this round (3: g changed since the screen)
+    unsigned long long its_all = 0;
+    unsigned n_evals = 0, n_pdas = 0, n_fallback = 0;
+    double flops = 0.0;
+    long long tc[5] = {0, 0, 0, 0, 0}, t0 = clock64(), t1;   // phase cycles (debug)
+    int m = 0, ok = 0;
+    bool finished = false, handed = false;
+    for (int pass = 0; pass < kCtaPassMax; ++pass) {
     // ------------------------------------------------------------ working set
-    int m = 0;
-    bool clean = false;   // step launch that found no violated row: v is still valid if g stays put
+    bool clean = false;   // no violated row found: v is still valid if g stays put
     {
-        if (P.v32_t) {
+        if (pass == 0 && P.sweep && inner_prev == 3 && self_verify) {
+            exact_voltages<THREADS>(R, ld, n, g, v);
+        } else if (P.v32_t && pass == 0) {
             // Voltages came from the BF16 screening pass: rows at or below (1-margin) u are
             // proven feasible; every other row without a multiplier is a candidate whose
             // voltage is recomputed here exactly (FP64 row of R times g), one warp per row.
@@ -532,7 +565,9 @@ __global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
         double prev_v = 1e300;
         int prev_i = -1;
         int added = 0, n_viol_left = 0;
-        const int room = min(kAddMax, WMAX - m);
+        // zones that verify in-kernel admit few rows per pass: after a re-solve with the most violated
+        // rows most neighbouring violations are gone
+        const int room = min(self_verify ? kAddMaxVerify : kAddMax, WMAX - m);
         for (int round = 0; round <= room; ++round) {
             double best = -1.0;
             int besti = 0x7fffffff;
@@ -564,18 +599,26 @@ __global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
             prev_v = best; prev_i = besti;
         }
         __syncthreads();
-        if (added == 0 && n_viol_left == 0 && P.inner_ok[c]) {
+        if (added == 0 && n_viol_left == 0 && inner_prev == 1) {
             if (tid == 0) P.status[c] = 1;      // KKT point of the full problem
-            return;
+            finished = true;
+            break;
         }
         if (n_viol_left && m + added == WMAX) {
-            if (!BIG) {                         // hand the column over, state untouched
-                if (tid == 0) { P.cls[c] = CLS + 1; atomicAdd(P.n_running, 1); atomicAdd(P.n_cls + CLS + 1, 1); }
-                return;
+            if (!BIG) {                         // hand the column over (state consistent; 3: g moved since the screen)
+                if (tid == 0) {
+                    P.cls[c] = CLS + 1;
+                    P.inner_ok[c] = (pass > 0 || inner_prev == 3) ? 3 : 2;
+                    atomicAdd(P.n_running, 1);
+                    atomicAdd(P.n_cls + CLS + 1, 1);
+                }
+                handed = true;
+                break;
             }
             if (added == 0) {
                 if (tid == 0) { P.status[c] = 2; atomicAdd(P.n_failed, 1); }
-                return;
+                finished = true;
+                break;
             }
         }
         clean = (added == 0 && n_viol_left == 0);
@@ -589,11 +632,10 @@ __global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
     __nv_bfloat16* gbf = P.gbf_t ? reinterpret_cast<__nv_bfloat16*>(P.gbf_t) + col : nullptr;
     double phi = eval_phi<THREADS>(R, ld, n, z, sm.idx, sm.lam, m, u, g, sm, nullptr, nullptr, nullptr, gbf);
     double tau = 1.0;
-    int ok = 0, its = 0;
-    unsigned n_evals = 0, n_pdas = 0, n_fallback = 0;
-    double flops = 2.0 * m * n;                 // algorithmic FP64 flops of this launch (first evaluation)
+    int its = 0;
+    ok = 0;
+    flops += 2.0 * m * n;                       // algorithmic FP64 flops of this launch (first evaluation)
     bool have_H = false;   // Hb/hdiag hold the Hessian for the mask in sm.fmask
-    long long tc[5] = {0, 0, 0, 0, 0}, t0 = clock64(), t1;   // phase cycles (debug)
 #define PHASE(i) do { t1 = clock64(); tc[i] += t1 - t0; t0 = t1; } while (0)
     const int inner_max = P.inner_max;
     double scale = 0.0;                         // mean |R_a|^2 over W: curvature scale of the Hessian shifts
@@ -775,15 +817,26 @@ __global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
     // no violated row and the stored iterate already satisfies KKT on W: it is the solution
     // (g was not touched, so the voltages the violation scan used are its voltages)
     const bool done = clean && ok && its == 0;
+    its_all += (unsigned long long)its;
     if (tid == 0) {
         P.wcount[c] = m;
         P.inner_ok[c] = ok;
         P.status[c] = done ? 1 : 0;
-        if (!done) atomicAdd(P.n_running, 1);
-        atomicAdd(P.n_cls + CLS, 1);
-        atomicAdd(P.newton_its, (unsigned long long)its);
+    }
+    if (done) { finished = true; break; }
+    if (!self_verify || !ok || inner_max <= 0) break;      // the next screening pass checks the other rows
+    __syncthreads();
+    exact_voltages<THREADS>(R, ld, n, g, v);
+    flops += 2.0 * n * n;
+    inner_prev = 1;
+    }   // pass
+
+    if (tid == 0) {
+        if (!finished && !handed) { atomicAdd(P.n_running, 1); atomicAdd(P.n_cls + CLS, 1); }
+        atomicAdd(P.newton_its, its_all);
         atomicMax(P.max_ws, m);
         atomicAdd(P.flops, (unsigned long long)flops);
+        const unsigned long long its = its_all;
         if (P.trace) {
             long long tr_end; unsigned smid;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_end));
@@ -803,29 +856,62 @@ __global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
     }
 }
 
-// Work list per class for one working-set round: the running columns of each class,
-// compacted (block-level counts, one atomic per class and CTA).  order_count must be zero.
-__global__ void __launch_bounds__(256) order_columns_kernel(const int* __restrict__ status, const int* __restrict__ cls,
-                                                            int ncols, int* __restrict__ order, int* __restrict__ order_count) {
-    __shared__ int cnt[kQpClasses], base[kQpClasses];
-    const int tid = threadIdx.x;
-    if (tid < kQpClasses) cnt[tid] = 0;
-    __syncthreads();
-    const int c = blockIdx.x * blockDim.x + tid;
-    int cl = -1, pos = 0;
-    if (c < ncols && status[c] == 0) { cl = cls[c]; pos = atomicAdd(&cnt[cl], 1); }
-    __syncthreads();
-    if (tid < kQpClasses) base[tid] = cnt[tid] ? atomicAdd(&order_count[tid], cnt[tid]) : 0;
-    __syncthreads();
-    if (cl >= 0) order[(size_t)cl * ncols + base[cl] + pos] = c;
+// The kernel proper: CTAs pull the running columns of their class from a device-side queue
+// (list built by order_columns_kernel), so the grid does not depend on counts the host would
+// have to read back.
+template <int WMAX, int THREADS, int CLS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
+    using S = QpSmem<WMAX, THREADS>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    S& sm = *reinterpret_cast<S*>(smem_raw);
+    const int count = P.order_count[CLS];
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) sm.ibcast[0] = atomicAdd(P.queue + CLS, 1);
+        __syncthreads();
+        const int slot = sm.ibcast[0];
+        if (slot >= count) break;
+        qp_column<WMAX, THREADS, CLS>(P, P.order[(size_t)CLS * P.ncols + slot], sm);
+    }
 }
 
-cudaError_t launch_order_columns(const int* status, const int* cls, const int* wcount, int ncols, int* order,
-                                 int* order_count, cudaStream_t stream) {
-    (void)wcount;
-    cudaError_t e = cudaMemsetAsync(order_count, 0, kQpClasses * sizeof(int), stream);
+// Work lists for one working-set round (block-level counts, one atomic per list and CTA):
+// lists 1..3 = running columns of the CTA classes, lists 4..7 = the warp kernel's columns by
+// working-set size (>= 3, 2, 1, 0).  mode 0 (first round): a warp-class column without
+// multipliers and without a screening candidate is already solved (g = [z]_+) and never
+// reaches a QP kernel.  mode 2 (sweep): only columns handed over during this round.
+// order_count must be zero.
+__global__ void __launch_bounds__(256) order_columns_kernel(QpParams P, int mode, int* __restrict__ order,
+                                                            int* __restrict__ order_count) {
+    __shared__ int cnt[kQpLists], base[kQpLists];
+    const int tid = threadIdx.x;
+    if (tid < kQpLists) cnt[tid] = 0;
+    __syncthreads();
+    const int c = blockIdx.x * blockDim.x + tid;
+    int li = -1, pos = 0;
+    if (c < P.ncols && P.status[c] == 0) {
+        const int cl = P.cls[c];
+        if (mode == 2) {
+            if (cl >= 1 && P.inner_ok[c] >= 2) li = cl;
+        } else if (cl >= 1) {
+            li = cl;
+        } else {
+            const int m = P.wcount[c];
+            if (mode == 0 && m == 0 && P.cand && P.cand[c] == 0) { P.status[c] = 1; P.inner_ok[c] = 1; }
+            else li = kQpClasses + (P.feeders[c / P.T].n <= 128 ? 0 : kQpBuckets) + (m >= 3 ? 0 : 3 - m);
+        }
+        if (li >= 0) pos = atomicAdd(&cnt[li], 1);
+    }
+    __syncthreads();
+    if (tid < kQpLists) base[tid] = cnt[tid] ? atomicAdd(&order_count[tid], cnt[tid]) : 0;
+    __syncthreads();
+    if (li >= 0) order[(size_t)li * P.ncols + base[li] + pos] = c;
+}
+
+cudaError_t launch_order_columns(const QpParams& P, int mode, int* order, int* order_count, cudaStream_t stream) {
+    cudaError_t e = cudaMemsetAsync(order_count, 0, 2 * kQpLists * sizeof(int), stream);   // counts and queue heads
     if (e != cudaSuccess) return e;
-    order_columns_kernel<<<(ncols + 255) / 256, 256, 0, stream>>>(status, cls, ncols, order, order_count);
+    order_columns_kernel<<<(P.ncols + 255) / 256, 256, 0, stream>>>(P, mode, order, order_count);
     return cudaGetLastError();
 }
 
@@ -849,9 +935,17 @@ cudaError_t launch_utility_qp(const QpParams& P, int grid, int cls, cudaStream_t
         attr_set = true;
     }
     if (grid <= 0) return cudaSuccess;
-    if (cls == 1) k0<<<grid, 128, sizeof(S0), stream>>>(P);
-    else if (cls == 2) k1<<<grid, 256, sizeof(S1), stream>>>(P);
-    else if (cls == 3) k2<<<grid, 256, sizeof(S2), stream>>>(P);
+    static int n_sm = 0;
+    if (!n_sm) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+    }
+    // at most one wave of resident CTAs; they pull columns from the class queue
+    if (cls == 1) k0<<<std::min(grid, n_sm * kMinB0), 128, sizeof(S0), stream>>>(P);
+    else if (cls == 2) k1<<<std::min(grid, n_sm * kMinB1), 256, sizeof(S1), stream>>>(P);
+    else if (cls == 3) k2<<<std::min(grid, n_sm), 256, sizeof(S2), stream>>>(P);
     else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }

@@ -1,20 +1,33 @@
-// Utility QP, small columns: ONE WARP per (zone, hour) column, no block barriers.
+// Utility QP, small columns: ONE WARP per (zone, hour) column, no block barriers, no host
+// round trips.
 //
 // After a feeder is split into its voltage zones (feeder.py:split_zones) most columns have
-// n ~ 10^2 residences and a handful of binding voltage rows.  For those the CTA-wide kernel of
-// utility_qp.cu spends its time in barriers and in latency it cannot hide; here a column
-// lives in the registers of a single warp:
-//   lanes own the homes   j = lane + 32 k  (k < NJ, n <= 32 NJ): z_j, g_j, trial g_j
+// n ~ 10^2 residences and one or two binding voltage rows.  A column lives in the registers
+// of a single warp:
+//   lanes own the homes   j = lane + 32 k  (k < NJ, n <= 32 NJ): z_j, g_j, voltage bound of row j
 //   lanes own the rows    a < m <= 16 of the working set: idx_a, lam_a, grad_a, H[a][.]
-// and every step of the algorithm of utility_qp.cu (same fixed point, same tolerances) is a
-// few shuffles: Hessian = rank-1 updates over the homes of F (row a of H accumulates in lane
-// a's registers; later pieces apply signed updates for the homes that crossed g = 0),
-// primal-dual active-set loop with a 16x16 Cholesky in shared memory, segment line search.
-// Anything unusual -- working set outgrowing 16 rows, active-set guesses cycling, line search
-// failing -- hands the column, untouched, to the CTA kernel of the next class.
+// and the kernel is persistent: every warp pulls columns from a device-side queue (hardest
+// first, lists built by order_columns_kernel), so a finished column frees its slot at once and
+// columns that need no work never occupy one.
+//
+// Per column (same fixed point and tolerances as utility_qp.cu / oracle project_voltage):
+//   1. screened voltages (BF16 tensor pass) -> exact FP64 recheck of the candidate rows,
+//   2. admit the most violated rows, copy the working rows of R into shared memory (8 KB per
+//      warp) so that gradient / Hessian / line search never go back to L2,
+//   3. minimise the dual on W: |W| = 1 is a monotone Newton iteration on a convex piecewise
+//      linear function in registers; otherwise piecewise-quadratic descent with an exact
+//      primal-dual active-set step (16x16 Cholesky in shared memory) and a segment line search,
+//   4. VERIFY every row outside W without leaving the kernel: with D+ = sum_j (g_new - g_old)_+,
+//      v_i(g_new) <= v_i(g_old) + max_j R_ij * D+  (all entries of R are >= 0), so rows whose bound
+//      stays below u are proven feasible -- usually all of them, because raising multipliers
+//      only lowers g -- and the few others are recomputed exactly; violated rows join W -> 2.
+// Nothing is written until the column is finished; a column that outgrows 16 rows, cycles or
+// fails a line search is handed, untouched, to the CTA kernel of the next class (same round).
 //
 // qp_init_kernel (also one warp per column, any size) starts a utility solve: working set =
 // support of the stored multipliers, class by its size, g = [z - R lam]_+ for the new target.
+#include <cstdlib>
+
 #include <cuda_bf16.h>
 
 #include "kernels.cuh"
@@ -23,19 +36,603 @@ namespace revs {
 
 namespace {
 
-constexpr int kWarpsPerCta = 1;              // one column per CTA: a finished column frees its slot at once
+constexpr int kWarpsPerCta = 4;
+constexpr int kCtasPerSm = 4;                // 16 resident columns per SM
 constexpr int kHW = kWW + 1;                 // leading dim of the per-warp 16x16 matrices
+constexpr int kCacheDoubles = 1024;          // per-warp cache of working rows of R
 constexpr double kArcMinW = 9.5367431640625e-07;
 constexpr int kPdasMaxW = 40;
 constexpr double kHessShiftW = 1e-12;
-constexpr int kAddMaxW = 8;                  // violated rows admitted per round by the warp kernel
+constexpr int kAddMaxW = 8;                  // violated rows admitted per pass
+constexpr int kPassMaxW = 10;                // admit / solve / verify passes before the column is handed on
+constexpr int kRecheckMaxW = 256;             // rows re-evaluated exactly per verification; more -> next screening pass
+constexpr int kHysteresisW = 8;              // warm working sets above kWW - this start in class 1 (long columns: a whole CTA each)
 
 struct WarpSmem {
     double H[kWW * kHW];      // model Hessian, full symmetric
     double L[kWW * kHW];      // Cholesky factor of the active sub-matrix
+    double rows[kCacheDoubles];
+};
+
+struct WarpStats {
+    unsigned long long its = 0;
+    double flops = 0.0;
+    int handed = 0, deferred = 0, max_ws = 0;
 };
 
 __device__ __forceinline__ double warp_bcast(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+// Exact FP64 voltages of the rows flagged in candk (bit k of a lane: row lane+32k) for the
+// schedule in gj[]: four rows at a time so that their loads and reductions overlap.  The loop
+// over k is a run-time loop on purpose (code size: the kernel must stay in the instruction cache).
+template <int NJ>
+__device__ __forceinline__ void recheck_rows(unsigned candk, const double* __restrict__ R, int ld, int n,
+                                             const double (&gj)[NJ], double (&vub)[NJ]) {
+    const int lane = threadIdx.x & 31;
+    const unsigned full = 0xffffffffu;
+    if (!__any_sync(full, candk != 0u)) return;
+#pragma unroll 1
+    for (int k = 0; k < NJ; ++k) {
+        unsigned cand = __ballot_sync(full, (candk >> k) & 1u);
+        while (cand) {
+            int s[4], cnt = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (cand) { s[q] = __ffs(cand) - 1; cand &= cand - 1; ++cnt; }
+                else s[q] = s[0];
+            }
+            double a[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int kk = 0; kk < NJ; ++kk) {
+                const int jj = lane + 32 * kk;
+                if (jj < n) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) a[q] = fma(R[(size_t)(s[q] + 32 * k) * ld + jj], gj[kk], a[q]);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) a[q] += __shfl_xor_sync(full, a[q], o);
+            }
+            double mine = 0.0;
+            bool hit = false;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (q < cnt && lane == s[q]) { mine = a[q]; hit = true; }
+            if (hit) {
+#pragma unroll
+                for (int kk = 0; kk < NJ; ++kk)
+                    if (kk == k) vub[kk] = mine;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+template <int NJ>
+__device__ __forceinline__ void solve_column(const QpParams& P, const int c, WarpSmem& sm, WarpStats& st) {
+    const int lane = threadIdx.x & 31;
+    const unsigned full = 0xffffffffu;
+    const int f = c / P.T, t = c - f * P.T;
+    const int m_old = P.wcount[c];
+    const bool solved_before = P.inner_ok[c] == 1;
+    int* widx = P.widx + (size_t)c * kWMax;
+    const int wi = lane < m_old ? widx[lane] : 0;      // issued early: the multipliers depend on it
+    const FeederDev fd = P.feeders[f];
+    const int n = fd.n, ld = fd.np;
+    const double* __restrict__ R = P.Rpool + fd.roff;
+    const size_t col = (size_t)t * P.Hp + fd.off;
+    const double* z = P.z_t + col;
+    double* lam_g = P.lam_t + col;
+    double* g = P.g_t + col;
+    const double u = P.u, tol = P.tol;
+
+    long long tr_start = 0;
+    if (P.trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_start));
+    const long long tr_clk0 = clock64();
+    const double thr = (1.0 - kScreenMargin) * u;
+
+    // ---- this lane's homes; vub[k] is an upper bound of the voltage of row lane+32k for the g
+    // in g0[] and EXACT whenever it exceeds u (invariant kept by every step below)
+    double zj[NJ], gj[NJ], g0[NJ], vub[NJ];
+    unsigned inw = 0;                          // bit k: row lane+32k is in the working set
+    unsigned candk = 0;                        // bit k: row lane+32k must be re-evaluated exactly
+    {
+        const float* v32 = P.v32_t ? P.v32_t + col : nullptr;
+        const double* v64 = P.v_t + col;
+#pragma unroll
+        for (int k = 0; k < NJ; ++k) {
+            const int j = lane + 32 * k;
+            const bool in = j < n;
+            zj[k] = in ? z[j] : 0.0;
+            gj[k] = in ? g[j] : 0.0;
+            g0[k] = gj[k];
+            if (m_old > 0 && in && lam_g[j] > 0.0) inw |= 1u << k;
+            if (v32) {
+                const double a = in ? (double)v32[j] : 0.0;
+                vub[k] = kScreenUp * a;
+                if (in && a > thr) candk |= 1u << k;
+            } else {
+                vub[k] = in ? v64[j] : 0.0;
+            }
+        }
+        candk &= ~inw;
+    }
+
+    // ---- working set: rows with a positive multiplier (order preserved), lanes = rows
+    int idx = 0, m = 0;
+    double lam = 0.0;
+    if (m_old > 0) {
+        const double l = lane < m_old ? lam_g[wi] : 0.0;
+        const unsigned keep = __ballot_sync(full, lane < m_old && l > 0.0);
+        m = __popc(keep);
+        const int src = __fns(keep, 0, lane + 1);          // lane a takes the a-th kept row
+        const int si = __shfl_sync(full, wi, src & 31);
+        const double sl = __shfl_sync(full, l, src & 31);
+        if (lane < m) { idx = si; lam = sl; }
+    }
+
+    double flops = 0.0;
+    int its_total = 0;
+    bool changed = false;                      // g differs from the stored iterate
+    long long tph[4] = {0, 0, 0, 0}, tq0 = clock64(), tq1;   // debug trace: cycles in load / admit+cache / solve / verify
+    int npass = 0;
+#define WPHASE(i) do { if (P.trace) { tq1 = clock64(); tph[i] += tq1 - tq0; tq0 = tq1; } } while (0)
+    auto trace_out = [&](int kind) {
+        if (P.trace && lane == 0) {
+            long long tr_end; unsigned smid;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_end));
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            long long* rec = P.trace + 12 * (size_t)c;
+            rec[0] = tr_start; rec[1] = tr_end; rec[2] = smid; rec[3] = ((long long)m << 20) | its_total;
+            for (int i = 0; i < 4; ++i) rec[4 + i] = tph[i];
+            rec[8] = npass; rec[9] = kind; rec[10] = m_old; rec[11] = clock64() - tr_clk0;
+        }
+    };
+    tph[0] = tq0 - tr_clk0;
+    // exit kinds: 0 finished (persist), 1 deferred to the next screening pass (persist, still running),
+    // 2 handed to the CTA class untouched
+    int exit_kind = 0, reason = 0;             // reason of a hand-over (debug trace)
+    double grad = 0.0;                         // u - v of this lane's row at the last solution
+
+    for (int pass = 0;; ++pass) {
+        // ---- exact voltages of the candidate rows (screening candidates / rows whose bound failed)
+        recheck_rows<NJ>(candk, R, ld, n, gj, vub);
+        candk = 0;
+        WPHASE(pass == 0 ? 0 : 3);
+
+        // ---- rows whose multiplier went to zero leave W (their exact voltage is u - grad)
+        if (pass > 0) {
+            const bool row = lane < m;
+            unsigned drop = __ballot_sync(full, row && !(lam > 0.0));
+            if (drop) {
+                const unsigned keep = __ballot_sync(full, row && lam > 0.0);
+                while (drop) {
+                    const int a = __ffs(drop) - 1;
+                    drop &= drop - 1;
+                    const int h = __shfl_sync(full, idx, a);
+                    const double vr = u - warp_bcast(grad, a);
+                    if ((h & 31) == lane) {
+#pragma unroll
+                        for (int k = 0; k < NJ; ++k)
+                            if (k == (h >> 5)) { vub[k] = vr; inw &= ~(1u << k); }
+                    }
+                }
+                m = __popc(keep);
+                const int src = __fns(keep, 0, lane + 1);
+                const int si = __shfl_sync(full, idx, src & 31);
+                const double sl = __shfl_sync(full, lam, src & 31);
+                idx = lane < m ? si : 0;
+                lam = lane < m ? sl : 0.0;
+            }
+        }
+
+        // ---- violated rows outside W, most violated first (ties: lowest row)
+        int added = 0;
+        bool left = false;
+        const int room = min(kAddMaxW, kWW - m);
+#pragma unroll 1
+        for (int r = 0; r <= room; ++r) {
+            double best = -1.0;
+            int bj = 0x7fffffff;
+#pragma unroll
+            for (int k = 0; k < NJ; ++k) {
+                const int j = lane + 32 * k;
+                const double viol = vub[k] - u;
+                if (j < n && !((inw >> k) & 1u) && viol > tol && viol > best) { best = viol; bj = j; }
+            }
+            if (!__any_sync(full, best >= 0.0)) break;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ob = __shfl_xor_sync(full, best, o);
+                const int oj = __shfl_xor_sync(full, bj, o);
+                if (ob > best || (ob == best && oj < bj)) { best = ob; bj = oj; }
+            }
+            if (r == room) { left = true; break; }
+            if (lane == m + added) { idx = bj; lam = 0.0; }
+            if ((bj & 31) == lane) inw |= 1u << (bj >> 5);
+            ++added;
+        }
+        if (added == 0 && !left) {
+            // no violated row: after a solve + verification this is the KKT point; at the start it
+            // is one if there is nothing to solve or the stored iterate was solved already
+            if (pass > 0 || m == 0 || solved_before) break;
+        }
+        if ((left && m + added == kWW) || pass >= kPassMaxW) { exit_kind = 2; reason = pass >= kPassMaxW ? 2 : 1; break; }
+        m += added;
+        ++npass;
+        const bool row = lane < m;
+
+        // ---- working rows of R into shared memory (as many as fit)
+        const int ncache = min(m, kCacheDoubles / ld);
+        __syncwarp();
+#pragma unroll 1
+        for (int a = 0; a < ncache; ++a) {
+            const double* src = R + (size_t)__shfl_sync(full, idx, a) * ld;
+            double tmp[NJ];
+#pragma unroll
+            for (int k = 0; k < NJ; ++k) {
+                const int j = lane + 32 * k;
+                tmp[k] = j < n ? src[j] : 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < NJ; ++k) {
+                const int j = lane + 32 * k;
+                if (j < n) sm.rows[a * ld + j] = tmp[k];
+            }
+        }
+        __syncwarp();
+        auto rowp = [&](int a) -> const double* {      // a is warp-uniform
+            const int ia = __shfl_sync(full, idx, a);
+            return a < ncache ? sm.rows + a * ld : R + (size_t)ia * ld;
+        };
+
+        int ok = 0, its = 0;
+        bool bail = false;
+        WPHASE(1);
+
+        // ---- |W| = 1: the dual is one-dimensional, v(lam) = r . [z - r lam]_+ is convex, piecewise
+        // linear and non-increasing; Newton on v(lam) = u converges monotonically from the left and
+        // lands on the exact root of the final piece
+        if (m == 1) {
+            const double* rp = rowp(0);
+            double r1[NJ];
+#pragma unroll
+            for (int k = 0; k < NJ; ++k) {
+                const int j = lane + 32 * k;
+                r1[k] = j < n ? rp[j] : 0.0;
+            }
+            const double l_in = warp_bcast(lam, 0);
+            double l = l_in;
+#pragma unroll 1
+            for (int it = 0; it < 48; ++it) {
+                double v = 0.0, S = 0.0;
+#pragma unroll
+                for (int k = 0; k < NJ; ++k) {
+                    const double gk = fmax(zj[k] - r1[k] * l, 0.0);
+                    gj[k] = gk;
+                    v = fma(r1[k], gk, v);
+                    if (gk > 0.0) S = fma(r1[k], r1[k], S);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    v += __shfl_xor_sync(full, v, o);
+                    S += __shfl_xor_sync(full, S, o);
+                }
+                ++its;
+                const double fr = v - u;
+                if ((l > 0.0 ? fabs(fr) : fmax(fr, 0.0)) < tol) { ok = 1; grad = -fr; break; }
+                double ln = S > 0.0 ? l + fr / S : 0.0;
+                if (ln < 0.0) ln = 0.0;
+                if (ln == l) break;                    // stagnation: let the general path decide
+                l = ln;
+            }
+            flops += 4.0 * n * its;
+            lam = lane == 0 ? l : 0.0;                 // gj[] is [z - r l]_+ either way
+            if (l != l_in) changed = true;
+            if (ok && l == l_in) its = 0;
+            if (!ok) its = 0;
+        }
+
+        if (!ok) {
+            // ---- general path: piecewise-quadratic descent on W
+            const double scale = warp_sum(row ? P.rn2[fd.off + idx] : 0.0) / (double)max(m, 1);
+            const double shift = kHessShiftW * scale + 1e-300;
+            double phi;
+            {
+                double acc = 0.0;
+#pragma unroll
+                for (int k = 0; k < NJ; ++k) acc = fma(gj[k], gj[k], acc);
+                phi = 0.5 * warp_sum(acc) + u * warp_sum(row ? lam : 0.0);
+            }
+            double hrow[kWW];                 // row `lane` of H (columns <= lane are maintained)
+#pragma unroll
+            for (int q = 0; q < kWW; ++q) hrow[q] = 0.0;
+            unsigned fbits = 0;               // bit k: home lane+32k was in F when H was last updated
+            bool have_H = false;
+
+#pragma unroll 1
+            for (; its < P.inner_max; ++its) {
+                // gradient on W
+                grad = 0.0;
+#pragma unroll 1
+                for (int a = 0; a < m; ++a) {
+                    const double* rr = rowp(a);
+                    double acc = 0.0;
+#pragma unroll
+                    for (int k = 0; k < NJ; ++k) {
+                        const int j = lane + 32 * k;
+                        if (j < n) acc = fma(rr[j], gj[k], acc);
+                    }
+                    acc = warp_sum(acc);
+                    if (lane == a) grad = u - acc;
+                }
+                flops += 2.0 * m * n;
+                const double kk = row ? fabs(lam > 0.0 ? grad : fmin(grad, 0.0)) : 0.0;
+                const double kkt = warp_max(kk);
+                if (kkt < tol) { ok = 1; break; }
+
+                // Hessian.  First piece: H[p][q] = sum over F of row p times row q (lanes = homes),
+                // two q at a time so the loads overlap.  Later pieces: signed rank-1 updates for the
+                // homes whose membership of F changed.
+                {
+                    int nupd = 0;
+                    unsigned nowmask = 0;
+#pragma unroll
+                    for (int k = 0; k < NJ; ++k)
+                        if (gj[k] > 0.0) nowmask |= 1u << k;
+                    if (!have_H) {
+#pragma unroll 1
+                        for (int p = 0; p < m; ++p) {
+                            const double* rp_ptr = rowp(p);
+                            double rp[NJ];
+#pragma unroll
+                            for (int k = 0; k < NJ; ++k) {
+                                const int j = lane + 32 * k;
+                                rp[k] = (j < n && gj[k] > 0.0) ? rp_ptr[j] : 0.0;
+                            }
+#pragma unroll 1
+                            for (int q = 0; q <= p; q += 2) {
+                                const double* r0 = rowp(q);
+                                const double* r1 = rowp(min(q + 1, p));
+                                double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                                for (int k = 0; k < NJ; ++k) {
+                                    const int j = lane + 32 * k;
+                                    if (j < n) { a0 = fma(rp[k], r0[j], a0); a1 = fma(rp[k], r1[j], a1); }
+                                }
+#pragma unroll
+                                for (int o = 16; o > 0; o >>= 1) {
+                                    a0 += __shfl_xor_sync(full, a0, o);
+                                    a1 += __shfl_xor_sync(full, a1, o);
+                                }
+                                if (lane == p) {
+#pragma unroll
+                                    for (int qq = 0; qq < kWW; ++qq) {
+                                        if (qq == q) hrow[qq] = a0;
+                                        if (qq == q + 1 && q + 1 <= p) hrow[qq] = a1;
+                                    }
+                                }
+                            }
+                        }
+                        nupd = __reduce_add_sync(full, __popc(nowmask));
+                    } else {
+#pragma unroll 1
+                        for (int k = 0; k < NJ; ++k) {
+                            const bool now = (nowmask >> k) & 1u;
+                            const bool was = (fbits >> k) & 1u;
+                            unsigned chg = __ballot_sync(full, now != was);
+                            const unsigned nowb = __ballot_sync(full, now);
+                            while (chg) {
+                                const int src = __ffs(chg) - 1;
+                                chg &= chg - 1;
+                                const int j = src + 32 * k;
+                                const double sgn = ((nowb >> src) & 1u) ? 1.0 : -1.0;
+                                const double ra = row ? (lane < ncache ? sm.rows[lane * ld + j] : R[(size_t)idx * ld + j]) : 0.0;
+#pragma unroll
+                                for (int q = 0; q < kWW; ++q) {
+                                    const double rq = warp_bcast(ra, q);
+                                    if (q <= lane) hrow[q] = fma(sgn * ra, rq, hrow[q]);
+                                }
+                                ++nupd;
+                            }
+                        }
+                    }
+                    fbits = nowmask;
+                    have_H = true;
+                    flops += (double)m * (m + 1) * nupd;
+                    __syncwarp();
+#pragma unroll
+                    for (int q = 0; q < kWW; ++q)
+                        if (row && q <= lane) { sm.H[lane * kHW + q] = hrow[q]; sm.H[q * kHW + lane] = hrow[q]; }
+                    __syncwarp();
+                }
+
+                // ---- exact minimiser of the piece over lam_W >= 0: primal-dual active set, lanes = rows
+                double b = 0.0;
+#pragma unroll 1
+                for (int q = 0; q < m; ++q) {
+                    const double lq = warp_bcast(lam, q);
+                    if (row && lq != 0.0) b = fma(sm.H[lane * kHW + q], lq, b);
+                }
+                b += shift * lam - grad;
+                bool inA = row && (lam > 0.0 || grad < 0.0);
+                double x = 0.0;
+                bool pdas_ok = false;
+#pragma unroll 1
+                for (int guess = 0; guess < kPdasMaxW; ++guess) {
+                    const unsigned Am = __ballot_sync(full, inA);
+                    const int ma = __popc(Am);
+                    const int pos = __popc(Am & ((1u << lane) - 1));
+                    double xs = 0.0;
+                    if (ma > 0) {
+                        const int o = (lane < ma) ? (int)__fns(Am, 0, lane + 1) : 0;     // original row of compact row `lane`
+                        // gather H_AA (+ shift) into L, lane = compact row
+#pragma unroll 1
+                        for (int cidx = 0; cidx < ma; ++cidx) {
+                            const int oc = __shfl_sync(full, o, cidx);
+                            if (lane < ma && cidx <= lane) sm.L[lane * kHW + cidx] = sm.H[o * kHW + oc] + (cidx == lane ? shift : 0.0);
+                        }
+                        __syncwarp();
+#pragma unroll 1
+                        for (int k2 = 0; k2 < ma; ++k2) {            // Cholesky, lanes own rows
+                            const double dkk = sqrt(fmax(sm.L[k2 * kHW + k2], 1e-300));
+                            __syncwarp();
+                            if (lane == k2) sm.L[k2 * kHW + k2] = dkk;
+                            double lik = 0.0;
+                            if (lane > k2 && lane < ma) { lik = sm.L[lane * kHW + k2] / dkk; sm.L[lane * kHW + k2] = lik; }
+                            __syncwarp();
+                            if (lane > k2 && lane < ma)
+                                for (int j2 = k2 + 1; j2 <= lane; ++j2)
+                                    sm.L[lane * kHW + j2] = fma(-lik, sm.L[j2 * kHW + k2], sm.L[lane * kHW + j2]);
+                            __syncwarp();
+                        }
+                        double y = warp_bcast(b, o);                   // rhs of compact row `lane`
+                        if (lane >= ma) y = 0.0;
+#pragma unroll 1
+                        for (int k2 = 0; k2 < ma; ++k2) {
+                            const double yk = warp_bcast(y, k2) / sm.L[k2 * kHW + k2];
+                            if (lane == k2) y = yk;
+                            if (lane > k2 && lane < ma) y = fma(-sm.L[lane * kHW + k2], yk, y);
+                        }
+#pragma unroll 1
+                        for (int k2 = ma - 1; k2 >= 0; --k2) {
+                            const double xk = warp_bcast(y, k2) / sm.L[k2 * kHW + k2];
+                            if (lane == k2) y = xk;
+                            if (lane < k2) y = fma(-sm.L[k2 * kHW + lane], xk, y);
+                        }
+                        xs = y;
+                        flops += (2.0 / 3.0) * ma * ma * ma + 4.0 * ma * ma + 2.0 * m * ma;
+                    }
+                    const double xg = warp_bcast(xs, pos & 31);
+                    x = inA ? xg : 0.0;
+                    double mu = 0.0;
+#pragma unroll 1
+                    for (int q = 0; q < m; ++q) {
+                        const double xq = warp_bcast(x, q);
+                        if (row && xq != 0.0) mu = fma(sm.H[lane * kHW + q], xq, mu);
+                    }
+                    mu -= b;                                           // excludes the shift term: x_i = 0 off A
+                    const bool bad = row && (inA ? (x <= 0.0) : (mu < 0.0));
+                    if (!__any_sync(full, bad)) { pdas_ok = true; break; }
+                    if (bad) inA = !inA;
+                }
+                if (!pdas_ok) { bail = true; reason = 3; break; }
+
+                // ---- line search of phi on the segment lam -> x
+                const double dir = x - lam;
+                double gt[NJ];
+                double alpha = 1.0, phin = phi, lt = lam;
+                bool stepped = false;
+#pragma unroll 1
+                for (; alpha >= kArcMinW; alpha *= 0.5) {
+                    lt = row ? fmax(fma(alpha, dir, lam), 0.0) : 0.0;
+                    {   // phi(lt), gt = [z - R lt]_+
+                        double pi[NJ];
+#pragma unroll
+                        for (int k = 0; k < NJ; ++k) pi[k] = 0.0;
+#pragma unroll 1
+                        for (int a = 0; a < m; ++a) {
+                            const double la = warp_bcast(lt, a);
+                            const double* rr = rowp(a);
+                            if (la != 0.0) {
+#pragma unroll
+                                for (int k = 0; k < NJ; ++k) {
+                                    const int j = lane + 32 * k;
+                                    if (j < n) pi[k] = fma(rr[j], la, pi[k]);
+                                }
+                            }
+                        }
+                        double acc = 0.0;
+#pragma unroll
+                        for (int k = 0; k < NJ; ++k) {
+                            const int j = lane + 32 * k;
+                            gt[k] = j < n ? fmax(zj[k] - pi[k], 0.0) : 0.0;
+                            acc = fma(gt[k], gt[k], acc);
+                        }
+                        phin = 0.5 * warp_sum(acc) + u * warp_sum(row ? lt : 0.0);
+                    }
+                    flops += 2.0 * m * n;
+                    const double slope = warp_sum(row ? grad * (lt - lam) : 0.0);
+                    if (phin <= phi + 1e-4 * slope + 1e-14 * fabs(phi)) { stepped = true; break; }
+                }
+                if (!stepped) { bail = true; reason = 4; break; }
+                lam = lt;
+                phi = phin;
+                changed = true;
+#pragma unroll
+                for (int k = 0; k < NJ; ++k) gj[k] = gt[k];
+            }
+        }
+        its_total += its;
+        WPHASE(2);
+        if (bail || !ok) { exit_kind = 2; if (!reason) reason = 5; break; }
+
+        // ---- verification of the rows outside W for the new g (see the header): rows whose
+        // bound fails are re-evaluated at the top of the next pass
+        double dp = 0.0;
+#pragma unroll
+        for (int k = 0; k < NJ; ++k) dp += fmax(gj[k] - g0[k], 0.0);
+        dp = warp_sum(dp) * (1.0 + 1e-9);
+        int ncand = 0;
+        {
+            const double* rmax = P.rmax + fd.off;
+#pragma unroll
+            for (int k = 0; k < NJ; ++k) {
+                const int j = lane + 32 * k;
+                if (j < n && !((inw >> k) & 1u)) {
+                    const double bnd = dp > 0.0 ? fma(rmax[j], dp, vub[k]) : vub[k];
+                    if (bnd - u > tol) { candk |= 1u << k; ++ncand; }
+                    else vub[k] = bnd;
+                }
+            }
+            ncand = __reduce_add_sync(full, ncand);
+        }
+#pragma unroll
+        for (int k = 0; k < NJ; ++k) g0[k] = gj[k];
+        flops += 2.0 * n * min(ncand, kRecheckMaxW);
+        if (ncand == 0) break;                         // every row proven feasible: KKT point
+        if (ncand > kRecheckMaxW) { exit_kind = 1; break; }   // too many rows to settle here
+    }
+    WPHASE(3);
+
+    if (exit_kind == 2) {                      // nothing was written: the next class redoes the column
+        if (lane == 0) { P.cls[c] = 1; P.inner_ok[c] = 2; }
+        ++st.handed;
+        trace_out(2 + 16 * reason);
+        return;
+    }
+    // ---- persist: finished column, or (exit_kind 1) an iterate for the next tensor-core
+    // screening pass to check
+    if (changed || m != m_old) {
+        if (lane < m_old) lam_g[wi] = 0.0;
+        __syncwarp();
+        if (lane < m) { lam_g[idx] = lam; widx[lane] = idx; }
+        if (changed) {
+            __nv_bfloat16* gbf = P.gbf_t ? reinterpret_cast<__nv_bfloat16*>(P.gbf_t) + col : nullptr;
+#pragma unroll
+            for (int k = 0; k < NJ; ++k) {
+                const int j = lane + 32 * k;
+                if (j < n) {
+                    g[j] = gj[k];
+                    if (gbf) gbf[j] = __float2bfloat16_rn((float)gj[k]);
+                }
+            }
+        }
+    }
+    if (lane == 0) {
+        P.wcount[c] = m;
+        P.inner_ok[c] = 1;
+        if (exit_kind == 0) P.status[c] = 1;
+    }
+    if (exit_kind == 1) ++st.deferred;
+    trace_out(exit_kind);
+    st.its += (unsigned long long)its_total;
+    st.flops += flops;
+    st.max_ws = max(st.max_ws, m);
+#undef WPHASE
+}
 
 }  // namespace
 
@@ -70,7 +667,7 @@ __global__ void __launch_bounds__(256) qp_init_kernel(QpParams P, int max_warp_n
     }
     m = min(m, kWMax);
     __syncwarp();
-    int cl = (n <= max_warp_n) ? 0 : 1;
+    int cl = (n <= max_warp_n && m <= P.warp_m_max) ? 0 : 1;
     while (cl < kQpClasses - 1 && m > qp_class_cap(cl)) ++cl;
 
     // g = [z - R_W lam]_+
@@ -91,6 +688,7 @@ __global__ void __launch_bounds__(256) qp_init_kernel(QpParams P, int max_warp_n
         P.cls[c] = cl;
         P.status[c] = 0;
         P.inner_ok[c] = 0;
+        if (P.cand) P.cand[c] = 0;
     }
 }
 
@@ -102,402 +700,65 @@ cudaError_t launch_qp_init(const QpParams& P, int max_warp_n, cudaStream_t strea
 
 // ------------------------------------------------------------------------------------------
 template <int NJ>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, 20) utility_qp_warp_kernel(QpParams P) {
-    __shared__ WarpSmem smem_all[kWarpsPerCta];
+__global__ void __launch_bounds__(32 * kWarpsPerCta, kCtasPerSm) utility_qp_warp_kernel(QpParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    WarpSmem& sm = smem_all[wib];
-    const int slot = blockIdx.x * kWarpsPerCta + wib;
-    if (slot >= P.order_count[0]) return;
-    const int c = P.order[slot];
-    if (P.status[c] != 0 || P.cls[c] != 0) return;
-    const int f = c / P.T, t = c % P.T;
-    const FeederDev fd = P.feeders[f];
-    const int n = fd.n, ld = fd.np;
-    const double* R = P.Rpool + fd.roff;
-    const size_t col = (size_t)t * P.Hp + fd.off;
-    const double* z = P.z_t + col;
-    double* lam_g = P.lam_t + col;
-    double* g = P.g_t + col;
-    double* v = P.v_t + col;
-    const double u = P.u, tol = P.tol;
-    int* widx = P.widx + (size_t)c * kWMax;
-    const unsigned full = 0xffffffffu;
-
-    long long tr_start = 0;
-    if (P.trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_start));
-    const long long tr_clk0 = clock64();
-    const int m_old = P.wcount[c];
-    const double thr = (1.0 - kScreenMargin) * u;
-    // ---- fast exit: no multipliers and every screened voltage below the safe threshold ->
-    // g = [z]_+ from qp_init_kernel is already the projection (most columns, most rounds)
-    if (m_old == 0) {
-        bool any_cand = false;
+    WarpSmem& sm = reinterpret_cast<WarpSmem*>(smem_raw)[wib];
+    // four bucket lists (|W| >= 3, 2, 1, 0) per zone-size group form one queue, hardest columns first
+    constexpr int kList0 = kQpClasses + (NJ == 4 ? 0 : kQpBuckets);
+    int cnt[kQpBuckets], total = 0;
 #pragma unroll
-        for (int k = 0; k < NJ; ++k) {
-            const int j = lane + 32 * k;
-            if (j < n) any_cand |= P.v32_t ? ((double)(P.v32_t + col)[j] > thr) : (v[j] - u > tol);
-        }
-        if (!__any_sync(full, any_cand)) {
-            if (lane == 0) { P.status[c] = 1; P.inner_ok[c] = 1; atomicAdd(P.n_cls + 0, 1); }
-            return;
-        }
+    for (int b = 0; b < kQpBuckets; ++b) { cnt[b] = P.order_count[kList0 + b]; total += cnt[b]; }
+    WarpStats st;
+    for (;;) {
+        int slot = 0;
+        if (lane == 0) slot = atomicAdd(P.queue + kList0, 1);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        if (slot >= total) break;
+        int b = 0;
+#pragma unroll
+        for (int bb = 0; bb < kQpBuckets - 1; ++bb)
+            if (b == bb && slot >= cnt[bb]) { slot -= cnt[bb]; ++b; }
+        const int c = P.order[(size_t)(kList0 + b) * P.ncols + slot];
+        solve_column<NJ>(P, c, sm, st);
+        __syncwarp();
     }
-
-    // ---- this lane's homes
-    double zj[NJ], gj[NJ], vj[NJ];
-    bool haslam[NJ];
-#pragma unroll
-    for (int k = 0; k < NJ; ++k) {
-        const int j = lane + 32 * k;
-        zj[k] = j < n ? z[j] : 0.0;
-        gj[k] = j < n ? g[j] : 0.0;
-        haslam[k] = m_old > 0 && j < n && lam_g[j] > 0.0;
-    }
-    // ---- voltages: screened (BF16) values, exact FP64 recheck of the candidates
-    if (P.v32_t) {
-        const float* v32 = P.v32_t + col;
-#pragma unroll
-        for (int k = 0; k < NJ; ++k) {
-            const int j = lane + 32 * k;
-            const double a = j < n ? (double)v32[j] : 0.0;
-            vj[k] = a;
-            unsigned cand = __ballot_sync(full, j < n && a > thr && !haslam[k]);
-            while (cand) {
-                const int src = __ffs(cand) - 1;
-                cand &= cand - 1;
-                const double* row = R + (size_t)(src + 32 * k) * ld;
-                double acc = 0.0;
-#pragma unroll
-                for (int kk = 0; kk < NJ; ++kk) {
-                    const int jj = lane + 32 * kk;
-                    if (jj < n) acc = fma(row[jj], gj[kk], acc);
-                }
-                acc = warp_sum(acc);
-                if (lane == src) vj[k] = acc;
-            }
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < NJ; ++k) { const int j = lane + 32 * k; vj[k] = j < n ? v[j] : 0.0; }
-    }
-
-    // ---- working set: keep rows with a positive multiplier (order preserved), lanes = rows
-    int idx = 0;
-    double lam = 0.0;
-    int m = 0;
-    {
-        const int i = lane < m_old ? widx[lane] : 0;
-        const double l = lane < m_old ? lam_g[i] : 0.0;
-        const unsigned keep = __ballot_sync(full, lane < m_old && l > 0.0);
-        m = __popc(keep);
-        const int src = __fns(keep, 0, lane + 1);          // lane a takes the a-th kept row
-        const int si = __shfl_sync(full, i, src & 31);
-        const double sl = __shfl_sync(full, l, src & 31);
-        if (lane < m) { idx = si; lam = sl; }
-    }
-    // ---- violated rows outside W, most violated first (ties: lowest row)
-    double viol[NJ];
-#pragma unroll
-    for (int k = 0; k < NJ; ++k) {
-        const int j = lane + 32 * k;
-        viol[k] = (j < n && !haslam[k] && vj[k] - u > tol) ? vj[k] - u : -1.0;
-    }
-    int added = 0;
-    const int room = min(kAddMaxW, kWW - m);
-    bool left = false;
-    for (int r = 0; r <= room; ++r) {
-        double best = -1.0;
-        int bj = 0x7fffffff;
-#pragma unroll
-        for (int k = 0; k < NJ; ++k)
-            if (viol[k] > best) { best = viol[k]; bj = lane + 32 * k; }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ob = __shfl_xor_sync(full, best, o);
-            const int oj = __shfl_xor_sync(full, bj, o);
-            if (ob > best || (ob == best && oj < bj)) { best = ob; bj = oj; }
-        }
-        if (best < 0.0) break;
-        if (r == room) { left = true; break; }
-        if (lane == m + added) { idx = bj; lam = 0.0; }
-#pragma unroll
-        for (int k = 0; k < NJ; ++k)
-            if (bj == lane + 32 * k) viol[k] = -1.0;
-        ++added;
-    }
-    if (added == 0 && !left && P.inner_ok[c]) {
-        if (lane == 0) P.status[c] = 1;
-        return;
-    }
-    auto hand_over = [&]() {
-        if (lane == 0) { P.cls[c] = 1; atomicAdd(P.n_running, 1); atomicAdd(P.n_cls + 1, 1); }
-    };
-    if (left && m + added == kWW) { hand_over(); return; }
-    const bool clean = (added == 0 && !left);
-    m += added;
-    const bool row = lane < m;
-
-    // curvature scale of the Hessian shift
-    double scale = warp_sum(row ? P.rn2[fd.off + idx] : 0.0) / (double)max(m, 1);
-    const double shift = kHessShiftW * scale + 1e-300;
-
-    // ---- evaluation of phi at multipliers (lane a holds lam_a): fills out[] = [z - R lam]_+
-    auto eval = [&](double lam_a, double (&out)[NJ]) -> double {
-        double pi[NJ];
-#pragma unroll
-        for (int k = 0; k < NJ; ++k) pi[k] = 0.0;
-        for (int a = 0; a < m; ++a) {
-            const double la = warp_bcast(lam_a, a);
-            const int ia = __shfl_sync(full, idx, a);
-            if (la != 0.0) {
-                const double* rr = R + (size_t)ia * ld;
-#pragma unroll
-                for (int k = 0; k < NJ; ++k) {
-                    const int j = lane + 32 * k;
-                    if (j < n) pi[k] = fma(rr[j], la, pi[k]);
-                }
-            }
-        }
-        double acc = 0.0;
-#pragma unroll
-        for (int k = 0; k < NJ; ++k) {
-            const int j = lane + 32 * k;
-            out[k] = j < n ? fmax(zj[k] - pi[k], 0.0) : 0.0;
-            acc = fma(out[k], out[k], acc);
-        }
-        return 0.5 * warp_sum(acc) + u * warp_sum(row ? lam_a : 0.0);
-    };
-
-    double phi = eval(lam, gj);
-    double hrow[kWW];                 // row `lane` of H (columns <= lane are maintained)
-#pragma unroll
-    for (int q = 0; q < kWW; ++q) hrow[q] = 0.0;
-    unsigned fbits = 0;               // bit k: home lane+32k was in F when H was last updated
-    bool have_H = false;
-    int ok = 0, its = 0;
-    bool bail = false;
-    double flops = 2.0 * m * n;
-
-    for (; its < P.inner_max; ++its) {
-        // gradient on W
-        double grad = 0.0;
-        for (int a = 0; a < m; ++a) {
-            const int ia = __shfl_sync(full, idx, a);
-            const double* rr = R + (size_t)ia * ld;
-            double acc = 0.0;
-#pragma unroll
-            for (int k = 0; k < NJ; ++k) {
-                const int j = lane + 32 * k;
-                if (j < n) acc = fma(rr[j], gj[k], acc);
-            }
-            acc = warp_sum(acc);
-            if (lane == a) grad = u - acc;
-        }
-        flops += 2.0 * m * n;
-        const double kk = row ? fabs(lam > 0.0 ? grad : fmin(grad, 0.0)) : 0.0;
-        const double kkt = warp_max(kk);
-        if (kkt < tol) { ok = 1; break; }
-
-        // Hessian.  First piece: H[p][q] = sum over F of row p times row q, every row read
-        // coalesced (lanes = homes), two q at a time so the loads overlap.  Later pieces:
-        // signed rank-1 updates for the homes whose membership of F changed.
-        {
-            int nupd = 0;
-            if (!have_H) {
-                for (int p = 0; p < m; ++p) {
-                    const double* rp_ptr = R + (size_t)__shfl_sync(full, idx, p) * ld;
-                    double rp[NJ];
-#pragma unroll
-                    for (int k = 0; k < NJ; ++k) {
-                        const int j = lane + 32 * k;
-                        rp[k] = (j < n && gj[k] > 0.0) ? rp_ptr[j] : 0.0;
-                    }
-                    for (int q = 0; q <= p; q += 2) {
-                        const double* r0 = R + (size_t)__shfl_sync(full, idx, q) * ld;
-                        const double* r1 = R + (size_t)__shfl_sync(full, idx, min(q + 1, p)) * ld;
-                        double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-                        for (int k = 0; k < NJ; ++k) {
-                            const int j = lane + 32 * k;
-                            if (j < n) { a0 = fma(rp[k], r0[j], a0); a1 = fma(rp[k], r1[j], a1); }
-                        }
-                        a0 = warp_sum(a0);
-                        a1 = warp_sum(a1);
-                        if (lane == p) {
-#pragma unroll
-                            for (int qq = 0; qq < kWW; ++qq) {
-                                if (qq == q) hrow[qq] = a0;
-                                if (qq == q + 1 && q + 1 <= p) hrow[qq] = a1;
-                            }
-                        }
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < NJ; ++k) { if (gj[k] > 0.0) { fbits |= 1u << k; ++nupd; } else fbits &= ~(1u << k); }
-                nupd = __reduce_add_sync(full, nupd);
-            } else {
-#pragma unroll
-                for (int k = 0; k < NJ; ++k) {
-                    const bool now = gj[k] > 0.0;
-                    const bool was = (fbits >> k) & 1u;
-                    unsigned chg = __ballot_sync(full, now != was);
-                    const unsigned nowb = __ballot_sync(full, now);
-                    while (chg) {
-                        const int src = __ffs(chg) - 1;
-                        chg &= chg - 1;
-                        const int j = src + 32 * k;
-                        const double sgn = ((nowb >> src) & 1u) ? 1.0 : -1.0;
-                        const double ra = row ? R[(size_t)idx * ld + j] : 0.0;
-#pragma unroll
-                        for (int q = 0; q < kWW; ++q) {
-                            const double rq = warp_bcast(ra, q);
-                            if (q <= lane) hrow[q] = fma(sgn * ra, rq, hrow[q]);
-                        }
-                        ++nupd;
-                    }
-                    fbits = now ? (fbits | (1u << k)) : (fbits & ~(1u << k));
-                }
-            }
-            have_H = true;
-            flops += (double)m * (m + 1) * nupd;
-            __syncwarp();
-#pragma unroll
-            for (int q = 0; q < kWW; ++q)
-                if (row && q <= lane) { sm.H[lane * kHW + q] = hrow[q]; sm.H[q * kHW + lane] = hrow[q]; }
-            __syncwarp();
-        }
-
-        // ---- exact minimiser of the piece over lam_W >= 0: primal-dual active set, lanes = rows
-        double b = 0.0;
-        for (int q = 0; q < m; ++q) {
-            const double lq = warp_bcast(lam, q);
-            if (row && lq != 0.0) b = fma(sm.H[lane * kHW + q], lq, b);
-        }
-        b += shift * lam - grad;
-        bool inA = row && (lam > 0.0 || grad < 0.0);
-        double x = 0.0;
-        bool pdas_ok = false;
-        for (int guess = 0; guess < kPdasMaxW; ++guess) {
-            const unsigned Am = __ballot_sync(full, inA);
-            const int ma = __popc(Am);
-            const int pos = __popc(Am & ((1u << lane) - 1));
-            double xs = 0.0;
-            if (ma > 0) {
-                const int o = (lane < ma) ? (int)__fns(Am, 0, lane + 1) : 0;     // original row of compact row `lane`
-                // gather H_AA (+ shift) into L, lane = compact row
-                for (int cidx = 0; cidx < ma; ++cidx) {
-                    const int oc = __shfl_sync(full, o, cidx);
-                    if (lane < ma && cidx <= lane) sm.L[lane * kHW + cidx] = sm.H[o * kHW + oc] + (cidx == lane ? shift : 0.0);
-                }
-                __syncwarp();
-                for (int k2 = 0; k2 < ma; ++k2) {            // Cholesky, lanes own rows
-                    const double dkk = sqrt(fmax(sm.L[k2 * kHW + k2], 1e-300));
-                    __syncwarp();
-                    if (lane == k2) sm.L[k2 * kHW + k2] = dkk;
-                    double lik = 0.0;
-                    if (lane > k2 && lane < ma) { lik = sm.L[lane * kHW + k2] / dkk; sm.L[lane * kHW + k2] = lik; }
-                    __syncwarp();
-                    if (lane > k2 && lane < ma)
-                        for (int j2 = k2 + 1; j2 <= lane; ++j2)
-                            sm.L[lane * kHW + j2] = fma(-lik, sm.L[j2 * kHW + k2], sm.L[lane * kHW + j2]);
-                    __syncwarp();
-                }
-                double y = warp_bcast(b, o);                   // rhs of compact row `lane`
-                if (lane >= ma) y = 0.0;
-                for (int k2 = 0; k2 < ma; ++k2) {
-                    const double yk = warp_bcast(y, k2) / sm.L[k2 * kHW + k2];
-                    if (lane == k2) y = yk;
-                    if (lane > k2 && lane < ma) y = fma(-sm.L[lane * kHW + k2], yk, y);
-                }
-                for (int k2 = ma - 1; k2 >= 0; --k2) {
-                    const double xk = warp_bcast(y, k2) / sm.L[k2 * kHW + k2];
-                    if (lane == k2) y = xk;
-                    if (lane < k2) y = fma(-sm.L[k2 * kHW + lane], xk, y);
-                }
-                xs = y;
-                flops += (2.0 / 3.0) * ma * ma * ma + 4.0 * ma * ma + 2.0 * m * ma;
-            }
-            const double xg = warp_bcast(xs, pos & 31);
-            x = inA ? xg : 0.0;
-            double mu = 0.0;
-            for (int q = 0; q < m; ++q) {
-                const double xq = warp_bcast(x, q);
-                if (row && xq != 0.0) mu = fma(sm.H[lane * kHW + q], xq, mu);
-            }
-            mu -= b;                                           // excludes the shift term: x_i = 0 off A
-            const bool bad = row && (inA ? (x <= 0.0) : (mu < 0.0));
-            if (!__any_sync(full, bad)) { pdas_ok = true; break; }
-            if (bad) inA = !inA;
-        }
-        if (!pdas_ok) { bail = true; break; }
-
-        // ---- line search of phi on the segment lam -> x
-        const double dir = x - lam;
-        const double slope0 = warp_sum(row ? grad * dir : 0.0);
-        double gt[NJ];
-        double alpha = 1.0, phin = phi, lt = lam;
-        bool stepped = false;
-        for (; alpha >= kArcMinW; alpha *= 0.5) {
-            lt = row ? fmax(fma(alpha, dir, lam), 0.0) : 0.0;
-            phin = eval(lt, gt);
-            flops += 2.0 * m * n;
-            const double slope = warp_sum(row ? grad * (lt - lam) : 0.0);
-            if (phin <= phi + 1e-4 * slope + 1e-14 * fabs(phi)) { stepped = true; break; }
-        }
-        (void)slope0;
-        if (!stepped) { bail = true; break; }
-        lam = lt;
-        phi = phin;
-#pragma unroll
-        for (int k = 0; k < NJ; ++k) gj[k] = gt[k];
-    }
-    if (bail) { hand_over(); return; }       // nothing was written: the CTA kernel redoes the column
-
-    // ---- persist
-    if (lane < m_old) lam_g[widx[lane]] = 0.0;
-    __syncwarp();
-    if (row) { lam_g[idx] = lam; widx[lane] = idx; }
-    if (its > 0) {
-        __nv_bfloat16* gbf = P.gbf_t ? reinterpret_cast<__nv_bfloat16*>(P.gbf_t) + col : nullptr;
-#pragma unroll
-        for (int k = 0; k < NJ; ++k) {
-            const int j = lane + 32 * k;
-            if (j < n) {
-                g[j] = gj[k];
-                if (gbf) gbf[j] = __float2bfloat16_rn((float)gj[k]);
-            }
-        }
-    }
-    const bool done = clean && ok && its == 0;
     if (lane == 0) {
-        P.wcount[c] = m;
-        P.inner_ok[c] = ok;
-        P.status[c] = done ? 1 : 0;
-        if (!done) atomicAdd(P.n_running, 1);
-        atomicAdd(P.n_cls + 0, 1);
-        atomicAdd(P.newton_its, (unsigned long long)its);
-        atomicMax(P.max_ws, m);
-        atomicAdd(P.flops, (unsigned long long)flops);
-        if (P.trace) {
-            long long tr_end; unsigned smid;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_end));
-            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            long long* rec = P.trace + 12 * (size_t)c;
-            rec[0] = tr_start; rec[1] = tr_end; rec[2] = smid; rec[3] = ((long long)m << 20) | its;
-            rec[11] = clock64() - tr_clk0;
-        }
+        if (st.its) atomicAdd(P.newton_its, st.its);
+        if (st.flops > 0.0) atomicAdd(P.flops, (unsigned long long)st.flops);
+        if (st.max_ws) atomicMax(P.max_ws, st.max_ws);
+        if (st.handed) { atomicAdd(P.n_running, st.handed); atomicAdd(P.n_cls + 1, st.handed); }
+        if (st.deferred) { atomicAdd(P.n_running, st.deferred); atomicAdd(P.n_cls + 0, st.deferred); }
     }
 }
 
-int qp_warp_max_n() { return 32 * 16; }
+int qp_warp_max_n() { return kWarpMaxN; }
 
-cudaError_t launch_utility_qp_warp(const QpParams& P, int n_cols_bound, int max_n, cudaStream_t stream) {
-    if (n_cols_bound <= 0) return cudaSuccess;
-    const int grid = (n_cols_bound + kWarpsPerCta - 1) / kWarpsPerCta;
-    if (max_n <= 128) utility_qp_warp_kernel<4><<<grid, 32 * kWarpsPerCta, 0, stream>>>(P);
-    else if (max_n <= 256) utility_qp_warp_kernel<8><<<grid, 32 * kWarpsPerCta, 0, stream>>>(P);
-    else utility_qp_warp_kernel<16><<<grid, 32 * kWarpsPerCta, 0, stream>>>(P);
+// Zones up to 128 residences run the NJ = 4 instantiation, zones up to 256 the NJ = 8 one (own
+// work lists); each fits the instruction cache.  ctas_per_sm sizes the persistent grid so that
+// the two can be co-resident on different streams.
+cudaError_t launch_utility_qp_warp(const QpParams& P, int nj, int ctas_per_sm, cudaStream_t stream) {
+    static int n_sm = 0;
+    static bool attr_set = false;
+    const int smem = (int)sizeof(WarpSmem) * kWarpsPerCta;
+    if (!attr_set) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(utility_qp_warp_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(utility_qp_warp_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess && !getenv("REVS_NO_CARVEOUT")) e = cudaFuncSetAttribute(utility_qp_warp_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e == cudaSuccess && !getenv("REVS_NO_CARVEOUT")) e = cudaFuncSetAttribute(utility_qp_warp_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > kCtasPerSm ? kCtasPerSm : ctas_per_sm);
+    if (nj == 8) utility_qp_warp_kernel<8><<<n_sm * ctas_per_sm, 32 * kWarpsPerCta, smem, stream>>>(P);
+    else utility_qp_warp_kernel<4><<<n_sm * ctas_per_sm, 32 * kWarpsPerCta, smem, stream>>>(P);
     return cudaGetLastError();
 }
+
+int qp_warp_ctas_per_sm() { return kCtasPerSm; }
+int qp_warp_m_max_default() { return kWW - kHysteresisW; }
 
 }  // namespace revs
