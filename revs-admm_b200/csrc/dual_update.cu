@@ -15,6 +15,8 @@
 // read and written in full 256-byte runs.  Per-home norms use warp shuffles; the two
 // global sums are one atomicAdd per CTA, and the last CTA to finish turns them into the
 // residuals and the converged flag.
+#include <cuda_bf16.h>
+
 #include "kernels.cuh"
 
 namespace revs {
@@ -64,9 +66,19 @@ __global__ void __launch_bounds__(256, 4) dual_update_kernel(DualParams P) {
     if (lane == 0) { s_part[0][warp] = blk_p; s_part[1][warp] = blk_d; }
     __syncthreads();
 
+    __nv_bfloat16* gbf = reinterpret_cast<__nv_bfloat16*>(P.gbf_next);
     for (int t = warp; t < P.T; t += 8) {
         int h = h0 + lane;
-        if (h < P.Hp) P.z_t[(size_t)t * P.Hp + h] = tile[lane * ldt + t];
+        if (h < P.Hp) {
+            const double zv = tile[lane * ldt + t];
+            const size_t o = (size_t)t * P.Hp + h;
+            P.z_t[o] = zv;
+            if (P.g_next) {                    // start of the next utility solve: g = [z]_+ wherever no multiplier is stored
+                const double gv = fmax(zv, 0.0);
+                P.g_next[o] = gv;
+                if (gbf) gbf[o] = __float2bfloat16_rn((float)gv);
+            }
+        }
     }
 
     if (threadIdx.x == 0) {

@@ -47,6 +47,8 @@ struct DualParams {
     double* gamma;             // [Hp][T]  in: G[k]  out: G[k+1]
     double* p_est;             // [Hp][T]  out: P_est[k+1], home-major
     double* z_t;               // [T][Hp]  out: next projection target
+    double* g_next;            // optional [T][Hp] (may alias g_t): [z]_+, the next utility iterate of columns without multipliers
+    void* gbf_next;            // optional [T][Hp] __nv_bfloat16 copy of g_next
     double* diff_k;            // [Hp]     out
     ResidualOut* res;
     int Hp, T;

@@ -252,7 +252,7 @@ int check_ready(const revs_solver* s) {
 }
 
 // One utility solve: project z_t onto the voltage polytope of every (feeder,hour) column.
-int utility_solve(revs_solver* s) {
+int utility_solve(revs_solver* s, bool in_loop = false) {
     QpParams Q;
     Q.feeders = s->d_feeders;
     Q.Rpool = s->d_Rpool;
@@ -304,7 +304,7 @@ int utility_solve(revs_solver* s) {
 
     // Start of the solve: working sets from the stored multipliers, class by their size,
     // g = [z - R lam]_+ for the new target -- one warp per column.
-    Q.init = 0;
+    Q.init = in_loop ? 2 : 0;                      // 2: dual_update_kernel prepared g, multipliers sit on the stored rows
     int max_n = 0, warp_n = 0, small_n = 0;        // largest zone / largest zone the warp kernel takes / zones <= 128
     for (int f = 0; f < s->nf; ++f) {
         max_n = std::max(max_n, s->feeders[f].n);
@@ -586,11 +586,15 @@ int revs_create(revs_solver** out, int device, int n_feeders, const int64_t* fee
             return fail(REVS_ERR_CUDA, "%s failed: %s", #x, cudaGetErrorString(e_));               \
         }                                                                                          \
     } while (0)
-    TRY(cudaStreamCreateWithFlags(&s->sU, cudaStreamNonBlocking));
-    TRY(cudaStreamCreateWithFlags(&s->sH, cudaStreamNonBlocking));
+    // the operator side is the critical path of an iteration; the home solve only has to be done
+    // by the dual update, so its CTAs yield the SMs to the utility kernels
+    int prio_lo = 0, prio_hi = 0;
+    TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    TRY(cudaStreamCreateWithPriority(&s->sU, cudaStreamNonBlocking, prio_hi));
+    TRY(cudaStreamCreateWithPriority(&s->sH, cudaStreamNonBlocking, prio_lo));
     TRY(cudaEventCreateWithFlags(&s->evV, cudaEventDisableTiming));
     for (int cl = 0; cl < kQpClasses; ++cl) {
-        TRY(cudaStreamCreateWithFlags(&s->sQ[cl], cudaStreamNonBlocking));
+        TRY(cudaStreamCreateWithPriority(&s->sQ[cl], cudaStreamNonBlocking, prio_hi));
         TRY(cudaEventCreateWithFlags(&s->evQ[cl], cudaEventDisableTiming));
     }
     TRY(cudaEventCreateWithFlags(&s->evHomeDone, cudaEventDisableTiming));
@@ -875,6 +879,7 @@ int revs_admm_begin(revs_solver* s, double kappa, int iter_max, double vset, dou
     for (double* p : zero) CU(cudaMemsetAsync(p, 0, HT, s->sU));
     CU(cudaMemsetAsync(s->d_cnt, 0, sizeof(Counters), s->sU));
     CU(cudaMemsetAsync(s->d_wcount, 0, sizeof(int) * s->ncols, s->sU));
+    CU(cudaMemsetAsync(s->d_gbf, 0, HT / sizeof(double) * 2, s->sU));
     if (s->diff_cap < iter_max) {
         if (s->d_diff) CU(cudaFree(s->d_diff));
         s->d_diff = nullptr;
@@ -902,7 +907,7 @@ int admm_step_impl(revs_solver* s, double sums[3], bool sync_now) {
     s->stats.kernel_launches++;
 
     // operator side
-    int rc = utility_solve(s);
+    int rc = utility_solve(s, true);
     if (rc) { s->running = false; cudaDeviceSynchronize(); return rc; }
 
     // fused dual update / residuals / next target
@@ -915,6 +920,8 @@ int admm_step_impl(revs_solver* s, double sums[3], bool sync_now) {
     D.gamma = s->d_gamma;
     D.p_est = s->d_pest;
     D.z_t = s->d_zt;
+    D.g_next = s->d_gt;
+    D.gbf_next = s->screen ? s->d_gbf : nullptr;
     D.diff_k = s->d_diff + (size_t)s->k * s->Hp;
     D.res = &s->d_cnt->res;
     D.Hp = (int)s->Hp;

@@ -652,20 +652,44 @@ __global__ void __launch_bounds__(256) qp_init_kernel(QpParams P, int max_warp_n
     __nv_bfloat16* gbf = P.gbf_t ? reinterpret_cast<__nv_bfloat16*>(P.gbf_t) + col : nullptr;
     int* widx = P.widx + (size_t)c * kWMax;
 
-    // working set = rows with a positive multiplier, in row order (reproducible)
     int m = 0;
-    for (int j0 = 0; j0 < n; j0 += 32) {
-        const int j = j0 + lane;
-        const bool on = j < n && lam_g[j] > 0.0;
-        const unsigned bal = __ballot_sync(0xffffffffu, on);
-        if (on) {
-            const int pos = m + __popc(bal & ((1u << lane) - 1));
-            if (pos < kWMax) widx[pos] = j;
-            else lam_g[j] = 0.0;                 // cannot be carried; re-admitted if violated
+    if (P.init == 2) {
+        // inside the ADMM loop: the multipliers live on the stored working rows only, and
+        // dual_update_kernel has already written g = [z]_+ -- a column without a stored row is ready
+        const int wc = P.wcount[c];
+        if (wc == 0) {
+            if (lane == 0) {
+                P.cls[c] = n <= max_warp_n ? 0 : 1;
+                P.status[c] = 0;
+                P.inner_ok[c] = 0;
+                if (P.cand) P.cand[c] = 0;
+            }
+            return;
         }
-        m += __popc(bal);
+        for (int a0 = 0; a0 < wc; a0 += 32) {      // compact in place: rows with a positive multiplier, order kept
+            const int a = a0 + lane;
+            const int i = a < wc ? widx[a] : 0;
+            const bool on = a < wc && lam_g[i] > 0.0;
+            const unsigned bal = __ballot_sync(0xffffffffu, on);
+            __syncwarp();
+            if (on) widx[m + __popc(bal & ((1u << lane) - 1))] = i;
+            m += __popc(bal);
+        }
+    } else {
+        // working set = rows with a positive multiplier, in row order (reproducible)
+        for (int j0 = 0; j0 < n; j0 += 32) {
+            const int j = j0 + lane;
+            const bool on = j < n && lam_g[j] > 0.0;
+            const unsigned bal = __ballot_sync(0xffffffffu, on);
+            if (on) {
+                const int pos = m + __popc(bal & ((1u << lane) - 1));
+                if (pos < kWMax) widx[pos] = j;
+                else lam_g[j] = 0.0;                 // cannot be carried; re-admitted if violated
+            }
+            m += __popc(bal);
+        }
+        m = min(m, kWMax);
     }
-    m = min(m, kWMax);
     __syncwarp();
     int cl = (n <= max_warp_n && m <= P.warp_m_max) ? 0 : 1;
     while (cl < kQpClasses - 1 && m > qp_class_cap(cl)) ++cl;
