@@ -65,6 +65,9 @@ typedef struct revs_stats {
     float qp_ms;                  /* device time in the per-column QP kernels (both)    */
     float qp_big_ms;              /* ... of which the |W|>32 instantiation              */
     float total_ms;               /* device time of the whole solve                     */
+    float qp_warp_ms;             /* ... of qp_ms: warp-per-column kernels (zones <= 256) */
+    float qp_init_ms;             /* ... of qp_ms: start-of-solve kernel                 */
+    int64_t qp_columns;           /* (zone,hour) columns that entered a QP kernel, summed over rounds */
 } revs_stats;
 
 const char* revs_last_error(void);

@@ -73,9 +73,7 @@ __global__ void __launch_bounds__(256) home_solve_kernel(HomeParams P) {
 
     int in_window = 0;
 #pragma unroll
-    for (int j = 0; j < SLOTS; ++j) in_window += (d[j] < CUDART_INF) ? 1 : 0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) in_window += __shfl_xor_sync(0xffffffffu, in_window, o);
+    for (int j = 0; j < SLOTS; ++j) in_window += __popc(__ballot_sync(0xffffffffu, d[j] < CUDART_INF));
     if (nmin > nmax || nmin > in_window) {
         if (lane == 0) atomicExch(P.infeasible, 1);
     }
@@ -85,35 +83,62 @@ __global__ void __launch_bounds__(256) home_solve_kernel(HomeParams P) {
     for (int j = 0; j < SLOTS; ++j) on[j] = false;
     if (nmax <= kSelectRounds) {
         // few charging hours (the usual case): pull the cheapest remaining hour out of the
-        // warp nmax times.  Costs become order-preserving 64-bit integer keys, so the
-        // (cost, hour) lexicographic arg-min is three hardware warp reductions (REDUX)
-        // instead of a shuffle tree on doubles.
+        // warp nmax times.  Costs become order-preserving 64-bit integer keys and every lane
+        // keeps its own hours sorted (ties: earlier hour first), so a pick is two hardware warp
+        // reductions (REDUX) on the lanes' current heads plus a ballot; only if two lanes hold
+        // the same cost does a third reduction on the hour break the tie.
         unsigned long long key[SLOTS];
+        unsigned slots = 0;                       // nibble i: slot index of the i-th smallest key of this lane
 #pragma unroll
         for (int j = 0; j < SLOTS; ++j) {
             const unsigned long long b = (unsigned long long)__double_as_longlong(d[j] + 0.0);   // -0 -> +0
             key[j] = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+            slots |= (unsigned)j << (4 * j);
         }
-        const unsigned long long kInf = 0xFFF0000000000000ull;      // key of +inf
+#pragma unroll
+        for (int i = 1; i < SLOTS; ++i)            // insertion sort, stable (strict <)
+#pragma unroll
+            for (int jj = i; jj >= 1; --jj) {
+                const bool sw = key[jj] < key[jj - 1];
+                const unsigned long long lo_k = sw ? key[jj] : key[jj - 1], hi_k = sw ? key[jj - 1] : key[jj];
+                key[jj - 1] = lo_k;
+                key[jj] = hi_k;
+                if (sw) {
+                    const unsigned a = (slots >> (4 * jj)) & 15u, c = (slots >> (4 * (jj - 1))) & 15u;
+                    slots = (slots & ~((15u << (4 * jj)) | (15u << (4 * (jj - 1))))) | (c << (4 * jj)) | (a << (4 * (jj - 1)));
+                }
+            }
+        unsigned onmask = 0;
         for (int cnt = 0; cnt < nmax; ++cnt) {
-            unsigned long long best = ~0ull;
+            // the high word (sign, exponent, 20 mantissa bits) of the cheapest head almost always
+            // identifies the winner on its own; low word and hour are only consulted on ties
+            const unsigned long long head = key[0];
+            const unsigned hw = (unsigned)(head >> 32);
+            const unsigned hi = __reduce_min_sync(0xffffffffu, hw);
+            if (hi >= 0xFFF00000u) break;                             // window exhausted (+inf)
+            if (cnt >= nmin && hi >= 0x80000000u) break;              // optional hours only while cost < 0
+            unsigned tied = __ballot_sync(0xffffffffu, hw == hi);
+            int wl = __ffs(tied) - 1;
+            if (tied & (tied - 1)) {
+                const unsigned lo = __reduce_min_sync(0xffffffffu, hw == hi ? (unsigned)head : 0xffffffffu);
+                const bool mine = hw == hi && (unsigned)head == lo;
+                tied = __ballot_sync(0xffffffffu, mine);
+                wl = __ffs(tied) - 1;
+                if (tied & (tied - 1)) {                              // same cost in several lanes: earliest hour wins
+                    const unsigned myt = mine ? (unsigned)(lane + 32 * (int)(slots & 15u)) : 0x7fffffffu;
+                    wl = (int)(__reduce_min_sync(0xffffffffu, myt) & 31u);
+                }
+            }
+            if (lane == wl) {
+                onmask |= 1u << (slots & 15u);
+                slots >>= 4;
 #pragma unroll
-            for (int j = 0; j < SLOTS; ++j)
-                if (!on[j] && key[j] < best) best = key[j];
-            const unsigned hi = __reduce_min_sync(0xffffffffu, (unsigned)(best >> 32));
-            const unsigned lo = __reduce_min_sync(0xffffffffu, (unsigned)(best >> 32) == hi ? (unsigned)best : 0xffffffffu);
-            const unsigned long long win = ((unsigned long long)hi << 32) | lo;
-            if (win >= kInf) break;                                   // window exhausted
-            if (cnt >= nmin && win >= 0x8000000000000000ull) break;   // optional hours only while cost < 0
-            int myt = 0x7fffffff;
-#pragma unroll
-            for (int j = SLOTS - 1; j >= 0; --j)
-                if (!on[j] && key[j] == win) myt = lane + 32 * j;
-            const int bt = (int)__reduce_min_sync(0xffffffffu, (unsigned)myt);
-#pragma unroll
-            for (int j = 0; j < SLOTS; ++j)
-                if (bt == lane + 32 * j) on[j] = true;
+                for (int j = 0; j + 1 < SLOTS; ++j) key[j] = key[j + 1];
+                key[SLOTS - 1] = ~0ull;
+            }
         }
+#pragma unroll
+        for (int j = 0; j < SLOTS; ++j) on[j] = (onmask >> j) & 1u;
     } else {
         // rank[j] = #{hours s : d_s < d_t  or (d_s == d_t and s < t)}
         int rank[SLOTS];

@@ -80,6 +80,7 @@ struct QpParams {
     unsigned long long* newton_its;
     int* max_ws;
     unsigned long long* flops;   // algorithmic FP64 flops executed by the QP kernels
+    unsigned long long* cols;    // columns that entered a QP kernel
     int* n_failed;         // columns whose working set overflowed kWMax
     int* cls;              // [ncols] instantiation that owns the column (see qp_class_cap)
     int* n_cls;            // [kQpClasses] running columns per class after this round

@@ -65,6 +65,7 @@ struct Counters {
     int max_ws;
     unsigned long long newton_its;
     unsigned long long qp_flops;
+    unsigned long long qp_cols;
     unsigned long long dbg[4 + 5 * kQpClasses];
     ResidualOut res;
 };
@@ -108,6 +109,7 @@ struct revs_solver {
     ContractTile* d_stiles = nullptr;
     int n_stiles = 0;
     bool use_warp_kernel = true;               // class 0: one warp per small column (utility_qp_warp.cu)
+    bool overlap_home = true;                  // home solve on its own (low priority) stream beside the utility kernels
     bool screen = true;                        // BF16 screening + exact recheck instead of the FP64 contraction in the loop
     int screen_impl = 0;                       // 0: mma.sync kernel, 1: tcgen05/TMEM/TMA kernel
     void *d_maps_a = nullptr, *d_map_b = nullptr;   // CUtensorMap per feeder block / for the bf16 schedule
@@ -202,7 +204,9 @@ void spans_collect(revs_solver* s) {   // after the streams are synchronised
             case 5: s->stats.gemm_ms += ms; s->stats.gemm_full_ms += ms; break;
             case 1: s->stats.home_ms += ms; break;
             case 2: s->stats.dual_ms += ms; break;
-            case 3: case 6: case 7: case 8: case 9: s->stats.qp_ms += ms; break;
+            case 3: case 9: s->stats.qp_ms += ms; break;
+            case 6: s->stats.qp_ms += ms; s->stats.qp_init_ms += ms; break;
+            case 7: case 8: s->stats.qp_ms += ms; s->stats.qp_warp_ms += ms; break;
             case 4: s->stats.qp_ms += ms; s->stats.qp_big_ms += ms; break;
         }
     }
@@ -282,6 +286,7 @@ int utility_solve(revs_solver* s, bool in_loop = false) {
     Q.newton_its = &s->d_cnt->newton_its;
     Q.max_ws = &s->d_cnt->max_ws;
     Q.flops = &s->d_cnt->qp_flops;
+    Q.cols = &s->d_cnt->qp_cols;
     Q.n_failed = &s->d_cnt->n_failed;
     Q.cls = s->d_cls;
     Q.n_cls = s->d_cnt->n_cls;
@@ -898,12 +903,13 @@ int admm_step_impl(revs_solver* s, double sums[3], bool sync_now) {
     CU(cudaSetDevice(s->device));
 
     // consumer side on its own stream: uses P_est[k], P_sch[k], Gamma[k] (lpsolver.py:275)
-    CU(cudaStreamWaitEvent(s->sH, s->evDualDone, 0));
+    cudaStream_t sHome = s->overlap_home ? s->sH : s->sU;   // overlap_home = 0: in line, for an undisturbed kernel time
+    CU(cudaStreamWaitEvent(sHome, s->evDualDone, 0));
     HomeParams hp = home_params(s, 0);
-    TimedSpan* sp = span_begin(s, 1, s->sH);
-    CU(launch_home_solve(hp, s->sH));
-    span_end(sp, s->sH);
-    CU(cudaEventRecord(s->evHomeDone, s->sH));
+    TimedSpan* sp = span_begin(s, 1, sHome);
+    CU(launch_home_solve(hp, sHome));
+    span_end(sp, sHome);
+    CU(cudaEventRecord(s->evHomeDone, sHome));
     s->stats.kernel_launches++;
 
     // operator side
@@ -951,6 +957,7 @@ int admm_step_impl(revs_solver* s, double sums[3], bool sync_now) {
     s->stats.dual_residual = s->h_cnt->res.dual;
     s->stats.qp_newton_iterations = (int64_t)s->h_cnt->newton_its;
     s->stats.qp_flops = (double)s->h_cnt->qp_flops;
+    s->stats.qp_columns = (int64_t)s->h_cnt->qp_cols;
     s->stats.max_working_set = s->h_cnt->max_ws;
     float ms = 0.f;
     cudaEventElapsedTime(&ms, s->evT0, s->evT1);
@@ -1301,6 +1308,7 @@ int revs_set_option(revs_solver* s, const char* name, double value) {
     if (!s || !name) return fail(REVS_ERR_ARG, "bad arguments");
     if (!strcmp(name, "screen")) { s->screen = value != 0.0; return REVS_OK; }
     if (!strcmp(name, "warp_kernel")) { s->use_warp_kernel = value != 0.0; return REVS_OK; }
+    if (!strcmp(name, "overlap_home")) { s->overlap_home = value != 0.0; return REVS_OK; }
     if (!strcmp(name, "screen_impl")) {
         if (value != 0.0 && !s->tc5_ready) return fail(REVS_ERR_ARG, "tcgen05 screening kernel unavailable (T > 96 or tensor-map encoding failed)");
         s->screen_impl = value != 0.0 ? 1 : 0;

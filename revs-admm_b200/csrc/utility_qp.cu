@@ -834,6 +834,7 @@ __device__ void qp_column(const QpParams& P, const int c, S& sm) {
     if (tid == 0) {
         if (!finished && !handed) { atomicAdd(P.n_running, 1); atomicAdd(P.n_cls + CLS, 1); }
         atomicAdd(P.newton_its, its_all);
+        atomicAdd(P.cols, 1ull);
         atomicMax(P.max_ws, m);
         atomicAdd(P.flops, (unsigned long long)flops);
         const unsigned long long its = its_all;

@@ -57,7 +57,7 @@ struct WarpSmem {
 struct WarpStats {
     unsigned long long its = 0;
     double flops = 0.0;
-    int handed = 0, deferred = 0, max_ws = 0;
+    int handed = 0, deferred = 0, max_ws = 0, cols = 0;
 };
 
 __device__ __forceinline__ double warp_bcast(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
@@ -745,12 +745,14 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, kCtasPerSm) utility_qp_warp
             if (b == bb && slot >= cnt[bb]) { slot -= cnt[bb]; ++b; }
         const int c = P.order[(size_t)(kList0 + b) * P.ncols + slot];
         solve_column<NJ>(P, c, sm, st);
+        ++st.cols;
         __syncwarp();
     }
     if (lane == 0) {
         if (st.its) atomicAdd(P.newton_its, st.its);
         if (st.flops > 0.0) atomicAdd(P.flops, (unsigned long long)st.flops);
         if (st.max_ws) atomicMax(P.max_ws, st.max_ws);
+        if (st.cols) atomicAdd(P.cols, (unsigned long long)st.cols);
         if (st.handed) { atomicAdd(P.n_running, st.handed); atomicAdd(P.n_cls + 1, st.handed); }
         if (st.deferred) { atomicAdd(P.n_running, st.deferred); atomicAdd(P.n_cls + 0, st.deferred); }
     }
