@@ -322,7 +322,9 @@ int utility_solve(revs_solver* s, bool in_loop = false) {
     span_end(sp, s->sU);
     s->stats.kernel_launches++;
     bool use[kQpClasses];
-    for (int cl = 0; cl < kQpClasses; ++cl) use[cl] = cl <= s->warm_cls || cl <= 1;
+    // first round: every class is launched -- which classes hold columns is decided on the device
+    // (qp_init_kernel), and a class whose list is empty costs a few microseconds
+    for (int cl = 0; cl < kQpClasses; ++cl) use[cl] = true;
     if (max_warp_n == 0 || warp_n == 0) use[0] = false;
     Q.init = 0;
     Q.order = s->d_order;

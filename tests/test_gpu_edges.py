@@ -152,3 +152,56 @@ def test_working_set_overflow_is_loud(gpu_lib):
         with pytest.raises(gpu_lib.RevsError) as e:
             s.solve_admm(iter_max=4, vset=1.03, vlow=0.95, vhigh=1.05)
         assert e.value.code == 4
+
+
+@pytest.mark.parametrize("sizes,vhigh", [([100, 200], 1.02), ([300], 1.02), ([600, 90], 1.05)])
+def test_zone_size_classes_match_oracle(gpu_lib, sizes, vhigh):
+    """Zones <= 128 / <= 256 (warp-per-column kernels, NJ = 4 / 8), <= 512 (CTA kernel with in-kernel
+    verification) and larger (CTA kernel + re-screening rounds) under limits tight enough to bind."""
+    T = 24
+    trees, hm, cost = _problem(sizes, T, seed=sum(sizes), r_secondary=1e-3)
+    kw = dict(kappa=5.0, iter_max=5, vset=1.0, vlow=0.95, vhigh=vhigh)
+    out = _gpu(gpu_lib, sizes, T, trees, hm, cost, kw)
+    ref = _oracle(trees, hm, cost, kw)
+    assert out["stats"]["max_working_set"] >= 10         # the limits do bind (tens of rows per column)
+    assert np.array_equal(out["P_ev"], ref["P_ev"])
+    assert np.abs(out["P_sch"] - ref["P_sch"]).max() <= 1e-4
+    assert np.abs(out["P_est"] - ref["P_est"]).max() <= 1e-4
+    assert np.abs(out["diff"] - ref["diff"]).max() <= 1e-7
+
+
+def test_many_binding_rows_hand_over(gpu_lib):
+    """Working sets that outgrow the warp kernel (16 rows) and the first CTA class (32 rows):
+    columns are handed from class to class and still land on the oracle's projection."""
+    sizes, T = [120, 96], 12
+    trees, hm, cost = _problem(sizes, T, seed=77, r_secondary=2e-3, adoption=1.0)
+    hm["start"][:] = 0
+    hm["end"][:] = T
+    kw = dict(kappa=5.0, iter_max=4, vset=1.0, vlow=0.95, vhigh=1.02)
+    out = _gpu(gpu_lib, sizes, T, trees, hm, cost, kw)
+    ref = _oracle(trees, hm, cost, kw)
+    assert out["stats"]["max_working_set"] > 16
+    assert np.array_equal(out["P_ev"], ref["P_ev"])
+    assert np.abs(out["P_est"] - ref["P_est"]).max() <= 1e-4
+    assert np.abs(out["P_sch"] - ref["P_sch"]).max() <= 1e-4
+
+
+def test_scheduling_options_do_not_change_results(gpu_lib):
+    """Home solve in line vs on its own stream, solve_admm (iterations enqueued back to back) vs
+    admm_begin/admm_step (host sync per iteration): bit-identical outputs."""
+    sizes, T = [140, 60, 33], 48
+    trees, hm, cost = _problem(sizes, T, seed=3)
+    kw = dict(kappa=5.0, iter_max=6, vset=1.0, vlow=0.95, vhigh=1.015)
+    base = _gpu(gpu_lib, sizes, T, trees, hm, cost, kw)
+    with gpu_lib.Solver(sizes, T) as s:
+        s.set_option("overlap_home", 0)
+        s.set_feeder_trees(trees)
+        s.set_homes(**hm)
+        s.set_tariff(cost)
+        s.admm_begin(**kw)
+        for _ in range(kw["iter_max"]):
+            s.admm_step()
+        out = s.results(kw["iter_max"])
+        out["P_est"], out["Gamma"] = s.estimate()
+    for k in ("P_sch", "P_ev", "SOC", "diff", "P_est", "Gamma"):
+        assert np.array_equal(base[k], out[k]), k
