@@ -86,6 +86,7 @@ struct QpParams {
     int* n_cls;            // [kQpClasses] running columns per class after this round
     const int* order;      // optional [kQpLists][ncols] work lists (order_columns_kernel)
     const int* order_count;   // [kQpLists + 1]
+    int4* order4;          // warp-kernel lists [kQpLists - kQpClasses][ncols]: {column, first home, n | ld << 16, R offset / 16}
     int sweep;             // 1: this launch only takes columns handed over during the current round
     int warp_m_max;        // warm working sets above this size start in class 1 (qp_init_kernel)
     int ncols;

@@ -132,6 +132,7 @@ struct revs_solver {
     double *d_zt = nullptr, *d_lamt = nullptr, *d_gt = nullptr, *d_vt = nullptr;
     int *d_wcount = nullptr, *d_widx = nullptr, *d_status = nullptr, *d_innerok = nullptr, *d_cls = nullptr;
     int *d_order = nullptr, *d_order_count = nullptr;
+    int4* d_order4 = nullptr;
     Counters* d_cnt = nullptr;
     Counters* h_cnt = nullptr;           // pinned mirror
     double* d_diff = nullptr;
@@ -150,6 +151,7 @@ struct revs_solver {
     double kappa = 5.0, vset = 1.0, vlow = 0.95, vhigh = 1.05, tol = 0.0;
     int iter_max = 0, k = 0, cur = 0;
     int warm_cls = kQpClasses - 1;   // largest QP class the stored multipliers can need
+    int ws_bound = kWMax;            // upper bound of every stored working-set size (decides which classes the first round launches)
     bool running = false;
     revs_stats stats{};
 };
@@ -322,12 +324,14 @@ int utility_solve(revs_solver* s, bool in_loop = false) {
     span_end(sp, s->sU);
     s->stats.kernel_launches++;
     bool use[kQpClasses];
-    // first round: every class is launched -- which classes hold columns is decided on the device
-    // (qp_init_kernel), and a class whose list is empty costs a few microseconds
-    for (int cl = 0; cl < kQpClasses; ++cl) use[cl] = true;
+    // first round: qp_init_kernel assigns classes on the device by the size of the stored working
+    // sets; the largest working set any column has had in this solve (read back at every round
+    // sync) bounds them, so larger classes need no launch
+    for (int cl = 0; cl < kQpClasses; ++cl) use[cl] = cl <= 1 || qp_class_cap(cl - 1) < s->ws_bound;
     if (max_warp_n == 0 || warp_n == 0) use[0] = false;
     Q.init = 0;
     Q.order = s->d_order;
+    Q.order4 = s->d_order4;
     int top_cls = 0;
     int grid[kQpClasses];
     for (int cl = 0; cl < kQpClasses; ++cl) grid[cl] = s->ncols;
@@ -384,18 +388,23 @@ int utility_solve(revs_solver* s, bool in_loop = false) {
             // zones of 129..256 residences (NJ = 8 instantiation, few and long columns) share the SMs
             // with the small zones: one CTA per SM on a side stream
             const bool two = warp_n > 128 && small_n > 0;
-            static const int split = getenv("REVS_WARP_SPLIT") ? atoi(getenv("REVS_WARP_SPLIT")) : 0;   // CTAs/SM of the big-zone kernel; 0: one after the other
-            cudaStream_t sBig = split > 0 ? s->sQ[0] : s->sU;
+            // default: one after the other (sharing the SMs slowed both down when measured).  -1: both get
+            // a full persistent grid, the big-zone one first and on a side stream (back-fill);
+            // k > 0: k CTAs/SM for the big-zone kernel, the rest for the small-zone one (REVS_WARP_SPLIT).
+            static const int split = getenv("REVS_WARP_SPLIT") ? atoi(getenv("REVS_WARP_SPLIT")) : 0;
+            cudaStream_t sBig = split != 0 ? s->sQ[0] : s->sU;
+            const int full = qp_warp_ctas_per_sm();
+            const int big_nj = warp_n <= 192 ? 6 : 8;
             if (two) {
-                if (split > 0) CU(cudaStreamWaitEvent(sBig, s->evV, 0));
+                if (split != 0) CU(cudaStreamWaitEvent(sBig, s->evV, 0));
                 sp = span_begin(s, 7, sBig);
-                CU(launch_utility_qp_warp(Q, 8, split > 0 ? split : qp_warp_ctas_per_sm(), sBig));
+                CU(launch_utility_qp_warp(Q, big_nj, split > 0 ? split : full, sBig));
                 span_end(sp, sBig);
                 CU(cudaEventRecord(s->evQ[0], sBig));
                 s->stats.kernel_launches++;
             }
             sp = span_begin(s, 8, s->sU);
-            CU(launch_utility_qp_warp(Q, (warp_n > 128 && !two) ? 8 : 4, qp_warp_ctas_per_sm() - (two ? split : 0), s->sU));
+            CU(launch_utility_qp_warp(Q, (warp_n > 128 && !two) ? big_nj : 4, (two && split > 0) ? full - split : full, s->sU));
             span_end(sp, s->sU);
             s->stats.kernel_launches++;
             if (two) CU(cudaStreamWaitEvent(s->sU, s->evQ[0], 0));
@@ -465,6 +474,7 @@ int utility_solve(revs_solver* s, bool in_loop = false) {
                     s->k, round, s->h_cnt->n_running, s->h_cnt->n_cls[0], s->h_cnt->n_cls[1], s->h_cnt->n_cls[2], s->h_cnt->n_cls[3],
                     s->h_cnt->newton_its, s->h_cnt->max_ws, s->h_cnt->dbg[0], s->h_cnt->dbg[1], s->h_cnt->dbg[2],
                     s->h_cnt->dbg[3]);
+        s->ws_bound = std::max(s->ws_bound, s->h_cnt->max_ws);
         if (s->h_cnt->n_running == 0) break;
         for (int cl = 0; cl < kQpClasses; ++cl) {
             // n_cls: columns of the class that are still running (or were handed to it)
@@ -512,7 +522,7 @@ void free_all(revs_solver* s) {
     void* ptrs[] = {s->d_feeders, s->d_Rpool, s->d_rn2, s->d_rmax, s->d_cand, s->d_stage, s->d_hmap, s->d_Rbf, s->d_gbf, s->d_v32, s->d_sprob, s->d_stiles, s->d_maps_a, s->d_map_b, s->d_bcol0, s->d_pool_parent, s->d_pool_res, s->d_pool_cumr, s->d_pool_off, s->d_load, s->d_pest, s->d_psch[0], s->d_psch[1], s->d_gamma,
                     s->d_pev, s->d_soc, s->d_has_ev, s->d_rating, s->d_capacity, s->d_initial, s->d_indconst,
                     s->d_start, s->d_end, s->d_nmin, s->d_nmax, s->d_zero_i, s->d_cost, s->d_zt, s->d_lamt,
-                    s->d_gt, s->d_vt, s->d_wcount, s->d_widx, s->d_status, s->d_innerok, s->d_cls, s->d_order, s->d_order_count, s->d_cnt, s->d_diff,
+                    s->d_gt, s->d_vt, s->d_wcount, s->d_widx, s->d_status, s->d_innerok, s->d_cls, s->d_order, s->d_order4, s->d_order_count, s->d_cnt, s->d_diff,
                     s->d_cprob, s->d_ctiles};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -656,7 +666,9 @@ int revs_create(revs_solver** out, int device, int n_feeders, const int64_t* fee
     TRY(dalloc(&s->d_status, (size_t)s->ncols));
     TRY(dalloc(&s->d_innerok, (size_t)s->ncols));
     TRY(dalloc(&s->d_cls, (size_t)s->ncols));
-    TRY(dalloc(&s->d_order, (size_t)s->ncols * kQpLists));
+    TRY(dalloc(&s->d_order, (size_t)s->ncols * kQpClasses));
+    TRY(dalloc(&s->d_order4, (size_t)s->ncols * (kQpLists - kQpClasses)));
+    if (hp >= (int64_t)1 << 31 || (rp >> 4) >= (int64_t)1 << 31) s->use_warp_kernel = false;   // 32-bit work-list entries
     TRY(dalloc(&s->d_order_count, (size_t)2 * kQpLists));
     TRY(dalloc(&s->d_cnt, (size_t)1));
     TRY(cudaHostAlloc((void**)&s->h_cnt, sizeof(Counters), cudaHostAllocDefault));
@@ -880,6 +892,7 @@ int revs_admm_begin(revs_solver* s, double kappa, int iter_max, double vset, dou
     s->kappa = kappa; s->iter_max = iter_max; s->vset = vset; s->vlow = vlow; s->vhigh = vhigh;
     s->k = 0; s->cur = 0; s->running = true;
     s->warm_cls = 0;                 // multipliers start at zero
+    s->ws_bound = 0;
     memset(&s->stats, 0, sizeof s->stats);
     const size_t HT = (size_t)s->Hp * s->T * sizeof(double);
     double* zero[] = {s->d_pest, s->d_psch[0], s->d_psch[1], s->d_gamma, s->d_pev, s->d_zt, s->d_lamt, s->d_gt, s->d_vt};
@@ -1112,6 +1125,7 @@ int revs_utility_step(revs_solver* s, double kappa, double vset, double vlow, do
     CU(cudaMemsetAsync(s->d_wcount, 0, sizeof(int) * s->ncols, s->sU));
     memset(&s->stats, 0, sizeof s->stats);
     s->warm_cls = kQpClasses - 1;    // caller-supplied multipliers: any class
+    s->ws_bound = kWMax;
     int rc = utility_solve(s);
     spans_collect(s);
     if (rc) return rc;

@@ -890,6 +890,7 @@ __global__ void __launch_bounds__(256) order_columns_kernel(QpParams P, int mode
     __syncthreads();
     const int c = blockIdx.x * blockDim.x + tid;
     int li = -1, pos = 0;
+    FeederDev fd{};
     if (c < P.ncols && P.status[c] == 0) {
         const int cl = P.cls[c];
         if (mode == 2) {
@@ -899,14 +900,17 @@ __global__ void __launch_bounds__(256) order_columns_kernel(QpParams P, int mode
         } else {
             const int m = P.wcount[c];
             if (mode == 0 && m == 0 && P.cand && P.cand[c] == 0) { P.status[c] = 1; P.inner_ok[c] = 1; }
-            else li = kQpClasses + (P.feeders[c / P.T].n <= 128 ? 0 : kQpBuckets) + (m >= 3 ? 0 : 3 - m);
+            else { fd = P.feeders[c / P.T]; li = kQpClasses + (fd.n <= 128 ? 0 : kQpBuckets) + (m >= 3 ? 0 : 3 - m); }
         }
         if (li >= 0) pos = atomicAdd(&cnt[li], 1);
     }
     __syncthreads();
     if (tid < kQpLists) base[tid] = cnt[tid] ? atomicAdd(&order_count[tid], cnt[tid]) : 0;
     __syncthreads();
-    if (li >= 0) order[(size_t)li * P.ncols + base[li] + pos] = c;
+    if (li >= kQpClasses)       // warp kernels: everything a column needs to start loading, in one 16-byte entry
+        P.order4[(size_t)(li - kQpClasses) * P.ncols + base[li] + pos] =
+            make_int4(c, (int)fd.off, fd.n | (fd.np << 16), (int)(fd.roff >> 4));
+    else if (li >= 0) order[(size_t)li * P.ncols + base[li] + pos] = c;
 }
 
 cudaError_t launch_order_columns(const QpParams& P, int mode, int* order, int* order_count, cudaStream_t stream) {

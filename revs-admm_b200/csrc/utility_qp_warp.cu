@@ -111,22 +111,24 @@ __device__ __forceinline__ void recheck_rows(unsigned candk, const double* __res
 
 // ------------------------------------------------------------------------------------------
 template <int NJ>
-__device__ __forceinline__ void solve_column(const QpParams& P, const int c, WarpSmem& sm, WarpStats& st) {
+__device__ __forceinline__ void solve_column(const QpParams& P, const int4 ent, WarpSmem& sm, WarpStats& st) {
     const int lane = threadIdx.x & 31;
     const unsigned full = 0xffffffffu;
-    const int f = c / P.T, t = c - f * P.T;
-    const int m_old = P.wcount[c];
-    const bool solved_before = P.inner_ok[c] == 1;
-    int* widx = P.widx + (size_t)c * kWMax;
-    const int wi = lane < m_old ? widx[lane] : 0;      // issued early: the multipliers depend on it
-    const FeederDev fd = P.feeders[f];
-    const int n = fd.n, ld = fd.np;
-    const double* __restrict__ R = P.Rpool + fd.roff;
-    const size_t col = (size_t)t * P.Hp + fd.off;
+    // the work-list entry carries the zone geometry, so every load of the column starts at once
+    const int c = ent.x;
+    const int n = ent.z & 0xffff, ld = ent.z >> 16;
+    const int t = c % P.T;
+    const size_t hoff = (size_t)ent.y;
+    const double* __restrict__ R = P.Rpool + ((size_t)ent.w << 4);
+    const size_t col = (size_t)t * P.Hp + hoff;
     const double* z = P.z_t + col;
     double* lam_g = P.lam_t + col;
     double* g = P.g_t + col;
     const double u = P.u, tol = P.tol;
+    int* widx = P.widx + (size_t)c * kWMax;
+    const int m_old = P.wcount[c];
+    const bool solved_before = P.inner_ok[c] == 1;
+    const int wi = lane < kWW ? widx[lane] : 0;        // speculative (valid for lane < m_old): the multipliers depend on it
 
     long long tr_start = 0;
     if (P.trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_start));
@@ -148,7 +150,6 @@ __device__ __forceinline__ void solve_column(const QpParams& P, const int c, War
             zj[k] = in ? z[j] : 0.0;
             gj[k] = in ? g[j] : 0.0;
             g0[k] = gj[k];
-            if (m_old > 0 && in && lam_g[j] > 0.0) inw |= 1u << k;
             if (v32) {
                 const double a = in ? (double)v32[j] : 0.0;
                 vub[k] = kScreenUp * a;
@@ -157,7 +158,6 @@ __device__ __forceinline__ void solve_column(const QpParams& P, const int c, War
                 vub[k] = in ? v64[j] : 0.0;
             }
         }
-        candk &= ~inw;
     }
 
     // ---- working set: rows with a positive multiplier (order preserved), lanes = rows
@@ -171,6 +171,12 @@ __device__ __forceinline__ void solve_column(const QpParams& P, const int c, War
         const int si = __shfl_sync(full, wi, src & 31);
         const double sl = __shfl_sync(full, l, src & 31);
         if (lane < m) { idx = si; lam = sl; }
+#pragma unroll 1
+        for (int a = 0; a < m; ++a) {                      // membership bits of the homes that own a working row
+            const int h = __shfl_sync(full, idx, a);
+            if ((h & 31) == lane) inw |= 1u << (h >> 5);
+        }
+        candk &= ~inw;
     }
 
     double flops = 0.0;
@@ -337,7 +343,7 @@ __device__ __forceinline__ void solve_column(const QpParams& P, const int c, War
 
         if (!ok) {
             // ---- general path: piecewise-quadratic descent on W
-            const double scale = warp_sum(row ? P.rn2[fd.off + idx] : 0.0) / (double)max(m, 1);
+            const double scale = warp_sum(row ? P.rn2[hoff + idx] : 0.0) / (double)max(m, 1);
             const double shift = kHessShiftW * scale + 1e-300;
             double phi;
             {
@@ -577,7 +583,7 @@ __device__ __forceinline__ void solve_column(const QpParams& P, const int c, War
         dp = warp_sum(dp) * (1.0 + 1e-9);
         int ncand = 0;
         {
-            const double* rmax = P.rmax + fd.off;
+            const double* rmax = P.rmax + hoff;
 #pragma unroll
             for (int k = 0; k < NJ; ++k) {
                 const int j = lane + 32 * k;
@@ -743,8 +749,8 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, kCtasPerSm) utility_qp_warp
 #pragma unroll
         for (int bb = 0; bb < kQpBuckets - 1; ++bb)
             if (b == bb && slot >= cnt[bb]) { slot -= cnt[bb]; ++b; }
-        const int c = P.order[(size_t)(kList0 + b) * P.ncols + slot];
-        solve_column<NJ>(P, c, sm, st);
+        const int4 ent = P.order4[(size_t)(kList0 - kQpClasses + b) * P.ncols + slot];
+        solve_column<NJ>(P, ent, sm, st);
         ++st.cols;
         __syncwarp();
     }
@@ -760,8 +766,8 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, kCtasPerSm) utility_qp_warp
 
 int qp_warp_max_n() { return kWarpMaxN; }
 
-// Zones up to 128 residences run the NJ = 4 instantiation, zones up to 256 the NJ = 8 one (own
-// work lists); each fits the instruction cache.  ctas_per_sm sizes the persistent grid so that
+// Zones up to 128 residences run the NJ = 4 instantiation, larger ones (own work lists) NJ = 6 if
+// no zone exceeds 192 residences, else NJ = 8; each fits the instruction cache.  ctas_per_sm sizes the persistent grid so that
 // the two can be co-resident on different streams.
 cudaError_t launch_utility_qp_warp(const QpParams& P, int nj, int ctas_per_sm, cudaStream_t stream) {
     static int n_sm = 0;
@@ -773,6 +779,8 @@ cudaError_t launch_utility_qp_warp(const QpParams& P, int nj, int ctas_per_sm, c
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(utility_qp_warp_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(utility_qp_warp_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(utility_qp_warp_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess && !getenv("REVS_NO_CARVEOUT")) e = cudaFuncSetAttribute(utility_qp_warp_kernel<6>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e == cudaSuccess && !getenv("REVS_NO_CARVEOUT")) e = cudaFuncSetAttribute(utility_qp_warp_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e == cudaSuccess && !getenv("REVS_NO_CARVEOUT")) e = cudaFuncSetAttribute(utility_qp_warp_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
@@ -780,6 +788,7 @@ cudaError_t launch_utility_qp_warp(const QpParams& P, int nj, int ctas_per_sm, c
     }
     ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > kCtasPerSm ? kCtasPerSm : ctas_per_sm);
     if (nj == 8) utility_qp_warp_kernel<8><<<n_sm * ctas_per_sm, 32 * kWarpsPerCta, smem, stream>>>(P);
+    else if (nj == 6) utility_qp_warp_kernel<6><<<n_sm * ctas_per_sm, 32 * kWarpsPerCta, smem, stream>>>(P);
     else utility_qp_warp_kernel<4><<<n_sm * ctas_per_sm, 32 * kWarpsPerCta, smem, stream>>>(P);
     return cudaGetLastError();
 }
