@@ -68,6 +68,7 @@ typedef struct revs_stats {
     float qp_warp_ms;             /* ... of qp_ms: warp-per-column kernels (zones <= 256) */
     float qp_init_ms;             /* ... of qp_ms: start-of-solve kernel                 */
     int64_t qp_columns;           /* (zone,hour) columns that entered a QP kernel, summed over rounds */
+    int64_t qp_warp_rounds;       /* working-set rounds in which the warp-per-column kernels ran */
 } revs_stats;
 
 const char* revs_last_error(void);

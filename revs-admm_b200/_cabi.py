@@ -27,7 +27,8 @@ class Stats(C.Structure):
                 ("primal_residual", C.c_double), ("dual_residual", C.c_double), ("qp_flops", C.c_double),
                 ("gemm_ms", C.c_float), ("gemm_full_ms", C.c_float), ("home_ms", C.c_float), ("dual_ms", C.c_float),
                 ("qp_ms", C.c_float), ("qp_big_ms", C.c_float), ("total_ms", C.c_float),
-                ("qp_warp_ms", C.c_float), ("qp_init_ms", C.c_float), ("qp_columns", C.c_int64)]
+                ("qp_warp_ms", C.c_float), ("qp_init_ms", C.c_float), ("qp_columns", C.c_int64),
+                ("qp_warp_rounds", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

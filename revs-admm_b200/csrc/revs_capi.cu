@@ -388,6 +388,7 @@ int utility_solve(revs_solver* s, bool in_loop = false) {
             // zones of 129..256 residences (NJ = 8 instantiation, few and long columns) share the SMs
             // with the small zones: one CTA per SM on a side stream
             const bool two = warp_n > 128 && small_n > 0;
+            s->stats.qp_warp_rounds++;
             // default: one after the other (sharing the SMs slowed both down when measured).  -1: both get
             // a full persistent grid, the big-zone one first and on a side stream (back-fill);
             // k > 0: k CTAs/SM for the big-zone kernel, the rest for the small-zone one (REVS_WARP_SPLIT).
