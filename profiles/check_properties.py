@@ -1,0 +1,66 @@
+"""Size-independent checks of the utility projection at the benchmark's full size (run on a B200):
+for several synthetic populations the final operator estimate P_est must be non-negative and
+satisfy the voltage rows R P_est <= vhigh^2 - vset^2 in every sampled zone (dense FP64 check on the
+host), and the two scheduling modes (iterations enqueued back to back / host sync per iteration)
+and the two voltage-check modes (BF16 screening / FP64 contraction) must agree bit for bit."""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+import revs_admm_b200 as R  # noqa: E402
+
+
+def run(workload, seed, screen=1, stepwise=False):
+    os.environ["REVS_BENCH_SEED"] = str(seed)
+    trees, hm, cost, sizes, T = bench.make_rank_problem(workload, 0)
+    with R.Solver(sizes, T) as s:
+        s.set_option("screen", screen)
+        s.set_feeder_trees(trees)
+        s.set_homes(**hm)
+        s.set_tariff(cost)
+        if stepwise:
+            s.admm_begin(**bench.ADMM)
+            for _ in range(bench.ADMM["iter_max"]):
+                s.admm_step()
+        else:
+            s.solve_admm(**bench.ADMM)
+        pe, gm = s.estimate()
+        res = s.results(bench.ADMM["iter_max"])
+        st = s.stats()
+    return trees, pe, gm, res, st
+
+
+def feasibility(trees, pe, zones=200):
+    u = bench.ADMM["vhigh"] ** 2 - bench.ADMM["vset"] ** 2
+    worst, off = -np.inf, 0
+    idx = set(np.linspace(0, len(trees) - 1, min(zones, len(trees))).astype(int).tolist())
+    for z, tr in enumerate(trees):
+        n = tr.n_res
+        if z in idx:
+            Rm = tr.rmat()[np.ix_(tr.res_node, tr.res_node)]
+            worst = max(worst, float((Rm @ pe[off:off + n] - u).max()))
+        off += n
+    return worst
+
+
+if __name__ == "__main__":
+    wl = sys.argv[1] if len(sys.argv) > 1 else "synthetic-multifeeder-125k-homes-per-gpu-x96"
+    out = []
+    for seed in (0, 1, 2, 3):
+        trees, pe, gm, res, st = run(wl, seed)
+        rec = {"seed": seed, "min_P_est": float(pe.min()), "max_voltage_excess_pu2": feasibility(trees, pe),
+               "max_working_set": st["max_working_set"], "rounds": st["qp_outer_iterations"], "ms": st["total_ms"]}
+        if seed == 0:
+            _, pe2, gm2, res2, _ = run(wl, seed, stepwise=True)
+            rec["stepwise_identical"] = bool(np.array_equal(pe, pe2) and np.array_equal(gm, gm2) and np.array_equal(res["P_sch"], res2["P_sch"]))
+            _, pe3, gm3, res3, _ = run(wl, seed, screen=0)
+            rec["fp64_contraction_identical"] = bool(np.array_equal(pe, pe3) and np.array_equal(gm, gm3) and np.array_equal(res["P_sch"], res3["P_sch"]))
+        out.append(rec)
+        print(json.dumps(rec), flush=True)
+    ok = all(r["min_P_est"] >= 0.0 and r["max_voltage_excess_pu2"] <= 1e-9 for r in out) and out[0]["stepwise_identical"] and out[0]["fp64_contraction_identical"]
+    print("PROPERTIES", "OK" if ok else "FAILED")
