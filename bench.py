@@ -281,7 +281,8 @@ def run_gpu(args, rank, world, local_rank):
     cost_p, t = pinned_like(cost)
     keep.append(t)
 
-    s = R.Solver(sizes, T, device=local_rank)
+    # K independent stream pipelines on this GPU (zones never exchange data): see parallel.PipelinedSolver
+    s = R.PipelinedSolver(sizes, T, device=local_rank, pipelines=args.pipelines)
 
     out_p = {}
     for k, shape in (("P_sch", (H, T)), ("P_ev", (H, T)), ("SOC", (H, T + 1)), ("diff", (ADMM["iter_max"], H))):
@@ -294,7 +295,7 @@ def run_gpu(args, rank, world, local_rank):
         s.set_tariff(cost_p)
 
     upload()
-    stats_acc = {k: 0.0 for k in ("gemm_ms", "gemm_full_ms", "gemm_full_launches", "home_ms", "dual_ms", "qp_ms", "qp_big_ms", "qp_warp_ms", "qp_init_ms", "qp_columns", "qp_warp_rounds", "qp_flops", "total_ms", "kernel_launches",
+    stats_acc = {k: 0.0 for k in ("gemm_ms", "gemm_full_ms", "gemm_full_launches", "home_ms", "dual_ms", "qp_ms", "qp_big_ms", "qp_warp_ms", "qp_init_ms", "qp_columns", "qp_warp_rounds", "qp_flops", "total_ms", "total_ms_sum", "kernel_launches",
                                   "gemm_launches", "qp_outer_iterations", "qp_newton_iterations")}
     # ---- device-resident leg ("value")
     for _ in range(args.warmup):
@@ -369,30 +370,40 @@ def run_gpu(args, rank, world, local_rank):
     # the home solve runs on a low-priority stream beside the utility kernels and yields the SMs to
     # them, so its in-loop span is not a kernel time: one extra solve with the kernel in line
     # (outside the timed region) gives the undisturbed launch duration
-    s.set_option("overlap_home", 0)
-    s.solve_admm(**ADMM)
-    st_iso = s.stats()
-    s.set_option("overlap_home", 1)
+    # Kernel quality is reported at the workload's full launch size: one extra single-pipeline
+    # solver over all zones of this GPU, home solve in line, outside the timed region.  (Inside the
+    # timed region every pipeline launches over its share of the zones, side by side with the others.)
+    s1 = R.PipelinedSolver(sizes, T, device=local_rank, pipelines=1)
+    s1.set_feeder_trees(trees)
+    s1.set_homes(**hm_p)
+    s1.set_tariff(cost_p)
+    s1.set_option("overlap_home", 0)
+    s1.solve_admm(**ADMM)
+    s1.solve_admm(**ADMM)
+    st_iso = s1.stats()
+    n_pipe = last.get("pipelines", 1)
+    iso_note = "one launch over all homes of the GPU: extra single-pipeline solve with the home solve in line, outside the timed " \
+               "region; ms_span_in_loop: spans inside the timed region (%d pipelines side by side, each over its share), summed" % n_pipe
     if st_iso["home_ms"] > 0:
         ms = st_iso["home_ms"] / ADMM["iter_max"]
         kernels["home_solve"] = {"bound": "hbm", "ms_per_launch": ms, "achieved": home_bytes / (ms * 1e-3) / 1e9,
                                  "peak": hbm_peak, "unit": "GB/s", "bytes_per_launch": home_bytes,
-                                 "ms_span_in_loop": stats_acc["home_ms"] / iters,
-                                 "note": "ms_per_launch: kernel in line (extra solve, same data); ms_span_in_loop: low-priority stream, overlapped with the utility kernels"}
-    if stats_acc["dual_ms"] > 0:
-        ms = stats_acc["dual_ms"] / iters
+                                 "ms_span_in_loop": stats_acc["home_ms"] / iters, "note": iso_note}
+    if st_iso["dual_ms"] > 0:
+        ms = st_iso["dual_ms"] / ADMM["iter_max"]
         dual_bytes_now = Hp * T * (56 + 8 + 2)    # + g = [z]_+ and its bf16 copy for the next utility solve
         kernels["dual_update"] = {"bound": "hbm", "ms_per_launch": ms, "achieved": dual_bytes_now / (ms * 1e-3) / 1e9,
-                                  "peak": hbm_peak, "unit": "GB/s", "bytes_per_launch": dual_bytes_now}
-    if stats_acc["gemm_full_launches"] > 0:
+                                  "peak": hbm_peak, "unit": "GB/s", "bytes_per_launch": dual_bytes_now,
+                                  "ms_span_in_loop": stats_acc["dual_ms"] / iters, "note": iso_note}
+    if st_iso["gemm_full_launches"] > 0:
         # in-loop voltage check over ALL columns: BF16 screening contraction
-        ms = stats_acc["gemm_full_ms"] / stats_acc["gemm_full_launches"]
+        ms = st_iso["gemm_full_ms"] / ADMM["iter_max"]
         sbytes = sum(2.0 * n * n for n in n_p) + Hp * T * (2 + 4)
         kernels["screen_bf16"] = {"bound": "hbm", "ms_per_launch": ms, "achieved": sbytes / (ms * 1e-3) / 1e9,
                                   "peak": hbm_peak, "unit": "GB/s", "tflops": gemm_flops / (ms * 1e-3) / 1e12,
                                   "tensor_peak_tflops": bf16_peak, "bytes_per_launch": sbytes,
                                   "launches_per_step": stats_acc["gemm_launches"] / args.steps,
-                                  "ms_total_per_step": stats_acc["gemm_ms"] / args.steps}
+                                  "ms_total_per_step": stats_acc["gemm_ms"] / args.steps, "note": iso_note}
     qp_flops = stats_acc["qp_flops"]
     if stats_acc["qp_ms"] > 0:
         # Spans of the QP classes overlap (separate streams): the wall share is total - rest.
@@ -400,7 +411,7 @@ def run_gpu(args, rank, world, local_rank):
         # per round; a column that enters a QP kernel reads z, g, the screened voltages and its
         # multipliers and writes g, its bf16 copy and the multipliers back: 38 B per residence.
         rest = stats_acc["gemm_ms"] + stats_acc["dual_ms"]
-        qp_wall = max(stats_acc["total_ms"] - rest, 1e-9)
+        qp_wall = max(stats_acc["total_ms_sum"] - rest, 1e-9) / n_pipe      # pipelines run side by side
         n_mean = Hp / max(len(sizes), 1)
         qp_bytes = stats_acc["qp_columns"] * n_mean * 38.0 + stats_acc["qp_outer_iterations"] * len(sizes) * T * 16.0
         kernels["utility_qp"] = {"bound": "hbm", "note": "latency-bound active-set solver (one warp or one CTA per column); rows of R come from L2",
@@ -416,21 +427,22 @@ def run_gpu(args, rank, world, local_rank):
                                  "ms_classes_ge_33_rows": stats_acc["qp_big_ms"] / args.steps}
     # FP64 DMMA contraction (reliability check / exact mode): one extra solve outside the timed region
     if rank == 0 and not args.no_exact:
-        s.set_option("screen", 0)
-        s.solve_admm(**ADMM)
-        st = s.stats()
-        s.set_option("screen", 1)
+        s1.set_option("screen", 0)
+        s1.set_option("overlap_home", 1)
+        s1.solve_admm(**ADMM)
+        st = s1.stats()
         if st["gemm_full_launches"] > 0:
             ms = st["gemm_full_ms"] / st["gemm_full_launches"]
             kernels["contract_f64"] = {"bound": "tensor", "ms_per_launch": ms, "achieved": gemm_flops / (ms * 1e-3) / 1e12,
                                        "peak": f64_peak, "unit": "TFLOP/s",
                                        "peak_source": "cuBLAS DGEMM 6144^3 measured in this run",
-                                       "note": "exact mode (screen=0), measured outside the timed region",
+                                       "note": "exact mode (screen=0), single pipeline, measured outside the timed region",
                                        "ms_per_step_exact_mode": st["total_ms"]}
+    s1.close()
     for k in kernels.values():
         if "peak" in k and k["peak"]:
             k["frac"] = k["achieved"] / k["peak"]
-    tot = max(stats_acc["total_ms"], 1e-9)
+    tot = max(stats_acc["total_ms_sum"], 1e-9)      # spans and totals summed over the pipelines
     share = {"screen_bf16": stats_acc["gemm_ms"] / tot, "home_solve(overlapped, yielding)": stats_acc["home_ms"] / tot,
              "dual_update": stats_acc["dual_ms"] / tot,
              "utility_qp": 1.0 - (stats_acc["gemm_ms"] + stats_acc["dual_ms"]) / tot}
@@ -458,7 +470,7 @@ def run_gpu(args, rank, world, local_rank):
                     "note": "dominant kernel by time; an active-set solver, latency-bound by design (one warp per (zone,hour) column, "
                             "rows of R served from L2): DESIGN.md section 3.  The HBM-bound kernels of the path are in `kernels` "
                             "(home_solve 0.60, dual_update 0.71 of the measured copy bandwidth)"}
-    kernels.get("utility_qp", {})["share_warp_kernels"] = stats_acc["qp_warp_ms"] / max(stats_acc["total_ms"], 1e-9)
+    kernels.get("utility_qp", {})["share_warp_kernels"] = stats_acc["qp_warp_ms"] / max(stats_acc["total_ms_sum"], 1e-9)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -472,7 +484,7 @@ def run_gpu(args, rank, world, local_rank):
             "metric": "home_hours_scheduled_per_sec", "value": value, "unit": "home-hours/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "feeders_per_gpu": nf, "homes_per_feeder": n, "T": T,
+            "config": {"workload": args.workload, "feeders_per_gpu": nf, "homes_per_feeder": n, "T": T, "pipelines_per_gpu": n_pipe,
                        "voltage_zones_per_gpu": len(sizes), "homes_total": int(total_homes), **ADMM,
                        "population": "same synthetic draw on every rank (fixed work per GPU)",
                        "l2": "working set per solve > L2 (sensitivity blocks %.2f GB per GPU)" % (sum(8.0 * x * x for x in n_p) / 1e9)},
@@ -509,6 +521,7 @@ def main():
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
     ap.add_argument("--workload", default="synthetic-multifeeder-125k-homes-per-gpu-x96", choices=list(WORKLOADS))
     ap.add_argument("--cpu-sample-homes", type=int, default=None)
+    ap.add_argument("--pipelines", type=int, default=3, help="independent stream pipelines per GPU (parallel.PipelinedSolver)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-exact", action="store_true", help="skip the extra exact-mode (FP64 contraction) solve used for the contract_f64 figure")
     ap.add_argument("--no-split", action="store_true", help="hand whole feeders to the solver instead of their voltage zones")

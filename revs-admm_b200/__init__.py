@@ -6,6 +6,7 @@ path is hand-written CUDA for sm_100a behind the C ABI of include/revs_admm.h
 """
 from . import _cabi, extract, feeder, lpsolver, revs_fixture  # noqa: F401
 from ._cabi import RevsError, Solver, contract, device_count, screen_contract  # noqa: F401
+from .parallel import PipelinedSolver  # noqa: F401
 from .revs_fixture import REVS  # noqa: F401
 
 __version__ = "0.1.0"

@@ -56,3 +56,116 @@ def run_admm(stepper, kappa=5.0, iter_max=15, vset=1.0, vlow=0.95, vhigh=1.05, t
         else:
             history.append(tuple(local[:2]))
     return iter_max, history
+
+
+class PipelinedSolver:
+    """Several independent solver pipelines on ONE GPU.
+
+    The sensitivity matrix is block diagonal over voltage zones, so a GPU's zones can be cut into
+    K contiguous groups that never exchange data.  Each group gets its own device solver (own
+    streams, own working-set state) and its own host thread; while one pipeline sits in the
+    latency-bound tail of a utility solve or in a host round trip, the others keep the SMs busy.
+    Same methods as ``_cabi.Solver``; results are those of a single solver, bit for bit.
+    """
+
+    def __init__(self, feeder_sizes, T, device=0, pipelines=3):
+        from concurrent.futures import ThreadPoolExecutor
+        from ._cabi import Solver
+        self.sizes = [int(n) for n in feeder_sizes]
+        self.T, self.nf = int(T), len(self.sizes)
+        self.off = np.concatenate([[0], np.cumsum(self.sizes)]).astype(np.int64)
+        self.H = int(self.off[-1])
+        K = max(1, min(int(pipelines), self.nf))
+        self.cuts = [shard_feeders(self.sizes, K, k) for k in range(K)]
+        self.cuts = [(a, b) for a, b in self.cuts if b > a]
+        self.parts = [Solver(self.sizes[a:b], T, device=device) for a, b in self.cuts]
+        self.rows = [(int(self.off[a]), int(self.off[b])) for a, b in self.cuts]
+        self.pool = ThreadPoolExecutor(max_workers=len(self.parts))
+
+    # ---- plumbing
+    def _each(self, fn, concurrent=True):
+        if concurrent and len(self.parts) > 1:
+            return list(self.pool.map(fn, range(len(self.parts))))
+        return [fn(k) for k in range(len(self.parts))]
+
+    def close(self):
+        for p in getattr(self, "parts", []):
+            p.close()
+        self.parts = []
+        if getattr(self, "pool", None):
+            self.pool.shutdown(wait=True)
+            self.pool = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- inputs
+    def set_feeder_trees(self, trees):
+        assert len(trees) == self.nf
+        self._each(lambda k: self.parts[k].set_feeder_trees(trees[self.cuts[k][0]:self.cuts[k][1]]))
+
+    def set_homes(self, **hm):
+        def f(k):
+            lo, hi = self.rows[k]
+            self.parts[k].set_homes(**{n: v[lo:hi] for n, v in hm.items()})
+        self._each(f)
+
+    def set_tariff(self, cost):
+        self._each(lambda k: self.parts[k].set_tariff(cost), concurrent=False)
+
+    def set_option(self, name, value):
+        self._each(lambda k: self.parts[k].set_option(name, value), concurrent=False)
+
+    # ---- solves
+    def solve_admm(self, concurrent=True, **kw):
+        return max(self._each(lambda k: self.parts[k].solve_admm(**kw), concurrent=concurrent))
+
+    def results(self, iters=None, want_diff=True, out=None):
+        H, T = self.H, self.T
+        iters = self.parts[0].stats()["admm_iterations"] if iters is None else iters
+        if out is None:
+            out = dict(P_sch=np.empty((H, T)), P_ev=np.empty((H, T)), SOC=np.empty((H, T + 1)),
+                       diff=np.empty((iters, H)) if want_diff else None)
+        D = out.get("diff")
+
+        def f(k):
+            lo, hi = self.rows[k]
+            sub = dict(P_sch=out["P_sch"][lo:hi], P_ev=out["P_ev"][lo:hi], SOC=out["SOC"][lo:hi],
+                       diff=np.empty((iters, hi - lo)) if D is not None else None)
+            self.parts[k].results(iters, want_diff=D is not None, out=sub)
+            if D is not None:
+                D[:iters, lo:hi] = sub["diff"]
+        self._each(f)
+        return dict(P_sch=out["P_sch"], P_ev=out["P_ev"], SOC=out["SOC"], diff=D)
+
+    def estimate(self):
+        pe, gm = np.empty((self.H, self.T)), np.empty((self.H, self.T))
+
+        def f(k):
+            lo, hi = self.rows[k]
+            pe[lo:hi], gm[lo:hi] = self.parts[k].estimate()
+        self._each(f)
+        return pe, gm
+
+    def stats(self):
+        """Counters and CUDA-event spans summed over the pipelines; total_ms is the longest
+        pipeline (they run side by side), residuals are recombined from the per-pipeline norms."""
+        sts = [p.stats() for p in self.parts]
+        out = {}
+        for key in sts[0]:
+            vals = [s[key] for s in sts]
+            if key in ("total_ms", "admm_iterations", "max_working_set"):
+                out[key] = max(vals)
+            elif key in ("primal_residual", "dual_residual"):
+                w = [hi - lo for lo, hi in self.rows]
+                out[key] = float(np.sqrt(sum(v * v * n for v, n in zip(vals, w)) / max(sum(w), 1)))
+            else:
+                out[key] = sum(vals)
+        out["total_ms_sum"] = sum(s["total_ms"] for s in sts)
+        out["pipelines"] = len(sts)
+        return out

@@ -205,3 +205,24 @@ def test_scheduling_options_do_not_change_results(gpu_lib):
         out["P_est"], out["Gamma"] = s.estimate()
     for k in ("P_sch", "P_ev", "SOC", "diff", "P_est", "Gamma"):
         assert np.array_equal(base[k], out[k]), k
+
+
+@pytest.mark.parametrize("pipelines", [2, 3, 7])
+def test_pipelined_solver_equals_single_solver(gpu_lib, pipelines):
+    """K stream pipelines over contiguous groups of zones (parallel.PipelinedSolver) return the single
+    solver's results bit for bit: zones never exchange data."""
+    sizes, T = [60, 45, 33, 80, 20], 24
+    trees, hm, cost = _problem(sizes, T, seed=11)
+    kw = dict(kappa=5.0, iter_max=5, vset=1.0, vlow=0.95, vhigh=1.015)
+    base = _gpu(gpu_lib, sizes, T, trees, hm, cost, kw)
+    with gpu_lib.PipelinedSolver(sizes, T, pipelines=pipelines) as s:
+        s.set_feeder_trees(trees)
+        s.set_homes(**hm)
+        s.set_tariff(cost)
+        done = s.solve_admm(**kw)
+        out = s.results(done)
+        out["P_est"], out["Gamma"] = s.estimate()
+        st = s.stats()
+    assert 2 <= st["pipelines"] <= min(pipelines, len(sizes)) and st["admm_iterations"] == kw["iter_max"]
+    for k in ("P_sch", "P_ev", "SOC", "diff", "P_est", "Gamma"):
+        assert np.array_equal(base[k], out[k]), k

@@ -100,3 +100,16 @@ def test_revs_fixture_interface(case121144):
     assert len(case121144["saved"]["ev_homes"]) == 267
     with pytest.raises(NotImplementedError):
         fx.get_centralized_optimal(case121144["tariff"], case121144["homes"], case121144["dist"])
+
+
+def test_pipeline_cuts_cover_all_zones():
+    """parallel.PipelinedSolver cuts the zone list with shard_feeders: contiguous, complete, home-balanced."""
+    from revs_admm_b200.parallel import shard_feeders
+    rng = np.random.default_rng(0)
+    sizes = rng.integers(40, 170, size=1250)
+    for K in (1, 2, 3, 4, 8):
+        cuts = [shard_feeders(sizes, K, k) for k in range(K)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == len(sizes)
+        assert all(cuts[k][1] == cuts[k + 1][0] for k in range(K - 1))
+        homes = [int(sizes[a:b].sum()) for a, b in cuts]
+        assert max(homes) - min(homes) <= 2 * sizes.max()
