@@ -329,15 +329,14 @@ def run_gpu(args, rank, world, local_rank):
 
     # ---- end-to-end leg: host buffers in, host results out, every step
     for _ in range(min(args.warmup, 1)):
-        upload(); s.solve_admm(**ADMM); s.results(out=out_p)
+        s.schedule(trees, hm_p, cost_p, out=out_p, **ADMM)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        upload()
-        s.solve_admm(**ADMM)
-        out = s.results(out=out_p)
+        # one call: feeder trees, homes and tariff up from pinned host buffers, solve, results back to pinned host buffers
+        out = s.schedule(trees, hm_p, cost_p, out=out_p, **ADMM)
     torch.cuda.synchronize()
     e2e_wall = (time.perf_counter() - t0) * 1e3 / args.steps
     e1.record()

@@ -29,3 +29,9 @@ for K in (1, 3):
     r = np.mean([once() for _ in range(4)], axis=0)
     print(f"K={K}: trees {r[0]:.2f} ms, homes+tariff {r[1]:.2f} ms, solve {r[2]:.2f} ms, results {r[3]:.2f} ms, total {r.sum():.2f} ms", flush=True)
     s.close()
+    s = R.PipelinedSolver(sizes, T, pipelines=K)
+    for _ in range(2): s.schedule(trees, hm_p, cost, out=out_p, **bench.ADMM)
+    t0 = time.perf_counter()
+    for _ in range(4): s.schedule(trees, hm_p, cost, out=out_p, **bench.ADMM)
+    print(f"K={K}: schedule() {1e3 * (time.perf_counter() - t0) / 4:.2f} ms per step (upload -> solve -> download per pipeline, overlapped)", flush=True)
+    s.close()

@@ -89,6 +89,7 @@ struct QpParams {
     int4* order4;          // warp-kernel lists [kQpLists - kQpClasses][ncols]: {column, first home, n | ld << 16, R offset / 16}
     int sweep;             // 1: this launch only takes columns handed over during the current round
     int warp_m_max;        // warm working sets above this size start in class 1 (qp_init_kernel)
+    int warp_m_max_big;    // the same for zones of more than 128 residences (longer columns)
     int ncols;
     long long* trace;      // optional debug [ncols][12]: start ns, end ns, smid, class/m/pieces, phase cycles ...
     unsigned long long* dbg;  // optional [4 + 5*kQpClasses]: counts, then per-class phase cycles

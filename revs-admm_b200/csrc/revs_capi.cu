@@ -151,6 +151,7 @@ struct revs_solver {
     double kappa = 5.0, vset = 1.0, vlow = 0.95, vhigh = 1.05, tol = 0.0;
     int iter_max = 0, k = 0, cur = 0;
     int warm_cls = kQpClasses - 1;   // largest QP class the stored multipliers can need
+    int prio_lo = 0, prio_hi = 0;    // stream priority range of the device
     int ws_bound = kWMax;            // upper bound of every stored working-set size (decides which classes the first round launches)
     bool running = false;
     revs_stats stats{};
@@ -268,6 +269,7 @@ int utility_solve(revs_solver* s, bool in_loop = false) {
     Q.queue = s->d_order_count + kQpLists;
     Q.sweep = 0;
     Q.warp_m_max = getenv("REVS_WARP_M_MAX") ? atoi(getenv("REVS_WARP_M_MAX")) : qp_warp_m_max_default();
+    Q.warp_m_max_big = getenv("REVS_WARP_M_MAX_BIG") ? atoi(getenv("REVS_WARP_M_MAX_BIG")) : std::min(Q.warp_m_max, 5);
     if (!s->rn2_valid) {
         CU(launch_row_norms(s->d_feeders, s->nf, s->d_Rpool, s->d_rn2, s->d_rmax, s->sU));
         CU(launch_to_bf16(s->d_Rpool, s->d_Rbf, s->Rpool_elems, s->sU));
@@ -608,6 +610,8 @@ int revs_create(revs_solver** out, int device, int n_feeders, const int64_t* fee
     // by the dual update, so its CTAs yield the SMs to the utility kernels
     int prio_lo = 0, prio_hi = 0;
     TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    s->prio_lo = prio_lo;
+    s->prio_hi = prio_hi;
     TRY(cudaStreamCreateWithPriority(&s->sU, cudaStreamNonBlocking, prio_hi));
     TRY(cudaStreamCreateWithPriority(&s->sH, cudaStreamNonBlocking, prio_lo));
     TRY(cudaEventCreateWithFlags(&s->evV, cudaEventDisableTiming));
@@ -1326,6 +1330,23 @@ int revs_set_option(revs_solver* s, const char* name, double value) {
     if (!strcmp(name, "screen")) { s->screen = value != 0.0; return REVS_OK; }
     if (!strcmp(name, "warp_kernel")) { s->use_warp_kernel = value != 0.0; return REVS_OK; }
     if (!strcmp(name, "overlap_home")) { s->overlap_home = value != 0.0; return REVS_OK; }
+    if (!strcmp(name, "priority")) {
+        // rank of this solver among several on one GPU (0 = served first): its utility streams are
+        // re-created `value` levels below the highest stream priority, still above every home solve
+        CU(cudaSetDevice(s->device));
+        CU(cudaStreamSynchronize(s->sU));
+        int pr = s->prio_hi + (int)value;
+        if (pr > s->prio_lo - 1) pr = s->prio_lo - 1;
+        if (pr < s->prio_hi) pr = s->prio_hi;
+        CU(cudaStreamDestroy(s->sU));
+        CU(cudaStreamCreateWithPriority(&s->sU, cudaStreamNonBlocking, pr));
+        for (int cl = 0; cl < kQpClasses; ++cl) {
+            CU(cudaStreamSynchronize(s->sQ[cl]));
+            CU(cudaStreamDestroy(s->sQ[cl]));
+            CU(cudaStreamCreateWithPriority(&s->sQ[cl], cudaStreamNonBlocking, pr));
+        }
+        return REVS_OK;
+    }
     if (!strcmp(name, "screen_impl")) {
         if (value != 0.0 && !s->tc5_ready) return fail(REVS_ERR_ARG, "tcgen05 screening kernel unavailable (T > 96 or tensor-map encoding failed)");
         s->screen_impl = value != 0.0 ? 1 : 0;

@@ -457,6 +457,88 @@ __device__ __forceinline__ double hess_row_dot(int i, const double* v, int ma, S
     return acc;
 }
 
+// Primal-dual active-set minimisation of one quadratic piece for working sets of up to 32 rows,
+// executed by ONE warp (lanes = rows) without block barriers: the first CTA class spends most of
+// its time here and the block-wide version costs a dozen __syncthreads per guess.  Same
+// arithmetic as the block version below: b = H lam + shift lam - grad, A = {lam > 0} u {grad < 0},
+// solve (H_AA + shift I) x_A = b_A, flip the rows with x <= 0 (in A) or mu < 0 (outside).
+// Returns whether the guesses settled; the minimiser is left in sm.trial.
+template <int WMAX, class S>
+__device__ bool pdas_warp(int m, double shift, S& sm, unsigned& n_pdas, double& flops) {
+    constexpr int HLD = WMAX + 1;
+    double* Hb = sm.Hb;
+#define LVW(p, q) Hb[(q) * HLD + (p) + 1]
+    const int lane = threadIdx.x & 31;
+    const unsigned full = 0xffffffffu;
+    const bool row = lane < m;
+    auto Hij = [&](int i, int j) -> double { return i > j ? Hb[i * HLD + j] : (i < j ? Hb[j * HLD + i] : sm.hdiag[i]); };
+    const double lam = row ? sm.lam[lane] : 0.0, grad = row ? sm.grad[lane] : 0.0;
+    double b = 0.0;
+    for (int q = 0; q < m; ++q) {
+        const double lq = __shfl_sync(full, lam, q);
+        if (row && lq > 0.0) b = fma(Hij(lane, q), lq, b);
+    }
+    b += shift * lam - grad;
+    bool inA = row && (lam > 0.0 || grad < 0.0);
+    double x = 0.0;
+    bool settled = false;
+    for (int guess = 0; guess < kPdasMax; ++guess) {
+        ++n_pdas;
+        const unsigned Am = __ballot_sync(full, inA);
+        const int ma = __popc(Am);
+        const int pos = __popc(Am & ((1u << lane) - 1));
+        flops += (2.0 / 3.0) * ma * ma * ma + 4.0 * ma * ma + 2.0 * m * ma;
+        double xs = 0.0;
+        if (ma > 0) {
+            const int o = lane < ma ? (int)__fns(Am, 0, lane + 1) : 0;       // original row of compact row `lane`
+            for (int c = 0; c < ma; ++c) {
+                const int oc = __shfl_sync(full, o, c);
+                if (lane < ma && c <= lane) LVW(lane, c) = Hij(o, oc) + (c == lane ? shift : 0.0);
+            }
+            __syncwarp();
+            for (int k = 0; k < ma; ++k) {                                    // Cholesky, lanes own rows
+                const double dkk = sqrt(fmax(LVW(k, k), 1e-300));
+                __syncwarp();
+                if (lane == k) LVW(k, k) = dkk;
+                double lik = 0.0;
+                if (lane > k && lane < ma) { lik = LVW(lane, k) / dkk; LVW(lane, k) = lik; }
+                __syncwarp();
+                if (lane > k && lane < ma)
+                    for (int j = k + 1; j <= lane; ++j) LVW(lane, j) = fma(-lik, LVW(j, k), LVW(lane, j));
+                __syncwarp();
+            }
+            double y = __shfl_sync(full, b, o);                               // rhs of compact row `lane`
+            if (lane >= ma) y = 0.0;
+            for (int k = 0; k < ma; ++k) {
+                const double yk = __shfl_sync(full, y, k) / LVW(k, k);
+                if (lane == k) y = yk;
+                if (lane > k && lane < ma) y = fma(-LVW(lane, k), yk, y);
+            }
+            for (int k = ma - 1; k >= 0; --k) {
+                const double xk = __shfl_sync(full, y, k) / LVW(k, k);
+                if (lane == k) y = xk;
+                if (lane < k) y = fma(-LVW(k, lane), xk, y);
+            }
+            xs = y;
+        }
+        const double xg = __shfl_sync(full, xs, pos & 31);
+        x = inA ? xg : 0.0;
+        double mu = 0.0;
+        for (int q = 0; q < m; ++q) {
+            const double xq = __shfl_sync(full, x, q);
+            if (row && xq != 0.0) mu = fma(Hij(lane, q), xq, mu);
+        }
+        mu -= b;
+        const bool bad = row && (inA ? (x <= 0.0) : (mu < 0.0));
+        if (!__any_sync(full, bad)) { settled = true; break; }
+        if (bad) inA = !inA;
+        __syncwarp();
+    }
+    if (row) sm.trial[lane] = x;
+#undef LVW
+    return settled;
+}
+
 constexpr int kAddMaxVerify = 8;
 constexpr int kCtaPassMax = 16;          // admit / solve / verify passes of one launch (zones <= kVerifyMaxN)
 
@@ -714,37 +796,48 @@ __device__ void qp_column(const QpParams& P, const int c, S& sm) {
 
         // ---- exact minimiser of the piece over lam_W >= 0: primal-dual active set
         // b = H lam - grad ; A = {lam > 0} u {grad < 0}
-        for (int a = tid; a < m; a += THREADS) sm.inA[a] = (sm.lam[a] > 0.0) ? 1 : 0;
-        __syncthreads();
-        int ma = compact_flags<THREADS>(sm.inA, m, sm);
-        for (int i = tid; i < m; i += THREADS)
-            sm.b[i] = hess_row_dot<WMAX>(i, sm.lam, ma, sm) + shift * sm.lam[i] - sm.grad[i];
-        __syncthreads();
-        for (int a = tid; a < m; a += THREADS) sm.inA[a] = (sm.lam[a] > 0.0 || sm.grad[a] < 0.0) ? 1 : 0;
-        __syncthreads();
         bool pdas_ok = false;
-        for (int guess = 0; guess < kPdasMax; ++guess) {
-            ++n_pdas;
-            ma = compact_flags<THREADS>(sm.inA, m, sm);
-            flops += (2.0 / 3.0) * ma * ma * ma + 4.0 * ma * ma + 2.0 * m * ma;
-            for (int a = tid; a < m; a += THREADS) sm.trial[a] = 0.0;
-            if (ma > 0) {
-                for (int p = tid; p < ma; p += THREADS) sm.y[p] = sm.b[sm.fl[p]];
-                __syncthreads();
-                factor_solve<WMAX, THREADS>(ma, shift, sm);
-                for (int p = tid; p < ma; p += THREADS) sm.trial[sm.fl[p]] = sm.y[p];
+        if constexpr (WMAX <= 32) {
+            __syncthreads();
+            if (warp == 0) {
+                const bool settled = pdas_warp<WMAX>(m, shift, sm, n_pdas, flops);
+                if (lane == 0) sm.ibcast[1] = settled ? 1 : 0;
             }
             __syncthreads();
-            bool bad = false;
-            for (int i = tid; i < m; i += THREADS) {
-                if (sm.inA[i]) {
-                    if (sm.trial[i] <= 0.0) { bad = true; sm.inA[i] = 0; }
-                } else {
-                    const double mu = hess_row_dot<WMAX>(i, sm.trial, ma, sm) - sm.b[i];
-                    if (mu < 0.0) { bad = true; sm.inA[i] = 1; }
+            pdas_ok = sm.ibcast[1] != 0;
+        } else {
+            for (int a = tid; a < m; a += THREADS) sm.inA[a] = (sm.lam[a] > 0.0) ? 1 : 0;
+            __syncthreads();
+            int ma = compact_flags<THREADS>(sm.inA, m, sm);
+            for (int i = tid; i < m; i += THREADS)
+                sm.b[i] = hess_row_dot<WMAX>(i, sm.lam, ma, sm) + shift * sm.lam[i] - sm.grad[i];
+            __syncthreads();
+            for (int a = tid; a < m; a += THREADS) sm.inA[a] = (sm.lam[a] > 0.0 || sm.grad[a] < 0.0) ? 1 : 0;
+            __syncthreads();
+            for (int guess = 0; guess < kPdasMax; ++guess) {
+                ++n_pdas;
+                ma = compact_flags<THREADS>(sm.inA, m, sm);
+                flops += (2.0 / 3.0) * ma * ma * ma + 4.0 * ma * ma + 2.0 * m * ma;
+                for (int a = tid; a < m; a += THREADS) sm.trial[a] = 0.0;
+                if (ma > 0) {
+                    for (int p = tid; p < ma; p += THREADS) sm.y[p] = sm.b[sm.fl[p]];
+                    __syncthreads();
+                    factor_solve<WMAX, THREADS>(ma, shift, sm);
+                    for (int p = tid; p < ma; p += THREADS) sm.trial[sm.fl[p]] = sm.y[p];
                 }
+                __syncthreads();
+                bool bad = false;
+                for (int i = tid; i < m; i += THREADS) {
+                    if (sm.inA[i]) {
+                        if (sm.trial[i] <= 0.0) { bad = true; sm.inA[i] = 0; }
+                    } else {
+                        const double mu = hess_row_dot<WMAX>(i, sm.trial, ma, sm) - sm.b[i];
+                        if (mu < 0.0) { bad = true; sm.inA[i] = 1; }
+                    }
+                }
+                if (block_count<THREADS>(bad, sm) == 0) { pdas_ok = true; break; }
             }
-            if (block_count<THREADS>(bad, sm) == 0) { pdas_ok = true; break; }
+
         }
 
         PHASE(2);

@@ -697,7 +697,7 @@ __global__ void __launch_bounds__(256) qp_init_kernel(QpParams P, int max_warp_n
         m = min(m, kWMax);
     }
     __syncwarp();
-    int cl = (n <= max_warp_n && m <= P.warp_m_max) ? 0 : 1;
+    int cl = (n <= max_warp_n && m <= (n <= 128 ? P.warp_m_max : P.warp_m_max_big)) ? 0 : 1;
     while (cl < kQpClasses - 1 && m > qp_class_cap(cl)) ++cl;
 
     // g = [z - R_W lam]_+

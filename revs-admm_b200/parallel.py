@@ -8,6 +8,8 @@ global convergence test -- three scalars (residual sums and the home-hour count)
 with one all-reduce (NCCL over NVLink on GPUs, gloo in the CPU tests).  With tol <= 0 (the
 reference's fixed iteration count) even that is only needed for reporting.
 """
+import os
+
 import numpy as np
 
 
@@ -81,6 +83,11 @@ class PipelinedSolver:
         self.parts = [Solver(self.sizes[a:b], T, device=device) for a, b in self.cuts]
         self.rows = [(int(self.off[a]), int(self.off[b])) for a, b in self.cuts]
         self.pool = ThreadPoolExecutor(max_workers=len(self.parts))
+        if len(self.parts) > 1 and os.environ.get("REVS_PIPELINE_PRIORITY", "0") != "0":
+            # optional (REVS_PIPELINE_PRIORITY=1; measured: no gain): earlier pipelines are served first, so their download
+            # would overlap the compute of the later ones in schedule()
+            for k, p in enumerate(self.parts):
+                p.set_option("priority", k)
 
     # ---- plumbing
     def _each(self, fn, concurrent=True):
@@ -124,6 +131,42 @@ class PipelinedSolver:
     # ---- solves
     def solve_admm(self, concurrent=True, **kw):
         return max(self._each(lambda k: self.parts[k].solve_admm(**kw), concurrent=concurrent))
+
+    def schedule(self, trees, homes, cost, out=None, **admm):
+        """Host buffers in, host results out -- the whole path of lpsolver.solve_ADMM for this GPU's
+        zones.  Every pipeline runs upload -> solve -> download on its own thread; uploads and
+        downloads take the PCIe link one pipeline at a time (in pipeline order), so the copies of one
+        pipeline overlap the compute of the others instead of sharing the link three ways."""
+        import threading
+        H, T = self.H, self.T
+        iters = int(admm.get("iter_max", 15))
+        if out is None:
+            out = dict(P_sch=np.empty((H, T)), P_ev=np.empty((H, T)), SOC=np.empty((H, T + 1)), diff=np.empty((iters, H)))
+        D = out.get("diff")
+        turn = [threading.Event() for _ in range(len(self.parts) + 1)]
+        turn[0].set()
+        d2h = threading.Lock()
+
+        def f(k):
+            lo, hi = self.rows[k]
+            a, b = self.cuts[k]
+            turn[k].wait()
+            try:
+                self.parts[k].set_feeder_trees(trees[a:b])
+                self.parts[k].set_homes(**{n: v[lo:hi] for n, v in homes.items()})
+                self.parts[k].set_tariff(cost)
+            finally:
+                turn[k + 1].set()
+            done = self.parts[k].solve_admm(**admm)
+            sub = dict(P_sch=out["P_sch"][lo:hi], P_ev=out["P_ev"][lo:hi], SOC=out["SOC"][lo:hi],
+                       diff=np.empty((iters, hi - lo)) if D is not None else None)
+            with d2h:
+                self.parts[k].results(iters, want_diff=D is not None, out=sub)
+            if D is not None:
+                D[:iters, lo:hi] = sub["diff"]
+            return done
+        self._each(f)
+        return dict(P_sch=out["P_sch"], P_ev=out["P_ev"], SOC=out["SOC"], diff=D)
 
     def results(self, iters=None, want_diff=True, out=None):
         H, T = self.H, self.T
