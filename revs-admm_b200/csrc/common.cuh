@@ -10,7 +10,9 @@ constexpr int kWMax = 128;      // largest working set of a (feeder,hour) utilit
 constexpr int kAddMax = 32;     // violated voltage rows admitted per working-set round
 constexpr int kWW = 16;         // working-set capacity of the warp-per-column QP kernel
 constexpr int kQpClasses = 4;   // utility QP instantiations: 0 = warp kernel, 1..3 = CTA kernels by capacity
-constexpr int kQpLists = 12;    // work lists: classes 1..3 at [1..3], the warp kernel's buckets at [4..7] (zones <= 128) and [8..11] (<= 256)
+constexpr int kQpLists = 13;    // work lists: classes 1..3 at [1..3], the warp kernels' buckets at [4..7] (zones <= 128) and [8..11] (<= 256),
+                                // [12] = columns the one-row kernel passes on to the general warp kernel
+constexpr int kListLeftover = 12;
 constexpr int kWarpMaxN = 256;  // largest zone the warp-per-column QP kernel takes
 __host__ __device__ constexpr int qp_class_cap(int cls) { return cls == 0 ? kWW : (cls == 1 ? 32 : (cls == 2 ? 64 : kWMax)); }
 

@@ -88,6 +88,8 @@ struct QpParams {
     const int* order_count;   // [kQpLists + 1]
     int4* order4;          // warp-kernel lists [kQpLists - kQpClasses][ncols]: {column, first home, n | ld << 16, R offset / 16}
     int sweep;             // 1: this launch only takes columns handed over during the current round
+    int list0, nlists;     // work lists [list0, list0 + nlists) this launch of a warp kernel drains (one queue) ...
+    int list_extra;        // ... followed by this list (-1: none)
     int warp_m_max;        // warm working sets above this size start in class 1 (qp_init_kernel)
     int warp_m_max_big;    // the same for zones of more than 128 residences (longer columns)
     int ncols;
@@ -107,6 +109,9 @@ cudaError_t launch_qp_init(const QpParams& P, int max_warp_n, cudaStream_t strea
 int qp_warp_ctas_per_sm();
 int qp_warp_m_max_default();
 cudaError_t launch_utility_qp_warp(const QpParams& P, int nj, int ctas_per_sm, cudaStream_t stream);
+// one-row columns of the small zones (lists kQpClasses+2, +3): everything in registers, high occupancy;
+// columns that turn out to need more are appended to list kListLeftover for the general kernel
+cudaError_t launch_utility_qp_fast(const QpParams& P, cudaStream_t stream);
 // mode 0: first round of a solve (columns without multipliers and without screening candidates finish here);
 // mode 1: later rounds (every running column); mode 2: sweep (columns handed over in this round)
 cudaError_t launch_order_columns(const QpParams& P, int mode, int* order, int* order_count, cudaStream_t stream);

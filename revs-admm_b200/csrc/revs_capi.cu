@@ -268,6 +268,9 @@ int utility_solve(revs_solver* s, bool in_loop = false) {
     Q.cand = s->screen ? s->d_cand : nullptr;
     Q.queue = s->d_order_count + kQpLists;
     Q.sweep = 0;
+    Q.list0 = kQpClasses;
+    Q.nlists = kQpBuckets;
+    Q.list_extra = -1;
     Q.warp_m_max = getenv("REVS_WARP_M_MAX") ? atoi(getenv("REVS_WARP_M_MAX")) : qp_warp_m_max_default();
     Q.warp_m_max_big = getenv("REVS_WARP_M_MAX_BIG") ? atoi(getenv("REVS_WARP_M_MAX_BIG")) : std::min(Q.warp_m_max, 5);
     if (!s->rn2_valid) {
@@ -398,18 +401,36 @@ int utility_solve(revs_solver* s, bool in_loop = false) {
             cudaStream_t sBig = split != 0 ? s->sQ[0] : s->sU;
             const int full = qp_warp_ctas_per_sm();
             const int big_nj = warp_n <= 192 ? 6 : 8;
-            if (two) {
-                if (split != 0) CU(cudaStreamWaitEvent(sBig, s->evV, 0));
-                sp = span_begin(s, 7, sBig);
-                CU(launch_utility_qp_warp(Q, big_nj, split > 0 ? split : full, sBig));
-                span_end(sp, sBig);
-                CU(cudaEventRecord(s->evQ[0], sBig));
+            const bool only_big = warp_n > 128 && !two;
+            if (two || only_big) {                                   // zones of 129..256 residences: lists 8..11
+                if (two && split != 0) CU(cudaStreamWaitEvent(sBig, s->evV, 0));
+                cudaStream_t sb = two ? sBig : s->sU;
+                Q.list0 = kQpClasses + kQpBuckets;
+                Q.nlists = kQpBuckets;
+                sp = span_begin(s, 7, sb);
+                CU(launch_utility_qp_warp(Q, big_nj, (two && split > 0) ? split : full, sb));
+                span_end(sp, sb);
+                if (two) CU(cudaEventRecord(s->evQ[0], sb));
                 s->stats.kernel_launches++;
             }
-            sp = span_begin(s, 8, s->sU);
-            CU(launch_utility_qp_warp(Q, (warp_n > 128 && !two) ? big_nj : 4, (two && split > 0) ? full - split : full, s->sU));
-            span_end(sp, s->sU);
-            s->stats.kernel_launches++;
+            if (!only_big) {
+                // small zones: the one-row kernel first (short columns, twice the occupancy), then the general
+                // kernel for the columns with two or more stored rows (hardest first) and what the first passed on
+                static const bool use_fast = !(getenv("REVS_NO_FAST") && atoi(getenv("REVS_NO_FAST")));
+                const int small_ctas = (two && split > 0) ? full - split : full;
+                sp = span_begin(s, 8, s->sU);
+                if (use_fast) {
+                    CU(launch_utility_qp_fast(Q, s->sU));
+                    s->stats.kernel_launches++;
+                }
+                Q.list0 = kQpClasses;
+                Q.nlists = use_fast ? 2 : kQpBuckets;
+                Q.list_extra = use_fast ? kListLeftover : -1;
+                CU(launch_utility_qp_warp(Q, 4, small_ctas, s->sU));
+                Q.list_extra = -1;
+                s->stats.kernel_launches++;
+                span_end(sp, s->sU);
+            }
             if (two) CU(cudaStreamWaitEvent(s->sU, s->evQ[0], 0));
         }
         for (int cl = 1; cl < kQpClasses; ++cl)

@@ -734,22 +734,27 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, kCtasPerSm) utility_qp_warp
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     WarpSmem& sm = reinterpret_cast<WarpSmem*>(smem_raw)[wib];
-    // four bucket lists (|W| >= 3, 2, 1, 0) per zone-size group form one queue, hardest columns first
-    constexpr int kList0 = kQpClasses + (NJ == 4 ? 0 : kQpBuckets);
+    // the bucket lists [list0, list0 + nlists) (hardest first), then list_extra, form one queue
+    const int l0 = P.list0, nl = P.nlists;
     int cnt[kQpBuckets], total = 0;
 #pragma unroll
-    for (int b = 0; b < kQpBuckets; ++b) { cnt[b] = P.order_count[kList0 + b]; total += cnt[b]; }
+    for (int b = 0; b < kQpBuckets; ++b) {
+        const int li = b < nl ? l0 + b : ((b == nl && P.list_extra >= 0) ? P.list_extra : -1);
+        cnt[b] = li >= 0 ? P.order_count[li] : 0;
+        total += cnt[b];
+    }
     WarpStats st;
     for (;;) {
         int slot = 0;
-        if (lane == 0) slot = atomicAdd(P.queue + kList0, 1);
+        if (lane == 0) slot = atomicAdd(P.queue + l0, 1);
         slot = __shfl_sync(0xffffffffu, slot, 0);
         if (slot >= total) break;
         int b = 0;
 #pragma unroll
         for (int bb = 0; bb < kQpBuckets - 1; ++bb)
             if (b == bb && slot >= cnt[bb]) { slot -= cnt[bb]; ++b; }
-        const int4 ent = P.order4[(size_t)(kList0 - kQpClasses + b) * P.ncols + slot];
+        const int li = b < nl ? l0 + b : P.list_extra;
+        const int4 ent = P.order4[(size_t)(li - kQpClasses) * P.ncols + slot];
         solve_column<NJ>(P, ent, sm, st);
         ++st.cols;
         __syncwarp();
@@ -762,6 +767,218 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, kCtasPerSm) utility_qp_warp
         if (st.handed) { atomicAdd(P.n_running, st.handed); atomicAdd(P.n_cls + 1, st.handed); }
         if (st.deferred) { atomicAdd(P.n_running, st.deferred); atomicAdd(P.n_cls + 0, st.deferred); }
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// One-row columns of the small zones (stored working set of 0 or 1 rows: 85 % of the columns that
+// need a QP kernel).  The whole column lives in ~60 registers per lane -- z, the single working
+// row of R, the voltage bounds -- so twice as many columns are resident per SM as in the general
+// kernel, and the code is a tenth of its size.  Handled here: no violated row (clean), or exactly
+// one binding row before and after the solve (monotone Newton on v(lam) = u, then the same
+// in-kernel verification as the general kernel).  Anything else -- a second violated row, a
+// returning column -- is appended, untouched, to the leftover list for the general kernel.
+constexpr int kFastWarps = 8;
+
+__global__ void __launch_bounds__(32 * kFastWarps, 4) utility_qp_fast_kernel(QpParams P) {
+    constexpr int NJ = 4;
+    const int lane = threadIdx.x & 31;
+    const unsigned full = 0xffffffffu;
+    const int l0 = kQpClasses + 2;
+    const int c1 = P.order_count[l0], total = c1 + P.order_count[l0 + 1];
+    const double u = P.u, tol = P.tol, thr = (1.0 - kScreenMargin) * u;
+    unsigned long long its_sum = 0;
+    double flops = 0.0;
+    int cols = 0, passed = 0, maxws = 0;
+    for (;;) {
+        int slot = 0;
+        if (lane == 0) slot = atomicAdd(P.queue + l0, 1);
+        slot = __shfl_sync(full, slot, 0);
+        if (slot >= total) break;
+        const int4 ent = slot < c1 ? P.order4[(size_t)(l0 - kQpClasses) * P.ncols + slot]
+                                   : P.order4[(size_t)(l0 + 1 - kQpClasses) * P.ncols + slot - c1];
+        const int c = ent.x, n = ent.z & 0xffff, ld = ent.z >> 16;
+        const size_t hoff = (size_t)ent.y;
+        const double* __restrict__ R = P.Rpool + ((size_t)ent.w << 4);
+        const size_t col = (size_t)(c % P.T) * P.Hp + hoff;
+        const double* z = P.z_t + col;
+        double* lam_g = P.lam_t + col;
+        int* widx = P.widx + (size_t)c * kWMax;
+        const int m_old = P.wcount[c];
+        const int solved_before = P.inner_ok[c];
+        const int w0 = widx[0];                          // valid if m_old == 1
+        ++cols;
+
+        double zj[NJ], rj[NJ], vub[NJ], gj[NJ];
+        unsigned candk = 0;
+        {
+            const float* v32 = P.v32_t ? P.v32_t + col : nullptr;
+            const double* v64 = P.v_t + col;
+#pragma unroll
+            for (int k = 0; k < NJ; ++k) {
+                const int j = lane + 32 * k;
+                const bool in = j < n;
+                zj[k] = in ? z[j] : 0.0;
+                if (v32) {
+                    const double a = in ? (double)v32[j] : 0.0;
+                    vub[k] = kScreenUp * a;
+                    if (in && a > thr) candk |= 1u << k;
+                } else {
+                    vub[k] = in ? v64[j] : 0.0;
+                }
+            }
+        }
+        auto pass_on = [&]() {                           // untouched: the general kernel redoes the column
+            if (lane == 0) {
+                const int pos = atomicAdd(const_cast<int*>(P.order_count) + kListLeftover, 1);
+                P.order4[(size_t)(kListLeftover - kQpClasses) * P.ncols + pos] = ent;
+            }
+            ++passed;
+        };
+        if (m_old > 1 || solved_before != 0) { pass_on(); continue; }
+        int i0 = -1;                                     // the working row
+        double lam_old = 0.0;
+        if (m_old == 1) {
+            lam_old = lam_g[w0];
+            if (lam_old > 0.0) i0 = w0; else lam_old = 0.0;
+        }
+        // stored iterate g = [z - r lam_old]_+ (qp_init_kernel / dual_update_kernel wrote exactly this)
+#pragma unroll
+        for (int k = 0; k < NJ; ++k) {
+            const int j = lane + 32 * k;
+            rj[k] = (i0 >= 0 && j < n) ? R[(size_t)i0 * ld + j] : 0.0;
+            gj[k] = fmax(zj[k] - rj[k] * lam_old, 0.0);
+        }
+        if (i0 >= 0 && (i0 & 31) == lane) candk &= ~(1u << (i0 >> 5));
+        recheck_rows<NJ>(candk, R, ld, n, gj, vub);
+        // violated rows outside W (vub is exact wherever it exceeds u)
+        double best = -1.0;
+        int bj = 0x7fffffff, nviol = 0;
+#pragma unroll
+        for (int k = 0; k < NJ; ++k) {
+            const int j = lane + 32 * k;
+            const double viol = vub[k] - u;
+            if (j < n && j != i0 && viol > tol) { ++nviol; if (viol > best) { best = viol; bj = j; } }
+        }
+        nviol = __reduce_add_sync(full, nviol);
+        if (nviol > 1 || (nviol == 1 && i0 >= 0)) { pass_on(); continue; }
+        if (nviol == 1) {                                // admit the one violated row
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ob = __shfl_xor_sync(full, best, o);
+                const int oj = __shfl_xor_sync(full, bj, o);
+                if (ob > best || (ob == best && oj < bj)) { best = ob; bj = oj; }
+            }
+            i0 = bj;
+#pragma unroll
+            for (int k = 0; k < NJ; ++k) {
+                const int j = lane + 32 * k;
+                rj[k] = j < n ? R[(size_t)i0 * ld + j] : 0.0;
+            }
+        }
+        double l = lam_old;
+        int its = 0;
+        bool ok = i0 < 0;                                // nothing to solve: g = [z]_+ is the projection
+        if (i0 >= 0) {
+#pragma unroll 1
+            for (int it = 0; it < 48; ++it) {
+                double v = 0.0, S = 0.0;
+#pragma unroll
+                for (int k = 0; k < NJ; ++k) {
+                    const double gk = fmax(zj[k] - rj[k] * l, 0.0);
+                    gj[k] = gk;
+                    v = fma(rj[k], gk, v);
+                    if (gk > 0.0) S = fma(rj[k], rj[k], S);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    v += __shfl_xor_sync(full, v, o);
+                    S += __shfl_xor_sync(full, S, o);
+                }
+                ++its;
+                const double fr = v - u;
+                if ((l > 0.0 ? fabs(fr) : fmax(fr, 0.0)) < tol) { ok = true; break; }
+                double ln = S > 0.0 ? l + fr / S : 0.0;
+                if (ln < 0.0) ln = 0.0;
+                if (ln == l) break;
+                l = ln;
+            }
+            flops += 4.0 * n * its;
+        }
+        if (!ok) { pass_on(); continue; }
+        // verification of the other rows for the new g: monotone bound, exact recheck of the rest
+        double dp = 0.0;
+#pragma unroll
+        for (int k = 0; k < NJ; ++k) dp += fmax(gj[k] - fmax(zj[k] - rj[k] * lam_old, 0.0), 0.0);   // lam_old = 0 for a newly admitted row
+        dp = warp_sum(dp) * (1.0 + 1e-9);
+        candk = 0;
+        {
+            const double* rmax = P.rmax + hoff;
+            int ncand = 0;
+#pragma unroll
+            for (int k = 0; k < NJ; ++k) {
+                const int j = lane + 32 * k;
+                if (j < n && j != i0) {
+                    const double bnd = dp > 0.0 ? fma(rmax[j], dp, vub[k]) : vub[k];
+                    if (bnd - u > tol) { candk |= 1u << k; ++ncand; }
+                    else vub[k] = bnd;
+                }
+            }
+            flops += 2.0 * n * __reduce_add_sync(full, ncand);
+        }
+        recheck_rows<NJ>(candk, R, ld, n, gj, vub);
+        bool viol = false;
+#pragma unroll
+        for (int k = 0; k < NJ; ++k) {
+            const int j = lane + 32 * k;
+            viol |= j < n && j != i0 && vub[k] - u > tol;
+        }
+        if (__any_sync(full, viol)) { pass_on(); continue; }       // a second row binds: general kernel
+
+        // persist
+        const bool changed = (i0 >= 0) && (l != lam_old || nviol == 1);
+        const int m_new = i0 >= 0 ? 1 : 0;
+        if (lane == 0) {
+            if (m_old == 1) lam_g[w0] = 0.0;
+            if (i0 >= 0) { lam_g[i0] = l; widx[0] = i0; }
+            P.wcount[c] = m_new;
+            P.inner_ok[c] = 1;
+            P.status[c] = 1;
+        }
+        if (changed) {
+            double* g = P.g_t + col;
+            __nv_bfloat16* gbf = P.gbf_t ? reinterpret_cast<__nv_bfloat16*>(P.gbf_t) + col : nullptr;
+#pragma unroll
+            for (int k = 0; k < NJ; ++k) {
+                const int j = lane + 32 * k;
+                if (j < n) {
+                    g[j] = gj[k];
+                    if (gbf) gbf[j] = __float2bfloat16_rn((float)gj[k]);
+                }
+            }
+            its_sum += (unsigned long long)its;
+        }
+        maxws = max(maxws, m_new);
+        __syncwarp();
+    }
+    if (lane == 0) {
+        if (its_sum) atomicAdd(P.newton_its, its_sum);
+        if (flops > 0.0) atomicAdd(P.flops, (unsigned long long)flops);
+        if (maxws) atomicMax(P.max_ws, maxws);
+        if (cols - passed > 0) atomicAdd(P.cols, (unsigned long long)(cols - passed));
+        if (P.dbg && passed) atomicAdd(P.dbg + 3, (unsigned long long)passed);     // debug: shown as `fallbacks`
+    }
+}
+
+cudaError_t launch_utility_qp_fast(const QpParams& P, cudaStream_t stream) {
+    static int n_sm = 0;
+    if (!n_sm) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+    }
+    utility_qp_fast_kernel<<<n_sm * 4, 32 * kFastWarps, 0, stream>>>(P);
+    return cudaGetLastError();
 }
 
 int qp_warp_max_n() { return kWarpMaxN; }
