@@ -445,9 +445,10 @@ def run_gpu(args, rank, world, local_rank):
     share = {"screen_bf16": stats_acc["gemm_ms"] / tot, "home_solve(overlapped, yielding)": stats_acc["home_ms"] / tot,
              "dual_update": stats_acc["dual_ms"] / tot,
              "utility_qp": 1.0 - (stats_acc["gemm_ms"] + stats_acc["dual_ms"]) / tot}
-    # Dominant kernel: the warp-per-column QP kernels (NJ = 4 and NJ = 6/8 instantiations of
-    # utility_qp_warp_kernel, launched as a pair once per working-set round).  achieved =
-    # algorithmic HBM bytes of the columns they solve per round / their CUDA-event span per round.
+    # Dominant kernels: the warp-per-column QP kernels (utility_qp_fast_kernel for one-row columns,
+    # utility_qp_warp_kernel<4> and <6|8> for the rest; launched as a group once per working-set
+    # round).  achieved = algorithmic HBM bytes of the columns they solve per round / their
+    # CUDA-event span per round.
     dom_name = "utility_qp_warp_kernel"
     roofline = None
     if stats_acc["qp_warp_rounds"] > 0 and stats_acc["qp_warp_ms"] > 0:
@@ -466,7 +467,7 @@ def run_gpu(args, rank, world, local_rank):
         roofline = {"kernel": dom_name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                     "traffic": traffic, "ms_per_launch_pair": ms_round, "bytes_per_launch_pair": bytes_round,
                     "launch_pairs_per_step": rounds_w / args.steps, "peak_source": peak_src,
-                    "note": "dominant kernel by time; an active-set solver, latency-bound by design (one warp per (zone,hour) column, "
+                    "note": "dominant kernel group by time (one-row kernel + general warp kernels); an active-set solver, latency-bound by design (one warp per (zone,hour) column, "
                             "rows of R served from L2): DESIGN.md section 3.  The HBM-bound kernels of the path are in `kernels` "
                             "(home_solve 0.60, dual_update 0.71 of the measured copy bandwidth)"}
     kernels.get("utility_qp", {})["share_warp_kernels"] = stats_acc["qp_warp_ms"] / max(stats_acc["total_ms_sum"], 1e-9)
