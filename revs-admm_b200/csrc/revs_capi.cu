@@ -135,6 +135,8 @@ struct revs_solver {
     int4* d_order4 = nullptr;
     Counters* d_cnt = nullptr;
     Counters* h_cnt = nullptr;           // pinned mirror
+    void* h_homes = nullptr;             // pinned staging of the per-home vectors (revs_set_homes)
+    size_t h_homes_bytes = 0;
     double* d_diff = nullptr;
     int diff_cap = 0;
     ContractProblem* d_cprob = nullptr;
@@ -237,15 +239,6 @@ int d2h_homes(const revs_solver* s, double* dst, const double* src, int w) {
     if (s->H == 0) return REVS_OK;
     CU(launch_pack_rows(src, s->d_stage, s->d_hmap, s->H, w, 0, s->sU));
     CU(cudaMemcpyAsync(dst, s->d_stage, (size_t)s->H * w * sizeof(double), cudaMemcpyDeviceToHost, s->sU));
-    return REVS_OK;
-}
-
-template <class Tp>
-int h2d_padded_vec(revs_solver* s, Tp* dst, const Tp* src, Tp fill) {
-    std::vector<Tp> tmp((size_t)s->Hp, fill);
-    for (int f = 0; f < s->nf; ++f)
-        for (int64_t i = s->off[f]; i < s->off[f + 1]; ++i) tmp[s->feeders[f].off + (i - s->off[f])] = src[i];
-    CU(cudaMemcpy(dst, tmp.data(), tmp.size() * sizeof(Tp), cudaMemcpyHostToDevice));
     return REVS_OK;
 }
 
@@ -557,6 +550,7 @@ void free_all(revs_solver* s) {
         if (t.d_res_node) cudaFree(t.d_res_node);
     }
     if (s->h_cnt) cudaFreeHost(s->h_cnt);
+    if (s->h_homes) cudaFreeHost(s->h_homes);
     for (auto& sp : s->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     if (s->evHomeDone) cudaEventDestroy(s->evHomeDone);
     if (s->evDualDone) cudaEventDestroy(s->evDualDone);
@@ -871,30 +865,49 @@ int revs_set_homes(revs_solver* s, const double* load, const uint8_t* has_ev, co
                    const double* capacity, const double* initial, const int32_t* start, const int32_t* end) {
     if (!s || !load || !has_ev) return fail(REVS_ERR_ARG, "bad arguments");
     CU(cudaSetDevice(s->device));
-    const int64_t H = s->H;
-    std::vector<double> rt(H, 0.0), cp(H, 1.0), in(H, 0.0), ic(H, 0.0);
-    std::vector<int> st(H, 0), en(H, 0), nmin(H, 0), nmax(H, 0);
-    for (int64_t i = 0; i < H; ++i) {
-        if (!has_ev[i]) continue;
-        if (!rating || !capacity || !initial || !start || !end) return fail(REVS_ERR_ARG, "EV arrays missing");
-        if (!(rating[i] > 0.0) || !(capacity[i] > 0.0)) return fail(REVS_ERR_ARG, "home %lld: rating and capacity must be positive", (long long)i);
-        rt[i] = rating[i]; cp[i] = capacity[i]; in[i] = initial[i];
-        st[i] = start[i]; en[i] = end[i];
-        count_window(rating[i], capacity[i], initial[i], &nmin[i], &nmax[i]);
-        ic[i] = -(0.99 * (rating[i] / capacity[i]));
+    const int64_t H = s->H, Hp = s->Hp;
+    // the per-home vectors go through one page-locked staging block in the padded layout, so
+    // that every copy is asynchronous and the call synchronises once
+    const size_t nd = (size_t)Hp, bytes = nd * (4 * sizeof(double) + 4 * sizeof(int)) + nd;
+    if (s->h_homes_bytes < bytes) {
+        if (s->h_homes) cudaFreeHost(s->h_homes);
+        s->h_homes = nullptr;
+        CU(cudaHostAlloc(&s->h_homes, bytes, cudaHostAllocDefault));
+        s->h_homes_bytes = bytes;
+    }
+    double* rt = reinterpret_cast<double*>(s->h_homes);
+    double *cp = rt + nd, *in = cp + nd, *ic = in + nd;
+    int* st = reinterpret_cast<int*>(ic + nd);
+    int *en = st + nd, *nmin = en + nd, *nmax = nmin + nd;
+    uint8_t* ev = reinterpret_cast<uint8_t*>(nmax + nd);
+    for (size_t i = 0; i < nd; ++i) { rt[i] = 0.0; cp[i] = 1.0; in[i] = 0.0; ic[i] = 0.0; st[i] = en[i] = nmin[i] = nmax[i] = 0; ev[i] = 0; }
+    for (int f = 0; f < s->nf; ++f) {
+        const int64_t po = s->feeders[f].off - s->off[f];       // padded index = compact index + po
+        for (int64_t i = s->off[f]; i < s->off[f + 1]; ++i) {
+            if (!has_ev[i]) continue;
+            if (!rating || !capacity || !initial || !start || !end) return fail(REVS_ERR_ARG, "EV arrays missing");
+            if (!(rating[i] > 0.0) || !(capacity[i] > 0.0)) return fail(REVS_ERR_ARG, "home %lld: rating and capacity must be positive", (long long)i);
+            const int64_t p = i + po;
+            ev[p] = 1;
+            rt[p] = rating[i]; cp[p] = capacity[i]; in[p] = initial[i];
+            st[p] = start[i]; en[p] = end[i];
+            count_window(rating[i], capacity[i], initial[i], &nmin[p], &nmax[p]);
+            ic[p] = -(0.99 * (rating[i] / capacity[i]));
+        }
     }
     int rc;
     if ((rc = h2d_homes(s, s->d_load, load, s->T))) return rc;
-    if ((rc = h2d_padded_vec<uint8_t>(s, s->d_has_ev, has_ev, 0))) return rc;
-    if ((rc = h2d_padded_vec<double>(s, s->d_rating, rt.data(), 0.0))) return rc;
-    if ((rc = h2d_padded_vec<double>(s, s->d_capacity, cp.data(), 1.0))) return rc;
-    if ((rc = h2d_padded_vec<double>(s, s->d_initial, in.data(), 0.0))) return rc;
-    if ((rc = h2d_padded_vec<double>(s, s->d_indconst, ic.data(), 0.0))) return rc;
-    if ((rc = h2d_padded_vec<int>(s, s->d_start, st.data(), 0))) return rc;
-    if ((rc = h2d_padded_vec<int>(s, s->d_end, en.data(), 0))) return rc;
-    if ((rc = h2d_padded_vec<int>(s, s->d_nmin, nmin.data(), 0))) return rc;
-    if ((rc = h2d_padded_vec<int>(s, s->d_nmax, nmax.data(), 0))) return rc;
+    CU(cudaMemcpyAsync(s->d_has_ev, ev, nd, cudaMemcpyHostToDevice, s->sU));
+    CU(cudaMemcpyAsync(s->d_rating, rt, nd * sizeof(double), cudaMemcpyHostToDevice, s->sU));
+    CU(cudaMemcpyAsync(s->d_capacity, cp, nd * sizeof(double), cudaMemcpyHostToDevice, s->sU));
+    CU(cudaMemcpyAsync(s->d_initial, in, nd * sizeof(double), cudaMemcpyHostToDevice, s->sU));
+    CU(cudaMemcpyAsync(s->d_indconst, ic, nd * sizeof(double), cudaMemcpyHostToDevice, s->sU));
+    CU(cudaMemcpyAsync(s->d_start, st, nd * sizeof(int), cudaMemcpyHostToDevice, s->sU));
+    CU(cudaMemcpyAsync(s->d_end, en, nd * sizeof(int), cudaMemcpyHostToDevice, s->sU));
+    CU(cudaMemcpyAsync(s->d_nmin, nmin, nd * sizeof(int), cudaMemcpyHostToDevice, s->sU));
+    CU(cudaMemcpyAsync(s->d_nmax, nmax, nd * sizeof(int), cudaMemcpyHostToDevice, s->sU));
     CU(cudaStreamSynchronize(s->sU));
+    (void)H;
     s->homes_set = true;
     return REVS_OK;
 }
@@ -1052,9 +1065,16 @@ int revs_get_results(const revs_solver* s, double* P_sch, double* P_ev, double* 
         const_cast<revs_solver*>(s)->stats.kernel_launches++;
         if ((rc = d2h_homes(s, SOC, s->d_soc, s->T + 1))) return rc;
     }
-    if (diff)
-        for (int k = 0; k < s->k; ++k)
-            if ((rc = d2h_homes(s, diff + (size_t)k * s->H, s->d_diff + (size_t)k * s->Hp, 1))) return rc;
+    if (diff && s->H > 0) {
+        // all iterations through the staging buffer in as few transfers as it holds (T + 1 rows each)
+        const int chunk = s->T + 1;
+        for (int k0 = 0; k0 < s->k; k0 += chunk) {
+            const int nk = std::min(chunk, s->k - k0);
+            for (int k = 0; k < nk; ++k)
+                CU(launch_pack_rows(s->d_diff + (size_t)(k0 + k) * s->Hp, s->d_stage + (size_t)k * s->H, s->d_hmap, s->H, 1, 0, s->sU));
+            CU(cudaMemcpyAsync(diff + (size_t)k0 * s->H, s->d_stage, (size_t)nk * s->H * sizeof(double), cudaMemcpyDeviceToHost, s->sU));
+        }
+    }
     CU(cudaStreamSynchronize(s->sU));
     return REVS_OK;
 }

@@ -60,6 +60,18 @@ def run_admm(stepper, kappa=5.0, iter_max=15, vset=1.0, vlow=0.95, vhigh=1.05, t
     return iter_max, history
 
 
+def _pinned_empty(shape):
+    """Page-locked host scratch (torch is only the allocator); plain numpy if torch has no CUDA."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            t = torch.empty(tuple(shape), dtype=torch.float64).pin_memory()
+            return t.numpy(), t
+    except Exception:
+        pass
+    return np.empty(shape), None
+
+
 class PipelinedSolver:
     """Several independent solver pipelines on ONE GPU.
 
@@ -83,6 +95,7 @@ class PipelinedSolver:
         self.parts = [Solver(self.sizes[a:b], T, device=device) for a, b in self.cuts]
         self.rows = [(int(self.off[a]), int(self.off[b])) for a, b in self.cuts]
         self.pool = ThreadPoolExecutor(max_workers=len(self.parts))
+        self._diff_scratch = {}
         if len(self.parts) > 1 and os.environ.get("REVS_PIPELINE_PRIORITY", "0") != "0":
             # optional (REVS_PIPELINE_PRIORITY=1; measured: no gain): earlier pipelines are served first, so their download
             # would overlap the compute of the later ones in schedule()
@@ -90,6 +103,15 @@ class PipelinedSolver:
                 p.set_option("priority", k)
 
     # ---- plumbing
+    def _diff_buf(self, k, iters):
+        """Page-locked [iters, homes of pipeline k] buffer for the per-iteration convergence values
+        (a column slice of the caller's [iters, H] array is not contiguous)."""
+        lo, hi = self.rows[k]
+        key = (k, iters)
+        if key not in self._diff_scratch:
+            self._diff_scratch[key] = _pinned_empty((iters, hi - lo))
+        return self._diff_scratch[key][0]
+
     def _each(self, fn, concurrent=True):
         if concurrent and len(self.parts) > 1:
             return list(self.pool.map(fn, range(len(self.parts))))
@@ -159,7 +181,7 @@ class PipelinedSolver:
                 turn[k + 1].set()
             done = self.parts[k].solve_admm(**admm)
             sub = dict(P_sch=out["P_sch"][lo:hi], P_ev=out["P_ev"][lo:hi], SOC=out["SOC"][lo:hi],
-                       diff=np.empty((iters, hi - lo)) if D is not None else None)
+                       diff=self._diff_buf(k, iters) if D is not None else None)
             with d2h:
                 self.parts[k].results(iters, want_diff=D is not None, out=sub)
             if D is not None:
@@ -179,7 +201,7 @@ class PipelinedSolver:
         def f(k):
             lo, hi = self.rows[k]
             sub = dict(P_sch=out["P_sch"][lo:hi], P_ev=out["P_ev"][lo:hi], SOC=out["SOC"][lo:hi],
-                       diff=np.empty((iters, hi - lo)) if D is not None else None)
+                       diff=self._diff_buf(k, iters) if D is not None else None)
             self.parts[k].results(iters, want_diff=D is not None, out=sub)
             if D is not None:
                 D[:iters, lo:hi] = sub["diff"]
