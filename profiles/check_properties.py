@@ -16,8 +16,15 @@ import revs_admm_b200 as R  # noqa: E402
 
 
 def run(workload, seed, screen=1, stepwise=False):
+    old = os.environ.get("REVS_BENCH_SEED")
     os.environ["REVS_BENCH_SEED"] = str(seed)
-    trees, hm, cost, sizes, T = bench.make_rank_problem(workload, 0)
+    try:
+        trees, hm, cost, sizes, T = bench.make_rank_problem(workload, 0)
+    finally:
+        if old is None:
+            os.environ.pop("REVS_BENCH_SEED", None)
+        else:
+            os.environ["REVS_BENCH_SEED"] = old
     with R.Solver(sizes, T) as s:
         s.set_option("screen", screen)
         s.set_feeder_trees(trees)

@@ -113,3 +113,42 @@ def test_pipeline_cuts_cover_all_zones():
         assert all(cuts[k][1] == cuts[k + 1][0] for k in range(K - 1))
         homes = [int(sizes[a:b].sum()) for a, b in cuts]
         assert max(homes) - min(homes) <= 2 * sizes.max()
+
+
+def test_objective_sandwich_lower_bound():
+    """bench.objective_check: the cost of the cheapest SOC-feasible schedule without voltage limits is a
+    lower bound of any feasible schedule's cost; the load-only schedule (no charging) is below it."""
+    import bench
+    trees, hm, cost, sizes, T = bench.make_rank_problem("tiny", 0)
+    dist, lb, viol = bench.objective_check(trees, hm, cost, hm["load"].copy(), T)
+    assert dist < lb                                   # no charging at all is cheaper than any feasible schedule
+    # a feasible schedule: every EV home charges in its n_min cheapest window hours -> cost == lower bound
+    P = hm["load"].copy()
+    step = hm["rating"] / np.maximum(hm["capacity"], 1e-300)
+    for h in np.nonzero(hm["has_ev"])[0]:
+        nmin = max(int(np.ceil((0.9 - hm["initial"][h]) / step[h] - 1e-9)), 0)
+        win = np.arange(hm["start"][h], hm["end"][h])
+        pick = win[np.argsort(np.asarray(cost)[win], kind="stable")[:nmin]]
+        P[h, pick] += hm["rating"][h]
+    dist2, lb2, _ = bench.objective_check(trees, hm, cost, P, T)
+    assert lb2 == lb and abs(dist2 - lb) <= 1e-9 * abs(lb)
+
+
+def test_pipelined_stats_combination():
+    """PipelinedSolver.stats(): counters add up, total_ms is the longest pipeline, residuals recombine as RMS."""
+    from revs_admm_b200.parallel import PipelinedSolver
+
+    class Fake:
+        def __init__(self, d): self.d = d
+        def stats(self): return dict(self.d)
+
+    ps = PipelinedSolver.__new__(PipelinedSolver)
+    ps.parts = [Fake(dict(kernel_launches=10, total_ms=3.0, admm_iterations=5, max_working_set=4, primal_residual=1.0, dual_residual=2.0, qp_ms=1.5)),
+                Fake(dict(kernel_launches=7, total_ms=4.0, admm_iterations=5, max_working_set=9, primal_residual=3.0, dual_residual=0.0, qp_ms=0.5))]
+    ps.rows = [(0, 100), (100, 400)]
+    st = ps.stats()
+    assert st["kernel_launches"] == 17 and st["total_ms"] == 4.0 and st["total_ms_sum"] == 7.0 and st["max_working_set"] == 9
+    assert st["pipelines"] == 2 and st["qp_ms"] == 2.0
+    assert abs(st["primal_residual"] - np.sqrt((1.0 * 100 + 9.0 * 300) / 400)) < 1e-12
+    ps.parts = []          # nothing to close
+    ps.pool = None
