@@ -40,3 +40,26 @@ def gpu_lib():
     if r.device_count() < 1:
         pytest.fail("no CUDA device visible")
     return r
+
+
+def _case(adoption, rating):
+    from revs_admm_b200.revs_fixture import REVS
+    fx = REVS(data_path=INPUT, out_path="/tmp/revs_out", grb_path="/tmp/revs_grb",
+              fig_path="/tmp/revs_fig", regionID=121, networkID=121144, comunityID=2,
+              optimizer_mode="individual")
+    tariff, homes, dist, saved = fx.read_inputs(adoption=adoption, rating=rating, seed=1234, capacity=20,
+                                                initial_soc=0.2, start_time=11, end_time=23,
+                                                shift_time=6)
+    return dict(fx=fx, tariff=tariff, homes=homes, dist=dist, saved=saved)
+
+
+@pytest.fixture(scope="session")
+def case_adopt70():
+    """Second reference run shipped in out/121144-com2/individual: 70 % adoption, 4800 W."""
+    return _case(70, 4800)
+
+
+@pytest.fixture(scope="session")
+def case_rating3600():
+    """Third reference run shipped in out/121144-com2/individual: 90 % adoption, 3600 W."""
+    return _case(90, 3600)

@@ -13,7 +13,8 @@ committed so that nothing at test/bench time reads /root/reference.
         by shift_time=6 and converted kW -> W, i.e. the inverse of
         extract.py:34-54 (GetHomeLoad).
   tests/golden/ref_out_121144_com2.npz         the reference's result files
-        out/121144-com2/{individual,centralized,distributed}/adopt90-rating4800-seed1234.txt
+        out/121144-com2/{individual,centralized,distributed}/adopt90-rating4800-seed1234.txt,
+        individual/adopt90-rating3600-seed1234.txt and individual/adopt70-rating4800-seed1234.txt
         parsed into arrays (home ids, P_res, P_ev, SOC, per-iteration diff).
 """
 import os
@@ -72,6 +73,12 @@ def main():
     out["individual3600_ev_ids"] = ev
     out["individual3600_P_ev"] = np.array([s["EV Charger Usage Profile"][h] for h in ev])
     out["individual3600_SOC"] = np.array([s["EV Charger State of Charge Profile"][h] for h in ev])
+    # ... and one with 70 % adoption: pins the seeded EV-home draw at a second adoption level
+    s = parse_result(os.path.join(base, "individual", "adopt70-rating4800-seed1234.txt"))
+    ev = np.array(list(s["EV Charger Usage Profile"]), dtype=np.int64)
+    out["individual70_ev_ids"] = ev
+    out["individual70_P_ev"] = np.array([s["EV Charger Usage Profile"][h] for h in ev])
+    out["individual70_SOC"] = np.array([s["EV Charger State of Charge Profile"][h] for h in ev])
     np.savez_compressed(os.path.join(HERE, "ref_out_121144_com2.npz"), **out)
 
     # reconstruct the home-load CSV (hid,hour1..hour24 in W, un-shifted)

@@ -110,6 +110,26 @@ def test_individual_matches_oracle_and_golden_objective(gpu_lib, case121144, gol
         assert abs(obj - obj_gold) <= 1e-6 * abs(obj_gold)
 
 
+@pytest.mark.parametrize("which", ["individual70", "individual3600"])
+def test_individual_matches_other_reference_runs(gpu_lib, which, case_adopt70, case_rating3600, golden):
+    """Device individual optimum against the two further result files of the reference
+    (70 % adoption; 3600 W chargers): identical to the oracle, objective equal to the reference's."""
+    from revs_admm_b200.lpsolver import solve_residences
+    case = case_adopt70 if which == "individual70" else case_rating3600
+    homes, tariff = case["homes"], case["tariff"]
+    Pev, soc, Pres = solve_residences(tariff, homes)
+    c = np.asarray(tariff)
+    for k, h in enumerate(golden[f"{which}_ev_ids"]):
+        h = int(h)
+        po, so, go = O.solve_residence(tariff, homes[h])
+        assert np.array_equal(Pev[h], po)
+        gold_p, gold_s = golden[f"{which}_P_ev"][k], golden[f"{which}_SOC"][k]
+        load = Pres[h] - Pev[h]
+        obj = 0.01 * c @ Pres[h] + 0.99 * (1 - soc[h][-1])
+        obj_gold = 0.01 * c @ (load + gold_p) + 0.99 * (1 - gold_s[-1])
+        assert abs(obj - obj_gold) <= 1e-9 * abs(obj_gold)
+
+
 # ----------------------------------------------------------------- utility step
 def _rand_state(H, T, load, seed):
     rng = np.random.default_rng(seed)

@@ -170,3 +170,27 @@ def test_reliability_check_matches_reference_formula(case121144, golden):
     sub_edges = [e for e in dist.edges if dist.nodes[e[0]]["label"] == "S" or dist.nodes[e[1]]["label"] == "S"]
     s = sum(np.abs(F[e]) * O.LINE_RATING[dist.edges[e]["type"]] for e in sub_edges)
     assert np.abs(s - tot).max() < 1e-8
+
+
+@pytest.mark.parametrize("which", ["individual70", "individual3600"])
+def test_other_reference_runs_pin_draw_and_individual_optimum(which, case_adopt70, case_rating3600, golden):
+    """The two further result files the reference ships (70 % adoption; 3600 W chargers): the seeded
+    EV-home draw of the fixture must select exactly the reference's EV homes, in the reference's
+    order, and the individual optimum of every one of them must reach the reference's objective and
+    final SOC (charging hours may differ only where tariffs tie)."""
+    case = case_adopt70 if which == "individual70" else case_rating3600
+    rate = 4.8 if which == "individual70" else 3.6
+    homes, tariff, saved = case["homes"], case["tariff"], case["saved"]
+    assert [int(h) for h in saved["ev_homes"]] == [int(h) for h in golden[f"{which}_ev_ids"]]     # draw order = file order
+    assert sorted(h for h in homes if homes[h]["EV"]) == sorted(int(h) for h in golden[f"{which}_ev_ids"])
+    c = np.asarray(tariff)
+    n_hours = O.count_window(rate, 20.0, 0.2)[0]
+    for k, h in enumerate(golden[f"{which}_ev_ids"]):
+        h = int(h)
+        p, s, g = O.solve_residence(tariff, homes[h])
+        gp, gs = golden[f"{which}_P_ev"][k], golden[f"{which}_SOC"][k]
+        load = np.asarray(homes[h]["LOAD"])
+        assert abs((0.01 * c @ (load + p) + 0.99 * (1 - s[-1])) - (0.01 * c @ (load + gp) + 0.99 * (1 - gs[-1]))) < 1e-12
+        assert abs(s[-1] - gs[-1]) < 1e-12
+        assert (p > 1e-9).sum() == (gp > 1e-9).sum() == n_hours and np.allclose(gp[gp > 1e-9], rate)
+        assert np.abs(O.soc_profile(gp, 20.0, 0.2) - gs).max() < 1e-12
