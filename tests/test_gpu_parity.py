@@ -90,6 +90,27 @@ def test_home_step_infeasible_is_an_error(gpu_lib):
         assert e.value.code == 3
 
 
+# ----------------------------------------------------------------- other communities / adoption / rating (BASELINE config 2)
+@pytest.mark.parametrize("com,adoption,rating", [(1, 30, 3600), (4, 60, 4800), (5, 90, 3600)])
+def test_sweep_points_match_oracle(gpu_lib, com, adoption, rating):
+    """Points of the community x adoption x rating sweep on the reference's feeder (all 30 points:
+    profiles/run_config1_sweep.py): the distributed schedule equals the oracle's."""
+    from conftest import INPUT
+    from revs_admm_b200.lpsolver import solve_ADMM
+    from revs_admm_b200.revs_fixture import REVS
+    fx = REVS(data_path=INPUT, out_path="/tmp/revs_out", grb_path="/tmp/revs_grb", fig_path="/tmp/revs_fig",
+              regionID=121, networkID=121144, comunityID=com, optimizer_mode="distributed")
+    tariff, homes, dist, saved = fx.read_inputs(adoption=adoption, rating=rating, seed=1234)
+    kw = dict(kappa=5.0, iter_max=15, vset=1.03, vlow=0.95, vhigh=1.05)
+    diff, P, S, C = solve_ADMM(homes, dist, tariff, None, **kw)
+    do, Po, So, Co = O.solve_ADMM(homes, dist, tariff, None, **kw)
+    assert len(saved["ev_homes"]) == int(adoption * 1e-2 * len(saved["community"]))
+    assert all(np.array_equal(S[h], So[h]) for h in So)
+    assert max(np.abs(P[h] - Po[h]).max() for h in Po) <= 1e-4
+    assert max(abs(diff[k][h] - do[k][h]) for k in do for h in do[k]) <= 1e-7
+    assert max(np.abs(C[h] - Co[h]).max() for h in Co) <= 1e-12
+
+
 # ----------------------------------------------------------------- individual optimum
 def test_individual_matches_oracle_and_golden_objective(gpu_lib, case121144, golden):
     from revs_admm_b200.lpsolver import solve_residences
