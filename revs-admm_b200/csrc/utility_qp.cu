@@ -21,12 +21,15 @@
 //      Cholesky of H_AA, the sequential part inside one warp); search phi along the segment
 //      to that minimiser.  If the active-set guesses cycle, take a projected-Newton arc step
 //      with a Levenberg-Marquardt shift instead.
-// and the host alternates it with the contraction until no column has a violated row.
+// Zones of up to 512 residences then recompute the voltages of ALL rows exactly for the new g
+// (a warp per four rows) and go back to 2 inside the same launch; for larger zones the host
+// alternates the launch with the screening contraction until no column has a violated row.
+// The CTAs are persistent and pull columns from a per-class device queue.
 //
 // Three instantiations share the code (classes 1-3): |W| <= 32 (128 threads, ~30 KB of shared
 // memory, 6 CTAs per SM), |W| <= 64 (256 threads, ~73 KB, 3 per SM) and |W| <= 128 (256
-// threads, ~210 KB, 1 per SM).  Class 0 is the warp-per-column kernel of utility_qp_warp.cu
-// for small columns.  A column carries a class flag; qp_init_kernel classifies it by the size
+// threads, ~210 KB, 1 per SM); the first runs its active-set guesses in one warp (pdas_warp).
+// Class 0 is the warp-per-column path of utility_qp_warp.cu for small columns.  A column carries a class flag; qp_init_kernel classifies it by the size
 // of its warm-start set and a kernel hands it to the next class when it outgrows its own.
 #include <algorithm>
 

@@ -24,8 +24,17 @@
 // Nothing is written until the column is finished; a column that outgrows 16 rows, cycles or
 // fails a line search is handed, untouched, to the CTA kernel of the next class (same round).
 //
-// qp_init_kernel (also one warp per column, any size) starts a utility solve: working set =
-// support of the stored multipliers, class by its size, g = [z - R lam]_+ for the new target.
+// Three kernels live in this file:
+//   utility_qp_warp_kernel<NJ>   the general kernel described above (NJ = 4: zones <= 128 residences,
+//                                NJ = 6 / 8: zones <= 192 / 256), drains a queue of work lists;
+//   utility_qp_fast_kernel       columns with a stored working set of 0 or 1 rows (85 % of the
+//                                columns that need a QP kernel): steps 1, 3 (Newton) and 4 entirely
+//                                in ~60 registers, 32 resident warps per SM; what needs a second row
+//                                is appended to the general kernel's queue;
+//   qp_init_kernel               (one warp per column, any size) starts a utility solve: working set
+//                                = support of the stored multipliers, class by its size,
+//                                g = [z - R lam]_+ for the new target (inside the ADMM loop only for
+//                                columns that carry multipliers: dual_update_kernel wrote g = [z]_+).
 #include <cstdlib>
 
 #include <cuda_bf16.h>
