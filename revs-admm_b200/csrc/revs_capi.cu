@@ -659,6 +659,8 @@ int revs_create(revs_solver** out, int device, int n_feeders, const int64_t* fee
     TRY(cudaMemset(s->d_gbf, 0, HT * 2));
     TRY(dalloc(&s->d_v32, HT));
     if (getenv("REVS_EXACT_GEMM")) s->screen = false;
+    for (int f = 0; f < n_feeders; ++f)          // the error bound of the BF16 screening pass (kScreenUp) holds up to 16384 terms
+        if (s->feeders[f].n > 16384) s->screen = false;
     TRY(dalloc(&s->d_load, HT));
     TRY(dalloc(&s->d_pest, HT));
     TRY(dalloc(&s->d_psch[0], HT));
