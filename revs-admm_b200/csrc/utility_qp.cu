@@ -499,26 +499,28 @@ __device__ bool pdas_warp(int m, double shift, S& sm, unsigned& n_pdas, double& 
                 if (lane < ma && c <= lane) LVW(lane, c) = Hij(o, oc) + (c == lane ? shift : 0.0);
             }
             __syncwarp();
-            for (int k = 0; k < ma; ++k) {                                    // Cholesky, lanes own rows
-                const double dkk = sqrt(fmax(LVW(k, k), 1e-300));
-                __syncwarp();
-                if (lane == k) LVW(k, k) = dkk;
-                double lik = 0.0;
-                if (lane > k && lane < ma) { lik = LVW(lane, k) / dkk; LVW(lane, k) = lik; }
-                __syncwarp();
-                if (lane > k && lane < ma)
-                    for (int j = k + 1; j <= lane; ++j) LVW(lane, j) = fma(-lik, LVW(j, k), LVW(lane, j));
+            double rdiag = 1.0;
+            for (int k = 0; k < ma; ++k) {                                    // Cholesky, left-looking, lanes own rows
+                double sv = 0.0;
+                if (lane >= k && lane < ma) {
+                    sv = LVW(lane, k);
+                    for (int p = 0; p < k; ++p) sv = fma(-LVW(lane, p), LVW(k, p), sv);
+                }
+                const double dkk = sqrt(fmax(__shfl_sync(full, sv, k), 1e-300));
+                const double rk = 1.0 / dkk;
+                if (lane == k) rdiag = rk;                                    // reciprocal pivots in registers
+                if (lane >= k && lane < ma) LVW(lane, k) = lane == k ? dkk : sv * rk;
                 __syncwarp();
             }
             double y = __shfl_sync(full, b, o);                               // rhs of compact row `lane`
             if (lane >= ma) y = 0.0;
             for (int k = 0; k < ma; ++k) {
-                const double yk = __shfl_sync(full, y, k) / LVW(k, k);
+                const double yk = __shfl_sync(full, y, k) * __shfl_sync(full, rdiag, k);
                 if (lane == k) y = yk;
                 if (lane > k && lane < ma) y = fma(-LVW(lane, k), yk, y);
             }
             for (int k = ma - 1; k >= 0; --k) {
-                const double xk = __shfl_sync(full, y, k) / LVW(k, k);
+                const double xk = __shfl_sync(full, y, k) * __shfl_sync(full, rdiag, k);
                 if (lane == k) y = xk;
                 if (lane < k) y = fma(-LVW(k, lane), xk, y);
             }

@@ -490,30 +490,31 @@ __device__ __forceinline__ void solve_column(const QpParams& P, const int4 ent, 
                             if (lane < ma && cidx <= lane) sm.L[lane * kHW + cidx] = sm.H[o * kHW + oc] + (cidx == lane ? shift : 0.0);
                         }
                         __syncwarp();
+                        double rdiag = 1.0;
 #pragma unroll 1
-                        for (int k2 = 0; k2 < ma; ++k2) {            // Cholesky, lanes own rows
-                            const double dkk = sqrt(fmax(sm.L[k2 * kHW + k2], 1e-300));
-                            __syncwarp();
-                            if (lane == k2) sm.L[k2 * kHW + k2] = dkk;
-                            double lik = 0.0;
-                            if (lane > k2 && lane < ma) { lik = sm.L[lane * kHW + k2] / dkk; sm.L[lane * kHW + k2] = lik; }
-                            __syncwarp();
-                            if (lane > k2 && lane < ma)
-                                for (int j2 = k2 + 1; j2 <= lane; ++j2)
-                                    sm.L[lane * kHW + j2] = fma(-lik, sm.L[j2 * kHW + k2], sm.L[lane * kHW + j2]);
+                        for (int k2 = 0; k2 < ma; ++k2) {            // Cholesky, left-looking: lanes own rows, one column
+                            double sv = 0.0;                         // per step, no stores inside the dot product
+                            if (lane >= k2 && lane < ma) {
+                                sv = sm.L[lane * kHW + k2];
+                                for (int p2 = 0; p2 < k2; ++p2) sv = fma(-sm.L[lane * kHW + p2], sm.L[k2 * kHW + p2], sv);
+                            }
+                            const double dkk = sqrt(fmax(warp_bcast(sv, k2), 1e-300));
+                            const double rk = 1.0 / dkk;
+                            if (lane == k2) rdiag = rk;              // reciprocal pivots stay in registers: no division in the solves
+                            if (lane >= k2 && lane < ma) sm.L[lane * kHW + k2] = lane == k2 ? dkk : sv * rk;
                             __syncwarp();
                         }
                         double y = warp_bcast(b, o);                   // rhs of compact row `lane`
                         if (lane >= ma) y = 0.0;
 #pragma unroll 1
                         for (int k2 = 0; k2 < ma; ++k2) {
-                            const double yk = warp_bcast(y, k2) / sm.L[k2 * kHW + k2];
+                            const double yk = warp_bcast(y, k2) * warp_bcast(rdiag, k2);
                             if (lane == k2) y = yk;
                             if (lane > k2 && lane < ma) y = fma(-sm.L[lane * kHW + k2], yk, y);
                         }
 #pragma unroll 1
                         for (int k2 = ma - 1; k2 >= 0; --k2) {
-                            const double xk = warp_bcast(y, k2) / sm.L[k2 * kHW + k2];
+                            const double xk = warp_bcast(y, k2) * warp_bcast(rdiag, k2);
                             if (lane == k2) y = xk;
                             if (lane < k2) y = fma(-sm.L[k2 * kHW + lane], xk, y);
                         }
