@@ -506,8 +506,9 @@ __device__ bool pdas_warp(int m, double shift, S& sm, unsigned& n_pdas, double& 
                     sv = LVW(lane, k);
                     for (int p = 0; p < k; ++p) sv = fma(-LVW(lane, p), LVW(k, p), sv);
                 }
-                const double dkk = sqrt(fmax(__shfl_sync(full, sv, k), 1e-300));
-                const double rk = 1.0 / dkk;
+                const double skk = fmax(__shfl_sync(full, sv, k), 1e-300);
+                const double rk = rsqrt(skk);                                 // instead of sqrt + divide
+                const double dkk = skk * rk;
                 if (lane == k) rdiag = rk;                                    // reciprocal pivots in registers
                 if (lane >= k && lane < ma) LVW(lane, k) = lane == k ? dkk : sv * rk;
                 __syncwarp();

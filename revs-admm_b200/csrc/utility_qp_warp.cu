@@ -498,8 +498,9 @@ __device__ __forceinline__ void solve_column(const QpParams& P, const int4 ent, 
                                 sv = sm.L[lane * kHW + k2];
                                 for (int p2 = 0; p2 < k2; ++p2) sv = fma(-sm.L[lane * kHW + p2], sm.L[k2 * kHW + p2], sv);
                             }
-                            const double dkk = sqrt(fmax(warp_bcast(sv, k2), 1e-300));
-                            const double rk = 1.0 / dkk;
+                            const double skk = fmax(warp_bcast(sv, k2), 1e-300);
+                            const double rk = rsqrt(skk);            // one special-function call per column instead of sqrt + divide
+                            const double dkk = skk * rk;
                             if (lane == k2) rdiag = rk;              // reciprocal pivots stay in registers: no division in the solves
                             if (lane >= k2 && lane < ma) sm.L[lane * kHW + k2] = lane == k2 ? dkk : sv * rk;
                             __syncwarp();
