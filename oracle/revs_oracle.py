@@ -59,6 +59,10 @@ ARC_MIN = 2.0 ** -20   # shortest step of the line search before falling back / 
 PDAS_MAX = 40          # active-set guesses per quadratic piece before falling back
 HESS_SHIFT = 1e-12     # relative diagonal shift of the model Hessian (keeps it positive definite)
 COUNT_TOL = 1e-9      # slack on the SOC count window (Gurobi's own FeasibilityTol is 1e-6)
+TIE_GRID = 2.0 ** 20  # hour costs are compared on a grid of 2^-20 (~1e-6, in tariff*kW): differences below it
+                      # are ties and go to the earliest hour.  The reference stops its MIQP at MIPGap 1e-4
+                      # (relative), i.e. is itself indifferent to cost differences five orders larger; the
+                      # grid makes the selection immune to the ~1e-12 noise of two QP solvers (oracle / CUDA).
 
 
 # --------------------------------------------------------------------------- network
@@ -122,7 +126,8 @@ def count_window(rating, capacity, initial):
 
 def pick_hours(delta, start, end, n_min, n_max):
     """Indices of the optimal charging hours: the n_min smallest ``delta`` inside
-    [start,end) and then more while delta<0 (ties: lowest hour first)."""
+    [start,end) and then more while delta<0 (ties on the TIE_GRID: lowest hour first)."""
+    delta = np.rint(np.asarray(delta) * TIE_GRID)   # exact: a power-of-two scale and one rounding
     T = len(delta)
     lo, hi = max(int(start), 0), min(int(end), T)
     win = np.arange(lo, hi)
@@ -305,12 +310,14 @@ def utility_subproblem(R, p_est, p_sch, gamma, kappa, vset, vlow, vhigh, lam0=No
 # --------------------------------------------------------------------------- ADMM
 def solve_ADMM_arrays(R_blocks, load, cost, ev_mask, rating, capacity, initial, start, end,
                       kappa=5.0, iter_max=15, vset=1.0, vlow=0.95, vhigh=1.05,
-                      return_history=False):
+                      return_history=False, forced_hours=None):
     """solve_ADMM (lpsolver.py:244-293) on arrays.
 
     R_blocks: list of residence sensitivity blocks, one per feeder; homes are the
     concatenation of the feeders' residences.  load [H,T]; per-home EV arrays [H].
-    Returns dict(diff [iter_max,H], P_sch, P_ev, SOC, P_est, Gamma)."""
+    Returns dict(diff [iter_max,H], P_sch, P_ev, SOC, P_est, Gamma).
+    ``forced_hours`` {(k, home): hours} overrides the selection of a home in iteration k (0-based)
+    -- used only by tests/golden/reconstruct_ties.py to replay the reference's own tie-breaks."""
     load = np.asarray(load, float)
     cost = np.asarray(cost, float)
     H, T = load.shape
@@ -338,6 +345,8 @@ def solve_ADMM_arrays(R_blocks, load, cost, ev_mask, rating, capacity, initial, 
         for i in np.nonzero(ev_mask)[0]:
             d = home_delta(cost, load[i], P_est[i], P_sch[i], Gam[i], kappa, rating[i])
             hrs = pick_hours(d, start[i], end[i], *nwin[i])
+            if forced_hours is not None and (k, int(i)) in forced_hours:
+                hrs = np.asarray(forced_hours[(k, int(i))], dtype=int)
             P_ev[i] = 0.0
             P_ev[i, hrs] = rating[i]
             P_sch_new[i] += P_ev[i]

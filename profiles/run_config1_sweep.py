@@ -47,12 +47,8 @@ def main():
                                  max_abs_ddiff=float(max(abs(diff[k][h] - do[k][h]) for k in do for h in do[k])),
                                  cost=float(sum(c @ P[h] for h in P))))
                 print(json.dumps(rows[-1]), flush=True)
-    # A home may end on different hours than the oracle only through an exact tie of two hours in the
-    # last iteration (equal tariff, symmetric iterates), which 1e-12 differences of the QP solutions
-    # break either way: the convergence values of ALL iterations still agree and the number of hours
-    # is the same.  Everything else must match to the tolerances of the parity tests.
-    ok = all(r["max_abs_ddiff"] <= 1e-7 and r["same_number_of_hours"] and r["homes_with_other_hours"] <= 2 and
-             (r["max_abs_dP_kw"] <= 1e-4 or not r["charging_hours_identical"]) for r in rows)
+    # charging hours must be identical in all 30 points (hour costs are compared on a 2^-20 grid)
+    ok = all(r["max_abs_ddiff"] <= 1e-7 and r["charging_hours_identical"] and r["max_abs_dP_kw"] <= 1e-4 for r in rows)
     print("SWEEP", "OK" if ok else "FAILED", len(rows), "points")
     if len(sys.argv) > 1:
         json.dump(rows, open(sys.argv[1], "w"), indent=1)

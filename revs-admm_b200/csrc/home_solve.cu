@@ -5,7 +5,7 @@
 // objective is separable and linear in e, and the SOC rows collapse to a window on the
 // number of charging hours, so the exact optimum is a selection: the n_min cheapest
 // hours of the plug-in window, then further hours while their cost is negative (up to
-// n_max); ties go to the earliest hour.  Lanes hold the hours (t = lane + 32 j); hours are
+// n_max); hour costs are compared on a 2^-20 grid and ties go to the earliest hour.  Lanes hold the hours (t = lane + 32 j); hours are
 // picked with warp-shuffle arg-min rounds (or a full shuffle ranking when many hours are
 // needed), no sort and no shared memory.
 //
@@ -68,7 +68,10 @@ __global__ void __launch_bounds__(256) home_solve_kernel(HomeParams P) {
                 v = __dadd_rn(__dadd_rn(x, y), c0);
             }
         }
-        d[j] = v;
+        // hour costs are compared on a grid of 2^-20 (oracle/revs_oracle.py:TIE_GRID): the scale is a
+        // power of two and rint rounds once, so the key is bit-identical with the oracle's, and the
+        // ~1e-12 noise of the utility QP cannot reorder two hours that tie mathematically
+        d[j] = v < CUDART_INF ? rint(v * 1048576.0) : v;
     }
 
     int in_window = 0;

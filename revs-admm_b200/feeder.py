@@ -183,3 +183,125 @@ def synthetic_tariff(T):
     day = np.roll(day, -6)
     sph = max(1, T // 24)
     return np.resize(np.repeat(day, sph), T) if T >= 24 else day[:T]
+
+
+def reference_shaped_feeder(n_homes, seed=0, zone_lo=157, zone_hi=297, homes_per_xfmr=2.4,
+                            r_primary=6.0e-7, r_secondary=2.2e-4, sigma_secondary=0.95, r_scale=1.0):
+    """Synthetic radial feeder with the anatomy of the reference's 121144 network (tests/golden/input):
+
+    * the substation feeds several independent voltage zones of ``zone_lo..zone_hi`` residences
+      (121144: 157, 208, 216, 248, 297),
+    * a zone is a primary tree of transformer / road nodes -- mostly a chain, with side branches,
+      40..50 levels deep, edges of ~6e-7 ohm-equivalents (121144: median 5.1e-7, max 1e-5),
+    * 2..3 residences per transformer on secondary lines (median 2.2e-4, long tail up to ~15x),
+      about half of them daisy-chained behind another residence (121144: 99 of 216 residences
+      have a residence below them).
+
+    ``r_scale`` multiplies every resistance: 1.0 reproduces the reference's own regime, in which
+    the base load alone exceeds the voltage limit u = vhigh^2 - vset^2 by 1.5x..5x in every zone
+    (ADMM then never reaches P_est = P_sch); ~0.2 gives a voltage-feasible population whose
+    limits bind only when the chargers run."""
+    rng = np.random.default_rng(seed)
+    sizes = []
+    left = int(n_homes)
+    while left > 0:
+        n = int(rng.integers(zone_lo, zone_hi + 1))
+        if left - n < zone_lo:
+            n = left if left <= zone_hi else left // 2
+        sizes.append(n)
+        left -= n
+    parent, r, res_node = [], [], []
+    for n in sizes:
+        base = len(parent)
+        n_x = max(2, int(round(n / homes_per_xfmr)))
+        # primary tree: chain with side branches
+        xp = np.empty(n_x, dtype=np.int64)
+        xp[0] = -1
+        for i in range(1, n_x):
+            xp[i] = i - 1 if rng.random() < 0.78 else int(rng.integers(0, i))
+        parent.extend([-1 if p < 0 else base + int(p) for p in xp])
+        r.extend((r_scale * r_primary * rng.lognormal(0.0, 0.6, size=n_x)).tolist())
+        # residences: every one hangs on a transformer or behind the previous residence of that transformer
+        owner = np.sort(rng.integers(0, n_x, size=n))
+        rh = r_scale * r_secondary * rng.lognormal(0.0, sigma_secondary, size=n)
+        last_of = {}
+        for j in range(n):
+            x = int(owner[j])
+            node = len(parent)
+            if x in last_of and rng.random() < 0.55:
+                parent.append(last_of[x])              # daisy chain
+            else:
+                parent.append(base + x)
+            r.append(float(rh[j]))
+            last_of[x] = node
+            res_node.append(node)
+    parent = np.asarray(parent, dtype=np.int32)
+    # topological order: parents precede children by construction (transformers of a zone first,
+    # a residence's parent is an earlier node)
+    return FeederTree(parent=parent, r=np.asarray(r, dtype=np.float64), res_node=np.asarray(res_node, dtype=np.int32),
+                      edge_sign=np.ones(len(parent)))
+
+
+# Named synthetic populations of bench.py and of the full-size tests: (homes per feeder, T, generator).
+POPULATIONS = {
+    # reference-shaped zones (157..297 residences), base load <= ~0.7 u, limits bind when the chargers run
+    "refshape": dict(homes=1000, T=96, gen=lambda n, seed: reference_shaped_feeder(n, seed=seed, r_scale=0.7)),
+    # round-1 population: zones of 43..165 residences, every lateral on the substation, base load over the limit
+    "laterals": dict(homes=1000, T=96, gen=lambda n, seed: synthetic_feeder(n, seed=seed, laterals=max(5, n // 100))),
+    # one radial feeder: trunk + laterals, a single voltage zone (BASELINE.json config 3)
+    "radial10k": dict(homes=10000, T=96, gen=lambda n, seed: radial_feeder(n, seed=seed)),
+}
+
+
+def radial_feeder(n_homes, seed=0, homes_per_xfmr=2.5, lateral_len=40, r_trunk=2.0e-7, r_primary=6.0e-7,
+                  r_secondary=2.2e-4, r_scale=1.0):
+    """A genuinely radial feeder: ONE trunk leaves the substation, laterals of ``lateral_len``
+    transformers branch off it, residences hang on the transformers.  Every pair of homes shares
+    at least the first trunk segment, so the sensitivity matrix is a single dense block."""
+    rng = np.random.default_rng(seed)
+    n_x = max(2, int(np.ceil(n_homes / homes_per_xfmr)))
+    n_lat = max(1, int(np.ceil(n_x / lateral_len)))
+    parent, r = [], []
+    for k in range(n_lat):                                   # trunk nodes 0..n_lat-1
+        parent.append(k - 1)
+        r.append(r_scale * r_trunk * rng.lognormal(0.0, 0.4))
+    xf = []
+    for k in range(n_lat):
+        prev = k
+        for i in range(min(lateral_len, n_x - k * lateral_len)):
+            parent.append(prev)
+            r.append(r_scale * r_primary * rng.lognormal(0.0, 0.6))
+            prev = len(parent) - 1
+            xf.append(prev)
+    owner = np.sort(rng.integers(0, len(xf), size=n_homes))
+    rh = r_scale * r_secondary * rng.lognormal(0.0, 0.95, size=n_homes)
+    res_node = []
+    for j in range(n_homes):
+        parent.append(xf[int(owner[j])])
+        r.append(float(rh[j]))
+        res_node.append(len(parent) - 1)
+    return FeederTree(parent=np.asarray(parent, dtype=np.int32), r=np.asarray(r, dtype=np.float64),
+                      res_node=np.asarray(res_node, dtype=np.int32), edge_sign=np.ones(len(parent)))
+
+
+def population(name, n_feeders, seed=0, split=True, first_feeder=0):
+    """Feeders ``first_feeder .. first_feeder + n_feeders - 1`` of population ``name`` with draw ``seed``:
+    (trees, homes dict, tariff, zone sizes, T).  With ``split`` every feeder is handed over as its
+    independent voltage zones (what lpsolver.solve_ADMM of this package does for a networkx feeder)
+    and the homes are reordered accordingly.  Feeder f of a population is the same whatever slice it
+    is generated in, so a test can compare the first feeders of the benchmark population with the oracle."""
+    spec = POPULATIONS[name]
+    n, T = spec["homes"], spec["T"]
+    feeders = [spec["gen"](n, 100003 * seed + f) for f in range(first_feeder, first_feeder + n_feeders)]
+    parts = [synthetic_homes(n, T, seed=100003 * seed + 77 + f) for f in range(first_feeder, first_feeder + n_feeders)]
+    hm = {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
+    if not split:
+        return feeders, hm, synthetic_tariff(T), [n] * n_feeders, T
+    trees, perm = [], []
+    for f, tr in enumerate(feeders):
+        for zt, homes in split_zones(tr):
+            trees.append(zt)
+            perm.append(f * n + homes)
+    perm = np.concatenate(perm)
+    hm = {k: np.ascontiguousarray(v[perm]) for k, v in hm.items()}
+    return trees, hm, synthetic_tariff(T), [t.n_res for t in trees], T
