@@ -32,38 +32,37 @@ sys.path.insert(0, ROOT)
 
 HOURS = 24.0
 WORKLOADS = {
-    # name: (feeders per GPU, homes per feeder, T)
-    "synthetic-multifeeder-125k-homes-per-gpu-x96": (125, 1000, 96),
-    "synthetic-radial-10k-homes-x96": (1, 10000, 96),
-    "synthetic-12x1000-homes-x24": (12, 1000, 24),
-    "tiny": (4, 200, 96),
+    # name: (population of revs_admm_b200/feeder.py:POPULATIONS, feeders per GPU)
+    "synthetic-refshape-125k-homes-per-gpu-x96": ("refshape", 125),      # zones of 149..297 residences, voltage-feasible base load
+    "synthetic-multifeeder-125k-homes-per-gpu-x96": ("laterals", 125),   # round-1 population: zones of 43..165, base load over the limit
+    "synthetic-radial-10k-homes-x96": ("radial10k", 1),                  # BASELINE.json config 3: one dense 10k x 10k zone
+    "synthetic-refshape-100k-homes-x96": ("refshape", 100),              # BASELINE.json config 4 (strong scaling over 2/4/8 GPUs)
+    "tiny": ("refshape", 1),
 }
 ADMM = dict(kappa=5.0, iter_max=15, vset=1.03, vlow=0.95, vhigh=1.05)   # revs_config.yaml / revs_fixture.py:245-249
 
 
-def make_rank_problem(workload, rank, split=True):
-    """Synthetic feeders + homes of this rank.  With `split` every feeder is handed to the solver
-    as its independent voltage zones (the subtrees below the substation, over which the
-    sensitivity matrix is block diagonal -- what lpsolver.solve_ADMM of this package does for a
-    networkx feeder); homes are reordered accordingly."""
-    from revs_admm_b200.feeder import split_zones, synthetic_feeder, synthetic_homes, synthetic_tariff
-    nf, n, T = WORKLOADS[workload]
-    # weak scaling = fixed work per GPU: every rank holds a copy of the same synthetic population
-    # (different random draws differ by up to 30 % in QP work); REVS_BENCH_SEED=rank restores distinct draws
-    seed_env = os.environ.get("REVS_BENCH_SEED", "0")
-    rank = rank if seed_env == "rank" else int(seed_env)
-    feeders = [synthetic_feeder(n, seed=1000 * rank + f, laterals=max(5, n // 100)) for f in range(nf)]
-    hm = synthetic_homes(nf * n, T, seed=77 + rank)
-    if not split:
-        return feeders, hm, synthetic_tariff(T), [n] * nf, T
-    trees, perm = [], []
-    for f, tr in enumerate(feeders):
-        for zt, homes in split_zones(tr):
-            trees.append(zt)
-            perm.append(f * n + homes)
-    perm = np.concatenate(perm)
-    hm = {k: np.ascontiguousarray(v[perm]) for k, v in hm.items()}
-    return trees, hm, synthetic_tariff(T), [t.n_res for t in trees], T
+def workload_shape(workload):
+    """(feeders per GPU, homes per feeder, T) of a workload."""
+    from revs_admm_b200.feeder import POPULATIONS
+    pop, nf = WORKLOADS[workload]
+    return nf, POPULATIONS[pop]["homes"], POPULATIONS[pop]["T"]
+
+
+def make_rank_problem(workload, rank, split=True, strong=None):
+    """Synthetic feeders + homes of this rank.  Every rank draws ITS OWN population (seed = rank;
+    REVS_BENCH_SEED=<int> pins one draw for all ranks).  With `split` every feeder is handed to the
+    solver as its independent voltage zones.  `strong` = (world, rank): the workload's feeders are
+    one fixed population cut into `world` contiguous shares (strong scaling)."""
+    from revs_admm_b200.feeder import population
+    pop, nf = WORKLOADS[workload]
+    seed_env = os.environ.get("REVS_BENCH_SEED", "rank")
+    if strong is not None:
+        world, r = strong
+        lo, hi = nf * r // world, nf * (r + 1) // world
+        return population(pop, hi - lo, seed=0 if seed_env == "rank" else int(seed_env), split=split, first_feeder=lo)
+    seed = rank if seed_env == "rank" else int(seed_env)
+    return population(pop, nf, seed=seed, split=split)
 
 
 def pinned_like(a):
@@ -157,27 +156,45 @@ def fp64_gemm_peak_tflops():
 
 
 # ------------------------------------------------------------------------------ CPU reference arm
-def cpu_port_sample(workload, budget_homes=None, no_split=False):
-    """One bounded sample of the workload through the CPU oracle: one synthetic feeder of the
-    workload's shape, full horizon, all 15 ADMM iterations.  Returns (home_hours/s, seconds, desc)."""
+def _cpu_feeder_job(job):
+    """One feeder of the workload through the CPU oracle (runs in a worker process, BLAS single-threaded)."""
+    workload, first, no_split = job
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import revs_oracle as O
-    from revs_admm_b200.feeder import synthetic_feeder, synthetic_homes, synthetic_tariff
-    nf, n, T = WORKLOADS[workload]
-    n_s = min(n, budget_homes or n)
-    from revs_admm_b200.feeder import split_zones
-    tree = synthetic_feeder(n_s, seed=0, laterals=max(5, n_s // 100))
-    hm = synthetic_homes(n_s, T, seed=77)
-    zones = [(tree, np.arange(n_s))] if no_split else split_zones(tree)
-    perm = np.concatenate([h for _, h in zones])
-    hm = {k: v[perm] for k, v in hm.items()}
-    Rb = [O.rmat_from_tree(z.parent, z.r)[np.ix_(z.res_node, z.res_node)] for z, _ in zones]
+    from revs_admm_b200.feeder import population
+    pop, _ = WORKLOADS[workload]
+    trees, hm, cost, sizes, T = population(pop, 1, seed=0, split=not no_split, first_feeder=first)
+    Rb = [O.rmat_from_tree(z.parent, z.r)[np.ix_(z.res_node, z.res_node)] for z in trees]
     t0 = time.perf_counter()
-    O.solve_ADMM_arrays(Rb, load=hm["load"], cost=synthetic_tariff(T), ev_mask=hm["has_ev"].astype(bool),
+    O.solve_ADMM_arrays(Rb, load=hm["load"], cost=cost, ev_mask=hm["has_ev"].astype(bool),
                         rating=hm["rating"], capacity=hm["capacity"], initial=hm["initial"],
                         start=hm["start"], end=hm["end"], **ADMM)
+    return sum(sizes), time.perf_counter() - t0
+
+
+def cpu_port_sample(workload, n_feeders=None, no_split=False, workers=None):
+    """A bounded sample of the workload through the CPU oracle with ALL host cores: the first
+    `n_feeders` feeders of the workload's population (the same feeders the GPU arm's rank 0 holds),
+    one worker process per core, feeders dealt to the workers (the ADMM loop is independent per
+    feeder), full horizon, all 15 ADMM iterations.  Returns (home_hours/s, seconds, description)."""
+    import multiprocessing as mp
+    nf, n, T = workload_shape(workload)
+    cores = os.cpu_count() or 1
+    workers = workers or cores
+    k = min(nf, n_feeders or 4 * workers)
+    jobs = [(workload, f, no_split) for f in range(k)]
+    t0 = time.perf_counter()
+    if workers > 1 and k > 1:
+        with mp.get_context("fork").Pool(min(workers, k)) as pool:
+            res = pool.map(_cpu_feeder_job, jobs, chunksize=1)
+    else:
+        res = [_cpu_feeder_job(j) for j in jobs]
     dt = time.perf_counter() - t0
-    return n_s * HOURS / dt, dt, f"1 feeder x {n_s} homes ({len(zones)} voltage zones) x {T} steps x {ADMM['iter_max']} ADMM iterations (oracle/revs_oracle.py, numpy/BLAS)"
+    homes = sum(r[0] for r in res)
+    return homes * HOURS / dt, dt, (f"first {k} of {nf} feeders x {n} homes x {T} steps x {ADMM['iter_max']} ADMM iterations "
+                                    f"(oracle/revs_oracle.py, numpy), {min(workers, k)} worker processes on {cores} cores; "
+                                    f"sum of per-feeder CPU seconds {sum(r[1] for r in res):.1f}")
 
 
 def run_reference(args, rank, world):
@@ -186,12 +203,12 @@ def run_reference(args, rank, world):
     cores = os.cpu_count() or 1
     vals, secs, desc = [], [], ""
     for i in range(args.warmup + args.steps):
-        v, dt, desc = max(cpu_port_sample(args.workload, args.cpu_sample_homes, ns) for ns in (False, True))   # the faster layout
+        v, dt, desc = cpu_port_sample(args.workload, args.cpu_sample_feeders)
         if i >= args.warmup:
             vals.append(v)
             secs.append(dt)
     value = float(np.mean(vals))
-    nf, n, T = WORKLOADS[args.workload]
+    nf, n, T = workload_shape(args.workload)
     line = {
         "impl": "reference", "metric": "home_hours_scheduled_per_sec", "value": value, "unit": "home-hours/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)),
@@ -474,12 +491,12 @@ def run_gpu(args, rank, world, local_rank):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, dt, desc = max(cpu_port_sample(args.workload, args.cpu_sample_homes, ns) for ns in (False, True))   # the faster layout
+        v, dt, desc = cpu_port_sample(args.workload, args.cpu_sample_feeders, no_split=args.no_split)
         cpu = {"value": v, "unit": "home-hours/s", "cores": os.cpu_count() or 1, "kind": "port", "sample": desc,
                "seconds": dt}
 
     if rank == 0:
-        nf, n, _ = WORKLOADS[args.workload]
+        nf, n, _ = workload_shape(args.workload)
         line = {
             "metric": "home_hours_scheduled_per_sec", "value": value, "unit": "home-hours/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -519,8 +536,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
-    ap.add_argument("--workload", default="synthetic-multifeeder-125k-homes-per-gpu-x96", choices=list(WORKLOADS))
-    ap.add_argument("--cpu-sample-homes", type=int, default=None)
+    ap.add_argument("--workload", default="synthetic-refshape-125k-homes-per-gpu-x96", choices=list(WORKLOADS))
+    ap.add_argument("--cpu-sample-feeders", type=int, default=None, help="feeders of the workload the CPU port is timed on (default: 4 per core)")
     ap.add_argument("--pipelines", type=int, default=3, help="independent stream pipelines per GPU (parallel.PipelinedSolver)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-exact", action="store_true", help="skip the extra exact-mode (FP64 contraction) solve used for the contract_f64 figure")
