@@ -39,7 +39,7 @@ WORKLOADS = {
     "synthetic-refshape-100k-homes-x96": ("refshape", 100),              # BASELINE.json config 4 (strong scaling over 2/4/8 GPUs)
     "tiny": ("refshape", 1),
 }
-ADMM = dict(kappa=5.0, iter_max=15, vset=1.03, vlow=0.95, vhigh=1.05)   # revs_config.yaml / revs_fixture.py:245-249
+ADMM = dict(kappa=5.0, iter_max=15, vset=1.03, vlow=0.95, vhigh=1.05)   # revs_config.yaml / revs_fixture.py:255-259
 
 
 def workload_shape(workload):
@@ -224,7 +224,7 @@ def run_reference(args, rank, world):
 
 def objective_check(trees, hm, cost, P_sch, T, sample_zones=64):
     """Centralized-vs-distributed cross-check without a MILP solver (the reference's solve_central,
-    lpsolver.py:466-502, minimises sum_h tariff . g_h under the SOC and voltage rows).  A rigorous
+    lpsolver.py:463-502, minimises sum_h tariff . g_h under the SOC and voltage rows).  A rigorous
     sandwich:  cost of the cheapest SOC-feasible schedule of every home WITHOUT voltage limits
     <= centralized optimum <= cost of the distributed schedule wherever that is voltage-feasible.
     Returns this rank's sums; the voltage check uses dense host matrices of a sample of zones."""

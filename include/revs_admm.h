@@ -11,17 +11,17 @@
  * Reference interface replaced by each entry point (file:line in /root/reference):
  *
  *   revs_set_sensitivity / revs_set_feeder_tree(s) lpsolver.py:17-26  compute_Rmat()
- *                                                 lpsolver.py:179-190 Utility.network()
- *   revs_set_homes / revs_set_tariff              lpsolver.py:45-62   Home.__init__ inputs
- *                                                 extract.py:77-119   get_homes_ev_param()
- *   revs_solve_admm                               lpsolver.py:244-293 solve_ADMM()
- *   revs_admm_begin / revs_admm_step              lpsolver.py:256-289 one while-iteration
- *   revs_home_step                                lpsolver.py:45-157  Home(...).solve()
- *   revs_utility_step                             lpsolver.py:160-240 Utility(...).solve()
- *   revs_solve_individual                         lpsolver.py:433-463 solve_residence()
- *   revs_reliability                              drawing.py:28-78    compute_flows(),
+ *                                                 lpsolver.py:183-194 Utility.network()
+ *   revs_set_homes / revs_set_tariff              lpsolver.py:45-58   Home.__init__ inputs
+ *                                                 extract.py:91-132   get_homes_ev_param()
+ *   revs_solve_admm                               lpsolver.py:242-290 solve_ADMM()
+ *   revs_admm_begin / revs_admm_step              lpsolver.py:254-287 one while-iteration
+ *   revs_home_step                                lpsolver.py:44-160  Home(...).solve()
+ *   revs_utility_step                             lpsolver.py:163-238 Utility(...).solve()
+ *   revs_solve_individual                         lpsolver.py:430-460 solve_residence()
+ *   revs_reliability                              drawing.py:29-78    compute_flows(),
  *                                                                     compute_voltage()
- *   revs_get_results                              lpsolver.py:292-293 return diff,P_sch,S,C
+ *   revs_get_results                              lpsolver.py:289-290 return diff,P_sch,S,C
  *   revs_set_option / revs_get_stats / revs_version / revs_last_error / revs_device_count
  *                                                 no reference counterpart (library plumbing)
  */
@@ -37,12 +37,12 @@ extern "C" {
 #define REVS_OK 0
 #define REVS_ERR_ARG 1          /* bad argument / call order                          */
 #define REVS_ERR_CUDA 2         /* CUDA error or no usable device                     */
-#define REVS_ERR_INFEASIBLE 3   /* a home sub-problem has no solution (lpsolver.py:148)*/
+#define REVS_ERR_INFEASIBLE 3   /* a home sub-problem has no solution (lpsolver.py:154)*/
 #define REVS_ERR_NOCONV 4       /* utility QP hit its iteration / working-set limit    */
 
-#define REVS_REL_VOLTAGE 0      /* out = sqrt(vset^2 - S_v P)   (drawing.py:76)        */
-#define REVS_REL_FLOW 1         /* out = scale[row] * (S_f P)   (drawing.py:57-59)     */
-#define REVS_REL_DROP 2         /* out = S_v P                  (R@P of lpsolver.py:188)*/
+#define REVS_REL_VOLTAGE 0      /* out = sqrt(vset^2 - S_v P)   (drawing.py:75)        */
+#define REVS_REL_FLOW 1         /* out = scale[row] * (S_f P)   (drawing.py:56-58)     */
+#define REVS_REL_DROP 2         /* out = S_v P                  (R@P of lpsolver.py:192)*/
 
 typedef struct revs_solver revs_solver;
 
@@ -132,9 +132,10 @@ int revs_utility_step(revs_solver* s, double kappa, double vset, double vlow, do
                       const double* lam0, double* P_est_new, double* lam_out);
 
 /* Results of the last ADMM run, to host.  Any pointer may be NULL.
- * P_sch [H,T], P_ev [H,T], SOC [H,T+1], diff [iters_done,H] (lpsolver.py:286). */
+ * P_sch [H,T], P_ev [H,T], SOC [H,T+1], diff [diff_rows,H] (lpsolver.py:284): one row per iteration
+ * that ran; REVS_ERR_ARG when diff_rows is smaller than that (nothing is written past the buffer). */
 int revs_get_results(const revs_solver* s, double* P_sch, double* P_ev, double* SOC,
-                     double* diff);
+                     double* diff, int diff_rows);
 /* Utility-side iterates of the last run: P_est [H,T], Gamma [H,T]. */
 int revs_get_estimate(const revs_solver* s, double* P_est, double* Gamma);
 
@@ -159,7 +160,9 @@ int revs_contract(int device, int M, int K, int T, const double* A, const double
 int revs_screen_contract(int device, int M, int K, int T, const double* A, const double* B, double* C,
                          int impl);
 
-/* Options: "screen" (default 1) = BF16 tensor-core screening of the voltage rows with exact
+/* Options: "graph" (default 1) = revs_solve_admm runs the whole loop from one captured CUDA graph whose loops
+ * (ADMM iterations, working-set rounds) are decided on the device; 0 = host-driven loop with CUDA-event spans per
+ * kernel family in revs_stats (profiling).  "screen" (default 1) = BF16 tensor-core screening of the voltage rows with exact
  * FP64 recheck of the candidates inside the loop; 0 = FP64 DMMA contraction of every row.
  * "screen_impl" = 0 mma.sync screening kernel, 1 tcgen05/TMEM/TMA screening kernel. */
 int revs_set_option(revs_solver* s, const char* name, double value);

@@ -7,13 +7,13 @@ product package ``revs-admm_b200`` never does.
 
 What it restates (reference file:line, /root/reference):
 
-* ``compute_Rmat``          lpsolver.py:17-26 / drawing.py:17-26
-* ``home_subproblem``       lpsolver.py:45-157  (class Home: binary charger MIQP)
-* ``utility_subproblem``    lpsolver.py:160-240 (class Utility: voltage-limited QP)
+* ``compute_Rmat``          lpsolver.py:17-26 / drawing.py:18-27
+* ``home_subproblem``       lpsolver.py:44-160  (class Home: binary charger MIQP)
+* ``utility_subproblem``    lpsolver.py:163-238 (class Utility: voltage-limited QP)
 * ``solve_ADMM_arrays`` /
-  ``solve_ADMM``            lpsolver.py:244-293 (the iteration, incl. its use of the
+  ``solve_ADMM``            lpsolver.py:242-290 (the iteration, incl. its use of the
                             *previous* P_est/P_sch/Gamma in the home step)
-* ``solve_residence``       lpsolver.py:433-463 (individual optimum)
+* ``solve_residence``       lpsolver.py:430-460 (individual optimum)
 * ``compute_voltage`` /
   ``compute_flows``         drawing.py:29-78    (LinDistFlow reliability check)
 
@@ -52,8 +52,8 @@ from __future__ import annotations
 
 import numpy as np
 
-SOC_TARGET = 0.9      # lpsolver.py:111  s[T] >= 0.9
-SOC_MAX = 1.0         # lpsolver.py:102  ub = 1.0
+SOC_TARGET = 0.9      # lpsolver.py:109  s[T] >= 0.9
+SOC_MAX = 1.0         # lpsolver.py:103  ub = 1.0
 PHI_NOISE = 1e-14     # relative rounding noise admitted by the line search of the utility QP
 ARC_MIN = 2.0 ** -20   # shortest step of the line search before falling back / raising the shift
 PDAS_MAX = 40          # active-set guesses per quadratic piece before falling back
@@ -106,7 +106,7 @@ def rmat_from_tree(parent, r):
 
 def residence_block(graph):
     """Rows/cols of R at the residences, ordered as ``[n for n in graph if label=='H']``
-    (lpsolver.py:184-185)."""
+    (lpsolver.py:188-189)."""
     nodes = [n for n in graph.nodes if graph.nodes[n]["label"] != "S"]
     res = [n for n in graph if graph.nodes[n]["label"] == "H"]
     R = compute_Rmat(graph)
@@ -117,7 +117,7 @@ def residence_block(graph):
 
 # --------------------------------------------------------------------------- home step
 def count_window(rating, capacity, initial):
-    """Number of charging hours allowed by the SOC rows (lpsolver.py:100-111)."""
+    """Number of charging hours allowed by the SOC rows (lpsolver.py:101-109)."""
     step = rating / capacity
     n_min = int(np.ceil((SOC_TARGET - initial) / step - COUNT_TOL))
     n_max = int(np.floor((SOC_MAX - initial) / step + COUNT_TOL))
@@ -143,7 +143,7 @@ def pick_hours(delta, start, end, n_min, n_max):
 def home_delta(cost, load, p_est, p_sch, gamma, kappa, rating):
     """Cost of switching the charger on in each hour, in a fixed evaluation order
     (every operation individually rounded; the CUDA kernel uses the same order)."""
-    a = gamma + (kappa / 2.0) * (p_est + p_sch)             # lpsolver.py:119-120
+    a = gamma + (kappa / 2.0) * (p_est + p_sch)             # lpsolver.py:118-119
     return rating * (cost - a) + (kappa * load) * rating + ((0.5 * kappa) * rating) * rating
 
 
@@ -151,12 +151,12 @@ def soc_profile(p, capacity, initial):
     s = np.empty(len(p) + 1)
     s[0] = initial
     for t in range(len(p)):
-        s[t + 1] = s[t] + p[t] / capacity                    # lpsolver.py:109
+        s[t + 1] = s[t] + p[t] / capacity                    # lpsolver.py:108
     return s
 
 
 def home_subproblem(cost, load, ev, p_est, p_sch, gamma, kappa=5.0):
-    """class Home (lpsolver.py:45-157).  ``ev`` is {} or the dict of extract.py:109-116.
+    """class Home (lpsolver.py:44-160).  ``ev`` is {} or the dict of extract.py:123-129.
     Returns (p_opt, s_opt, g_opt)."""
     cost = np.asarray(cost, float)
     load = np.asarray(load, float)
@@ -174,7 +174,7 @@ def home_subproblem(cost, load, ev, p_est, p_sch, gamma, kappa=5.0):
 
 
 def solve_residence_arrays(tariff, load, ev):
-    """solve_residence (lpsolver.py:433-463): minimise 0.01*cost + 0.99*(1-s[T])."""
+    """solve_residence (lpsolver.py:430-460): minimise 0.01*cost + 0.99*(1-s[T])."""
     tariff = np.asarray(tariff, float)
     load = np.asarray(load, float)
     T = len(tariff)
@@ -290,7 +290,7 @@ def project_voltage(z, R, u, lam0=None, tol=1e-11, maxit=200, rn2=None):
 
 
 def utility_subproblem(R, p_est, p_sch, gamma, kappa, vset, vlow, vhigh, lam0=None):
-    """class Utility (lpsolver.py:160-240) for one feeder.  Arrays are [homes, T]."""
+    """class Utility (lpsolver.py:163-238) for one feeder.  Arrays are [homes, T]."""
     u = vhigh * vhigh - vset * vset
     lo = vlow * vlow - vset * vset
     if not (u > 0 and lo <= 0 and R.min() >= 0):
@@ -311,7 +311,7 @@ def utility_subproblem(R, p_est, p_sch, gamma, kappa, vset, vlow, vhigh, lam0=No
 def solve_ADMM_arrays(R_blocks, load, cost, ev_mask, rating, capacity, initial, start, end,
                       kappa=5.0, iter_max=15, vset=1.0, vlow=0.95, vhigh=1.05,
                       return_history=False, forced_hours=None):
-    """solve_ADMM (lpsolver.py:244-293) on arrays.
+    """solve_ADMM (lpsolver.py:242-290) on arrays.
 
     R_blocks: list of residence sensitivity blocks, one per feeder; homes are the
     concatenation of the feeders' residences.  load [H,T]; per-home EV arrays [H].
@@ -334,13 +334,13 @@ def solve_ADMM_arrays(R_blocks, load, cost, ev_mask, rating, capacity, initial, 
     nwin = [count_window(rating[i], capacity[i], initial[i]) if ev_mask[i] else (0, 0)
             for i in range(H)]
     for k in range(iter_max):
-        # utility estimate (lpsolver.py:258-261)
+        # utility estimate (lpsolver.py:255-259)
         P_est_new = np.empty((H, T))
         for f, Rb in enumerate(R_blocks):
             s = slice(offs[f], offs[f + 1])
             P_est_new[s], lam[s], _ = utility_subproblem(
                 Rb, P_est[s], P_sch[s], Gam[s], kappa, vset, vlow, vhigh, lam[s])
-        # every home, with the PREVIOUS iterates (lpsolver.py:275)
+        # every home, with the PREVIOUS iterates (lpsolver.py:273)
         P_sch_new = load.copy()
         for i in np.nonzero(ev_mask)[0]:
             d = home_delta(cost, load[i], P_est[i], P_sch[i], Gam[i], kappa, rating[i])
@@ -350,9 +350,9 @@ def solve_ADMM_arrays(R_blocks, load, cost, ev_mask, rating, capacity, initial, 
             P_ev[i] = 0.0
             P_ev[i, hrs] = rating[i]
             P_sch_new[i] += P_ev[i]
-        check = P_est_new - P_sch_new                        # lpsolver.py:282-283
-        Gam = Gam + (kappa / 2) * check                       # lpsolver.py:284-285
-        diff[k] = np.sqrt((check * check).sum(axis=1)) / T    # lpsolver.py:286
+        check = P_est_new - P_sch_new                        # lpsolver.py:280-281
+        Gam = Gam + (kappa / 2) * check                       # lpsolver.py:282-283
+        diff[k] = np.sqrt((check * check).sum(axis=1)) / T    # lpsolver.py:284
         P_est, P_sch = P_est_new, P_sch_new
         if return_history:
             hist.append((P_est.copy(), P_sch.copy(), Gam.copy()))
@@ -365,7 +365,7 @@ def solve_ADMM_arrays(R_blocks, load, cost, ev_mask, rating, capacity, initial, 
 
 
 def homes_to_arrays(homes, res):
-    """dict-of-homes (extract.py:103-119) -> arrays in residence order."""
+    """dict-of-homes (extract.py:120-132) -> arrays in residence order."""
     H = len(res)
     T = len(homes[res[0]]["LOAD"])
     load = np.array([homes[h]["LOAD"] for h in res], float)
@@ -379,7 +379,7 @@ def homes_to_arrays(homes, res):
 
 def solve_ADMM(homes, graph, cost, grbpath=None, kappa=5.0, iter_max=15,
                vset=1.0, vlow=0.95, vhigh=1.05):
-    """Same signature and return value as lpsolver.py:244 (grbpath unused)."""
+    """Same signature and return value as lpsolver.py:242 (grbpath unused)."""
     res, Rres = residence_block(graph)
     arr, T, H = homes_to_arrays(homes, res)
     out = solve_ADMM_arrays([Rres], cost=cost, kappa=kappa, iter_max=iter_max,
@@ -392,13 +392,13 @@ def solve_ADMM(homes, graph, cost, grbpath=None, kappa=5.0, iter_max=15,
 
 
 def solve_residence(tariff, data, path=None):
-    """Same signature as lpsolver.py:433."""
+    """Same signature as lpsolver.py:430."""
     return solve_residence_arrays(tariff, data["LOAD"], data["EV"])
 
 
 # --------------------------------------------------------------------------- reliability check
 def compute_voltage(graph, p_sch, vset=1.0):
-    """drawing.py:62-78."""
+    """drawing.py:61-78."""
     nodelist = [n for n in graph if graph.nodes[n]["label"] != "S"]
     res = set(n for n in graph if graph.nodes[n]["label"] == "H")
     T = len(next(iter(p_sch.values())))
@@ -411,7 +411,7 @@ def compute_voltage(graph, p_sch, vset=1.0):
     return {h: V[i] for i, h in enumerate(nodelist)}
 
 
-LINE_RATING = {  # drawing.py:29-40 (kVA), repeated in test-dist-ind-opt.py:156-166
+LINE_RATING = {  # drawing.py:30-41 (kVA), repeated in test-dist-ind-opt.py:156-166
     "OH_Voluta": np.sqrt(3) * 95 * 0.24, "OH_Periwinkle": np.sqrt(3) * 125 * 0.24,
     "OH_Conch": np.sqrt(3) * 165 * 0.24, "OH_Neritina": np.sqrt(3) * 220 * 0.24,
     "OH_Runcina": np.sqrt(3) * 265 * 0.24, "OH_Zuzara": np.sqrt(3) * 350 * 0.24,
@@ -422,7 +422,7 @@ LINE_RATING = {  # drawing.py:29-40 (kVA), repeated in test-dist-ind-opt.py:156-
 
 
 def compute_flows(graph, p_sch):
-    """drawing.py:28-60.  Per-edge loading (signed flow / rating)."""
+    """drawing.py:29-59.  Per-edge loading (signed flow / rating)."""
     nodelist = [n for n in graph if graph.nodes[n]["label"] != "S"]
     res = set(n for n in graph if graph.nodes[n]["label"] == "H")
     nodeind = [i for i, n in enumerate(graph.nodes) if graph.nodes[n]["label"] != "S"]

@@ -55,7 +55,7 @@ SIGNATURES = {
     "revs_admm_step": ([_P, _D], C.c_int),
     "revs_home_step": ([_P, C.c_double, _D, _D, _D, _D, _D], C.c_int),
     "revs_utility_step": ([_P, C.c_double, C.c_double, C.c_double, C.c_double, _D, _D, _D, _D, _D, _D], C.c_int),
-    "revs_get_results": ([_P, _D, _D, _D, _D], C.c_int),
+    "revs_get_results": ([_P, _D, _D, _D, _D, C.c_int], C.c_int),
     "revs_get_estimate": ([_P, _D, _D], C.c_int),
     "revs_solve_individual": ([_P, _D, _D, _D], C.c_int),
     "revs_reliability": ([_P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), _D, C.c_double, _D, _D], C.c_int),
@@ -228,16 +228,21 @@ class Solver:
     def results(self, iters=None, want_diff=True, out=None):
         """`out`: optional dict of preallocated (e.g. page-locked) arrays P_sch, P_ev, SOC, diff."""
         H, T = self.H, self.T
-        iters = self.stats()["admm_iterations"] if iters is None else iters
+        done = self.stats()["admm_iterations"]
+        iters = done if iters is None else iters
         if out is not None:
             P, E, S, D = out["P_sch"], out["P_ev"], out["SOC"], out.get("diff")
-            assert P.shape == (H, T) and E.shape == (H, T) and S.shape == (H, T + 1)
-            assert D is None or (D.shape[0] >= iters and D.shape[1] == H and D.flags.c_contiguous)
+            for a, shape in ((P, (H, T)), (E, (H, T)), (S, (H, T + 1))):
+                if a.shape != shape or a.dtype != np.float64 or not a.flags.c_contiguous:
+                    raise ValueError(f"out arrays must be C-contiguous float64 of shape {shape}")
+            if D is not None and (D.ndim != 2 or D.shape[1] != H or D.dtype != np.float64 or not D.flags.c_contiguous):
+                raise ValueError("out['diff'] must be a C-contiguous float64 [rows, H] array")
         else:
             P, E, S = np.empty((H, T)), np.empty((H, T)), np.empty((H, T + 1))
-            D = np.empty((iters, H)) if want_diff else None
-        _check(self.lib.revs_get_results(self._h, _dp(P), _dp(E), _dp(S), _dp(D)))
-        return dict(P_sch=P, P_ev=E, SOC=S, diff=D)
+            D = np.empty((max(iters, done), H)) if want_diff else None
+        # the library refuses a diff buffer with fewer rows than iterations that ran
+        _check(self.lib.revs_get_results(self._h, _dp(P), _dp(E), _dp(S), _dp(D), 0 if D is None else D.shape[0]))
+        return dict(P_sch=P, P_ev=E, SOC=S, diff=None if D is None else D[:done] if out is None else D)
 
     def estimate(self):
         H, T = self.H, self.T

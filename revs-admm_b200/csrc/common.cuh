@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 namespace revs {
 
 constexpr int kPad = 16;        // residences of a feeder are padded to a multiple of this
@@ -10,10 +12,11 @@ constexpr int kWMax = 128;      // largest working set of a (feeder,hour) utilit
 constexpr int kAddMax = 32;     // violated voltage rows admitted per working-set round
 constexpr int kWW = 16;         // working-set capacity of the warp-per-column QP kernel
 constexpr int kQpClasses = 4;   // utility QP instantiations: 0 = warp kernel, 1..3 = CTA kernels by capacity
-constexpr int kQpLists = 13;    // work lists: classes 1..3 at [1..3], the warp kernels' buckets at [4..7] (zones <= 128) and [8..11] (<= 256),
-                                // [12] = columns the one-row kernel passes on to the general warp kernel
+constexpr int kQpLists = 17;    // work lists: classes 1..3 at [1..3], the warp kernels' buckets at [4..7] (zones <= 128), [8..11] (<= 256)
+                                // and [13..16] (<= 320), [12] = columns the one-row kernel passes on to the general warp kernel
 constexpr int kListLeftover = 12;
-constexpr int kWarpMaxN = 256;  // largest zone the warp-per-column QP kernel takes
+constexpr int kListBig = 13;    // first bucket of the zones of 257..kWarpMaxN residences
+constexpr int kWarpMaxN = 320;  // largest zone the warp-per-column QP kernel takes (the reference feeder's zones: 157..297)
 __host__ __device__ constexpr int qp_class_cap(int cls) { return cls == 0 ? kWW : (cls == 1 ? 32 : (cls == 2 ? 64 : kWMax)); }
 
 // One feeder of the batch as the kernels see it.
@@ -56,6 +59,15 @@ constexpr double kScreenMargin = 0.01;   // rows with v~ <= (1-margin) u are pro
 constexpr double kScreenUp = 1.005;      // v <= kScreenUp * v~ for the BF16/FP32 product of non-negative terms, K <= 16384
 constexpr int kVerifyMaxN = 512;         // zones up to this size verify all voltage rows inside the QP kernels
 constexpr int kQpBuckets = 4;            // work lists of the warp kernel: |W| >= 3, 2, 1, 0 (hardest first)
+
+// Function attributes (dynamic shared-memory size, carve-out) are per device.  Returns true the first time it is
+// called for `mask` on the current device, so a launcher sets its attributes once per device, from any host thread.
+inline bool first_use_on_device(std::atomic<unsigned long long>& mask) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return true;
+    const unsigned long long bit = 1ull << (dev & 63);
+    return (mask.fetch_or(bit) & bit) == 0;
+}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -1,7 +1,7 @@
 // Sensitivity contraction  C = A * B^T  in FP64 on the tensor cores (DMMA m8n8k4).
 //
 // This is the LinDistFlow reliability check of the reference: R_res @ g in
-// Utility.network (lpsolver.py:179-190) and R @ P / A_inv @ P in drawing.py:28-78.
+// Utility.network (lpsolver.py:183-194) and R @ P / A_inv @ P in drawing.py:29-78.
 // A is a feeder's dense sensitivity block (voltage: R, flow: subtree incidence), B^T is
 // the schedule in time-major layout [T][homes], so the contraction runs over the homes
 // and all T hours of a feeder share one pass over the sensitivity block.

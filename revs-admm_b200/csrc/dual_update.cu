@@ -2,11 +2,11 @@
 // convergence test and the target of the next utility step -- one kernel per ADMM
 // iteration, nothing leaves the device.
 //
-// Reference: the tail of the home loop of solve_ADMM (lpsolver.py:281-286)
+// Reference: the tail of the home loop of solve_ADMM (lpsolver.py:280-284)
 //     check = P_est[k+1] - P_sch[k+1]
 //     G[k+1] = G[k] + kappa/2 * check
 //     diff[k+1][h] = ||check|| / T
-// plus the objective data of the next Utility (lpsolver.py:209-211), which is the
+// plus the objective data of the next Utility (lpsolver.py:202-204), which is the
 // projection target  z = (P_est + P_sch)/2 - G/kappa.
 //
 // Layout: the utility side keeps its arrays time-major [T][Hp] (one contiguous column per
@@ -29,6 +29,10 @@ __global__ void __launch_bounds__(256, 4) dual_update_kernel(DualParams P) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int h0 = blockIdx.x * 32;
     const int ldt = P.T + 1;
+    const int it = P.iter ? *P.iter : 0;          // read by every CTA before the last one increments it (ticket below)
+    const double* __restrict__ p_sch_new = (it & 1) ? P.p_sch_old : P.p_sch_new;
+    const double* __restrict__ p_sch_old = (it & 1) ? P.p_sch_new : P.p_sch_old;
+    double* __restrict__ diff_k = P.diff_k + (size_t)it * P.Hp;
 
     for (int t = warp; t < P.T; t += 8) {
         int h = h0 + lane;
@@ -45,8 +49,8 @@ __global__ void __launch_bounds__(256, 4) dual_update_kernel(DualParams P) {
         double a1 = 0.0, a2 = 0.0;
         for (int t = lane; t < P.T; t += 32) {
             const double e = tile[hl * ldt + t];
-            const double sn = P.p_sch_new[base + t];
-            const double so = P.p_sch_old[base + t];
+            const double sn = p_sch_new[base + t];
+            const double so = p_sch_old[base + t];
             const double gm = P.gamma[base + t];
             const double check = __dadd_rn(e, -sn);
             const double g2 = __dadd_rn(gm, __dmul_rn(hk, check));
@@ -59,7 +63,7 @@ __global__ void __launch_bounds__(256, 4) dual_update_kernel(DualParams P) {
         }
         a1 = warp_sum(a1);
         a2 = warp_sum(a2);
-        if (lane == 0) P.diff_k[h] = sqrt(a1) / (double)P.T;
+        if (lane == 0) diff_k[h] = sqrt(a1) / (double)P.T;
         blk_p += a1;
         blk_d += a2;
     }
@@ -81,21 +85,49 @@ __global__ void __launch_bounds__(256, 4) dual_update_kernel(DualParams P) {
         }
     }
 
+    // residuals: per-CTA partial sums, added by the last CTA in a fixed order (no floating-point atomics: the
+    // residuals and the convergence decision are reproducible run to run)
+    __shared__ int s_last;
+    __shared__ double s_fin[2][8];
     if (threadIdx.x == 0) {
         double sp = 0.0, sd = 0.0;
         for (int w = 0; w < 8; ++w) { sp += s_part[0][w]; sd += s_part[1][w]; }
-        atomicAdd(&P.res->sum_primal, sp);
-        atomicAdd(&P.res->sum_dual, sd);
+        P.partials[blockIdx.x] = sp;
+        P.partials[gridDim.x + blockIdx.x] = sd;
         __threadfence();
-        unsigned done = atomicAdd(&P.res->ticket, 1u);
-        if (done == gridDim.x - 1) {   // last CTA: residuals + convergence test
-            __threadfence();
-            double tp = atomicAdd(&P.res->sum_primal, 0.0);
-            double td = atomicAdd(&P.res->sum_dual, 0.0);
-            double r = sqrt(tp / P.count), s = P.kappa * sqrt(td / P.count);
-            P.res->primal = r;
-            P.res->dual = s;
-            P.res->converged = (P.tol > 0.0 && r < P.tol && s < P.tol) ? 1 : 0;
+        const unsigned done = atomicAdd(&P.res->ticket, 1u);
+        s_last = done == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double tp = 0.0, td = 0.0;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+        tp += __ldcg(P.partials + b);
+        td += __ldcg(P.partials + gridDim.x + b);
+    }
+    tp = warp_sum(tp);
+    td = warp_sum(td);
+    if (lane == 0) { s_fin[0][warp] = tp; s_fin[1][warp] = td; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tp = 0.0; td = 0.0;
+        for (int w = 0; w < 8; ++w) { tp += s_fin[0][w]; td += s_fin[1][w]; }
+        const double r = sqrt(tp / P.count), sres = P.kappa * sqrt(td / P.count);
+        const int conv = (P.tol > 0.0 && r < P.tol && sres < P.tol) ? 1 : 0;
+        P.res->sum_primal = tp;
+        P.res->sum_dual = td;
+        P.res->primal = r;
+        P.res->dual = sres;
+        P.res->converged = conv;
+        P.res->ticket = 0u;                        // ready for the next iteration of a captured loop
+        if (P.iter) {
+            const int k = it + 1;
+            *P.iter = k;
+            if (P.use_cond) {
+                const bool err = (P.err_a && *P.err_a) || (P.err_b && *P.err_b);
+                cudaGraphSetConditional((cudaGraphConditionalHandle)P.cond_loop, (k < P.iter_max && !conv && !err) ? 1u : 0u);
+            }
         }
     }
 }

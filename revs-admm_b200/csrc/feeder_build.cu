@@ -1,7 +1,7 @@
 // Sensitivity matrices of a radial feeder, built on the device from the tree itself.
 //
 // Reference: compute_Rmat (lpsolver.py:17-26) forms R = 2 F D F^T by inverting the reduced
-// incidence matrix with numpy; compute_flows (drawing.py:28-60) inverts it again for the
+// incidence matrix with numpy; compute_flows (drawing.py:29-59) inverts it again for the
 // flow sensitivities.  For a radial feeder both inverses are path indicators, so
 //     R[a][b]   = 2 * (resistance of the common part of the root paths of a and b)
 //     A_inv[e][b] = +-1 iff edge e lies on the root path of b

@@ -1,6 +1,6 @@
 // Batched per-consumer charging sub-problem: one warp per home.
 //
-// Reference: class Home (lpsolver.py:45-157) and solve_residence (lpsolver.py:433-463),
+// Reference: class Home (lpsolver.py:44-160) and solve_residence (lpsolver.py:430-460),
 // one Gurobi MIQP per home per ADMM iteration.  With p[t] = e[t]*rating, e binary, the
 // objective is separable and linear in e, and the SOC rows collapse to a window on the
 // number of charging hours, so the exact optimum is a selection: the n_min cheapest
@@ -29,6 +29,10 @@ __global__ void __launch_bounds__(256) home_solve_kernel(HomeParams P) {
     if (h >= P.Hp) return;
     const size_t base = (size_t)h * P.T;
     const bool ev = P.has_ev[h] != 0;
+    // ping-pong of the schedules by the device iteration counter (see HomeParams::iter)
+    const bool odd = P.iter != nullptr && (*P.iter & 1);
+    const double* __restrict__ p_sch_in = odd ? P.p_sch_new : P.p_sch;
+    double* __restrict__ p_sch_out = odd ? const_cast<double*>(P.p_sch) : P.p_sch_new;
 
     double ld[SLOTS];
 #pragma unroll
@@ -40,7 +44,7 @@ __global__ void __launch_bounds__(256) home_solve_kernel(HomeParams P) {
 #pragma unroll
         for (int j = 0; j < SLOTS; ++j) {
             int t = lane + 32 * j;
-            if (t < P.T) { P.p_sch_new[base + t] = ld[j]; P.p_ev[base + t] = 0.0; }
+            if (t < P.T) { p_sch_out[base + t] = ld[j]; P.p_ev[base + t] = 0.0; }
         }
         return;
     }
@@ -58,10 +62,10 @@ __global__ void __launch_bounds__(256) home_solve_kernel(HomeParams P) {
         double v = CUDART_INF;
         if (t < P.T && t >= st && t < en) {
             if (P.individual) {
-                // (0.01*c_t)*rating - 0.99*(rating/capacity)   (lpsolver.py:408-415)
+                // (0.01*c_t)*rating - 0.99*(rating/capacity)   (lpsolver.py:407-415)
                 v = __dadd_rn(__dmul_rn(__dmul_rn(0.01, P.cost[t]), rate), P.ind_const[h]);
             } else {
-                double s = __dadd_rn(P.p_est[base + t], P.p_sch[base + t]);
+                double s = __dadd_rn(P.p_est[base + t], p_sch_in[base + t]);
                 double a = __dadd_rn(P.gamma[base + t], __dmul_rn(0.5 * kap, s));
                 double x = __dmul_rn(rate, __dadd_rn(P.cost[t], -a));
                 double y = __dmul_rn(__dmul_rn(kap, ld[j]), rate);
@@ -169,7 +173,7 @@ __global__ void __launch_bounds__(256) home_solve_kernel(HomeParams P) {
         if (t >= P.T) continue;
         double p = on[j] ? rate : 0.0;
         P.p_ev[base + t] = p;
-        P.p_sch_new[base + t] = __dadd_rn(ld[j], p);
+        p_sch_out[base + t] = __dadd_rn(ld[j], p);
     }
 }
 
@@ -184,7 +188,7 @@ cudaError_t launch_home_solve(const HomeParams& P, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
-// SOC[h][t+1] = SOC[h][t] + p_ev[h][t]/capacity  (lpsolver.py:104-109), one thread per home
+// SOC[h][t+1] = SOC[h][t] + p_ev[h][t]/capacity  (lpsolver.py:105-108), one thread per home
 // hour would need a scan; T is tiny, so one lane walks a home and a warp covers 32 homes.
 __global__ void soc_profile_kernel(const double* __restrict__ p_ev, const uint8_t* __restrict__ has_ev,
                                    const double* __restrict__ capacity,

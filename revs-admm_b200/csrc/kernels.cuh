@@ -8,7 +8,9 @@ namespace revs {
 struct HomeParams {
     const double* load;       // [Hp][T]
     const double* p_est;      // [Hp][T]  previous utility estimate
-    const double* p_sch;      // [Hp][T]  previous schedule
+    const double* p_sch;      // [Hp][T]  previous schedule ...
+    const int* iter;          // ... optional device iteration counter k of the ADMM loop: the schedules ping-pong, odd k reads
+                              //     p_sch_new and writes p_sch (so one captured launch serves every iteration)
     const double* gamma;      // [Hp][T]
     const double* cost;       // [T]
     const uint8_t* has_ev;    // [Hp]
@@ -17,7 +19,7 @@ struct HomeParams {
     const int* end;           // [Hp]
     const int* n_min;         // [Hp]  from the SOC rows, host-computed
     const int* n_max;         // [Hp]
-    double* p_sch_new;        // [Hp][T]
+    double* p_sch_new;        // [Hp][T]  (const-cast of p_sch is written instead when *iter is odd)
     double* p_ev;             // [Hp][T]
     int* infeasible;          // flag
     int Hp, T;
@@ -32,7 +34,7 @@ cudaError_t launch_soc_profile(const double* p_ev, const uint8_t* has_ev, const 
 
 // ---- dual_update.cu
 struct ResidualOut {
-    double sum_primal;     // sum (P_est - P_sch)^2        (this device)
+    double sum_primal;     // sum (P_est - P_sch)^2        (this device, last iteration)
     double sum_dual;       // sum (P_sch - P_sch_prev)^2
     double primal;         // sqrt(sum_primal / count)
     double dual;           // kappa * sqrt(sum_dual / count)
@@ -42,15 +44,23 @@ struct ResidualOut {
 
 struct DualParams {
     const double* g_t;         // [T][Hp]  P_est[k+1], time-major (utility output)
-    const double* p_sch_new;   // [Hp][T]
+    const double* p_sch_new;   // [Hp][T]  (swapped with p_sch_old when *iter is odd)
     const double* p_sch_old;   // [Hp][T]
+    int* iter;                 // optional device iteration counter k: selects the ping-pong side and the row of diff, and is
+                               // incremented by the last CTA (the whole ADMM loop then runs from one captured graph)
+    int iter_max;              // with `iter`: the loop condition is cleared after iter_max iterations, on convergence or on an error flag
+    const int* err_a;          // optional error flags (infeasible home, failed QP column): stop the device loop
+    const int* err_b;
+    unsigned long long cond_loop;   // cudaGraphConditionalHandle of the ADMM while node (use_cond != 0)
+    int use_cond;
     double* gamma;             // [Hp][T]  in: G[k]  out: G[k+1]
     double* p_est;             // [Hp][T]  out: P_est[k+1], home-major
     double* z_t;               // [T][Hp]  out: next projection target
     double* g_next;            // optional [T][Hp] (may alias g_t): [z]_+, the next utility iterate of columns without multipliers
     void* gbf_next;            // optional [T][Hp] __nv_bfloat16 copy of g_next
-    double* diff_k;            // [Hp]     out
+    double* diff_k;            // [Hp]     out: row k of diff (row 0 when `iter` is given; the kernel adds k * Hp)
     ResidualOut* res;
+    double* partials;          // [2][gridDim.x] per-CTA partial sums: the last CTA adds them in a fixed order (reproducible residuals)
     int Hp, T;
     double kappa, tol, count;  // count = real homes * T
 };
@@ -100,7 +110,36 @@ struct QpParams {
     double u, tol;
     int init;              // 1: first launch of a utility solve (warm start from lam_t)
     int inner_max;
+    int* round_ctr;        // device counter of the working-set rounds of the current utility solve (reset by qp_init_kernel);
+                           // order_columns_kernel called with mode < 0 takes its mode from it
+    unsigned long long cond_round;   // cudaGraphConditionalHandle of the working-set while node (use_cond != 0)
+    int use_cond;
 };
+
+// End of a working-set round inside a captured graph: decides whether another round runs.
+struct RoundEndParams {
+    const int* n_running;
+    const int* n_failed;
+    const int* infeasible;
+    int* round_ctr;
+    int* noconv;                 // set when round_max rounds did not finish the solve
+    unsigned long long* rounds_total;
+    int round_max;
+    unsigned long long cond_round;
+    int use_cond;
+};
+cudaError_t launch_round_end(const RoundEndParams& P, cudaStream_t stream);
+
+// Captured loop: IF-node conditions of the CTA classes first_gated.. from their work-list counts.
+struct ClassGateParams {
+    const int* order_count;
+    unsigned long long cond[kQpClasses];
+    int first_gated;
+};
+cudaError_t launch_class_gate(const ClassGateParams& P, cudaStream_t stream);
+cudaError_t qp_warp_prepare();       // function attributes of every warp-kernel instantiation on the current device
+cudaError_t screen_prepare();
+cudaError_t screen_tc5_prepare();
 
 cudaError_t launch_utility_qp(const QpParams& P, int grid, int cls, cudaStream_t stream);
 // ---- utility_qp_warp.cu

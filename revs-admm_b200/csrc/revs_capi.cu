@@ -7,7 +7,7 @@
 // side, the per-(feeder,hour) working sets and a small pinned block of counters that is
 // the only thing the host reads while the loop runs.
 //
-// An ADMM iteration (lpsolver.py:256-289) is, on the device:
+// An ADMM iteration (lpsolver.py:254-287) is, on the device:
 //   stream U:  utility_qp(init) -> { contract_f64 ; utility_qp(step) } until no column runs
 //   stream H:  home_solve           (uses the PREVIOUS iterates, so it overlaps stream U)
 //   stream U:  dual_update          (after both)
@@ -48,14 +48,12 @@ int fail(int code, const char* fmt, ...) {
                         __FILE__, __LINE__);                                                \
     } while (0)
 
-constexpr double kSocTarget = 0.9;   // lpsolver.py:111
-constexpr double kSocMax = 1.0;      // lpsolver.py:102
+constexpr double kSocTarget = 0.9;   // lpsolver.py:109
+constexpr double kSocMax = 1.0;      // lpsolver.py:103
 constexpr double kCountTol = 1e-9;
 constexpr double kQpTol = 1e-11;     // KKT / feasibility tolerance of the utility QP
 constexpr int kQpInnerMax = 60;      // Newton steps per launch
 constexpr int kQpRoundMax = 400;     // working-set rounds per utility solve
-constexpr int kSweepGrid = 64;       // CTAs per class of the hand-over sweep launch
-constexpr int kSpecGrid = 148;       // CTAs per class of a speculatively enqueued round
 
 struct Counters {
     int n_running;   // n_running and n_cls are reset together before every working-set round
@@ -68,6 +66,15 @@ struct Counters {
     unsigned long long qp_cols;
     unsigned long long dbg[4 + 5 * kQpClasses];
     ResidualOut res;
+    int round;       // working-set round of the current utility solve (device-side loop)
+    int noconv;      // a utility solve hit kQpRoundMax rounds
+    int iter;        // ADMM iterations done (device-side loop; selects the ping-pong side of the schedules)
+    int pad_;
+    unsigned long long rounds_total;   // working-set rounds since revs_admm_begin
+};
+
+struct ZoneGroups {  // static: which warp-kernel instantiations the zone sizes of this solver need
+    int max_n = 0, warp_n = 0, n_small = 0, n_mid = 0, n_big = 0, mid_max = 0;
 };
 
 struct Tree {
@@ -80,7 +87,6 @@ struct Tree {
 
 struct TimedSpan { cudaEvent_t a, b; int cat; };
 
-double g_host_sync_ms = 0.0, g_host_round_ms = 0.0, g_cat_ms[16] = {0};   // REVS_DEBUG_HOST: host time waiting / per working-set round
 inline double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -108,6 +114,20 @@ struct revs_solver {
     ScreenProblem* d_sprob = nullptr;
     ContractTile* d_stiles = nullptr;
     int n_stiles = 0;
+    ZoneGroups zg;
+    // tuning / debug options, read ONCE (environment at revs_create, revs_set_option afterwards): nothing in the
+    // solve path calls getenv
+    int warp_m_max = 0, warp_m_max_big = 0;    // warm working sets above this size start in CTA class 1
+    bool use_fast = true;                      // one-row register kernel for the small zones
+    bool debug = false, debug_host = false;    // REVS_DEBUG / REVS_DEBUG_HOST: per-round / per-solve lines on stderr
+    bool use_graph = true;                     // revs_solve_admm: whole loop from one captured graph, loops decided on the device
+    double host_sync_ms = 0.0, cat_ms[16] = {0};   // host time waiting in round syncs / span sums per category (debug_host)
+    // captured ADMM loop (capture_loop): rebuilt when a parameter baked into it changes
+    cudaGraph_t loop_graph = nullptr;
+    cudaGraphExec_t loop_exec = nullptr;
+    double gk_kappa = 0, gk_vset = 0, gk_vhigh = 0, gk_tol = 0;
+    int gk_iter_max = 0, gk_flags = -1;
+    double* d_respart = nullptr;               // per-CTA partial residual sums of dual_update_kernel
     bool use_warp_kernel = true;               // class 0: one warp per small column (utility_qp_warp.cu)
     bool overlap_home = true;                  // home solve on its own (low priority) stream beside the utility kernels
     bool screen = true;                        // BF16 screening + exact recheck instead of the FP64 contraction in the loop
@@ -203,7 +223,7 @@ void spans_collect(revs_solver* s) {   // after the streams are synchronised
     for (size_t i = 0; i < s->span_used; ++i) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, s->spans[i].a, s->spans[i].b) != cudaSuccess) continue;
-        g_cat_ms[s->spans[i].cat & 15] += ms;
+        s->cat_ms[s->spans[i].cat & 15] += ms;
         switch (s->spans[i].cat) {
             case 0: s->stats.gemm_ms += ms; break;
             case 5: s->stats.gemm_ms += ms; s->stats.gemm_full_ms += ms; break;
@@ -251,9 +271,8 @@ int check_ready(const revs_solver* s) {
     return REVS_OK;
 }
 
-// One utility solve: project z_t onto the voltage polytope of every (feeder,hour) column.
-int utility_solve(revs_solver* s, bool in_loop = false) {
-    QpParams Q;
+QpParams qp_params(revs_solver* s) {
+    QpParams Q{};
     Q.feeders = s->d_feeders;
     Q.Rpool = s->d_Rpool;
     Q.rn2 = s->d_rn2;
@@ -264,14 +283,8 @@ int utility_solve(revs_solver* s, bool in_loop = false) {
     Q.list0 = kQpClasses;
     Q.nlists = kQpBuckets;
     Q.list_extra = -1;
-    Q.warp_m_max = getenv("REVS_WARP_M_MAX") ? atoi(getenv("REVS_WARP_M_MAX")) : qp_warp_m_max_default();
-    Q.warp_m_max_big = getenv("REVS_WARP_M_MAX_BIG") ? atoi(getenv("REVS_WARP_M_MAX_BIG")) : std::min(Q.warp_m_max, 5);
-    if (!s->rn2_valid) {
-        CU(launch_row_norms(s->d_feeders, s->nf, s->d_Rpool, s->d_rn2, s->d_rmax, s->sU));
-        CU(launch_to_bf16(s->d_Rpool, s->d_Rbf, s->Rpool_elems, s->sU));
-        s->rn2_valid = true;
-        s->stats.kernel_launches += 2;
-    }
+    Q.warp_m_max = s->warp_m_max;
+    Q.warp_m_max_big = s->warp_m_max_big;
     Q.z_t = s->d_zt;
     Q.lam_t = s->d_lamt;
     Q.g_t = s->d_gt;
@@ -290,202 +303,210 @@ int utility_solve(revs_solver* s, bool in_loop = false) {
     Q.n_failed = &s->d_cnt->n_failed;
     Q.cls = s->d_cls;
     Q.n_cls = s->d_cnt->n_cls;
-    Q.order = nullptr;
+    Q.order = s->d_order;
+    Q.order4 = s->d_order4;
     Q.order_count = s->d_order_count;
     Q.ncols = s->ncols;
     Q.trace = nullptr;
-    long long* d_trace = nullptr;
-    int trace_round = -1;
-    if (const char* e = getenv("REVS_DEBUG_TRACE")) {   // "<admm iteration>,<round>": per-column timeline of that launch
-        int ti = -1, tr = -1;
-        if (sscanf(e, "%d,%d", &ti, &tr) == 2 && ti == s->k) trace_round = tr;
-    }
-    Q.dbg = getenv("REVS_DEBUG") ? s->d_cnt->dbg : nullptr;
+    Q.dbg = s->debug ? s->d_cnt->dbg : nullptr;
     Q.T = s->T;
     Q.Hp = s->Hp;
     Q.u = s->vhigh * s->vhigh - s->vset * s->vset;
     Q.tol = kQpTol;
     Q.inner_max = kQpInnerMax;
+    Q.init = 0;
+    Q.round_ctr = &s->d_cnt->round;
+    Q.cond_round = 0;
+    Q.use_cond = 0;
+    return Q;
+}
 
+int prepare_sensitivity(revs_solver* s) {
+    if (s->rn2_valid) return REVS_OK;
+    CU(launch_row_norms(s->d_feeders, s->nf, s->d_Rpool, s->d_rn2, s->d_rmax, s->sU));
+    CU(launch_to_bf16(s->d_Rpool, s->d_Rbf, s->Rpool_elems, s->sU));
+    s->rn2_valid = true;
+    s->stats.kernel_launches += 2;
+    return REVS_OK;
+}
+
+int launch_init(revs_solver* s, QpParams Q, bool in_loop, bool timed) {
     // Start of the solve: working sets from the stored multipliers, class by their size,
     // g = [z - R lam]_+ for the new target -- one warp per column.
     Q.init = in_loop ? 2 : 0;                      // 2: dual_update_kernel prepared g, multipliers sit on the stored rows
-    int max_n = 0, warp_n = 0, small_n = 0;        // largest zone / largest zone the warp kernel takes / zones <= 128
-    for (int f = 0; f < s->nf; ++f) {
-        max_n = std::max(max_n, s->feeders[f].n);
-        if (s->feeders[f].n <= qp_warp_max_n()) warp_n = std::max(warp_n, s->feeders[f].n);
-        if (s->feeders[f].n <= 128) ++small_n;
+    Q.order = nullptr;
+    TimedSpan* sp = timed ? span_begin(s, 6, s->sU) : nullptr;
+    CU(launch_qp_init(Q, s->use_warp_kernel ? qp_warp_max_n() : 0, s->sU));
+    if (sp) span_end(sp, s->sU);
+    return REVS_OK;
+}
+
+// kernels one working-set round launches when every class runs (launch accounting of the captured loop)
+int round_launches(const revs_solver* s) {
+    const bool warp = s->use_warp_kernel && s->zg.warp_n > 0;
+    int n = 2 + (kQpClasses - 1) + 1;              // screening / contraction, work lists, CTA classes, round end
+    if (warp) n += (s->zg.n_big > 0) + (s->zg.n_mid > 0) + (s->zg.n_small > 0 ? 1 + (s->use_fast ? 1 : 0) : 0);
+    return n;
+}
+
+// One working-set round, enqueued without waiting: screening pass, work lists, the QP classes side by side.
+// mode 0: first round of a solve, 1: later rounds, -1: by the device round counter (captured loop).
+// use / grid: which CTA classes can have work and how many columns (host-driven loop); nullptr = all, full grids.
+// timed: CUDA-event spans around the kernels (not inside a stream capture: event nodes are not allowed in loop bodies).
+struct GateCapture {   // captured loop: CTA classes 2 and 3 sit behind IF nodes decided on the device
+    cudaGraphConditionalHandle h[kQpClasses];
+    cudaGraph_t body[kQpClasses];
+};
+
+int enqueue_round(revs_solver* s, QpParams& Q, int mode, const bool* use, const int* grid, bool timed, GateCapture* gc = nullptr) {
+    const double thr = (1.0 - kScreenMargin) * Q.u;
+    TimedSpan* sp = timed ? span_begin(s, mode == 0 ? 5 : 0, s->sU) : nullptr;   // round 0: every column is running
+    if (s->screen) {
+        if (s->screen_impl == 1 && s->tc5_ready)
+            CU(launch_screen_tc5(s->d_sprob, s->d_stiles, s->n_stiles, s->d_maps_a,
+                                 (const char*)s->d_maps_a + (size_t)s->nf * screen_tc5_map_bytes(), s->d_bcol0, s->T, thr, s->sU));
+        else
+            CU(launch_screen(s->d_sprob, s->d_stiles, s->n_stiles, s->T, thr, s->sU));
+    } else {
+        CU(launch_contract(s->d_cprob, s->d_ctiles, s->n_ctiles, s->T, kOutTimeMajor, 0.0, s->sU));
     }
-    const int max_warp_n = s->use_warp_kernel ? qp_warp_max_n() : 0;
-    TimedSpan* sp = span_begin(s, 6, s->sU);
-    CU(launch_qp_init(Q, max_warp_n, s->sU));
-    span_end(sp, s->sU);
+    if (sp) span_end(sp, s->sU);
+    s->stats.kernel_launches++;
+    if (mode == 0) s->stats.gemm_full_launches++;
+    CU(cudaMemsetAsync(&s->d_cnt->n_running, 0, (1 + kQpClasses) * sizeof(int), s->sU));
+    CU(launch_order_columns(Q, mode, s->d_order, s->d_order_count, s->sU));
+    s->stats.kernel_launches++;
+    if (gc) {
+        // classes 2 and 3 need 73 / 210 KB of shared memory per CTA: even an empty launch of them would wait for (or
+        // evict) the warp kernels' CTAs, so in the captured loop they run only when their work list is not empty
+        ClassGateParams G{};
+        G.order_count = s->d_order_count;
+        for (int cl = 0; cl < kQpClasses; ++cl) G.cond[cl] = (unsigned long long)gc->h[cl];
+        G.first_gated = 2;
+        CU(launch_class_gate(G, s->sU));
+    }
+    // the larger classes go first, each on its own stream, so that their long CTAs
+    // overlap with the many short columns of the small classes
+    CU(cudaEventRecord(s->evV, s->sU));
+    for (int cl = kQpClasses - 1; cl >= 1; --cl) {
+        if (use && !use[cl]) continue;
+        CU(cudaStreamWaitEvent(s->sQ[cl], s->evV, 0));
+        if (gc && cl >= 2) {
+            cudaStreamCaptureStatus st;
+            cudaGraph_t g_cap = nullptr;
+            const cudaGraphNode_t* deps = nullptr;
+            size_t n_deps = 0;
+            CU(cudaStreamGetCaptureInfo(s->sQ[cl], &st, nullptr, &g_cap, &deps, &n_deps));
+            cudaGraphNodeParams np{};
+            np.type = cudaGraphNodeTypeConditional;
+            np.conditional.handle = gc->h[cl];
+            np.conditional.type = cudaGraphCondTypeIf;
+            np.conditional.size = 1;
+            cudaGraphNode_t node;
+            CU(cudaGraphAddNode(&node, g_cap, deps, n_deps, &np));
+            gc->body[cl] = np.conditional.phGraph_out[0];
+            CU(cudaStreamUpdateCaptureDependencies(s->sQ[cl], &node, 1, cudaStreamSetCaptureDependencies));
+            CU(cudaEventRecord(s->evQ[cl], s->sQ[cl]));
+            continue;
+        }
+        sp = timed ? span_begin(s, cl == 1 ? 3 : 4, s->sQ[cl]) : nullptr;
+        CU(launch_utility_qp(Q, grid ? grid[cl] : s->ncols, cl, s->sQ[cl]));
+        if (sp) span_end(sp, s->sQ[cl]);
+        CU(cudaEventRecord(s->evQ[cl], s->sQ[cl]));
+        s->stats.kernel_launches++;
+    }
+    if ((!use || use[0]) && s->use_warp_kernel && s->zg.warp_n > 0) {
+        // one persistent warp-per-column kernel per zone-size group, one after the other on the utility stream
+        // (sharing the SMs between two QP kernels slowed both down whenever it was measured): the groups of
+        // long columns first, the many short columns of the small zones fill the tail
+        s->stats.qp_warp_rounds++;
+        const int full = qp_warp_ctas_per_sm();
+        if (s->zg.n_big > 0) {                                    // zones of 257..320 residences: lists 13..16
+            Q.list0 = kListBig;
+            Q.nlists = kQpBuckets;
+            Q.list_extra = -1;
+            sp = timed ? span_begin(s, 7, s->sU) : nullptr;
+            CU(launch_utility_qp_warp(Q, 10, full, s->sU));
+            if (sp) span_end(sp, s->sU);
+            s->stats.kernel_launches++;
+        }
+        if (s->zg.n_mid > 0) {                                    // zones of 129..256 residences: lists 8..11
+            Q.list0 = kQpClasses + kQpBuckets;
+            Q.nlists = kQpBuckets;
+            Q.list_extra = -1;
+            sp = timed ? span_begin(s, 7, s->sU) : nullptr;
+            CU(launch_utility_qp_warp(Q, s->zg.mid_max <= 192 ? 6 : 8, full, s->sU));
+            if (sp) span_end(sp, s->sU);
+            s->stats.kernel_launches++;
+        }
+        if (s->zg.n_small > 0) {
+            // small zones: the one-row kernel first (short columns, twice the occupancy), then the general
+            // kernel for the columns with two or more stored rows (hardest first) and what the first passed on
+            sp = timed ? span_begin(s, 8, s->sU) : nullptr;
+            if (s->use_fast) {
+                CU(launch_utility_qp_fast(Q, s->sU));
+                s->stats.kernel_launches++;
+            }
+            Q.list0 = kQpClasses;
+            Q.nlists = s->use_fast ? 2 : kQpBuckets;
+            Q.list_extra = s->use_fast ? kListLeftover : -1;
+            CU(launch_utility_qp_warp(Q, 4, full, s->sU));
+            Q.list_extra = -1;
+            s->stats.kernel_launches++;
+            if (sp) span_end(sp, s->sU);
+        }
+    }
+    for (int cl = 1; cl < kQpClasses; ++cl)
+        if (!use || use[cl]) CU(cudaStreamWaitEvent(s->sU, s->evQ[cl], 0));
+    s->stats.gemm_launches++;
+    s->stats.qp_outer_iterations++;
+    return REVS_OK;
+}
+
+int check_device_flags(revs_solver* s) {
+    if (s->h_cnt->infeasible)
+        return fail(REVS_ERR_INFEASIBLE, "a home charging sub-problem is infeasible (SOC window vs plug-in window)");
+    if (s->h_cnt->n_failed)
+        return fail(REVS_ERR_NOCONV,
+                    "utility QP: %d (feeder,hour) columns need more than %d simultaneously active "
+                    "voltage rows", s->h_cnt->n_failed, kWMax);
+    if (s->h_cnt->noconv)
+        return fail(REVS_ERR_NOCONV, "utility QP: %d columns still running after %d working-set rounds",
+                    s->h_cnt->n_running, kQpRoundMax);
+    return REVS_OK;
+}
+
+// One utility solve, driven from the host (one pinned counter block read back per working-set round):
+// project z_t onto the voltage polytope of every (feeder,hour) column.  Used by revs_utility_step,
+// revs_admm_step and the profiling mode of revs_solve_admm; the default revs_solve_admm runs the same
+// kernels from a captured graph whose loops are decided on the device (capture_loop below).
+int utility_solve(revs_solver* s, bool in_loop = false) {
+    int rc = prepare_sensitivity(s);
+    if (rc) return rc;
+    QpParams Q = qp_params(s);
+    if ((rc = launch_init(s, Q, in_loop, true))) return rc;
     s->stats.kernel_launches++;
     bool use[kQpClasses];
     // first round: qp_init_kernel assigns classes on the device by the size of the stored working
     // sets; the largest working set any column has had in this solve (read back at every round
     // sync) bounds them, so larger classes need no launch
     for (int cl = 0; cl < kQpClasses; ++cl) use[cl] = cl <= 1 || qp_class_cap(cl - 1) < s->ws_bound;
-    if (max_warp_n == 0 || warp_n == 0) use[0] = false;
-    Q.init = 0;
-    Q.order = s->d_order;
-    Q.order4 = s->d_order4;
     int top_cls = 0;
     int grid[kQpClasses];
     for (int cl = 0; cl < kQpClasses; ++cl) grid[cl] = s->ncols;
-    const double thr = (1.0 - kScreenMargin) * Q.u;
-    // One working-set round, enqueued without waiting: screening pass, work lists, the QP classes
-    // side by side.  `spec`: the round is enqueued before the host knows whether any column is
-    // still running (small CTA grids; with empty lists every kernel exits at once).
-    auto enqueue_round = [&](int round, bool spec) -> int {
-        sp = span_begin(s, round == 0 ? 5 : 0, s->sU);   // round 0: every column is running
-        if (s->screen) {
-            if (s->screen_impl == 1 && s->tc5_ready)
-                CU(launch_screen_tc5(s->d_sprob, s->d_stiles, s->n_stiles, s->d_maps_a,
-                                     (const char*)s->d_maps_a + (size_t)s->nf * screen_tc5_map_bytes(), s->d_bcol0, s->T, thr, s->sU));
-            else
-                CU(launch_screen(s->d_sprob, s->d_stiles, s->n_stiles, s->T, thr, s->sU));
-        } else {
-            CU(launch_contract(s->d_cprob, s->d_ctiles, s->n_ctiles, s->T, kOutTimeMajor, 0.0, s->sU));
-        }
-        span_end(sp, s->sU);
-        s->stats.kernel_launches++;
-        if (round == 0) s->stats.gemm_full_launches++;
-        CU(cudaMemsetAsync(&s->d_cnt->n_running, 0, (1 + kQpClasses) * sizeof(int), s->sU));
-        if (round == trace_round) {
-            CU(cudaMalloc(&d_trace, sizeof(long long) * 12 * s->ncols));
-            CU(cudaMemsetAsync(d_trace, 0, sizeof(long long) * 12 * s->ncols, s->sU));
-            Q.trace = d_trace;
-        }
-        CU(launch_order_columns(Q, round == 0 ? 0 : 1, s->d_order, s->d_order_count, s->sU));
-        s->stats.kernel_launches++;
-        if (getenv("REVS_DEBUG_LISTS")) {
-            int oc[kQpLists];
-            std::vector<int> cd((size_t)s->ncols);
-            cudaStreamSynchronize(s->sU);
-            cudaMemcpy(oc, s->d_order_count, sizeof oc, cudaMemcpyDeviceToHost);
-            cudaMemcpy(cd.data(), s->d_cand, sizeof(int) * s->ncols, cudaMemcpyDeviceToHost);
-            long nc = 0;
-            for (int v : cd) nc += v != 0;
-            fprintf(stderr, "[revs] admm %d round %d lists: cls1-3 %d/%d/%d warp buckets %d/%d/%d/%d + %d/%d/%d/%d, cand flags %ld, thr %.6g\n", s->k, round,
-                    oc[1], oc[2], oc[3], oc[4], oc[5], oc[6], oc[7], oc[8], oc[9], oc[10], oc[11], nc, thr);
-        }
-        // the larger classes go first, each on its own stream, so that their long CTAs
-        // overlap with the many short columns of the small classes
-        CU(cudaEventRecord(s->evV, s->sU));
-        for (int cl = kQpClasses - 1; cl >= 1; --cl) {
-            if (!use[cl] && !spec) continue;       // a speculative round takes hand-overs to any class
-            CU(cudaStreamWaitEvent(s->sQ[cl], s->evV, 0));
-            sp = span_begin(s, cl == 1 ? 3 : 4, s->sQ[cl]);
-            CU(launch_utility_qp(Q, spec ? std::min(grid[cl], kSpecGrid) : grid[cl], cl, s->sQ[cl]));
-            span_end(sp, s->sQ[cl]);
-            CU(cudaEventRecord(s->evQ[cl], s->sQ[cl]));
-            s->stats.kernel_launches++;
-        }
-        if (use[0]) {
-            // zones of 129..256 residences (NJ = 8 instantiation, few and long columns) share the SMs
-            // with the small zones: one CTA per SM on a side stream
-            const bool two = warp_n > 128 && small_n > 0;
-            s->stats.qp_warp_rounds++;
-            // default: one after the other (sharing the SMs slowed both down when measured).  -1: both get
-            // a full persistent grid, the big-zone one first and on a side stream (back-fill);
-            // k > 0: k CTAs/SM for the big-zone kernel, the rest for the small-zone one (REVS_WARP_SPLIT).
-            static const int split = getenv("REVS_WARP_SPLIT") ? atoi(getenv("REVS_WARP_SPLIT")) : 0;
-            cudaStream_t sBig = split != 0 ? s->sQ[0] : s->sU;
-            const int full = qp_warp_ctas_per_sm();
-            const int big_nj = warp_n <= 192 ? 6 : 8;
-            const bool only_big = warp_n > 128 && !two;
-            if (two || only_big) {                                   // zones of 129..256 residences: lists 8..11
-                if (two && split != 0) CU(cudaStreamWaitEvent(sBig, s->evV, 0));
-                cudaStream_t sb = two ? sBig : s->sU;
-                Q.list0 = kQpClasses + kQpBuckets;
-                Q.nlists = kQpBuckets;
-                sp = span_begin(s, 7, sb);
-                CU(launch_utility_qp_warp(Q, big_nj, (two && split > 0) ? split : full, sb));
-                span_end(sp, sb);
-                if (two) CU(cudaEventRecord(s->evQ[0], sb));
-                s->stats.kernel_launches++;
-            }
-            if (!only_big) {
-                // small zones: the one-row kernel first (short columns, twice the occupancy), then the general
-                // kernel for the columns with two or more stored rows (hardest first) and what the first passed on
-                static const bool use_fast = !(getenv("REVS_NO_FAST") && atoi(getenv("REVS_NO_FAST")));
-                const int small_ctas = (two && split > 0) ? full - split : full;
-                sp = span_begin(s, 8, s->sU);
-                if (use_fast) {
-                    CU(launch_utility_qp_fast(Q, s->sU));
-                    s->stats.kernel_launches++;
-                }
-                Q.list0 = kQpClasses;
-                Q.nlists = use_fast ? 2 : kQpBuckets;
-                Q.list_extra = use_fast ? kListLeftover : -1;
-                CU(launch_utility_qp_warp(Q, 4, small_ctas, s->sU));
-                Q.list_extra = -1;
-                s->stats.kernel_launches++;
-                span_end(sp, s->sU);
-            }
-            if (two) CU(cudaStreamWaitEvent(s->sU, s->evQ[0], 0));
-        }
-        for (int cl = 1; cl < kQpClasses; ++cl)
-            if (use[cl] || spec) CU(cudaStreamWaitEvent(s->sU, s->evQ[cl], 0));
-        // sweep: columns handed to a larger class during this round are taken by that class
-        // at once (their state is consistent with the last screening pass), without a host
-        // round trip; one small grid per class, empty lists cost a few microseconds
-        static const bool do_sweep = getenv("REVS_SWEEP") && atoi(getenv("REVS_SWEEP"));
-        if (do_sweep && (max_n <= kVerifyMaxN || use[0])) {
-            Q.sweep = 1;
-            sp = span_begin(s, 9, s->sU);
-            CU(launch_order_columns(Q, 2, s->d_order, s->d_order_count, s->sU));
-            s->stats.kernel_launches++;
-            for (int cl = 1; cl < kQpClasses; ++cl) {
-                CU(launch_utility_qp(Q, kSweepGrid, cl, s->sU));
-                s->stats.kernel_launches++;
-            }
-            span_end(sp, s->sU);
-            Q.sweep = 0;
-        }
-        s->stats.gemm_launches++;
-        s->stats.qp_outer_iterations++;
-        return REVS_OK;
-    };
-    static const bool want_spec = getenv("REVS_SPEC") && atoi(getenv("REVS_SPEC"));   // off: with in-kernel verification one round is the norm
-    const bool speculate = want_spec && trace_round < 0 && !getenv("REVS_DEBUG") && !getenv("REVS_DEBUG_LISTS");
     for (int round = 0;; ++round) {
         if (round >= kQpRoundMax)
             return fail(REVS_ERR_NOCONV, "utility QP: %d columns still running after %d working-set rounds",
                         s->h_cnt->n_running, round);
-        int rc = enqueue_round(round, false);
-        if (rc) return rc;
-        if (round == 0 && speculate) {
-            // most solves need exactly one more round for a handful of columns: enqueue it now
-            // instead of idling the GPU over a host round trip
-            rc = enqueue_round(++round, true);
-            if (rc) return rc;
-        }
+        if ((rc = enqueue_round(s, Q, round == 0 ? 0 : 1, use, grid, true))) return rc;
         CU(cudaMemcpyAsync(s->h_cnt, s->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, s->sU));
         {
             const double t0 = now_ms();
             CU(cudaStreamSynchronize(s->sU));
-            g_host_sync_ms += now_ms() - t0;
+            s->host_sync_ms += now_ms() - t0;
         }
-        if (d_trace) {
-            std::vector<long long> hb((size_t)12 * s->ncols);
-            cudaMemcpy(hb.data(), d_trace, hb.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-            if (FILE* fp = fopen(getenv("REVS_DEBUG_TRACE_FILE") ? getenv("REVS_DEBUG_TRACE_FILE") : "revs_trace.bin", "wb")) {
-                fwrite(hb.data(), sizeof(long long), hb.size(), fp);
-                fclose(fp);
-            }
-            cudaFree(d_trace);
-            d_trace = nullptr;
-            Q.trace = nullptr;
-        }
-        if (s->h_cnt->infeasible)
-            return fail(REVS_ERR_INFEASIBLE, "a home charging sub-problem is infeasible (SOC window vs plug-in window)");
-        if (s->h_cnt->n_failed)
-            return fail(REVS_ERR_NOCONV,
-                        "utility QP: %d (feeder,hour) columns need more than %d simultaneously active "
-                        "voltage rows", s->h_cnt->n_failed, kWMax);
-        if (getenv("REVS_DEBUG"))
+        if ((rc = check_device_flags(s))) return rc;
+        if (s->debug)
             fprintf(stderr, "[revs] admm %d round %d: running %d by class %d/%d/%d/%d pieces_total %llu max_ws %d | phi evals %llu "
                     "pdas guesses %llu max pieces/launch %llu fallbacks %llu\n",
                     s->k, round, s->h_cnt->n_running, s->h_cnt->n_cls[0], s->h_cnt->n_cls[1], s->h_cnt->n_cls[2], s->h_cnt->n_cls[3],
@@ -501,7 +522,7 @@ int utility_solve(revs_solver* s, bool in_loop = false) {
         }
     }
     s->warm_cls = top_cls;
-    if (getenv("REVS_DEBUG") && s->k == s->iter_max - 1)
+    if (s->debug && s->k == s->iter_max - 1)
         for (int cl = 0; cl < kQpClasses; ++cl) {
             const unsigned long long* p = s->h_cnt->dbg + 4 + 5 * cl;
             fprintf(stderr, "[revs] class %d phase Mcycles: grad+kkt %.1f hessian %.1f pdas %.1f search %.1f final-eval %.1f\n", cl,
@@ -515,6 +536,7 @@ HomeParams home_params(revs_solver* s, int individual) {
     P.load = s->d_load;
     P.p_est = s->d_pest;
     P.p_sch = s->d_psch[s->cur];
+    P.iter = nullptr;
     P.gamma = s->d_gamma;
     P.cost = s->d_cost;
     P.has_ev = s->d_has_ev;
@@ -540,7 +562,9 @@ void free_all(revs_solver* s) {
                     s->d_pev, s->d_soc, s->d_has_ev, s->d_rating, s->d_capacity, s->d_initial, s->d_indconst,
                     s->d_start, s->d_end, s->d_nmin, s->d_nmax, s->d_zero_i, s->d_cost, s->d_zt, s->d_lamt,
                     s->d_gt, s->d_vt, s->d_wcount, s->d_widx, s->d_status, s->d_innerok, s->d_cls, s->d_order, s->d_order4, s->d_order_count, s->d_cnt, s->d_diff,
-                    s->d_cprob, s->d_ctiles};
+                    s->d_cprob, s->d_ctiles, s->d_respart};
+    if (s->loop_exec) cudaGraphExecDestroy(s->loop_exec);
+    if (s->loop_graph) cudaGraphDestroy(s->loop_graph);
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (auto& t : s->trees) {
@@ -658,7 +682,7 @@ int revs_create(revs_solver** out, int device, int n_feeders, const int64_t* fee
     TRY(cudaMalloc(&s->d_gbf, HT * 2));
     TRY(cudaMemset(s->d_gbf, 0, HT * 2));
     TRY(dalloc(&s->d_v32, HT));
-    if (getenv("REVS_EXACT_GEMM")) s->screen = false;
+    if (getenv("REVS_EXACT_GEMM")) s->screen = false;          // (create time only)
     for (int f = 0; f < n_feeders; ++f)          // the error bound of the BF16 screening pass (kScreenUp) holds up to 16384 terms
         if (s->feeders[f].n > 16384) s->screen = false;
     TRY(dalloc(&s->d_load, HT));
@@ -693,6 +717,27 @@ int revs_create(revs_solver** out, int device, int n_feeders, const int64_t* fee
     if (hp >= (int64_t)1 << 31 || (rp >> 4) >= (int64_t)1 << 31) s->use_warp_kernel = false;   // 32-bit work-list entries
     TRY(dalloc(&s->d_order_count, (size_t)2 * kQpLists));
     TRY(dalloc(&s->d_cnt, (size_t)1));
+    TRY(dalloc(&s->d_respart, (size_t)2 * ((hp + 31) / 32)));
+    // options from the environment, read here and nowhere else
+    {
+        const char* e;
+        s->warp_m_max = (e = getenv("REVS_WARP_M_MAX")) ? atoi(e) : qp_warp_m_max_default();
+        s->warp_m_max_big = (e = getenv("REVS_WARP_M_MAX_BIG")) ? atoi(e) : std::min(s->warp_m_max, 5);
+        s->use_fast = !((e = getenv("REVS_NO_FAST")) && atoi(e));
+        s->debug = getenv("REVS_DEBUG") != nullptr;
+        s->debug_host = getenv("REVS_DEBUG_HOST") != nullptr;
+        if ((e = getenv("REVS_NO_GRAPH")) && atoi(e)) s->use_graph = false;
+        if (s->debug) s->use_graph = false;      // the per-round lines need the host-driven loop
+    }
+    for (int f = 0; f < n_feeders; ++f) {
+        const int n = s->feeders[f].n;
+        s->zg.max_n = std::max(s->zg.max_n, n);
+        if (n > qp_warp_max_n()) continue;
+        s->zg.warp_n = std::max(s->zg.warp_n, n);
+        if (n <= 128) ++s->zg.n_small;
+        else if (n <= 256) { ++s->zg.n_mid; s->zg.mid_max = std::max(s->zg.mid_max, n); }
+        else ++s->zg.n_big;
+    }
     TRY(cudaHostAlloc((void**)&s->h_cnt, sizeof(Counters), cudaHostAllocDefault));
     memset(s->h_cnt, 0, sizeof(Counters));
 
@@ -928,7 +973,7 @@ int revs_admm_begin(revs_solver* s, double kappa, int iter_max, double vset, dou
     if (!(kappa > 0.0) || iter_max <= 0) return fail(REVS_ERR_ARG, "kappa and iter_max must be positive");
     const double u = vhigh * vhigh - vset * vset, lo = vlow * vlow - vset * vset;
     if (!(u > 0.0) || !(lo <= 0.0))
-        return fail(REVS_ERR_ARG, "need vlow <= vset < vhigh (lpsolver.py:181-190 with g >= 0, R >= 0)");
+        return fail(REVS_ERR_ARG, "need vlow <= vset < vhigh (lpsolver.py:185-193 with g >= 0, R >= 0)");
     CU(cudaSetDevice(s->device));
     s->kappa = kappa; s->iter_max = iter_max; s->vset = vset; s->vlow = vlow; s->vhigh = vhigh;
     s->k = 0; s->cur = 0; s->running = true;
@@ -953,62 +998,40 @@ int revs_admm_begin(revs_solver* s, double kappa, int iter_max, double vset, dou
 }
 
 namespace {
-int admm_step_impl(revs_solver* s, double sums[3], bool sync_now) {
-    if (!s || !s->running) return fail(REVS_ERR_ARG, "revs_admm_begin has not been called");
-    if (s->k >= s->iter_max) return fail(REVS_ERR_ARG, "iter_max iterations already done");
-    CU(cudaSetDevice(s->device));
-
-    // consumer side on its own stream: uses P_est[k], P_sch[k], Gamma[k] (lpsolver.py:275)
-    cudaStream_t sHome = s->overlap_home ? s->sH : s->sU;   // overlap_home = 0: in line, for an undisturbed kernel time
-    CU(cudaStreamWaitEvent(sHome, s->evDualDone, 0));
-    HomeParams hp = home_params(s, 0);
-    TimedSpan* sp = span_begin(s, 1, sHome);
-    CU(launch_home_solve(hp, sHome));
-    span_end(sp, sHome);
-    CU(cudaEventRecord(s->evHomeDone, sHome));
-    s->stats.kernel_launches++;
-
-    // operator side
-    int rc = utility_solve(s, true);
-    if (rc) { s->running = false; cudaDeviceSynchronize(); return rc; }
-
-    // fused dual update / residuals / next target
-    CU(cudaStreamWaitEvent(s->sU, s->evHomeDone, 0));
-    CU(cudaMemsetAsync(&s->d_cnt->res, 0, sizeof(ResidualOut), s->sU));
-    DualParams D;
+DualParams dual_params(revs_solver* s) {
+    DualParams D{};
     D.g_t = s->d_gt;
-    D.p_sch_new = s->d_psch[s->cur ^ 1];
-    D.p_sch_old = s->d_psch[s->cur];
+    D.p_sch_new = s->d_psch[1];
+    D.p_sch_old = s->d_psch[0];
+    D.iter = nullptr;
+    D.iter_max = s->iter_max;
+    D.err_a = &s->d_cnt->infeasible;
+    D.err_b = &s->d_cnt->n_failed;
+    D.cond_loop = 0;
+    D.use_cond = 0;
+    D.partials = s->d_respart;
     D.gamma = s->d_gamma;
     D.p_est = s->d_pest;
     D.z_t = s->d_zt;
     D.g_next = s->d_gt;
     D.gbf_next = s->screen ? s->d_gbf : nullptr;
-    D.diff_k = s->d_diff + (size_t)s->k * s->Hp;
+    D.diff_k = s->d_diff;
     D.res = &s->d_cnt->res;
     D.Hp = (int)s->Hp;
     D.T = s->T;
     D.kappa = s->kappa;
     D.tol = s->tol;
     D.count = (double)s->H * s->T;
-    sp = span_begin(s, 2, s->sU);
-    CU(launch_dual_update(D, s->sU));
-    span_end(sp, s->sU);
-    s->stats.kernel_launches++;
-    CU(cudaEventRecord(s->evDualDone, s->sU));
-    CU(cudaMemcpyAsync(s->h_cnt, s->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, s->sU));
-    CU(cudaEventRecord(s->evT1, s->sU));
-    s->cur ^= 1;
-    s->k++;
-    s->stats.admm_iterations = s->k;
-    if (!sync_now) return REVS_OK;       // the next iteration is enqueued behind this one
+    return D;
+}
+
+// wait for the enqueued work, collect spans and counters of the run so far
+int finish_sync(revs_solver* s, double sums[3]) {
     CU(cudaStreamSynchronize(s->sU));
     CU(cudaStreamSynchronize(s->sH));
     spans_collect(s);
-    if (s->h_cnt->infeasible) {
-        s->running = false;
-        return fail(REVS_ERR_INFEASIBLE, "a home charging sub-problem is infeasible (SOC window vs plug-in window)");
-    }
+    int rc = check_device_flags(s);
+    if (rc) { s->running = false; return rc; }
     s->stats.primal_residual = s->h_cnt->res.primal;
     s->stats.dual_residual = s->h_cnt->res.dual;
     s->stats.qp_newton_iterations = (int64_t)s->h_cnt->newton_its;
@@ -1025,6 +1048,173 @@ int admm_step_impl(revs_solver* s, double sums[3], bool sync_now) {
     }
     return REVS_OK;
 }
+
+int admm_step_impl(revs_solver* s, double sums[3], bool sync_now) {
+    if (!s || !s->running) return fail(REVS_ERR_ARG, "revs_admm_begin has not been called");
+    if (s->k >= s->iter_max) return fail(REVS_ERR_ARG, "iter_max iterations already done");
+    CU(cudaSetDevice(s->device));
+
+    // consumer side on its own stream: uses P_est[k], P_sch[k], Gamma[k] (lpsolver.py:273)
+    cudaStream_t sHome = s->overlap_home ? s->sH : s->sU;   // overlap_home = 0: in line, for an undisturbed kernel time
+    CU(cudaStreamWaitEvent(sHome, s->evDualDone, 0));
+    HomeParams hp = home_params(s, 0);
+    TimedSpan* sp = span_begin(s, 1, sHome);
+    CU(launch_home_solve(hp, sHome));
+    span_end(sp, sHome);
+    CU(cudaEventRecord(s->evHomeDone, sHome));
+    s->stats.kernel_launches++;
+
+    // operator side
+    int rc = utility_solve(s, true);
+    if (rc) { s->running = false; cudaDeviceSynchronize(); return rc; }
+
+    // fused dual update / residuals / next target
+    CU(cudaStreamWaitEvent(s->sU, s->evHomeDone, 0));
+    DualParams D = dual_params(s);
+    D.p_sch_new = s->d_psch[s->cur ^ 1];
+    D.p_sch_old = s->d_psch[s->cur];
+    D.diff_k = s->d_diff + (size_t)s->k * s->Hp;
+    sp = span_begin(s, 2, s->sU);
+    CU(launch_dual_update(D, s->sU));
+    span_end(sp, s->sU);
+    s->stats.kernel_launches++;
+    CU(cudaEventRecord(s->evDualDone, s->sU));
+    CU(cudaMemcpyAsync(s->h_cnt, s->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, s->sU));
+    CU(cudaEventRecord(s->evT1, s->sU));
+    s->cur ^= 1;
+    s->k++;
+    s->stats.admm_iterations = s->k;
+    if (!sync_now) return REVS_OK;       // the next iteration is enqueued behind this one
+    return finish_sync(s, sums);
+}
+
+// ---- the whole ADMM loop as ONE captured graph whose two loops are decided on the device:
+//
+//   while (k < iter_max && !converged && !error)            cudaGraphCondTypeWhile, condition set by the last CTA of dual_update_kernel
+//       home_solve            (own branch: uses the previous iterates, joins before dual_update)
+//       qp_init
+//       while (columns running)                             cudaGraphCondTypeWhile, condition set by round_end_kernel
+//           screening pass, work lists, QP classes side by side, round end
+//       dual_update           (k += 1)
+//
+// Every kernel reads what changes from iteration to iteration (ping-pong side of the schedules, row of diff,
+// round number) from device counters, so the bodies are captured once.  Nothing returns to the host until the
+// schedule is finished: no round trip per working-set round, no launch latency per kernel.
+int capture_loop(revs_solver* s) {
+    const int flags = (s->screen ? 1 : 0) | (s->screen_impl << 1) | (s->overlap_home ? 4 : 0) | (s->use_warp_kernel ? 8 : 0) | (s->use_fast ? 16 : 0);
+    if (s->loop_exec && s->gk_kappa == s->kappa && s->gk_vset == s->vset && s->gk_vhigh == s->vhigh && s->gk_tol == s->tol &&
+        s->gk_iter_max == s->iter_max && s->gk_flags == flags)
+        return REVS_OK;
+    if (s->loop_exec) { cudaGraphExecDestroy(s->loop_exec); s->loop_exec = nullptr; }
+    if (s->loop_graph) { cudaGraphDestroy(s->loop_graph); s->loop_graph = nullptr; }
+    // function attributes are set outside the capture
+    for (int cl = 1; cl < kQpClasses; ++cl) CU(launch_utility_qp(QpParams{}, 0, cl, s->sU));
+    CU(qp_warp_prepare());
+    CU(screen_prepare());
+    CU(screen_tc5_prepare());
+    CU(cudaGraphCreate(&s->loop_graph, 0));
+    cudaGraphConditionalHandle h_loop, h_round;
+    CU(cudaGraphConditionalHandleCreate(&h_loop, s->loop_graph, 1, cudaGraphCondAssignDefault));
+    CU(cudaGraphConditionalHandleCreate(&h_round, s->loop_graph, 0, cudaGraphCondAssignDefault));
+    GateCapture gc{};
+    for (int cl = 2; cl < kQpClasses; ++cl) CU(cudaGraphConditionalHandleCreate(&gc.h[cl], s->loop_graph, 0, cudaGraphCondAssignDefault));
+    cudaGraphNodeParams np_loop{};
+    np_loop.type = cudaGraphNodeTypeConditional;
+    np_loop.conditional.handle = h_loop;
+    np_loop.conditional.type = cudaGraphCondTypeWhile;
+    np_loop.conditional.size = 1;
+    cudaGraphNode_t n_loop;
+    CU(cudaGraphAddNode(&n_loop, s->loop_graph, nullptr, 0, &np_loop));
+    cudaGraph_t body_loop = np_loop.conditional.phGraph_out[0];
+
+    // ---- body of the ADMM loop
+    cudaGraph_t body_round = nullptr;
+    CU(cudaStreamBeginCaptureToGraph(s->sU, body_loop, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+    int rc = REVS_OK;
+    auto capture_body = [&]() -> int {
+        cudaStream_t sHome = s->overlap_home ? s->sH : s->sU;
+        if (s->overlap_home) {
+            CU(cudaEventRecord(s->evV, s->sU));
+            CU(cudaStreamWaitEvent(s->sH, s->evV, 0));
+        }
+        HomeParams hp = home_params(s, 0);
+        hp.p_sch = s->d_psch[0];
+        hp.p_sch_new = s->d_psch[1];
+        hp.iter = &s->d_cnt->iter;
+        CU(launch_home_solve(hp, sHome));
+        if (s->overlap_home) CU(cudaEventRecord(s->evHomeDone, s->sH));
+        QpParams Q = qp_params(s);
+        Q.cond_round = (unsigned long long)h_round;
+        Q.use_cond = 1;
+        int r = launch_init(s, Q, true, false);
+        if (r) return r;
+        // the working-set while node goes into the graph being captured, after what the stream has enqueued so far
+        cudaStreamCaptureStatus st;
+        cudaGraph_t g_cap = nullptr;
+        const cudaGraphNode_t* deps = nullptr;
+        size_t n_deps = 0;
+        CU(cudaStreamGetCaptureInfo(s->sU, &st, nullptr, &g_cap, &deps, &n_deps));
+        cudaGraphNodeParams np_round{};
+        np_round.type = cudaGraphNodeTypeConditional;
+        np_round.conditional.handle = h_round;
+        np_round.conditional.type = cudaGraphCondTypeWhile;
+        np_round.conditional.size = 1;
+        cudaGraphNode_t n_round;
+        CU(cudaGraphAddNode(&n_round, g_cap, deps, n_deps, &np_round));
+        body_round = np_round.conditional.phGraph_out[0];
+        CU(cudaStreamUpdateCaptureDependencies(s->sU, &n_round, 1, cudaStreamSetCaptureDependencies));
+        if (s->overlap_home) CU(cudaStreamWaitEvent(s->sU, s->evHomeDone, 0));
+        DualParams D = dual_params(s);
+        D.iter = &s->d_cnt->iter;
+        D.cond_loop = (unsigned long long)h_loop;
+        D.use_cond = 1;
+        CU(launch_dual_update(D, s->sU));
+        return REVS_OK;
+    };
+    rc = capture_body();
+    cudaGraph_t got = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(s->sU, &got);
+    if (rc) return rc;
+    if (ce != cudaSuccess) return fail(REVS_ERR_CUDA, "capture of the ADMM loop body failed: %s", cudaGetErrorString(ce));
+
+    // ---- body of the working-set loop
+    CU(cudaStreamBeginCaptureToGraph(s->sU, body_round, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+    auto capture_round = [&]() -> int {
+        QpParams Q = qp_params(s);
+        const revs_stats keep = s->stats;             // launch accounting of a captured run comes from the device counters
+        int r = enqueue_round(s, Q, -1, nullptr, nullptr, false, &gc);
+        s->stats = keep;
+        if (r) return r;
+        RoundEndParams E{};
+        E.n_running = &s->d_cnt->n_running;
+        E.n_failed = &s->d_cnt->n_failed;
+        E.infeasible = &s->d_cnt->infeasible;
+        E.round_ctr = &s->d_cnt->round;
+        E.noconv = &s->d_cnt->noconv;
+        E.rounds_total = &s->d_cnt->rounds_total;
+        E.round_max = kQpRoundMax;
+        E.cond_round = (unsigned long long)h_round;
+        E.use_cond = 1;
+        CU(launch_round_end(E, s->sU));
+        return REVS_OK;
+    };
+    rc = capture_round();
+    ce = cudaStreamEndCapture(s->sU, &got);
+    if (rc) return rc;
+    if (ce != cudaSuccess) return fail(REVS_ERR_CUDA, "capture of the working-set loop body failed: %s", cudaGetErrorString(ce));
+    for (int cl = 2; cl < kQpClasses; ++cl) {          // bodies of the class gates: the CTA kernel of that class
+        CU(cudaStreamBeginCaptureToGraph(s->sQ[cl], gc.body[cl], nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+        QpParams Q = qp_params(s);
+        cudaError_t le = launch_utility_qp(Q, s->ncols, cl, s->sQ[cl]);
+        ce = cudaStreamEndCapture(s->sQ[cl], &got);
+        if (le != cudaSuccess || ce != cudaSuccess)
+            return fail(REVS_ERR_CUDA, "capture of QP class %d failed: %s", cl, cudaGetErrorString(le != cudaSuccess ? le : ce));
+    }
+    CU(cudaGraphInstantiate(&s->loop_exec, s->loop_graph, 0));
+    s->gk_kappa = s->kappa; s->gk_vset = s->vset; s->gk_vhigh = s->vhigh; s->gk_tol = s->tol;
+    s->gk_iter_max = s->iter_max; s->gk_flags = flags;
+    return REVS_OK;
+}
 }  // namespace
 
 int revs_admm_step(revs_solver* s, double sums[3]) { return admm_step_impl(s, sums, true); }
@@ -1032,32 +1222,55 @@ int revs_admm_step(revs_solver* s, double sums[3]) { return admm_step_impl(s, su
 int revs_solve_admm(revs_solver* s, double kappa, int iter_max, double vset, double vlow, double vhigh,
                     double tol, int* iters_done) {
     const double th0 = now_ms();
-    g_host_sync_ms = 0.0;
-    for (double& v : g_cat_ms) v = 0.0;
     int rc = revs_admm_begin(s, kappa, iter_max, vset, vlow, vhigh);
     if (rc) return rc;
+    s->host_sync_ms = 0.0;
+    for (double& v : s->cat_ms) v = 0.0;
     const double th1 = now_ms();
     s->tol = tol;
-    for (int k = 0; k < iter_max; ++k) {
-        // with a fixed iteration count (tol <= 0, the reference's setting) nothing has to come
-        // back to the host between iterations
-        rc = admm_step_impl(s, nullptr, tol > 0.0 || k == iter_max - 1);
+    if (s->use_graph) {
+        // one graph launch: both loops run on the device (capture_loop)
+        if ((rc = prepare_sensitivity(s))) return rc;
+        if ((rc = capture_loop(s))) { s->tol = 0.0; return rc; }
+        CU(cudaGraphLaunch(s->loop_exec, s->sU));
+        CU(cudaMemcpyAsync(s->h_cnt, s->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, s->sU));
+        CU(cudaEventRecord(s->evT1, s->sU));
+        CU(cudaEventRecord(s->evDualDone, s->sU));
+        rc = finish_sync(s, nullptr);
+        s->tol = 0.0;
+        s->k = s->h_cnt->iter;
+        s->cur = s->k & 1;
+        s->stats.admm_iterations = s->k;
+        s->stats.qp_outer_iterations = (int64_t)s->h_cnt->rounds_total;
+        s->stats.gemm_launches = (int64_t)s->h_cnt->rounds_total;
+        s->stats.gemm_full_launches = s->k;
+        s->stats.qp_warp_rounds = (s->use_warp_kernel && s->zg.warp_n > 0) ? (int64_t)s->h_cnt->rounds_total : 0;
+        s->stats.kernel_launches += (int64_t)s->k * 3 + (int64_t)s->h_cnt->rounds_total * round_launches(s);
         if (rc) return rc;
-        if (tol > 0.0 && s->h_cnt->res.converged) break;
+    } else {
+        for (int k = 0; k < iter_max; ++k) {
+            // with a fixed iteration count (tol <= 0, the reference's setting) nothing has to come
+            // back to the host between iterations
+            rc = admm_step_impl(s, nullptr, tol > 0.0 || k == iter_max - 1);
+            if (rc) { s->tol = 0.0; return rc; }
+            if (tol > 0.0 && s->h_cnt->res.converged) break;
+        }
+        s->tol = 0.0;
     }
-    s->tol = 0.0;
-    if (getenv("REVS_DEBUG_HOST"))
-        fprintf(stderr, "[revs host] dev %d: begin %.3f ms, loop %.3f ms (waiting in round syncs %.3f ms), device span %.3f ms | "
-                "span sums: screen %.2f+%.2f home %.2f dual %.2f cls1 %.2f cls2-3 %.2f init %.2f warp8 %.2f warp4 %.2f sweep %.2f\n",
-                s->device, th1 - th0, now_ms() - th1, g_host_sync_ms, s->stats.total_ms, g_cat_ms[5], g_cat_ms[0], g_cat_ms[1],
-                g_cat_ms[2], g_cat_ms[3], g_cat_ms[4], g_cat_ms[6], g_cat_ms[7], g_cat_ms[8], g_cat_ms[9]);
+    if (s->debug_host)
+        fprintf(stderr, "[revs host] dev %d: begin %.3f ms, loop %.3f ms (waiting in round syncs %.3f ms), device span %.3f ms, %s | "
+                "span sums: screen %.2f+%.2f home %.2f dual %.2f cls1 %.2f cls2-3 %.2f init %.2f warp-mid/big %.2f warp-small %.2f\n",
+                s->device, th1 - th0, now_ms() - th1, s->host_sync_ms, s->stats.total_ms, s->use_graph ? "captured loop" : "host-driven loop",
+                s->cat_ms[5], s->cat_ms[0], s->cat_ms[1], s->cat_ms[2], s->cat_ms[3], s->cat_ms[4], s->cat_ms[6], s->cat_ms[7], s->cat_ms[8]);
     if (iters_done) *iters_done = s->k;
     return REVS_OK;
 }
 
-int revs_get_results(const revs_solver* s, double* P_sch, double* P_ev, double* SOC, double* diff) {
+int revs_get_results(const revs_solver* s, double* P_sch, double* P_ev, double* SOC, double* diff, int diff_rows) {
     if (!s) return fail(REVS_ERR_ARG, "null solver");
     if (s->k == 0) return fail(REVS_ERR_ARG, "no ADMM iteration has run");
+    if (diff && diff_rows < s->k)
+        return fail(REVS_ERR_ARG, "diff holds %d rows but %d ADMM iterations have run", diff_rows, s->k);
     CU(cudaSetDevice(s->device));
     int rc;
     if (P_sch && (rc = d2h_homes(s, P_sch, s->d_psch[s->cur], s->T))) return rc;
@@ -1370,7 +1583,16 @@ int revs_screen_contract(int device, int M, int K, int T, const double* A, const
 
 int revs_set_option(revs_solver* s, const char* name, double value) {
     if (!s || !name) return fail(REVS_ERR_ARG, "bad arguments");
-    if (!strcmp(name, "screen")) { s->screen = value != 0.0; return REVS_OK; }
+    const bool mid_run = s->running && s->k > 0 && s->k < s->iter_max;
+    if (!strcmp(name, "screen")) {
+        // the error bound of the BF16 screening pass (kScreenUp) holds up to 16384 residences per zone, and the
+        // bf16 copy of the iterate is only maintained while screening is on
+        if (value != 0.0 && s->zg.max_n > 16384) return fail(REVS_ERR_ARG, "screening is limited to zones of at most 16384 residences");
+        if (mid_run) return fail(REVS_ERR_ARG, "'screen' cannot change between revs_admm_step calls of one run");
+        s->screen = value != 0.0;
+        return REVS_OK;
+    }
+    if (!strcmp(name, "graph")) { s->use_graph = value != 0.0; return REVS_OK; }   // 0: host-driven loop with per-kernel event spans (profiling)
     if (!strcmp(name, "warp_kernel")) { s->use_warp_kernel = value != 0.0; return REVS_OK; }
     if (!strcmp(name, "overlap_home")) { s->overlap_home = value != 0.0; return REVS_OK; }
     if (!strcmp(name, "priority")) {

@@ -1,7 +1,7 @@
 // Voltage SCREENING contraction  V~ = R * G  in BF16 on the tensor cores, FP32 accumulate.
 //
 // Inside the ADMM loop the operator's LinDistFlow check (R_res @ g of Utility.network,
-// lpsolver.py:179-190) only has to answer "which rows can violate v <= u?".  All terms of
+// lpsolver.py:183-194) only has to answer "which rows can violate v <= u?".  All terms of
 // R g are non-negative, so a low-precision product has a rigorous RELATIVE error bound:
 //     |R~ - R| <= 2^-9 R,  |g~ - g| <= 2^-9 g   (round to nearest BF16, via FP32)
 //     FP32 accumulation of K <= 65536 exact BF16xBF16 products: <= K 2^-24 relative
@@ -178,15 +178,18 @@ cudaError_t launch_to_bf16(const double* in, void* out, size_t n, cudaStream_t s
     return cudaGetLastError();
 }
 
+cudaError_t screen_prepare() {
+    static std::atomic<unsigned long long> attr_devices{0};
+    if (first_use_on_device(attr_devices))
+        return cudaFuncSetAttribute(screen_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSSmem);
+    return cudaSuccess;
+}
+
 cudaError_t launch_screen(const ScreenProblem* d_problems, const ContractTile* d_tiles, int n_tiles, int T, double thr,
                           cudaStream_t stream) {
     if (n_tiles == 0) return cudaSuccess;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(screen_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSSmem);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    cudaError_t pe = screen_prepare();
+    if (pe != cudaSuccess) return pe;
     screen_bf16_kernel<<<dim3(n_tiles, (T + kSBN - 1) / kSBN), kSThreads, kSSmem, stream>>>(d_problems, d_tiles, T, thr);
     return cudaGetLastError();
 }

@@ -227,16 +227,19 @@ cudaError_t screen_tc5_encode(void* host_map, const void* gptr, uint64_t rows, u
 uint32_t screen_tc5_box_rows_a() { return kBM; }
 uint32_t screen_tc5_box_rows_b() { return kBN; }
 
+cudaError_t screen_tc5_prepare() {
+    static std::atomic<unsigned long long> attr_devices{0};
+    if (first_use_on_device(attr_devices))
+        return cudaFuncSetAttribute(screen_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemT);
+    return cudaSuccess;
+}
+
 cudaError_t launch_screen_tc5(const ScreenProblem* d_problems, const ContractTile* d_tiles, int n_tiles, const void* d_maps_a,
                               const void* d_map_b, const int* d_b_col0, int T, double thr, cudaStream_t stream) {
     if (n_tiles == 0) return cudaSuccess;
     if (T > kBN) return cudaErrorInvalidValue;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(screen_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemT);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    cudaError_t pe = screen_tc5_prepare();
+    if (pe != cudaSuccess) return pe;
     screen_tc5_kernel<<<n_tiles, kThreadsT, kSmemT, stream>>>(d_problems, d_tiles, reinterpret_cast<const CUtensorMap*>(d_maps_a),
                                                             reinterpret_cast<const CUtensorMap*>(d_map_b), d_b_col0, T, thr);
     return cudaGetLastError();

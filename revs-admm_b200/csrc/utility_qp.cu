@@ -1,6 +1,6 @@
 // Operator (utility) sub-problem of the ADMM loop: one CTA per (feeder, hour) column.
 //
-// Reference: class Utility (lpsolver.py:160-240), a Gurobi QP over all residences and
+// Reference: class Utility (lpsolver.py:163-238), a Gurobi QP over all residences and
 // hours at once.  It separates over hours; each hour is the Euclidean projection of
 //     z = (P_est + P_sch)/2 - Gamma/kappa
 // onto { g >= 0,  R g <= u },  u = vhigh^2 - vset^2  (Gurobi's default lb=0; the vlow row
@@ -980,7 +980,7 @@ __global__ void __launch_bounds__(THREADS, MINB) utility_qp_kernel(QpParams P) {
 // working-set size (>= 3, 2, 1, 0).  mode 0 (first round): a warp-class column without
 // multipliers and without a screening candidate is already solved (g = [z]_+) and never
 // reaches a QP kernel.  mode 2 (sweep): only columns handed over during this round.
-// order_count must be zero.
+// order_count must be zero.  mode < 0: mode 0 / 1 by the device round counter.
 __global__ void __launch_bounds__(256) order_columns_kernel(QpParams P, int mode, int* __restrict__ order,
                                                             int* __restrict__ order_count) {
     __shared__ int cnt[kQpLists], base[kQpLists];
@@ -990,6 +990,7 @@ __global__ void __launch_bounds__(256) order_columns_kernel(QpParams P, int mode
     const int c = blockIdx.x * blockDim.x + tid;
     int li = -1, pos = 0;
     FeederDev fd{};
+    if (mode < 0) mode = (P.round_ctr && *P.round_ctr > 0) ? 1 : 0;     // captured graph: the round counter lives on the device
     if (c < P.ncols && P.status[c] == 0) {
         const int cl = P.cls[c];
         if (mode == 2) {
@@ -999,7 +1000,10 @@ __global__ void __launch_bounds__(256) order_columns_kernel(QpParams P, int mode
         } else {
             const int m = P.wcount[c];
             if (mode == 0 && m == 0 && P.cand && P.cand[c] == 0) { P.status[c] = 1; P.inner_ok[c] = 1; }
-            else { fd = P.feeders[c / P.T]; li = kQpClasses + (fd.n <= 128 ? 0 : kQpBuckets) + (m >= 3 ? 0 : 3 - m); }
+            else {
+                fd = P.feeders[c / P.T];
+                li = (fd.n <= 128 ? kQpClasses : (fd.n <= 256 ? kQpClasses + kQpBuckets : kListBig)) + (m >= 3 ? 0 : 3 - m);
+            }
         }
         if (li >= 0) pos = atomicAdd(&cnt[li], 1);
     }
@@ -1019,6 +1023,33 @@ cudaError_t launch_order_columns(const QpParams& P, int mode, int* order, int* o
     return cudaGetLastError();
 }
 
+__global__ void round_end_kernel(RoundEndParams P) {
+    if (threadIdx.x != 0) return;
+    const int running = *P.n_running;
+    const int round = *P.round_ctr + 1;
+    *P.round_ctr = round;
+    *P.rounds_total += 1ull;
+    const bool err = *P.n_failed != 0 || *P.infeasible != 0;
+    bool more = running > 0 && !err;
+    if (more && round >= P.round_max) { *P.noconv = 1; more = false; }
+    if (P.use_cond) cudaGraphSetConditional((cudaGraphConditionalHandle)P.cond_round, more ? 1u : 0u);
+}
+
+__global__ void class_gate_kernel(ClassGateParams P) {
+    const int cl = P.first_gated + threadIdx.x;
+    if (cl < kQpClasses) cudaGraphSetConditional((cudaGraphConditionalHandle)P.cond[cl], P.order_count[cl] > 0 ? 1u : 0u);
+}
+
+cudaError_t launch_class_gate(const ClassGateParams& P, cudaStream_t stream) {
+    class_gate_kernel<<<1, 32, 0, stream>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_round_end(const RoundEndParams& P, cudaStream_t stream) {
+    round_end_kernel<<<1, 32, 0, stream>>>(P);
+    return cudaGetLastError();
+}
+
 constexpr int kMinB0 = 6, kMinB1 = 3;    // resident CTAs per SM the small / medium instantiations are compiled for
 
 cudaError_t launch_utility_qp(const QpParams& P, int grid, int cls, cudaStream_t stream) {
@@ -1028,24 +1059,25 @@ cudaError_t launch_utility_qp(const QpParams& P, int grid, int cls, cudaStream_t
     auto k0 = utility_qp_kernel<32, 128, 1, kMinB0>;
     auto k1 = utility_qp_kernel<64, 256, 2, kMinB1>;
     auto k2 = utility_qp_kernel<kWMax, 256, 3, 1>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S1));
+    // function attributes are per device: set once for every device this process launches on
+    static int n_sm_dev[64] = {0};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    dev &= 63;
+    if (!n_sm_dev[dev]) {
+        int n = 0;
+        e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S1));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S2));
         // many small CTAs per SM: ask for the largest shared-memory carve-out
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k0, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k1, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        n_sm_dev[dev] = n;
     }
     if (grid <= 0) return cudaSuccess;
-    static int n_sm = 0;
-    if (!n_sm) {
-        int dev = 0;
-        cudaError_t e = cudaGetDevice(&dev);
-        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (e != cudaSuccess) return e;
-    }
+    const int n_sm = n_sm_dev[dev];
     // at most one wave of resident CTAs; they pull columns from the class queue
     if (cls == 1) k0<<<std::min(grid, n_sm * kMinB0), 128, sizeof(S0), stream>>>(P);
     else if (cls == 2) k1<<<std::min(grid, n_sm * kMinB1), 256, sizeof(S1), stream>>>(P);

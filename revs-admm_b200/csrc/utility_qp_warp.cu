@@ -57,11 +57,15 @@ constexpr int kPassMaxW = 10;                // admit / solve / verify passes be
 constexpr int kRecheckMaxW = 256;             // rows re-evaluated exactly per verification; more -> next screening pass
 constexpr int kHysteresisW = 8;              // warm working sets above kWW - this start in class 1 (long columns: a whole CTA each)
 
-struct WarpSmem {
+template <int CACHE>
+struct WarpSmemT {
     double H[kWW * kHW];      // model Hessian, full symmetric
     double L[kWW * kHW];      // Cholesky factor of the active sub-matrix
-    double rows[kCacheDoubles];
+    double rows[CACHE];
 };
+// zones of up to 256 residences: 1024 doubles of cached working rows per warp (4 CTAs per SM);
+// 257..320 residences (NJ = 10, 3 CTAs per SM): 1536, i.e. at least four full rows
+template <int NJ> struct WarpCfg { static constexpr int kCache = NJ <= 8 ? kCacheDoubles : 1536; static constexpr int kCtas = NJ <= 8 ? kCtasPerSm : 3; };
 
 struct WarpStats {
     unsigned long long its = 0;
@@ -120,7 +124,8 @@ __device__ __forceinline__ void recheck_rows(unsigned candk, const double* __res
 
 // ------------------------------------------------------------------------------------------
 template <int NJ>
-__device__ __forceinline__ void solve_column(const QpParams& P, const int4 ent, WarpSmem& sm, WarpStats& st) {
+__device__ __forceinline__ void solve_column(const QpParams& P, const int4 ent, WarpSmemT<WarpCfg<NJ>::kCache>& sm, WarpStats& st) {
+    constexpr int kCacheD = WarpCfg<NJ>::kCache;
     const int lane = threadIdx.x & 31;
     const unsigned full = 0xffffffffu;
     // the work-list entry carries the zone geometry, so every load of the column starts at once
@@ -280,7 +285,7 @@ __device__ __forceinline__ void solve_column(const QpParams& P, const int4 ent, 
         const bool row = lane < m;
 
         // ---- working rows of R into shared memory (as many as fit)
-        const int ncache = min(m, kCacheDoubles / ld);
+        const int ncache = min(m, kCacheD / ld);
         __syncwarp();
 #pragma unroll 1
         for (int a = 0; a < ncache; ++a) {
@@ -657,6 +662,10 @@ __device__ __forceinline__ void solve_column(const QpParams& P, const int4 ent, 
 __global__ void __launch_bounds__(256) qp_init_kernel(QpParams P, int max_warp_n) {
     const int lane = threadIdx.x & 31;
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && P.round_ctr) {     // start of a utility solve: first working-set round follows
+        *P.round_ctr = 0;
+        if (P.use_cond) cudaGraphSetConditional((cudaGraphConditionalHandle)P.cond_round, 1u);
+    }
     if (c >= P.ncols) return;
     const int f = c / P.T, t = c % P.T;
     const FeederDev fd = P.feeders[f];
@@ -741,10 +750,11 @@ cudaError_t launch_qp_init(const QpParams& P, int max_warp_n, cudaStream_t strea
 
 // ------------------------------------------------------------------------------------------
 template <int NJ>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, kCtasPerSm) utility_qp_warp_kernel(QpParams P) {
+__global__ void __launch_bounds__(32 * kWarpsPerCta, WarpCfg<NJ>::kCtas) utility_qp_warp_kernel(QpParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    using Smem = WarpSmemT<WarpCfg<NJ>::kCache>;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    WarpSmem& sm = reinterpret_cast<WarpSmem*>(smem_raw)[wib];
+    Smem& sm = reinterpret_cast<Smem*>(smem_raw)[wib];
     // the bucket lists [list0, list0 + nlists) (hardest first), then list_extra, form one queue
     const int l0 = P.list0, nl = P.nlists;
     int cnt[kQpBuckets], total = 0;
@@ -981,44 +991,68 @@ __global__ void __launch_bounds__(32 * kFastWarps, 4) utility_qp_fast_kernel(QpP
 }
 
 cudaError_t launch_utility_qp_fast(const QpParams& P, cudaStream_t stream) {
-    static int n_sm = 0;
-    if (!n_sm) {
-        int dev = 0;
-        cudaError_t e = cudaGetDevice(&dev);
-        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (e != cudaSuccess) return e;
-    }
+    int dev = 0, n_sm = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
     utility_qp_fast_kernel<<<n_sm * 4, 32 * kFastWarps, 0, stream>>>(P);
     return cudaGetLastError();
 }
 
 int qp_warp_max_n() { return kWarpMaxN; }
 
-// Zones up to 128 residences run the NJ = 4 instantiation, larger ones (own work lists) NJ = 6 if
-// no zone exceeds 192 residences, else NJ = 8; each fits the instruction cache.  ctas_per_sm sizes the persistent grid so that
-// the two can be co-resident on different streams.
-cudaError_t launch_utility_qp_warp(const QpParams& P, int nj, int ctas_per_sm, cudaStream_t stream) {
-    static int n_sm = 0;
-    static bool attr_set = false;
-    const int smem = (int)sizeof(WarpSmem) * kWarpsPerCta;
-    if (!attr_set) {
-        int dev = 0;
-        cudaError_t e = cudaGetDevice(&dev);
-        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(utility_qp_warp_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(utility_qp_warp_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(utility_qp_warp_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e == cudaSuccess && !getenv("REVS_NO_CARVEOUT")) e = cudaFuncSetAttribute(utility_qp_warp_kernel<6>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (e == cudaSuccess && !getenv("REVS_NO_CARVEOUT")) e = cudaFuncSetAttribute(utility_qp_warp_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (e == cudaSuccess && !getenv("REVS_NO_CARVEOUT")) e = cudaFuncSetAttribute(utility_qp_warp_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+// Zones up to 128 residences run the NJ = 4 instantiation, larger ones (own work lists) NJ = 6 / 8 / 10 by the
+// largest zone present (<= 192 / 256 / 320 residences); each fits the instruction cache.  Function attributes
+// are per device: they are set once for every device this process launches on.
+static int g_warp_n_sm[4][64] = {};     // per instantiation and device: SM count once the attributes are set
+
+template <int NJ>
+static cudaError_t prepare_warp_nj(int* n_sm_out) {
+    const int smem = (int)sizeof(WarpSmemT<WarpCfg<NJ>::kCache>) * kWarpsPerCta;
+    int* n_sm = g_warp_n_sm[(NJ - 4) / 2];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    dev &= 63;
+    if (!n_sm[dev]) {
+        int n = 0;
+        e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(utility_qp_warp_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(utility_qp_warp_kernel<NJ>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        n_sm[dev] = n;
     }
-    ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > kCtasPerSm ? kCtasPerSm : ctas_per_sm);
-    if (nj == 8) utility_qp_warp_kernel<8><<<n_sm * ctas_per_sm, 32 * kWarpsPerCta, smem, stream>>>(P);
-    else if (nj == 6) utility_qp_warp_kernel<6><<<n_sm * ctas_per_sm, 32 * kWarpsPerCta, smem, stream>>>(P);
-    else utility_qp_warp_kernel<4><<<n_sm * ctas_per_sm, 32 * kWarpsPerCta, smem, stream>>>(P);
+    if (n_sm_out) *n_sm_out = n_sm[dev];
+    return cudaSuccess;
+}
+
+cudaError_t qp_warp_prepare() {
+    cudaError_t e = prepare_warp_nj<4>(nullptr);
+    if (e == cudaSuccess) e = prepare_warp_nj<6>(nullptr);
+    if (e == cudaSuccess) e = prepare_warp_nj<8>(nullptr);
+    if (e == cudaSuccess) e = prepare_warp_nj<10>(nullptr);
+    return e;
+}
+
+template <int NJ>
+static cudaError_t launch_warp_nj(const QpParams& P, int ctas_per_sm, cudaStream_t stream) {
+    const int smem = (int)sizeof(WarpSmemT<WarpCfg<NJ>::kCache>) * kWarpsPerCta;
+    int nsm = 0;
+    cudaError_t e = prepare_warp_nj<NJ>(&nsm);
+    if (e != cudaSuccess) return e;
+    int n_sm[1] = {nsm};
+    const int dev = 0;
+    const int cmax = WarpCfg<NJ>::kCtas;
+    ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > cmax ? cmax : ctas_per_sm);
+    utility_qp_warp_kernel<NJ><<<n_sm[dev] * ctas_per_sm, 32 * kWarpsPerCta, smem, stream>>>(P);
     return cudaGetLastError();
+}
+
+cudaError_t launch_utility_qp_warp(const QpParams& P, int nj, int ctas_per_sm, cudaStream_t stream) {
+    if (nj == 10) return launch_warp_nj<10>(P, ctas_per_sm, stream);
+    if (nj == 8) return launch_warp_nj<8>(P, ctas_per_sm, stream);
+    if (nj == 6) return launch_warp_nj<6>(P, ctas_per_sm, stream);
+    return launch_warp_nj<4>(P, ctas_per_sm, stream);
 }
 
 int qp_warp_ctas_per_sm() { return kCtasPerSm; }

@@ -3,12 +3,12 @@
 Same function names, arguments and return values as the reference module so that a
 pipeline written against it keeps working:
 
-  GetTariff(path, region, shift)            <region>-tariff.txt            extract.py:15-25
-  GetHomeLoad(path, region_list, shift)     <region>-home-load.csv         extract.py:27-46
-  GetDistNet(path, code)                    <code>-dist-net.gpickle        extract.py:49-86
-  GetCommunity(filename, com_index)         <network>-com.txt              extract.py:88-94
-  get_homes_ev_param(...)                   per-home EV dictionaries       extract.py:97-141
-  combine_result(...)                       result text file               extract.py:143-174
+  GetTariff(path, region, shift)            <region>-tariff.txt            extract.py:16-24
+  GetHomeLoad(path, region_list, shift)     <region>-home-load.csv         extract.py:26-46
+  GetDistNet(path, code)                    <code>-dist-net.gpickle        extract.py:48-80
+  GetCommunity(filename, com_index)         <network>-com.txt              extract.py:82-89
+  get_homes_ev_param(...)                   per-home EV dictionaries       extract.py:91-132
+  combine_result(...)                       result text file               extract.py:134-174
 
 GetDistNet differs in mechanism only: networkx >= 3 no longer ships read_gpickle, and the
 pickles embed shapely geometries that are irrelevant to the optimisation, so the file is

@@ -1,6 +1,6 @@
 """Radial feeders as arrays: what the device needs of the reference's networkx graph.
 
-The reference keeps the feeder as a networkx graph (extract.py:56-88 GetDistNet) and turns
+The reference keeps the feeder as a networkx graph (extract.py:48-80 GetDistNet) and turns
 it into dense sensitivity matrices by inverting its incidence matrix (lpsolver.py:17-26).
 Here the graph is reduced once, on the host, to a rooted tree in topological order
 (parent index, resistance of the edge above each node, residence -> node index); the
@@ -178,7 +178,7 @@ def synthetic_homes(n_homes, T, seed=0, adoption=0.9, rating_kw=4.8, capacity=20
 
 def synthetic_tariff(T):
     """The DVP time-of-use tariff of the reference (input/DVP-tariff.txt) rolled to a day
-    that starts at 06:00 (extract.py:24 with shift=6), repeated to T steps."""
+    that starts at 06:00 (extract.py:23 with shift=6), repeated to T steps."""
     day = np.array([0.07866] * 5 + [0.095111] * 10 + [0.214357] * 3 + [0.095111] * 6)
     day = np.roll(day, -6)
     sph = max(1, T // 24)

@@ -4,11 +4,11 @@ Reference                                   here
 ------------------------------------------  ---------------------------------------------
 compute_Rmat(graph)        lpsolver.py:17   same matrix, from the rooted tree (host; setup only)
 Home(...).solve()          lpsolver.py:45   Home(...)    -> revs_home_step    (1 warp / home)
-Utility(...).solve()       lpsolver.py:160  Utility(...) -> revs_utility_step (working-set QP
+Utility(...).solve()       lpsolver.py:163  Utility(...) -> revs_utility_step (working-set QP
                                             + FP64 tensor-core contraction)
-solve_ADMM(...)            lpsolver.py:244  whole loop on the device -> revs_solve_admm
-solve_residence(...)       lpsolver.py:433  revs_solve_individual
-solve_central(...)         lpsolver.py:466  out of scope of this path (raises)
+solve_ADMM(...)            lpsolver.py:242  whole loop on the device -> revs_solve_admm
+solve_residence(...)       lpsolver.py:430  revs_solve_individual
+solve_central(...)         lpsolver.py:463  out of scope of this path (raises)
 
 Arguments keep the reference's meaning; ``grbpath`` / ``path`` (Gurobi log directories)
 are accepted and ignored.  Everything numerical runs in hand-written CUDA through the C
@@ -80,7 +80,7 @@ def compute_Rmat(graph):
 
 # ------------------------------------------------------------------ sub-problems
 class Home:
-    """One consumer's charging problem (lpsolver.py:45-157); solved on the GPU."""
+    """One consumer's charging problem (lpsolver.py:44-160); solved on the GPU."""
 
     def __init__(self, cost, homedata, p_est, p_sch, gamma, kappa=5.0):
         self.c = list(cost)
@@ -108,7 +108,7 @@ class Home:
 
 
 class Utility:
-    """The operator's estimate under the voltage limits (lpsolver.py:160-240)."""
+    """The operator's estimate under the voltage limits (lpsolver.py:163-238)."""
 
     def __init__(self, graph, P_util, P_sch, Gamma, kappa=5.0, vset=1.0, low=0.95, high=1.05):
         self.tree, self.zones, self.perm = _zones(graph)
@@ -132,7 +132,7 @@ class Utility:
 # ------------------------------------------------------------------ the ADMM loop
 def solve_ADMM(homes, graph, cost, grbpath=None, kappa=5.0, iter_max=15,
                vset=1.0, vlow=0.95, vhigh=1.05, tol=0.0, device=0, return_stats=False):
-    """Iterative ADMM of lpsolver.py:244-293, entirely on the device.
+    """Iterative ADMM of lpsolver.py:242-290, entirely on the device.
 
     Returns ``diff, P_sch, S, C`` exactly like the reference: diff[k][h] for k=1..iter_max,
     and the last iterate's residence profile, EV charger profile and SOC profile per home.
@@ -167,14 +167,14 @@ def solve_residences(tariff, homes, device=0):
 
 
 def solve_residence(tariff, data, path=None):
-    """lpsolver.py:433-463: returns p_opt, s_opt, g_opt of one home."""
+    """lpsolver.py:430-460: returns p_opt, s_opt, g_opt of one home."""
     p, s, g = solve_residences(tariff, {0: data})
     return p[0], s[0], g[0]
 
 
 def solve_central(tariff, homes, dist, path=None, vset=1.0, vmin=0.9, vmax=1.05):
     raise NotImplementedError(
-        "solve_central (lpsolver.py:466-502, one network-wide MILP) is outside the distributed "
+        "solve_central (lpsolver.py:463-502, one network-wide MILP) is outside the distributed "
         "ADMM hot path this package accelerates; see DESIGN.md, scope table row (f)")
 
 
@@ -197,7 +197,7 @@ def _reliability(graph, p_sch, kind, vset, scale_of_zone, fill, device):
 
 
 def compute_voltage(graph, p_sch, vset=1.0, device=0):
-    """drawing.py:62-78: {node: voltage profile} for every non-substation node."""
+    """drawing.py:61-78: {node: voltage profile} for every non-substation node."""
     tree, T, out, _ = _reliability(graph, p_sch, _cabi.REVS_REL_VOLTAGE, vset, lambda z: None, vset, device)
     volt = {n: [vset] * T for n in tree.node_ids}
     for z, V in out.values():
@@ -206,7 +206,7 @@ def compute_voltage(graph, p_sch, vset=1.0, device=0):
     return volt
 
 
-LINE_RATING_KVA = {  # conductor ampacity x voltage, drawing.py:30-40
+LINE_RATING_KVA = {  # conductor ampacity x voltage, drawing.py:30-41
     "OH_Voluta": 95 * 0.24, "OH_Periwinkle": 125 * 0.24, "OH_Conch": 165 * 0.24,
     "OH_Neritina": 220 * 0.24, "OH_Runcina": 265 * 0.24, "OH_Zuzara": 350 * 0.24,
     "OH_Swanate": 145 * 12.47, "OH_Sparrow": 185 * 12.47, "OH_Raven": 240 * 12.47,
@@ -215,7 +215,7 @@ LINE_RATING_KVA = {  # conductor ampacity x voltage, drawing.py:30-40
 
 
 def compute_flows(graph, p_sch, device=0):
-    """drawing.py:28-60: {edge: signed loading = flow / rating} for every line."""
+    """drawing.py:29-59: {edge: signed loading = flow / rating} for every line."""
     def scale(z):
         rating = np.array([np.sqrt(3) * LINE_RATING_KVA[t] for t in z.edge_type])
         return z.edge_sign / rating

@@ -1,7 +1,7 @@
 """Multi-GPU driver: one process per B200, feeders sharded across ranks.
 
 The ADMM loop of the reference couples homes only through their own feeder's sensitivity
-block (Utility.network, lpsolver.py:179-190, is block-diagonal over feeders), so whole
+block (Utility.network, lpsolver.py:183-194, is block-diagonal over feeders), so whole
 feeders are the unit of distribution: every rank owns a contiguous, home-balanced slice of
 the feeder list and runs the device loop on it.  The only exchange per iteration is the
 global convergence test -- three scalars (residual sums and the home-hour count) summed
@@ -152,7 +152,22 @@ class PipelinedSolver:
 
     # ---- solves
     def solve_admm(self, concurrent=True, **kw):
-        return max(self._each(lambda k: self.parts[k].solve_admm(**kw), concurrent=concurrent))
+        """tol <= 0 (the reference's fixed iteration count): every pipeline runs its whole captured loop on its
+        own.  tol > 0: the stopping rule is GLOBAL (both residuals over all homes below tol), so the pipelines
+        advance in lock-step, one iteration at a time, and their residual sums are combined between steps --
+        every pipeline runs the same number of iterations and the result is that of a single solver."""
+        tol = float(kw.get("tol", 0.0) or 0.0)
+        if tol <= 0.0 or len(self.parts) == 1:
+            return max(self._each(lambda k: self.parts[k].solve_admm(**kw), concurrent=concurrent))
+        kw = {k: v for k, v in kw.items() if k != "tol"}
+        kappa, iter_max = float(kw.get("kappa", 5.0)), int(kw.get("iter_max", 15))
+        self._each(lambda k: self.parts[k].admm_begin(**kw), concurrent=concurrent)
+        for it in range(iter_max):
+            sums = np.sum(self._each(lambda k: self.parts[k].admm_step(), concurrent=concurrent), axis=0)
+            r, s_ = residuals(sums, kappa)
+            if r < tol and s_ < tol:
+                return it + 1
+        return iter_max
 
     def schedule(self, trees, homes, cost, out=None, **admm):
         """Host buffers in, host results out -- the whole path of lpsolver.solve_ADMM for this GPU's
@@ -160,6 +175,9 @@ class PipelinedSolver:
         downloads take the PCIe link one pipeline at a time (in pipeline order), so the copies of one
         pipeline overlap the compute of the others instead of sharing the link three ways."""
         import threading
+        if float(admm.get("tol", 0.0) or 0.0) > 0.0 and len(self.parts) > 1:
+            raise ValueError("schedule() overlaps whole pipelines and cannot apply a global stopping rule; "
+                             "use the set_* calls and solve_admm(tol=...) (lock-step) instead")
         H, T = self.H, self.T
         iters = int(admm.get("iter_max", 15))
         if out is None:
@@ -185,26 +203,29 @@ class PipelinedSolver:
             with d2h:
                 self.parts[k].results(iters, want_diff=D is not None, out=sub)
             if D is not None:
-                D[:iters, lo:hi] = sub["diff"]
+                D[:done, lo:hi] = sub["diff"][:done]
             return done
         self._each(f)
         return dict(P_sch=out["P_sch"], P_ev=out["P_ev"], SOC=out["SOC"], diff=D)
 
     def results(self, iters=None, want_diff=True, out=None):
         H, T = self.H, self.T
-        iters = self.parts[0].stats()["admm_iterations"] if iters is None else iters
+        done = [p.stats()["admm_iterations"] for p in self.parts]      # equal: fixed count, or lock-step under tol > 0
+        iters = max(done) if iters is None else max(iters, max(done))
         if out is None:
             out = dict(P_sch=np.empty((H, T)), P_ev=np.empty((H, T)), SOC=np.empty((H, T + 1)),
-                       diff=np.empty((iters, H)) if want_diff else None)
+                       diff=np.zeros((iters, H)) if want_diff else None)
         D = out.get("diff")
+        if D is not None and D.shape[0] < max(done):
+            raise ValueError(f"out['diff'] has {D.shape[0]} rows but {max(done)} iterations ran")
 
         def f(k):
             lo, hi = self.rows[k]
             sub = dict(P_sch=out["P_sch"][lo:hi], P_ev=out["P_ev"][lo:hi], SOC=out["SOC"][lo:hi],
                        diff=self._diff_buf(k, iters) if D is not None else None)
-            self.parts[k].results(iters, want_diff=D is not None, out=sub)
+            self.parts[k].results(iters, want_diff=D is not None, out=sub)       # the library checks the row capacity
             if D is not None:
-                D[:iters, lo:hi] = sub["diff"]
+                D[:done[k], lo:hi] = sub["diff"][:done[k]]
         self._each(f)
         return dict(P_sch=out["P_sch"], P_ev=out["P_ev"], SOC=out["SOC"], diff=D)
 

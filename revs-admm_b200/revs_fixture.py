@@ -4,10 +4,10 @@
     tariff, homes, dist, saved = fx.read_inputs(**input_parameters)
     fx.get_distributed_optimal(tariff, homes, dist, save=True, **optimizer_parameters)
 
-Method names, keyword names and defaults follow revs_fixture.py:59-321, including its
+Method names, keyword names and defaults follow revs_fixture.py:60-330, including its
 quirks that matter for parity: the constructor reads the community from the key
-``comunityID`` (sic, revs_fixture.py:63) and the distributed run reads ``vlow``/``vhigh``
-(revs_fixture.py:248-249) while the YAML provides ``vmin``/``vmax``, so the distributed
+``comunityID`` (sic, revs_fixture.py:64) and the distributed run reads ``vlow``/``vhigh``
+(revs_fixture.py:258-259) while the YAML provides ``vmin``/``vmax``, so the distributed
 optimiser always runs with vlow=0.95, vhigh=1.05.  Optimisation runs on the GPU through
 lpsolver.py of this package.
 """
@@ -64,7 +64,7 @@ class REVS:
         dist = self.read_network(networkID=networkID)
         com = self.read_community(networkID=networkID, com_index=self.com)
         if ev_homes is None or len(ev_homes) == 0:
-            np.random.seed(int(seed))                       # same draw as revs_fixture.py:170-172
+            np.random.seed(int(seed))                       # same draw as revs_fixture.py:174-177
             ev_homes = np.random.choice(com, int(adoption * 1e-2 * len(com)), replace=False)
         homes = get_homes_ev_param(all_homes, dist, ev_homes, rating * 1e-3, capacity,
                                    initial, start, end)
@@ -102,7 +102,7 @@ class REVS:
 
     # ------------------------------------------------------------ reliability check
     def reliability(self, demand, dist, vset=1.0):
-        """Numbers behind plot_result (revs_fixture.py:274-321): per-line loading and
+        """Numbers behind plot_result (revs_fixture.py:282-330): per-line loading and
         per-node voltage of a schedule, computed on the GPU."""
         return compute_flows(dist, demand), compute_voltage(dist, demand, vset=vset)
 

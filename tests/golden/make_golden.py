@@ -11,7 +11,7 @@ committed so that nothing at test/bench time reads /root/reference.
         in .MISSING_LARGE_BLOBS): hourly load = "Residence Usage Profile" minus
         "EV Charger Usage Profile" of the reference's own result files, un-rolled
         by shift_time=6 and converted kW -> W, i.e. the inverse of
-        extract.py:34-54 (GetHomeLoad).
+        extract.py:26-46 (GetHomeLoad).
   tests/golden/ref_out_121144_com2.npz         the reference's result files
         out/121144-com2/{individual,centralized,distributed}/adopt90-rating4800-seed1234.txt,
         individual/adopt90-rating3600-seed1234.txt and individual/adopt70-rating4800-seed1234.txt
@@ -28,7 +28,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def parse_result(path):
-    """Parse the text layout written by extract.py:126-174 (combine_result)."""
+    """Parse the text layout written by extract.py:134-174 (combine_result)."""
     with open(path) as f:
         lines = f.read().split("\n")
     secs, cur, i = {}, None, 0

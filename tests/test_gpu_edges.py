@@ -154,10 +154,11 @@ def test_working_set_overflow_is_loud(gpu_lib):
         assert e.value.code == 4
 
 
-@pytest.mark.parametrize("sizes,vhigh", [([100, 200], 1.02), ([300], 1.02), ([600, 90], 1.05)])
+@pytest.mark.parametrize("sizes,vhigh", [([100, 200], 1.02), ([300], 1.02), ([297, 157, 257, 320, 129], 1.02), ([400], 1.02), ([600, 90], 1.05)])
 def test_zone_size_classes_match_oracle(gpu_lib, sizes, vhigh):
-    """Zones <= 128 / <= 256 (warp-per-column kernels, NJ = 4 / 8), <= 512 (CTA kernel with in-kernel
-    verification) and larger (CTA kernel + re-screening rounds) under limits tight enough to bind."""
+    """Zones <= 128 / <= 256 / <= 320 (warp-per-column kernels, NJ = 4 / 6 / 8 / 10 -- the reference feeder's zones
+    are 157..297), <= 512 (CTA kernel with in-kernel verification) and larger (CTA kernel + re-screening rounds)
+    under limits tight enough to bind."""
     T = 24
     trees, hm, cost = _problem(sizes, T, seed=sum(sizes), r_secondary=1e-3)
     kw = dict(kappa=5.0, iter_max=5, vset=1.0, vlow=0.95, vhigh=vhigh)
@@ -226,3 +227,110 @@ def test_pipelined_solver_equals_single_solver(gpu_lib, pipelines):
     assert 2 <= st["pipelines"] <= min(pipelines, len(sizes)) and st["admm_iterations"] == kw["iter_max"]
     for k in ("P_sch", "P_ev", "SOC", "diff", "P_est", "Gamma"):
         assert np.array_equal(base[k], out[k]), k
+
+
+@pytest.mark.parametrize("sizes,T,vhigh", [([140, 60, 33], 48, 1.015), ([300, 210], 24, 1.02), ([600, 90], 24, 1.05), ([120, 96], 12, 1.02)])
+def test_captured_loop_equals_host_driven_loop(gpu_lib, sizes, T, vhigh):
+    """revs_solve_admm from ONE captured graph (ADMM iterations and working-set rounds decided on the
+    device, CTA classes behind IF nodes) against the host-driven loop (one host sync per round):
+    bit-identical results, same number of working-set rounds -- including zones that need several rounds
+    (> 512 residences: re-screening) and columns handed from class to class."""
+    trees, hm, cost = _problem(sizes, T, seed=5 + sum(sizes), r_secondary=2e-3 if T == 12 else 1e-3)
+    kw = dict(kappa=5.0, iter_max=6, vset=1.0, vlow=0.95, vhigh=vhigh)
+    outs, rounds = [], []
+    for graph in (1, 0):
+        with gpu_lib.Solver(sizes, T) as s:
+            s.set_option("graph", graph)
+            s.set_feeder_trees(trees)
+            s.set_homes(**hm)
+            s.set_tariff(cost)
+            for rep in range(2):                      # the second run re-launches the instantiated graph
+                done = s.solve_admm(**kw)
+            out = s.results(done)
+            out["P_est"], out["Gamma"] = s.estimate()
+            st = s.stats()
+            assert done == kw["iter_max"] and st["admm_iterations"] == done and st["kernel_launches"] > 5 * done
+            rounds.append(st["qp_outer_iterations"])
+            outs.append(out)
+    for k in ("P_sch", "P_ev", "SOC", "diff", "P_est", "Gamma"):
+        assert np.array_equal(outs[0][k], outs[1][k]), k
+    assert rounds[0] == rounds[1] >= kw["iter_max"]
+
+
+def test_captured_loop_stops_on_the_device(gpu_lib):
+    """tol > 0: the last CTA of dual_update_kernel clears the loop condition; same iteration count and
+    results as the host-driven loop, and an infeasible home stops the loop with REVS_ERR_INFEASIBLE."""
+    from revs_admm_b200.feeder import synthetic_feeder, synthetic_homes, synthetic_tariff
+    n, T = 50, 24
+    t = synthetic_feeder(n, seed=2, r_secondary=1e-5)
+    hm = synthetic_homes(n, T, seed=2)
+    res = []
+    for graph in (1, 0):
+        with gpu_lib.Solver([n], T) as s:
+            s.set_option("graph", graph)
+            s.set_feeder_tree(0, t.parent, t.r, t.res_node)
+            s.set_homes(**hm)
+            s.set_tariff(synthetic_tariff(T))
+            done = s.solve_admm(iter_max=40, tol=1e-6)
+            st = s.stats()
+            assert 1 < done < 40 and st["primal_residual"] < 1e-6 and st["dual_residual"] < 1e-6
+            res.append((done, s.results(done)))
+    assert res[0][0] == res[1][0]
+    for k in ("P_sch", "P_ev", "diff"):
+        assert np.array_equal(res[0][1][k], res[1][1][k])
+    hm["end"][:] = hm["start"] + 1                   # one-step window: SOC target unreachable
+    with gpu_lib.Solver([n], T) as s:
+        s.set_feeder_tree(0, t.parent, t.r, t.res_node)
+        s.set_homes(**hm)
+        s.set_tariff(synthetic_tariff(T))
+        with pytest.raises(gpu_lib.RevsError) as e:
+            s.solve_admm(iter_max=5)
+        assert e.value.code == 3
+
+
+def test_pipelined_solver_global_stopping_rule(gpu_lib):
+    """tol > 0 with several pipelines: lock-step iterations, residual sums combined between steps --
+    the iteration count and every result equal the single solver's (pipelines used to stop
+    on their own residuals)."""
+    from revs_admm_b200.feeder import synthetic_feeder, synthetic_homes, synthetic_tariff
+    sizes, T = [50, 40, 30, 60], 24
+    trees = [synthetic_feeder(n, seed=20 + i, r_secondary=(1e-5 if i % 2 else 4e-5)) for i, n in enumerate(sizes)]
+    hm = synthetic_homes(sum(sizes), T, seed=21)
+    cost = synthetic_tariff(T)
+    kw = dict(kappa=5.0, iter_max=60, vset=1.0, vlow=0.95, vhigh=1.05, tol=1e-5)
+    with gpu_lib.Solver(sizes, T) as s:
+        s.set_feeder_trees(trees)
+        s.set_homes(**hm)
+        s.set_tariff(cost)
+        done1 = s.solve_admm(**kw)
+        one = s.results(done1)
+    with gpu_lib.PipelinedSolver(sizes, T, pipelines=3) as s:
+        s.set_feeder_trees(trees)
+        s.set_homes(**hm)
+        s.set_tariff(cost)
+        done3 = s.solve_admm(**kw)
+        three = s.results()
+        with pytest.raises(ValueError):
+            s.results(out=dict(P_sch=np.empty((sum(sizes), T)), P_ev=np.empty((sum(sizes), T)),
+                               SOC=np.empty((sum(sizes), T + 1)), diff=np.empty((done3 - 1, sum(sizes)))))
+    assert 1 < done1 < 60 and done3 == done1
+    for k in ("P_sch", "P_ev", "SOC"):
+        assert np.array_equal(one[k], three[k]), k
+    assert np.array_equal(one["diff"][:done1], three["diff"][:done1])
+
+
+def test_results_buffer_capacity_is_checked(gpu_lib):
+    """revs_get_results refuses a diff buffer with fewer rows than iterations ran."""
+    sizes, T = [20], 24
+    trees, hm, cost = _problem(sizes, T, seed=1)
+    with gpu_lib.Solver(sizes, T) as s:
+        s.set_feeder_trees(trees)
+        s.set_homes(**hm)
+        s.set_tariff(cost)
+        s.solve_admm(iter_max=4)
+        out = dict(P_sch=np.empty((20, T)), P_ev=np.empty((20, T)), SOC=np.empty((20, T + 1)), diff=np.empty((3, 20)))
+        with pytest.raises(gpu_lib.RevsError) as e:
+            s.results(out=out)
+        assert e.value.code == 1
+        with pytest.raises(ValueError):
+            s.results(out=dict(out, P_sch=np.empty((20, T), dtype=np.float32)))

@@ -142,7 +142,7 @@ def test_individual_objective_equals_reference(case121144, golden):
 
 def test_centralized_reference_is_load_only(case121144, golden):
     """The reference's centralized file has no charging at all (no SOC target in
-    solve_central) -- it pins the voltage-row sign and vmin of lpsolver.py:386-387 only."""
+    solve_central) -- it pins the voltage-row sign and vmin of lpsolver.py:403-404 only."""
     assert np.abs(golden["centralized_P_ev"]).max() == 0.0
     res, Rres = O.residence_block(case121144["dist"])
     drop = Rres @ golden["centralized_P_res"]
