@@ -21,9 +21,10 @@
  *   revs_solve_individual                         lpsolver.py:430-460 solve_residence()
  *   revs_reliability                              drawing.py:29-78    compute_flows(),
  *                                                                     compute_voltage()
- *   revs_get_results                              lpsolver.py:289-290 return diff,P_sch,S,C
- *   revs_set_option / revs_get_stats / revs_version / revs_last_error / revs_device_count
- *                                                 no reference counterpart (library plumbing)
+ *   revs_get_results / revs_get_schedule          lpsolver.py:289-290 return diff,P_sch,S,C
+ *   revs_set_option / revs_get_stats / revs_version / revs_last_error / revs_device_count /
+ *   revs_comm_export / revs_comm_attach / revs_comm_detach
+ *                                                 no reference counterpart (library plumbing; the reference is one process)
  */
 #ifndef REVS_ADMM_H
 #define REVS_ADMM_H
@@ -136,6 +137,13 @@ int revs_utility_step(revs_solver* s, double kappa, double vset, double vlow, do
  * that ran; REVS_ERR_ARG when diff_rows is smaller than that (nothing is written past the buffer). */
 int revs_get_results(const revs_solver* s, double* P_sch, double* P_ev, double* SOC,
                      double* diff, int diff_rows);
+/* The same results in compact form: the schedule P_sch [H,T] and the charging decisions as bit masks,
+ * hour_mask [H, mask_words] with mask_words = ceil(T/64), bit (t % 64) of word t/64 set when the charger of the
+ * home runs in step t.  S = rating * bit and the SOC recursion C (lpsolver.py:105-108) follow from the mask and
+ * the per-home inputs the caller already holds, so a third of the bytes of revs_get_results cross PCIe. */
+int revs_get_schedule(const revs_solver* s, double* P_sch, uint64_t* hour_mask, int mask_words,
+                      double* diff, int diff_rows);
+
 /* Utility-side iterates of the last run: P_est [H,T], Gamma [H,T]. */
 int revs_get_estimate(const revs_solver* s, double* P_est, double* Gamma);
 
@@ -159,6 +167,19 @@ int revs_contract(int device, int M, int K, int T, const double* A, const double
  * impl 1 = tcgen05 / TMEM / TMA kernel (T <= 96). */
 int revs_screen_contract(int device, int M, int K, int T, const double* A, const double* B, double* C,
                          int impl);
+
+/* Global stopping rule over the GPUs of one box (one process per GPU, each with its own revs_solver over its
+ * share of the feeders): the residual sums of revs_stats / revs_admm_step / the tol test of revs_solve_admm then
+ * run over ALL ranks.  The all-reduce happens inside the fused dual-update kernel, through mailboxes in peer
+ * (NVLink) memory -- no NCCL call, no extra launch, nothing returns to the host.  Protocol: every rank calls
+ * revs_comm_export (a 64-byte CUDA IPC handle of its mailbox), the host exchanges the handles (e.g.
+ * torch.distributed.all_gather), every rank calls revs_comm_attach with all `world` handles in rank order
+ * (<= 16 ranks).  The mailbox is zeroed by attach: synchronise the ranks (a barrier) between attach and the
+ * first revs_admm_begin.  All ranks must then make the same sequence of revs_admm_begin / step / solve calls.
+ * No reference counterpart (the reference is a single process). */
+int revs_comm_export(revs_solver* s, void* handle64);
+int revs_comm_attach(revs_solver* s, int world, int rank, const void* handles);
+int revs_comm_detach(revs_solver* s);
 
 /* Options: "graph" (default 1) = revs_solve_admm runs the whole loop from one captured CUDA graph whose loops
  * (ADMM iterations, working-set rounds) are decided on the device; 0 = host-driven loop with CUDA-event spans per

@@ -56,6 +56,7 @@ SIGNATURES = {
     "revs_home_step": ([_P, C.c_double, _D, _D, _D, _D, _D], C.c_int),
     "revs_utility_step": ([_P, C.c_double, C.c_double, C.c_double, C.c_double, _D, _D, _D, _D, _D, _D], C.c_int),
     "revs_get_results": ([_P, _D, _D, _D, _D, C.c_int], C.c_int),
+    "revs_get_schedule": ([_P, _D, C.POINTER(C.c_uint64), C.c_int, _D, C.c_int], C.c_int),
     "revs_get_estimate": ([_P, _D, _D], C.c_int),
     "revs_solve_individual": ([_P, _D, _D, _D], C.c_int),
     "revs_reliability": ([_P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), _D, C.c_double, _D, _D], C.c_int),
@@ -63,6 +64,9 @@ SIGNATURES = {
     "revs_set_option": ([_P, C.c_char_p, C.c_double], C.c_int),
     "revs_screen_contract": ([C.c_int, C.c_int, C.c_int, C.c_int, _D, _D, _D, C.c_int], C.c_int),
     "revs_get_stats": ([_P, C.POINTER(Stats)], C.c_int),
+    "revs_comm_export": ([_P, C.c_void_p], C.c_int),
+    "revs_comm_attach": ([_P, C.c_int, C.c_int, C.c_void_p], C.c_int),
+    "revs_comm_detach": ([_P], C.c_int),
 }
 
 _lib = None
@@ -125,6 +129,24 @@ def screen_contract(A, B, impl=0, device=0):
     out = np.empty((M, T))
     _check(load().revs_screen_contract(device, M, K, T, _dp(A), _dp(B), _dp(out), impl))
     return out
+
+
+def expand_schedule(mask, T, has_ev, rating, capacity, initial):
+    """P_ev [H,T] and SOC [H,T+1] (the S and C of lpsolver.py:289-290) from the charging bit masks of
+    Solver.schedule_compact and the per-home inputs: P_ev = rating * bit, SOC[t+1] = SOC[t] + P_ev[t] / capacity
+    (same operation order as the device kernel, so bit-identical with Solver.results)."""
+    mask = np.asarray(mask, dtype=np.uint64)
+    H = mask.shape[0]
+    t = np.arange(T)
+    bits = ((mask[:, t // 64] >> (t % 64).astype(np.uint64)) & np.uint64(1)).astype(bool)
+    ev = np.asarray(has_ev).astype(bool)
+    p_ev = np.where(bits & ev[:, None], np.asarray(rating, dtype=np.float64)[:, None], 0.0)
+    soc = np.zeros((H, T + 1))
+    soc[:, 0] = np.where(ev, initial, 0.0)
+    inc = p_ev / np.where(ev, capacity, 1.0)[:, None]
+    for k in range(T):
+        soc[:, k + 1] = soc[:, k] + inc[:, k]
+    return p_ev, soc
 
 
 class Solver:
@@ -244,6 +266,26 @@ class Solver:
         _check(self.lib.revs_get_results(self._h, _dp(P), _dp(E), _dp(S), _dp(D), 0 if D is None else D.shape[0]))
         return dict(P_sch=P, P_ev=E, SOC=S, diff=None if D is None else D[:done] if out is None else D)
 
+    def schedule_compact(self, want_diff=True, out=None):
+        """P_sch, the charging decisions as bit masks [H, ceil(T/64)] (uint64) and diff -- a third of the
+        bytes of results(); expand_schedule() rebuilds P_ev and SOC from the mask on the host."""
+        H, T = self.H, self.T
+        W = (T + 63) // 64
+        done = self.stats()["admm_iterations"]
+        if out is None:
+            out = dict(P_sch=np.empty((H, T)), mask=np.empty((H, W), dtype=np.uint64),
+                       diff=np.empty((done, H)) if want_diff else None)
+        P, M, D = out["P_sch"], out["mask"], out.get("diff")
+        if P.shape != (H, T) or P.dtype != np.float64 or not P.flags.c_contiguous:
+            raise ValueError("out['P_sch'] must be a C-contiguous float64 [H, T] array")
+        if M.shape != (H, W) or M.dtype != np.uint64 or not M.flags.c_contiguous:
+            raise ValueError("out['mask'] must be a C-contiguous uint64 [H, ceil(T/64)] array")
+        if D is not None and (D.ndim != 2 or D.shape[1] != H or D.dtype != np.float64 or not D.flags.c_contiguous):
+            raise ValueError("out['diff'] must be a C-contiguous float64 [rows, H] array")
+        _check(self.lib.revs_get_schedule(self._h, _dp(P), M.ctypes.data_as(C.POINTER(C.c_uint64)), W, _dp(D),
+                                          0 if D is None else D.shape[0]))
+        return dict(P_sch=P, mask=M, diff=D)
+
     def estimate(self):
         H, T = self.H, self.T
         P, G = np.empty((H, T)), np.empty((H, T))
@@ -265,6 +307,20 @@ class Solver:
                                          rows.ctypes.data_as(C.POINTER(C.c_int32)), _dp(sc), vset,
                                          _dp(Pp), _dp(out)))
         return out
+
+    # ---- residual all-reduce over the GPUs of the box (peer-memory mailboxes, see include/revs_admm.h)
+    def comm_export(self):
+        buf = C.create_string_buffer(64)
+        _check(self.lib.revs_comm_export(self._h, buf))
+        return buf.raw
+
+    def comm_attach(self, world, rank, handles):
+        handles = bytes(handles)
+        assert len(handles) == 64 * world
+        _check(self.lib.revs_comm_attach(self._h, world, rank, handles))
+
+    def comm_detach(self):
+        _check(self.lib.revs_comm_detach(self._h))
 
     def set_option(self, name, value):
         _check(self.lib.revs_set_option(self._h, name.encode(), float(value)))

@@ -23,6 +23,15 @@ namespace revs {
 
 
 
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 __global__ void __launch_bounds__(256, 4) dual_update_kernel(DualParams P) {
     extern __shared__ double tile[];   // [32][T+1]
     __shared__ double s_part[2][8];
@@ -110,13 +119,49 @@ __global__ void __launch_bounds__(256, 4) dual_update_kernel(DualParams P) {
     td = warp_sum(td);
     if (lane == 0) { s_fin[0][warp] = tp; s_fin[1][warp] = td; }
     __syncthreads();
+    __shared__ double s_peer[3][kMaxPeers];
+    if (P.peer.world > 1) {
+        // ---- all-reduce over the GPUs of the box (see PeerReduce): thread r talks to rank r
+        const int r = threadIdx.x;
+        if (r < P.peer.world) {
+            double lp = 0.0, ld = 0.0;
+            for (int w = 0; w < 8; ++w) { lp += s_fin[0][w]; ld += s_fin[1][w]; }
+            const unsigned long long seq = *P.peer.run_seq + (unsigned long long)it + 1ull;
+            const int par = it & 1;
+            PeerSlot* out = P.peer.box[r] + par * P.peer.world + P.peer.rank;       // my slot in rank r's mailbox
+            out->v[0] = lp;
+            out->v[1] = ld;
+            out->v[2] = P.count;
+            __threadfence_system();
+            st_release_sys(&out->seq, seq);
+            PeerSlot* in = P.peer.box[P.peer.rank] + par * P.peer.world + r;         // rank r's slot in my mailbox
+            const long long t0 = clock64();
+            bool ok = true;
+            while (ld_acquire_sys(&in->seq) != seq) {
+                if (clock64() - t0 > 20000000000ll) { ok = false; break; }           // ~10 s: a peer died
+                __nanosleep(200);
+            }
+            if (!ok) atomicExch(P.peer.timeout, 1);
+            s_peer[0][r] = ok ? in->v[0] : 0.0;
+            s_peer[1][r] = ok ? in->v[1] : 0.0;
+            s_peer[2][r] = ok ? in->v[2] : 0.0;
+        }
+        __syncthreads();
+    }
     if (threadIdx.x == 0) {
         tp = 0.0; td = 0.0;
-        for (int w = 0; w < 8; ++w) { tp += s_fin[0][w]; td += s_fin[1][w]; }
-        const double r = sqrt(tp / P.count), sres = P.kappa * sqrt(td / P.count);
+        double count = P.count;
+        if (P.peer.world > 1) {
+            count = 0.0;
+            for (int r = 0; r < P.peer.world; ++r) { tp += s_peer[0][r]; td += s_peer[1][r]; count += s_peer[2][r]; }
+        } else {
+            for (int w = 0; w < 8; ++w) { tp += s_fin[0][w]; td += s_fin[1][w]; }
+        }
+        const double r = sqrt(tp / count), sres = P.kappa * sqrt(td / count);
         const int conv = (P.tol > 0.0 && r < P.tol && sres < P.tol) ? 1 : 0;
-        P.res->sum_primal = tp;
+        P.res->sum_primal = tp;                    // global sums when peers are attached
         P.res->sum_dual = td;
+        P.res->count = count;
         P.res->primal = r;
         P.res->dual = sres;
         P.res->converged = conv;
@@ -125,7 +170,7 @@ __global__ void __launch_bounds__(256, 4) dual_update_kernel(DualParams P) {
             const int k = it + 1;
             *P.iter = k;
             if (P.use_cond) {
-                const bool err = (P.err_a && *P.err_a) || (P.err_b && *P.err_b);
+                const bool err = (P.err_a && *P.err_a) || (P.err_b && *P.err_b) || (P.peer.world > 1 && *P.peer.timeout);
                 cudaGraphSetConditional((cudaGraphConditionalHandle)P.cond_loop, (k < P.iter_max && !conv && !err) ? 1u : 0u);
             }
         }

@@ -149,6 +149,29 @@ cudaError_t launch_pack_rows(const double* src, double* dst, const int64_t* hmap
     return cudaGetLastError();
 }
 
+// charging decisions as bit masks: bit (t & 63) of word t / 64 of compact home h is set when the charger runs in
+// step t.  One warp per home, two ballots per 64-bit word.
+__global__ void hour_mask_kernel(const double* __restrict__ p_ev, const int64_t* __restrict__ hmap, int64_t H, int T,
+                                 int words, unsigned long long* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t h = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (h >= H) return;
+    const double* row = p_ev + hmap[h] * T;
+    for (int w = 0; w < words; ++w) {
+        const int t0 = 64 * w + lane, t1 = t0 + 32;
+        const unsigned lo = __ballot_sync(0xffffffffu, t0 < T && row[t0] > 0.0);
+        const unsigned hi = __ballot_sync(0xffffffffu, t1 < T && row[t1] > 0.0);
+        if (lane == 0) out[h * words + w] = (unsigned long long)lo | ((unsigned long long)hi << 32);
+    }
+}
+
+cudaError_t launch_hour_mask(const double* p_ev, const int64_t* hmap, int64_t H, int T, unsigned long long* out, cudaStream_t s) {
+    if (H == 0) return cudaSuccess;
+    const int wpb = 8;
+    hour_mask_kernel<<<(unsigned)((H + wpb - 1) / wpb), 32 * wpb, 0, s>>>(p_ev, hmap, H, T, (T + 63) / 64, out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_to_time_major(const double* in, int n, int T, double* out, int64_t ld, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
     dim3 grid((n + 31) / 32, (T + 31) / 32), block(32, 8);

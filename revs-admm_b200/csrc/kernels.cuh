@@ -38,8 +38,23 @@ struct ResidualOut {
     double sum_dual;       // sum (P_sch - P_sch_prev)^2
     double primal;         // sqrt(sum_primal / count)
     double dual;           // kappa * sqrt(sum_dual / count)
+    double count;          // home-hours the sums run over (all ranks when peers are attached)
     int converged;
     unsigned ticket;
+};
+
+// All-reduce of the residual sums over the GPUs of one box, done by the last CTA of dual_update_kernel itself
+// through peer-mapped mailboxes (NVLink P2P stores + system-scope release/acquire flags): every rank pushes
+// {sum primal, sum dual, home-hours} into its slot of every peer's mailbox, then collects the slots of its own
+// mailbox in rank order -- the same additions in the same order on every rank, so all ranks take the same
+// convergence decision, and the exchange needs no extra launch and works inside the captured loop.
+constexpr int kMaxPeers = 16;
+struct PeerSlot { double v[3]; unsigned long long seq; };     // 32 bytes; seq = run sequence + iteration + 1
+struct PeerReduce {
+    int world, rank;                          // world <= 1: off
+    PeerSlot* box[kMaxPeers];                 // box[r]: mailbox on GPU r, [2 parities][world slots]; box[rank] is local
+    const unsigned long long* run_seq;        // device word, changed by every revs_admm_begin (stale slots never match)
+    int* timeout;                             // set when a peer did not show up within ~10 s
 };
 
 struct DualParams {
@@ -60,6 +75,7 @@ struct DualParams {
     void* gbf_next;            // optional [T][Hp] __nv_bfloat16 copy of g_next
     double* diff_k;            // [Hp]     out: row k of diff (row 0 when `iter` is given; the kernel adds k * Hp)
     ResidualOut* res;
+    PeerReduce peer;
     double* partials;          // [2][gridDim.x] per-CTA partial sums: the last CTA adds them in a fixed order (reproducible residuals)
     int Hp, T;
     double kappa, tol, count;  // count = real homes * T
@@ -189,6 +205,7 @@ cudaError_t launch_row_norms(const FeederDev* feeders, int n_feeders, const doub
                              cudaStream_t s);
 cudaError_t launch_pack_rows(const double* src, double* dst, const int64_t* hmap, int64_t H, int w, int to_padded,
                              cudaStream_t s);
+cudaError_t launch_hour_mask(const double* p_ev, const int64_t* hmap, int64_t H, int T, unsigned long long* out, cudaStream_t s);
 cudaError_t launch_to_time_major(const double* in, int n, int T, double* out, int64_t ld, cudaStream_t s);
 
 }  // namespace revs

@@ -128,6 +128,13 @@ struct revs_solver {
     double gk_kappa = 0, gk_vset = 0, gk_vhigh = 0, gk_tol = 0;
     int gk_iter_max = 0, gk_flags = -1;
     double* d_respart = nullptr;               // per-CTA partial residual sums of dual_update_kernel
+    // all-reduce of the residual sums over the GPUs of the box (revs_comm_*): peer-mapped mailboxes
+    PeerSlot* d_mailbox = nullptr;             // [2][kMaxPeers] on this device, exported by IPC handle
+    PeerSlot* peer_box[kMaxPeers] = {};        // mailboxes of all ranks as mapped into this process (peer_box[rank] == d_mailbox)
+    int comm_world = 1, comm_rank = 0;
+    unsigned long long comm_run = 0;           // run sequence, advanced by every revs_admm_begin on every rank alike
+    unsigned long long* d_run_seq = nullptr;
+    int* d_comm_timeout = nullptr;
     bool use_warp_kernel = true;               // class 0: one warp per small column (utility_qp_warp.cu)
     bool overlap_home = true;                  // home solve on its own (low priority) stream beside the utility kernels
     bool screen = true;                        // BF16 screening + exact recheck instead of the FP64 contraction in the loop
@@ -563,6 +570,11 @@ void free_all(revs_solver* s) {
                     s->d_start, s->d_end, s->d_nmin, s->d_nmax, s->d_zero_i, s->d_cost, s->d_zt, s->d_lamt,
                     s->d_gt, s->d_vt, s->d_wcount, s->d_widx, s->d_status, s->d_innerok, s->d_cls, s->d_order, s->d_order4, s->d_order_count, s->d_cnt, s->d_diff,
                     s->d_cprob, s->d_ctiles, s->d_respart};
+    for (int r = 0; r < kMaxPeers; ++r)
+        if (s->peer_box[r] && s->peer_box[r] != s->d_mailbox) cudaIpcCloseMemHandle(s->peer_box[r]);
+    if (s->d_mailbox) cudaFree(s->d_mailbox);
+    if (s->d_run_seq) cudaFree(s->d_run_seq);
+    if (s->d_comm_timeout) cudaFree(s->d_comm_timeout);
     if (s->loop_exec) cudaGraphExecDestroy(s->loop_exec);
     if (s->loop_graph) cudaGraphDestroy(s->loop_graph);
     for (void* p : ptrs)
@@ -992,6 +1004,11 @@ int revs_admm_begin(revs_solver* s, double kappa, int iter_max, double vset, dou
         CU(dalloc(&s->d_diff, (size_t)iter_max * s->Hp));
         s->diff_cap = iter_max;
     }
+    if (s->comm_world > 1) {
+        s->comm_run += 1ull << 20;             // every rank calls revs_admm_begin the same number of times
+        CU(cudaMemcpyAsync(s->d_run_seq, &s->comm_run, sizeof(unsigned long long), cudaMemcpyHostToDevice, s->sU));
+        CU(cudaMemsetAsync(s->d_comm_timeout, 0, sizeof(int), s->sU));
+    }
     CU(cudaEventRecord(s->evT0, s->sU));
     CU(cudaEventRecord(s->evDualDone, s->sU));
     return REVS_OK;
@@ -1010,6 +1027,11 @@ DualParams dual_params(revs_solver* s) {
     D.cond_loop = 0;
     D.use_cond = 0;
     D.partials = s->d_respart;
+    D.peer.world = s->comm_world;
+    D.peer.rank = s->comm_rank;
+    for (int r = 0; r < kMaxPeers; ++r) D.peer.box[r] = s->peer_box[r];
+    D.peer.run_seq = s->d_run_seq;
+    D.peer.timeout = s->d_comm_timeout;
     D.gamma = s->d_gamma;
     D.p_est = s->d_pest;
     D.z_t = s->d_zt;
@@ -1031,6 +1053,11 @@ int finish_sync(revs_solver* s, double sums[3]) {
     CU(cudaStreamSynchronize(s->sH));
     spans_collect(s);
     int rc = check_device_flags(s);
+    if (rc == REVS_OK && s->comm_world > 1) {
+        int to = 0;
+        CU(cudaMemcpy(&to, s->d_comm_timeout, sizeof(int), cudaMemcpyDeviceToHost));
+        if (to) rc = fail(REVS_ERR_CUDA, "a peer GPU did not deliver its residual sums within 10 s (rank %d of %d)", s->comm_rank, s->comm_world);
+    }
     if (rc) { s->running = false; return rc; }
     s->stats.primal_residual = s->h_cnt->res.primal;
     s->stats.dual_residual = s->h_cnt->res.dual;
@@ -1044,7 +1071,7 @@ int finish_sync(revs_solver* s, double sums[3]) {
     if (sums) {
         sums[0] = s->h_cnt->res.sum_primal;
         sums[1] = s->h_cnt->res.sum_dual;
-        sums[2] = (double)s->H * s->T;
+        sums[2] = s->comm_world > 1 ? s->h_cnt->res.count : (double)s->H * s->T;
     }
     return REVS_OK;
 }
@@ -1101,7 +1128,7 @@ int admm_step_impl(revs_solver* s, double sums[3], bool sync_now) {
 // round number) from device counters, so the bodies are captured once.  Nothing returns to the host until the
 // schedule is finished: no round trip per working-set round, no launch latency per kernel.
 int capture_loop(revs_solver* s) {
-    const int flags = (s->screen ? 1 : 0) | (s->screen_impl << 1) | (s->overlap_home ? 4 : 0) | (s->use_warp_kernel ? 8 : 0) | (s->use_fast ? 16 : 0);
+    const int flags = (s->screen ? 1 : 0) | (s->screen_impl << 1) | (s->overlap_home ? 4 : 0) | (s->use_warp_kernel ? 8 : 0) | (s->use_fast ? 16 : 0) | (s->comm_world << 8) | (s->comm_rank << 16);
     if (s->loop_exec && s->gk_kappa == s->kappa && s->gk_vset == s->vset && s->gk_vhigh == s->vhigh && s->gk_tol == s->tol &&
         s->gk_iter_max == s->iter_max && s->gk_flags == flags)
         return REVS_OK;
@@ -1292,6 +1319,21 @@ int revs_get_results(const revs_solver* s, double* P_sch, double* P_ev, double* 
     }
     CU(cudaStreamSynchronize(s->sU));
     return REVS_OK;
+}
+
+int revs_get_schedule(const revs_solver* s, double* P_sch, uint64_t* hour_mask, int mask_words, double* diff, int diff_rows) {
+    if (!s) return fail(REVS_ERR_ARG, "null solver");
+    if (s->k == 0) return fail(REVS_ERR_ARG, "no ADMM iteration has run");
+    if (hour_mask && mask_words != (s->T + 63) / 64) return fail(REVS_ERR_ARG, "mask_words must be ceil(T / 64) = %d", (s->T + 63) / 64);
+    CU(cudaSetDevice(s->device));
+    if (hour_mask && s->H > 0) {
+        // the staging buffer holds H (T + 1) doubles >= H ceil(T / 64) words
+        unsigned long long* d_mask = reinterpret_cast<unsigned long long*>(s->d_stage);
+        CU(launch_hour_mask(s->d_pev, s->d_hmap, s->H, s->T, d_mask, s->sU));
+        const_cast<revs_solver*>(s)->stats.kernel_launches++;
+        CU(cudaMemcpyAsync(hour_mask, d_mask, (size_t)s->H * mask_words * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->sU));
+    }
+    return revs_get_results(s, P_sch, nullptr, nullptr, diff, diff_rows);
 }
 
 int revs_get_estimate(const revs_solver* s, double* P_est, double* Gamma) {
@@ -1578,6 +1620,56 @@ int revs_screen_contract(int device, int M, int K, int T, const double* A, const
     for (int i = 0; i < M; ++i)
         for (int t = 0; t < T; ++t) C[(size_t)i * T + t] = (double)out[(size_t)t * M + i];
     cleanup();
+    return REVS_OK;
+}
+
+int revs_comm_export(revs_solver* s, void* handle64) {
+    if (!s || !handle64) return fail(REVS_ERR_ARG, "bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CU(cudaSetDevice(s->device));
+    if (!s->d_mailbox) {
+        CU(dalloc(&s->d_mailbox, (size_t)2 * kMaxPeers));
+        CU(dalloc(&s->d_run_seq, (size_t)1));
+        CU(dalloc(&s->d_comm_timeout, (size_t)1));
+    }
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, s->d_mailbox));
+    memcpy(handle64, &h, sizeof h);
+    return REVS_OK;
+}
+
+int revs_comm_attach(revs_solver* s, int world, int rank, const void* handles) {
+    if (!s || !handles || world < 1 || world > kMaxPeers || rank < 0 || rank >= world)
+        return fail(REVS_ERR_ARG, "bad arguments (world 1..%d)", kMaxPeers);
+    if (!s->d_mailbox) return fail(REVS_ERR_ARG, "call revs_comm_export first");
+    CU(cudaSetDevice(s->device));
+    int rc = revs_comm_detach(s);
+    if (rc) return rc;
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) { s->peer_box[r] = s->d_mailbox; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)handles + (size_t)r * sizeof h, sizeof h);
+        void* ptr = nullptr;
+        CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        s->peer_box[r] = reinterpret_cast<PeerSlot*>(ptr);
+    }
+    CU(cudaMemset(s->d_mailbox, 0, sizeof(PeerSlot) * 2 * kMaxPeers));
+    s->comm_world = world;
+    s->comm_rank = rank;
+    s->comm_run = 0;
+    return REVS_OK;
+}
+
+int revs_comm_detach(revs_solver* s) {
+    if (!s) return fail(REVS_ERR_ARG, "null solver");
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->sU));
+    for (int r = 0; r < kMaxPeers; ++r) {
+        if (s->peer_box[r] && s->peer_box[r] != s->d_mailbox) CU(cudaIpcCloseMemHandle(s->peer_box[r]));
+        s->peer_box[r] = nullptr;
+    }
+    s->comm_world = 1;
+    s->comm_rank = 0;
     return REVS_OK;
 }
 

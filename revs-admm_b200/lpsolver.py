@@ -8,7 +8,7 @@ Utility(...).solve()       lpsolver.py:163  Utility(...) -> revs_utility_step (w
                                             + FP64 tensor-core contraction)
 solve_ADMM(...)            lpsolver.py:242  whole loop on the device -> revs_solve_admm
 solve_residence(...)       lpsolver.py:430  revs_solve_individual
-solve_central(...)         lpsolver.py:463  out of scope of this path (raises)
+solve_central(...)         lpsolver.py:463  the reference's program in closed form + GPU voltage check
 
 Arguments keep the reference's meaning; ``grbpath`` / ``path`` (Gurobi log directories)
 are accepted and ignored.  Everything numerical runs in hand-written CUDA through the C
@@ -172,10 +172,46 @@ def solve_residence(tariff, data, path=None):
     return p[0], s[0], g[0]
 
 
-def solve_central(tariff, homes, dist, path=None, vset=1.0, vmin=0.9, vmax=1.05):
-    raise NotImplementedError(
-        "solve_central (lpsolver.py:463-502, one network-wide MILP) is outside the distributed "
-        "ADMM hot path this package accelerates; see DESIGN.md, scope table row (f)")
+def solve_central(tariff, homes, dist, path=None, vset=1.0, vmin=0.9, vmax=1.05, device=0):
+    """Centralized schedule, lpsolver.py:463-502, with the reference's exact semantics.
+
+    The reference's program minimises the tariff cost of g = load + p (objective_centralized,
+    lpsolver.py:418-428) over the charger variables of add_home_EV (lpsolver.py:338-379: binary
+    status, init <= soc <= 1 -- and, unlike class Home, NO final-SOC row) under the voltage rows of
+    network_constraints (lpsolver.py:386-405):  -R g <= vmax^2 - vset^2  (vacuous for g >= 0) and
+    -R g >= vmin^2 - vset^2, i.e.  R g <= vset^2 - vmin^2.  Charging only adds cost and voltage drop,
+    so with a positive tariff the optimum is p = 0 if the base load satisfies the voltage rows, and the
+    program is infeasible otherwise -- the reference's own centralized result file
+    (out/121144-com2/centralized) holds exactly that: no charging, SOC constant at its initial value.
+
+    What remains to compute is the reliability check of the base load: R_res @ load on the GPU (FP64
+    tensor-core contraction, revs_reliability) against vset^2 - vmin^2 for every residence and hour.
+    Returns p_opt, s_opt, g_opt like the reference; raises RuntimeError where the reference prints
+    'No solution found' and exits."""
+    tariff = np.asarray(tariff, dtype=np.float64)
+    if not (tariff > 0).all():
+        raise NotImplementedError("solve_central: a non-positive tariff makes charging profitable; the closed form "
+                                  "used here (see docstring) needs tariff > 0")
+    tree, zones, perm = _zones(dist)
+    res = tree.res_ids
+    T = len(tariff)
+    limit = vset * vset - vmin * vmin
+    if zones:
+        P = np.array([np.asarray(homes[res[j]]["LOAD"], dtype=np.float64) for j in perm]).reshape(len(perm), T)
+        off = np.concatenate([[0], np.cumsum([len(h) for _, h in zones])])
+        worst = -np.inf
+        with _cabi.Solver([len(h) for _, h in zones], T, device=device) as s:
+            s.set_feeder_trees([z for z, _ in zones])
+            for f, (z, _) in enumerate(zones):
+                drop = s.reliability(f, _cabi.REVS_REL_DROP, z.res_node, P=P[off[f]:off[f + 1]])
+                worst = max(worst, float(drop.max()))
+        if worst > limit + 1e-9 or not (vmax * vmax - vset * vset >= 0.0):
+            raise RuntimeError(f"No solution found: the base load alone drops the squared voltage by {worst:.6g} pu "
+                               f"(limit vset^2 - vmin^2 = {limit:.6g}); the reference's centralized program is infeasible")
+    p_opt = {h: np.zeros(T) for h in res}
+    s_opt = {h: np.full(T + 1, float(homes[h]["EV"]["initial"]) if homes[h]["EV"] else 0.0) for h in res}
+    g_opt = {h: np.asarray(homes[h]["LOAD"], dtype=np.float64).copy() for h in res}
+    return p_opt, s_opt, g_opt
 
 
 # ------------------------------------------------------------------ reliability check

@@ -38,20 +38,41 @@ def allreduce_sums(sums, device=None):
     return t.cpu().numpy()
 
 
+def attach_peers(solver):
+    """Give `solver` (a _cabi.Solver on this rank's GPU) the global stopping rule: exchange the IPC handles of
+    the residual mailboxes over torch.distributed and attach them (include/revs_admm.h: revs_comm_*).  From then
+    on the all-reduce of the residual sums happens inside the fused dual-update kernel, over NVLink peer memory,
+    every iteration -- also inside the captured loop of solve_admm(tol > 0).  No-op for a single rank."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return False
+    world, rank = dist.get_world_size(), dist.get_rank()
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    mine = torch.frombuffer(bytearray(solver.comm_export()), dtype=torch.uint8).to(dev)
+    got = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(got, mine)
+    solver.comm_attach(world, rank, b"".join(bytes(t.cpu().numpy().tobytes()) for t in got))
+    dist.barrier()                      # every mailbox is zeroed and mapped before anyone starts a run
+    return True
+
+
 def residuals(total_sums, kappa):
     sp, sd, cnt = total_sums
     return float(np.sqrt(sp / cnt)), float(kappa * np.sqrt(sd / cnt))
 
 
-def run_admm(stepper, kappa=5.0, iter_max=15, vset=1.0, vlow=0.95, vhigh=1.05, tol=0.0, device=None):
+def run_admm(stepper, kappa=5.0, iter_max=15, vset=1.0, vlow=0.95, vhigh=1.05, tol=0.0, device=None, global_sums=False):
     """Drive `stepper` (a _cabi.Solver, or anything with admm_begin/admm_step) for this
-    rank's feeders; stop on the GLOBAL residuals.  Returns (iterations, history)."""
+    rank's feeders one iteration at a time; stop on the GLOBAL residuals.  Returns (iterations, history).
+    ``global_sums``: the stepper's sums already run over all ranks (attach_peers), no host all-reduce.
+    (The fast path is ``attach_peers(solver); solver.solve_admm(tol=...)``: one captured loop per rank.)"""
     stepper.admm_begin(kappa=kappa, iter_max=iter_max, vset=vset, vlow=vlow, vhigh=vhigh)
     history = []
     for k in range(iter_max):
         local = stepper.admm_step()
         if tol > 0.0:
-            r, s = residuals(allreduce_sums(local, device), kappa)
+            r, s = residuals(local if global_sums else allreduce_sums(local, device), kappa)
             history.append((r, s))
             if r < tol and s < tol:
                 return k + 1, history
@@ -169,11 +190,13 @@ class PipelinedSolver:
                 return it + 1
         return iter_max
 
-    def schedule(self, trees, homes, cost, out=None, **admm):
+    def schedule(self, trees, homes, cost, out=None, compact=False, **admm):
         """Host buffers in, host results out -- the whole path of lpsolver.solve_ADMM for this GPU's
         zones.  Every pipeline runs upload -> solve -> download on its own thread; uploads and
         downloads take the PCIe link one pipeline at a time (in pipeline order), so the copies of one
-        pipeline overlap the compute of the others instead of sharing the link three ways."""
+        pipeline overlap the compute of the others instead of sharing the link three ways.
+        ``compact``: results come back as P_sch + charging bit masks + diff (Solver.schedule_compact;
+        _cabi.expand_schedule rebuilds P_ev / SOC on request) -- a third of the D2H bytes."""
         import threading
         if float(admm.get("tol", 0.0) or 0.0) > 0.0 and len(self.parts) > 1:
             raise ValueError("schedule() overlaps whole pipelines and cannot apply a global stopping rule; "
@@ -181,7 +204,11 @@ class PipelinedSolver:
         H, T = self.H, self.T
         iters = int(admm.get("iter_max", 15))
         if out is None:
-            out = dict(P_sch=np.empty((H, T)), P_ev=np.empty((H, T)), SOC=np.empty((H, T + 1)), diff=np.empty((iters, H)))
+            out = dict(P_sch=np.empty((H, T)), diff=np.empty((iters, H)))
+            if compact:
+                out["mask"] = np.empty((H, (T + 63) // 64), dtype=np.uint64)
+            else:
+                out.update(P_ev=np.empty((H, T)), SOC=np.empty((H, T + 1)))
         D = out.get("diff")
         turn = [threading.Event() for _ in range(len(self.parts) + 1)]
         turn[0].set()
@@ -198,15 +225,20 @@ class PipelinedSolver:
             finally:
                 turn[k + 1].set()
             done = self.parts[k].solve_admm(**admm)
-            sub = dict(P_sch=out["P_sch"][lo:hi], P_ev=out["P_ev"][lo:hi], SOC=out["SOC"][lo:hi],
-                       diff=self._diff_buf(k, iters) if D is not None else None)
+            dbuf = self._diff_buf(k, iters) if D is not None else None
             with d2h:
-                self.parts[k].results(iters, want_diff=D is not None, out=sub)
+                if compact:
+                    sub = dict(P_sch=out["P_sch"][lo:hi], mask=out["mask"][lo:hi], diff=dbuf)
+                    self.parts[k].schedule_compact(want_diff=D is not None, out=sub)
+                else:
+                    sub = dict(P_sch=out["P_sch"][lo:hi], P_ev=out["P_ev"][lo:hi], SOC=out["SOC"][lo:hi], diff=dbuf)
+                    self.parts[k].results(iters, want_diff=D is not None, out=sub)
             if D is not None:
                 D[:done, lo:hi] = sub["diff"][:done]
             return done
         self._each(f)
-        return dict(P_sch=out["P_sch"], P_ev=out["P_ev"], SOC=out["SOC"], diff=D)
+        out["diff"] = D
+        return out
 
     def results(self, iters=None, want_diff=True, out=None):
         H, T = self.H, self.T

@@ -334,3 +334,26 @@ def test_results_buffer_capacity_is_checked(gpu_lib):
         assert e.value.code == 1
         with pytest.raises(ValueError):
             s.results(out=dict(out, P_sch=np.empty((20, T), dtype=np.float32)))
+
+
+def test_compact_schedule_download_equals_full_results(gpu_lib):
+    """revs_get_schedule (P_sch + charging bit masks + diff) and expand_schedule on the host give exactly
+    the arrays of revs_get_results, for a single solver and through PipelinedSolver.schedule(compact=True)."""
+    sizes, T = [70, 45, 33], 96
+    trees, hm, cost = _problem(sizes, T, seed=9)
+    kw = dict(kappa=5.0, iter_max=4, vset=1.0, vlow=0.95, vhigh=1.015)
+    with gpu_lib.Solver(sizes, T) as s:
+        s.set_feeder_trees(trees)
+        s.set_homes(**hm)
+        s.set_tariff(cost)
+        done = s.solve_admm(**kw)
+        full = s.results(done)
+        comp = s.schedule_compact()
+    assert comp["mask"].shape == (sum(sizes), 2) and comp["mask"].dtype == np.uint64
+    p_ev, soc = gpu_lib.expand_schedule(comp["mask"], T, hm["has_ev"], hm["rating"], hm["capacity"], hm["initial"])
+    assert np.array_equal(comp["P_sch"], full["P_sch"]) and np.array_equal(comp["diff"], full["diff"])
+    assert np.array_equal(p_ev, full["P_ev"]) and np.array_equal(soc, full["SOC"])
+    with gpu_lib.PipelinedSolver(sizes, T, pipelines=2) as ps:
+        out = ps.schedule(trees, hm, cost, compact=True, **kw)
+    assert np.array_equal(out["P_sch"], full["P_sch"]) and np.array_equal(out["mask"], comp["mask"])
+    assert np.array_equal(out["diff"][:done], full["diff"])

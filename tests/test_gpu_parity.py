@@ -327,3 +327,23 @@ def test_screen_impls_agree_in_the_loop(gpu_lib):
             outs.append(s.results(done))
     for k in ("P_sch", "P_ev", "SOC", "diff"):
         assert np.array_equal(outs[0][k], outs[1][k]), k
+
+
+# ----------------------------------------------------------------- centralized schedule
+def test_centralized_matches_reference_file(gpu_lib, case121144, golden):
+    """solve_central (lpsolver.py:463-502) through REVS.get_centralized_optimal against the reference's own
+    result file out/121144-com2/centralized/adopt90-rating4800-seed1234.txt: residence profiles, charger
+    profiles and SOC profiles equal (the reference's program has no final-SOC row: no charging)."""
+    fx, homes, tariff, dist = case121144["fx"], case121144["homes"], case121144["tariff"], case121144["dist"]
+    Pres, Pev, soc = fx.get_centralized_optimal(tariff, homes, dist, save=False, v0=1.03, vmin=0.90, vmax=1.05)
+    res = [int(h) for h in golden["centralized_res_ids"]]
+    assert list(Pres) == res
+    for i, h in enumerate(res):
+        assert np.abs(np.asarray(Pres[h]) - golden["centralized_P_res"][i]).max() <= 1e-12
+    for k, h in enumerate(golden["centralized_ev_ids"]):
+        assert np.array_equal(Pev[int(h)], golden["centralized_P_ev"][k])
+        assert np.array_equal(soc[int(h)], golden["centralized_SOC"][k])
+    # the voltage rows decide feasibility: with vmin just below v0 the base load alone violates them
+    from revs_admm_b200.lpsolver import solve_central
+    with pytest.raises(RuntimeError, match="No solution found"):
+        solve_central(tariff, homes, dist, None, 1.03, 1.0299, 1.05)

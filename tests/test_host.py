@@ -99,7 +99,35 @@ def test_revs_fixture_interface(case121144):
     assert fx.out_dir.endswith("121144-com2/distributed")
     assert len(case121144["saved"]["ev_homes"]) == 267
     with pytest.raises(NotImplementedError):
-        fx.get_centralized_optimal(case121144["tariff"], case121144["homes"], case121144["dist"])
+        fx.plot_result({}, case121144["dist"])            # plotting is out of scope
+    # no CPU fallback: without a GPU the centralized entry point fails loudly in the library, not silently on the host
+    from revs_admm_b200 import RevsError, device_count
+    try:
+        n_gpu = device_count()
+    except RevsError:
+        n_gpu = 0
+    if n_gpu == 0:
+        with pytest.raises(RevsError):
+            fx.get_centralized_optimal(case121144["tariff"], case121144["homes"], case121144["dist"])
+
+
+def test_config_yaml_has_the_reference_schema():
+    """revs_config.yaml: the key set of the reference's file (revs_config.yaml:1-39), including the
+    draw_parameters / init_parameters blocks its test-optimizer.py:25 reads."""
+    import os
+    import yaml
+    from conftest import ROOT
+    cfg = yaml.safe_load(open(os.path.join(ROOT, "revs-admm_b200", "revs_config.yaml")))
+    assert set(cfg) == {"run_parameters", "init_parameters"}
+    run = cfg["run_parameters"]
+    assert set(run) == {"input_filepath", "input_parameters", "optimizer_parameters", "draw_parameters"}
+    assert set(run["input_filepath"]) == {"data_path", "out_path", "fig_path", "grb_path", "regionID", "networkID",
+                                          "communityID", "tariffID", "optimizer_mode"}
+    assert set(run["input_parameters"]) == {"adoption", "rating", "seed", "capacity", "initial_soc", "start_time",
+                                            "end_time", "shift_time"}
+    assert set(run["optimizer_parameters"]) == {"v0", "vmin", "vmax", "max_iterations", "kappa"}
+    assert set(run["draw_parameters"]) == {"figwidth", "figheight", "fontsize", "labelsize", "tick_labelsize"}
+    assert set(cfg["init_parameters"]) == {"nodes", "module"}
 
 
 def test_pipeline_cuts_cover_all_zones():
