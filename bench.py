@@ -394,6 +394,7 @@ def run_gpu(args, rank, world, local_rank):
     s1.set_homes(**hm_p)
     s1.set_tariff(cost_p)
     s1.set_option("overlap_home", 0)
+    s1.set_option("graph", 0)          # host-driven loop: CUDA-event spans per kernel family
     s1.solve_admm(**ADMM)
     s1.solve_admm(**ADMM)
     st_iso = s1.stats()
@@ -411,7 +412,7 @@ def run_gpu(args, rank, world, local_rank):
         kernels["dual_update"] = {"bound": "hbm", "ms_per_launch": ms, "achieved": dual_bytes_now / (ms * 1e-3) / 1e9,
                                   "peak": hbm_peak, "unit": "GB/s", "bytes_per_launch": dual_bytes_now,
                                   "ms_span_in_loop": stats_acc["dual_ms"] / iters, "note": iso_note}
-    if st_iso["gemm_full_launches"] > 0:
+    if st_iso["gemm_full_launches"] > 0 and st_iso["gemm_full_ms"] > 0:
         # in-loop voltage check over ALL columns: BF16 screening contraction
         ms = st_iso["gemm_full_ms"] / ADMM["iter_max"]
         sbytes = sum(2.0 * n * n for n in n_p) + Hp * T * (2 + 4)

@@ -171,6 +171,25 @@ cudaError_t launch_utility_qp_fast(const QpParams& P, cudaStream_t stream);
 // mode 1: later rounds (every running column); mode 2: sweep (columns handed over in this round)
 cudaError_t launch_order_columns(const QpParams& P, int mode, int* order, int* order_count, cudaStream_t stream);
 
+// ---- tree_qp.cu: the operator QP on the feeder tree (no sensitivity matrix)
+struct TreeParams {             // static per-zone arrays, pools indexed by FeederDev::off + depth-first position
+    const int* perm;            // depth-first position -> home index within the zone
+    const int* iperm;           // home index -> depth-first position
+    const double* c;            // c[p] = 2 cumr(lca(p, p+1)), p < n - 1
+    const double* d;            // d[p] = R[p][p]
+    const double* e;            // d[p] - max(c[p-1], c[p])
+    const int* nodeA;           // Cartesian-tree nodes sorted by lo: lo | hi << 16   (n - 1 entries)
+    const double* wA;
+    const int* nodeB;           // ... sorted by hi
+    const double* wB;
+    const int* cnt;             // #nodes with lo <= p | (#nodes with hi < p) << 16
+    int* left;                  // out: columns left to the dense kernels
+};
+int tree_qp_group(int n);       // instantiation (NJ = 4, 6, 8, 10) a zone of n residences runs in, -1: too large
+cudaError_t tree_qp_prepare();
+cudaError_t launch_tree_qp(const QpParams& P, const TreeParams& TP, int group, const int* cols, int ncols, int* queue, cudaStream_t stream);
+cudaError_t launch_tree_gate(const int* left, unsigned long long cond_round, cudaStream_t stream);
+
 // ---- contract_f64.cu
 int contract_tile_rows(int T);
 cudaError_t launch_contract(const ContractProblem* d_problems, const ContractTile* d_tiles, int n_tiles,

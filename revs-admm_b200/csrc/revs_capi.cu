@@ -71,6 +71,10 @@ struct Counters {
     int iter;        // ADMM iterations done (device-side loop; selects the ping-pong side of the schedules)
     int pad_;
     unsigned long long rounds_total;   // working-set rounds since revs_admm_begin
+    int tree_left;         // columns the tree kernels left to the dense kernels in the current utility solve ...
+    int tree_queue[4];     // ... and their work-queue heads (reset together)
+    int pad2_[3];
+    unsigned long long tree_left_total;
 };
 
 struct ZoneGroups {  // static: which warp-kernel instantiations the zone sizes of this solver need
@@ -120,7 +124,10 @@ struct revs_solver {
     int warp_m_max = 0, warp_m_max_big = 0;    // warm working sets above this size start in CTA class 1
     bool use_fast = true;                      // one-row register kernel for the small zones
     bool debug = false, debug_host = false;    // REVS_DEBUG / REVS_DEBUG_HOST: per-round / per-solve lines on stderr
+    int trace_iter = -1, trace_round = -1;     // REVS_DEBUG_TRACE="<admm iteration>,<round>": per-column timeline of that round
+    std::string trace_file = "revs_trace.bin"; // ... written here (REVS_DEBUG_TRACE_FILE), [ncols][12] int64
     bool use_graph = true;                     // revs_solve_admm: whole loop from one captured graph, loops decided on the device
+    long long tree_left_total = 0;            // columns the tree kernels left to the dense kernels (host-driven loop, debug)
     double host_sync_ms = 0.0, cat_ms[16] = {0};   // host time waiting in round syncs / span sums per category (debug_host)
     // captured ADMM loop (capture_loop): rebuilt when a parameter baked into it changes
     cudaGraph_t loop_graph = nullptr;
@@ -128,6 +135,13 @@ struct revs_solver {
     double gk_kappa = 0, gk_vset = 0, gk_vhigh = 0, gk_tol = 0;
     int gk_iter_max = 0, gk_flags = -1;
     double* d_respart = nullptr;               // per-CTA partial residual sums of dual_update_kernel
+    // operator QP on the feeder tree (tree_qp.cu): static per-zone arrays, pools of Hp entries
+    bool use_tree = true, tree_on = false;
+    std::vector<char> tree_ok;                 // per feeder: arrays built (revs_set_feeder_tree(s)), not overridden by a dense block
+    int *d_t_perm = nullptr, *d_t_iperm = nullptr, *d_t_nodeA = nullptr, *d_t_nodeB = nullptr, *d_t_cnt = nullptr;
+    double *d_t_c = nullptr, *d_t_d = nullptr, *d_t_e = nullptr, *d_t_wA = nullptr, *d_t_wB = nullptr;
+    int* d_tree_cols[4] = {nullptr, nullptr, nullptr, nullptr};   // columns by instantiation (NJ = 4, 6, 8, 10)
+    int n_tree_cols[4] = {0, 0, 0, 0};
     // all-reduce of the residual sums over the GPUs of the box (revs_comm_*): peer-mapped mailboxes
     PeerSlot* d_mailbox = nullptr;             // [2][kMaxPeers] on this device, exported by IPC handle
     PeerSlot* peer_box[kMaxPeers] = {};        // mailboxes of all ranks as mapped into this process (peer_box[rank] == d_mailbox)
@@ -278,6 +292,139 @@ int check_ready(const revs_solver* s) {
     return REVS_OK;
 }
 
+// Static arrays of the tree kernel for one zone (tree_qp.cu header; numpy restatement: tests/tree_arrays_ref.py).
+// parent / cumr: the zone's nodes in topological order (local indices, -1 = substation), res: node of every home.
+struct ZoneHost {
+    std::vector<int> perm, iperm, nodeA, nodeB, cnt;
+    std::vector<double> c, d, e, wA, wB;
+};
+
+void build_zone_arrays(int n_nodes, const int* parent, const double* cumr, int n, const int* res, ZoneHost& Z) {
+    std::vector<int> depth(n_nodes, 0), first_child(n_nodes, -1), next_sib(n_nodes, -1), last_child(n_nodes, -1), roots;
+    for (int i = 0; i < n_nodes; ++i) {
+        const int p = parent[i];
+        if (p < 0) { roots.push_back(i); continue; }
+        depth[i] = depth[p] + 1;
+        if (first_child[p] < 0) first_child[p] = i; else next_sib[last_child[p]] = i;
+        last_child[p] = i;
+    }
+    std::vector<int> head(n_nodes, -1), nxt(n, -1), tail(n_nodes, -1);       // homes of a node, in home order
+    for (int h = 0; h < n; ++h) {
+        const int x = res[h];
+        if (head[x] < 0) head[x] = h; else nxt[tail[x]] = h;
+        tail[x] = h;
+    }
+    Z.perm.assign(n, 0); Z.iperm.assign(n, 0);
+    std::vector<int> leaf(n, 0), stack;
+    int cntp = 0;
+    for (int ri = (int)roots.size() - 1; ri >= 0; --ri) stack.push_back(roots[ri]);
+    while (!stack.empty()) {                         // depth-first preorder, children in index order
+        const int x = stack.back();
+        stack.pop_back();
+        for (int h = head[x]; h >= 0; h = nxt[h]) { Z.perm[cntp] = h; Z.iperm[h] = cntp; leaf[cntp] = x; ++cntp; }
+        const size_t at = stack.size();
+        for (int ch = first_child[x]; ch >= 0; ch = next_sib[ch]) stack.push_back(ch);
+        std::reverse(stack.begin() + at, stack.end());
+    }
+    const int m = n > 0 ? n - 1 : 0;
+    Z.c.assign(n, 0.0); Z.d.assign(n, 0.0); Z.e.assign(n, 0.0);
+    for (int p = 0; p < n; ++p) Z.d[p] = 2.0 * cumr[leaf[p]];
+    for (int p = 0; p < m; ++p) {
+        int a = leaf[p], b = leaf[p + 1];
+        while (a != b && a >= 0 && b >= 0) {
+            if (depth[a] > depth[b]) a = parent[a];
+            else if (depth[b] > depth[a]) b = parent[b];
+            else { a = parent[a]; b = parent[b]; }
+        }
+        Z.c[p] = (a >= 0 && a == b) ? 2.0 * cumr[a] : 0.0;
+    }
+    // Cartesian tree of c: previous strictly smaller, next smaller-or-equal
+    std::vector<int> prev_s(m, -1), next_se(m, m), st;
+    for (int q = 0; q < m; ++q) {
+        while (!st.empty() && Z.c[st.back()] >= Z.c[q]) { next_se[st.back()] = q; st.pop_back(); }
+        prev_s[q] = st.empty() ? -1 : st.back();
+        st.push_back(q);
+    }
+    std::vector<int> lo(m), hi(m), ord(m);
+    std::vector<double> w(m);
+    for (int q = 0; q < m; ++q) {
+        lo[q] = prev_s[q] + 1;
+        hi[q] = next_se[q] < m ? next_se[q] : n - 1;
+        const double pv = std::max(prev_s[q] >= 0 ? Z.c[prev_s[q]] : 0.0, next_se[q] < m ? Z.c[next_se[q]] : 0.0);
+        w[q] = Z.c[q] - pv;
+        ord[q] = q;
+    }
+    for (int p = 0; p < n; ++p) Z.e[p] = Z.d[p] - std::max(p > 0 ? Z.c[p - 1] : 0.0, p < m ? Z.c[p] : 0.0);
+    Z.nodeA.assign(n, 0); Z.nodeB.assign(n, 0); Z.cnt.assign(n, 0); Z.wA.assign(n, 0.0); Z.wB.assign(n, 0.0);
+    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return lo[a] < lo[b]; });
+    for (int k = 0; k < m; ++k) { Z.nodeA[k] = lo[ord[k]] | (hi[ord[k]] << 16); Z.wA[k] = w[ord[k]]; }
+    std::vector<int> clo(n + 1, 0), chi(n + 1, 0);
+    for (int q = 0; q < m; ++q) { clo[lo[q]]++; chi[hi[q] + 1]++; }      // #nodes with lo == p ; #nodes with hi == p - 1
+    for (int q = 0; q < m; ++q) ord[q] = q;
+    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return hi[a] < hi[b]; });
+    for (int k = 0; k < m; ++k) { Z.nodeB[k] = lo[ord[k]] | (hi[ord[k]] << 16); Z.wB[k] = w[ord[k]]; }
+    int a = 0, b = 0;
+    for (int p = 0; p < n; ++p) {
+        a += clo[p];                                 // nodes with lo <= p
+        b += chi[p];                                 // nodes with hi <  p
+        Z.cnt[p] = a | (b << 16);
+    }
+}
+
+// upload the arrays of feeder f (zone arrays at the feeder's padded offset)
+int upload_zone_arrays(revs_solver* s, int f, const ZoneHost& Z) {
+    const FeederDev& fd = s->feeders[f];
+    if (!s->d_t_perm) {
+        const size_t hp = (size_t)s->Hp;
+        CU(dalloc(&s->d_t_perm, hp)); CU(dalloc(&s->d_t_iperm, hp)); CU(dalloc(&s->d_t_nodeA, hp)); CU(dalloc(&s->d_t_nodeB, hp));
+        CU(dalloc(&s->d_t_cnt, hp)); CU(dalloc(&s->d_t_c, hp)); CU(dalloc(&s->d_t_d, hp)); CU(dalloc(&s->d_t_e, hp));
+        CU(dalloc(&s->d_t_wA, hp)); CU(dalloc(&s->d_t_wB, hp));
+    }
+    const size_t ni = sizeof(int) * fd.n, nd = sizeof(double) * fd.n;
+    if (fd.n == 0) return REVS_OK;
+    CU(cudaMemcpy(s->d_t_perm + fd.off, Z.perm.data(), ni, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s->d_t_iperm + fd.off, Z.iperm.data(), ni, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s->d_t_nodeA + fd.off, Z.nodeA.data(), ni, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s->d_t_nodeB + fd.off, Z.nodeB.data(), ni, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s->d_t_cnt + fd.off, Z.cnt.data(), ni, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s->d_t_c + fd.off, Z.c.data(), nd, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s->d_t_d + fd.off, Z.d.data(), nd, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s->d_t_e + fd.off, Z.e.data(), nd, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s->d_t_wA + fd.off, Z.wA.data(), nd, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s->d_t_wB + fd.off, Z.wB.data(), nd, cudaMemcpyHostToDevice));
+    return REVS_OK;
+}
+
+// column lists of the tree kernels: every (zone, hour) of the zones that have tree arrays, by instantiation
+int rebuild_tree_lists(revs_solver* s) {
+    std::vector<int> cols[4];
+    for (int f = 0; f < s->nf; ++f) {
+        if (!s->tree_ok[f] || s->feeders[f].n == 0) continue;
+        const int g = tree_qp_group(s->feeders[f].n);
+        if (g < 0) continue;
+        for (int t = 0; t < s->T; ++t) cols[g].push_back(f * s->T + t);
+    }
+    s->tree_on = false;
+    for (int g = 0; g < 4; ++g) {
+        if (s->d_tree_cols[g]) { cudaFree(s->d_tree_cols[g]); s->d_tree_cols[g] = nullptr; }
+        s->n_tree_cols[g] = (int)cols[g].size();
+        if (cols[g].empty()) continue;
+        CU(dalloc(&s->d_tree_cols[g], cols[g].size()));
+        CU(cudaMemcpy(s->d_tree_cols[g], cols[g].data(), sizeof(int) * cols[g].size(), cudaMemcpyHostToDevice));
+        s->tree_on = true;
+    }
+    if (s->loop_exec) { cudaGraphExecDestroy(s->loop_exec); s->loop_exec = nullptr; }     // the captured loop bakes the lists in
+    return REVS_OK;
+}
+
+TreeParams tree_params(revs_solver* s) {
+    TreeParams TP{};
+    TP.perm = s->d_t_perm; TP.iperm = s->d_t_iperm; TP.c = s->d_t_c; TP.d = s->d_t_d; TP.e = s->d_t_e;
+    TP.nodeA = s->d_t_nodeA; TP.wA = s->d_t_wA; TP.nodeB = s->d_t_nodeB; TP.wB = s->d_t_wB; TP.cnt = s->d_t_cnt;
+    TP.left = &s->d_cnt->tree_left;
+    return TP;
+}
+
 QpParams qp_params(revs_solver* s) {
     QpParams Q{};
     Q.feeders = s->d_feeders;
@@ -344,6 +491,24 @@ int launch_init(revs_solver* s, QpParams Q, bool in_loop, bool timed) {
     Q.order = nullptr;
     TimedSpan* sp = timed ? span_begin(s, 6, s->sU) : nullptr;
     CU(launch_qp_init(Q, s->use_warp_kernel ? qp_warp_max_n() : 0, s->sU));
+    if (sp) span_end(sp, s->sU);
+    return REVS_OK;
+}
+
+// The tree kernels: every column of a zone that was given as a tree is solved here, from z alone; what they
+// cannot finish (more than 16 binding rows, a failed safeguard) stays for the working-set rounds of the dense kernels.
+bool tree_active(const revs_solver* s) { return s->use_tree && s->tree_on; }
+
+int launch_tree_stage(revs_solver* s, const QpParams& Q, bool timed) {
+    if (!tree_active(s)) return REVS_OK;
+    CU(cudaMemsetAsync(&s->d_cnt->tree_left, 0, 5 * sizeof(int), s->sU));
+    TreeParams TP = tree_params(s);
+    TimedSpan* sp = timed ? span_begin(s, 8, s->sU) : nullptr;
+    for (int g = 3; g >= 0; --g) {
+        if (s->n_tree_cols[g] == 0) continue;
+        CU(launch_tree_qp(Q, TP, g, s->d_tree_cols[g], s->n_tree_cols[g], &s->d_cnt->tree_queue[g], s->sU));
+        s->stats.kernel_launches++;
+    }
     if (sp) span_end(sp, s->sU);
     return REVS_OK;
 }
@@ -493,6 +658,19 @@ int utility_solve(revs_solver* s, bool in_loop = false) {
     QpParams Q = qp_params(s);
     if ((rc = launch_init(s, Q, in_loop, true))) return rc;
     s->stats.kernel_launches++;
+    if (tree_active(s)) {
+        if ((rc = launch_tree_stage(s, Q, true))) return rc;
+        CU(cudaMemcpyAsync(s->h_cnt, s->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, s->sU));
+        const double t0 = now_ms();
+        CU(cudaStreamSynchronize(s->sU));
+        s->host_sync_ms += now_ms() - t0;
+        if ((rc = check_device_flags(s))) return rc;
+        s->ws_bound = std::max(s->ws_bound, s->h_cnt->max_ws);
+        s->tree_left_total += s->h_cnt->tree_left;
+        if (s->debug)
+            fprintf(stderr, "[revs] admm %d tree stage: %d columns left to the dense kernels, max_ws %d\n", s->k, s->h_cnt->tree_left, s->h_cnt->max_ws);
+        if (s->h_cnt->tree_left == 0) return REVS_OK;
+    }
     bool use[kQpClasses];
     // first round: qp_init_kernel assigns classes on the device by the size of the stored working
     // sets; the largest working set any column has had in this solve (read back at every round
@@ -505,7 +683,24 @@ int utility_solve(revs_solver* s, bool in_loop = false) {
         if (round >= kQpRoundMax)
             return fail(REVS_ERR_NOCONV, "utility QP: %d columns still running after %d working-set rounds",
                         s->h_cnt->n_running, round);
+        long long* d_trace = nullptr;
+        if (in_loop && s->k == s->trace_iter && round == s->trace_round) {
+            CU(cudaMalloc(&d_trace, sizeof(long long) * 12 * s->ncols));
+            CU(cudaMemsetAsync(d_trace, 0, sizeof(long long) * 12 * s->ncols, s->sU));
+            Q.trace = d_trace;
+        }
         if ((rc = enqueue_round(s, Q, round == 0 ? 0 : 1, use, grid, true))) return rc;
+        if (d_trace) {
+            std::vector<long long> hb((size_t)12 * s->ncols);
+            CU(cudaStreamSynchronize(s->sU));
+            CU(cudaMemcpy(hb.data(), d_trace, hb.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+            if (FILE* fp = fopen(s->trace_file.c_str(), "wb")) {
+                fwrite(hb.data(), sizeof(long long), hb.size(), fp);
+                fclose(fp);
+            }
+            cudaFree(d_trace);
+            Q.trace = nullptr;
+        }
         CU(cudaMemcpyAsync(s->h_cnt, s->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, s->sU));
         {
             const double t0 = now_ms();
@@ -569,7 +764,9 @@ void free_all(revs_solver* s) {
                     s->d_pev, s->d_soc, s->d_has_ev, s->d_rating, s->d_capacity, s->d_initial, s->d_indconst,
                     s->d_start, s->d_end, s->d_nmin, s->d_nmax, s->d_zero_i, s->d_cost, s->d_zt, s->d_lamt,
                     s->d_gt, s->d_vt, s->d_wcount, s->d_widx, s->d_status, s->d_innerok, s->d_cls, s->d_order, s->d_order4, s->d_order_count, s->d_cnt, s->d_diff,
-                    s->d_cprob, s->d_ctiles, s->d_respart};
+                    s->d_cprob, s->d_ctiles, s->d_respart, s->d_t_perm, s->d_t_iperm, s->d_t_nodeA, s->d_t_nodeB, s->d_t_cnt,
+                    s->d_t_c, s->d_t_d, s->d_t_e, s->d_t_wA, s->d_t_wB, s->d_tree_cols[0], s->d_tree_cols[1], s->d_tree_cols[2],
+                    s->d_tree_cols[3]};
     for (int r = 0; r < kMaxPeers; ++r)
         if (s->peer_box[r] && s->peer_box[r] != s->d_mailbox) cudaIpcCloseMemHandle(s->peer_box[r]);
     if (s->d_mailbox) cudaFree(s->d_mailbox);
@@ -635,6 +832,7 @@ int revs_create(revs_solver** out, int device, int n_feeders, const int64_t* fee
     s->H = feeder_off[n_feeders];
     s->feeders.resize(n_feeders);
     s->sens_set.assign(n_feeders, 0);
+    s->tree_ok.assign(n_feeders, 0);
     s->trees.resize(n_feeders);
     int64_t hp = 0, rp = 0;
     for (int f = 0; f < n_feeders; ++f) {
@@ -739,6 +937,9 @@ int revs_create(revs_solver** out, int device, int n_feeders, const int64_t* fee
         s->debug = getenv("REVS_DEBUG") != nullptr;
         s->debug_host = getenv("REVS_DEBUG_HOST") != nullptr;
         if ((e = getenv("REVS_NO_GRAPH")) && atoi(e)) s->use_graph = false;
+        if ((e = getenv("REVS_NO_TREE")) && atoi(e)) s->use_tree = false;
+        if ((e = getenv("REVS_DEBUG_TRACE")) && sscanf(e, "%d,%d", &s->trace_iter, &s->trace_round) == 2) s->use_graph = false;
+        if ((e = getenv("REVS_DEBUG_TRACE_FILE"))) s->trace_file = e;
         if (s->debug) s->use_graph = false;      // the per-round lines need the host-driven loop
     }
     for (int f = 0; f < n_feeders; ++f) {
@@ -832,6 +1033,11 @@ int revs_set_sensitivity(revs_solver* s, int feeder, const double* R_res) {
                         (size_t)fd.n * sizeof(double), fd.n, cudaMemcpyHostToDevice));
     s->sens_set[feeder] = 1;
     s->rn2_valid = false;
+    if (s->tree_ok[feeder]) {            // a dense block replaces the tree: this zone runs in the dense kernels
+        s->tree_ok[feeder] = 0;
+        int rc = rebuild_tree_lists(s);
+        if (rc) return rc;
+    }
     return REVS_OK;
 }
 
@@ -863,7 +1069,16 @@ int revs_set_feeder_tree(revs_solver* s, int feeder, int n_nodes, const int32_t*
     CU(cudaStreamSynchronize(s->sU));
     s->sens_set[feeder] = 1;
     s->rn2_valid = false;
-    return REVS_OK;
+    if (tree_qp_group(fd.n) >= 0) {
+        ZoneHost Z;
+        build_zone_arrays(n_nodes, parent, cumr.data(), fd.n, res_node, Z);
+        int rc = upload_zone_arrays(s, feeder, Z);
+        if (rc) return rc;
+        s->tree_ok[feeder] = 1;
+    } else {
+        s->tree_ok[feeder] = 0;
+    }
+    return rebuild_tree_lists(s);
 }
 
 int revs_set_feeder_trees(revs_solver* s, const int64_t* node_off, const int32_t* parent, const double* r,
@@ -914,10 +1129,50 @@ int revs_set_feeder_trees(revs_solver* s, const int64_t* node_off, const int32_t
     }
     CU(launch_sens_voltage_batched(s->d_feeders, s->nf, max_n, s->d_pool_off, s->d_pool_parent, s->d_pool_cumr,
                                    s->d_pool_res, s->d_Rpool, s->sU));
-    CU(cudaStreamSynchronize(s->sU));     // the host staging vectors die here
+    // static arrays of the tree kernels, all zones into page-able host pools, one upload per array
+    {
+        const size_t hp = (size_t)s->Hp;
+        std::vector<int> perm(hp, 0), iperm(hp, 0), nodeA(hp, 0), nodeB(hp, 0), cnt(hp, 0);
+        std::vector<double> c(hp, 0.0), d(hp, 0.0), e(hp, 0.0), wA(hp, 0.0), wB(hp, 0.0);
+        ZoneHost Z;
+        for (int f = 0; f < s->nf; ++f) {
+            const FeederDev& fd = s->feeders[f];
+            s->tree_ok[f] = 0;
+            if (fd.n == 0 || tree_qp_group(fd.n) < 0) continue;
+            const int64_t o = node_off[f];
+            build_zone_arrays((int)(node_off[f + 1] - o), parent + o, cumr.data() + o, fd.n, res_node + s->off[f], Z);
+            std::copy(Z.perm.begin(), Z.perm.end(), perm.begin() + fd.off);
+            std::copy(Z.iperm.begin(), Z.iperm.end(), iperm.begin() + fd.off);
+            std::copy(Z.nodeA.begin(), Z.nodeA.end(), nodeA.begin() + fd.off);
+            std::copy(Z.nodeB.begin(), Z.nodeB.end(), nodeB.begin() + fd.off);
+            std::copy(Z.cnt.begin(), Z.cnt.end(), cnt.begin() + fd.off);
+            std::copy(Z.c.begin(), Z.c.end(), c.begin() + fd.off);
+            std::copy(Z.d.begin(), Z.d.end(), d.begin() + fd.off);
+            std::copy(Z.e.begin(), Z.e.end(), e.begin() + fd.off);
+            std::copy(Z.wA.begin(), Z.wA.end(), wA.begin() + fd.off);
+            std::copy(Z.wB.begin(), Z.wB.end(), wB.begin() + fd.off);
+            s->tree_ok[f] = 1;
+        }
+        if (!s->d_t_perm) {
+            CU(dalloc(&s->d_t_perm, hp)); CU(dalloc(&s->d_t_iperm, hp)); CU(dalloc(&s->d_t_nodeA, hp)); CU(dalloc(&s->d_t_nodeB, hp));
+            CU(dalloc(&s->d_t_cnt, hp)); CU(dalloc(&s->d_t_c, hp)); CU(dalloc(&s->d_t_d, hp)); CU(dalloc(&s->d_t_e, hp));
+            CU(dalloc(&s->d_t_wA, hp)); CU(dalloc(&s->d_t_wB, hp));
+        }
+        CU(cudaMemcpyAsync(s->d_t_perm, perm.data(), sizeof(int) * hp, cudaMemcpyHostToDevice, s->sU));
+        CU(cudaMemcpyAsync(s->d_t_iperm, iperm.data(), sizeof(int) * hp, cudaMemcpyHostToDevice, s->sU));
+        CU(cudaMemcpyAsync(s->d_t_nodeA, nodeA.data(), sizeof(int) * hp, cudaMemcpyHostToDevice, s->sU));
+        CU(cudaMemcpyAsync(s->d_t_nodeB, nodeB.data(), sizeof(int) * hp, cudaMemcpyHostToDevice, s->sU));
+        CU(cudaMemcpyAsync(s->d_t_cnt, cnt.data(), sizeof(int) * hp, cudaMemcpyHostToDevice, s->sU));
+        CU(cudaMemcpyAsync(s->d_t_c, c.data(), sizeof(double) * hp, cudaMemcpyHostToDevice, s->sU));
+        CU(cudaMemcpyAsync(s->d_t_d, d.data(), sizeof(double) * hp, cudaMemcpyHostToDevice, s->sU));
+        CU(cudaMemcpyAsync(s->d_t_e, e.data(), sizeof(double) * hp, cudaMemcpyHostToDevice, s->sU));
+        CU(cudaMemcpyAsync(s->d_t_wA, wA.data(), sizeof(double) * hp, cudaMemcpyHostToDevice, s->sU));
+        CU(cudaMemcpyAsync(s->d_t_wB, wB.data(), sizeof(double) * hp, cudaMemcpyHostToDevice, s->sU));
+        CU(cudaStreamSynchronize(s->sU));     // the host staging vectors die here
+    }
     s->stats.kernel_launches++;
     s->rn2_valid = false;
-    return REVS_OK;
+    return rebuild_tree_lists(s);
 }
 
 int revs_set_homes(revs_solver* s, const double* load, const uint8_t* has_ev, const double* rating,
@@ -1128,7 +1383,7 @@ int admm_step_impl(revs_solver* s, double sums[3], bool sync_now) {
 // round number) from device counters, so the bodies are captured once.  Nothing returns to the host until the
 // schedule is finished: no round trip per working-set round, no launch latency per kernel.
 int capture_loop(revs_solver* s) {
-    const int flags = (s->screen ? 1 : 0) | (s->screen_impl << 1) | (s->overlap_home ? 4 : 0) | (s->use_warp_kernel ? 8 : 0) | (s->use_fast ? 16 : 0) | (s->comm_world << 8) | (s->comm_rank << 16);
+    const int flags = (s->screen ? 1 : 0) | (s->screen_impl << 1) | (s->overlap_home ? 4 : 0) | (s->use_warp_kernel ? 8 : 0) | (s->use_fast ? 16 : 0) | (s->comm_world << 8) | (s->comm_rank << 16) | (tree_active(s) ? 32 : 0);
     if (s->loop_exec && s->gk_kappa == s->kappa && s->gk_vset == s->vset && s->gk_vhigh == s->vhigh && s->gk_tol == s->tol &&
         s->gk_iter_max == s->iter_max && s->gk_flags == flags)
         return REVS_OK;
@@ -1137,6 +1392,7 @@ int capture_loop(revs_solver* s) {
     // function attributes are set outside the capture
     for (int cl = 1; cl < kQpClasses; ++cl) CU(launch_utility_qp(QpParams{}, 0, cl, s->sU));
     CU(qp_warp_prepare());
+    CU(tree_qp_prepare());
     CU(screen_prepare());
     CU(screen_tc5_prepare());
     CU(cudaGraphCreate(&s->loop_graph, 0));
@@ -1175,6 +1431,13 @@ int capture_loop(revs_solver* s) {
         Q.use_cond = 1;
         int r = launch_init(s, Q, true, false);
         if (r) return r;
+        if (tree_active(s)) {
+            const revs_stats keep = s->stats;
+            r = launch_tree_stage(s, Q, false);
+            s->stats = keep;
+            if (r) return r;
+            CU(launch_tree_gate(&s->d_cnt->tree_left, (unsigned long long)h_round, s->sU));
+        }
         // the working-set while node goes into the graph being captured, after what the stream has enqueued so far
         cudaStreamCaptureStatus st;
         cudaGraph_t g_cap = nullptr;
@@ -1272,7 +1535,11 @@ int revs_solve_admm(revs_solver* s, double kappa, int iter_max, double vset, dou
         s->stats.gemm_launches = (int64_t)s->h_cnt->rounds_total;
         s->stats.gemm_full_launches = s->k;
         s->stats.qp_warp_rounds = (s->use_warp_kernel && s->zg.warp_n > 0) ? (int64_t)s->h_cnt->rounds_total : 0;
-        s->stats.kernel_launches += (int64_t)s->k * 3 + (int64_t)s->h_cnt->rounds_total * round_launches(s);
+        int tree_launches = 0;
+        if (tree_active(s))
+            for (int g = 0; g < 4; ++g) tree_launches += s->n_tree_cols[g] > 0;
+        if (tree_launches) ++tree_launches;            // + the gate of the working-set loop
+        s->stats.kernel_launches += (int64_t)s->k * (3 + tree_launches) + (int64_t)s->h_cnt->rounds_total * round_launches(s);
         if (rc) return rc;
     } else {
         for (int k = 0; k < iter_max; ++k) {
@@ -1623,6 +1890,26 @@ int revs_screen_contract(int device, int M, int K, int T, const double* A, const
     return REVS_OK;
 }
 
+int revs_zone_arrays(int n_nodes, const int32_t* parent, const double* r, int n_res, const int32_t* res_node, int32_t* perm,
+                     double* c, double* d, double* e, int32_t* node_lo, double* w_lo, int32_t* node_hi, double* w_hi, int32_t* cnt) {
+    if (n_nodes <= 0 || n_res <= 0 || !parent || !r || !res_node || !perm || !c || !d || !e || !node_lo || !w_lo || !node_hi || !w_hi || !cnt)
+        return fail(REVS_ERR_ARG, "bad arguments");
+    std::vector<double> cumr(n_nodes);
+    for (int i = 0; i < n_nodes; ++i) {
+        if (parent[i] >= i || parent[i] < -1) return fail(REVS_ERR_ARG, "nodes must be topologically ordered (parent[i] < i)");
+        cumr[i] = (parent[i] < 0 ? 0.0 : cumr[parent[i]]) + r[i];
+    }
+    for (int j = 0; j < n_res; ++j)
+        if (res_node[j] < 0 || res_node[j] >= n_nodes) return fail(REVS_ERR_ARG, "res_node[%d] out of range", j);
+    ZoneHost Z;
+    build_zone_arrays(n_nodes, parent, cumr.data(), n_res, res_node, Z);
+    for (int p = 0; p < n_res; ++p) {
+        perm[p] = Z.perm[p]; c[p] = Z.c[p]; d[p] = Z.d[p]; e[p] = Z.e[p];
+        node_lo[p] = Z.nodeA[p]; w_lo[p] = Z.wA[p]; node_hi[p] = Z.nodeB[p]; w_hi[p] = Z.wB[p]; cnt[p] = Z.cnt[p];
+    }
+    return REVS_OK;
+}
+
 int revs_comm_export(revs_solver* s, void* handle64) {
     if (!s || !handle64) return fail(REVS_ERR_ARG, "bad arguments");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -1682,6 +1969,11 @@ int revs_set_option(revs_solver* s, const char* name, double value) {
         if (value != 0.0 && s->zg.max_n > 16384) return fail(REVS_ERR_ARG, "screening is limited to zones of at most 16384 residences");
         if (mid_run) return fail(REVS_ERR_ARG, "'screen' cannot change between revs_admm_step calls of one run");
         s->screen = value != 0.0;
+        return REVS_OK;
+    }
+    if (!strcmp(name, "tree")) {        // 0: dense kernels only (BF16 screening + working rows of R), also for zones given as trees
+        if (mid_run) return fail(REVS_ERR_ARG, "'tree' cannot change between revs_admm_step calls of one run");
+        s->use_tree = value != 0.0;
         return REVS_OK;
     }
     if (!strcmp(name, "graph")) { s->use_graph = value != 0.0; return REVS_OK; }   // 0: host-driven loop with per-kernel event spans (profiling)

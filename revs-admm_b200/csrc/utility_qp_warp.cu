@@ -65,7 +65,16 @@ struct WarpSmemT {
 };
 // zones of up to 256 residences: 1024 doubles of cached working rows per warp (4 CTAs per SM);
 // 257..320 residences (NJ = 10, 3 CTAs per SM): 1536, i.e. at least four full rows
-template <int NJ> struct WarpCfg { static constexpr int kCache = NJ <= 8 ? kCacheDoubles : 1536; static constexpr int kCtas = NJ <= 8 ? kCtasPerSm : 3; };
+#ifndef REVS_WARP_CTAS_SMALL      // build-time experiment knobs (profiles/build_variants.sh); the defaults are the measured best
+#define REVS_WARP_CTAS_SMALL kCtasPerSm
+#endif
+#ifndef REVS_WARP_CTAS_BIG
+#define REVS_WARP_CTAS_BIG 3
+#endif
+template <int NJ> struct WarpCfg {
+    static constexpr int kCache = NJ <= 8 ? kCacheDoubles : 1536;
+    static constexpr int kCtas = NJ <= 8 ? (NJ <= 4 ? kCtasPerSm : REVS_WARP_CTAS_SMALL) : REVS_WARP_CTAS_BIG;
+};
 
 struct WarpStats {
     unsigned long long its = 0;
@@ -1018,7 +1027,9 @@ static cudaError_t prepare_warp_nj(int* n_sm_out) {
         int n = 0;
         e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(utility_qp_warp_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+#ifndef REVS_WARP_NO_CARVEOUT
         if (e == cudaSuccess) e = cudaFuncSetAttribute(utility_qp_warp_kernel<NJ>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+#endif
         if (e != cudaSuccess) return e;
         n_sm[dev] = n;
     }

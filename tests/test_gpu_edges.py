@@ -235,7 +235,11 @@ def test_captured_loop_equals_host_driven_loop(gpu_lib, sizes, T, vhigh):
     device, CTA classes behind IF nodes) against the host-driven loop (one host sync per round):
     bit-identical results, same number of working-set rounds -- including zones that need several rounds
     (> 512 residences: re-screening) and columns handed from class to class."""
-    trees, hm, cost = _problem(sizes, T, seed=5 + sum(sizes), r_secondary=2e-3 if T == 12 else 1e-3)
+    trees, hm, cost = _problem(sizes, T, seed=5 + sum(sizes), r_secondary=2e-3 if T == 12 else 1e-3,
+                               **(dict(adoption=1.0) if T == 12 else {}))
+    if T == 12:                                      # every charger may run in any step: working sets beyond the warp kernel
+        hm["start"][:] = 0
+        hm["end"][:] = T
     kw = dict(kappa=5.0, iter_max=6, vset=1.0, vlow=0.95, vhigh=vhigh)
     outs, rounds = [], []
     for graph in (1, 0):
@@ -357,3 +361,37 @@ def test_compact_schedule_download_equals_full_results(gpu_lib):
         out = ps.schedule(trees, hm, cost, compact=True, **kw)
     assert np.array_equal(out["P_sch"], full["P_sch"]) and np.array_equal(out["mask"], comp["mask"])
     assert np.array_equal(out["diff"][:done], full["diff"])
+
+
+@pytest.mark.parametrize("sizes,T,vhigh", [([140, 60, 33], 48, 1.015), ([297, 157, 257, 320, 129], 24, 1.02), ([120, 96], 12, 1.02), ([1, 2, 31, 33], 24, 1.01)])
+def test_tree_kernel_equals_dense_kernels(gpu_lib, sizes, T, vhigh):
+    """The tree-structured operator kernel (no sensitivity matrix: rows and products from the feeder tree) against
+    the dense kernels (BF16 screening + FP64 rows of R) and the oracle: identical charging hours, estimates within
+    1e-7 kW of each other, the tree path never launching a screening contraction unless it leaves columns behind."""
+    trees, hm, cost = _problem(sizes, T, seed=13 + sum(sizes), r_secondary=2e-3 if T == 12 else 1e-3,
+                               **(dict(adoption=1.0) if T == 12 else {}))
+    if T == 12:
+        hm["start"][:] = 0
+        hm["end"][:] = T
+    kw = dict(kappa=5.0, iter_max=6, vset=1.0, vlow=0.95, vhigh=vhigh)
+    outs = []
+    for tree in (1, 0):
+        with gpu_lib.Solver(sizes, T) as s:
+            s.set_option("tree", tree)
+            s.set_feeder_trees(trees)
+            s.set_homes(**hm)
+            s.set_tariff(cost)
+            done = s.solve_admm(**kw)
+            out = s.results(done)
+            out["P_est"], out["Gamma"] = s.estimate()
+            out["stats"] = s.stats()
+            outs.append(out)
+    ref = _oracle(trees, hm, cost, kw)
+    for out in outs:
+        assert np.array_equal(out["P_ev"], ref["P_ev"])
+        assert np.abs(out["P_est"] - ref["P_est"]).max() <= 1e-6
+        assert np.abs(out["diff"] - ref["diff"]).max() <= 1e-7
+    assert np.abs(outs[0]["P_est"] - outs[1]["P_est"]).max() <= 1e-7
+    assert outs[0]["stats"]["max_working_set"] >= 2
+    if T != 12:                                      # (T = 12: working sets beyond 16 rows go on to the dense kernels)
+        assert outs[0]["stats"]["gemm_launches"] == 0 < outs[1]["stats"]["gemm_launches"]
