@@ -190,8 +190,9 @@ int revs_comm_export(revs_solver* s, void* handle64);
 int revs_comm_attach(revs_solver* s, int world, int rank, const void* handles);
 int revs_comm_detach(revs_solver* s);
 
-/* Options: "tree" (default 1) = zones given as trees (revs_set_feeder_tree(s), up to 320 residences) are solved by the
- * tree-structured kernel, which needs no sensitivity matrix; 0 = dense kernels for every zone.  "graph" (default 1) = revs_solve_admm runs the whole loop from one captured CUDA graph whose loops
+/* Options: "tree" (default 0; set it BEFORE revs_set_feeder_tree(s)) = zones given as trees (up to 320 residences) are
+ * solved by the tree-structured kernel, which needs no sensitivity matrix (rows and products of R from O(n) static
+ * arrays); 0 = dense kernels (BF16 tensor-core screening + FP64 rows of R), the faster of the two on B200.  "graph" (default 1) = revs_solve_admm runs the whole loop from one captured CUDA graph whose loops
  * (ADMM iterations, working-set rounds) are decided on the device; 0 = host-driven loop with CUDA-event spans per
  * kernel family in revs_stats (profiling).  "screen" (default 1) = BF16 tensor-core screening of the voltage rows with exact
  * FP64 recheck of the candidates inside the loop; 0 = FP64 DMMA contraction of every row.

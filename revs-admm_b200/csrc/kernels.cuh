@@ -172,22 +172,23 @@ cudaError_t launch_utility_qp_fast(const QpParams& P, cudaStream_t stream);
 cudaError_t launch_order_columns(const QpParams& P, int mode, int* order, int* order_count, cudaStream_t stream);
 
 // ---- tree_qp.cu: the operator QP on the feeder tree (no sensitivity matrix)
-struct TreeParams {             // static per-zone arrays, pools indexed by FeederDev::off + depth-first position
-    const int* perm;            // depth-first position -> home index within the zone
-    const int* iperm;           // home index -> depth-first position
-    const double* c;            // c[p] = 2 cumr(lca(p, p+1)), p < n - 1
-    const double* d;            // d[p] = R[p][p]
-    const double* e;            // d[p] - max(c[p-1], c[p])
-    const int* nodeA;           // Cartesian-tree nodes sorted by lo: lo | hi << 16   (n - 1 entries)
+struct TreeParams {             // static per-zone arrays (layout: tree_qp.cu:ZonePtr)
+    const int64_t* zoff;        // [n_feeders] offset of the zone in the strided pools (32 NJ entries per zone)
+    const int* perm;            // strided: home index of every depth-first position
+    const int* iperm;           // [Hp] at FeederDev::off + home: depth-first position
+    const double* c;            // strided: c[p] = 2 cumr(lca(p, p+1))
+    const double* d;            // strided: R[p][p]
+    const double* e;            // strided: d[p] - max(c[p-1], c[p])
+    const int* nodeA;           // strided: Cartesian-tree nodes in lo-order, shared-memory slots of G[hi] | G[lo-1] << 16
     const double* wA;
-    const int* nodeB;           // ... sorted by hi
-    const double* wB;
-    const int* cnt;             // #nodes with lo <= p | (#nodes with hi < p) << 16
+    const int* permB;           // strided: nodes in hi-order -> slot in lo-order
+    const int* cnt;             // strided: slots of S1[#lo <= p] | S2[#hi < p] << 16
     int* left;                  // out: columns left to the dense kernels
 };
 int tree_qp_group(int n);       // instantiation (NJ = 4, 6, 8, 10) a zone of n residences runs in, -1: too large
 cudaError_t tree_qp_prepare();
-cudaError_t launch_tree_qp(const QpParams& P, const TreeParams& TP, int group, const int* cols, int ncols, int* queue, cudaStream_t stream);
+int tree_qp_chunk();            // columns per work chunk (all of one zone)
+cudaError_t launch_tree_qp(const QpParams& P, const TreeParams& TP, int group, const int2* chunks, int nchunks, int* queue, cudaStream_t stream);
 cudaError_t launch_tree_gate(const int* left, unsigned long long cond_round, cudaStream_t stream);
 
 // ---- contract_f64.cu

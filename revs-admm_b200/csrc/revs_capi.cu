@@ -136,11 +136,15 @@ struct revs_solver {
     int gk_iter_max = 0, gk_flags = -1;
     double* d_respart = nullptr;               // per-CTA partial residual sums of dual_update_kernel
     // operator QP on the feeder tree (tree_qp.cu): static per-zone arrays, pools of Hp entries
-    bool use_tree = true, tree_on = false;
+    bool use_tree = false, tree_on = false;    // opt-in (option "tree" / REVS_TREE=1, before the trees are set): see tree_qp.cu
     std::vector<char> tree_ok;                 // per feeder: arrays built (revs_set_feeder_tree(s)), not overridden by a dense block
     int *d_t_perm = nullptr, *d_t_iperm = nullptr, *d_t_nodeA = nullptr, *d_t_nodeB = nullptr, *d_t_cnt = nullptr;
     double *d_t_c = nullptr, *d_t_d = nullptr, *d_t_e = nullptr, *d_t_wA = nullptr, *d_t_wB = nullptr;
-    int* d_tree_cols[4] = {nullptr, nullptr, nullptr, nullptr};   // columns by instantiation (NJ = 4, 6, 8, 10)
+    int64_t* d_t_zoff = nullptr;               // offset of every zone in the strided pools (32 NJ entries per zone)
+    std::vector<int64_t> tree_zoff;
+    size_t tree_pool_n = 0;
+    int n_dense_cols = 0;                      // columns of zones without tree arrays: the dense kernels always run for them
+    int2* d_tree_cols[4] = {nullptr, nullptr, nullptr, nullptr};  // chunks of columns by instantiation (NJ = 4, 6, 8, 10)
     int n_tree_cols[4] = {0, 0, 0, 0};
     // all-reduce of the residual sums over the GPUs of the box (revs_comm_*): peer-mapped mailboxes
     PeerSlot* d_mailbox = nullptr;             // [2][kMaxPeers] on this device, exported by IPC handle
@@ -295,7 +299,7 @@ int check_ready(const revs_solver* s) {
 // Static arrays of the tree kernel for one zone (tree_qp.cu header; numpy restatement: tests/tree_arrays_ref.py).
 // parent / cumr: the zone's nodes in topological order (local indices, -1 = substation), res: node of every home.
 struct ZoneHost {
-    std::vector<int> perm, iperm, nodeA, nodeB, cnt;
+    std::vector<int> perm, iperm, nodeA, nodeB, cnt, ordB_in_A;   // ordB_in_A[k]: rank in lo-order of the k-th node in hi-order
     std::vector<double> c, d, e, wA, wB;
 };
 
@@ -357,12 +361,14 @@ void build_zone_arrays(int n_nodes, const int* parent, const double* cumr, int n
     for (int p = 0; p < n; ++p) Z.e[p] = Z.d[p] - std::max(p > 0 ? Z.c[p - 1] : 0.0, p < m ? Z.c[p] : 0.0);
     Z.nodeA.assign(n, 0); Z.nodeB.assign(n, 0); Z.cnt.assign(n, 0); Z.wA.assign(n, 0.0); Z.wB.assign(n, 0.0);
     std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return lo[a] < lo[b]; });
-    for (int k = 0; k < m; ++k) { Z.nodeA[k] = lo[ord[k]] | (hi[ord[k]] << 16); Z.wA[k] = w[ord[k]]; }
+    std::vector<int> rank_lo(m, 0);
+    for (int k = 0; k < m; ++k) { Z.nodeA[k] = lo[ord[k]] | (hi[ord[k]] << 16); Z.wA[k] = w[ord[k]]; rank_lo[ord[k]] = k; }
     std::vector<int> clo(n + 1, 0), chi(n + 1, 0);
     for (int q = 0; q < m; ++q) { clo[lo[q]]++; chi[hi[q] + 1]++; }      // #nodes with lo == p ; #nodes with hi == p - 1
     for (int q = 0; q < m; ++q) ord[q] = q;
     std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return hi[a] < hi[b]; });
-    for (int k = 0; k < m; ++k) { Z.nodeB[k] = lo[ord[k]] | (hi[ord[k]] << 16); Z.wB[k] = w[ord[k]]; }
+    Z.ordB_in_A.assign(m, 0);
+    for (int k = 0; k < m; ++k) { Z.nodeB[k] = lo[ord[k]] | (hi[ord[k]] << 16); Z.wB[k] = w[ord[k]]; Z.ordB_in_A[k] = rank_lo[ord[k]]; }
     int a = 0, b = 0;
     for (int p = 0; p < n; ++p) {
         a += clo[p];                                 // nodes with lo <= p
@@ -371,38 +377,89 @@ void build_zone_arrays(int n_nodes, const int* parent, const double* cumr, int n
     }
 }
 
-// upload the arrays of feeder f (zone arrays at the feeder's padded offset)
+// The kernel's layout of one zone (tree_qp.cu:ZonePtr): 32 NJ entries per array, position p at slot(p), nodes and
+// counts as shared-memory slots.
+struct ZonePacked {
+    std::vector<int> perm, nodeA, permB, cnt;
+    std::vector<double> c, d, e, wA;
+};
+
+void pack_zone(const ZoneHost& Z, int n, int nj, ZonePacked& K) {
+    const int S = 32 * nj, zero = S;
+    auto slot = [&](int p) { return (p % nj) * 32 + p / nj; };
+    K.perm.assign(S, -1); K.nodeA.assign(S, zero | (zero << 16)); K.permB.assign(S, 0); K.cnt.assign(S, zero | (zero << 16));
+    K.c.assign(S, 0.0); K.d.assign(S, 0.0); K.e.assign(S, 0.0); K.wA.assign(S, 0.0);
+    for (int p = 0; p < S; ++p) K.permB[slot(p)] = slot(p);            // padded nodes: weight 0, map to themselves
+    const int m = n > 0 ? n - 1 : 0;
+    for (int p = 0; p < n; ++p) {
+        const int sp = slot(p);
+        K.perm[sp] = Z.perm[p];
+        K.c[sp] = p < m ? Z.c[p] : 0.0;
+        K.d[sp] = Z.d[p];
+        K.e[sp] = Z.e[p];
+        const int a = Z.cnt[p] & 0xffff, b = Z.cnt[p] >> 16;            // S1[a], S2[b]: sums of the first a / b node terms
+        K.cnt[sp] = (a ? slot(a - 1) : zero) | ((b ? slot(b - 1) : zero) << 16);
+    }
+    for (int k = 0; k < m; ++k) {
+        const int lo = Z.nodeA[k] & 0xffff, hi = Z.nodeA[k] >> 16;
+        K.nodeA[slot(k)] = slot(hi) | ((lo ? slot(lo - 1) : zero) << 16);
+        K.wA[slot(k)] = Z.wA[k];
+    }
+    for (int k = 0; k < m; ++k) K.permB[slot(k)] = slot(Z.ordB_in_A[k]);
+}
+
+int alloc_tree_pools(revs_solver* s) {
+    if (s->d_t_perm) return REVS_OK;
+    std::vector<int64_t> zoff((size_t)s->nf, 0);
+    int64_t tot = 0;
+    for (int f = 0; f < s->nf; ++f) {
+        zoff[f] = tot;
+        const int g = tree_qp_group(s->feeders[f].n);
+        if (g >= 0) tot += 32 * (4 + 2 * g);
+    }
+    s->tree_zoff = zoff;
+    const size_t n = (size_t)tot, hp = (size_t)s->Hp;
+    CU(dalloc(&s->d_t_zoff, (size_t)s->nf));
+    CU(cudaMemcpy(s->d_t_zoff, zoff.data(), sizeof(int64_t) * s->nf, cudaMemcpyHostToDevice));
+    CU(dalloc(&s->d_t_perm, n)); CU(dalloc(&s->d_t_iperm, hp)); CU(dalloc(&s->d_t_nodeA, n)); CU(dalloc(&s->d_t_nodeB, n));
+    CU(dalloc(&s->d_t_cnt, n)); CU(dalloc(&s->d_t_c, n)); CU(dalloc(&s->d_t_d, n)); CU(dalloc(&s->d_t_e, n)); CU(dalloc(&s->d_t_wA, n));
+    s->tree_pool_n = n;
+    return REVS_OK;
+}
+
+// upload the arrays of feeder f
 int upload_zone_arrays(revs_solver* s, int f, const ZoneHost& Z) {
     const FeederDev& fd = s->feeders[f];
-    if (!s->d_t_perm) {
-        const size_t hp = (size_t)s->Hp;
-        CU(dalloc(&s->d_t_perm, hp)); CU(dalloc(&s->d_t_iperm, hp)); CU(dalloc(&s->d_t_nodeA, hp)); CU(dalloc(&s->d_t_nodeB, hp));
-        CU(dalloc(&s->d_t_cnt, hp)); CU(dalloc(&s->d_t_c, hp)); CU(dalloc(&s->d_t_d, hp)); CU(dalloc(&s->d_t_e, hp));
-        CU(dalloc(&s->d_t_wA, hp)); CU(dalloc(&s->d_t_wB, hp));
-    }
-    const size_t ni = sizeof(int) * fd.n, nd = sizeof(double) * fd.n;
-    if (fd.n == 0) return REVS_OK;
-    CU(cudaMemcpy(s->d_t_perm + fd.off, Z.perm.data(), ni, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(s->d_t_iperm + fd.off, Z.iperm.data(), ni, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(s->d_t_nodeA + fd.off, Z.nodeA.data(), ni, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(s->d_t_nodeB + fd.off, Z.nodeB.data(), ni, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(s->d_t_cnt + fd.off, Z.cnt.data(), ni, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(s->d_t_c + fd.off, Z.c.data(), nd, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(s->d_t_d + fd.off, Z.d.data(), nd, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(s->d_t_e + fd.off, Z.e.data(), nd, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(s->d_t_wA + fd.off, Z.wA.data(), nd, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(s->d_t_wB + fd.off, Z.wB.data(), nd, cudaMemcpyHostToDevice));
+    int rc = alloc_tree_pools(s);
+    if (rc) return rc;
+    const int g = tree_qp_group(fd.n);
+    if (fd.n == 0 || g < 0) return REVS_OK;
+    ZonePacked K;
+    pack_zone(Z, fd.n, 4 + 2 * g, K);
+    const size_t S = K.perm.size(), o = (size_t)s->tree_zoff[f];
+    CU(cudaMemcpy(s->d_t_perm + o, K.perm.data(), sizeof(int) * S, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s->d_t_nodeA + o, K.nodeA.data(), sizeof(int) * S, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s->d_t_nodeB + o, K.permB.data(), sizeof(int) * S, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s->d_t_cnt + o, K.cnt.data(), sizeof(int) * S, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s->d_t_c + o, K.c.data(), sizeof(double) * S, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s->d_t_d + o, K.d.data(), sizeof(double) * S, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s->d_t_e + o, K.e.data(), sizeof(double) * S, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s->d_t_wA + o, K.wA.data(), sizeof(double) * S, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s->d_t_iperm + fd.off, Z.iperm.data(), sizeof(int) * fd.n, cudaMemcpyHostToDevice));
     return REVS_OK;
 }
 
 // column lists of the tree kernels: every (zone, hour) of the zones that have tree arrays, by instantiation
 int rebuild_tree_lists(revs_solver* s) {
-    std::vector<int> cols[4];
+    std::vector<int2> cols[4];                     // chunks of columns of one zone: {zone, first hour | count << 16}
+    const int ch = tree_qp_chunk();
+    s->n_dense_cols = s->ncols;
     for (int f = 0; f < s->nf; ++f) {
         if (!s->tree_ok[f] || s->feeders[f].n == 0) continue;
         const int g = tree_qp_group(s->feeders[f].n);
         if (g < 0) continue;
-        for (int t = 0; t < s->T; ++t) cols[g].push_back(f * s->T + t);
+        for (int t = 0; t < s->T; t += ch) cols[g].push_back(make_int2(f, t | (std::min(ch, s->T - t) << 16)));
+        s->n_dense_cols -= s->T;
     }
     s->tree_on = false;
     for (int g = 0; g < 4; ++g) {
@@ -410,7 +467,7 @@ int rebuild_tree_lists(revs_solver* s) {
         s->n_tree_cols[g] = (int)cols[g].size();
         if (cols[g].empty()) continue;
         CU(dalloc(&s->d_tree_cols[g], cols[g].size()));
-        CU(cudaMemcpy(s->d_tree_cols[g], cols[g].data(), sizeof(int) * cols[g].size(), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(s->d_tree_cols[g], cols[g].data(), sizeof(int2) * cols[g].size(), cudaMemcpyHostToDevice));
         s->tree_on = true;
     }
     if (s->loop_exec) { cudaGraphExecDestroy(s->loop_exec); s->loop_exec = nullptr; }     // the captured loop bakes the lists in
@@ -419,8 +476,9 @@ int rebuild_tree_lists(revs_solver* s) {
 
 TreeParams tree_params(revs_solver* s) {
     TreeParams TP{};
+    TP.zoff = s->d_t_zoff;
     TP.perm = s->d_t_perm; TP.iperm = s->d_t_iperm; TP.c = s->d_t_c; TP.d = s->d_t_d; TP.e = s->d_t_e;
-    TP.nodeA = s->d_t_nodeA; TP.wA = s->d_t_wA; TP.nodeB = s->d_t_nodeB; TP.wB = s->d_t_wB; TP.cnt = s->d_t_cnt;
+    TP.nodeA = s->d_t_nodeA; TP.wA = s->d_t_wA; TP.permB = s->d_t_nodeB; TP.cnt = s->d_t_cnt;
     TP.left = &s->d_cnt->tree_left;
     return TP;
 }
@@ -669,7 +727,7 @@ int utility_solve(revs_solver* s, bool in_loop = false) {
         s->tree_left_total += s->h_cnt->tree_left;
         if (s->debug)
             fprintf(stderr, "[revs] admm %d tree stage: %d columns left to the dense kernels, max_ws %d\n", s->k, s->h_cnt->tree_left, s->h_cnt->max_ws);
-        if (s->h_cnt->tree_left == 0) return REVS_OK;
+        if (s->h_cnt->tree_left == 0 && s->n_dense_cols == 0) return REVS_OK;
     }
     bool use[kQpClasses];
     // first round: qp_init_kernel assigns classes on the device by the size of the stored working
@@ -765,7 +823,7 @@ void free_all(revs_solver* s) {
                     s->d_start, s->d_end, s->d_nmin, s->d_nmax, s->d_zero_i, s->d_cost, s->d_zt, s->d_lamt,
                     s->d_gt, s->d_vt, s->d_wcount, s->d_widx, s->d_status, s->d_innerok, s->d_cls, s->d_order, s->d_order4, s->d_order_count, s->d_cnt, s->d_diff,
                     s->d_cprob, s->d_ctiles, s->d_respart, s->d_t_perm, s->d_t_iperm, s->d_t_nodeA, s->d_t_nodeB, s->d_t_cnt,
-                    s->d_t_c, s->d_t_d, s->d_t_e, s->d_t_wA, s->d_t_wB, s->d_tree_cols[0], s->d_tree_cols[1], s->d_tree_cols[2],
+                    s->d_t_c, s->d_t_d, s->d_t_e, s->d_t_wA, s->d_t_wB, s->d_t_zoff, s->d_tree_cols[0], s->d_tree_cols[1], s->d_tree_cols[2],
                     s->d_tree_cols[3]};
     for (int r = 0; r < kMaxPeers; ++r)
         if (s->peer_box[r] && s->peer_box[r] != s->d_mailbox) cudaIpcCloseMemHandle(s->peer_box[r]);
@@ -932,12 +990,14 @@ int revs_create(revs_solver** out, int device, int n_feeders, const int64_t* fee
     {
         const char* e;
         s->warp_m_max = (e = getenv("REVS_WARP_M_MAX")) ? atoi(e) : qp_warp_m_max_default();
-        s->warp_m_max_big = (e = getenv("REVS_WARP_M_MAX_BIG")) ? atoi(e) : std::min(s->warp_m_max, 5);
+        // zones above 128 residences: the same threshold (the first CTA class re-evaluates ALL voltage rows per pass, which on
+        // zones of 150..300 residences costs 30x what the warp kernel's bound-and-recheck does; measured, README_r02.md)
+        s->warp_m_max_big = (e = getenv("REVS_WARP_M_MAX_BIG")) ? atoi(e) : s->warp_m_max;
         s->use_fast = !((e = getenv("REVS_NO_FAST")) && atoi(e));
         s->debug = getenv("REVS_DEBUG") != nullptr;
         s->debug_host = getenv("REVS_DEBUG_HOST") != nullptr;
         if ((e = getenv("REVS_NO_GRAPH")) && atoi(e)) s->use_graph = false;
-        if ((e = getenv("REVS_NO_TREE")) && atoi(e)) s->use_tree = false;
+        if ((e = getenv("REVS_TREE")) && atoi(e)) s->use_tree = true;
         if ((e = getenv("REVS_DEBUG_TRACE")) && sscanf(e, "%d,%d", &s->trace_iter, &s->trace_round) == 2) s->use_graph = false;
         if ((e = getenv("REVS_DEBUG_TRACE_FILE"))) s->trace_file = e;
         if (s->debug) s->use_graph = false;      // the per-round lines need the host-driven loop
@@ -1069,7 +1129,7 @@ int revs_set_feeder_tree(revs_solver* s, int feeder, int n_nodes, const int32_t*
     CU(cudaStreamSynchronize(s->sU));
     s->sens_set[feeder] = 1;
     s->rn2_valid = false;
-    if (tree_qp_group(fd.n) >= 0) {
+    if (s->use_tree && tree_qp_group(fd.n) >= 0) {
         ZoneHost Z;
         build_zone_arrays(n_nodes, parent, cumr.data(), fd.n, res_node, Z);
         int rc = upload_zone_arrays(s, feeder, Z);
@@ -1129,45 +1189,45 @@ int revs_set_feeder_trees(revs_solver* s, const int64_t* node_off, const int32_t
     }
     CU(launch_sens_voltage_batched(s->d_feeders, s->nf, max_n, s->d_pool_off, s->d_pool_parent, s->d_pool_cumr,
                                    s->d_pool_res, s->d_Rpool, s->sU));
-    // static arrays of the tree kernels, all zones into page-able host pools, one upload per array
-    {
-        const size_t hp = (size_t)s->Hp;
-        std::vector<int> perm(hp, 0), iperm(hp, 0), nodeA(hp, 0), nodeB(hp, 0), cnt(hp, 0);
-        std::vector<double> c(hp, 0.0), d(hp, 0.0), e(hp, 0.0), wA(hp, 0.0), wB(hp, 0.0);
+    // static arrays of the tree kernels, all zones into host pools, one upload per array
+    for (int f = 0; f < s->nf; ++f) s->tree_ok[f] = 0;
+    if (s->use_tree) {
+        int rc = alloc_tree_pools(s);
+        if (rc) return rc;
+        const size_t np_ = s->tree_pool_n, hp = (size_t)s->Hp;
+        std::vector<int> perm(np_, -1), iperm(hp, 0), nodeA(np_, 0), permB(np_, 0), cnt(np_, 0);
+        std::vector<double> c(np_, 0.0), d(np_, 0.0), e(np_, 0.0), wA(np_, 0.0);
         ZoneHost Z;
+        ZonePacked K;
         for (int f = 0; f < s->nf; ++f) {
             const FeederDev& fd = s->feeders[f];
             s->tree_ok[f] = 0;
-            if (fd.n == 0 || tree_qp_group(fd.n) < 0) continue;
+            const int g = tree_qp_group(fd.n);
+            if (fd.n == 0 || g < 0) continue;
             const int64_t o = node_off[f];
             build_zone_arrays((int)(node_off[f + 1] - o), parent + o, cumr.data() + o, fd.n, res_node + s->off[f], Z);
-            std::copy(Z.perm.begin(), Z.perm.end(), perm.begin() + fd.off);
+            pack_zone(Z, fd.n, 4 + 2 * g, K);
+            const size_t zo = (size_t)s->tree_zoff[f];
+            std::copy(K.perm.begin(), K.perm.end(), perm.begin() + zo);
+            std::copy(K.nodeA.begin(), K.nodeA.end(), nodeA.begin() + zo);
+            std::copy(K.permB.begin(), K.permB.end(), permB.begin() + zo);
+            std::copy(K.cnt.begin(), K.cnt.end(), cnt.begin() + zo);
+            std::copy(K.c.begin(), K.c.end(), c.begin() + zo);
+            std::copy(K.d.begin(), K.d.end(), d.begin() + zo);
+            std::copy(K.e.begin(), K.e.end(), e.begin() + zo);
+            std::copy(K.wA.begin(), K.wA.end(), wA.begin() + zo);
             std::copy(Z.iperm.begin(), Z.iperm.end(), iperm.begin() + fd.off);
-            std::copy(Z.nodeA.begin(), Z.nodeA.end(), nodeA.begin() + fd.off);
-            std::copy(Z.nodeB.begin(), Z.nodeB.end(), nodeB.begin() + fd.off);
-            std::copy(Z.cnt.begin(), Z.cnt.end(), cnt.begin() + fd.off);
-            std::copy(Z.c.begin(), Z.c.end(), c.begin() + fd.off);
-            std::copy(Z.d.begin(), Z.d.end(), d.begin() + fd.off);
-            std::copy(Z.e.begin(), Z.e.end(), e.begin() + fd.off);
-            std::copy(Z.wA.begin(), Z.wA.end(), wA.begin() + fd.off);
-            std::copy(Z.wB.begin(), Z.wB.end(), wB.begin() + fd.off);
             s->tree_ok[f] = 1;
         }
-        if (!s->d_t_perm) {
-            CU(dalloc(&s->d_t_perm, hp)); CU(dalloc(&s->d_t_iperm, hp)); CU(dalloc(&s->d_t_nodeA, hp)); CU(dalloc(&s->d_t_nodeB, hp));
-            CU(dalloc(&s->d_t_cnt, hp)); CU(dalloc(&s->d_t_c, hp)); CU(dalloc(&s->d_t_d, hp)); CU(dalloc(&s->d_t_e, hp));
-            CU(dalloc(&s->d_t_wA, hp)); CU(dalloc(&s->d_t_wB, hp));
-        }
-        CU(cudaMemcpyAsync(s->d_t_perm, perm.data(), sizeof(int) * hp, cudaMemcpyHostToDevice, s->sU));
+        CU(cudaMemcpyAsync(s->d_t_perm, perm.data(), sizeof(int) * np_, cudaMemcpyHostToDevice, s->sU));
         CU(cudaMemcpyAsync(s->d_t_iperm, iperm.data(), sizeof(int) * hp, cudaMemcpyHostToDevice, s->sU));
-        CU(cudaMemcpyAsync(s->d_t_nodeA, nodeA.data(), sizeof(int) * hp, cudaMemcpyHostToDevice, s->sU));
-        CU(cudaMemcpyAsync(s->d_t_nodeB, nodeB.data(), sizeof(int) * hp, cudaMemcpyHostToDevice, s->sU));
-        CU(cudaMemcpyAsync(s->d_t_cnt, cnt.data(), sizeof(int) * hp, cudaMemcpyHostToDevice, s->sU));
-        CU(cudaMemcpyAsync(s->d_t_c, c.data(), sizeof(double) * hp, cudaMemcpyHostToDevice, s->sU));
-        CU(cudaMemcpyAsync(s->d_t_d, d.data(), sizeof(double) * hp, cudaMemcpyHostToDevice, s->sU));
-        CU(cudaMemcpyAsync(s->d_t_e, e.data(), sizeof(double) * hp, cudaMemcpyHostToDevice, s->sU));
-        CU(cudaMemcpyAsync(s->d_t_wA, wA.data(), sizeof(double) * hp, cudaMemcpyHostToDevice, s->sU));
-        CU(cudaMemcpyAsync(s->d_t_wB, wB.data(), sizeof(double) * hp, cudaMemcpyHostToDevice, s->sU));
+        CU(cudaMemcpyAsync(s->d_t_nodeA, nodeA.data(), sizeof(int) * np_, cudaMemcpyHostToDevice, s->sU));
+        CU(cudaMemcpyAsync(s->d_t_nodeB, permB.data(), sizeof(int) * np_, cudaMemcpyHostToDevice, s->sU));
+        CU(cudaMemcpyAsync(s->d_t_cnt, cnt.data(), sizeof(int) * np_, cudaMemcpyHostToDevice, s->sU));
+        CU(cudaMemcpyAsync(s->d_t_c, c.data(), sizeof(double) * np_, cudaMemcpyHostToDevice, s->sU));
+        CU(cudaMemcpyAsync(s->d_t_d, d.data(), sizeof(double) * np_, cudaMemcpyHostToDevice, s->sU));
+        CU(cudaMemcpyAsync(s->d_t_e, e.data(), sizeof(double) * np_, cudaMemcpyHostToDevice, s->sU));
+        CU(cudaMemcpyAsync(s->d_t_wA, wA.data(), sizeof(double) * np_, cudaMemcpyHostToDevice, s->sU));
         CU(cudaStreamSynchronize(s->sU));     // the host staging vectors die here
     }
     s->stats.kernel_launches++;
@@ -1383,7 +1443,7 @@ int admm_step_impl(revs_solver* s, double sums[3], bool sync_now) {
 // round number) from device counters, so the bodies are captured once.  Nothing returns to the host until the
 // schedule is finished: no round trip per working-set round, no launch latency per kernel.
 int capture_loop(revs_solver* s) {
-    const int flags = (s->screen ? 1 : 0) | (s->screen_impl << 1) | (s->overlap_home ? 4 : 0) | (s->use_warp_kernel ? 8 : 0) | (s->use_fast ? 16 : 0) | (s->comm_world << 8) | (s->comm_rank << 16) | (tree_active(s) ? 32 : 0);
+    const int flags = (s->screen ? 1 : 0) | (s->screen_impl << 1) | (s->overlap_home ? 4 : 0) | (s->use_warp_kernel ? 8 : 0) | (s->use_fast ? 16 : 0) | (s->comm_world << 8) | (s->comm_rank << 16) | (tree_active(s) ? 32 : 0) | (s->n_dense_cols ? 64 : 0);
     if (s->loop_exec && s->gk_kappa == s->kappa && s->gk_vset == s->vset && s->gk_vhigh == s->vhigh && s->gk_tol == s->tol &&
         s->gk_iter_max == s->iter_max && s->gk_flags == flags)
         return REVS_OK;
@@ -1436,7 +1496,8 @@ int capture_loop(revs_solver* s) {
             r = launch_tree_stage(s, Q, false);
             s->stats = keep;
             if (r) return r;
-            CU(launch_tree_gate(&s->d_cnt->tree_left, (unsigned long long)h_round, s->sU));
+            if (s->n_dense_cols == 0)          // zones without tree arrays always need the rounds of the dense kernels
+                CU(launch_tree_gate(&s->d_cnt->tree_left, (unsigned long long)h_round, s->sU));
         }
         // the working-set while node goes into the graph being captured, after what the stream has enqueued so far
         cudaStreamCaptureStatus st;
@@ -1538,7 +1599,7 @@ int revs_solve_admm(revs_solver* s, double kappa, int iter_max, double vset, dou
         int tree_launches = 0;
         if (tree_active(s))
             for (int g = 0; g < 4; ++g) tree_launches += s->n_tree_cols[g] > 0;
-        if (tree_launches) ++tree_launches;            // + the gate of the working-set loop
+        if (tree_launches && s->n_dense_cols == 0) ++tree_launches;            // + the gate of the working-set loop
         s->stats.kernel_launches += (int64_t)s->k * (3 + tree_launches) + (int64_t)s->h_cnt->rounds_total * round_launches(s);
         if (rc) return rc;
     } else {
@@ -1971,8 +2032,13 @@ int revs_set_option(revs_solver* s, const char* name, double value) {
         s->screen = value != 0.0;
         return REVS_OK;
     }
-    if (!strcmp(name, "tree")) {        // 0: dense kernels only (BF16 screening + working rows of R), also for zones given as trees
+    if (!strcmp(name, "tree")) {
+        // 1: zones given as trees (<= 320 residences) are solved by the tree-structured kernel, which needs no sensitivity
+        // matrix (tree_qp.cu); the static arrays are built by revs_set_feeder_tree(s), so set the option before them
         if (mid_run) return fail(REVS_ERR_ARG, "'tree' cannot change between revs_admm_step calls of one run");
+        if (value != 0.0 && !s->use_tree)
+            for (int f = 0; f < s->nf; ++f)
+                if (s->sens_set[f]) return fail(REVS_ERR_ARG, "set option 'tree' before revs_set_feeder_tree(s): the tree arrays are built there");
         s->use_tree = value != 0.0;
         return REVS_OK;
     }

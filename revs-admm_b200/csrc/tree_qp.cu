@@ -42,28 +42,32 @@ constexpr int kPassMaxT = 12;                // admit / solve / verify passes be
 
 template <int NJ>
 struct TreeSmem {
-    double G[32 * NJ + 1];                   // prefix sums / scatter-gather scratch
-    double S1[32 * NJ + 1];
+    double X[32 * NJ + 1];                   // argument of tree_product / result of gen_row   (slot layout, see CtaZone)
+    double V[32 * NJ + 1];                   // result of tree_product; inside it: the prefix sums of X (slot 32 NJ holds 0)
+    double S1[32 * NJ + 1];                  // scratch of tree_product (slot 32 NJ holds 0)
     double S2[32 * NJ + 1];
     double H[kWW * kTH];
     double L[kWW * kTH];
 };
 
-template <int NJ> struct TreeCfg { static constexpr int kCtas = NJ <= 6 ? 4 : 3; };
+template <int NJ> struct TreeCfg { static constexpr int kCtas = NJ <= 4 ? 4 : 3; };
 
-struct ZonePtr {                             // static arrays of one zone (TreeParams pools + zone offset)
-    const int* perm;
-    const int* iperm;
-    const double* c;
-    const double* d;
-    const double* e;
-    const int* nodeA;
-    const double* wA;
-    const int* nodeB;
-    const double* wB;
-    const int* cnt;
-    int n;
+// Static arrays of one zone, staged in shared memory once per CTA and chunk of columns (all four warps of a CTA work
+// on columns of the same zone).  Position p (lane p / NJ, slot p % NJ) is stored at slot(p) = (p % NJ) * 32 + p / NJ,
+// so the k-th element of every lane is one conflict-free 32-wide access; the Cartesian-tree nodes and the counts carry
+// ready-made slots into the per-warp arrays (the extra slot 32 NJ holds 0).
+template <int NJ>
+struct CtaZone {
+    double c[32 * NJ];    // [slot(p)] c[p] = 2 cumr(lca(p, p+1)), 0 beyond the zone
+    double d[32 * NJ];    // R[p][p]
+    double e[32 * NJ];    // d[p] - max(c[p-1], c[p])
+    double wA[32 * NJ];   // weight of the k-th Cartesian-tree node in lo-order, at slot(k)
+    int perm[32 * NJ];    // home index of position p, -1 beyond the zone
+    int nodeA[32 * NJ];   // k-th node in lo-order: slot of G[hi] | slot of G[lo - 1] << 16
+    int permB[32 * NJ];   // k-th node in hi-order: slot of that node in lo-order
+    int cnt[32 * NJ];     // slot of S1[#lo <= p] | slot of S2[#hi < p] << 16
 };
+template <int NJ> __device__ __forceinline__ int slot_of(int p) { return (p % NJ) * 32 + p / NJ; }
 
 // in-place inclusive prefix sum over the warp's 32 * NJ positions (lane-major, contiguous)
 template <int NJ>
@@ -83,65 +87,57 @@ __device__ __forceinline__ void scan_incl(double (&x)[NJ]) {
     for (int k = 0; k < NJ; ++k) x[k] += ex;
 }
 
-// v = R x for every row of the zone (see the header).  x is kept; smem arrays are scratch.
+// sm.V = R sm.X for every row of the zone (see the header).  ONE copy of this code per kernel (not inlined: with the
+// products inlined at their seven call sites the kernel outgrew the instruction cache and stalled on fetches);
+// vectors travel through shared memory in the slot layout.
 template <int NJ>
-__device__ __forceinline__ void tree_product(const ZonePtr& Z, const double (&x)[NJ], double (&v)[NJ], TreeSmem<NJ>& sm) {
-    const int lane = threadIdx.x & 31, p0 = lane * NJ, n = Z.n;
+__device__ __noinline__ void tree_product(const CtaZone<NJ>* Zp, TreeSmem<NJ>* smp) {
+    const CtaZone<NJ>& Z = *Zp;
+    TreeSmem<NJ>& sm = *smp;
+    double* G = sm.V;
+    const int lane = threadIdx.x & 31;
     double t[NJ];
+    __syncwarp();
 #pragma unroll
-    for (int k = 0; k < NJ; ++k) t[k] = x[k];
+    for (int k = 0; k < NJ; ++k) t[k] = sm.X[k * 32 + lane];
     scan_incl<NJ>(t);
-    __syncwarp();
-    if (lane == 0) { sm.G[0] = 0.0; sm.S1[0] = 0.0; sm.S2[0] = 0.0; }
 #pragma unroll
-    for (int k = 0; k < NJ; ++k) sm.G[p0 + k + 1] = t[k];
+    for (int k = 0; k < NJ; ++k) G[k * 32 + lane] = t[k];             // G[slot(p)] = sum of x over positions <= p
     __syncwarp();
 #pragma unroll
-    for (int k = 0; k < NJ; ++k) {
-        const int q = p0 + k;
-        double tq = 0.0;
-        if (q < n - 1) {
-            const int nd = Z.nodeA[q];
-            tq = Z.wA[q] * (sm.G[(nd >> 16) + 1] - sm.G[nd & 0xffff]);
-        }
-        t[k] = tq;
+    for (int k = 0; k < NJ; ++k) {                                     // node weights times subtree sums, nodes in lo-order
+        const int nd = Z.nodeA[k * 32 + lane];
+        t[k] = Z.wA[k * 32 + lane] * (G[nd & 0xffff] - G[nd >> 16]);
+        sm.S2[k * 32 + lane] = t[k];
     }
     scan_incl<NJ>(t);
 #pragma unroll
-    for (int k = 0; k < NJ; ++k) sm.S1[p0 + k + 1] = t[k];
+    for (int k = 0; k < NJ; ++k) sm.S1[k * 32 + lane] = t[k];
+    __syncwarp();
 #pragma unroll
-    for (int k = 0; k < NJ; ++k) {
-        const int q = p0 + k;
-        double tq = 0.0;
-        if (q < n - 1) {
-            const int nd = Z.nodeB[q];
-            tq = Z.wB[q] * (sm.G[(nd >> 16) + 1] - sm.G[nd & 0xffff]);
-        }
-        t[k] = tq;
-    }
+    for (int k = 0; k < NJ; ++k) t[k] = sm.S2[Z.permB[k * 32 + lane]];  // the same products, nodes in hi-order
+    __syncwarp();
     scan_incl<NJ>(t);
 #pragma unroll
-    for (int k = 0; k < NJ; ++k) sm.S2[p0 + k + 1] = t[k];
+    for (int k = 0; k < NJ; ++k) sm.S2[k * 32 + lane] = t[k];
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < NJ; ++k) {
-        const int p = p0 + k;
-        double r = 0.0;
-        if (p < n) {
-            const int cn = Z.cnt[p];
-            r = fma(Z.e[p], x[k], sm.S1[cn & 0xffff] - sm.S2[cn >> 16]);
-        }
-        v[k] = r;
+        const int cn = Z.cnt[k * 32 + lane];
+        sm.V[k * 32 + lane] = fma(Z.e[k * 32 + lane], sm.X[k * 32 + lane], sm.S1[cn & 0xffff] - sm.S2[cn >> 16]);
     }
+    __syncwarp();
 }
 
-// row i of R (depth-first positions): min of c over the positions between i and j, d[i] on the diagonal
+// sm.X = row i of R (depth-first positions): min of c over the positions between i and j, d[i] on the diagonal
 template <int NJ>
-__device__ __forceinline__ void gen_row(const ZonePtr& Z, int i, double (&row)[NJ]) {
-    const int lane = threadIdx.x & 31, p0 = lane * NJ, n = Z.n;
+__device__ __noinline__ void gen_row(const CtaZone<NJ>* Zp, int i, TreeSmem<NJ>* smp) {
+    const CtaZone<NJ>& Z = *Zp;
+    TreeSmem<NJ>& sm = *smp;
+    const int lane = threadIdx.x & 31, p0 = lane * NJ;
     double cq[NJ], right[NJ], left[NJ];
 #pragma unroll
-    for (int k = 0; k < NJ; ++k) cq[k] = (p0 + k < n - 1) ? Z.c[p0 + k] : 0.0;     // beyond the zone: 0 -> padded entries are 0
+    for (int k = 0; k < NJ; ++k) cq[k] = Z.c[k * 32 + lane];          // beyond the zone: 0 -> padded entries are 0
     double run = CUDART_INF;
 #pragma unroll
     for (int k = 0; k < NJ; ++k) {                     // j > i: min over c-positions [i, j-1]
@@ -170,37 +166,33 @@ __device__ __forceinline__ void gen_row(const ZonePtr& Z, int i, double (&row)[N
     }
     double offl = __shfl_down_sync(0xffffffffu, t, 1);
     if (lane == 31) offl = CUDART_INF;
-    const double di = Z.d[i];
+    const double di = Z.d[slot_of<NJ>(i)];
+    __syncwarp();
 #pragma unroll
     for (int k = 0; k < NJ; ++k) {
         const int p = p0 + k;
-        row[k] = p > i ? fmin(offr, right[k]) : (p < i ? fmin(offl, left[k]) : di);
+        sm.X[k * 32 + lane] = p > i ? fmin(offr, right[k]) : (p < i ? fmin(offl, left[k]) : di);
     }
+    __syncwarp();
 }
 
-// x[p] = val_a at the positions pos_a of the working rows (lanes a < m), 0 elsewhere
+// sm.X[p] = val_a at the positions pos_a of the working rows (lanes a < m), 0 elsewhere
 template <int NJ>
-__device__ __forceinline__ void scatter_rows(int m, int pos, double val, double (&x)[NJ], TreeSmem<NJ>& sm) {
-    const int lane = threadIdx.x & 31, p0 = lane * NJ;
+__device__ __forceinline__ void scatter_rows(int m, int pos, double val, TreeSmem<NJ>& sm) {
+    const int lane = threadIdx.x & 31;
     __syncwarp();
 #pragma unroll
-    for (int k = 0; k < NJ; ++k) sm.G[p0 + k] = 0.0;
+    for (int k = 0; k < NJ; ++k) sm.X[k * 32 + lane] = 0.0;
     __syncwarp();
-    if (lane < m) sm.G[pos] = val;
-    __syncwarp();
-#pragma unroll
-    for (int k = 0; k < NJ; ++k) x[k] = sm.G[p0 + k];
+    if (lane < m) sm.X[slot_of<NJ>(pos)] = val;
 }
 
-// value of the position vector v at the position of this lane's working row
 template <int NJ>
-__device__ __forceinline__ double gather_rows(int m, int pos, const double (&v)[NJ], TreeSmem<NJ>& sm) {
-    const int lane = threadIdx.x & 31, p0 = lane * NJ;
+__device__ __forceinline__ void store_x(const double (&x)[NJ], TreeSmem<NJ>& sm) {
+    const int lane = threadIdx.x & 31;
     __syncwarp();
 #pragma unroll
-    for (int k = 0; k < NJ; ++k) sm.G[p0 + k] = v[k];
-    __syncwarp();
-    return lane < m ? sm.G[pos] : 0.0;
+    for (int k = 0; k < NJ; ++k) sm.X[k * 32 + lane] = x[k];
 }
 
 struct TreeStats {
@@ -210,14 +202,17 @@ struct TreeStats {
 };
 
 template <int NJ>
-__device__ __forceinline__ void tree_column(const QpParams& P, const TreeParams& TP, const int c, TreeSmem<NJ>& sm, TreeStats& st) {
+__device__ __forceinline__ void tree_column(const QpParams& P, const TreeParams& TP, const int c, const CtaZone<NJ>* Zp, TreeSmem<NJ>& sm, TreeStats& st) {
     const int lane = threadIdx.x & 31, p0 = lane * NJ;
     const unsigned full = 0xffffffffu;
     const int f = c / P.T, t = c % P.T;
     const FeederDev fd = P.feeders[f];
     const int n = fd.n;
     const size_t zo = (size_t)fd.off;
-    ZonePtr Z{TP.perm + zo, TP.iperm + zo, TP.c + zo, TP.d + zo, TP.e + zo, TP.nodeA + zo, TP.wA + zo, TP.nodeB + zo, TP.wB + zo, TP.cnt + zo, n};
+    const CtaZone<NJ>& Z = *Zp;
+    const CtaZone<NJ>* Zc = Zp;
+    const int* __restrict__ iperm = TP.iperm + zo;
+    if (lane == 0) { sm.V[32 * NJ] = 0.0; sm.S1[32 * NJ] = 0.0; sm.S2[32 * NJ] = 0.0; }     // the zero slot of the products
     const size_t col = (size_t)t * P.Hp + zo;
     const double* __restrict__ z = P.z_t + col;
     double* lam_g = P.lam_t + col;
@@ -232,8 +227,8 @@ __device__ __forceinline__ void tree_column(const QpParams& P, const TreeParams&
 #pragma unroll
     for (int k = 0; k < NJ; ++k) {
         const int p = p0 + k;
-        hk[k] = p < n ? Z.perm[p] : -1;
-        zj[k] = p < n ? z[hk[k]] : 0.0;
+        hk[k] = Z.perm[k * 32 + lane];
+        zj[k] = (p < n && hk[k] >= 0) ? z[hk[k]] : 0.0;
     }
 
     // ---- working set: rows with a positive multiplier (order kept), lanes = rows; pos = depth-first position
@@ -246,23 +241,22 @@ __device__ __forceinline__ void tree_column(const QpParams& P, const TreeParams&
         const int src = __fns(keep, 0, lane + 1);
         const int si = __shfl_sync(full, wi, src & 31);
         const double sl = __shfl_sync(full, l, src & 31);
-        if (lane < m) { pos = Z.iperm[si]; lam = sl; }
+        if (lane < m) { pos = iperm[si]; lam = sl; }
     }
     // g = [z - R lam]_+ , v = R g
-    {
-        double pi[NJ];
-        if (m > 0) {
-            double x[NJ];
-            scatter_rows<NJ>(m, pos, lam, x, sm);
-            tree_product<NJ>(Z, x, pi, sm);
-        } else {
+    if (m > 0) {
+        scatter_rows<NJ>(m, pos, lam, sm);
+        tree_product<NJ>(Zc, &sm);
 #pragma unroll
-            for (int k = 0; k < NJ; ++k) pi[k] = 0.0;
-        }
+        for (int k = 0; k < NJ; ++k) gj[k] = fmax(zj[k] - sm.V[k * 32 + lane], 0.0);
+    } else {
 #pragma unroll
-        for (int k = 0; k < NJ; ++k) gj[k] = fmax(zj[k] - pi[k], 0.0);
+        for (int k = 0; k < NJ; ++k) gj[k] = fmax(zj[k], 0.0);
     }
-    tree_product<NJ>(Z, gj, v, sm);
+    store_x<NJ>(gj, sm);
+    tree_product<NJ>(Zc, &sm);
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) v[k] = sm.V[k * 32 + lane];
 
     double flops = 0.0;
     int its_total = 0;
@@ -309,7 +303,9 @@ __device__ __forceinline__ void tree_column(const QpParams& P, const TreeParams&
         if (m == 1) {
             // one row: v(l) = r . [z - r l]_+ is convex, piecewise linear, non-increasing; Newton on v(l) = u
             double r1[NJ];
-            gen_row<NJ>(Z, __shfl_sync(full, pos, 0), r1);
+            gen_row<NJ>(Zc, __shfl_sync(full, pos, 0), &sm);
+#pragma unroll
+            for (int k = 0; k < NJ; ++k) r1[k] = sm.X[k * 32 + lane];
             const double l_in = __shfl_sync(full, lam, 0);
             double l = l_in;
 #pragma unroll 1
@@ -343,7 +339,7 @@ __device__ __forceinline__ void tree_column(const QpParams& P, const TreeParams&
 
         if (!ok) {
             // ---- piecewise-quadratic descent on W; every matrix-vector product is a tree product
-            const double scale = warp_sum(row ? P.rn2[zo + Z.perm[pos]] : 0.0) / (double)max(m, 1);
+            const double scale = warp_sum(row ? P.rn2[zo + Z.perm[slot_of<NJ>(pos)]] : 0.0) / (double)max(m, 1);
             const double shift = kHessShiftT * scale + 1e-300;
             double phi;
             {
@@ -356,11 +352,9 @@ __device__ __forceinline__ void tree_column(const QpParams& P, const TreeParams&
 #pragma unroll 1
             for (; its < P.inner_max; ++its) {
                 // gradient on W from the exact voltages of the current g
-                {
-                    double vv[NJ];
-                    tree_product<NJ>(Z, gj, vv, sm);
-                    grad = u - gather_rows<NJ>(m, pos, vv, sm);
-                }
+                store_x<NJ>(gj, sm);
+                tree_product<NJ>(Zc, &sm);
+                grad = row ? u - sm.V[slot_of<NJ>(pos)] : 0.0;
                 flops += 6.0 * n;
                 const double kk = row ? fabs(lam > 0.0 ? grad : fmin(grad, 0.0)) : 0.0;
                 if (warp_max(kk) < tol) { ok = 1; break; }
@@ -368,14 +362,12 @@ __device__ __forceinline__ void tree_column(const QpParams& P, const TreeParams&
                 // Hessian of the current piece: column q = R (row_q restricted to {g > 0}) at the working rows
 #pragma unroll 1
                 for (int q = 0; q < m; ++q) {
-                    double x[NJ], y[NJ];
-                    gen_row<NJ>(Z, __shfl_sync(full, pos, q), x);
+                    gen_row<NJ>(Zc, __shfl_sync(full, pos, q), &sm);
 #pragma unroll
                     for (int k = 0; k < NJ; ++k)
-                        if (!(gj[k] > 0.0)) x[k] = 0.0;
-                    tree_product<NJ>(Z, x, y, sm);
-                    const double h = gather_rows<NJ>(m, pos, y, sm);
-                    if (row) sm.H[lane * kTH + q] = h;
+                        if (!(gj[k] > 0.0)) sm.X[k * 32 + lane] = 0.0;
+                    tree_product<NJ>(Zc, &sm);
+                    if (row) sm.H[lane * kTH + q] = sm.V[slot_of<NJ>(pos)];
                 }
                 flops += 8.0 * n * m;
                 __syncwarp();
@@ -465,13 +457,12 @@ __device__ __forceinline__ void tree_column(const QpParams& P, const TreeParams&
                 for (; alpha >= kArcMinT; alpha *= 0.5) {
                     lt = row ? fmax(fma(alpha, dir, lam), 0.0) : 0.0;
                     {
-                        double x[NJ], pi[NJ];
-                        scatter_rows<NJ>(m, pos, lt, x, sm);
-                        tree_product<NJ>(Z, x, pi, sm);
+                        scatter_rows<NJ>(m, pos, lt, sm);
+                        tree_product<NJ>(Zc, &sm);
                         double acc = 0.0;
 #pragma unroll
                         for (int k = 0; k < NJ; ++k) {
-                            gt[k] = fmax(zj[k] - pi[k], 0.0);
+                            gt[k] = fmax(zj[k] - sm.V[k * 32 + lane], 0.0);
                             acc = fma(gt[k], gt[k], acc);
                         }
                         phin = 0.5 * warp_sum(acc) + u * warp_sum(row ? lt : 0.0);
@@ -509,7 +500,10 @@ __device__ __forceinline__ void tree_column(const QpParams& P, const TreeParams&
                 }
             }
         }
-        tree_product<NJ>(Z, gj, v, sm);
+        store_x<NJ>(gj, sm);
+        tree_product<NJ>(Zc, &sm);
+#pragma unroll
+        for (int k = 0; k < NJ; ++k) v[k] = sm.V[k * 32 + lane];
         flops += 6.0 * n;
     }
 
@@ -520,7 +514,7 @@ __device__ __forceinline__ void tree_column(const QpParams& P, const TreeParams&
         if (lane < m_old) lam_g[wi] = 0.0;
         __syncwarp();
         if (lane < m) {
-            const int h = Z.perm[pos];
+            const int h = Z.perm[slot_of<NJ>(pos)];
             lam_g[h] = lam;
             widx[lane] = h;
         }
@@ -539,21 +533,41 @@ __device__ __forceinline__ void tree_column(const QpParams& P, const TreeParams&
     st.max_ws = max(st.max_ws, m);
 }
 
+// Work comes in CHUNKS of columns of one zone (int2 {zone, first hour | count << 16}, built on the host): the CTA stages
+// the zone's static arrays in shared memory once per chunk (skipped when the zone is the one already staged) and its
+// four warps take the chunk's columns round-robin.
 template <int NJ>
-__global__ void __launch_bounds__(32 * kTWarps, TreeCfg<NJ>::kCtas) tree_qp_kernel(QpParams P, TreeParams TP, const int* __restrict__ cols,
-                                                                                  int ncols, int* __restrict__ queue) {
+__global__ void __launch_bounds__(32 * kTWarps, TreeCfg<NJ>::kCtas) tree_qp_kernel(QpParams P, TreeParams TP, const int2* __restrict__ chunks,
+                                                                                  int nchunks, int* __restrict__ queue) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using Smem = TreeSmem<NJ>;
+    CtaZone<NJ>& Z = *reinterpret_cast<CtaZone<NJ>*>(smem_raw);
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    Smem& sm = reinterpret_cast<Smem*>(smem_raw)[wib];
+    Smem& sm = reinterpret_cast<Smem*>(smem_raw + sizeof(CtaZone<NJ>))[wib];
+    __shared__ int s_slot;
     TreeStats st;
+    int staged = -1;
     for (;;) {
-        int slot = 0;
-        if (lane == 0) slot = atomicAdd(queue, 1);
-        slot = __shfl_sync(0xffffffffu, slot, 0);
-        if (slot >= ncols) break;
-        tree_column<NJ>(P, TP, cols[slot], sm, st);
-        __syncwarp();
+        __syncthreads();                                   // everybody is done with the staged zone and with s_slot
+        if (threadIdx.x == 0) s_slot = atomicAdd(queue, 1);
+        __syncthreads();
+        const int slot = s_slot;
+        if (slot >= nchunks) break;
+        const int2 ch = chunks[slot];
+        const int f = ch.x, t0 = ch.y & 0xffff, cnt = ch.y >> 16;
+        if (f != staged) {
+            const size_t so = (size_t)TP.zoff[f];
+            for (int i = threadIdx.x; i < 32 * NJ; i += 32 * kTWarps) {
+                Z.c[i] = TP.c[so + i]; Z.d[i] = TP.d[so + i]; Z.e[i] = TP.e[so + i]; Z.wA[i] = TP.wA[so + i];
+                Z.perm[i] = TP.perm[so + i]; Z.nodeA[i] = TP.nodeA[so + i]; Z.permB[i] = TP.permB[so + i]; Z.cnt[i] = TP.cnt[so + i];
+            }
+            staged = f;
+            __syncthreads();
+        }
+        for (int k = wib; k < cnt; k += kTWarps) {
+            tree_column<NJ>(P, TP, f * P.T + t0 + k, &Z, sm, st);
+            __syncwarp();
+        }
     }
     if (lane == 0) {
         if (st.its) atomicAdd(P.newton_its, st.its);
@@ -567,7 +581,7 @@ __global__ void __launch_bounds__(32 * kTWarps, TreeCfg<NJ>::kCtas) tree_qp_kern
 template <int NJ>
 cudaError_t prepare_tree_nj(int* n_sm_out) {
     static int n_sm[64] = {0};
-    const int smem = (int)sizeof(TreeSmem<NJ>) * kTWarps;
+    const int smem = (int)(sizeof(TreeSmem<NJ>) * kTWarps + sizeof(CtaZone<NJ>));
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
@@ -584,11 +598,11 @@ cudaError_t prepare_tree_nj(int* n_sm_out) {
 }
 
 template <int NJ>
-cudaError_t launch_tree_nj(const QpParams& P, const TreeParams& TP, const int* cols, int ncols, int* queue, cudaStream_t stream) {
+cudaError_t launch_tree_nj(const QpParams& P, const TreeParams& TP, const int2* cols, int ncols, int* queue, cudaStream_t stream) {
     int n_sm = 0;
     cudaError_t e = prepare_tree_nj<NJ>(&n_sm);
     if (e != cudaSuccess) return e;
-    const int smem = (int)sizeof(TreeSmem<NJ>) * kTWarps;
+    const int smem = (int)(sizeof(TreeSmem<NJ>) * kTWarps + sizeof(CtaZone<NJ>));
     tree_qp_kernel<NJ><<<n_sm * TreeCfg<NJ>::kCtas, 32 * kTWarps, smem, stream>>>(P, TP, cols, ncols, queue);
     return cudaGetLastError();
 }
@@ -613,9 +627,11 @@ cudaError_t tree_qp_prepare() {
     return e;
 }
 
+int tree_qp_chunk() { return 2 * kTWarps; }
+
 int tree_qp_group(int n) { return n <= 128 ? 0 : (n <= 192 ? 1 : (n <= 256 ? 2 : (n <= kWarpMaxN ? 3 : -1))); }
 
-cudaError_t launch_tree_qp(const QpParams& P, const TreeParams& TP, int group, const int* cols, int ncols, int* queue, cudaStream_t stream) {
+cudaError_t launch_tree_qp(const QpParams& P, const TreeParams& TP, int group, const int2* cols, int ncols, int* queue, cudaStream_t stream) {
     if (ncols <= 0) return cudaSuccess;
     switch (group) {
         case 0: return launch_tree_nj<4>(P, TP, cols, ncols, queue, stream);

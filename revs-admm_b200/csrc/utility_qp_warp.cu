@@ -65,11 +65,14 @@ struct WarpSmemT {
 };
 // zones of up to 256 residences: 1024 doubles of cached working rows per warp (4 CTAs per SM);
 // 257..320 residences (NJ = 10, 3 CTAs per SM): 1536, i.e. at least four full rows
-#ifndef REVS_WARP_CTAS_SMALL      // build-time experiment knobs (profiles/build_variants.sh); the defaults are the measured best
-#define REVS_WARP_CTAS_SMALL kCtasPerSm
+// CTAs per SM of the NJ >= 6 instantiations.  Measured on the reference-shaped population (profiles/README_r02.md):
+// at 4 (128 registers) and 3 (168) the kernels spill 130..570 bytes per thread into a 28 KB L1 and every phase of a column
+// runs twice as long; at 2 (255 registers, no spills) the step is 13 % faster in spite of half the resident warps.
+#ifndef REVS_WARP_CTAS_SMALL      // build-time experiment knobs (profiles/build_variants.sh)
+#define REVS_WARP_CTAS_SMALL 2
 #endif
 #ifndef REVS_WARP_CTAS_BIG
-#define REVS_WARP_CTAS_BIG 3
+#define REVS_WARP_CTAS_BIG 2
 #endif
 template <int NJ> struct WarpCfg {
     static constexpr int kCache = NJ <= 8 ? kCacheDoubles : 1536;
@@ -1067,6 +1070,6 @@ cudaError_t launch_utility_qp_warp(const QpParams& P, int nj, int ctas_per_sm, c
 }
 
 int qp_warp_ctas_per_sm() { return kCtasPerSm; }
-int qp_warp_m_max_default() { return kWW - kHysteresisW; }
+int qp_warp_m_max_default() { return kWW; }
 
 }  // namespace revs

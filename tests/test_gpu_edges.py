@@ -229,8 +229,9 @@ def test_pipelined_solver_equals_single_solver(gpu_lib, pipelines):
         assert np.array_equal(base[k], out[k]), k
 
 
+@pytest.mark.parametrize("tree", [1, 0])
 @pytest.mark.parametrize("sizes,T,vhigh", [([140, 60, 33], 48, 1.015), ([300, 210], 24, 1.02), ([600, 90], 24, 1.05), ([120, 96], 12, 1.02)])
-def test_captured_loop_equals_host_driven_loop(gpu_lib, sizes, T, vhigh):
+def test_captured_loop_equals_host_driven_loop(gpu_lib, sizes, T, vhigh, tree):
     """revs_solve_admm from ONE captured graph (ADMM iterations and working-set rounds decided on the
     device, CTA classes behind IF nodes) against the host-driven loop (one host sync per round):
     bit-identical results, same number of working-set rounds -- including zones that need several rounds
@@ -245,6 +246,7 @@ def test_captured_loop_equals_host_driven_loop(gpu_lib, sizes, T, vhigh):
     for graph in (1, 0):
         with gpu_lib.Solver(sizes, T) as s:
             s.set_option("graph", graph)
+            s.set_option("tree", tree)
             s.set_feeder_trees(trees)
             s.set_homes(**hm)
             s.set_tariff(cost)
@@ -258,7 +260,9 @@ def test_captured_loop_equals_host_driven_loop(gpu_lib, sizes, T, vhigh):
             outs.append(out)
     for k in ("P_sch", "P_ev", "SOC", "diff", "P_est", "Gamma"):
         assert np.array_equal(outs[0][k], outs[1][k]), k
-    assert rounds[0] == rounds[1] >= kw["iter_max"]
+    assert rounds[0] == rounds[1]
+    if tree == 0 or max(sizes) > 320:                # the dense kernels run at least one working-set round per iteration
+        assert rounds[0] >= kw["iter_max"]
 
 
 def test_captured_loop_stops_on_the_device(gpu_lib):
@@ -377,7 +381,7 @@ def test_tree_kernel_equals_dense_kernels(gpu_lib, sizes, T, vhigh):
     outs = []
     for tree in (1, 0):
         with gpu_lib.Solver(sizes, T) as s:
-            s.set_option("tree", tree)
+            s.set_option("tree", tree)               # before the trees: the tree arrays are built by set_feeder_trees
             s.set_feeder_trees(trees)
             s.set_homes(**hm)
             s.set_tariff(cost)
@@ -394,4 +398,4 @@ def test_tree_kernel_equals_dense_kernels(gpu_lib, sizes, T, vhigh):
     assert np.abs(outs[0]["P_est"] - outs[1]["P_est"]).max() <= 1e-7
     assert outs[0]["stats"]["max_working_set"] >= 2
     if T != 12:                                      # (T = 12: working sets beyond 16 rows go on to the dense kernels)
-        assert outs[0]["stats"]["gemm_launches"] == 0 < outs[1]["stats"]["gemm_launches"]
+        assert outs[0]["stats"]["gemm_launches"] < outs[1]["stats"]["gemm_launches"]
