@@ -142,7 +142,7 @@ struct revs_solver {
     double *d_t_c = nullptr, *d_t_d = nullptr, *d_t_e = nullptr, *d_t_wA = nullptr, *d_t_wB = nullptr;
     int64_t* d_t_zoff = nullptr;               // offset of every zone in the strided pools (32 NJ entries per zone)
     std::vector<int64_t> tree_zoff;
-    size_t tree_pool_n = 0;
+    size_t tree_pool_n = 0, tree_sig = 0;
     int n_dense_cols = 0;                      // columns of zones without tree arrays: the dense kernels always run for them
     int2* d_tree_cols[4] = {nullptr, nullptr, nullptr, nullptr};  // chunks of columns by instantiation (NJ = 4, 6, 8, 10)
     int n_tree_cols[4] = {0, 0, 0, 0};
@@ -470,7 +470,12 @@ int rebuild_tree_lists(revs_solver* s) {
         CU(cudaMemcpy(s->d_tree_cols[g], cols[g].data(), sizeof(int2) * cols[g].size(), cudaMemcpyHostToDevice));
         s->tree_on = true;
     }
-    if (s->loop_exec) { cudaGraphExecDestroy(s->loop_exec); s->loop_exec = nullptr; }     // the captured loop bakes the lists in
+    // the captured loop bakes the lists in: a new capture only when they changed
+    size_t sig = 1469598103934665603ull;
+    for (int g = 0; g < 4; ++g)
+        for (const int2& c : cols[g]) { sig = (sig ^ (size_t)(unsigned)c.x) * 1099511628211ull; sig = (sig ^ (size_t)(unsigned)c.y) * 1099511628211ull; }
+    if (sig != s->tree_sig && s->loop_exec) { cudaGraphExecDestroy(s->loop_exec); s->loop_exec = nullptr; }
+    s->tree_sig = sig;
     return REVS_OK;
 }
 
@@ -990,8 +995,8 @@ int revs_create(revs_solver** out, int device, int n_feeders, const int64_t* fee
     {
         const char* e;
         s->warp_m_max = (e = getenv("REVS_WARP_M_MAX")) ? atoi(e) : qp_warp_m_max_default();
-        // zones above 128 residences: the same threshold (the first CTA class re-evaluates ALL voltage rows per pass, which on
-        // zones of 150..300 residences costs 30x what the warp kernel's bound-and-recheck does; measured, README_r02.md)
+        // zones above 128 residences: the same threshold (round 1 sent stored sets above 5 rows to the first CTA class, which
+        // cost 8.5 of 21 ms per schedule on zones of 150..300 residences; measured, profiles/README_r02.md)
         s->warp_m_max_big = (e = getenv("REVS_WARP_M_MAX_BIG")) ? atoi(e) : s->warp_m_max;
         s->use_fast = !((e = getenv("REVS_NO_FAST")) && atoi(e));
         s->debug = getenv("REVS_DEBUG") != nullptr;

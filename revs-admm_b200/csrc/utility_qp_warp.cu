@@ -1070,6 +1070,6 @@ cudaError_t launch_utility_qp_warp(const QpParams& P, int nj, int ctas_per_sm, c
 }
 
 int qp_warp_ctas_per_sm() { return kCtasPerSm; }
-int qp_warp_m_max_default() { return kWW; }
+int qp_warp_m_max_default() { return kWW - kHysteresisW; }
 
 }  // namespace revs
