@@ -24,7 +24,7 @@ struct FeederDev {
     int n;            // residences
     int np;           // padded residences (multiple of kPad) == leading dim of R block
     int64_t off;      // first padded home index
-    int64_t roff;     // offset (doubles) of the n_p x n_p block in the R pool
+    int64_t roff;     // offset (doubles) of the n_p x n_p block in the R pool; -1: no dense block (tree-Newton zone)
 };
 
 // Output layout / transform of the sensitivity contraction.

@@ -35,7 +35,7 @@ __global__ void sens_voltage_batched_kernel(const FeederDev* __restrict__ feeder
                                             const int* __restrict__ res_node, double* __restrict__ Rpool) {
     const FeederDev fd = feeders[blockIdx.z];
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= fd.n) return;
+    if (j >= fd.n || fd.roff < 0) return;          // roff < 0: zone of the tree-Newton path, no dense block
     const int* par = parent + node_off[blockIdx.z];
     const double* cr = cumr + node_off[blockIdx.z];
     const int* res = res_node + fd.off;
@@ -85,6 +85,7 @@ __global__ void row_norms_kernel(const FeederDev* __restrict__ feeders, const do
                                  double* __restrict__ rn2, double* __restrict__ rmax) {
     const FeederDev fd = feeders[blockIdx.y];
     const int lane = threadIdx.x & 31;
+    if (fd.roff < 0) return;
     for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < fd.n; i += gridDim.x * (blockDim.x >> 5)) {
         const double* row = Rpool + fd.roff + (size_t)i * fd.np;
         double acc = 0.0, mx = 0.0;

@@ -1,5 +1,7 @@
 // Parameter blocks and launchers of the REVS ADMM kernels (one .cu per kernel family).
 #pragma once
+#include <vector>
+
 #include "common.cuh"
 
 namespace revs {
@@ -190,6 +192,57 @@ cudaError_t tree_qp_prepare();
 int tree_qp_chunk();            // columns per work chunk (all of one zone)
 cudaError_t launch_tree_qp(const QpParams& P, const TreeParams& TP, int group, const int2* chunks, int nchunks, int* queue, cudaStream_t stream);
 cudaError_t launch_tree_gate(const int* left, unsigned long long cond_round, cudaStream_t stream);
+
+// ---- tree_newton.cu: the operator QP of a large radial zone, one CTA per column, all linear algebra on the tree
+struct NewtonZone {             // one zone of the Newton path
+    int feeder;                 // index of the zone in the solver
+    int nn, nlev, n;            // nodes (after the contraction of negligible edges), tree levels, residences
+    int wn;                     // max(nn, n): entries per column in the work pools
+    int col0;                   // first column of the zone in the launch (columns are zone-major, hour-minor)
+    int64_t node_off;           // offset of the zone in the static node pools
+    int64_t home_off;           // offset of its node-sorted home list
+    int64_t lvl_off;            // offset of its nlev + 1 level offsets
+    int64_t ws_off;             // offset (entries) of its T columns in the work pools
+    double scale;               // scale of the Hessian shift
+};
+struct NewtonParams {
+    const NewtonZone* zones;
+    int n_zones;
+    const int* lvl;             // level offsets, breadth-first node numbering
+    const int* parent;          // [nodes] parent (breadth-first index), -1: child of the substation
+    const int2* child;          // [nodes] {first child, number of children}
+    const int2* homes;          // [nodes] {first, number} of the node's residences in the node-sorted home list
+    const double* rho;          // [nodes] 2 r of the edge above the node
+    const int* hlist;           // [homes] home index inside the zone of every node-sorted position
+    double* ws;                 // work pools: kNewtonWsDoubles double arrays of ws_stride entries ...
+    double4* ws4;               // ... 4 double4 arrays ...
+    double2* ws2;               // ... 3 double2 arrays ...
+    int* wsi;                   // ... 2 int arrays
+    int64_t ws_stride;
+    const FeederDev* feeders;
+    const double* z_t;          // [T][Hp]
+    double* lam_t;              // [T][Hp]
+    double* g_t;                // [T][Hp]
+    int* status;                // [ncols]
+    int* inner_ok;
+    int* wcount;
+    int* noconv;                // raised by a column that does not reach the tolerance
+    unsigned long long* newton_its;
+    unsigned long long* cols;
+    unsigned long long* flops;
+    int* max_ws;
+    int T;
+    int64_t Hp;
+    double u, tol;
+};
+struct NewtonZoneHost {
+    std::vector<int> lvl, parent, child0, nchild, home0, nhome, hlist;
+    std::vector<double> rho;
+    double scale = 1.0;
+};
+void newton_build_zone(int n_nodes, const int* parent, const double* r, int n_res, const int* res_node, NewtonZoneHost& Z);
+cudaError_t launch_tree_newton(const NewtonParams& P, int n_cols, cudaStream_t stream);
+constexpr int kNewtonWsDoubles = 14, kNewtonWs4 = 4, kNewtonWs2 = 3, kNewtonWsInts = 2;
 
 // ---- contract_f64.cu
 int contract_tile_rows(int T);

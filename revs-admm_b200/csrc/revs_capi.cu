@@ -54,6 +54,7 @@ constexpr double kCountTol = 1e-9;
 constexpr double kQpTol = 1e-11;     // KKT / feasibility tolerance of the utility QP
 constexpr int kQpInnerMax = 60;      // Newton steps per launch
 constexpr int kQpRoundMax = 400;     // working-set rounds per utility solve
+constexpr int kDenseMaxN = 2048;     // zones above this size get no dense sensitivity block at all: tree input, tree-Newton path
 
 struct Counters {
     int n_running;   // n_running and n_cls are reset together before every working-set round
@@ -153,6 +154,21 @@ struct revs_solver {
     unsigned long long comm_run = 0;           // run sequence, advanced by every revs_admm_begin on every rank alike
     unsigned long long* d_run_seq = nullptr;
     int* d_comm_timeout = nullptr;
+    // large radial zones (tree_newton.cu): one CTA per column, products and active-set solves on the tree, no dense block
+    int newton_min_n = 512;                    // zones given as TREES with more residences than this take that path (option "newton_min_n")
+    std::vector<int64_t> roff_alloc;           // per feeder: its block in the R pool, -1 for zones above kDenseMaxN (tree input only)
+    std::vector<char> is_newton;               // per feeder
+    std::vector<NewtonZoneHost> nt_host;       // per feeder: breadth-first arrays (filled by revs_set_feeder_tree(s))
+    std::vector<NewtonZone> nt_zones;
+    NewtonZone* d_nt_zones = nullptr;
+    int *d_nt_lvl = nullptr, *d_nt_parent = nullptr, *d_nt_home = nullptr, *d_nt_wsi = nullptr;
+    int2 *d_nt_child = nullptr, *d_nt_homes = nullptr;
+    double *d_nt_rho = nullptr, *d_nt_ws = nullptr;
+    double4* d_nt_ws4 = nullptr;
+    double2* d_nt_ws2 = nullptr;
+    int64_t nt_ws_stride = 0;
+    int n_newton_cols = 0;
+    size_t nt_sig = 0;
     bool use_warp_kernel = true;               // class 0: one warp per small column (utility_qp_warp.cu)
     bool overlap_home = true;                  // home solve on its own (low priority) stream beside the utility kernels
     bool screen = true;                        // BF16 screening + exact recheck instead of the FP64 contraction in the loop
@@ -479,6 +495,200 @@ int rebuild_tree_lists(revs_solver* s) {
     return REVS_OK;
 }
 
+// Zone-size groups, contraction / screening tile tables and tensor maps over the zones that have a dense block
+// (everything but the tree-Newton zones).  Called by revs_create and again when option "newton_min_n" moves zones.
+int build_tables(revs_solver* s) {
+    const int n_feeders = s->nf, T = s->T;
+    const int64_t hp = s->Hp;
+    s->zg = ZoneGroups();
+    for (int f = 0; f < n_feeders; ++f) {
+        const int n = s->feeders[f].n;
+        if (s->is_newton[f]) continue;
+        s->zg.max_n = std::max(s->zg.max_n, n);
+        if (n > qp_warp_max_n()) continue;
+        s->zg.warp_n = std::max(s->zg.warp_n, n);
+        if (n <= 128) ++s->zg.n_small;
+        else if (n <= 256) { ++s->zg.n_mid; s->zg.mid_max = std::max(s->zg.mid_max, n); }
+        else ++s->zg.n_big;
+    }
+    if (s->zg.max_n > 16384) s->screen = false;    // the error bound of the BF16 screening pass (kScreenUp) holds up to 16384 terms
+    void* old[] = {s->d_sprob, s->d_stiles, s->d_maps_a, s->d_bcol0, s->d_cprob, s->d_ctiles};
+    for (void* q : old) if (q) cudaFree(q);
+    s->d_sprob = nullptr; s->d_stiles = nullptr; s->d_maps_a = nullptr; s->d_bcol0 = nullptr; s->d_cprob = nullptr; s->d_ctiles = nullptr;
+    s->tc5_ready = false;
+    if (s->loop_exec) { cudaGraphExecDestroy(s->loop_exec); s->loop_exec = nullptr; }
+
+    // contraction table: V_t = R_f * G_t for every feeder, BM-row tiles
+    std::vector<ContractProblem> probs(n_feeders);
+    std::vector<ContractTile> tiles;
+    const int bm = contract_tile_rows(T);
+    for (int f = 0; f < n_feeders; ++f) {
+        const FeederDev& fd = s->feeders[f];
+        if (fd.roff < 0) { probs[f] = ContractProblem{}; continue; }
+        probs[f] = ContractProblem{s->d_Rpool + fd.roff, fd.np, fd.np, fd.np, s->d_gt + fd.off, hp,
+                                   s->d_vt + fd.off, hp, nullptr, s->d_status + (size_t)f * T};
+        for (int r0 = 0; r0 < fd.np; r0 += bm) tiles.push_back(ContractTile{f, r0});
+    }
+    {   // screening table: same products in BF16 -> FP32
+        std::vector<ScreenProblem> sp(n_feeders);
+        std::vector<ContractTile> st;
+        const int sbm = screen_tile_rows();
+        for (int f = 0; f < n_feeders; ++f) {
+            const FeederDev& fd = s->feeders[f];
+            if (fd.roff < 0) { sp[f] = ScreenProblem{}; continue; }
+            sp[f] = ScreenProblem{(const char*)s->d_Rbf + 2 * fd.roff, fd.np, fd.np, fd.np,
+                                  (const char*)s->d_gbf + 2 * fd.off, hp, s->d_v32 + fd.off, hp,
+                                  s->d_status + (size_t)f * T, s->d_cand + (size_t)f * T};
+            for (int r0 = 0; r0 < fd.np; r0 += sbm) st.push_back(ContractTile{f, r0});
+        }
+        s->n_stiles = (int)st.size();
+        CU(dalloc(&s->d_sprob, sp.size()));
+        CU(cudaMemcpy(s->d_sprob, sp.data(), sp.size() * sizeof(ScreenProblem), cudaMemcpyHostToDevice));
+        CU(dalloc(&s->d_stiles, st.size()));
+        CU(cudaMemcpy(s->d_stiles, st.data(), st.size() * sizeof(ContractTile), cudaMemcpyHostToDevice));
+        // tensor maps of the tcgen05 implementation (same 128-row tiling)
+        if (T <= (int)screen_tc5_box_rows_b() && screen_tc5_tile_rows() == sbm) {
+            const size_t mb = screen_tc5_map_bytes();
+            std::vector<unsigned char> maps((size_t)(n_feeders + 1) * mb);
+            std::vector<int> bcol(n_feeders);
+            bool ok = true;
+            for (int f = 0; f < n_feeders && ok; ++f) {
+                const FeederDev& fd = s->feeders[f];
+                bcol[f] = (int)fd.off;
+                if (fd.roff < 0) continue;
+                ok = screen_tc5_encode(maps.data() + (size_t)f * mb, (const char*)s->d_Rbf + 2 * fd.roff, fd.np, fd.np, fd.np,
+                                       screen_tc5_box_rows_a()) == cudaSuccess;
+            }
+            ok = ok && screen_tc5_encode(maps.data() + (size_t)n_feeders * mb, s->d_gbf, T, hp, hp, screen_tc5_box_rows_b()) == cudaSuccess;
+            if (ok) {
+                CU(cudaMalloc(&s->d_maps_a, maps.size()));
+                CU(cudaMemcpy(s->d_maps_a, maps.data(), maps.size(), cudaMemcpyHostToDevice));
+                s->d_map_b = nullptr;   // last entry of the same allocation
+                CU(dalloc(&s->d_bcol0, (size_t)n_feeders));
+                CU(cudaMemcpy(s->d_bcol0, bcol.data(), sizeof(int) * n_feeders, cudaMemcpyHostToDevice));
+                s->tc5_ready = true;
+                s->screen_impl = 1;       // sm_100a-native kernel by default
+                if (getenv("REVS_SCREEN_TC5")) s->screen_impl = atoi(getenv("REVS_SCREEN_TC5"));
+            }
+        }
+    }
+    s->n_ctiles = (int)tiles.size();
+    CU(dalloc(&s->d_cprob, probs.size()));
+    CU(cudaMemcpy(s->d_cprob, probs.data(), probs.size() * sizeof(ContractProblem), cudaMemcpyHostToDevice));
+    CU(dalloc(&s->d_ctiles, tiles.size()));
+    CU(cudaMemcpy(s->d_ctiles, tiles.data(), tiles.size() * sizeof(ContractTile), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s->d_feeders, s->feeders.data(), sizeof(FeederDev) * n_feeders, cudaMemcpyHostToDevice));
+    return REVS_OK;
+}
+
+// moves a zone between the dense path and the tree-Newton path (the caller rebuilds the tables)
+int set_newton(revs_solver* s, int f, bool on) {
+    if (!on && s->roff_alloc[f] < 0) return fail(REVS_ERR_ARG, "zone %d has no dense block", f);
+    s->is_newton[f] = on ? 1 : 0;
+    s->feeders[f].roff = on ? (int64_t)-1 : s->roff_alloc[f];
+    s->rn2_valid = false;
+    return REVS_OK;
+}
+
+// Static pools and work arrays of the tree-Newton zones whose trees have been given; column list = their hours.
+int rebuild_newton(revs_solver* s) {
+    std::vector<int> lvl, parent, hlist;
+    std::vector<int2> child, homes;
+    std::vector<double> rho;
+    s->nt_zones.clear();
+    int col0 = 0;
+    int64_t ws = 0;
+    for (int f = 0; f < s->nf; ++f) {
+        if (!s->is_newton[f] || s->nt_host[f].parent.empty()) continue;
+        const NewtonZoneHost& Z = s->nt_host[f];
+        NewtonZone z{};
+        z.feeder = f;
+        z.nn = (int)Z.parent.size();
+        z.nlev = (int)Z.lvl.size() - 1;
+        z.n = (int)Z.hlist.size();
+        z.wn = std::max(z.nn, z.n);
+        z.col0 = col0;
+        z.node_off = (int64_t)parent.size();
+        z.home_off = (int64_t)hlist.size();
+        z.lvl_off = (int64_t)lvl.size();
+        z.ws_off = ws;
+        z.scale = Z.scale;
+        lvl.insert(lvl.end(), Z.lvl.begin(), Z.lvl.end());
+        parent.insert(parent.end(), Z.parent.begin(), Z.parent.end());
+        hlist.insert(hlist.end(), Z.hlist.begin(), Z.hlist.end());
+        rho.insert(rho.end(), Z.rho.begin(), Z.rho.end());
+        for (int i = 0; i < z.nn; ++i) { child.push_back(make_int2(Z.child0[i], Z.nchild[i])); homes.push_back(make_int2(Z.home0[i], Z.nhome[i])); }
+        col0 += s->T;
+        ws += (int64_t)z.wn * s->T;
+        s->nt_zones.push_back(z);
+    }
+    {   // the same zones as last time (a caller re-uploading its feeders every schedule): nothing to do
+        size_t sig = 1469598103934665603ull;
+        auto mix = [&](const void* q, size_t bytes) {
+            const unsigned char* b = (const unsigned char*)q;
+            for (size_t i = 0; i < bytes; ++i) sig = (sig ^ b[i]) * 1099511628211ull;
+        };
+        for (const NewtonZone& z : s->nt_zones) mix(&z.feeder, sizeof(int));
+        mix(lvl.data(), lvl.size() * sizeof(int));
+        mix(parent.data(), parent.size() * sizeof(int));
+        mix(hlist.data(), hlist.size() * sizeof(int));
+        mix(homes.data(), homes.size() * sizeof(int2));
+        mix(rho.data(), rho.size() * sizeof(double));
+        if (sig == s->nt_sig && col0 == s->n_newton_cols && (col0 == 0 || s->d_nt_ws)) return REVS_OK;
+        s->nt_sig = sig;
+    }
+    void* old[] = {s->d_nt_zones, s->d_nt_lvl, s->d_nt_parent, s->d_nt_home, s->d_nt_wsi, s->d_nt_child, s->d_nt_homes, s->d_nt_rho, s->d_nt_ws, s->d_nt_ws4, s->d_nt_ws2};
+    for (void* q : old) if (q) cudaFree(q);
+    s->d_nt_zones = nullptr; s->d_nt_lvl = nullptr; s->d_nt_parent = nullptr; s->d_nt_home = nullptr; s->d_nt_wsi = nullptr;
+    s->d_nt_child = nullptr; s->d_nt_homes = nullptr; s->d_nt_rho = nullptr; s->d_nt_ws = nullptr; s->d_nt_ws4 = nullptr; s->d_nt_ws2 = nullptr;
+    s->n_newton_cols = col0;
+    s->nt_ws_stride = ws;
+    if (s->loop_exec) { cudaGraphExecDestroy(s->loop_exec); s->loop_exec = nullptr; }   // the captured loop bakes the pointers in
+    if (col0 == 0) return REVS_OK;
+    CU(dalloc(&s->d_nt_zones, s->nt_zones.size()));
+    CU(cudaMemcpy(s->d_nt_zones, s->nt_zones.data(), sizeof(NewtonZone) * s->nt_zones.size(), cudaMemcpyHostToDevice));
+    CU(dalloc(&s->d_nt_lvl, lvl.size()));
+    CU(cudaMemcpy(s->d_nt_lvl, lvl.data(), sizeof(int) * lvl.size(), cudaMemcpyHostToDevice));
+    CU(dalloc(&s->d_nt_parent, parent.size()));
+    CU(cudaMemcpy(s->d_nt_parent, parent.data(), sizeof(int) * parent.size(), cudaMemcpyHostToDevice));
+    CU(dalloc(&s->d_nt_home, hlist.size()));
+    CU(cudaMemcpy(s->d_nt_home, hlist.data(), sizeof(int) * hlist.size(), cudaMemcpyHostToDevice));
+    CU(dalloc(&s->d_nt_homes, homes.size()));
+    CU(cudaMemcpy(s->d_nt_homes, homes.data(), sizeof(int2) * homes.size(), cudaMemcpyHostToDevice));
+    CU(dalloc(&s->d_nt_child, child.size()));
+    CU(cudaMemcpy(s->d_nt_child, child.data(), sizeof(int2) * child.size(), cudaMemcpyHostToDevice));
+    CU(dalloc(&s->d_nt_rho, rho.size()));
+    CU(cudaMemcpy(s->d_nt_rho, rho.data(), sizeof(double) * rho.size(), cudaMemcpyHostToDevice));
+    CU(dalloc(&s->d_nt_ws, (size_t)ws * kNewtonWsDoubles));
+    CU(dalloc(&s->d_nt_ws4, (size_t)ws * kNewtonWs4));
+    CU(dalloc(&s->d_nt_ws2, (size_t)ws * kNewtonWs2));
+    CU(dalloc(&s->d_nt_wsi, (size_t)ws * kNewtonWsInts));
+    return REVS_OK;
+}
+
+bool newton_active(const revs_solver* s) { return s->n_newton_cols > 0; }
+int dense_cols(const revs_solver* s) { return s->n_dense_cols - s->n_newton_cols; }   // columns only the dense kernels can solve
+
+int launch_newton_stage(revs_solver* s, bool timed) {
+    if (!newton_active(s)) return REVS_OK;
+    NewtonParams N{};
+    N.zones = s->d_nt_zones; N.n_zones = (int)s->nt_zones.size();
+    N.lvl = s->d_nt_lvl; N.parent = s->d_nt_parent; N.child = s->d_nt_child; N.homes = s->d_nt_homes; N.rho = s->d_nt_rho; N.hlist = s->d_nt_home;
+    N.ws = s->d_nt_ws; N.ws4 = s->d_nt_ws4; N.ws2 = s->d_nt_ws2; N.wsi = s->d_nt_wsi; N.ws_stride = s->nt_ws_stride;
+    N.feeders = s->d_feeders; N.z_t = s->d_zt; N.lam_t = s->d_lamt; N.g_t = s->d_gt;
+    N.status = s->d_status; N.inner_ok = s->d_innerok; N.wcount = s->d_wcount;
+    N.noconv = &s->d_cnt->noconv; N.newton_its = &s->d_cnt->newton_its; N.cols = &s->d_cnt->qp_cols; N.flops = &s->d_cnt->qp_flops;
+    N.max_ws = &s->d_cnt->max_ws;
+    N.T = s->T; N.Hp = s->Hp;
+    N.u = s->vhigh * s->vhigh - s->vset * s->vset;
+    N.tol = kQpTol;
+    TimedSpan* sp = timed ? span_begin(s, 9, s->sU) : nullptr;
+    CU(launch_tree_newton(N, s->n_newton_cols, s->sU));
+    if (sp) span_end(sp, s->sU);
+    s->stats.kernel_launches++;
+    return REVS_OK;
+}
+
 TreeParams tree_params(revs_solver* s) {
     TreeParams TP{};
     TP.zoff = s->d_t_zoff;
@@ -596,7 +806,9 @@ struct GateCapture {   // captured loop: CTA classes 2 and 3 sit behind IF nodes
 int enqueue_round(revs_solver* s, QpParams& Q, int mode, const bool* use, const int* grid, bool timed, GateCapture* gc = nullptr) {
     const double thr = (1.0 - kScreenMargin) * Q.u;
     TimedSpan* sp = timed ? span_begin(s, mode == 0 ? 5 : 0, s->sU) : nullptr;   // round 0: every column is running
-    if (s->screen) {
+    if (s->n_stiles == 0) {
+        // no zone with a dense block: nothing to contract
+    } else if (s->screen) {
         if (s->screen_impl == 1 && s->tc5_ready)
             CU(launch_screen_tc5(s->d_sprob, s->d_stiles, s->n_stiles, s->d_maps_a,
                                  (const char*)s->d_maps_a + (size_t)s->nf * screen_tc5_map_bytes(), s->d_bcol0, s->T, thr, s->sU));
@@ -706,8 +918,8 @@ int check_device_flags(revs_solver* s) {
                     "utility QP: %d (feeder,hour) columns need more than %d simultaneously active "
                     "voltage rows", s->h_cnt->n_failed, kWMax);
     if (s->h_cnt->noconv)
-        return fail(REVS_ERR_NOCONV, "utility QP: %d columns still running after %d working-set rounds",
-                    s->h_cnt->n_running, kQpRoundMax);
+        return fail(REVS_ERR_NOCONV, "utility QP: %d columns still running after %d working-set rounds (or a tree-Newton column "
+                    "that did not reach the tolerance)", s->h_cnt->n_running, kQpRoundMax);
     return REVS_OK;
 }
 
@@ -721,6 +933,14 @@ int utility_solve(revs_solver* s, bool in_loop = false) {
     QpParams Q = qp_params(s);
     if ((rc = launch_init(s, Q, in_loop, true))) return rc;
     s->stats.kernel_launches++;
+    if (newton_active(s)) {
+        if ((rc = launch_newton_stage(s, true))) return rc;
+        if (dense_cols(s) == 0 && !tree_active(s)) {
+            CU(cudaMemcpyAsync(s->h_cnt, s->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, s->sU));
+            CU(cudaStreamSynchronize(s->sU));
+            return check_device_flags(s);
+        }
+    }
     if (tree_active(s)) {
         if ((rc = launch_tree_stage(s, Q, true))) return rc;
         CU(cudaMemcpyAsync(s->h_cnt, s->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, s->sU));
@@ -732,7 +952,7 @@ int utility_solve(revs_solver* s, bool in_loop = false) {
         s->tree_left_total += s->h_cnt->tree_left;
         if (s->debug)
             fprintf(stderr, "[revs] admm %d tree stage: %d columns left to the dense kernels, max_ws %d\n", s->k, s->h_cnt->tree_left, s->h_cnt->max_ws);
-        if (s->h_cnt->tree_left == 0 && s->n_dense_cols == 0) return REVS_OK;
+        if (s->h_cnt->tree_left == 0 && dense_cols(s) == 0) return REVS_OK;
     }
     bool use[kQpClasses];
     // first round: qp_init_kernel assigns classes on the device by the size of the stored working
@@ -829,7 +1049,8 @@ void free_all(revs_solver* s) {
                     s->d_gt, s->d_vt, s->d_wcount, s->d_widx, s->d_status, s->d_innerok, s->d_cls, s->d_order, s->d_order4, s->d_order_count, s->d_cnt, s->d_diff,
                     s->d_cprob, s->d_ctiles, s->d_respart, s->d_t_perm, s->d_t_iperm, s->d_t_nodeA, s->d_t_nodeB, s->d_t_cnt,
                     s->d_t_c, s->d_t_d, s->d_t_e, s->d_t_wA, s->d_t_wB, s->d_t_zoff, s->d_tree_cols[0], s->d_tree_cols[1], s->d_tree_cols[2],
-                    s->d_tree_cols[3]};
+                    s->d_tree_cols[3], s->d_nt_zones, s->d_nt_lvl, s->d_nt_parent, s->d_nt_home, s->d_nt_wsi, s->d_nt_child, s->d_nt_homes, s->d_nt_rho,
+                    s->d_nt_ws, s->d_nt_ws4, s->d_nt_ws2};
     for (int r = 0; r < kMaxPeers; ++r)
         if (s->peer_box[r] && s->peer_box[r] != s->d_mailbox) cudaIpcCloseMemHandle(s->peer_box[r]);
     if (s->d_mailbox) cudaFree(s->d_mailbox);
@@ -897,14 +1118,21 @@ int revs_create(revs_solver** out, int device, int n_feeders, const int64_t* fee
     s->sens_set.assign(n_feeders, 0);
     s->tree_ok.assign(n_feeders, 0);
     s->trees.resize(n_feeders);
+    s->is_newton.assign(n_feeders, 0);
+    s->nt_host.resize(n_feeders);
+    s->roff_alloc.assign(n_feeders, -1);
+    if (const char* e = getenv("REVS_NEWTON_MIN_N")) s->newton_min_n = atoi(e);
     int64_t hp = 0, rp = 0;
     for (int f = 0; f < n_feeders; ++f) {
         int64_t n = feeder_off[f + 1] - feeder_off[f];
         int64_t np = (n + kPad - 1) / kPad * kPad;
         if (np == 0) np = kPad;
-        s->feeders[f] = FeederDev{(int)n, (int)np, hp, rp};
+        // zones above kDenseMaxN residences run on the tree only (tree_newton.cu): no n^2 block for them
+        s->is_newton[f] = n > kDenseMaxN;
+        s->roff_alloc[f] = s->is_newton[f] ? (int64_t)-1 : rp;
+        s->feeders[f] = FeederDev{(int)n, (int)np, hp, s->roff_alloc[f]};
         hp += np;
-        rp += np * np;
+        if (!s->is_newton[f]) rp += np * np;
     }
     s->Hp = hp;
     const size_t HT = (size_t)hp * T;
@@ -956,8 +1184,6 @@ int revs_create(revs_solver** out, int device, int n_feeders, const int64_t* fee
     TRY(cudaMemset(s->d_gbf, 0, HT * 2));
     TRY(dalloc(&s->d_v32, HT));
     if (getenv("REVS_EXACT_GEMM")) s->screen = false;          // (create time only)
-    for (int f = 0; f < n_feeders; ++f)          // the error bound of the BF16 screening pass (kScreenUp) holds up to 16384 terms
-        if (s->feeders[f].n > 16384) s->screen = false;
     TRY(dalloc(&s->d_load, HT));
     TRY(dalloc(&s->d_pest, HT));
     TRY(dalloc(&s->d_psch[0], HT));
@@ -1007,74 +1233,13 @@ int revs_create(revs_solver** out, int device, int n_feeders, const int64_t* fee
         if ((e = getenv("REVS_DEBUG_TRACE_FILE"))) s->trace_file = e;
         if (s->debug) s->use_graph = false;      // the per-round lines need the host-driven loop
     }
-    for (int f = 0; f < n_feeders; ++f) {
-        const int n = s->feeders[f].n;
-        s->zg.max_n = std::max(s->zg.max_n, n);
-        if (n > qp_warp_max_n()) continue;
-        s->zg.warp_n = std::max(s->zg.warp_n, n);
-        if (n <= 128) ++s->zg.n_small;
-        else if (n <= 256) { ++s->zg.n_mid; s->zg.mid_max = std::max(s->zg.mid_max, n); }
-        else ++s->zg.n_big;
-    }
     TRY(cudaHostAlloc((void**)&s->h_cnt, sizeof(Counters), cudaHostAllocDefault));
     memset(s->h_cnt, 0, sizeof(Counters));
 
-    // contraction table: V_t = R_f * G_t for every feeder, BM-row tiles
-    std::vector<ContractProblem> probs(n_feeders);
-    std::vector<ContractTile> tiles;
-    const int bm = contract_tile_rows(T);
-    for (int f = 0; f < n_feeders; ++f) {
-        const FeederDev& fd = s->feeders[f];
-        probs[f] = ContractProblem{s->d_Rpool + fd.roff, fd.np, fd.np, fd.np, s->d_gt + fd.off, hp,
-                                   s->d_vt + fd.off, hp, nullptr, s->d_status + (size_t)f * T};
-        for (int r0 = 0; r0 < fd.np; r0 += bm) tiles.push_back(ContractTile{f, r0});
+    {
+        int rc2 = build_tables(s);
+        if (rc2) { free_all(s); delete s; return rc2; }
     }
-    {   // screening table: same products in BF16 -> FP32
-        std::vector<ScreenProblem> sp(n_feeders);
-        std::vector<ContractTile> st;
-        const int sbm = screen_tile_rows();
-        for (int f = 0; f < n_feeders; ++f) {
-            const FeederDev& fd = s->feeders[f];
-            sp[f] = ScreenProblem{(const char*)s->d_Rbf + 2 * fd.roff, fd.np, fd.np, fd.np,
-                                  (const char*)s->d_gbf + 2 * fd.off, hp, s->d_v32 + fd.off, hp,
-                                  s->d_status + (size_t)f * T, s->d_cand + (size_t)f * T};
-            for (int r0 = 0; r0 < fd.np; r0 += sbm) st.push_back(ContractTile{f, r0});
-        }
-        s->n_stiles = (int)st.size();
-        TRY(dalloc(&s->d_sprob, sp.size()));
-        TRY(cudaMemcpy(s->d_sprob, sp.data(), sp.size() * sizeof(ScreenProblem), cudaMemcpyHostToDevice));
-        TRY(dalloc(&s->d_stiles, st.size()));
-        TRY(cudaMemcpy(s->d_stiles, st.data(), st.size() * sizeof(ContractTile), cudaMemcpyHostToDevice));
-        // tensor maps of the tcgen05 implementation (same 128-row tiling)
-        if (T <= (int)screen_tc5_box_rows_b() && screen_tc5_tile_rows() == sbm) {
-            const size_t mb = screen_tc5_map_bytes();
-            std::vector<unsigned char> maps((size_t)(n_feeders + 1) * mb);
-            std::vector<int> bcol(n_feeders);
-            bool ok = true;
-            for (int f = 0; f < n_feeders && ok; ++f) {
-                const FeederDev& fd = s->feeders[f];
-                ok = screen_tc5_encode(maps.data() + (size_t)f * mb, (const char*)s->d_Rbf + 2 * fd.roff, fd.np, fd.np, fd.np,
-                                       screen_tc5_box_rows_a()) == cudaSuccess;
-                bcol[f] = (int)fd.off;
-            }
-            ok = ok && screen_tc5_encode(maps.data() + (size_t)n_feeders * mb, s->d_gbf, T, hp, hp, screen_tc5_box_rows_b()) == cudaSuccess;
-            if (ok) {
-                TRY(cudaMalloc(&s->d_maps_a, maps.size()));
-                TRY(cudaMemcpy(s->d_maps_a, maps.data(), maps.size(), cudaMemcpyHostToDevice));
-                s->d_map_b = nullptr;   // last entry of the same allocation
-                TRY(dalloc(&s->d_bcol0, (size_t)n_feeders));
-                TRY(cudaMemcpy(s->d_bcol0, bcol.data(), sizeof(int) * n_feeders, cudaMemcpyHostToDevice));
-                s->tc5_ready = true;
-                s->screen_impl = 1;       // sm_100a-native kernel by default
-                if (getenv("REVS_SCREEN_TC5")) s->screen_impl = atoi(getenv("REVS_SCREEN_TC5"));
-            }
-        }
-    }
-    s->n_ctiles = (int)tiles.size();
-    TRY(dalloc(&s->d_cprob, probs.size()));
-    TRY(cudaMemcpy(s->d_cprob, probs.data(), probs.size() * sizeof(ContractProblem), cudaMemcpyHostToDevice));
-    TRY(dalloc(&s->d_ctiles, tiles.size()));
-    TRY(cudaMemcpy(s->d_ctiles, tiles.data(), tiles.size() * sizeof(ContractTile), cudaMemcpyHostToDevice));
 #undef TRY
     *out = s;
     return REVS_OK;
@@ -1091,6 +1256,15 @@ int revs_set_sensitivity(revs_solver* s, int feeder, const double* R_res) {
     if (!s || !R_res || feeder < 0 || feeder >= s->nf) return fail(REVS_ERR_ARG, "bad arguments");
     CU(cudaSetDevice(s->device));
     const FeederDev& fd = s->feeders[feeder];
+    if (s->roff_alloc[feeder] < 0)
+        return fail(REVS_ERR_ARG, "feeder %d has %d residences (> %d): it runs on its tree, give it with "
+                    "revs_set_feeder_tree(s) instead of a dense block", feeder, fd.n, kDenseMaxN);
+    if (s->is_newton[feeder]) {          // a dense block replaces the tree: back to the dense kernels
+        int rc = set_newton(s, feeder, false);
+        if (rc) return rc;
+        s->nt_host[feeder] = NewtonZoneHost();
+        if ((rc = build_tables(s)) || (rc = rebuild_newton(s))) return rc;
+    }
     for (int64_t i = 0; i < (int64_t)fd.n * fd.n; ++i)
         if (!(R_res[i] >= 0.0)) return fail(REVS_ERR_ARG, "sensitivity block of feeder %d has a negative or NaN entry", feeder);
     if (fd.n)
@@ -1130,6 +1304,20 @@ int revs_set_feeder_tree(revs_solver* s, int feeder, int n_nodes, const int32_t*
     CU(cudaMemcpy(t.d_parent, parent, sizeof(int) * n_nodes, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(t.d_cumr, cumr.data(), sizeof(double) * n_nodes, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(t.d_res_node, res_node, sizeof(int) * fd.n, cudaMemcpyHostToDevice));
+    {
+        const bool want = fd.n > s->newton_min_n || s->roff_alloc[feeder] < 0;
+        if (want != (bool)s->is_newton[feeder]) {
+            int rc = set_newton(s, feeder, want);
+            if (rc || (rc = build_tables(s))) return rc;
+        }
+    }
+    if (s->is_newton[feeder]) {
+        newton_build_zone(n_nodes, parent, r, fd.n, res_node, s->nt_host[feeder]);
+        s->sens_set[feeder] = 1;
+        s->tree_ok[feeder] = 0;
+        int rc = rebuild_newton(s);
+        return rc ? rc : rebuild_tree_lists(s);
+    }
     CU(launch_sens_voltage(t.d_parent, t.d_cumr, nullptr, t.d_res_node, fd.n, fd.n, s->d_Rpool + fd.roff, fd.np, s->sU));
     CU(cudaStreamSynchronize(s->sU));
     s->sens_set[feeder] = 1;
@@ -1180,6 +1368,27 @@ int revs_set_feeder_trees(revs_solver* s, const int64_t* node_off, const int32_t
     CU(cudaMemcpyAsync(s->d_pool_cumr, cumr.data(), sizeof(double) * total, cudaMemcpyHostToDevice, s->sU));
     CU(cudaMemcpyAsync(s->d_pool_res, res_p.data(), sizeof(int) * s->Hp, cudaMemcpyHostToDevice, s->sU));
     CU(cudaMemcpyAsync(s->d_pool_off, node_off, sizeof(int64_t) * (s->nf + 1), cudaMemcpyHostToDevice, s->sU));
+    {
+        bool any = false, moved = false;
+        for (int f = 0; f < s->nf; ++f) {
+            const bool want = s->feeders[f].n > s->newton_min_n || s->roff_alloc[f] < 0;
+            if (want != (bool)s->is_newton[f]) { set_newton(s, f, want); moved = true; }
+        }
+        if (moved) {
+            int rc = build_tables(s);
+            if (rc) return rc;
+        }
+        for (int f = 0; f < s->nf; ++f) {
+            if (!s->is_newton[f]) continue;
+            const int64_t o = node_off[f];
+            newton_build_zone((int)(node_off[f + 1] - o), parent + o, r + o, s->feeders[f].n, res_node + s->off[f], s->nt_host[f]);
+            any = true;
+        }
+        if (any || s->n_newton_cols) {
+            int rc = rebuild_newton(s);
+            if (rc) return rc;
+        }
+    }
     int max_n = 0;
     for (int f = 0; f < s->nf; ++f) {
         Tree& t = s->trees[f];
@@ -1190,8 +1399,9 @@ int revs_set_feeder_trees(revs_solver* s, const int64_t* node_off, const int32_t
         t.d_res_node = s->d_pool_res + s->feeders[f].off;
         t.pooled = true;
         s->sens_set[f] = 1;
-        if (s->feeders[f].n > max_n) max_n = s->feeders[f].n;
+        if (!s->is_newton[f] && s->feeders[f].n > max_n) max_n = s->feeders[f].n;
     }
+    if (max_n > 0)
     CU(launch_sens_voltage_batched(s->d_feeders, s->nf, max_n, s->d_pool_off, s->d_pool_parent, s->d_pool_cumr,
                                    s->d_pool_res, s->d_Rpool, s->sU));
     // static arrays of the tree kernels, all zones into host pools, one upload per array
@@ -1208,7 +1418,7 @@ int revs_set_feeder_trees(revs_solver* s, const int64_t* node_off, const int32_t
             const FeederDev& fd = s->feeders[f];
             s->tree_ok[f] = 0;
             const int g = tree_qp_group(fd.n);
-            if (fd.n == 0 || g < 0) continue;
+            if (fd.n == 0 || g < 0 || s->is_newton[f]) continue;
             const int64_t o = node_off[f];
             build_zone_arrays((int)(node_off[f + 1] - o), parent + o, cumr.data() + o, fd.n, res_node + s->off[f], Z);
             pack_zone(Z, fd.n, 4 + 2 * g, K);
@@ -1448,7 +1658,7 @@ int admm_step_impl(revs_solver* s, double sums[3], bool sync_now) {
 // round number) from device counters, so the bodies are captured once.  Nothing returns to the host until the
 // schedule is finished: no round trip per working-set round, no launch latency per kernel.
 int capture_loop(revs_solver* s) {
-    const int flags = (s->screen ? 1 : 0) | (s->screen_impl << 1) | (s->overlap_home ? 4 : 0) | (s->use_warp_kernel ? 8 : 0) | (s->use_fast ? 16 : 0) | (s->comm_world << 8) | (s->comm_rank << 16) | (tree_active(s) ? 32 : 0) | (s->n_dense_cols ? 64 : 0);
+    const int flags = (s->screen ? 1 : 0) | (s->screen_impl << 1) | (s->overlap_home ? 4 : 0) | (s->use_warp_kernel ? 8 : 0) | (s->use_fast ? 16 : 0) | (s->comm_world << 8) | (s->comm_rank << 16) | (tree_active(s) ? 32 : 0) | (dense_cols(s) ? 64 : 0) | (newton_active(s) ? 128 : 0);
     if (s->loop_exec && s->gk_kappa == s->kappa && s->gk_vset == s->vset && s->gk_vhigh == s->vhigh && s->gk_tol == s->tol &&
         s->gk_iter_max == s->iter_max && s->gk_flags == flags)
         return REVS_OK;
@@ -1496,14 +1706,20 @@ int capture_loop(revs_solver* s) {
         Q.use_cond = 1;
         int r = launch_init(s, Q, true, false);
         if (r) return r;
+        if (newton_active(s)) {
+            const revs_stats keep = s->stats;
+            r = launch_newton_stage(s, false);
+            s->stats = keep;
+            if (r) return r;
+        }
         if (tree_active(s)) {
             const revs_stats keep = s->stats;
             r = launch_tree_stage(s, Q, false);
             s->stats = keep;
             if (r) return r;
-            if (s->n_dense_cols == 0)          // zones without tree arrays always need the rounds of the dense kernels
-                CU(launch_tree_gate(&s->d_cnt->tree_left, (unsigned long long)h_round, s->sU));
         }
+        if ((tree_active(s) || newton_active(s)) && dense_cols(s) == 0)     // the rounds of the dense kernels run only for what is left
+            CU(launch_tree_gate(&s->d_cnt->tree_left, (unsigned long long)h_round, s->sU));
         // the working-set while node goes into the graph being captured, after what the stream has enqueued so far
         cudaStreamCaptureStatus st;
         cudaGraph_t g_cap = nullptr;
@@ -1604,7 +1820,8 @@ int revs_solve_admm(revs_solver* s, double kappa, int iter_max, double vset, dou
         int tree_launches = 0;
         if (tree_active(s))
             for (int g = 0; g < 4; ++g) tree_launches += s->n_tree_cols[g] > 0;
-        if (tree_launches && s->n_dense_cols == 0) ++tree_launches;            // + the gate of the working-set loop
+        if (newton_active(s)) ++tree_launches;
+        if (tree_launches && dense_cols(s) == 0) ++tree_launches;              // + the gate of the working-set loop
         s->stats.kernel_launches += (int64_t)s->k * (3 + tree_launches) + (int64_t)s->h_cnt->rounds_total * round_launches(s);
         if (rc) return rc;
     } else {
@@ -2045,6 +2262,14 @@ int revs_set_option(revs_solver* s, const char* name, double value) {
             for (int f = 0; f < s->nf; ++f)
                 if (s->sens_set[f]) return fail(REVS_ERR_ARG, "set option 'tree' before revs_set_feeder_tree(s): the tree arrays are built there");
         s->use_tree = value != 0.0;
+        return REVS_OK;
+    }
+    if (!strcmp(name, "newton_min_n")) {
+        // zones with more residences than this run on their tree (tree_newton.cu: no dense block, any number of binding
+        // rows); the default is 512.  Zones above 2048 residences never get a dense block.  Set it before the feeders are given.
+        for (int f = 0; f < s->nf; ++f)
+            if (s->sens_set[f]) return fail(REVS_ERR_ARG, "set option 'newton_min_n' before the feeders are given");
+        s->newton_min_n = value < 0.0 ? 0 : (value > 2e9 ? 2000000000 : (int)value);
         return REVS_OK;
     }
     if (!strcmp(name, "graph")) { s->use_graph = value != 0.0; return REVS_OK; }   // 0: host-driven loop with per-kernel event spans (profiling)

@@ -682,6 +682,10 @@ __global__ void __launch_bounds__(256) qp_init_kernel(QpParams P, int max_warp_n
     const int f = c / P.T, t = c % P.T;
     const FeederDev fd = P.feeders[f];
     const int n = fd.n, ld = fd.np;
+    if (fd.roff < 0) {                 // zone of the tree-Newton path (tree_newton.cu): not a column of the dense kernels
+        if (lane == 0) { P.cls[c] = 0; P.status[c] = 1; P.inner_ok[c] = 1; if (P.cand) P.cand[c] = 0; }
+        return;
+    }
     const double* R = P.Rpool + fd.roff;
     const size_t col = (size_t)t * P.Hp + fd.off;
     const double* z = P.z_t + col;

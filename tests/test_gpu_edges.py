@@ -20,9 +20,11 @@ def _oracle(trees, hm, cost, kw):
                                capacity=hm["capacity"], initial=hm["initial"], start=hm["start"], end=hm["end"], **kw)
 
 
-def _gpu(lib, sizes, T, trees, hm, cost, kw, screen=1):
+def _gpu(lib, sizes, T, trees, hm, cost, kw, screen=1, newton_min_n=None):
     with lib.Solver(sizes, T) as s:
         s.set_option("screen", screen)
+        if newton_min_n is not None:
+            s.set_option("newton_min_n", newton_min_n)
         s.set_feeder_trees(trees)
         s.set_homes(**hm)
         s.set_tariff(cost)
@@ -139,13 +141,16 @@ def test_argument_errors(gpu_lib):
 
 
 def test_working_set_overflow_is_loud(gpu_lib):
-    """More than 128 simultaneously binding voltage rows in one (feeder,hour) column is outside
-    what this round's QP kernel holds in shared memory: it must fail with REVS_ERR_NOCONV."""
+    """More than 128 simultaneously binding voltage rows in one (feeder,hour) column is outside what the DENSE QP kernels
+    hold in shared memory: forced onto them (newton_min_n above the zone size) the solve fails with REVS_ERR_NOCONV.
+    By default a zone of this size given as a tree runs on the tree-Newton path, which has no such limit
+    (test_gpu_newton.py::test_former_overflow_case_matches_oracle)."""
     from revs_admm_b200.feeder import synthetic_feeder, synthetic_homes, synthetic_tariff
     n, T = 1000, 24      # the oracle finds up to 149 binding rows per hour on this feeder
     t = synthetic_feeder(n, seed=0, laterals=5)
     hm = synthetic_homes(n, T, seed=77)
     with gpu_lib.Solver([n], T) as s:
+        s.set_option("newton_min_n", 4096)
         s.set_feeder_tree(0, t.parent, t.r, t.res_node)
         s.set_homes(**hm)
         s.set_tariff(synthetic_tariff(T))
@@ -162,7 +167,7 @@ def test_zone_size_classes_match_oracle(gpu_lib, sizes, vhigh):
     T = 24
     trees, hm, cost = _problem(sizes, T, seed=sum(sizes), r_secondary=1e-3)
     kw = dict(kappa=5.0, iter_max=5, vset=1.0, vlow=0.95, vhigh=vhigh)
-    out = _gpu(gpu_lib, sizes, T, trees, hm, cost, kw)
+    out = _gpu(gpu_lib, sizes, T, trees, hm, cost, kw, newton_min_n=4096)       # dense kernels for every size (tree-Newton: test_gpu_newton.py)
     ref = _oracle(trees, hm, cost, kw)
     assert out["stats"]["max_working_set"] >= 10         # the limits do bind (tens of rows per column)
     assert np.array_equal(out["P_ev"], ref["P_ev"])
@@ -288,6 +293,7 @@ def test_captured_loop_stops_on_the_device(gpu_lib):
         assert np.array_equal(res[0][1][k], res[1][1][k])
     hm["end"][:] = hm["start"] + 1                   # one-step window: SOC target unreachable
     with gpu_lib.Solver([n], T) as s:
+        s.set_option("newton_min_n", 4096)
         s.set_feeder_tree(0, t.parent, t.r, t.res_node)
         s.set_homes(**hm)
         s.set_tariff(synthetic_tariff(T))
