@@ -158,8 +158,13 @@ def fp64_gemm_peak_tflops():
 # ------------------------------------------------------------------------------ CPU reference arm
 def _cpu_feeder_job(job):
     """One feeder of the workload through the CPU oracle (runs in a worker process, BLAS single-threaded)."""
-    workload, first, no_split = job
-    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    workload, first, no_split, iters, one_thread = job
+    if one_thread:                                   # one feeder per worker process: BLAS single-threaded inside
+        try:
+            from threadpoolctl import threadpool_limits
+            threadpool_limits(limits=1)
+        except Exception:
+            pass
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import revs_oracle as O
     from revs_admm_b200.feeder import population
@@ -169,7 +174,7 @@ def _cpu_feeder_job(job):
     t0 = time.perf_counter()
     O.solve_ADMM_arrays(Rb, load=hm["load"], cost=cost, ev_mask=hm["has_ev"].astype(bool),
                         rating=hm["rating"], capacity=hm["capacity"], initial=hm["initial"],
-                        start=hm["start"], end=hm["end"], **ADMM)
+                        start=hm["start"], end=hm["end"], **dict(ADMM, iter_max=iters))
     return sum(sizes), time.perf_counter() - t0
 
 
@@ -183,7 +188,10 @@ def cpu_port_sample(workload, n_feeders=None, no_split=False, workers=None):
     cores = os.cpu_count() or 1
     workers = workers or cores
     k = min(nf, n_feeders or 4 * workers)
-    jobs = [(workload, f, no_split) for f in range(k)]
+    # one big zone (BASELINE.json config 3): the dense port needs minutes per iteration, so the sample is the first 3 of the
+    # 15 iterations (BLAS on all cores) and the rate is scaled by 3/15
+    iters = ADMM["iter_max"] if n <= 4000 else 3
+    jobs = [(workload, f, no_split, iters, workers > 1 and k > 1) for f in range(k)]
     t0 = time.perf_counter()
     if workers > 1 and k > 1:
         with mp.get_context("fork").Pool(min(workers, k)) as pool:
@@ -192,9 +200,10 @@ def cpu_port_sample(workload, n_feeders=None, no_split=False, workers=None):
         res = [_cpu_feeder_job(j) for j in jobs]
     dt = time.perf_counter() - t0
     homes = sum(r[0] for r in res)
-    return homes * HOURS / dt, dt, (f"first {k} of {nf} feeders x {n} homes x {T} steps x {ADMM['iter_max']} ADMM iterations "
-                                    f"(oracle/revs_oracle.py, numpy), {min(workers, k)} worker processes on {cores} cores; "
-                                    f"sum of per-feeder CPU seconds {sum(r[1] for r in res):.1f}")
+    part = iters / ADMM["iter_max"]
+    return homes * HOURS * part / dt, dt, (f"first {k} of {nf} feeders x {n} homes x {T} steps x {iters} of {ADMM['iter_max']} ADMM iterations "
+                                           f"(oracle/revs_oracle.py, numpy), {min(workers, k)} worker processes on {cores} cores; "
+                                           f"sum of per-feeder CPU seconds {sum(r[1] for r in res):.1f}")
 
 
 def run_reference(args, rank, world):
@@ -227,7 +236,7 @@ def objective_check(trees, hm, cost, P_sch, T, sample_zones=64):
     lpsolver.py:463-502, minimises sum_h tariff . g_h under the SOC and voltage rows).  A rigorous
     sandwich:  cost of the cheapest SOC-feasible schedule of every home WITHOUT voltage limits
     <= centralized optimum <= cost of the distributed schedule wherever that is voltage-feasible.
-    Returns this rank's sums; the voltage check uses dense host matrices of a sample of zones."""
+    Returns this rank's sums; the voltage check runs on the host over a sample of zones."""
     cost = np.asarray(cost)
     load_cost = float((hm["load"] @ cost).sum())
     ev = hm["has_ev"] > 0
@@ -245,8 +254,7 @@ def objective_check(trees, hm, cost, P_sch, T, sample_zones=64):
     for z, tr in enumerate(trees):
         n = tr.n_res
         if z < sample_zones:
-            R = tr.rmat()[np.ix_(tr.res_node, tr.res_node)]
-            worst = max(worst, float((R @ P_sch[off:off + n] - u).max()))
+            worst = max(worst, float((tr.drop(P_sch[off:off + n]) - u).max()))      # R_res @ P_sch on the tree, no dense matrix
         off += n
     return dist_cost, lb, worst
 
@@ -531,7 +539,12 @@ def run_gpu(args, rank, world, local_rank):
              "of": "device time of the host-driven single-pipeline solve (%.2f ms)" % st_iso["total_ms"]}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    big_zone = workload_shape(args.workload)[1] > 4000
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and big_zone and args.cpu_sample_feeders is None:
+        # one 10k-home zone: the dense CPU port needs a 0.8 GB matrix and minutes per ADMM iteration; timed only on request
+        cpu = {"value": None, "unit": "home-hours/s", "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": "not timed by default for this workload (dense 10k x 10k port: minutes per ADMM iteration); pass --cpu-sample-feeders 1"}
+    elif rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, dt, desc = cpu_port_sample(args.workload, args.cpu_sample_feeders, no_split=args.no_split)
         cpu = {"value": v, "unit": "home-hours/s", "cores": os.cpu_count() or 1, "kind": "port", "sample": desc,
                "seconds": dt}

@@ -52,6 +52,21 @@ class FeederTree:
         return R
 
 
+    def drop(self, P):
+        """R_res @ P for a residence schedule P [n_res, T] without forming R (host, O(n T)): subtree sums leaves ->
+        root, then the squared-voltage drop root -> leaves (v_k = v_parent + 2 r_k f_k).  The check of lpsolver.py:192."""
+        P = np.asarray(P, dtype=np.float64).reshape(self.n_res, -1)
+        f = np.zeros((self.n_nodes, P.shape[1]))
+        np.add.at(f, self.res_node, P)
+        for i in range(self.n_nodes - 1, -1, -1):
+            if self.parent[i] >= 0:
+                f[self.parent[i]] += f[i]
+        v = f
+        for i in range(self.n_nodes):
+            v[i] = 2.0 * self.r[i] * f[i] + (v[self.parent[i]] if self.parent[i] >= 0 else 0.0)
+        return v[self.res_node]
+
+
 def tree_from_graph(graph):
     """Root the reference's feeder graph at its substation (label 'S')."""
     roots = [n for n in graph.nodes if graph.nodes[n]["label"] == "S"]
@@ -249,7 +264,8 @@ POPULATIONS = {
     # round-1 population: zones of 43..165 residences, every lateral on the substation, base load over the limit
     "laterals": dict(homes=1000, T=96, gen=lambda n, seed: synthetic_feeder(n, seed=seed, laterals=max(5, n // 100))),
     # one radial feeder: trunk + laterals, a single voltage zone (BASELINE.json config 3)
-    "radial10k": dict(homes=10000, T=96, gen=lambda n, seed: radial_feeder(n, seed=seed)),
+    # (r_scale: the base load peaks at ~0.7 u at the end of the feeder, all chargers together would need 2.4 u)
+    "radial10k": dict(homes=10000, T=96, gen=lambda n, seed: radial_feeder(n, seed=seed, r_scale=0.07)),
 }
 
 

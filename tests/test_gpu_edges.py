@@ -252,6 +252,7 @@ def test_captured_loop_equals_host_driven_loop(gpu_lib, sizes, T, vhigh, tree):
         with gpu_lib.Solver(sizes, T) as s:
             s.set_option("graph", graph)
             s.set_option("tree", tree)
+            s.set_option("newton_min_n", 4096)            # zones above 512 on the dense kernels (tree-Newton: test_gpu_newton.py)
             s.set_feeder_trees(trees)
             s.set_homes(**hm)
             s.set_tariff(cost)
@@ -293,7 +294,6 @@ def test_captured_loop_stops_on_the_device(gpu_lib):
         assert np.array_equal(res[0][1][k], res[1][1][k])
     hm["end"][:] = hm["start"] + 1                   # one-step window: SOC target unreachable
     with gpu_lib.Solver([n], T) as s:
-        s.set_option("newton_min_n", 4096)
         s.set_feeder_tree(0, t.parent, t.r, t.res_node)
         s.set_homes(**hm)
         s.set_tariff(synthetic_tariff(T))

@@ -41,3 +41,35 @@ def test_modes_agree_bitwise_at_full_size(gpu_lib):
     _, pe3, gm3, res3, _ = cp.run(wl, 0, screen=0)
     for a, b in ((pe, pe2), (gm, gm2), (res["P_sch"], res2["P_sch"]), (pe, pe3), (gm, gm3), (res["P_sch"], res3["P_sch"])):
         assert np.array_equal(a, b)
+
+
+def test_radial_10k_single_zone_kkt(gpu_lib):
+    """BASELINE.json config 3: ONE radial feeder of 10 000 residences (a single dense voltage zone), 96 steps, limits
+    that bind on hundreds of rows per hour.  No dense matrix exists for it anywhere (device or host): the operator
+    estimate after a few ADMM iterations is checked through its KKT certificate with R applied on the tree
+    (FeederTree.drop = R_res @ x in O(n), lpsolver.py:192)."""
+    from revs_admm_b200.feeder import population
+    trees, hm, cost, sizes, T = population("radial10k", 1, seed=0)
+    assert sizes == [10000] and T == 96
+    tr = trees[0]
+    kw = dict(kappa=5.0, vset=1.03, vlow=0.95, vhigh=1.05)
+    u = kw["vhigh"] ** 2 - kw["vset"] ** 2
+    with gpu_lib.Solver(sizes, T) as s:
+        s.set_feeder_trees(trees)
+        s.set_homes(**hm)
+        s.set_tariff(cost)
+        done = s.solve_admm(iter_max=4, **kw)
+        out = s.results(done)
+        p_est, gamma = s.estimate()
+        st = s.stats()
+        # one more operator step from the final iterates, with its multipliers
+        g, lam = s.utility_step(p_est, out["P_sch"], gamma, **kw)
+    assert st["max_working_set"] > 128                      # far beyond what the dense kernels hold
+    z = (p_est + out["P_sch"]) / 2.0 - gamma / kw["kappa"]
+    assert g.min() >= 0.0 and lam.min() >= 0.0
+    v = tr.drop(g)
+    assert (v - u).max() <= 1e-9
+    assert np.abs(g - np.maximum(z - tr.drop(lam), 0.0)).max() <= 1e-8
+    assert np.abs(lam * (u - v)).max() <= 1e-7
+    assert (lam > 0).sum(axis=0).max() > 128
+    assert (tr.drop(p_est) - u).max() <= 1e-9               # the estimate of the loop itself is voltage-feasible
