@@ -214,10 +214,11 @@ struct NewtonParams {
     const int2* homes;          // [nodes] {first, number} of the node's residences in the node-sorted home list
     const double* rho;          // [nodes] 2 r of the edge above the node
     const int* hlist;           // [homes] home index inside the zone of every node-sorted position
+    const int* hnode;           // [homes] node of every node-sorted position
     double* ws;                 // work pools: kNewtonWsDoubles double arrays of ws_stride entries ...
-    double4* ws4;               // ... 4 double4 arrays ...
-    double2* ws2;               // ... 3 double2 arrays ...
-    int* wsi;                   // ... 2 int arrays
+    double4* ws4;               // ... kNewtonWs4 double4 arrays ...
+    double2* ws2;               // ... kNewtonWs2 double2 arrays ...
+    int* wsi;                   // ... kNewtonWsInts int arrays
     int64_t ws_stride;
     const FeederDev* feeders;
     const double* z_t;          // [T][Hp]
@@ -227,6 +228,10 @@ struct NewtonParams {
     int* inner_ok;
     int* wcount;
     int* noconv;                // raised by a column that does not reach the tolerance
+    double* dbg_dump;           // optional [8][nn]: x, v, flags, lam, nf, zf, mu, src of one guess of one column (REVS_NEWTON_DUMP=col,outer,guess)
+    int dbg_dump_col, dbg_dump_outer, dbg_dump_guess;
+    double* dbg_trace;          // optional [columns][16][4]: per outer iteration kkt, solves so far (< 0: guesses cycled), step (< 0: -tau of the safeguard), active rows
+    int* dbg_col;               // optional [2 * columns]: tree solves and outer iterations of every column (REVS_DEBUG)
     unsigned long long* newton_its;
     unsigned long long* cols;
     unsigned long long* flops;
@@ -236,13 +241,13 @@ struct NewtonParams {
     double u, tol;
 };
 struct NewtonZoneHost {
-    std::vector<int> lvl, parent, child0, nchild, home0, nhome, hlist;
+    std::vector<int> lvl, parent, child0, nchild, home0, nhome, hlist, hnode;
     std::vector<double> rho;
     double scale = 1.0;
 };
 void newton_build_zone(int n_nodes, const int* parent, const double* r, int n_res, const int* res_node, NewtonZoneHost& Z);
 cudaError_t launch_tree_newton(const NewtonParams& P, int n_cols, cudaStream_t stream);
-constexpr int kNewtonWsDoubles = 14, kNewtonWs4 = 4, kNewtonWs2 = 3, kNewtonWsInts = 2;
+constexpr int kNewtonWsDoubles = 18, kNewtonWs4 = 3, kNewtonWs2 = 2, kNewtonWsInts = 3;
 
 // ---- contract_f64.cu
 int contract_tile_rows(int T);

@@ -161,7 +161,7 @@ struct revs_solver {
     std::vector<NewtonZoneHost> nt_host;       // per feeder: breadth-first arrays (filled by revs_set_feeder_tree(s))
     std::vector<NewtonZone> nt_zones;
     NewtonZone* d_nt_zones = nullptr;
-    int *d_nt_lvl = nullptr, *d_nt_parent = nullptr, *d_nt_home = nullptr, *d_nt_wsi = nullptr;
+    int *d_nt_lvl = nullptr, *d_nt_parent = nullptr, *d_nt_home = nullptr, *d_nt_hnode = nullptr, *d_nt_wsi = nullptr;
     int2 *d_nt_child = nullptr, *d_nt_homes = nullptr;
     double *d_nt_rho = nullptr, *d_nt_ws = nullptr;
     double4* d_nt_ws4 = nullptr;
@@ -592,7 +592,7 @@ int set_newton(revs_solver* s, int f, bool on) {
 
 // Static pools and work arrays of the tree-Newton zones whose trees have been given; column list = their hours.
 int rebuild_newton(revs_solver* s) {
-    std::vector<int> lvl, parent, hlist;
+    std::vector<int> lvl, parent, hlist, hnode;
     std::vector<int2> child, homes;
     std::vector<double> rho;
     s->nt_zones.clear();
@@ -616,6 +616,7 @@ int rebuild_newton(revs_solver* s) {
         lvl.insert(lvl.end(), Z.lvl.begin(), Z.lvl.end());
         parent.insert(parent.end(), Z.parent.begin(), Z.parent.end());
         hlist.insert(hlist.end(), Z.hlist.begin(), Z.hlist.end());
+        hnode.insert(hnode.end(), Z.hnode.begin(), Z.hnode.end());
         rho.insert(rho.end(), Z.rho.begin(), Z.rho.end());
         for (int i = 0; i < z.nn; ++i) { child.push_back(make_int2(Z.child0[i], Z.nchild[i])); homes.push_back(make_int2(Z.home0[i], Z.nhome[i])); }
         col0 += s->T;
@@ -637,10 +638,10 @@ int rebuild_newton(revs_solver* s) {
         if (sig == s->nt_sig && col0 == s->n_newton_cols && (col0 == 0 || s->d_nt_ws)) return REVS_OK;
         s->nt_sig = sig;
     }
-    void* old[] = {s->d_nt_zones, s->d_nt_lvl, s->d_nt_parent, s->d_nt_home, s->d_nt_wsi, s->d_nt_child, s->d_nt_homes, s->d_nt_rho, s->d_nt_ws, s->d_nt_ws4, s->d_nt_ws2};
+    void* old[] = {s->d_nt_zones, s->d_nt_lvl, s->d_nt_parent, s->d_nt_home, s->d_nt_hnode, s->d_nt_wsi, s->d_nt_child, s->d_nt_homes, s->d_nt_rho, s->d_nt_ws, s->d_nt_ws4, s->d_nt_ws2};
     for (void* q : old) if (q) cudaFree(q);
     s->d_nt_zones = nullptr; s->d_nt_lvl = nullptr; s->d_nt_parent = nullptr; s->d_nt_home = nullptr; s->d_nt_wsi = nullptr;
-    s->d_nt_child = nullptr; s->d_nt_homes = nullptr; s->d_nt_rho = nullptr; s->d_nt_ws = nullptr; s->d_nt_ws4 = nullptr; s->d_nt_ws2 = nullptr;
+    s->d_nt_child = nullptr; s->d_nt_homes = nullptr; s->d_nt_hnode = nullptr; s->d_nt_rho = nullptr; s->d_nt_ws = nullptr; s->d_nt_ws4 = nullptr; s->d_nt_ws2 = nullptr;
     s->n_newton_cols = col0;
     s->nt_ws_stride = ws;
     if (s->loop_exec) { cudaGraphExecDestroy(s->loop_exec); s->loop_exec = nullptr; }   // the captured loop bakes the pointers in
@@ -653,6 +654,8 @@ int rebuild_newton(revs_solver* s) {
     CU(cudaMemcpy(s->d_nt_parent, parent.data(), sizeof(int) * parent.size(), cudaMemcpyHostToDevice));
     CU(dalloc(&s->d_nt_home, hlist.size()));
     CU(cudaMemcpy(s->d_nt_home, hlist.data(), sizeof(int) * hlist.size(), cudaMemcpyHostToDevice));
+    CU(dalloc(&s->d_nt_hnode, hnode.size()));
+    CU(cudaMemcpy(s->d_nt_hnode, hnode.data(), sizeof(int) * hnode.size(), cudaMemcpyHostToDevice));
     CU(dalloc(&s->d_nt_homes, homes.size()));
     CU(cudaMemcpy(s->d_nt_homes, homes.data(), sizeof(int2) * homes.size(), cudaMemcpyHostToDevice));
     CU(dalloc(&s->d_nt_child, child.size()));
@@ -673,7 +676,7 @@ int launch_newton_stage(revs_solver* s, bool timed) {
     if (!newton_active(s)) return REVS_OK;
     NewtonParams N{};
     N.zones = s->d_nt_zones; N.n_zones = (int)s->nt_zones.size();
-    N.lvl = s->d_nt_lvl; N.parent = s->d_nt_parent; N.child = s->d_nt_child; N.homes = s->d_nt_homes; N.rho = s->d_nt_rho; N.hlist = s->d_nt_home;
+    N.lvl = s->d_nt_lvl; N.parent = s->d_nt_parent; N.child = s->d_nt_child; N.homes = s->d_nt_homes; N.rho = s->d_nt_rho; N.hlist = s->d_nt_home; N.hnode = s->d_nt_hnode;
     N.ws = s->d_nt_ws; N.ws4 = s->d_nt_ws4; N.ws2 = s->d_nt_ws2; N.wsi = s->d_nt_wsi; N.ws_stride = s->nt_ws_stride;
     N.feeders = s->d_feeders; N.z_t = s->d_zt; N.lam_t = s->d_lamt; N.g_t = s->d_gt;
     N.status = s->d_status; N.inner_ok = s->d_innerok; N.wcount = s->d_wcount;
@@ -682,10 +685,59 @@ int launch_newton_stage(revs_solver* s, bool timed) {
     N.T = s->T; N.Hp = s->Hp;
     N.u = s->vhigh * s->vhigh - s->vset * s->vset;
     N.tol = kQpTol;
+    int* d_dbg = nullptr;
+    double* d_trace = nullptr;
+    if (s->debug && timed) {
+        CU(dalloc(&d_dbg, (size_t)2 * s->n_newton_cols)); N.dbg_col = d_dbg;
+        CU(dalloc(&d_trace, (size_t)64 * s->n_newton_cols)); N.dbg_trace = d_trace;
+    }
+    double* d_dump = nullptr;
+    size_t dump_n = 0;
+    if (s->debug && timed && getenv("REVS_NEWTON_DUMP") &&
+        sscanf(getenv("REVS_NEWTON_DUMP"), "%d,%d,%d", &N.dbg_dump_col, &N.dbg_dump_outer, &N.dbg_dump_guess) == 3) {     // (debug only)
+        int zi = 0;
+        while (zi + 1 < (int)s->nt_zones.size() && N.dbg_dump_col >= s->nt_zones[zi + 1].col0) ++zi;
+        dump_n = (size_t)8 * s->nt_zones[zi].nn;
+        CU(dalloc(&d_dump, dump_n));
+        N.dbg_dump = d_dump;
+    }
     TimedSpan* sp = timed ? span_begin(s, 9, s->sU) : nullptr;
     CU(launch_tree_newton(N, s->n_newton_cols, s->sU));
     if (sp) span_end(sp, s->sU);
     s->stats.kernel_launches++;
+    if (d_dump) {
+        std::vector<double> hd(dump_n);
+        CU(cudaStreamSynchronize(s->sU));
+        CU(cudaMemcpy(hd.data(), d_dump, dump_n * sizeof(double), cudaMemcpyDeviceToHost));
+        cudaFree(d_dump);
+        char name[128];
+        snprintf(name, sizeof name, "newton_dump_admm%d.bin", s->k);
+        if (FILE* fp = fopen(name, "wb")) { fwrite(hd.data(), sizeof(double), dump_n, fp); fclose(fp); }
+    }
+    if (d_dbg) {
+        std::vector<int> h((size_t)2 * s->n_newton_cols);
+        CU(cudaStreamSynchronize(s->sU));
+        CU(cudaMemcpy(h.data(), d_dbg, h.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        cudaFree(d_dbg);
+        long long sum_s = 0, sum_i = 0;
+        int max_s = 0, max_i = 0, arg_s = 0;
+        for (int c = 0; c < s->n_newton_cols; ++c) {
+            sum_s += h[2 * c]; sum_i += h[2 * c + 1];
+            if (h[2 * c] > max_s) { max_s = h[2 * c]; arg_s = c; }
+            max_i = std::max(max_i, h[2 * c + 1]);
+        }
+        float ms = 0.f;
+        if (sp) cudaEventElapsedTime(&ms, sp->a, sp->b);
+        if (max_s > 60) {
+            std::vector<double> tr(64);
+            CU(cudaMemcpy(tr.data(), d_trace + (size_t)64 * arg_s, 64 * sizeof(double), cudaMemcpyDeviceToHost));
+            for (int i = 0; i < 16 && i <= h[2 * arg_s + 1]; ++i)
+                fprintf(stderr, "[revs]   column %d outer %d: kkt %.3e solves %g step %g active %g\n", arg_s, i, tr[4 * i], tr[4 * i + 1], tr[4 * i + 2], tr[4 * i + 3]);
+        }
+        cudaFree(d_trace);
+        fprintf(stderr, "[revs] admm %d tree-Newton: %d columns, tree solves mean %.1f max %d (column %d), outer iterations mean %.1f max %d, %.3f ms\n", s->k,
+                s->n_newton_cols, (double)sum_s / s->n_newton_cols, max_s, arg_s, (double)sum_i / s->n_newton_cols, max_i, ms);
+    }
     return REVS_OK;
 }
 
@@ -1049,7 +1101,7 @@ void free_all(revs_solver* s) {
                     s->d_gt, s->d_vt, s->d_wcount, s->d_widx, s->d_status, s->d_innerok, s->d_cls, s->d_order, s->d_order4, s->d_order_count, s->d_cnt, s->d_diff,
                     s->d_cprob, s->d_ctiles, s->d_respart, s->d_t_perm, s->d_t_iperm, s->d_t_nodeA, s->d_t_nodeB, s->d_t_cnt,
                     s->d_t_c, s->d_t_d, s->d_t_e, s->d_t_wA, s->d_t_wB, s->d_t_zoff, s->d_tree_cols[0], s->d_tree_cols[1], s->d_tree_cols[2],
-                    s->d_tree_cols[3], s->d_nt_zones, s->d_nt_lvl, s->d_nt_parent, s->d_nt_home, s->d_nt_wsi, s->d_nt_child, s->d_nt_homes, s->d_nt_rho,
+                    s->d_tree_cols[3], s->d_nt_zones, s->d_nt_lvl, s->d_nt_parent, s->d_nt_home, s->d_nt_hnode, s->d_nt_wsi, s->d_nt_child, s->d_nt_homes, s->d_nt_rho,
                     s->d_nt_ws, s->d_nt_ws4, s->d_nt_ws2};
     for (int r = 0; r < kMaxPeers; ++r)
         if (s->peer_box[r] && s->peer_box[r] != s->d_mailbox) cudaIpcCloseMemHandle(s->peer_box[r]);

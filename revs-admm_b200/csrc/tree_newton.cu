@@ -31,8 +31,13 @@
 //
 // Layout: the nodes of a zone are renumbered breadth-first (a level = a contiguous range, the children of a node
 // contiguous in the next level), static arrays per zone, ~300 bytes of per-node work arrays per column in global memory
-// (L2-resident: a level pass touches each once, coalesced; plain loads -- the arrays are written by other threads of the
-// CTA, never through the read-only path).  numpy model of this file: tests/tree_newton_ref.py.
+// (L2-resident; plain loads -- the arrays are written by other threads of the CTA, never through the read-only path).
+// A level pass is a chain of dependent steps, one per tree level (141 for the 10k-home feeder), so what matters is the
+// latency of ONE step: the messages between adjacent levels (8 doubles per node up, 3 down) travel through a
+// double-buffered shared-memory exchange, everything a node needs that does not depend on the neighbouring level is
+// prefetched one level ahead into registers, results go to global memory as fire-and-forget stores, and all per-home
+// work (gathers, clipping, sums) happens in flat loops outside the level passes.  A step is then a barrier, a few
+// shared-memory reads and ~40 dependent FP64 operations.  numpy model of this file: tests/tree_newton_ref.py.
 #include <math_constants.h>
 
 #include <algorithm>
@@ -46,8 +51,10 @@ namespace revs {
 namespace {
 
 constexpr int kNtThreads = 256;
+constexpr int kXCap = 512;                         // nodes of a level whose messages travel through shared memory (the rest: global)
+constexpr int kLvlCap = 1024;                      // level offsets cached in shared memory
 constexpr double kArcMinN = 9.5367431640625e-07;   // 2^-20
-constexpr int kPdasMaxN = 40;
+constexpr int kPdasMaxN = 24;
 constexpr double kHessShiftN = 1e-20;              // structural singularities are handled by the pins, not by the shift
 constexpr double kLmShiftN = 1e-12;                // base shift of the Levenberg-Marquardt safeguard
 constexpr double kPhiNoiseN = 1e-14;
@@ -59,22 +66,25 @@ constexpr int kOuterMaxN = 200;
 enum : int { kRes = 1, kW = 2, kA = 4, kPin = 8, kEff = 16 };
 
 struct Col {                 // work arrays of one column
-    double *z, *g, *gn;                                            // per home (node-sorted order)
-    double *lam, *ln, *x, *mu, *v, *acc, *gr, *mrest, *tau, *tauP, *xi;   // per node
-    double4 *M, *K, *Kn, *P4;
-    double2 *m, *kv, *kvn;
-    int *fl, *src;
+    double *z, *g, *gn;                                                     // per home (node-sorted order)
+    double *lam, *ln, *x, *mu, *v, *acc, *gr, *mrest, *nf, *zf, *gs, *xig, *tauP, *cP, *tau;   // per node
+    double4 *M, *K, *P4;     // message of the subtree / back-substitution as the node acts / pin record
+    double2 *m, *kv;
+    int *fl, *src, *kept;
 };
 
 struct Zone {
     int nn, nlev, n;
-    const int* lvl;          // [nlev + 1]
+    const int* lvl;          // [nlev + 1] (shared-memory copy when it fits)
     const int* parent;
     const int2* child;       // {first child, number of children}
     const int2* homes;       // {first home, number of homes} in the node-sorted home order
     const double* rho;
     const int* hlist;        // [n] home index inside the zone of every node-sorted position
+    const int* hnode;        // [n] node of every node-sorted position
 };
+
+struct Xch { double (*up)[8]; };     // shared-memory exchange: [2][kXCap][8]
 
 __device__ __forceinline__ double block_sum(double v, double* red) {
     v = warp_sum(v);
@@ -110,50 +120,111 @@ __device__ __forceinline__ int block_count(bool p, int* red) {
     return t;
 }
 
-// acc[k] = src(k) + sum over the subtree below k (leaves -> root)
-template <class Src>
-__device__ __forceinline__ void tree_up(const Zone& Z, double* acc, Src src) {
-    for (int l = Z.nlev - 1; l >= 0; --l) {
-        const int lo = Z.lvl[l], hi = Z.lvl[l + 1];
-        for (int k = lo + threadIdx.x; k < hi; k += kNtThreads) {
-            double a = src(k);
-            const int2 ch = Z.child[k];
-            for (int j = 0; j < ch.y; ++j) a += acc[ch.x + j];
-            acc[k] = a;
+// ---- product: out = R x, x given per node in `src` (a global array).  Leaves -> root: acc = subtree sums (tree_sums);
+// root -> leaves: out_k = out_parent + rho_k acc_k.  Messages through X (one double per node), inputs prefetched a level ahead.
+template <bool MAX>
+__device__ __forceinline__ void tree_sums(const Zone& Z, const Xch& X, const double* src, double* acc) {
+    const int tid = threadIdx.x;
+    {
+        int l = Z.nlev - 1;
+        int kn = Z.lvl[l] + tid;
+        bool hn = kn < Z.lvl[l + 1];
+        int2 chn = hn ? Z.child[kn] : make_int2(0, 0);
+        double sn = hn ? src[kn] : 0.0;
+        for (; l >= 0; --l) {
+            const int lo = Z.lvl[l], hi = Z.lvl[l + 1];
+            const int2 ch0 = chn;
+            const double s0 = sn;
+            if (l > 0) {
+                kn = Z.lvl[l - 1] + tid;
+                hn = kn < lo;
+                chn = hn ? Z.child[kn] : make_int2(0, 0);
+                sn = hn ? src[kn] : 0.0;
+            }
+            double(*bc)[8] = X.up + ((l + 1) & 1) * kXCap;
+            double(*bo)[8] = X.up + (l & 1) * kXCap;
+            for (int k = lo + tid; k < hi; k += kNtThreads) {
+                const bool first = k == lo + tid;
+                const int2 ch = first ? ch0 : Z.child[k];
+                double a = first ? s0 : src[k];
+                for (int j = 0; j < ch.y; ++j) {
+                    const int cl = ch.x + j - hi;
+                    const double ac = cl < kXCap ? bc[cl][0] : acc[ch.x + j];
+                    a = MAX ? fmax(a, ac) : a + ac;
+                }
+                acc[k] = a;
+                if (k - lo < kXCap) bo[k - lo][0] = a;
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
 }
-// out[k] = out[parent] + rho_k acc[k] (root -> leaves); sink(k, out[k]) runs in the same pass
-template <class Sink>
-__device__ __forceinline__ void tree_down(const Zone& Z, const double* acc, double* out, Sink sink) {
-    for (int l = 0; l < Z.nlev; ++l) {
-        const int lo = Z.lvl[l], hi = Z.lvl[l + 1];
-        for (int k = lo + threadIdx.x; k < hi; k += kNtThreads) {
-            const int p = Z.parent[k];
-            const double o = fma(Z.rho[k], acc[k], p >= 0 ? out[p] : 0.0);
-            out[k] = o;
-            sink(k, o);
+__device__ __forceinline__ void tree_product(const Zone& Z, const Xch& X, const double* src, double* acc, double* out) {
+    const int tid = threadIdx.x;
+    tree_sums<false>(Z, X, src, acc);
+    {
+        int kn = Z.lvl[0] + tid;
+        bool hn = kn < Z.lvl[1];
+        int pn = hn ? Z.parent[kn] : -1;
+        double rn = hn ? Z.rho[kn] : 0.0, an = hn ? acc[kn] : 0.0;
+        for (int l = 0; l < Z.nlev; ++l) {
+            const int lo = Z.lvl[l], hi = Z.lvl[l + 1];
+            const int p0 = pn;
+            const double r0 = rn, a0 = an;
+            if (l + 1 < Z.nlev) {
+                kn = hi + tid;
+                hn = kn < Z.lvl[l + 2];
+                pn = hn ? Z.parent[kn] : -1;
+                rn = hn ? Z.rho[kn] : 0.0;
+                an = hn ? acc[kn] : 0.0;
+            }
+            const int lop = l > 0 ? Z.lvl[l - 1] : 0;
+            double(*bp)[8] = X.up + ((l + 1) & 1) * kXCap;       // == buffer (l - 1) & 1
+            double(*bo)[8] = X.up + (l & 1) * kXCap;
+            for (int k = lo + tid; k < hi; k += kNtThreads) {
+                const bool first = k == lo + tid;
+                const int p = first ? p0 : Z.parent[k];
+                const double r = first ? r0 : Z.rho[k], a = first ? a0 : acc[k];
+                double op = 0.0;
+                if (p >= 0) op = p - lop < kXCap ? bp[p - lop][0] : out[p];
+                const double o = fma(r, a, op);
+                out[k] = o;
+                if (k - lo < kXCap) bo[k - lo][0] = o;
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
 }
 
 // phi(lam_src) = 1/2 |[z - R lam]_+|^2 + u sum(lam); the iterate [z - R lam]_+ goes to gout (per home)
-template <class Src>
-__device__ __forceinline__ double eval_phi(const Zone& Z, const Col& C, double u, Src src, double* gout, double* red) {
-    tree_up(Z, C.acc, src);
+__device__ __forceinline__ double eval_phi(const Zone& Z, const Xch& X, const Col& C, double u, const double* lsrc, double* gout, double* red) {
+    tree_product(Z, X, lsrc, C.acc, C.mu);
     double part = 0.0;
-    tree_down(Z, C.acc, C.mu, [&](int k, double mu) {
-        const int2 hh = Z.homes[k];
-        for (int j = hh.x; j < hh.x + hh.y; ++j) {
-            const double gk = fmax(C.z[j] - mu, 0.0);
-            gout[j] = gk;
-            part = fma(0.5 * gk, gk, part);
-        }
-        part = fma(u, src(k), part);
-    });
+    for (int j = threadIdx.x; j < Z.n; j += kNtThreads) {
+        const double gk = fmax(C.z[j] - C.mu[Z.hnode[j]], 0.0);
+        gout[j] = gk;
+        part = fma(0.5 * gk, gk, part);
+    }
+    for (int k = threadIdx.x; k < Z.nn; k += kNtThreads) part = fma(u, lsrc[k], part);
     return block_sum(part, red);
+}
+
+// per node: sum of g over its homes (gs), number of homes on the piece and sum of their targets (nf, zf)
+__device__ __forceinline__ void node_sums(const Zone& Z, const Col& C, bool use_rest) {
+    for (int k = threadIdx.x; k < Z.nn; k += kNtThreads) {
+        const int2 hh = Z.homes[k];
+        double gsum = 0.0, nf = 0.0, zf = 0.0;
+        if (hh.y) {
+            const double rest = use_rest ? C.mrest[k] : 0.0;
+            for (int j = hh.x; j < hh.x + hh.y; ++j) {
+                const double gj = C.g[j];
+                gsum += gj;
+                if (gj > 0.0) { nf += 1.0; zf += C.z[j] - rest; }
+            }
+        }
+        C.gs[k] = gsum; C.nf[k] = nf; C.zf[k] = zf;
+    }
+    __syncthreads();
 }
 
 struct Elim { double4 M, K; double2 m, kv; };
@@ -190,109 +261,163 @@ __device__ __forceinline__ Elim elim_active(double S00, double S01, double S10, 
 }
 
 // One active-set guess: x on the node rows flagged kA with v - s x = u - s lam on the rows that take part, for
-// g_h = z_h - mu[node(h)] on the homes of the piece {C.g > 0} (0 elsewhere), v = R g.  use_rest: the target of a home
-// loses C.mrest[node] (rows held at their value by the safeguard).  Results: C.x (0 off A), C.v (voltages of the guess).
-__device__ __forceinline__ void tree_solve(const Zone& Z, const Col& C, double u, double s, bool use_rest) {
-    for (int l = Z.nlev - 1; l >= 0; --l) {
-        const int lo = Z.lvl[l], hi = Z.lvl[l + 1];
-        for (int k = lo + threadIdx.x; k < hi; k += kNtThreads) {
-            int fl = C.fl[k] & ~(kPin | kEff);
-            double tk = CUDART_INF;
-            int sk = -2;
-            if (fl & kA) { tk = u - s * C.lam[k]; sk = -1; }
-            const int2 ch = Z.child[k];
-            for (int j = 0; j < ch.y; ++j) {
-                const int c = ch.x + j;
-                if ((C.fl[c] & kPin) && C.tauP[c] < tk) { tk = C.tauP[c]; sk = c; }
+// g_h = z_h - mu[node(h)] on the homes of the piece (C.nf / C.zf, see node_sums), 0 elsewhere, v = R g.
+// Results: C.x (0 off A), C.v (voltages of the guess).
+// Message of node k to its parent (8 doubles): M (4), m (2), voltage it pins the parent to (inf: none), its constant flow.
+struct UpIn { int2 ch; int fl; double r, lam, nf, zf; int parent; };
+
+__device__ __forceinline__ UpIn load_up(const Zone& Z, const Col& C, int k) {
+    UpIn i;
+    i.ch = Z.child[k]; i.fl = C.fl[k]; i.r = Z.rho[k]; i.lam = C.lam[k]; i.nf = C.nf[k]; i.zf = C.zf[k]; i.parent = Z.parent[k];
+    return i;
+}
+struct DnIn { int parent, fl, kept, src; double4 K; double2 kv; double tau, lam; };
+
+__device__ __forceinline__ DnIn load_dn(const Zone& Z, const Col& C, int k) {
+    DnIn i;
+    i.parent = Z.parent[k]; i.fl = C.fl[k]; i.kept = C.kept[k]; i.src = C.src[k];
+    i.K = C.K[k]; i.kv = C.kv[k]; i.tau = C.tau[k]; i.lam = C.lam[k];
+    return i;
+}
+
+__device__ __forceinline__ void tree_solve(const Zone& Z, const Xch& X, const Col& C, double u, double s) {
+    const int tid = threadIdx.x;
+    {
+        int l = Z.nlev - 1;
+        int kn = Z.lvl[l] + tid;
+        UpIn nx{};
+        if (kn < Z.lvl[l + 1]) nx = load_up(Z, C, kn);
+        for (; l >= 0; --l) {
+            const int lo = Z.lvl[l], hi = Z.lvl[l + 1];
+            const UpIn c0 = nx;
+            if (l > 0) {
+                kn = Z.lvl[l - 1] + tid;
+                if (kn < lo) nx = load_up(Z, C, kn);
             }
-            double n00 = 0.0, n01 = 0.0, n10 = 0.0, n11 = 0.0, n0 = 0.0, n1 = 0.0;       // every child as a plain / regular node
-            double e00 = 0.0, e01 = 0.0, e10 = 0.0, e11 = 0.0, e0 = 0.0, e1 = 0.0;       // the kept pin replaced by its message
-            for (int j = 0; j < ch.y; ++j) {
-                const int c = ch.x + j;
-                const double4 Mc = C.M[c];
-                const double2 mc = C.m[c];
-                n00 += Mc.x; n01 += Mc.y; n10 += Mc.z; n11 += Mc.w; n0 += mc.x; n1 += mc.y;
-                if (c == sk) e1 += C.P4[c].w;
-                else { e00 += Mc.x; e01 += Mc.y; e10 += Mc.z; e11 += Mc.w; e0 += mc.x; e1 += mc.y; }
-            }
-            const int2 hh = Z.homes[k];
-            if (hh.y) {
-                const double rest = use_rest ? C.mrest[k] : 0.0;
-                double nf = 0.0, zf = 0.0;
-                for (int j = hh.x; j < hh.x + hh.y; ++j)
-                    if (C.g[j] > 0.0) { nf += 1.0; zf += C.z[j] - rest; }
-                n10 -= nf; e10 -= nf; n1 += zf; e1 += zf;
-            }
-            const double r = Z.rho[k];
-            Elim P = elim_plain(n00, n01, n10, n11, n0, n1, r);
-            C.Kn[k] = P.K; C.kvn[k] = P.kv;
-            if (sk != -2) {
-                if (fabs(e10) < kDegTolN) {
-                    // nothing below responds to the multiplier: the row pins the parent (no parent: it cannot bind)
-                    if (Z.parent[k] < 0) sk = -2;
-                    else {
-                        const double cf = fma(e11, tk, e1);
-                        fl |= kPin;
-                        C.tauP[k] = tk - r * cf;
-                        C.P4[k] = make_double4(e00, e01, e0, cf);
-                    }
-                } else {
-                    P = elim_active(e00, e01, e10, e11, e0, e1, r, tk, s);
-                    C.K[k] = P.K; C.kv[k] = P.kv;
-                    fl |= kEff;
+            double(*bc)[8] = X.up + ((l + 1) & 1) * kXCap;
+            double(*bo)[8] = X.up + (l & 1) * kXCap;
+            for (int k = lo + tid; k < hi; k += kNtThreads) {
+                const UpIn in = k == lo + tid ? c0 : load_up(Z, C, k);
+                int fl = in.fl & ~(kPin | kEff);
+                double tk = CUDART_INF;
+                int sk = -2;
+                if (fl & kA) { tk = u - s * in.lam; sk = -1; }
+                // the tightest pin among the children (and the own row) is the effective row of this node
+                for (int j = 0; j < in.ch.y; ++j) {
+                    const int c = in.ch.x + j, cl = c - hi;
+                    const double tp = cl < kXCap ? bc[cl][6] : C.tauP[c];
+                    if (tp < tk) { tk = tp; sk = c; }
                 }
+                double n00 = 0.0, n01 = 0.0, n10 = 0.0, n11 = 0.0, n0 = 0.0, n1 = 0.0;   // every child as it acts without a kept pin
+                double e00 = 0.0, e01 = 0.0, e10 = 0.0, e11 = 0.0, e0 = 0.0, e1 = 0.0;   // the kept pin replaced by its message: its constant flow
+                for (int j = 0; j < in.ch.y; ++j) {
+                    const int c = in.ch.x + j, cl = c - hi;
+                    double q[8];
+                    if (cl < kXCap) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) q[e] = bc[cl][e];
+                    } else {
+                        const double4 Mc = C.M[c];
+                        const double2 mc = C.m[c];
+                        q[0] = Mc.x; q[1] = Mc.y; q[2] = Mc.z; q[3] = Mc.w; q[4] = mc.x; q[5] = mc.y; q[6] = C.tauP[c]; q[7] = C.cP[c];
+                    }
+                    n00 += q[0]; n01 += q[1]; n10 += q[2]; n11 += q[3]; n0 += q[4]; n1 += q[5];
+                    if (c == sk) e1 += q[7];
+                    else { e00 += q[0]; e01 += q[1]; e10 += q[2]; e11 += q[3]; e0 += q[4]; e1 += q[5]; }
+                }
+                n10 -= in.nf; e10 -= in.nf; n1 += in.zf; e1 += in.zf;
+                Elim P = elim_plain(n00, n01, n10, n11, n0, n1, in.r);
+                double4 Kact = P.K;
+                double2 kvact = P.kv;
+                double tauP = CUDART_INF, cP = 0.0;
+                if (sk != -2) {
+                    if (fabs(e10) < kDegTolN) {
+                        // nothing below responds to the multiplier: the row pins the parent (no parent: it cannot bind)
+                        if (in.parent < 0) sk = -2;
+                        else {
+                            cP = fma(e11, tk, e1);
+                            tauP = tk - in.r * cP;
+                            fl |= kPin;
+                            C.P4[k] = make_double4(e00, e01, e0, cP);
+                        }
+                    } else {
+                        P = elim_active(e00, e01, e10, e11, e0, e1, in.r, tk, s);
+                        Kact = P.K; kvact = P.kv;
+                        fl |= kEff;
+                    }
+                }
+                if (k - lo < kXCap) {
+                    double* o = bo[k - lo];
+                    o[0] = P.M.x; o[1] = P.M.y; o[2] = P.M.z; o[3] = P.M.w; o[4] = P.m.x; o[5] = P.m.y; o[6] = tauP; o[7] = cP;
+                } else {
+                    C.M[k] = P.M; C.m[k] = P.m; C.tauP[k] = tauP; C.cP[k] = cP;
+                }
+                C.K[k] = Kact; C.kv[k] = kvact;
+                C.tau[k] = tk;
+                C.src[k] = sk;
+                C.fl[k] = fl;
+                C.kept[k] = 0;
+                if (sk >= 0) C.kept[sk] = 1;          // (the child reset its flag one level earlier)
             }
-            C.M[k] = P.M; C.m[k] = P.m;
-            C.tau[k] = tk;
-            C.src[k] = sk;
-            C.fl[k] = fl;
-            C.xi[k] = CUDART_NAN;
+            __syncthreads();
         }
-        __syncthreads();
     }
-    for (int l = 0; l < Z.nlev; ++l) {
-        const int lo = Z.lvl[l], hi = Z.lvl[l + 1];
-        for (int k = lo + threadIdx.x; k < hi; k += kNtThreads) {
-            const int p = Z.parent[k];
-            const double mp = p >= 0 ? C.mu[p] : 0.0, vp = p >= 0 ? C.v[p] : 0.0;
-            const int fl = C.fl[k];
-            double xi = 0.0;
-            bool eff = false;
-            if ((fl & kPin) && !isnan(C.xi[k])) {
-                const double Xi = C.xi[k];
-                const double4 P4 = C.P4[k];
-                const double muk = fma(Z.rho[k], Xi, mp), vk = C.tau[k];
-                C.mu[k] = muk; C.v[k] = vk;
-                xi = Xi - fma(P4.x, muk, fma(P4.y, vk, P4.z));
-                eff = true;
-            } else if (fl & kEff) {
-                const double4 Kk = C.K[k];
-                const double2 kk = C.kv[k];
-                C.mu[k] = fma(Kk.x, mp, fma(Kk.y, vp, kk.x));
-                xi = fma(Kk.z, mp, fma(Kk.w, vp, kk.y));
-                C.v[k] = fma(s, xi, C.tau[k]);
-                eff = true;
-            } else {
-                const double4 Kk = C.Kn[k];
-                const double2 kk = C.kvn[k];
-                C.mu[k] = fma(Kk.x, mp, fma(Kk.y, vp, kk.x));
-                C.v[k] = fma(Kk.z, mp, fma(Kk.w, vp, kk.y));
+    {
+        int kn = Z.lvl[0] + tid;
+        DnIn nx{};
+        if (kn < Z.lvl[1]) nx = load_dn(Z, C, kn);
+        for (int l = 0; l < Z.nlev; ++l) {
+            const int lo = Z.lvl[l], hi = Z.lvl[l + 1];
+            const DnIn c0 = nx;
+            if (l + 1 < Z.nlev) {
+                kn = hi + tid;
+                if (kn < Z.lvl[l + 2]) nx = load_dn(Z, C, kn);
             }
-            double xk = 0.0;
-            if (eff) {
-                const int sk = C.src[k];
-                if (sk == -1) xk = xi;
-                else if (sk >= 0) C.xi[sk] = xi;
+            const int lop = l > 0 ? Z.lvl[l - 1] : 0;
+            double(*bp)[8] = X.up + ((l + 1) & 1) * kXCap;
+            double(*bo)[8] = X.up + (l & 1) * kXCap;
+            for (int k = lo + tid; k < hi; k += kNtThreads) {
+                const DnIn in = k == lo + tid ? c0 : load_dn(Z, C, k);
+                double mp = 0.0, vp = 0.0, Xi = 0.0;
+                if (in.parent >= 0) {
+                    const int pl = in.parent - lop;
+                    if (pl < kXCap) { mp = bp[pl][0]; vp = bp[pl][1]; Xi = bp[pl][2]; }
+                    else { mp = C.mu[in.parent]; vp = C.v[in.parent]; Xi = C.xig[in.parent]; }
+                }
+                double muk, vk, xi = 0.0;
+                bool eff = false;
+                if ((in.fl & kPin) && in.kept && !isnan(Xi)) {
+                    const double4 P4 = C.P4[k];
+                    muk = fma(Z.rho[k], Xi, mp);
+                    vk = in.tau;
+                    xi = Xi - fma(P4.x, muk, fma(P4.y, vk, P4.z));
+                    eff = true;
+                } else if (in.fl & kEff) {
+                    muk = fma(in.K.x, mp, fma(in.K.y, vp, in.kv.x));
+                    xi = fma(in.K.z, mp, fma(in.K.w, vp, in.kv.y));
+                    vk = fma(s, xi, in.tau);
+                    eff = true;
+                } else {
+                    muk = fma(in.K.x, mp, fma(in.K.y, vp, in.kv.x));
+                    vk = fma(in.K.z, mp, fma(in.K.w, vp, in.kv.y));
+                }
+                const double xk = (eff && in.src == -1) ? xi : 0.0;
+                const double xo = (eff && in.src >= 0) ? xi : CUDART_NAN;   // dual flow handed to the kept pin below (nan: no pin is enforced)
+                if (k - lo < kXCap) { double* o = bo[k - lo]; o[0] = muk; o[1] = vk; o[2] = xo; }
+                C.mu[k] = muk; C.v[k] = vk; C.xig[k] = xo; C.x[k] = xk;
             }
-            C.x[k] = xk;
+            __syncthreads();
         }
-        __syncthreads();
     }
 }
 
 __global__ void __launch_bounds__(kNtThreads) tree_newton_kernel(NewtonParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red[kNtThreads / 32];
     __shared__ int redi[kNtThreads / 32];
+    __shared__ int slvl[kLvlCap + 1];
+    Xch X;
+    X.up = reinterpret_cast<double(*)[8]>(smem_raw);
     const int c = blockIdx.x;                       // column of the list: zone-major, hour-minor
     int zi = 0;
     while (zi + 1 < P.n_zones && c >= P.zones[zi + 1].col0) ++zi;
@@ -301,22 +426,27 @@ __global__ void __launch_bounds__(kNtThreads) tree_newton_kernel(NewtonParams P)
     Zone Z;
     Z.nn = nz.nn; Z.nlev = nz.nlev; Z.n = nz.n;
     Z.lvl = P.lvl + nz.lvl_off;
+    if (nz.nlev <= kLvlCap) {
+        for (int i = threadIdx.x; i <= nz.nlev; i += kNtThreads) slvl[i] = Z.lvl[i];
+        Z.lvl = slvl;
+    }
     Z.parent = P.parent + nz.node_off;
     Z.child = P.child + nz.node_off;
     Z.homes = P.homes + nz.node_off;
     Z.rho = P.rho + nz.node_off;
     Z.hlist = P.hlist + nz.home_off;
+    Z.hnode = P.hnode + nz.home_off;
     const size_t wo = (size_t)nz.ws_off + (size_t)t * nz.wn, st = (size_t)P.ws_stride;
     Col C;
     {
         double* w = P.ws + wo;
         C.z = w; C.g = w + st; C.gn = w + 2 * st; C.lam = w + 3 * st; C.ln = w + 4 * st; C.x = w + 5 * st; C.mu = w + 6 * st;
-        C.v = w + 7 * st; C.acc = w + 8 * st; C.gr = w + 9 * st; C.mrest = w + 10 * st; C.tau = w + 11 * st; C.tauP = w + 12 * st;
-        C.xi = w + 13 * st;
+        C.v = w + 7 * st; C.acc = w + 8 * st; C.gr = w + 9 * st; C.mrest = w + 10 * st; C.nf = w + 11 * st; C.zf = w + 12 * st;
+        C.gs = w + 13 * st; C.xig = w + 14 * st; C.tauP = w + 15 * st; C.cP = w + 16 * st; C.tau = w + 17 * st;
     }
-    C.M = P.ws4 + wo; C.K = C.M + st; C.Kn = C.K + st; C.P4 = C.Kn + st;
-    C.m = P.ws2 + wo; C.kv = C.m + st; C.kvn = C.kv + st;
-    C.fl = P.wsi + wo; C.src = C.fl + st;
+    C.M = P.ws4 + wo; C.K = C.M + st; C.P4 = C.K + st;
+    C.m = P.ws2 + wo; C.kv = C.m + st;
+    C.fl = P.wsi + wo; C.src = C.fl + st; C.kept = C.src + st;
     const int nn = Z.nn, n = Z.n;
     const double u = P.u, tol = P.tol;
     const FeederDev fd = P.feeders[nz.feeder];
@@ -336,42 +466,65 @@ __global__ void __launch_bounds__(kNtThreads) tree_newton_kernel(NewtonParams P)
     }
     __syncthreads();
     const double scale = nz.scale;
-    double f = eval_phi(Z, C, u, [&](int k) { return C.lam[k]; }, C.g, red);
+    double f = eval_phi(Z, X, C, u, C.lam, C.g, red);
     double tau = 1.0;
     int its = 0, n_solves = 0, status = 0, n_act = 0;
     for (; its < kOuterMaxN; ++its) {
         // ---- exact voltages of the iterate: KKT residual, gradient of the dual, working rows W (= first guess A)
-        tree_up(Z, C.acc, [&](int k) {
-            const int2 hh = Z.homes[k];
-            double a = 0.0;
-            for (int j = hh.x; j < hh.x + hh.y; ++j) a += C.g[j];
-            return a;
-        });
+        node_sums(Z, C, false);
+        tree_product(Z, X, C.gs, C.acc, C.v);
         double kk = 0.0;
         int nact = 0;
-        tree_down(Z, C.acc, C.v, [&](int k, double vk) {
-            int fl = C.fl[k] & kRes;
-            double grad = 0.0;
+        for (int k = threadIdx.x; k < nn; k += kNtThreads) {
+            const int fl = C.fl[k] & kRes;
+            double grad = 0.0, viol = 0.0;
             if (fl) {
                 const double lk = C.lam[k];
-                grad = u - vk;
+                grad = u - C.v[k];
                 kk = fmax(kk, lk > 0.0 ? fabs(grad) : fmax(-grad, 0.0));
-                if (lk > 0.0 || grad < 0.0) fl |= kW | kA;
+                viol = fmax(-grad, 0.0);
                 nact += lk > 0.0;
             }
             C.fl[k] = fl;
             C.gr[k] = grad;
-        });
+            C.ln[k] = viol;
+        }
         const double kkt = block_max(kk, red);
         n_act = (int)block_sum((double)nact, red);
+        double* tr = (P.dbg_trace && its < 16) ? P.dbg_trace + ((size_t)c * 16 + its) * 4 : nullptr;
+        if (tr && threadIdx.x == 0) { tr[0] = kkt; tr[1] = 0; tr[2] = 0; tr[3] = n_act; }
         if (kkt < tol) { status = 1; break; }
         const double shift = kHessShiftN * scale + 1e-300;
+
+        // ---- working rows (= first guess): the multipliers' support and the SKYLINE of the violated rows -- a violated row
+        // enters when no row in the subtree of its parent is more violated.  Under a heavy shared drop thousands of rows are
+        // violated by similar amounts and a hundred end up binding; holding the skyline repairs most of the others, what is
+        // left is admitted by the next iteration (the KKT test above always runs over all rows).
+        tree_sums<true>(Z, X, C.ln, C.acc);
+        for (int k = threadIdx.x; k < nn; k += kNtThreads) {
+            int fl = C.fl[k];
+            if (fl & kRes) {
+                const double viol = C.ln[k];
+                const int p = Z.parent[k];
+                if (C.lam[k] > 0.0 || (viol > 0.0 && viol >= C.acc[p >= 0 ? p : k])) fl |= kW | kA;
+                C.fl[k] = fl;
+            }
+        }
+        __syncthreads();
 
         // ---- exact minimiser of the piece over lam_W >= 0: primal-dual active set, one tree solve per guess
         bool ok = false;
         for (int guess = 0; guess < kPdasMaxN; ++guess) {
-            tree_solve(Z, C, u, shift, false);
+            tree_solve(Z, X, C, u, shift);
             ++n_solves;
+            if (P.dbg_dump && c == P.dbg_dump_col && its == P.dbg_dump_outer && guess == P.dbg_dump_guess) {
+                for (int k = threadIdx.x; k < nn; k += kNtThreads) {
+                    P.dbg_dump[k] = C.x[k]; P.dbg_dump[nn + k] = C.v[k]; P.dbg_dump[2 * nn + k] = (double)C.fl[k];
+                    P.dbg_dump[3 * nn + k] = C.lam[k]; P.dbg_dump[4 * nn + k] = C.nf[k]; P.dbg_dump[5 * nn + k] = C.zf[k];
+                    P.dbg_dump[6 * nn + k] = C.mu[k]; P.dbg_dump[7 * nn + k] = (double)C.src[k];
+                }
+                __syncthreads();
+            }
             bool bad = false;
             for (int k = threadIdx.x; k < nn; k += kNtThreads) {
                 int fl = C.fl[k];
@@ -382,22 +535,25 @@ __global__ void __launch_bounds__(kNtThreads) tree_newton_kernel(NewtonParams P)
             }
             if (block_count(bad, redi) == 0) { ok = true; break; }
         }
+        if (tr && threadIdx.x == 0) tr[1] = ok ? n_solves : -n_solves;
         double fn = f;
-        if (ok) {
-            // ---- line search of the dual on the segment lam -> minimiser (direction kept in x)
+        {
+            // ---- line search of the dual on the segment lam -> minimiser (direction kept in x).  When the guesses did not
+            // settle, the last one clipped to lam >= 0 still gives a feasible direction: it is tried before the safeguard.
             double sl = 0.0;
             for (int k = threadIdx.x; k < nn; k += kNtThreads) {
                 double d = 0.0;
-                if (C.fl[k] & kW) { d = C.x[k] - C.lam[k]; sl = fma(C.gr[k], d, sl); }
+                if (C.fl[k] & kW) { d = fmax(C.x[k], 0.0) - C.lam[k]; sl = fma(C.gr[k], d, sl); }
                 C.x[k] = d;
             }
             const double slope = block_sum(sl, red);
+            const bool settled = ok;
             ok = false;
-            for (double a = 1.0; a >= kArcMinN; a *= 0.5) {
+            for (double a = 1.0; slope < 0.0 && a >= (settled ? kArcMinN : 1.0 / 64.0); a *= 0.5) {
                 for (int k = threadIdx.x; k < nn; k += kNtThreads) C.ln[k] = fmax(fma(a, C.x[k], C.lam[k]), 0.0);
                 __syncthreads();
-                fn = eval_phi(Z, C, u, [&](int k) { return C.ln[k]; }, C.gn, red);
-                if (fn <= f + 1e-4 * a * slope + kPhiNoiseN * fabs(f)) { ok = true; break; }
+                fn = eval_phi(Z, X, C, u, C.ln, C.gn, red);
+                if (fn <= f + 1e-4 * a * slope + kPhiNoiseN * fabs(f)) { ok = true; if (tr && threadIdx.x == 0) tr[2] = a; break; }
             }
         }
         if (!ok) {
@@ -407,22 +563,23 @@ __global__ void __launch_bounds__(kNtThreads) tree_newton_kernel(NewtonParams P)
             bool rest = false;
             for (int k = threadIdx.x; k < nn; k += kNtThreads) {
                 int fl = C.fl[k] & ~kA;
+                double held = 0.0;
                 if (fl & kW) {
                     if (!(C.lam[k] <= eps && C.gr[k] > 0.0)) fl |= kA;
-                    else if (C.lam[k] > 0.0) rest = true;
+                    else if (C.lam[k] > 0.0) { rest = true; held = C.lam[k]; }
                 }
                 C.fl[k] = fl;
+                C.ln[k] = held;
             }
-            const bool use_rest = block_count(rest, redi) > 0;
-            if (use_rest) {
-                tree_up(Z, C.acc, [&](int k) { const int fl = C.fl[k]; return ((fl & kW) && !(fl & kA)) ? C.lam[k] : 0.0; });
-                tree_down(Z, C.acc, C.mrest, [&](int, double) {});
+            if (block_count(rest, redi) > 0) {
+                tree_product(Z, X, C.ln, C.acc, C.mrest);
+                node_sums(Z, C, true);
             }
             bool found = false;
             double a = 1.0;
             for (;;) {
                 const double sg = kLmShiftN * tau * scale + 1e-300;
-                tree_solve(Z, C, u, sg, use_rest);
+                tree_solve(Z, X, C, u, sg);
                 ++n_solves;
                 for (int k = threadIdx.x; k < nn; k += kNtThreads) {
                     const int fl = C.fl[k];
@@ -437,12 +594,13 @@ __global__ void __launch_bounds__(kNtThreads) tree_newton_kernel(NewtonParams P)
                         if (C.fl[k] & kW) sl = fma(C.gr[k], lnk - C.lam[k], sl);
                     }
                     const double slope = block_sum(sl, red);
-                    fn = eval_phi(Z, C, u, [&](int k) { return C.ln[k]; }, C.gn, red);
+                    fn = eval_phi(Z, X, C, u, C.ln, C.gn, red);
                     if (fn <= f + 1e-4 * slope + kPhiNoiseN * fabs(f)) { found = true; break; }
                 }
                 if (found || tau > 1e40) break;
                 tau *= 1e3;
             }
+            if (tr && threadIdx.x == 0) tr[2] = -tau;
             if (!found) { status = 2; break; }
             if (a == 1.0) tau = fmax(1.0, tau / 10.0);
         }
@@ -464,6 +622,7 @@ __global__ void __launch_bounds__(kNtThreads) tree_newton_kernel(NewtonParams P)
         P.status[colid] = 1;
         P.inner_ok[colid] = 1;
         P.wcount[colid] = 0;
+        if (P.dbg_col) { P.dbg_col[2 * c] = n_solves; P.dbg_col[2 * c + 1] = its; }
         if (status != 1) atomicAdd(P.noconv, 1);
         atomicAdd(P.newton_its, (unsigned long long)n_solves);
         atomicAdd(P.cols, 1ull);
@@ -471,6 +630,8 @@ __global__ void __launch_bounds__(kNtThreads) tree_newton_kernel(NewtonParams P)
         atomicAdd(P.flops, (unsigned long long)((double)nn * (90.0 * n_solves + 8.0 * (its + 1))));
     }
 }
+
+constexpr int kNtSmem = 2 * kXCap * 8 * (int)sizeof(double);
 
 }  // namespace
 
@@ -515,8 +676,9 @@ void newton_build_zone(int n_nodes, const int* parent, const double* r, int n_re
     int run = 0;
     for (int i = 0; i < n; ++i) { Z.home0[i] = run; run += Z.nhome[i]; }
     Z.hlist.assign(n_res, 0);
+    Z.hnode.assign(n_res, 0);
     std::vector<int> fill(n, 0);
-    for (int h = 0; h < n_res; ++h) { const int k = node_of[h]; Z.hlist[Z.home0[k] + fill[k]++] = h; }
+    for (int h = 0; h < n_res; ++h) { const int k = node_of[h]; const int j = Z.home0[k] + fill[k]++; Z.hlist[j] = h; Z.hnode[j] = k; }
     // scale of the shifts: mean over the residences of (row sum of R)^2 / n (a lower bound of the squared row norm)
     std::vector<double> acc(n, 0.0), mu(n, 0.0);
     for (int i = 0; i < n; ++i) acc[i] = (double)Z.nhome[i];
@@ -532,7 +694,12 @@ void newton_build_zone(int n_nodes, const int* parent, const double* r, int n_re
 
 cudaError_t launch_tree_newton(const NewtonParams& P, int n_cols, cudaStream_t stream) {
     if (n_cols <= 0) return cudaSuccess;
-    tree_newton_kernel<<<n_cols, kNtThreads, 0, stream>>>(P);
+    static std::atomic<unsigned long long> attr_done{0};
+    if (first_use_on_device(attr_done)) {
+        cudaError_t e = cudaFuncSetAttribute(tree_newton_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNtSmem);
+        if (e != cudaSuccess) return e;
+    }
+    tree_newton_kernel<<<n_cols, kNtThreads, kNtSmem, stream>>>(P);
     return cudaGetLastError();
 }
 

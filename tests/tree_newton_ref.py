@@ -93,7 +93,7 @@ def tree_solve(parent, rho, z, F, A, t, s):
 
 HESS_SHIFT = 1e-20        # relative diagonal shift: structural singularities are handled by the pins, not by the shift
 ARC_MIN = 2.0 ** -20
-PDAS_MAX = 40
+PDAS_MAX = 24
 PHI_NOISE = 1e-14
 CONTRACT_REL = 1e-10      # edges below this fraction of the largest root-to-node resistance are contracted
 DEG_TOL = 1e-9           # |d(flow of the subtree)/d(mu)| below this: no home of the piece below an effective row
@@ -322,7 +322,19 @@ class LevelTree:
                 first = np.unique(res, return_index=True)[1]
                 lam_h[first] = lam[res[first]]
                 return g, lam_h, it
-            W = isres & ((lam > 0) | (grad < 0))
+            # working rows: the multipliers' support and the SKYLINE of the violated rows -- a violated row enters when no row
+            # in the subtree of its parent is more violated.  Under a heavy shared drop thousands of rows are violated by
+            # similar amounts, a hundred end up binding; holding the skyline repairs most of the others, the rest is admitted
+            # by the next iteration (the KKT test always runs over all rows).
+            viol = np.where(isres, np.maximum(-grad, 0.0), 0.0)
+            sub = viol.copy()
+            for lo, hi in self.levels_up():
+                c0, nc = self.child0[lo:hi], self.nchild[lo:hi]
+                for j in range(int(nc.max()) if hi > lo else 0):
+                    m = nc > j
+                    sub[lo:hi][m] = np.maximum(sub[lo:hi][m], sub[c0[m] + j])
+            ref = np.where(self.parent >= 0, sub[np.maximum(self.parent, 0)], sub)
+            W = isres & ((lam > 0) | ((viol > 0) & (viol >= ref)))
             Fh = g > 0
             nF = node_sum(Fh.astype(float))
             zF = node_sum(np.where(Fh, z, 0.0))
@@ -339,19 +351,20 @@ class LevelTree:
                     ok = True
                     break
                 A = (A & ~bad_in) | bad_out
-            if ok:
-                d = np.where(W, x - lam, 0.0)
-                slope = float(np.where(W, grad, 0.0) @ d)
-                a = 1.0
-                while a >= ARC_MIN:
-                    ln = np.maximum(lam + a * d, 0.0)
-                    fn, gn = phi(ln)
-                    nprod += 1
-                    if fn <= f + 1e-4 * a * slope + PHI_NOISE * abs(f):
-                        break
-                    a *= 0.5
-                else:
-                    ok = False
+            # line search on the segment to the minimiser; guesses that did not settle: the last one, clipped, is tried first
+            settled = ok
+            d = np.where(W, np.maximum(x, 0.0) - lam, 0.0)
+            slope = float(np.where(W, grad, 0.0) @ d)
+            a = 1.0
+            ok = False
+            while slope < 0.0 and a >= (ARC_MIN if settled else 1.0 / 64.0):
+                ln = np.maximum(lam + a * d, 0.0)
+                fn, gn = phi(ln)
+                nprod += 1
+                if fn <= f + 1e-4 * a * slope + PHI_NOISE * abs(f):
+                    ok = True
+                    break
+                a *= 0.5
             if not ok:
                 eps = min(1e-8, kkt)
                 free = W & ~((lam <= eps) & (grad > 0))
