@@ -23,6 +23,8 @@
  *                                                                     compute_voltage()
  *   revs_get_results / revs_get_schedule          lpsolver.py:289-290 return diff,P_sch,S,C
  *   revs_set_option / revs_get_stats / revs_version / revs_last_error / revs_device_count /
+ *   revs_reliability_sharded / revs_gather_export / revs_gather_attach
+ *                                                 drawing.py:29-78 for one feeder over several GPUs (rows partitioned)
  *   revs_comm_export / revs_comm_attach / revs_comm_detach / revs_zone_arrays
  *                                                 no reference counterpart (library plumbing; the reference is one process)
  */
@@ -157,6 +159,22 @@ int revs_solve_individual(revs_solver* s, double* P_res, double* P_ev, double* S
  * 1/rating), may be NULL (=1). */
 int revs_reliability(revs_solver* s, int feeder, int kind, int n_rows, const int32_t* rows,
                      const double* scale, double vset, const double* P, double* out);
+
+/* The same check with the ROWS PARTITIONED over the GPUs of one box (one process per GPU, every process holds the
+ * feeder's tree; BASELINE north_star: "the sensitivity contraction is row-partitioned"): every rank builds and
+ * contracts only its block of the requested rows, and the epilogue of the contraction kernel stores each output
+ * element straight into the gather buffer of EVERY rank through peer-mapped (NVLink) memory -- the all-gather is
+ * fused into the FP64 tensor-core kernel, there is no NCCL call and no extra copy; arrival flags (system-scope
+ * release / acquire) close the exchange.  All ranks call it with the same arguments; P (the feeder's whole
+ * schedule, [n_f,T]) is required; out [n_rows,T] is complete on every rank.
+ * Protocol: revs_gather_export (allocates this rank's buffer for up to capacity_doubles = n_rows*T outputs, returns
+ * its 64-byte CUDA IPC handle), exchange the handles on the host, revs_gather_attach with all `world` handles in
+ * rank order (<= 16 ranks), a host barrier, then any number of revs_reliability_sharded calls (collective).
+ * Replaces drawing.py:29-78 for a feeder too large for one GPU's share of the time; the reference is one process. */
+int revs_gather_export(revs_solver* s, int64_t capacity_doubles, void* handle64);
+int revs_gather_attach(revs_solver* s, int world, int rank, const void* handles);
+int revs_reliability_sharded(revs_solver* s, int feeder, int kind, int n_rows, const int32_t* rows,
+                             const double* scale, double vset, const double* P, double* out);
 
 /* Plain sensitivity contraction C[M,T] = A[M,K] @ B[K,T] on the tensor cores (FP64
  * DMMA), host in/out -- exposed so that the GEMM kernel can be tested on its own. */

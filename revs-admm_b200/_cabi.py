@@ -69,6 +69,9 @@ SIGNATURES = {
     "revs_comm_export": ([_P, C.c_void_p], C.c_int),
     "revs_comm_attach": ([_P, C.c_int, C.c_int, C.c_void_p], C.c_int),
     "revs_comm_detach": ([_P], C.c_int),
+    "revs_gather_export": ([_P, C.c_int64, C.c_void_p], C.c_int),
+    "revs_gather_attach": ([_P, C.c_int, C.c_int, C.c_void_p], C.c_int),
+    "revs_reliability_sharded": ([_P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), _D, C.c_double, _D, _D], C.c_int),
 }
 
 _lib = None
@@ -327,6 +330,28 @@ class Solver:
         _check(self.lib.revs_reliability(self._h, feeder, kind, len(rows),
                                          rows.ctypes.data_as(C.POINTER(C.c_int32)), _dp(sc), vset,
                                          _dp(Pp), _dp(out)))
+        return out
+
+    # ---- the same check with the rows partitioned over the GPUs of the box; the all-gather of the result is fused
+    # into the epilogue of the contraction kernel (peer-memory stores, include/revs_admm.h: revs_gather_*)
+    def gather_export(self, capacity_doubles):
+        buf = C.create_string_buffer(64)
+        _check(self.lib.revs_gather_export(self._h, int(capacity_doubles), buf))
+        return buf.raw
+
+    def gather_attach(self, world, rank, handles):
+        handles = bytes(handles)
+        assert len(handles) == 64 * world
+        _check(self.lib.revs_gather_attach(self._h, world, rank, handles))
+
+    def reliability_sharded(self, feeder, kind, rows, P, vset=1.0, scale=None):
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        out = np.empty((len(rows), self.T))
+        sc = None if scale is None else _f64(scale, (len(rows),))
+        Pp = _f64(P, (self.sizes[feeder], self.T))
+        _check(self.lib.revs_reliability_sharded(self._h, feeder, kind, len(rows),
+                                                 rows.ctypes.data_as(C.POINTER(C.c_int32)), _dp(sc), vset,
+                                                 _dp(Pp), _dp(out)))
         return out
 
     # ---- residual all-reduce over the GPUs of the box (peer-memory mailboxes, see include/revs_admm.h)

@@ -35,6 +35,20 @@ enum ContractOut : int {
     kOutScaled = 3       // out[m*ldo + t] = scale[m] * acc
 };
 
+// All-gather fused into the contraction epilogue (one feeder row-partitioned over the GPUs of a box): every output
+// element is stored into the gather buffer of EVERY rank (peer-mapped memory, NVLink stores) at the rows this rank
+// owns; the last CTA of the kernel then raises this rank's flag in every peer's buffer (system-scope release).
+constexpr int kGatherMaxPeers = 16;
+struct GatherDev {
+    double* out[kGatherMaxPeers];                  // payload of every rank's gather buffer (out[rank] is local)
+    unsigned long long* flag[kGatherMaxPeers];     // flag[r] + my rank: my arrival flag in rank r's buffer
+    unsigned* ticket;                              // local CTA counter (zero before the launch)
+    unsigned long long seq;                        // value of this exchange
+    int world, rank;
+    int row_base;                                  // first gathered row this rank owns
+    int64_t ldo;                                   // leading dimension of the gathered output
+};
+
 // Batched contraction problem: C_f = A_f (M_f x K_f) * B_f^T (T x K_f).
 struct ContractProblem {
     const double* A; int lda; int M; int K;
@@ -42,6 +56,7 @@ struct ContractProblem {
     double* out; int64_t ldo;
     const double* scale;                 // per-row, kOutScaled only
     const int* col_status;               // optional [T]: columns with status != 0 are skipped
+    const GatherDev* gather;             // optional: node-major outputs go to every rank's gather buffer instead of `out`
 };
 
 struct ContractTile { int problem; int row0; };

@@ -153,11 +153,49 @@ contract_f64_kernel(const ContractProblem* __restrict__ problems,
                 } else {
                     if (mode == kOutVoltage) v = sqrt(v2 - v);
                     else if (mode == kOutScaled) v = sc * v;
-                    pb.out[(size_t)row * pb.ldo + col] = v;
+                    if (pb.gather) {
+                        // fused all-gather: the element goes to every rank's buffer over NVLink
+                        const GatherDev& G = *pb.gather;
+                        const size_t at = (size_t)(G.row_base + row) * G.ldo + col;
+                        for (int r = 0; r < G.world; ++r) G.out[r][at] = v;
+                    } else {
+                        pb.out[(size_t)row * pb.ldo + col] = v;
+                    }
                 }
             }
         }
     }
+    if (pb.gather) {
+        // every thread makes its peer stores visible system-wide, the last CTA of the launch raises the arrival flags
+        const GatherDev& G = *pb.gather;
+        __shared__ unsigned s_last;
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) s_last = atomicAdd(G.ticket, 1u) == gridDim.x * gridDim.y - 1 ? 1u : 0u;
+        __syncthreads();
+        if (s_last && tid < G.world) {
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(G.flag[tid] + G.rank), "l"(G.seq) : "memory");
+        }
+    }
+}
+
+// waits until every rank's arrival flag in THIS rank's gather buffer carries `seq` (one warp; ~10 s timeout)
+__global__ void gather_wait_kernel(const unsigned long long* flags, int world, unsigned long long seq, int* timeout) {
+    const int r = threadIdx.x;
+    if (r >= world) return;
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned long long v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + r) : "memory");
+        if (v >= seq) break;
+        if (clock64() - t0 > 20000000000ll) { atomicExch(timeout, 1); break; }
+    }
+}
+
+cudaError_t launch_gather_wait(const unsigned long long* flags, int world, unsigned long long seq, int* timeout, cudaStream_t s) {
+    gather_wait_kernel<<<1, 32, 0, s>>>(flags, world, seq, timeout);
+    return cudaGetLastError();
 }
 
 // Tile shape by horizon: T<=24 (the reference's hourly day) is HBM-bound -> tall, narrow

@@ -254,6 +254,8 @@ int contract_tile_rows(int T);
 cudaError_t launch_contract(const ContractProblem* d_problems, const ContractTile* d_tiles, int n_tiles,
                             int T, int mode, double v2, cudaStream_t stream);
 
+cudaError_t launch_gather_wait(const unsigned long long* flags, int world, unsigned long long seq, int* timeout, cudaStream_t s);
+
 // ---- screen_bf16.cu
 int screen_tile_rows();
 cudaError_t launch_to_bf16(const double* in, void* out, size_t n, cudaStream_t s);

@@ -169,6 +169,15 @@ struct revs_solver {
     int64_t nt_ws_stride = 0;
     int n_newton_cols = 0;
     size_t nt_sig = 0;
+    // one feeder's reliability check row-partitioned over the GPUs of the box (revs_gather_* / revs_reliability_sharded)
+    double* d_gather = nullptr;                // this rank's gather buffer: payload [gather_cap] + kGatherMaxPeers arrival flags
+    int64_t gather_cap = 0;
+    double* peer_gather[kGatherMaxPeers] = {}; // every rank's buffer as mapped into this process
+    int gather_world = 1, gather_rank = 0;
+    unsigned long long gather_seq = 0;         // advanced by every sharded call on every rank alike
+    GatherDev* d_gather_dev = nullptr;
+    unsigned* d_gather_ticket = nullptr;
+    int* d_gather_timeout = nullptr;
     bool use_warp_kernel = true;               // class 0: one warp per small column (utility_qp_warp.cu)
     bool overlap_home = true;                  // home solve on its own (low priority) stream beside the utility kernels
     bool screen = true;                        // BF16 screening + exact recheck instead of the FP64 contraction in the loop
@@ -1105,6 +1114,12 @@ void free_all(revs_solver* s) {
                     s->d_nt_ws, s->d_nt_ws4, s->d_nt_ws2};
     for (int r = 0; r < kMaxPeers; ++r)
         if (s->peer_box[r] && s->peer_box[r] != s->d_mailbox) cudaIpcCloseMemHandle(s->peer_box[r]);
+    for (int r = 0; r < kGatherMaxPeers; ++r)
+        if (s->peer_gather[r] && s->peer_gather[r] != s->d_gather) cudaIpcCloseMemHandle(s->peer_gather[r]);
+    if (s->d_gather) cudaFree(s->d_gather);
+    if (s->d_gather_dev) cudaFree(s->d_gather_dev);
+    if (s->d_gather_ticket) cudaFree(s->d_gather_ticket);
+    if (s->d_gather_timeout) cudaFree(s->d_gather_timeout);
     if (s->d_mailbox) cudaFree(s->d_mailbox);
     if (s->d_run_seq) cudaFree(s->d_run_seq);
     if (s->d_comm_timeout) cudaFree(s->d_comm_timeout);
@@ -2050,16 +2065,37 @@ int revs_utility_step(revs_solver* s, double kappa, double vset, double vlow, do
     return REVS_OK;
 }
 
-int revs_reliability(revs_solver* s, int feeder, int kind, int n_rows, const int32_t* rows, const double* scale,
-                     double vset, const double* P, double* out) {
-    if (!s || feeder < 0 || feeder >= s->nf || n_rows < 0 || !rows || !out) return fail(REVS_ERR_ARG, "bad arguments");
+}  // extern "C"
+
+namespace {
+// sharded: this rank contracts only its block of the rows; the epilogue stores them into every rank's gather buffer
+int reliability_impl(revs_solver* s, int feeder, int kind, int n_rows_all, const int32_t* rows_all, const double* scale_all,
+                     double vset, const double* P, double* out, bool sharded) {
+    if (!s || feeder < 0 || feeder >= s->nf || n_rows_all < 0 || !rows_all || !out) return fail(REVS_ERR_ARG, "bad arguments");
+    int n_rows = n_rows_all, row_lo = 0;
+    const int32_t* rows = rows_all;
+    const double* scale = scale_all;
+    if (sharded) {
+        if (s->gather_world < 1 || !s->d_gather) return fail(REVS_ERR_ARG, "call revs_gather_export / revs_gather_attach first");
+        if ((int64_t)n_rows_all * s->T > s->gather_cap)
+            return fail(REVS_ERR_ARG, "gather buffer holds %lld doubles, %lld needed", (long long)s->gather_cap, (long long)n_rows_all * s->T);
+        if (!P) return fail(REVS_ERR_ARG, "the sharded check needs the schedule of the whole feeder on every rank");
+        // contiguous blocks of whole contraction tiles, so that no tile straddles two ranks
+        const int bm = contract_tile_rows(s->T);
+        const int tiles = (n_rows_all + bm - 1) / bm;
+        const int t_lo = (int)((int64_t)tiles * s->gather_rank / s->gather_world), t_hi = (int)((int64_t)tiles * (s->gather_rank + 1) / s->gather_world);
+        row_lo = std::min(n_rows_all, t_lo * bm);
+        n_rows = std::min(n_rows_all, t_hi * bm) - row_lo;
+        rows = rows_all + row_lo;
+        scale = scale_all ? scale_all + row_lo : nullptr;
+    }
     if (kind != REVS_REL_VOLTAGE && kind != REVS_REL_FLOW && kind != REVS_REL_DROP) return fail(REVS_ERR_ARG, "bad kind");
     const Tree& t = s->trees[feeder];
     if (!t.d_parent) return fail(REVS_ERR_ARG, "feeder %d has no tree (call revs_set_feeder_tree)", feeder);
     if (!P && s->k == 0) return fail(REVS_ERR_ARG, "no schedule given and no ADMM result available");
-    for (int i = 0; i < n_rows; ++i)
-        if (rows[i] < 0 || rows[i] >= t.n_nodes) return fail(REVS_ERR_ARG, "rows[%d] out of range", i);
-    if (n_rows == 0) return REVS_OK;
+    for (int i = 0; i < n_rows_all; ++i)
+        if (rows_all[i] < 0 || rows_all[i] >= t.n_nodes) return fail(REVS_ERR_ARG, "rows[%d] out of range", i);
+    if (n_rows_all == 0) return REVS_OK;
     CU(cudaSetDevice(s->device));
     const FeederDev& fd = s->feeders[feeder];
     const int T = s->T;
@@ -2081,7 +2117,7 @@ int revs_reliability(revs_solver* s, int feeder, int kind, int n_rows, const int
         }                                                                                \
     } while (0)
     TRYR(dalloc(&d_rows, (size_t)n_rows));
-    TRYR(cudaMemcpy(d_rows, rows, sizeof(int) * n_rows, cudaMemcpyHostToDevice));
+    if (n_rows) TRYR(cudaMemcpy(d_rows, rows, sizeof(int) * n_rows, cudaMemcpyHostToDevice));
     TRYR(dalloc(&d_S, (size_t)n_rows * fd.np));
     TRYR(dalloc(&d_Pt, (size_t)T * fd.np));
     TRYR(dalloc(&d_out, (size_t)n_rows * T));
@@ -2091,7 +2127,9 @@ int revs_reliability(revs_solver* s, int feeder, int kind, int n_rows, const int
         TRYR(cudaMemcpy(d_P, P, sizeof(double) * fd.n * T, cudaMemcpyHostToDevice));
         src = d_P;
     }
-    if (kind == REVS_REL_FLOW) {
+    if (n_rows == 0) {
+        // (more ranks than tiles: this rank only signals and waits)
+    } else if (kind == REVS_REL_FLOW) {
         TRYR(launch_sens_flow(t.d_parent, d_rows, t.d_res_node, n_rows, fd.n, d_S, fd.np, s->sU));
         if (scale) {
             TRYR(dalloc(&d_scale, (size_t)n_rows));
@@ -2101,25 +2139,117 @@ int revs_reliability(revs_solver* s, int feeder, int kind, int n_rows, const int
         TRYR(launch_sens_voltage(t.d_parent, t.d_cumr, d_rows, t.d_res_node, n_rows, fd.n, d_S, fd.np, s->sU));
     }
     TRYR(launch_to_time_major(src, fd.n, T, d_Pt, fd.np, s->sU));
+    unsigned long long* my_flags = sharded ? reinterpret_cast<unsigned long long*>(s->d_gather + 2 * s->gather_cap) : nullptr;
+    size_t half = 0;           // the payload is double-buffered by the parity of the exchange: a peer may still be reading the last one
+    if (sharded) {
+        GatherDev G{};
+        G.seq = ++s->gather_seq;
+        half = (size_t)(G.seq & 1ull) * (size_t)s->gather_cap;
+        for (int r = 0; r < s->gather_world; ++r) {
+            G.out[r] = s->peer_gather[r] + half;
+            G.flag[r] = reinterpret_cast<unsigned long long*>(s->peer_gather[r] + 2 * s->gather_cap);
+        }
+        G.ticket = s->d_gather_ticket;
+        G.world = s->gather_world; G.rank = s->gather_rank;
+        G.row_base = row_lo;
+        G.ldo = T;
+        TRYR(cudaMemcpyAsync(s->d_gather_dev, &G, sizeof G, cudaMemcpyHostToDevice, s->sU));
+        TRYR(cudaMemsetAsync(s->d_gather_ticket, 0, sizeof(unsigned), s->sU));
+        TRYR(cudaMemsetAsync(s->d_gather_timeout, 0, sizeof(int), s->sU));
+    }
     {
-        ContractProblem pb{d_S, fd.np, n_rows, fd.np, d_Pt, fd.np, d_out, T, d_scale, nullptr};
+        ContractProblem pb{d_S, fd.np, n_rows, fd.np, d_Pt, fd.np, d_out, T, d_scale, nullptr, sharded ? s->d_gather_dev : nullptr};
         std::vector<ContractTile> tiles;
         const int bm = contract_tile_rows(T);
         for (int r0 = 0; r0 < n_rows; r0 += bm) tiles.push_back(ContractTile{0, r0});
         TRYR(dalloc(&d_prob, (size_t)1));
         TRYR(cudaMemcpy(d_prob, &pb, sizeof pb, cudaMemcpyHostToDevice));
         TRYR(dalloc(&d_tiles, tiles.size()));
-        TRYR(cudaMemcpy(d_tiles, tiles.data(), tiles.size() * sizeof(ContractTile), cudaMemcpyHostToDevice));
+        if (!tiles.empty()) TRYR(cudaMemcpy(d_tiles, tiles.data(), tiles.size() * sizeof(ContractTile), cudaMemcpyHostToDevice));
         int mode = kind == REVS_REL_VOLTAGE ? kOutVoltage : (kind == REVS_REL_FLOW ? kOutScaled : kOutNodeMajor);
         TRYR(launch_contract(d_prob, d_tiles, (int)tiles.size(), T, mode, vset * vset, s->sU));
     }
-    TRYR(cudaMemcpyAsync(out, d_out, sizeof(double) * n_rows * T, cudaMemcpyDeviceToHost, s->sU));
-    TRYR(cudaStreamSynchronize(s->sU));
+    if (sharded) {
+        if (n_rows == 0) {
+            // nothing contracted here: raise the arrival flags from the host side of this stream
+            for (int r = 0; r < s->gather_world; ++r)
+                TRYR(cudaMemcpyAsync(reinterpret_cast<unsigned long long*>(s->peer_gather[r] + 2 * s->gather_cap) + s->gather_rank, &s->gather_seq,
+                                     sizeof(unsigned long long), cudaMemcpyHostToDevice, s->sU));
+        }
+        TRYR(launch_gather_wait(my_flags, s->gather_world, s->gather_seq, s->d_gather_timeout, s->sU));
+        int to = 0;
+        TRYR(cudaMemcpyAsync(&to, s->d_gather_timeout, sizeof(int), cudaMemcpyDeviceToHost, s->sU));
+        TRYR(cudaMemcpyAsync(out, s->d_gather + half, sizeof(double) * n_rows_all * T, cudaMemcpyDeviceToHost, s->sU));
+        TRYR(cudaStreamSynchronize(s->sU));
+        if (to) { cleanup(); return fail(REVS_ERR_CUDA, "a peer GPU did not deliver its rows within 10 s (rank %d of %d)", s->gather_rank, s->gather_world); }
+    } else {
+        TRYR(cudaMemcpyAsync(out, d_out, sizeof(double) * n_rows * T, cudaMemcpyDeviceToHost, s->sU));
+        TRYR(cudaStreamSynchronize(s->sU));
+    }
 #undef TRYR
-    s->stats.kernel_launches += 3;
+    s->stats.kernel_launches += 3 + (sharded ? 1 : 0);
     s->stats.gemm_launches += 1;
     cleanup();
     return rc;
+}
+}  // namespace
+
+extern "C" {
+
+int revs_reliability(revs_solver* s, int feeder, int kind, int n_rows, const int32_t* rows, const double* scale,
+                     double vset, const double* P, double* out) {
+    return reliability_impl(s, feeder, kind, n_rows, rows, scale, vset, P, out, false);
+}
+
+int revs_reliability_sharded(revs_solver* s, int feeder, int kind, int n_rows, const int32_t* rows, const double* scale,
+                             double vset, const double* P, double* out) {
+    return reliability_impl(s, feeder, kind, n_rows, rows, scale, vset, P, out, true);
+}
+
+int revs_gather_export(revs_solver* s, int64_t capacity_doubles, void* handle64) {
+    if (!s || !handle64 || capacity_doubles <= 0) return fail(REVS_ERR_ARG, "bad arguments");
+    CU(cudaSetDevice(s->device));
+    for (int r = 0; r < kGatherMaxPeers; ++r) {
+        if (s->peer_gather[r] && s->peer_gather[r] != s->d_gather) cudaIpcCloseMemHandle(s->peer_gather[r]);
+        s->peer_gather[r] = nullptr;
+    }
+    if (s->d_gather) { cudaFree(s->d_gather); s->d_gather = nullptr; }
+    // two payload halves (alternating exchanges) + arrival flags in one allocation (one IPC handle); cudaMalloc'ed memory is what cudaIpcGetMemHandle exports
+    const size_t bytes = (size_t)2 * capacity_doubles * sizeof(double) + kGatherMaxPeers * sizeof(unsigned long long);
+    CU(cudaMalloc(&s->d_gather, bytes));
+    CU(cudaMemset(s->d_gather, 0, bytes));
+    s->gather_cap = capacity_doubles;
+    if (!s->d_gather_dev) {
+        CU(dalloc(&s->d_gather_dev, (size_t)1));
+        CU(dalloc(&s->d_gather_ticket, (size_t)1));
+        CU(dalloc(&s->d_gather_timeout, (size_t)1));
+    }
+    s->gather_world = 1; s->gather_rank = 0; s->gather_seq = 0;
+    s->peer_gather[0] = s->d_gather;
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, s->d_gather));
+    memcpy(handle64, &h, sizeof h);
+    return REVS_OK;
+}
+
+int revs_gather_attach(revs_solver* s, int world, int rank, const void* handles) {
+    if (!s || !handles || world < 1 || world > kGatherMaxPeers || rank < 0 || rank >= world)
+        return fail(REVS_ERR_ARG, "bad arguments (world 1..%d)", kGatherMaxPeers);
+    if (!s->d_gather) return fail(REVS_ERR_ARG, "call revs_gather_export first");
+    CU(cudaSetDevice(s->device));
+    for (int r = 0; r < kGatherMaxPeers; ++r) s->peer_gather[r] = nullptr;
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) { s->peer_gather[r] = s->d_gather; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)handles + (size_t)r * sizeof h, sizeof h);
+        void* ptr = nullptr;
+        CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        s->peer_gather[r] = reinterpret_cast<double*>(ptr);
+    }
+    s->gather_world = world;
+    s->gather_rank = rank;
+    s->gather_seq = 0;
+    return REVS_OK;
 }
 
 int revs_contract(int device, int M, int K, int T, const double* A, const double* B, double* C) {

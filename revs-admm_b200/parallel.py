@@ -57,6 +57,37 @@ def attach_peers(solver):
     return True
 
 
+def attach_gather(solver, capacity_doubles):
+    """Prepare `solver` for reliability_sharded(): every rank allocates its gather buffer (room for
+    `capacity_doubles` = rows x T outputs), the IPC handles travel over torch.distributed, every rank maps every
+    buffer.  Afterwards each rank contracts only its block of the rows of a feeder and the contraction kernel
+    itself stores the result into all buffers over NVLink (include/revs_admm.h: revs_gather_*).  Single rank:
+    the buffer is attached to itself, the call degenerates to the plain check."""
+    import torch
+    import torch.distributed as dist
+    mine_raw = solver.gather_export(capacity_doubles)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        solver.gather_attach(1, 0, mine_raw)
+        return 1
+    world, rank = dist.get_world_size(), dist.get_rank()
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    mine = torch.frombuffer(bytearray(mine_raw), dtype=torch.uint8).to(dev)
+    got = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(got, mine)
+    solver.gather_attach(world, rank, b"".join(bytes(t.cpu().numpy().tobytes()) for t in got))
+    dist.barrier()                      # every buffer is zeroed and mapped before anyone stores into it
+    return world
+
+
+def row_block(n_rows, tile_rows, world, rank):
+    """Rows [lo, hi) of a row-partitioned contraction that rank `rank` of `world` owns: contiguous blocks of whole
+    tiles (csrc/revs_capi.cu: reliability_impl uses the same rule)."""
+    tiles = (n_rows + tile_rows - 1) // tile_rows
+    lo = min(n_rows, (tiles * rank // world) * tile_rows)
+    hi = min(n_rows, (tiles * (rank + 1) // world) * tile_rows)
+    return lo, hi
+
+
 def residuals(total_sums, kappa):
     sp, sd, cnt = total_sums
     return float(np.sqrt(sp / cnt)), float(kappa * np.sqrt(sd / cnt))

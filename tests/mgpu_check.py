@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Multi-GPU check of the global stopping rule (run on a box with >= 2 B200s; not collected by pytest):
+"""Multi-GPU check of the global stopping rule and of the row-partitioned reliability check (run on a box with
+>= 2 B200s; not collected by pytest):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_check.py
 
@@ -21,7 +22,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import revs_admm_b200 as R  # noqa: E402
 from revs_admm_b200.feeder import synthetic_feeder, synthetic_homes, synthetic_tariff  # noqa: E402
-from revs_admm_b200.parallel import allreduce_sums, attach_peers, residuals, run_admm  # noqa: E402
+from revs_admm_b200.parallel import allreduce_sums, attach_gather, attach_peers, residuals, run_admm  # noqa: E402
 
 
 def main():
@@ -62,19 +63,43 @@ def main():
     with fresh() as s:
         s.admm_begin(**kw)
         loc = [allreduce_sums(s.admm_step(), dev) for _ in range(3)]
+    # (3) one feeder's reliability check with the rows partitioned over the ranks, all-gather fused into the contraction
+    # kernel (revs_reliability_sharded): every rank must end with the complete result of the single-GPU check
+    big = synthetic_feeder(1500, seed=4242, r_secondary=2e-4)          # the same feeder on every rank
+    Pb = np.random.default_rng(7).random((1500, T)) * 3.0
+    rows = np.arange(big.n_nodes, dtype=np.int32)
+    with R.Solver([1500], T, device=local) as s:
+        s.set_feeder_tree(0, big.parent, big.r, big.res_node)
+        full_v = s.reliability(0, R.REVS_REL_VOLTAGE, rows, vset=1.03, P=Pb)
+        full_f = s.reliability(0, R.REVS_REL_FLOW, rows, P=Pb)
+        assert attach_gather(s, len(rows) * T) == world
+        shard_ok = True
+        for rep in range(3):                                            # repeated exchanges (alternating payload halves)
+            sh_v = s.reliability_sharded(0, R.REVS_REL_VOLTAGE, rows, Pb * (1.0 + 0.0 * rep), vset=1.03)
+            sh_f = s.reliability_sharded(0, R.REVS_REL_FLOW, rows, Pb)
+            shard_ok = shard_ok and np.array_equal(sh_v, full_v) and np.array_equal(sh_f, full_f)
+        few = s.reliability_sharded(0, R.REVS_REL_DROP, rows[:5], Pb)   # fewer tiles than ranks: some ranks only signal and wait
+        shard_ok = shard_ok and np.array_equal(few, s.reliability(0, R.REVS_REL_DROP, rows[:5], P=Pb))
+        dist.barrier()
     its = [torch.zeros(3, dtype=torch.int64, device=dev) for _ in range(world)]
     dist.all_gather(its, torch.tensor([own, it_ref, it_peer], dtype=torch.int64, device=dev))
     its = [t.tolist() for t in its]
-    ok = all(t[1] == its[0][1] and t[2] == its[0][1] for t in its)
-    ok = ok and all(np.array_equal(ref[k], peer[k]) for k in ("P_sch", "P_ev", "diff"))
-    ok = ok and all(np.allclose(a, b, rtol=1e-12, atol=0) for a, b in zip(sums, loc))
+    checks = [all(t[1] == its[0][1] and t[2] == its[0][1] for t in its),
+              all(np.array_equal(ref[k], peer[k]) for k in ("P_sch", "P_ev", "diff")),
+              all(np.allclose(a, b, rtol=1e-12, atol=1e-18) for a, b in zip(sums, loc)),      # (iteration 2 of a loose network: sums at rounding level)
+              bool(shard_ok)]
+    ok = all(checks)
+    det = [torch.zeros(4, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(det, torch.tensor([int(c) for c in checks], dtype=torch.int64, device=dev))
+    det = [t.tolist() for t in det]
     r, d = residuals(sums[-1], kw["kappa"])
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(json.dumps({"mgpu_check": "ok" if int(flag.item()) else "FAILED", "world": world,
                           "iterations_per_rank [own rule, nccl all-reduce, peer mailboxes]": its,
-                          "residuals_after_3_iterations": [r, d], "final_residuals": [st["primal_residual"], st["dual_residual"]]}))
+                          "residuals_after_3_iterations": [r, d], "final_residuals": [st["primal_residual"], st["dual_residual"]],
+                          "checks_per_rank [same iterations, same schedules, global sums == nccl sums, row-partitioned reliability == single GPU]": det}))
     dist.destroy_process_group()
     sys.exit(0 if int(flag.item()) else 1)
 

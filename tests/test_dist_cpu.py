@@ -98,3 +98,18 @@ def test_two_rank_global_convergence_matches_single_process():
     assert iters == it0 and iters < 30
     assert np.allclose(hist, h0, rtol=1e-9, atol=1e-14)
     assert np.array_equal(st.out["P_sch"], np.vstack([P0, P1]))
+
+
+def test_row_blocks_partition_the_rows_by_whole_tiles():
+    """Row-partitioned contraction of one feeder (revs_reliability_sharded): the blocks of the ranks tile the rows,
+    are contiguous, and never cut a contraction tile."""
+    from revs_admm_b200.parallel import row_block
+    for n_rows, tile, world in [(2100, 64, 8), (5, 64, 4), (64, 64, 2), (1000, 128, 3), (0, 64, 2), (14100, 64, 16)]:
+        blocks = [row_block(n_rows, tile, world, r) for r in range(world)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == n_rows
+        for (lo, hi), (lo2, _) in zip(blocks, blocks[1:]):
+            assert hi == lo2 and lo <= hi
+        for lo, hi in blocks:
+            assert lo % tile == 0 and (hi % tile == 0 or hi == n_rows)
+        sizes = [hi - lo for lo, hi in blocks]
+        assert max(sizes) - min(sizes) <= tile or n_rows < tile * world

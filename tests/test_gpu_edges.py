@@ -405,3 +405,26 @@ def test_tree_kernel_equals_dense_kernels(gpu_lib, sizes, T, vhigh):
     assert outs[0]["stats"]["max_working_set"] >= 2
     if T != 12:                                      # (T = 12: working sets beyond 16 rows go on to the dense kernels)
         assert outs[0]["stats"]["gemm_launches"] < outs[1]["stats"]["gemm_launches"]
+
+
+def test_sharded_reliability_on_one_rank_equals_plain_check(gpu_lib):
+    """revs_reliability_sharded with a world of one (the gather buffer attached to itself): the contraction epilogue
+    stores through the gather path, the result equals revs_reliability bit for bit.  (Two and more ranks:
+    tests/mgpu_check.py on a multi-GPU box.)"""
+    from revs_admm_b200.feeder import synthetic_feeder
+    from revs_admm_b200.parallel import attach_gather
+    T = 24
+    t = synthetic_feeder(700, seed=12, r_secondary=2e-4)
+    P = np.random.default_rng(1).random((700, T)) * 2.0
+    rows = np.arange(t.n_nodes, dtype=np.int32)
+    with gpu_lib.Solver([700], T) as s:
+        s.set_feeder_tree(0, t.parent, t.r, t.res_node)
+        with pytest.raises(gpu_lib.RevsError):
+            s.reliability_sharded(0, gpu_lib.REVS_REL_DROP, rows, P)        # no gather buffer yet
+        assert attach_gather(s, len(rows) * T) == 1
+        for kind in (gpu_lib.REVS_REL_VOLTAGE, gpu_lib.REVS_REL_FLOW, gpu_lib.REVS_REL_DROP):
+            a = s.reliability(0, kind, rows, vset=1.03, P=P)
+            for _ in range(2):
+                assert np.array_equal(s.reliability_sharded(0, kind, rows, P, vset=1.03), a)
+        with pytest.raises(gpu_lib.RevsError):
+            s.reliability_sharded(0, gpu_lib.REVS_REL_DROP, np.arange(t.n_nodes, dtype=np.int32).repeat(2), P)   # beyond the buffer
