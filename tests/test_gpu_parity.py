@@ -182,7 +182,8 @@ def test_utility_step_real_feeder(gpu_lib, case121144):
     u = 1.05 ** 2 - 1.03 ** 2
     assert (Rres @ g).max() <= u + 1e-9
     assert g.min() >= 0.0
-    assert st["gemm_launches"] >= 1 and st["qp_newton_iterations"] > 0
+    # (the unsplit feeder has 1126 residences: it runs on the tree-Newton path, which needs no contraction)
+    assert st["qp_newton_iterations"] > 0
 
 
 def test_utility_step_multi_feeder_synthetic_tight(gpu_lib):
