@@ -21,7 +21,7 @@
  *   revs_solve_individual                         lpsolver.py:430-460 solve_residence()
  *   revs_reliability                              drawing.py:29-78    compute_flows(),
  *                                                                     compute_voltage()
- *   revs_get_results / revs_get_schedule          lpsolver.py:289-290 return diff,P_sch,S,C
+ *   revs_get_results / revs_get_schedule(_ld)     lpsolver.py:289-290 return diff,P_sch,S,C
  *   revs_set_option / revs_get_stats / revs_version / revs_last_error / revs_device_count /
  *   revs_reliability_sharded / revs_gather_export / revs_gather_attach
  *                                                 drawing.py:29-78 for one feeder over several GPUs (rows partitioned)
@@ -145,6 +145,11 @@ int revs_get_results(const revs_solver* s, double* P_sch, double* P_ev, double* 
  * the per-home inputs the caller already holds, so a third of the bytes of revs_get_results cross PCIe. */
 int revs_get_schedule(const revs_solver* s, double* P_sch, uint64_t* hour_mask, int mask_words,
                       double* diff, int diff_rows);
+/* revs_get_schedule with a row stride for diff: row k of the convergence values goes to diff + k * diff_ld
+ * (diff_ld >= H, in doubles), so that several solvers sharing one GPU write their column blocks of one
+ * [iterations, all homes] array (lpsolver.py:284 keeps one such array) straight from the device, without a host copy. */
+int revs_get_schedule_ld(const revs_solver* s, double* P_sch, uint64_t* hour_mask, int mask_words,
+                         double* diff, int diff_rows, int64_t diff_ld);
 
 /* Utility-side iterates of the last run: P_est [H,T], Gamma [H,T]. */
 int revs_get_estimate(const revs_solver* s, double* P_est, double* Gamma);

@@ -57,6 +57,7 @@ SIGNATURES = {
     "revs_utility_step": ([_P, C.c_double, C.c_double, C.c_double, C.c_double, _D, _D, _D, _D, _D, _D], C.c_int),
     "revs_get_results": ([_P, _D, _D, _D, _D, C.c_int], C.c_int),
     "revs_get_schedule": ([_P, _D, C.POINTER(C.c_uint64), C.c_int, _D, C.c_int], C.c_int),
+    "revs_get_schedule_ld": ([_P, _D, C.POINTER(C.c_uint64), C.c_int, _D, C.c_int, C.c_int64], C.c_int),
     "revs_get_estimate": ([_P, _D, _D], C.c_int),
     "revs_solve_individual": ([_P, _D, _D, _D], C.c_int),
     "revs_reliability": ([_P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), _D, C.c_double, _D, _D], C.c_int),
@@ -304,10 +305,17 @@ class Solver:
             raise ValueError("out['P_sch'] must be a C-contiguous float64 [H, T] array")
         if M.shape != (H, W) or M.dtype != np.uint64 or not M.flags.c_contiguous:
             raise ValueError("out['mask'] must be a C-contiguous uint64 [H, ceil(T/64)] array")
-        if D is not None and (D.ndim != 2 or D.shape[1] != H or D.dtype != np.float64 or not D.flags.c_contiguous):
-            raise ValueError("out['diff'] must be a C-contiguous float64 [rows, H] array")
-        _check(self.lib.revs_get_schedule(self._h, _dp(P), M.ctypes.data_as(C.POINTER(C.c_uint64)), W, _dp(D),
-                                          0 if D is None else D.shape[0]))
+        # diff may be a column block of a wider [rows, all homes] array (rows strided, elements contiguous): the
+        # library writes it in place (revs_get_schedule_ld)
+        ld = H
+        if D is not None:
+            if D.ndim != 2 or D.shape[1] != H or D.dtype != np.float64 or (H > 1 and D.strides[1] != 8) or \
+                    (D.shape[0] > 1 and (D.strides[0] % 8 or D.strides[0] < 8 * H)):
+                raise ValueError("out['diff'] must be a float64 [rows, H] array with contiguous rows")
+            ld = D.strides[0] // 8 if D.shape[0] > 1 else H
+        dptr = _dp(D)
+        _check(self.lib.revs_get_schedule_ld(self._h, _dp(P), M.ctypes.data_as(C.POINTER(C.c_uint64)), W, dptr,
+                                             0 if D is None else D.shape[0], ld))
         return dict(P_sch=P, mask=M, diff=D)
 
     def estimate(self):

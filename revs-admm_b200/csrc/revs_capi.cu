@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cmath>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -96,6 +97,14 @@ inline double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// Host-to-device uploads of the solvers that share one GPU take the PCIe link one at a time (parallel.PipelinedSolver
+// runs one host thread per pipeline): the host-side preparation of every pipeline runs concurrently, and the pipeline
+// whose inputs are complete starts computing while the next one is still uploading.
+std::mutex& upload_mutex(int device) {
+    static std::mutex mu[64];
+    return mu[device & 63];
+}
+
 }  // namespace
 
 struct revs_solver {
@@ -123,6 +132,7 @@ struct revs_solver {
     // tuning / debug options, read ONCE (environment at revs_create, revs_set_option afterwards): nothing in the
     // solve path calls getenv
     int warp_m_max = 0, warp_m_max_big = 0;    // warm working sets above this size start in CTA class 1
+    int warp_ctas = 0;                         // REVS_WARP_CTAS: CTAs per SM of the persistent warp kernels (0: as many as fit)
     bool use_fast = true;                      // one-row register kernel for the small zones
     bool debug = false, debug_host = false;    // REVS_DEBUG / REVS_DEBUG_HOST: per-round / per-solve lines on stderr
     int trace_iter = -1, trace_round = -1;     // REVS_DEBUG_TRACE="<admm iteration>,<round>": per-column timeline of that round
@@ -928,7 +938,7 @@ int enqueue_round(revs_solver* s, QpParams& Q, int mode, const bool* use, const 
         // (sharing the SMs between two QP kernels slowed both down whenever it was measured): the groups of
         // long columns first, the many short columns of the small zones fill the tail
         s->stats.qp_warp_rounds++;
-        const int full = qp_warp_ctas_per_sm();
+        const int full = s->warp_ctas > 0 ? s->warp_ctas : qp_warp_ctas_per_sm();
         if (s->zg.n_big > 0) {                                    // zones of 257..320 residences: lists 13..16
             Q.list0 = kListBig;
             Q.nlists = kQpBuckets;
@@ -1291,6 +1301,7 @@ int revs_create(revs_solver** out, int device, int n_feeders, const int64_t* fee
         // zones above 128 residences: the same threshold (round 1 sent stored sets above 5 rows to the first CTA class, which
         // cost 8.5 of 21 ms per schedule on zones of 150..300 residences; measured, profiles/README_r02.md)
         s->warp_m_max_big = (e = getenv("REVS_WARP_M_MAX_BIG")) ? atoi(e) : s->warp_m_max;
+        if ((e = getenv("REVS_WARP_CTAS"))) s->warp_ctas = atoi(e);
         s->use_fast = !((e = getenv("REVS_NO_FAST")) && atoi(e));
         s->debug = getenv("REVS_DEBUG") != nullptr;
         s->debug_host = getenv("REVS_DEBUG_HOST") != nullptr;
@@ -1404,6 +1415,7 @@ int revs_set_feeder_tree(revs_solver* s, int feeder, int n_nodes, const int32_t*
 int revs_set_feeder_trees(revs_solver* s, const int64_t* node_off, const int32_t* parent, const double* r,
                           const int32_t* res_node) {
     if (!s || !node_off || !parent || !r || !res_node) return fail(REVS_ERR_ARG, "bad arguments");
+    const double th0 = now_ms();
     CU(cudaSetDevice(s->device));
     if (node_off[0] != 0) return fail(REVS_ERR_ARG, "node_off[0] must be 0");
     const int64_t total = node_off[s->nf];
@@ -1431,10 +1443,14 @@ int revs_set_feeder_trees(revs_solver* s, const int64_t* node_off, const int32_t
     }
     if (!s->d_pool_res) CU(dalloc(&s->d_pool_res, (size_t)s->Hp));
     if (!s->d_pool_off) CU(dalloc(&s->d_pool_off, (size_t)s->nf + 1));
-    CU(cudaMemcpyAsync(s->d_pool_parent, parent, sizeof(int) * total, cudaMemcpyHostToDevice, s->sU));
-    CU(cudaMemcpyAsync(s->d_pool_cumr, cumr.data(), sizeof(double) * total, cudaMemcpyHostToDevice, s->sU));
-    CU(cudaMemcpyAsync(s->d_pool_res, res_p.data(), sizeof(int) * s->Hp, cudaMemcpyHostToDevice, s->sU));
-    CU(cudaMemcpyAsync(s->d_pool_off, node_off, sizeof(int64_t) * (s->nf + 1), cudaMemcpyHostToDevice, s->sU));
+    const double th1 = now_ms();
+    {
+        std::lock_guard<std::mutex> link(upload_mutex(s->device));
+        CU(cudaMemcpyAsync(s->d_pool_parent, parent, sizeof(int) * total, cudaMemcpyHostToDevice, s->sU));
+        CU(cudaMemcpyAsync(s->d_pool_cumr, cumr.data(), sizeof(double) * total, cudaMemcpyHostToDevice, s->sU));
+        CU(cudaMemcpyAsync(s->d_pool_res, res_p.data(), sizeof(int) * s->Hp, cudaMemcpyHostToDevice, s->sU));
+        CU(cudaMemcpyAsync(s->d_pool_off, node_off, sizeof(int64_t) * (s->nf + 1), cudaMemcpyHostToDevice, s->sU));
+    }
     {
         bool any = false, moved = false;
         for (int f = 0; f < s->nf; ++f) {
@@ -1514,12 +1530,18 @@ int revs_set_feeder_trees(revs_solver* s, const int64_t* node_off, const int32_t
     }
     s->stats.kernel_launches++;
     s->rn2_valid = false;
-    return rebuild_tree_lists(s);
+    const double th2 = now_ms();
+    const int rc_lists = rebuild_tree_lists(s);
+    if (s->debug_host)
+        fprintf(stderr, "[revs host] set_feeder_trees: checks + cumulative resistances %.3f ms, copies + zone tables + sensitivity launch %.3f ms, lists %.3f ms\n",
+                th1 - th0, th2 - th1, now_ms() - th2);
+    return rc_lists;
 }
 
 int revs_set_homes(revs_solver* s, const double* load, const uint8_t* has_ev, const double* rating,
                    const double* capacity, const double* initial, const int32_t* start, const int32_t* end) {
     if (!s || !load || !has_ev) return fail(REVS_ERR_ARG, "bad arguments");
+    const double th0 = now_ms();
     CU(cudaSetDevice(s->device));
     const int64_t H = s->H, Hp = s->Hp;
     // the per-home vectors go through one page-locked staging block in the padded layout, so
@@ -1552,6 +1574,9 @@ int revs_set_homes(revs_solver* s, const double* load, const uint8_t* has_ev, co
         }
     }
     int rc;
+    const double th1 = now_ms();
+    std::lock_guard<std::mutex> link(upload_mutex(s->device));     // held until the copies have landed
+    const double th2 = now_ms();
     if ((rc = h2d_homes(s, s->d_load, load, s->T))) return rc;
     CU(cudaMemcpyAsync(s->d_has_ev, ev, nd, cudaMemcpyHostToDevice, s->sU));
     CU(cudaMemcpyAsync(s->d_rating, rt, nd * sizeof(double), cudaMemcpyHostToDevice, s->sU));
@@ -1564,6 +1589,8 @@ int revs_set_homes(revs_solver* s, const double* load, const uint8_t* has_ev, co
     CU(cudaMemcpyAsync(s->d_nmax, nmax, nd * sizeof(int), cudaMemcpyHostToDevice, s->sU));
     CU(cudaStreamSynchronize(s->sU));
     (void)H;
+    if (s->debug_host)
+        fprintf(stderr, "[revs host] set_homes: staging %.3f ms, waiting for the link %.3f ms, copies %.3f ms\n", th1 - th0, th2 - th1, now_ms() - th2);
     s->homes_set = true;
     return REVS_OK;
 }
@@ -1910,8 +1937,9 @@ int revs_solve_admm(revs_solver* s, double kappa, int iter_max, double vset, dou
     return REVS_OK;
 }
 
-int revs_get_results(const revs_solver* s, double* P_sch, double* P_ev, double* SOC, double* diff, int diff_rows) {
+static int get_results_impl(const revs_solver* s, double* P_sch, double* P_ev, double* SOC, double* diff, int diff_rows, int64_t diff_ld) {
     if (!s) return fail(REVS_ERR_ARG, "null solver");
+    if (diff && diff_ld < s->H) return fail(REVS_ERR_ARG, "diff_ld must be at least the number of homes (%lld)", (long long)s->H);
     if (s->k == 0) return fail(REVS_ERR_ARG, "no ADMM iteration has run");
     if (diff && diff_rows < s->k)
         return fail(REVS_ERR_ARG, "diff holds %d rows but %d ADMM iterations have run", diff_rows, s->k);
@@ -1931,14 +1959,27 @@ int revs_get_results(const revs_solver* s, double* P_sch, double* P_ev, double* 
             const int nk = std::min(chunk, s->k - k0);
             for (int k = 0; k < nk; ++k)
                 CU(launch_pack_rows(s->d_diff + (size_t)(k0 + k) * s->Hp, s->d_stage + (size_t)k * s->H, s->d_hmap, s->H, 1, 0, s->sU));
-            CU(cudaMemcpyAsync(diff + (size_t)k0 * s->H, s->d_stage, (size_t)nk * s->H * sizeof(double), cudaMemcpyDeviceToHost, s->sU));
+            if (diff_ld == s->H)
+                CU(cudaMemcpyAsync(diff + (size_t)k0 * s->H, s->d_stage, (size_t)nk * s->H * sizeof(double), cudaMemcpyDeviceToHost, s->sU));
+            else      // rows of the caller's array are longer than this solver's homes (a column block of a shared array)
+                CU(cudaMemcpy2DAsync(diff + (size_t)k0 * diff_ld, (size_t)diff_ld * sizeof(double), s->d_stage, (size_t)s->H * sizeof(double),
+                                     (size_t)s->H * sizeof(double), (size_t)nk, cudaMemcpyDeviceToHost, s->sU));
         }
     }
     CU(cudaStreamSynchronize(s->sU));
     return REVS_OK;
 }
 
+int revs_get_results(const revs_solver* s, double* P_sch, double* P_ev, double* SOC, double* diff, int diff_rows) {
+    return get_results_impl(s, P_sch, P_ev, SOC, diff, diff_rows, s ? s->H : 0);
+}
+
 int revs_get_schedule(const revs_solver* s, double* P_sch, uint64_t* hour_mask, int mask_words, double* diff, int diff_rows) {
+    return revs_get_schedule_ld(s, P_sch, hour_mask, mask_words, diff, diff_rows, s ? s->H : 0);
+}
+
+int revs_get_schedule_ld(const revs_solver* s, double* P_sch, uint64_t* hour_mask, int mask_words, double* diff, int diff_rows,
+                         int64_t diff_ld) {
     if (!s) return fail(REVS_ERR_ARG, "null solver");
     if (s->k == 0) return fail(REVS_ERR_ARG, "no ADMM iteration has run");
     if (hour_mask && mask_words != (s->T + 63) / 64) return fail(REVS_ERR_ARG, "mask_words must be ceil(T / 64) = %d", (s->T + 63) / 64);
@@ -1950,7 +1991,7 @@ int revs_get_schedule(const revs_solver* s, double* P_sch, uint64_t* hour_mask, 
         const_cast<revs_solver*>(s)->stats.kernel_launches++;
         CU(cudaMemcpyAsync(hour_mask, d_mask, (size_t)s->H * mask_words * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->sU));
     }
-    return revs_get_results(s, P_sch, nullptr, nullptr, diff, diff_rows);
+    return get_results_impl(s, P_sch, nullptr, nullptr, diff, diff_rows, diff_ld);
 }
 
 int revs_get_estimate(const revs_solver* s, double* P_est, double* Gamma) {

@@ -48,7 +48,7 @@ namespace {
 constexpr int kWarpsPerCta = 4;
 constexpr int kCtasPerSm = 4;                // 16 resident columns per SM
 constexpr int kHW = kWW + 1;                 // leading dim of the per-warp 16x16 matrices
-constexpr int kCacheDoubles = 1024;          // per-warp cache of working rows of R
+constexpr int kCacheDoubles = 1024;          // per-warp cache of working rows of R (zones of up to 128 residences: 8 rows)
 constexpr double kArcMinW = 9.5367431640625e-07;
 constexpr int kPdasMaxW = 40;
 constexpr double kHessShiftW = 1e-12;
@@ -63,8 +63,8 @@ struct WarpSmemT {
     double L[kWW * kHW];      // Cholesky factor of the active sub-matrix
     double rows[CACHE];
 };
-// zones of up to 256 residences: 1024 doubles of cached working rows per warp (4 CTAs per SM);
-// 257..320 residences (NJ = 10, 3 CTAs per SM): 1536, i.e. at least four full rows
+// zones of up to 128 residences (NJ = 4, 4 CTAs per SM): 1024 doubles of cached working rows per warp;
+// larger zones (NJ >= 6, 2 CTAs per SM): REVS_WARP_CACHE_BIG doubles
 // CTAs per SM of the NJ >= 6 instantiations.  Measured on the reference-shaped population (profiles/README_r02.md):
 // at 4 (128 registers) and 3 (168) the kernels spill 130..570 bytes per thread into a 28 KB L1 and every phase of a column
 // runs twice as long; at 2 (255 registers, no spills) the step is 13 % faster in spite of half the resident warps.
@@ -74,8 +74,11 @@ struct WarpSmemT {
 #ifndef REVS_WARP_CTAS_BIG
 #define REVS_WARP_CTAS_BIG 2
 #endif
+#ifndef REVS_WARP_CACHE_BIG         // doubles of cached working rows per warp at NJ >= 6 (2 CTAs of 4 warps per SM): 20 KB = 13 / 10 / 8
+#define REVS_WARP_CACHE_BIG 2560    // rows of a zone of 192 / 256 / 320 residences, all rows of 97 % of the columns
+#endif
 template <int NJ> struct WarpCfg {
-    static constexpr int kCache = NJ <= 8 ? kCacheDoubles : 1536;
+    static constexpr int kCache = NJ <= 4 ? kCacheDoubles : REVS_WARP_CACHE_BIG;
     static constexpr int kCtas = NJ <= 8 ? (NJ <= 4 ? kCtasPerSm : REVS_WARP_CTAS_SMALL) : REVS_WARP_CTAS_BIG;
 };
 
@@ -166,23 +169,40 @@ __device__ __forceinline__ void solve_column(const QpParams& P, const int4 ent, 
     double zj[NJ], gj[NJ], g0[NJ], vub[NJ];
     unsigned inw = 0;                          // bit k: row lane+32k is in the working set
     unsigned candk = 0;                        // bit k: row lane+32k must be re-evaluated exactly
-    {
-        const float* v32 = P.v32_t ? P.v32_t + col : nullptr;
+    // (every load of the column is issued before the first value is used, with clamped indices instead of
+    // branches: one round trip to memory for the whole column, not one per slot)
+    if (P.v32_t) {
+        const float* v32 = P.v32_t + col;
+        float vf[NJ];
+#pragma unroll
+        for (int k = 0; k < NJ; ++k) {
+            const int jc = min(lane + 32 * k, n - 1);
+            zj[k] = z[jc];
+            gj[k] = g[jc];
+            vf[k] = v32[jc];
+        }
+#pragma unroll
+        for (int k = 0; k < NJ; ++k) {
+            const bool in = lane + 32 * k < n;
+            if (!in) { zj[k] = 0.0; gj[k] = 0.0; }
+            g0[k] = gj[k];
+            const double a = in ? (double)vf[k] : 0.0;
+            vub[k] = kScreenUp * a;
+            if (in && a > thr) candk |= 1u << k;
+        }
+    } else {
         const double* v64 = P.v_t + col;
 #pragma unroll
         for (int k = 0; k < NJ; ++k) {
-            const int j = lane + 32 * k;
-            const bool in = j < n;
-            zj[k] = in ? z[j] : 0.0;
-            gj[k] = in ? g[j] : 0.0;
+            const int jc = min(lane + 32 * k, n - 1);
+            zj[k] = z[jc];
+            gj[k] = g[jc];
+            vub[k] = v64[jc];
+        }
+#pragma unroll
+        for (int k = 0; k < NJ; ++k) {
+            if (lane + 32 * k >= n) { zj[k] = 0.0; gj[k] = 0.0; vub[k] = 0.0; }
             g0[k] = gj[k];
-            if (v32) {
-                const double a = in ? (double)v32[j] : 0.0;
-                vub[k] = kScreenUp * a;
-                if (in && a > thr) candk |= 1u << k;
-            } else {
-                vub[k] = in ? v64[j] : 0.0;
-            }
         }
     }
 
@@ -297,22 +317,21 @@ __device__ __forceinline__ void solve_column(const QpParams& P, const int4 ent, 
         const bool row = lane < m;
 
         // ---- working rows of R into shared memory (as many as fit)
+        // (cp.async, 16 bytes per request: all rows are in flight at once -- one L2 round trip for the whole
+        // working set instead of one per row; rows start on 128-byte boundaries, ld is a multiple of 16)
         const int ncache = min(m, kCacheD / ld);
         __syncwarp();
+        {
+            const int nchunk = (n + 1) >> 1;
 #pragma unroll 1
-        for (int a = 0; a < ncache; ++a) {
-            const double* src = R + (size_t)__shfl_sync(full, idx, a) * ld;
-            double tmp[NJ];
-#pragma unroll
-            for (int k = 0; k < NJ; ++k) {
-                const int j = lane + 32 * k;
-                tmp[k] = j < n ? src[j] : 0.0;
+            for (int a = 0; a < ncache; ++a) {
+                const double* src = R + (size_t)__shfl_sync(full, idx, a) * ld;
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(sm.rows + a * ld);
+                for (int ch = lane; ch < nchunk; ch += 32)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * ch), "l"(src + 2 * ch) : "memory");
             }
-#pragma unroll
-            for (int k = 0; k < NJ; ++k) {
-                const int j = lane + 32 * k;
-                if (j < n) sm.rows[a * ld + j] = tmp[k];
-            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncwarp();
         auto rowp = [&](int a) -> const double* {      // a is warp-uniform
@@ -612,11 +631,14 @@ __device__ __forceinline__ void solve_column(const QpParams& P, const int4 ent, 
         int ncand = 0;
         {
             const double* rmax = P.rmax + hoff;
+            double rm[NJ];
+#pragma unroll
+            for (int k = 0; k < NJ; ++k) rm[k] = rmax[min(lane + 32 * k, n - 1)];     // all in flight at once
 #pragma unroll
             for (int k = 0; k < NJ; ++k) {
                 const int j = lane + 32 * k;
                 if (j < n && !((inw >> k) & 1u)) {
-                    const double bnd = dp > 0.0 ? fma(rmax[j], dp, vub[k]) : vub[k];
+                    const double bnd = dp > 0.0 ? fma(rm[k], dp, vub[k]) : vub[k];
                     if (bnd - u > tol) { candk |= 1u << k; ++ncand; }
                     else vub[k] = bnd;
                 }
@@ -847,22 +869,34 @@ __global__ void __launch_bounds__(32 * kFastWarps, 4) utility_qp_fast_kernel(QpP
 
         double zj[NJ], rj[NJ], vub[NJ], gj[NJ];
         unsigned candk = 0;
-        {
-            const float* v32 = P.v32_t ? P.v32_t + col : nullptr;
+        if (P.v32_t) {                                   // (loads first, uses afterwards: see solve_column)
+            const float* v32 = P.v32_t + col;
+            float vf[NJ];
+#pragma unroll
+            for (int k = 0; k < NJ; ++k) {
+                const int jc = min(lane + 32 * k, n - 1);
+                zj[k] = z[jc];
+                vf[k] = v32[jc];
+            }
+#pragma unroll
+            for (int k = 0; k < NJ; ++k) {
+                const bool in = lane + 32 * k < n;
+                if (!in) zj[k] = 0.0;
+                const double a = in ? (double)vf[k] : 0.0;
+                vub[k] = kScreenUp * a;
+                if (in && a > thr) candk |= 1u << k;
+            }
+        } else {
             const double* v64 = P.v_t + col;
 #pragma unroll
             for (int k = 0; k < NJ; ++k) {
-                const int j = lane + 32 * k;
-                const bool in = j < n;
-                zj[k] = in ? z[j] : 0.0;
-                if (v32) {
-                    const double a = in ? (double)v32[j] : 0.0;
-                    vub[k] = kScreenUp * a;
-                    if (in && a > thr) candk |= 1u << k;
-                } else {
-                    vub[k] = in ? v64[j] : 0.0;
-                }
+                const int jc = min(lane + 32 * k, n - 1);
+                zj[k] = z[jc];
+                vub[k] = v64[jc];
             }
+#pragma unroll
+            for (int k = 0; k < NJ; ++k)
+                if (lane + 32 * k >= n) { zj[k] = 0.0; vub[k] = 0.0; }
         }
         auto pass_on = [&]() {                           // untouched: the general kernel redoes the column
             if (lane == 0) {
@@ -951,11 +985,14 @@ __global__ void __launch_bounds__(32 * kFastWarps, 4) utility_qp_fast_kernel(QpP
         {
             const double* rmax = P.rmax + hoff;
             int ncand = 0;
+            double rm[NJ];
+#pragma unroll
+            for (int k = 0; k < NJ; ++k) rm[k] = rmax[min(lane + 32 * k, n - 1)];
 #pragma unroll
             for (int k = 0; k < NJ; ++k) {
                 const int j = lane + 32 * k;
                 if (j < n && j != i0) {
-                    const double bnd = dp > 0.0 ? fma(rmax[j], dp, vub[k]) : vub[k];
+                    const double bnd = dp > 0.0 ? fma(rm[k], dp, vub[k]) : vub[k];
                     if (bnd - u > tol) { candk |= 1u << k; ++ncand; }
                     else vub[k] = bnd;
                 }

@@ -223,12 +223,15 @@ class PipelinedSolver:
 
     def schedule(self, trees, homes, cost, out=None, compact=False, **admm):
         """Host buffers in, host results out -- the whole path of lpsolver.solve_ADMM for this GPU's
-        zones.  Every pipeline runs upload -> solve -> download on its own thread; uploads and
-        downloads take the PCIe link one pipeline at a time (in pipeline order), so the copies of one
-        pipeline overlap the compute of the others instead of sharing the link three ways.
+        zones.  Every pipeline runs upload -> solve -> download on its own thread.  The host-side
+        preparation of the uploads (padded layouts, cumulative resistances) runs concurrently; the
+        copies themselves take the PCIe link one pipeline at a time (a per-device lock inside the
+        library), so a pipeline starts computing while the next one is still uploading, and the
+        downloads of the pipelines that finish first overlap the compute of the others.
         ``compact``: results come back as P_sch + charging bit masks + diff (Solver.schedule_compact;
         _cabi.expand_schedule rebuilds P_ev / SOC on request) -- a third of the D2H bytes."""
         import threading
+        import time
         if float(admm.get("tol", 0.0) or 0.0) > 0.0 and len(self.parts) > 1:
             raise ValueError("schedule() overlaps whole pipelines and cannot apply a global stopping rule; "
                              "use the set_* calls and solve_admm(tol=...) (lock-step) instead")
@@ -241,33 +244,45 @@ class PipelinedSolver:
             else:
                 out.update(P_ev=np.empty((H, T)), SOC=np.empty((H, T + 1)))
         D = out.get("diff")
-        turn = [threading.Event() for _ in range(len(self.parts) + 1)]
-        turn[0].set()
         d2h = threading.Lock()
+        trace = os.environ.get("REVS_DEBUG_E2E") is not None
+        t_origin = time.perf_counter()
+        marks = [None] * len(self.parts)
 
         def f(k):
             lo, hi = self.rows[k]
             a, b = self.cuts[k]
-            turn[k].wait()
-            try:
-                self.parts[k].set_feeder_trees(trees[a:b])
-                self.parts[k].set_homes(**{n: v[lo:hi] for n, v in homes.items()})
-                self.parts[k].set_tariff(cost)
-            finally:
-                turn[k + 1].set()
+            tm = [time.perf_counter()]
+            self.parts[k].set_feeder_trees(trees[a:b])
+            tm.append(time.perf_counter())
+            self.parts[k].set_homes(**{n: v[lo:hi] for n, v in homes.items()})
+            self.parts[k].set_tariff(cost)
+            tm.append(time.perf_counter())
             done = self.parts[k].solve_admm(**admm)
-            dbuf = self._diff_buf(k, iters) if D is not None else None
+            tm.append(time.perf_counter())
             with d2h:
+                tm.append(time.perf_counter())
                 if compact:
-                    sub = dict(P_sch=out["P_sch"][lo:hi], mask=out["mask"][lo:hi], diff=dbuf)
+                    # the convergence values go straight into this pipeline's column block of the caller's array
+                    sub = dict(P_sch=out["P_sch"][lo:hi], mask=out["mask"][lo:hi], diff=None if D is None else D[:, lo:hi])
                     self.parts[k].schedule_compact(want_diff=D is not None, out=sub)
                 else:
-                    sub = dict(P_sch=out["P_sch"][lo:hi], P_ev=out["P_ev"][lo:hi], SOC=out["SOC"][lo:hi], diff=dbuf)
+                    sub = dict(P_sch=out["P_sch"][lo:hi], P_ev=out["P_ev"][lo:hi], SOC=out["SOC"][lo:hi],
+                               diff=self._diff_buf(k, iters) if D is not None else None)
                     self.parts[k].results(iters, want_diff=D is not None, out=sub)
-            if D is not None:
+            tm.append(time.perf_counter())
+            if D is not None and not compact:
                 D[:done, lo:hi] = sub["diff"][:done]
+            tm.append(time.perf_counter())
+            marks[k] = tm
             return done
         self._each(f)
+        if trace:
+            import sys
+            for k, tm in enumerate(marks):
+                print("[revs e2e] pipeline %d: " % k + "  ".join(
+                    "%s %.2f" % (n, 1e3 * (t - t_origin)) for n, t in zip(
+                        ("start", "trees", "homes", "solved", "d2h-lock", "downloaded", "done"), tm)), file=sys.stderr, flush=True)
         out["diff"] = D
         return out
 
