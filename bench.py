@@ -604,7 +604,7 @@ def main():
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
     ap.add_argument("--workload", default="synthetic-refshape-125k-homes-per-gpu-x96", choices=list(WORKLOADS))
     ap.add_argument("--cpu-sample-feeders", type=int, default=None, help="feeders of the workload the CPU port is timed on (default: 4 per core)")
-    ap.add_argument("--pipelines", type=int, default=3, help="independent stream pipelines per GPU (parallel.PipelinedSolver)")
+    ap.add_argument("--pipelines", type=int, default=4, help="independent stream pipelines per GPU (parallel.PipelinedSolver)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-exact", action="store_true", help="skip the extra exact-mode (FP64 contraction) solve used for the contract_f64 figure")
     ap.add_argument("--no-split", action="store_true", help="hand whole feeders to the solver instead of their voltage zones")

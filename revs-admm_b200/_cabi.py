@@ -82,10 +82,11 @@ def load():
     """dlopen the in-tree library and type every entry point."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise RevsError(-1, f"{LIB_PATH} is missing -- run `python revs-admm_b200/_build.py` "
+        path = os.environ.get("REVS_LIB") or LIB_PATH        # REVS_LIB: another build of this library (A/B measurements)
+        if not os.path.exists(path):
+            raise RevsError(-1, f"{path} is missing -- run `python revs-admm_b200/_build.py` "
                                 "(there is no CPU fallback)")
-        lib = C.CDLL(LIB_PATH)
+        lib = C.CDLL(path)
         for name, (args, res) in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.argtypes, fn.restype = args, res
@@ -214,14 +215,19 @@ class Solver:
         _check(self.lib.revs_set_feeder_tree(self._h, feeder, len(parent), parent.ctypes.data_as(i32),
                                              _dp(r), res_node.ctypes.data_as(i32)))
 
-    def set_feeder_trees(self, trees):
-        """All feeders in one call; `trees` are feeder.FeederTree-like (parent, r, res_node)."""
+    def pack_trees(self, trees):
+        """The concatenated arrays revs_set_feeder_trees takes, from feeder.FeederTree-like objects (parent, r, res_node)."""
         assert len(trees) == self.nf
         node_off = np.concatenate([[0], np.cumsum([len(t.parent) for t in trees])]).astype(np.int64)
         parent = np.ascontiguousarray(np.concatenate([t.parent for t in trees]), dtype=np.int32)
         r = _f64(np.concatenate([t.r for t in trees]))
         res = np.ascontiguousarray(np.concatenate([t.res_node for t in trees]), dtype=np.int32)
         assert len(res) == self.H
+        return node_off, parent, r, res
+
+    def set_feeder_trees(self, trees, packed=None):
+        """All feeders in one call; `trees` are feeder.FeederTree-like (parent, r, res_node), or `packed` = pack_trees(trees)."""
+        node_off, parent, r, res = packed if packed is not None else self.pack_trees(trees)
         i32 = C.POINTER(C.c_int32)
         _check(self.lib.revs_set_feeder_trees(self._h, node_off.ctypes.data_as(C.POINTER(C.c_int64)),
                                               parent.ctypes.data_as(i32), _dp(r), res.ctypes.data_as(i32)))

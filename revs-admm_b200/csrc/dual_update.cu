@@ -32,6 +32,10 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// SLOTS = ceil(T / 32) hours per lane, compile-time: every load of a home (and of the second home a warp handles at
+// the same time) is issued before the first value is used -- two round trips to HBM per warp instead of twelve.
+// SLOTS = 0: any T, run-time loop over the hours.
+template <int SLOTS, bool DSUM>
 __global__ void __launch_bounds__(256, 4) dual_update_kernel(DualParams P) {
     extern __shared__ double tile[];   // [32][T+1]
     __shared__ double s_part[2][8];
@@ -43,38 +47,100 @@ __global__ void __launch_bounds__(256, 4) dual_update_kernel(DualParams P) {
     const double* __restrict__ p_sch_old = (it & 1) ? P.p_sch_new : P.p_sch_old;
     double* __restrict__ diff_k = P.diff_k + (size_t)it * P.Hp;
 
-    for (int t = warp; t < P.T; t += 8) {
-        int h = h0 + lane;
-        tile[lane * ldt + t] = h < P.Hp ? P.g_t[(size_t)t * P.Hp + h] : 0.0;
+    {
+        const int h = h0 + lane;
+        const bool in = h < P.Hp;
+        const double* src = P.g_t + (in ? h : 0);
+        int t = warp;
+        for (; t + 24 < P.T; t += 32) {               // four rows of the tile per step: the loads overlap
+            double v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[q] = in ? src[(size_t)(t + 8 * q) * P.Hp] : 0.0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) tile[lane * ldt + t + 8 * q] = v[q];
+        }
+        for (; t < P.T; t += 8) tile[lane * ldt + t] = in ? src[(size_t)t * P.Hp] : 0.0;
     }
     __syncthreads();
 
     const double hk = 0.5 * P.kappa;
     double blk_p = 0.0, blk_d = 0.0;
-    for (int hl = warp; hl < 32; hl += 8) {
-        const int h = h0 + hl;
-        if (h >= P.Hp) break;
-        const size_t base = (size_t)h * P.T;
-        double a1 = 0.0, a2 = 0.0;
-        for (int t = lane; t < P.T; t += 32) {
-            const double e = tile[hl * ldt + t];
-            const double sn = p_sch_new[base + t];
-            const double so = p_sch_old[base + t];
-            const double gm = P.gamma[base + t];
-            const double check = __dadd_rn(e, -sn);
-            const double g2 = __dadd_rn(gm, __dmul_rn(hk, check));
-            P.gamma[base + t] = g2;
-            P.p_est[base + t] = e;
-            tile[hl * ldt + t] = __dadd_rn(__dmul_rn(__dadd_rn(e, sn), 0.5), -__ddiv_rn(g2, P.kappa));
-            a1 = fma(check, check, a1);
-            const double ds = sn - so;
-            a2 = fma(ds, ds, a2);
+    // the sum of (P_sch[k+1] - P_sch[k])^2 of a home comes from home_solve_kernel when it left it behind (dsum): same
+    // additions in the same order as the loop below, without reading the previous schedule again
+    const double* dsum = DSUM ? P.dsum : nullptr;
+    if constexpr (SLOTS > 0) {
+        for (int hl = warp; hl < 32; hl += 16) {      // homes hl and hl + 8 of the tile together
+            double sn[2][SLOTS], gm[2][SLOTS], so[2][DSUM ? 1 : SLOTS];
+            bool okh[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int h = h0 + hl + 8 * q;
+                okh[q] = h < P.Hp;
+                const size_t base = (size_t)(okh[q] ? h : 0) * P.T;
+#pragma unroll
+                for (int j = 0; j < SLOTS; ++j) {
+                    const int t = min(lane + 32 * j, P.T - 1);
+                    sn[q][j] = p_sch_new[base + t];
+                    gm[q][j] = P.gamma[base + t];
+                    if constexpr (!DSUM) so[q][j] = p_sch_old[base + t];
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                if (!okh[q]) continue;                // warp-uniform
+                const int h = h0 + hl + 8 * q;
+                const size_t base = (size_t)h * P.T;
+                double a1 = 0.0, a2 = 0.0;
+#pragma unroll
+                for (int j = 0; j < SLOTS; ++j) {
+                    const int t = lane + 32 * j;
+                    if (t < P.T) {
+                        const double e = tile[(hl + 8 * q) * ldt + t];
+                        const double check = __dadd_rn(e, -sn[q][j]);
+                        const double g2 = __dadd_rn(gm[q][j], __dmul_rn(hk, check));
+                        P.gamma[base + t] = g2;
+                        P.p_est[base + t] = e;
+                        tile[(hl + 8 * q) * ldt + t] = __dadd_rn(__dmul_rn(__dadd_rn(e, sn[q][j]), 0.5), -__ddiv_rn(g2, P.kappa));
+                        a1 = fma(check, check, a1);
+                        if constexpr (!DSUM) {
+                            const double ds = sn[q][j] - so[q][j];
+                            a2 = fma(ds, ds, a2);
+                        }
+                    }
+                }
+                a1 = warp_sum(a1);
+                a2 = DSUM ? dsum[h] : warp_sum(a2);
+                if (lane == 0) diff_k[h] = sqrt(a1) / (double)P.T;
+                blk_p += a1;
+                blk_d += a2;
+            }
         }
-        a1 = warp_sum(a1);
-        a2 = warp_sum(a2);
-        if (lane == 0) diff_k[h] = sqrt(a1) / (double)P.T;
-        blk_p += a1;
-        blk_d += a2;
+    } else {
+        for (int hl = warp; hl < 32; hl += 8) {
+            const int h = h0 + hl;
+            if (h >= P.Hp) break;
+            const size_t base = (size_t)h * P.T;
+            double a1 = 0.0, a2 = 0.0;
+            for (int t = lane; t < P.T; t += 32) {
+                const double e = tile[hl * ldt + t];
+                const double sn = p_sch_new[base + t];
+                const double so = dsum ? 0.0 : p_sch_old[base + t];
+                const double gm = P.gamma[base + t];
+                const double check = __dadd_rn(e, -sn);
+                const double g2 = __dadd_rn(gm, __dmul_rn(hk, check));
+                P.gamma[base + t] = g2;
+                P.p_est[base + t] = e;
+                tile[hl * ldt + t] = __dadd_rn(__dmul_rn(__dadd_rn(e, sn), 0.5), -__ddiv_rn(g2, P.kappa));
+                a1 = fma(check, check, a1);
+                const double ds = sn - so;
+                a2 = fma(ds, ds, a2);
+            }
+            a1 = warp_sum(a1);
+            a2 = dsum ? dsum[h] : warp_sum(a2);
+            if (lane == 0) diff_k[h] = sqrt(a1) / (double)P.T;
+            blk_p += a1;
+            blk_d += a2;
+        }
     }
     if (lane == 0) { s_part[0][warp] = blk_p; s_part[1][warp] = blk_d; }
     __syncthreads();
@@ -178,11 +244,33 @@ __global__ void __launch_bounds__(256, 4) dual_update_kernel(DualParams P) {
 }
 
 cudaError_t launch_dual_update(const DualParams& P, cudaStream_t stream) {
-    size_t smem = (size_t)32 * (P.T + 1) * sizeof(double);
-    if (smem > 48 * 1024)
-        cudaFuncSetAttribute(dual_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    dual_update_kernel<<<(P.Hp + 31) / 32, 256, smem, stream>>>(P);
-    return cudaGetLastError();
+    const size_t smem = (size_t)32 * (P.T + 1) * sizeof(double);
+    const int slots = (P.T + 31) / 32;
+    const dim3 grid((P.Hp + 31) / 32);
+    auto go = [&](auto kernel) -> cudaError_t {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        kernel<<<grid, 256, smem, stream>>>(P);
+        return cudaGetLastError();
+    };
+    if (P.dsum) {
+        switch (slots) {
+            case 1: return go(dual_update_kernel<1, true>);
+            case 2: return go(dual_update_kernel<2, true>);
+            case 3: return go(dual_update_kernel<3, true>);
+            case 4: return go(dual_update_kernel<4, true>);
+            default: return go(dual_update_kernel<0, true>);
+        }
+    }
+    switch (slots) {
+        case 1: return go(dual_update_kernel<1, false>);
+        case 2: return go(dual_update_kernel<2, false>);
+        case 3: return go(dual_update_kernel<3, false>);
+        case 4: return go(dual_update_kernel<4, false>);
+        default: return go(dual_update_kernel<0, false>);
+    }
 }
 
 }  // namespace revs

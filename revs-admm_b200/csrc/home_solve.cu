@@ -29,6 +29,10 @@ __global__ void __launch_bounds__(256) home_solve_kernel(HomeParams P) {
     if (h >= P.Hp) return;
     const size_t base = (size_t)h * P.T;
     const bool ev = P.has_ev[h] != 0;
+    // (the per-home parameters travel together with the EV flag: one round trip instead of two for an EV home)
+    const double rate = P.rating[h];
+    const int st = P.start[h], en = P.end[h];
+    const int nmin = P.n_min[h], nmax = P.n_max[h];
     // ping-pong of the schedules by the device iteration counter (see HomeParams::iter)
     const bool odd = P.iter != nullptr && (*P.iter & 1);
     const double* __restrict__ p_sch_in = odd ? P.p_sch_new : P.p_sch;
@@ -40,32 +44,46 @@ __global__ void __launch_bounds__(256) home_solve_kernel(HomeParams P) {
         int t = lane + 32 * j;
         ld[j] = t < P.T ? P.load[base + t] : 0.0;
     }
+    // dual residual of the ADMM loop: sum over the hours of (new schedule - previous schedule)^2, for dual_update_kernel.
+    // The previous schedule is the zero start in the first iteration, otherwise what this kernel wrote last time: the
+    // load outside the plug-in window (difference exactly 0) and the value read below inside it.
+    const bool first = P.iter ? (*P.iter == 0) : (P.first != 0);
     if (!ev) {   // warp-uniform: a home without EV only moves its load through
+        double a2 = 0.0;
 #pragma unroll
         for (int j = 0; j < SLOTS; ++j) {
             int t = lane + 32 * j;
-            if (t < P.T) { p_sch_out[base + t] = ld[j]; P.p_ev[base + t] = 0.0; }
+            if (t < P.T) {
+                p_sch_out[base + t] = ld[j];
+                P.p_ev[base + t] = 0.0;
+                const double ds = first ? ld[j] : 0.0;
+                a2 = fma(ds, ds, a2);
+            }
+        }
+        if (P.dsum) {
+            a2 = warp_sum(a2);
+            if (lane == 0) P.dsum[h] = a2;
         }
         return;
     }
 
-    const double rate = P.rating[h];
-    const int st = P.start[h], en = P.end[h];
-    const int nmin = P.n_min[h], nmax = P.n_max[h];
     const double kap = P.kappa;
     const double c0 = __dmul_rn(__dmul_rn(0.5 * kap, rate), rate);
 
-    double d[SLOTS];
+    double d[SLOTS], prev[SLOTS];
 #pragma unroll
     for (int j = 0; j < SLOTS; ++j) {
         int t = lane + 32 * j;
         double v = CUDART_INF;
+        prev[j] = first ? 0.0 : ld[j];
         if (t < P.T && t >= st && t < en) {
             if (P.individual) {
                 // (0.01*c_t)*rating - 0.99*(rating/capacity)   (lpsolver.py:407-415)
                 v = __dadd_rn(__dmul_rn(__dmul_rn(0.01, P.cost[t]), rate), P.ind_const[h]);
             } else {
-                double s = __dadd_rn(P.p_est[base + t], p_sch_in[base + t]);
+                const double ps = p_sch_in[base + t];
+                prev[j] = ps;
+                double s = __dadd_rn(P.p_est[base + t], ps);
                 double a = __dadd_rn(P.gamma[base + t], __dmul_rn(0.5 * kap, s));
                 double x = __dmul_rn(rate, __dadd_rn(P.cost[t], -a));
                 double y = __dmul_rn(__dmul_rn(kap, ld[j]), rate);
@@ -167,13 +185,21 @@ __global__ void __launch_bounds__(256) home_solve_kernel(HomeParams P) {
         for (int j = 0; j < SLOTS; ++j)
             on[j] = d[j] < CUDART_INF && (rank[j] < nmin || (rank[j] < nmax && d[j] < 0.0));
     }
+    double a2 = 0.0;
 #pragma unroll
     for (int j = 0; j < SLOTS; ++j) {
         int t = lane + 32 * j;
         if (t >= P.T) continue;
         double p = on[j] ? rate : 0.0;
         P.p_ev[base + t] = p;
-        p_sch_out[base + t] = __dadd_rn(ld[j], p);
+        const double sn = __dadd_rn(ld[j], p);
+        p_sch_out[base + t] = sn;
+        const double ds = sn - prev[j];
+        a2 = fma(ds, ds, a2);
+    }
+    if (P.dsum) {
+        a2 = warp_sum(a2);
+        if (lane == 0) P.dsum[h] = a2;
     }
 }
 

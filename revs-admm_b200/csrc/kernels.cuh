@@ -23,6 +23,8 @@ struct HomeParams {
     const int* n_max;         // [Hp]
     double* p_sch_new;        // [Hp][T]  (const-cast of p_sch is written instead when *iter is odd)
     double* p_ev;             // [Hp][T]
+    double* dsum;             // optional [Hp] out: sum over the hours of (new schedule - previous schedule)^2 (dual residual of the ADMM loop)
+    int first;                // without `iter`: 1 when the previous schedule is the zero start of the loop (lpsolver.py:250)
     int* infeasible;          // flag
     int Hp, T;
     double kappa;
@@ -63,6 +65,8 @@ struct DualParams {
     const double* g_t;         // [T][Hp]  P_est[k+1], time-major (utility output)
     const double* p_sch_new;   // [Hp][T]  (swapped with p_sch_old when *iter is odd)
     const double* p_sch_old;   // [Hp][T]
+    const double* dsum;        // optional [Hp]: sum over the hours of (P_sch[k+1] - P_sch[k])^2 per home, left by home_solve_kernel;
+                               //     p_sch_old is then not read
     int* iter;                 // optional device iteration counter k: selects the ping-pong side and the row of diff, and is
                                // incremented by the last CTA (the whole ADMM loop then runs from one captured graph)
     int iter_max;              // with `iter`: the loop condition is cleared after iter_max iterations, on convergence or on an error flag

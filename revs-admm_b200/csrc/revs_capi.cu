@@ -132,7 +132,6 @@ struct revs_solver {
     // tuning / debug options, read ONCE (environment at revs_create, revs_set_option afterwards): nothing in the
     // solve path calls getenv
     int warp_m_max = 0, warp_m_max_big = 0;    // warm working sets above this size start in CTA class 1
-    int warp_ctas = 0;                         // REVS_WARP_CTAS: CTAs per SM of the persistent warp kernels (0: as many as fit)
     bool use_fast = true;                      // one-row register kernel for the small zones
     bool debug = false, debug_host = false;    // REVS_DEBUG / REVS_DEBUG_HOST: per-round / per-solve lines on stderr
     int trace_iter = -1, trace_round = -1;     // REVS_DEBUG_TRACE="<admm iteration>,<round>": per-column timeline of that round
@@ -146,6 +145,7 @@ struct revs_solver {
     double gk_kappa = 0, gk_vset = 0, gk_vhigh = 0, gk_tol = 0;
     int gk_iter_max = 0, gk_flags = -1;
     double* d_respart = nullptr;               // per-CTA partial residual sums of dual_update_kernel
+    double* d_dsum = nullptr;                  // [Hp] per-home sums of (P_sch[k+1] - P_sch[k])^2, home_solve_kernel -> dual_update_kernel
     // operator QP on the feeder tree (tree_qp.cu): static per-zone arrays, pools of Hp entries
     bool use_tree = false, tree_on = false;    // opt-in (option "tree" / REVS_TREE=1, before the trees are set): see tree_qp.cu
     std::vector<char> tree_ok;                 // per feeder: arrays built (revs_set_feeder_tree(s)), not overridden by a dense block
@@ -938,7 +938,7 @@ int enqueue_round(revs_solver* s, QpParams& Q, int mode, const bool* use, const 
         // (sharing the SMs between two QP kernels slowed both down whenever it was measured): the groups of
         // long columns first, the many short columns of the small zones fill the tail
         s->stats.qp_warp_rounds++;
-        const int full = s->warp_ctas > 0 ? s->warp_ctas : qp_warp_ctas_per_sm();
+        const int full = qp_warp_ctas_per_sm();
         if (s->zg.n_big > 0) {                                    // zones of 257..320 residences: lists 13..16
             Q.list0 = kListBig;
             Q.nlists = kQpBuckets;
@@ -1109,6 +1109,8 @@ HomeParams home_params(revs_solver* s, int individual) {
     P.kappa = s->kappa;
     P.individual = individual;
     P.ind_const = s->d_indconst;
+    P.dsum = nullptr;              // set by the ADMM loop (revs_admm_step / capture_loop)
+    P.first = 0;
     return P;
 }
 
@@ -1118,7 +1120,7 @@ void free_all(revs_solver* s) {
                     s->d_pev, s->d_soc, s->d_has_ev, s->d_rating, s->d_capacity, s->d_initial, s->d_indconst,
                     s->d_start, s->d_end, s->d_nmin, s->d_nmax, s->d_zero_i, s->d_cost, s->d_zt, s->d_lamt,
                     s->d_gt, s->d_vt, s->d_wcount, s->d_widx, s->d_status, s->d_innerok, s->d_cls, s->d_order, s->d_order4, s->d_order_count, s->d_cnt, s->d_diff,
-                    s->d_cprob, s->d_ctiles, s->d_respart, s->d_t_perm, s->d_t_iperm, s->d_t_nodeA, s->d_t_nodeB, s->d_t_cnt,
+                    s->d_cprob, s->d_ctiles, s->d_respart, s->d_dsum, s->d_t_perm, s->d_t_iperm, s->d_t_nodeA, s->d_t_nodeB, s->d_t_cnt,
                     s->d_t_c, s->d_t_d, s->d_t_e, s->d_t_wA, s->d_t_wB, s->d_t_zoff, s->d_tree_cols[0], s->d_tree_cols[1], s->d_tree_cols[2],
                     s->d_tree_cols[3], s->d_nt_zones, s->d_nt_lvl, s->d_nt_parent, s->d_nt_home, s->d_nt_hnode, s->d_nt_wsi, s->d_nt_child, s->d_nt_homes, s->d_nt_rho,
                     s->d_nt_ws, s->d_nt_ws4, s->d_nt_ws2};
@@ -1294,6 +1296,7 @@ int revs_create(revs_solver** out, int device, int n_feeders, const int64_t* fee
     TRY(dalloc(&s->d_order_count, (size_t)2 * kQpLists));
     TRY(dalloc(&s->d_cnt, (size_t)1));
     TRY(dalloc(&s->d_respart, (size_t)2 * ((hp + 31) / 32)));
+    TRY(dalloc(&s->d_dsum, (size_t)hp));
     // options from the environment, read here and nowhere else
     {
         const char* e;
@@ -1301,7 +1304,6 @@ int revs_create(revs_solver** out, int device, int n_feeders, const int64_t* fee
         // zones above 128 residences: the same threshold (round 1 sent stored sets above 5 rows to the first CTA class, which
         // cost 8.5 of 21 ms per schedule on zones of 150..300 residences; measured, profiles/README_r02.md)
         s->warp_m_max_big = (e = getenv("REVS_WARP_M_MAX_BIG")) ? atoi(e) : s->warp_m_max;
-        if ((e = getenv("REVS_WARP_CTAS"))) s->warp_ctas = atoi(e);
         s->use_fast = !((e = getenv("REVS_NO_FAST")) && atoi(e));
         s->debug = getenv("REVS_DEBUG") != nullptr;
         s->debug_host = getenv("REVS_DEBUG_HOST") != nullptr;
@@ -1651,6 +1653,7 @@ DualParams dual_params(revs_solver* s) {
     D.cond_loop = 0;
     D.use_cond = 0;
     D.partials = s->d_respart;
+    D.dsum = s->d_dsum;                        // every dual update of a loop follows a home solve of the same iteration
     D.peer.world = s->comm_world;
     D.peer.rank = s->comm_rank;
     for (int r = 0; r < kMaxPeers; ++r) D.peer.box[r] = s->peer_box[r];
@@ -1709,6 +1712,8 @@ int admm_step_impl(revs_solver* s, double sums[3], bool sync_now) {
     cudaStream_t sHome = s->overlap_home ? s->sH : s->sU;   // overlap_home = 0: in line, for an undisturbed kernel time
     CU(cudaStreamWaitEvent(sHome, s->evDualDone, 0));
     HomeParams hp = home_params(s, 0);
+    hp.dsum = s->d_dsum;
+    hp.first = s->k == 0 ? 1 : 0;
     TimedSpan* sp = span_begin(s, 1, sHome);
     CU(launch_home_solve(hp, sHome));
     span_end(sp, sHome);
@@ -1793,6 +1798,7 @@ int capture_loop(revs_solver* s) {
         hp.p_sch = s->d_psch[0];
         hp.p_sch_new = s->d_psch[1];
         hp.iter = &s->d_cnt->iter;
+        hp.dsum = s->d_dsum;
         CU(launch_home_solve(hp, sHome));
         if (s->overlap_home) CU(cudaEventRecord(s->evHomeDone, s->sH));
         QpParams Q = qp_params(s);

@@ -181,6 +181,8 @@ __device__ __forceinline__ void solve_column(const QpParams& P, const int4 ent, 
             gj[k] = g[jc];
             vf[k] = v32[jc];
         }
+        // the row maxima are needed after the solve (verification): on their way to L2 meanwhile
+        if (lane < (n + 15) / 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.rmax + hoff + 16 * lane));
 #pragma unroll
         for (int k = 0; k < NJ; ++k) {
             const bool in = lane + 32 * k < n;

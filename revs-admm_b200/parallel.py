@@ -134,7 +134,7 @@ class PipelinedSolver:
     Same methods as ``_cabi.Solver``; results are those of a single solver, bit for bit.
     """
 
-    def __init__(self, feeder_sizes, T, device=0, pipelines=3):
+    def __init__(self, feeder_sizes, T, device=0, pipelines=4):
         from concurrent.futures import ThreadPoolExecutor
         from ._cabi import Solver
         self.sizes = [int(n) for n in feeder_sizes]
@@ -245,6 +245,8 @@ class PipelinedSolver:
                 out.update(P_ev=np.empty((H, T)), SOC=np.empty((H, T + 1)))
         D = out.get("diff")
         d2h = threading.Lock()
+        prep = [threading.Event() for _ in range(len(self.parts) + 1)]
+        prep[0].set()
         trace = os.environ.get("REVS_DEBUG_E2E") is not None
         t_origin = time.perf_counter()
         marks = [None] * len(self.parts)
@@ -253,7 +255,14 @@ class PipelinedSolver:
             lo, hi = self.rows[k]
             a, b = self.cuts[k]
             tm = [time.perf_counter()]
-            self.parts[k].set_feeder_trees(trees[a:b])
+            # the interpreter-side packing of the zone arrays holds the GIL: pipeline by pipeline, in order, so that
+            # the first pipeline reaches the library (which releases it) as early as possible
+            prep[k].wait()
+            try:
+                packed = self.parts[k].pack_trees(trees[a:b])
+            finally:
+                prep[k + 1].set()
+            self.parts[k].set_feeder_trees(None, packed=packed)
             tm.append(time.perf_counter())
             self.parts[k].set_homes(**{n: v[lo:hi] for n, v in homes.items()})
             self.parts[k].set_tariff(cost)

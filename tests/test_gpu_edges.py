@@ -271,6 +271,37 @@ def test_captured_loop_equals_host_driven_loop(gpu_lib, sizes, T, vhigh, tree):
         assert rounds[0] >= kw["iter_max"]
 
 
+@pytest.mark.parametrize("sizes,T", [([70, 45, 33], 96), ([40, 21], 24), ([30], 100), ([12], 256)])
+def test_residual_sums_follow_the_iterates(gpu_lib, sizes, T):
+    """The residual sums of the stopping rule (lpsolver.py:280-284 restated as ADMM residuals): primal = sum (P_est[k+1] -
+    P_sch[k+1])^2, dual = sum (P_sch[k+1] - P_sch[k])^2 with P_sch[0] = 0.  The dual sum is accumulated per home by
+    home_solve_kernel and only added up by dual_update_kernel: checked against the downloaded schedules after every
+    iteration, and the captured loop must end on the same values as the stepped one."""
+    trees, hm, cost = _problem(sizes, T, seed=3 + sum(sizes))
+    kw = dict(kappa=5.0, iter_max=5, vset=1.0, vlow=0.95, vhigh=1.02)
+    H = sum(sizes)
+    with gpu_lib.Solver(sizes, T) as s:
+        s.set_feeder_trees(trees)
+        s.set_homes(**hm)
+        s.set_tariff(cost)
+        s.admm_begin(**kw)
+        prev = np.zeros((H, T))
+        for k in range(kw["iter_max"]):
+            sums = s.admm_step()
+            P = s.results(k + 1)["P_sch"]
+            P_est, _ = s.estimate()
+            want_d, want_p = ((P - prev) ** 2).sum(), ((P_est - P) ** 2).sum()
+            assert abs(sums[1] - want_d) <= 1e-12 * max(1.0, want_d), (k, sums[1], want_d)
+            assert abs(sums[0] - want_p) <= 1e-12 * max(1.0, want_p), (k, sums[0], want_p)
+            assert sums[2] == H * T
+            prev = P
+        st_step = s.stats()
+        s.solve_admm(**kw)                              # captured loop
+        st_loop = s.stats()
+    assert st_loop["dual_residual"] == st_step["dual_residual"] and st_loop["primal_residual"] == st_step["primal_residual"]
+    assert abs(st_step["dual_residual"] - kw["kappa"] * np.sqrt(want_d / (H * T))) <= 1e-12 * max(1.0, st_step["dual_residual"])
+
+
 def test_captured_loop_stops_on_the_device(gpu_lib):
     """tol > 0: the last CTA of dual_update_kernel clears the loop condition; same iteration count and
     results as the host-driven loop, and an infeasible home stops the loop with REVS_ERR_INFEASIBLE."""
