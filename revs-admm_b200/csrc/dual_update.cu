@@ -192,8 +192,9 @@ __global__ void __launch_bounds__(256, 4) dual_update_kernel(DualParams P) {
         if (r < P.peer.world) {
             double lp = 0.0, ld = 0.0;
             for (int w = 0; w < 8; ++w) { lp += s_fin[0][w]; ld += s_fin[1][w]; }
-            const unsigned long long seq = *P.peer.run_seq + (unsigned long long)it + 1ull;
-            const int par = it & 1;
+            const int pit = P.iter ? it : P.step;       // host-driven loop: the iteration number comes with the launch
+            const unsigned long long seq = *P.peer.run_seq + (unsigned long long)pit + 1ull;
+            const int par = pit & 1;
             PeerSlot* out = P.peer.box[r] + par * P.peer.world + P.peer.rank;       // my slot in rank r's mailbox
             out->v[0] = lp;
             out->v[1] = ld;

@@ -70,6 +70,8 @@ struct DualParams {
     int* iter;                 // optional device iteration counter k: selects the ping-pong side and the row of diff, and is
                                // incremented by the last CTA (the whole ADMM loop then runs from one captured graph)
     int iter_max;              // with `iter`: the loop condition is cleared after iter_max iterations, on convergence or on an error flag
+    int step;                  // without `iter` (host-driven loop): iteration number of this launch -- sequence number and payload
+                               //     half of the peer exchange, so that a rank running ahead never reads the previous iteration's slot
     const int* err_a;          // optional error flags (infeasible home, failed QP column): stop the device loop
     const int* err_b;
     unsigned long long cond_loop;   // cudaGraphConditionalHandle of the ADMM while node (use_cond != 0)

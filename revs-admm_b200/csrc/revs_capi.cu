@@ -1647,6 +1647,7 @@ DualParams dual_params(revs_solver* s) {
     D.p_sch_new = s->d_psch[1];
     D.p_sch_old = s->d_psch[0];
     D.iter = nullptr;
+    D.step = s->k;
     D.iter_max = s->iter_max;
     D.err_a = &s->d_cnt->infeasible;
     D.err_b = &s->d_cnt->n_failed;
