@@ -470,7 +470,9 @@ def run_gpu(args, rank, world, local_rank):
                                  "peak": hbm_peak, "unit": "GB/s", "bytes_per_launch": home_bytes, "note": iso_note}
     if st_iso["dual_ms"] > 0:
         ms = st_iso["dual_ms"] / it
-        dual_bytes_now = Hp * T * (56 + 8 + 2)    # + g = [z]_+ and its bf16 copy for the next utility solve
+        # reads P_est (time-major), P_sch, Gamma; writes Gamma, P_est (home-major), z and g = [z]_+ with its bf16 copy for
+        # the next utility solve (the previous schedule is not read: home_solve leaves the dual residual sums per home)
+        dual_bytes_now = Hp * T * (24 + 24 + 8 + 2)
         kernels["dual_update"] = {"bound": "hbm", "ms_per_launch": ms, "achieved": dual_bytes_now / (ms * 1e-3) / 1e9,
                                   "peak": hbm_peak, "unit": "GB/s", "bytes_per_launch": dual_bytes_now, "note": iso_note}
     if st_iso["gemm_full_launches"] > 0 and st_iso["gemm_full_ms"] > 0:

@@ -23,7 +23,7 @@ constexpr int kSelectRounds = 24;   // up to this many charging hours: iterative
 
 
 template <int SLOTS>
-__global__ void __launch_bounds__(256) home_solve_kernel(HomeParams P) {
+__global__ void __launch_bounds__(256, SLOTS <= 3 ? 6 : 1) home_solve_kernel(HomeParams P) {
     const int lane = threadIdx.x & 31;
     const int h = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (h >= P.Hp) return;
