@@ -224,3 +224,21 @@ def test_zone_tree_arrays_reproduce_the_dense_block(kind):
         assert np.abs(v - Rd @ g).max() <= 1e-13 * max(1.0, np.abs(Rd @ g).max())
         assert np.array_equal(ref["perm"], P) and np.array_equal(ref["c"], za["c"]) and np.array_equal(ref["d"], za["d"])
         assert np.abs(TA.product(ref, g) - v).max() <= 1e-14
+
+
+def test_pack_trees_concatenates_the_zone_arrays():
+    """Solver.pack_trees (the interpreter-side half of revs_set_feeder_trees, done pipeline by pipeline in
+    PipelinedSolver.schedule): node offsets, parents, resistances and residence nodes of all zones back to back, in the
+    dtypes the C ABI takes."""
+    from revs_admm_b200._cabi import Solver
+    from revs_admm_b200.feeder import synthetic_feeder
+    trees = [synthetic_feeder(n, seed=i, r_secondary=1e-3) for i, n in enumerate([20, 7, 33])]
+    s = Solver.__new__(Solver)                       # no device: only the packing is exercised
+    s.nf, s.H = 3, 60
+    off, parent, r, res = s.pack_trees(trees)
+    assert off.dtype == np.int64 and parent.dtype == np.int32 and r.dtype == np.float64 and res.dtype == np.int32
+    assert off.tolist() == [0] + list(np.cumsum([len(t.parent) for t in trees]))
+    for i, t in enumerate(trees):
+        assert np.array_equal(parent[off[i]:off[i + 1]], t.parent) and np.array_equal(r[off[i]:off[i + 1]], t.r)
+    assert len(res) == 60 and np.array_equal(res[20:27], trees[1].res_node)
+    s._h = None                                      # nothing to destroy
