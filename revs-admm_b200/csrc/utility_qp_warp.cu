@@ -45,8 +45,11 @@ namespace revs {
 
 namespace {
 
-constexpr int kWarpsPerCta = 4;
-constexpr int kCtasPerSm = 4;                // 16 resident columns per SM
+#ifndef REVS_WARPS_PER_CTA        // build-time experiment knob (profiles/build_variants.sh): warps (= columns in flight) per CTA
+#define REVS_WARPS_PER_CTA 4
+#endif
+constexpr int kWarpsPerCta = REVS_WARPS_PER_CTA;
+constexpr int kCtasPerSm = 16 / kWarpsPerCta;   // 16 resident columns per SM
 constexpr int kHW = kWW + 1;                 // leading dim of the per-warp 16x16 matrices
 constexpr int kCacheDoubles = 1024;          // per-warp cache of working rows of R (zones of up to 128 residences: 8 rows)
 constexpr double kArcMinW = 9.5367431640625e-07;
@@ -69,10 +72,10 @@ struct WarpSmemT {
 // at 4 (128 registers) and 3 (168) the kernels spill 130..570 bytes per thread into a 28 KB L1 and every phase of a column
 // runs twice as long; at 2 (255 registers, no spills) the step is 13 % faster in spite of half the resident warps.
 #ifndef REVS_WARP_CTAS_SMALL      // build-time experiment knobs (profiles/build_variants.sh)
-#define REVS_WARP_CTAS_SMALL 2
+#define REVS_WARP_CTAS_SMALL (8 / REVS_WARPS_PER_CTA)
 #endif
 #ifndef REVS_WARP_CTAS_BIG
-#define REVS_WARP_CTAS_BIG 2
+#define REVS_WARP_CTAS_BIG (8 / REVS_WARPS_PER_CTA)
 #endif
 #ifndef REVS_WARP_CACHE_BIG         // doubles of cached working rows per warp at NJ >= 6 (2 CTAs of 4 warps per SM): 20 KB = 13 / 10 / 8
 #define REVS_WARP_CACHE_BIG 2560    // rows of a zone of 192 / 256 / 320 residences, all rows of 97 % of the columns
