@@ -148,11 +148,15 @@ class PipelinedSolver:
         self.rows = [(int(self.off[a]), int(self.off[b])) for a, b in self.cuts]
         self.pool = ThreadPoolExecutor(max_workers=len(self.parts))
         self._diff_scratch = {}
-        if len(self.parts) > 1 and os.environ.get("REVS_PIPELINE_PRIORITY", "0") != "0":
-            # optional (REVS_PIPELINE_PRIORITY=1; measured: no gain): earlier pipelines are served first, so their download
-            # would overlap the compute of the later ones in schedule()
+        # Stream priorities: the first pipeline one level above the others.  It is the first to have its inputs on
+        # the device in schedule(), finishes ~2 ms before the rest, and its download overlaps their compute (end to end
+        # 15.2 -> 14.8 ms on the bench population; the device-resident time does not change).  Measured without gain:
+        # every pipeline on its own level, or any other pipeline favoured (profiles/README_r02.md).
+        # REVS_PIPELINE_PRIORITY=0 switches it off, =1 puts every pipeline on its own level.
+        mode = os.environ.get("REVS_PIPELINE_PRIORITY", "first")
+        if len(self.parts) > 1 and mode != "0":
             for k, p in enumerate(self.parts):
-                p.set_option("priority", k)
+                p.set_option("priority", k if mode == "1" else min(k, 1))
 
     # ---- plumbing
     def _diff_buf(self, k, iters):
