@@ -12,9 +12,17 @@
 // Layout: the utility side keeps its arrays time-major [T][Hp] (one contiguous column per
 // (feeder,hour) QP), the home side home-major [Hp][T] (one contiguous row per home).  A
 // CTA owns 32 homes x T hours and transposes through shared memory, so both sides are
-// read and written in full 256-byte runs.  Per-home norms use warp shuffles; the two
-// global sums are one atomicAdd per CTA, and the last CTA to finish turns them into the
-// residuals and the converged flag.
+// read and written in full 256-byte runs.  Per-home norms use warp shuffles; every CTA leaves
+// its two partial sums in global memory and the last CTA to finish adds them in a fixed order
+// (reproducible residuals), exchanges them with the other GPUs of the box over peer memory
+// when peers are attached, and sets the converged flag / the condition of the captured loop.
+//
+// HBM traffic: 58 bytes per home-step (reads P_est time-major, P_sch[k+1], Gamma; writes Gamma,
+// P_est home-major, z, g = [z]_+ and its bf16 copy).  The previous schedule P_sch[k] of the dual
+// residual is not read: home_solve_kernel, which had both schedules in registers, leaves the
+// per-home sums behind (DualParams::dsum).  The home-major loads of the two homes a warp handles
+// together are all issued before the first use (SLOTS = hours per lane at compile time); left to
+// the compiler they were three dependent round trips per home (profiles/README_r02.md).
 #include <cuda_bf16.h>
 
 #include "kernels.cuh"

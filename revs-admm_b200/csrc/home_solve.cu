@@ -9,6 +9,11 @@
 // picked with warp-shuffle arg-min rounds (or a full shuffle ranking when many hours are
 // needed), no sort and no shared memory.
 //
+// Besides the schedule the kernel leaves, per home, the sum over the hours of (new schedule -
+// previous schedule)^2 -- the dual residual of the ADMM loop, which dual_update_kernel then only
+// adds up (the previous schedule is the zero start in iteration 0, the load outside the plug-in
+// window, and the value the cost evaluation reads anyway inside it).
+//
 // The hour cost is evaluated with individually rounded operations (__dmul_rn/__dadd_rn)
 // in the order oracle/revs_oracle.py:home_delta uses, so that the selection is
 // bit-identical with the CPU oracle whenever the inputs are.

@@ -12,8 +12,9 @@
 //
 // Per column (same fixed point and tolerances as utility_qp.cu / oracle project_voltage):
 //   1. screened voltages (BF16 tensor pass) -> exact FP64 recheck of the candidate rows,
-//   2. admit the most violated rows, copy the working rows of R into shared memory (8 KB per
-//      warp) so that gradient / Hessian / line search never go back to L2,
+//   2. admit the most violated rows, copy the working rows of R into shared memory (cp.async, all
+//      rows in flight at once; 8 KB per warp for zones up to 128 residences, 20 KB above) so that
+//      gradient / Hessian / line search never go back to L2,
 //   3. minimise the dual on W: |W| = 1 is a monotone Newton iteration on a convex piecewise
 //      linear function in registers; otherwise piecewise-quadratic descent with an exact
 //      primal-dual active-set step (16x16 Cholesky in shared memory) and a segment line search,
@@ -23,6 +24,9 @@
 //      only lowers g -- and the few others are recomputed exactly; violated rows join W -> 2.
 // Nothing is written until the column is finished; a column that outgrows 16 rows, cycles or
 // fails a line search is handed, untouched, to the CTA kernel of the next class (same round).
+// Every group of loads a phase starts with (the column's z / g / screened voltages, the row maxima
+// of the verification) is issued before its first use, with clamped indices instead of branches:
+// left to the compiler each slot's load sat next to its use, one round trip to memory per slot.
 //
 // Three kernels live in this file:
 //   utility_qp_warp_kernel<NJ>   the general kernel described above (NJ = 4: zones <= 128 residences,
